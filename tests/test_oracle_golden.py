@@ -1,0 +1,123 @@
+"""Pin the oracle (oracle/xfm_oracle.py) against fixtures produced by the UNMODIFIED reference
+(tools/make_golden.py via oracle/ref_shim.py).  CPU only."""
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import xfm_oracle as O
+
+
+def _load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name), weights_only=False)
+
+
+def _masks(cfg, B, seed):
+    random.seed(seed)
+    np.random.seed(seed)
+    return O.sample_mim_masks(cfg, B)
+
+
+def test_masking_generator_bit_exact(golden_dir):
+    gold = _load(golden_dir, "masks.pt")
+    assert len(gold) == 9
+    for (size, n, mn, seed), ref in gold.items():
+        random.seed(seed)
+        np.random.seed(seed)
+        gen = O.MaskingGenerator(size, num_masking_patches=n, min_num_patches=mn)
+        mine = torch.from_numpy(np.stack([gen() for _ in range(6)]))
+        assert torch.equal(mine, ref), (size, n, mn, seed)
+        assert int(mine[0].sum()) == n
+
+
+def test_itc_with_idx_and_hard_negative_weights(golden_dir):
+    g = _load(golden_dir, "itc_idx.pt")
+    temp = torch.tensor(g["temp"])
+    li = O.contrastive_loss(g["image_feat"], g["text_feat"], temp, idx_all=g["idx"])
+    lp = O.contrastive_loss(g["image_feat"], g["text_feat"], temp)
+    assert abs(float(li) - g["loss_idx"]) < 1e-6
+    assert abs(float(lp) - g["loss_plain"]) < 1e-6
+    w_i2t, w_t2i = O.hard_negative_weights(g["image_feat"], g["text_feat"], temp, idx=g["idx"])
+    torch.testing.assert_close(w_i2t, g["weights_i2t"], rtol=1e-6, atol=1e-8)
+    torch.testing.assert_close(w_t2i, g["weights_t2i"], rtol=1e-6, atol=1e-8)
+
+
+def _run_oracle(g, want_grads=False):
+    cfg = g["cfg"]
+    sd = O.make_state_dict(cfg, seed=0)
+    if want_grads:
+        for v in sd.values():
+            v.requires_grad_(True)
+    batch = O.make_batch(cfg, g["B"], L=g["L"], M=g["M"], seed=1, image_uniform=g["image_uniform"])
+    ids_mask = _masks(cfg, g["B"], g["mask_seed"])
+    col = {}
+    with torch.set_grad_enabled(want_grads):
+        out = O.pretrain_forward(sd, cfg, batch, g["image_neg_idx"], g["text_neg_idx"], ids_mask=ids_mask, collect=col)
+    return sd, out, col, ids_mask
+
+
+@pytest.mark.parametrize("name", ["tiny_vq.pt", "tiny_mse.pt"])
+def test_tiny_losses_masks_and_grads(golden_dir, name):
+    g = _load(golden_dir, name)
+    sd, out, col, ids_mask = _run_oracle(g, want_grads=True)
+    assert torch.equal(ids_mask, g["ids_mask"])  # MIM masks: bit-exact
+    for k, v in g["losses"].items():
+        assert abs(float(out[k]) - v) <= 2e-5 * max(1.0, abs(v)), (k, float(out[k]), v)
+    torch.testing.assert_close(col["weights_i2t"], g["weights_i2t"], rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(col["weights_t2i"], g["weights_t2i"], rtol=1e-5, atol=1e-7)
+    assert torch.equal(torch.argmax(col["weights_t2i"], 1), g["image_neg_idx"])
+    total = out["loss_itc"] + out["loss_itm"] + out["loss_mlm"] + out["loss_mim"]
+    total.backward()
+    tied = {"fusion_encoder.roberta.embeddings.word_embeddings.weight", "text_encoder.roberta.embeddings.word_embeddings.weight"}
+    for n, gr in g["grads"].items():
+        mine = sd[n].grad
+        assert mine is not None, n
+        torch.testing.assert_close(mine, gr, rtol=2e-4, atol=2e-6, msg=lambda m, n=n: f"{n}: {m}")
+    # parameters the reference leaves without a gradient must not receive one from the oracle either
+    for n in g["grad_none"]:
+        if n in sd:
+            assert sd[n].grad is None or float(sd[n].grad.abs().max()) == 0.0, n
+
+
+def test_tiny_vq_activations_and_ids(golden_dir):
+    g = _load(golden_dir, "tiny_vq.pt")
+    sd, out, col, _ = _run_oracle(g)
+    for grp in ("vision", "text", "fusion_pos", "vision_masked"):
+        assert len(col[grp]) == len(g["acts"][grp])
+        for i, (a, b) in enumerate(zip(col[grp], g["acts"][grp])):
+            torch.testing.assert_close(a, b, rtol=1e-4, atol=2e-5, msg=lambda m, i=i, grp=grp: f"{grp}[{i}]: {m}")
+    for k in ("image_embeds", "text_embeds", "image_embeds_masked", "image_feat", "text_feat"):
+        torch.testing.assert_close(col[k], g[k], rtol=1e-4, atol=2e-5)
+    cfg = g["cfg"]
+    batch = O.make_batch(cfg, g["B"], L=g["L"], M=g["M"], seed=1, image_uniform=True)
+    ids = O.vqkd_codebook_indices(batch["image"], sd, cfg)
+    assert ids.dtype == torch.int64 and ids.shape == g["vq_ids"].shape
+    assert torch.equal(ids, g["vq_ids"])  # VQ-KD token ids: bit-exact
+    assert ids.unique().numel() > 8  # not collapsed
+
+
+@pytest.mark.parametrize("name", ["base_mse.pt", "base_vq.pt"])
+def test_base_config_against_reference(golden_dir, name):
+    path = os.path.join(golden_dir, name)
+    if not os.path.exists(path):
+        pytest.skip("base fixture not generated")
+    g = _load(golden_dir, name)
+    torch.set_num_threads(os.cpu_count())
+    sd, out, col, ids_mask = _run_oracle(g)
+    assert torch.equal(ids_mask, g["ids_mask"])
+    for k, v in g["losses"].items():
+        assert abs(float(out[k]) - v) <= 5e-5 * max(1.0, abs(v)), (k, float(out[k]), v)
+    tok, nd = [0, 1, 7, -1], 16
+    for grp in ("vision", "text", "fusion_pos", "vision_masked"):
+        for i, (a, s) in enumerate(zip(col[grp], g["acts_summary"][grp])):
+            torch.testing.assert_close(a[:, tok, :nd], s["slice"], rtol=2e-4, atol=1e-4)
+            assert abs(float(a.abs().max()) - s["absmax"]) <= 1e-3 * max(1.0, s["absmax"])
+    if "vq_ids" in g:
+        cfg = g["cfg"]
+        batch = O.make_batch(cfg, g["B"], L=g["L"], M=g["M"], seed=1, image_uniform=True)
+        ids = O.vqkd_codebook_indices(batch["image"], sd, cfg)
+        amb = O.quantizer_ambiguous(O.vqkd_features(O.vqkd_preprocess(batch["image"]), sd, cfg),
+                                    sd["vqkd.quantize.embedding.weight"]).view(ids.shape)
+        assert torch.equal(ids[~amb], g["vq_ids"][~amb])

@@ -1,0 +1,224 @@
+"""Generate tests/golden/*.pt from the UNMODIFIED reference (run in the build container only).
+
+    python tools/make_golden.py            # tiny + base fixtures
+
+What is recorded (all produced by the reference's own code, through oracle/ref_shim.py):
+  * tiny_vq.pt   — tiny config with the VQ-KD tokenizer: every per-layer activation, features, hard-negative
+                   weights, VQ ids, MIM masks, the four losses, gradients of a few parameters.
+  * tiny_mse.pt  — tiny config with the default MSE MIM loss: the four losses.
+  * base_vq.pt / base_mse.pt — XFM-base (224 px, 40 tokens, B=2): losses, VQ ids, masks and sampled slices
+                   of every layer's activations (full tensors would be ~100 MB).
+  * itc_idx.pt   — get_contrastive_loss / get_hard_negatives with `idx` (retrieval soft labels).
+  * masks.pt     — MaskingGenerator outputs for fixed (random, np.random) seeds.
+Synthetic weights come from oracle.xfm_oracle.make_state_dict (a pure function of parameter names), so the
+fixtures stay small: tests regenerate the same weights instead of loading them.
+"""
+import os
+import random
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_shim  # noqa: E402
+from oracle import xfm_oracle as O  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+MASK_SEED = 1234
+SLICE_TOK = [0, 1, 7, -1]
+SLICE_DIM = 16
+
+
+def run_reference(cfg, B, L, M, image_uniform, want_grads=False, full=True):
+    sd = O.make_state_dict(cfg, seed=0)
+    model = ref_shim.build_reference_xfm(cfg, O.expand_tied(sd, cfg))
+    batch = O.make_batch(cfg, B, L=L, M=M, seed=1, image_uniform=image_uniform)
+    acts = {"vision": [], "text": [], "fusion": []}
+    hooks = []
+    for blk in model.vision_encoder.blocks:
+        hooks.append(blk.register_forward_hook(lambda m, i, o: acts["vision"].append(o.detach().clone())))
+    for lay in model.text_encoder.roberta.encoder.layer:
+        hooks.append(lay.register_forward_hook(lambda m, i, o: acts["text"].append(o[0].detach().clone())))
+    for lay in model.fusion_encoder.roberta.encoder.layer:
+        hooks.append(lay.register_forward_hook(lambda m, i, o: acts["fusion"].append(o[0].detach().clone())))
+    rec = {}
+    orig_multinomial = torch.multinomial
+    calls = []
+
+    def fake_multinomial(w, n, *a, **k):  # deterministic "sample": the heaviest negative
+        calls.append(w.detach().clone())
+        return torch.argmax(w).view(1)
+
+    orig_get_features = model.get_features
+
+    def spy_features(*a, **k):
+        out = orig_get_features(*a, **k)
+        if isinstance(out, tuple):
+            rec["image_feat"], rec["text_feat"] = out[0].detach().clone(), out[1].detach().clone()
+        return out
+
+    orig_vis = model.get_vision_embeds
+
+    def spy_vis(*a, **k):
+        out = orig_vis(*a, **k)
+        if len(out) == 3:
+            rec["image_embeds_masked"], rec["ids_mask"] = out[0].detach().clone(), out[2].clone()
+        else:
+            rec["image_embeds"] = out[0].detach().clone()
+        return out
+
+    orig_text = model.get_text_embeds
+
+    def spy_text(*a, **k):
+        out = orig_text(*a, **k)
+        rec.setdefault("text_embeds", out.detach().clone())
+        return out
+
+    model.get_features, model.get_vision_embeds, model.get_text_embeds = spy_features, spy_vis, spy_text
+    if model.use_vision_tokenizer:
+        orig_ids = model.vqkd.get_codebook_indices
+
+        def spy_ids(x, **k):
+            out = orig_ids(x, **k)
+            rec["vq_ids"] = out.clone()
+            return out
+
+        model.vqkd.get_codebook_indices = spy_ids
+    random.seed(MASK_SEED)
+    np.random.seed(MASK_SEED)
+    torch.multinomial = fake_multinomial
+    try:
+        if want_grads:
+            model.zero_grad()
+            loss = model(ret_mim_loss=True, data_source="image", **batch)
+            total = loss["loss_itc"] + loss["loss_itm"] + loss["loss_mlm"] + loss["loss_mim"]
+            total.backward()
+        else:
+            with torch.no_grad():
+                loss = model(ret_mim_loss=True, data_source="image", **batch)
+    finally:
+        torch.multinomial = orig_multinomial
+        for h in hooks:
+            h.remove()
+    B_ = B
+    w_t2i = torch.stack(calls[:B_], 0)  # xfm.py:737-739 image negatives come first, from weights_t2i
+    w_i2t = torch.stack(calls[B_:2 * B_], 0)
+    nl_v, nl_t, nl_f = cfg["vision_depth"], cfg["text_layers"], cfg["fusion_layers"]
+    out = dict(
+        cfg=cfg, B=B, L=L, M=M, image_uniform=image_uniform, mask_seed=MASK_SEED,
+        losses={k: float(v) for k, v in loss.items() if k in ("loss_itc", "loss_itm", "loss_mlm", "loss_mim")},
+        weights_i2t=w_i2t, weights_t2i=w_t2i,
+        image_neg_idx=torch.argmax(w_t2i, 1), text_neg_idx=torch.argmax(w_i2t, 1),
+        ids_mask=rec["ids_mask"], image_feat=rec["image_feat"], text_feat=rec["text_feat"],
+    )
+    if "vq_ids" in rec:
+        out["vq_ids"] = rec["vq_ids"]
+    groups = dict(
+        vision=acts["vision"][:nl_v], vision_masked=acts["vision"][nl_v:2 * nl_v],
+        text=acts["text"][:nl_t], text_masked=acts["text"][nl_t:2 * nl_t],
+        fusion_pos=acts["fusion"][:nl_f], fusion_neg=acts["fusion"][nl_f:2 * nl_f],
+        fusion_mlm=acts["fusion"][2 * nl_f:3 * nl_f],
+    )
+    finals = dict(image_embeds=rec["image_embeds"], text_embeds=rec["text_embeds"],
+                  image_embeds_masked=rec["image_embeds_masked"])
+    if full:
+        out["acts"] = groups
+        out.update(finals)
+    else:
+        def summarize(t):
+            return dict(slice=t[:, SLICE_TOK, :SLICE_DIM].clone(), mean=float(t.mean()), absmax=float(t.abs().max()),
+                        std=float(t.std()))
+        out["acts_summary"] = {g: [summarize(t) for t in ts] for g, ts in groups.items()}
+        out["finals_summary"] = {k: summarize(t) for k, t in finals.items()}
+    if want_grads:
+        names = ["temp", "vision_encoder.blocks.0.attn.qkv.weight", "vision_encoder.blocks.0.attn.q_bias",
+                 "vision_encoder.blocks.0.attn.relative_position_bias_table", "vision_encoder.blocks.1.gamma_2",
+                 "vision_encoder.blocks.1.mlp.fc2.weight", "vision_encoder.fc_norm.weight",
+                 "vision_encoder.patch_embed.proj.weight", "vision_encoder.mask_token", "vision_encoder.cls_token",
+                 "text_encoder.roberta.embeddings.word_embeddings.weight",
+                 "text_encoder.roberta.embeddings.position_embeddings.weight",
+                 "text_encoder.roberta.encoder.layer.0.attention.self.key.weight",
+                 "text_encoder.roberta.encoder.layer.1.output.LayerNorm.weight",
+                 "fusion_encoder.roberta.encoder.layer.0.crossattention.self.key.weight",
+                 "fusion_encoder.roberta.encoder.layer.1.crossattention.output.dense.bias",
+                 "fusion_encoder.roberta.encoder.layer.1.intermediate.dense.weight",
+                 "fusion_encoder.roberta.embeddings.word_embeddings.weight",
+                 "fusion_encoder.lm_head.dense.weight", "fusion_encoder.lm_head.bias",
+                 "vision_proj.weight", "text_proj.bias", "itm_head.0.weight", "itm_head.1.weight", "itm_head.3.bias"]
+        if model.use_vision_tokenizer:
+            names += ["lm_head.weight", "lm_head.bias"]
+        params = dict(model.named_parameters())
+        out["grads"] = {n: params[n].grad.detach().clone() for n in names}
+        out["grad_none"] = sorted(n for n, p in params.items() if p.grad is None and p.requires_grad)
+    return out
+
+
+def itc_idx_golden():
+    cfg = O.tiny_config()
+    sd = O.make_state_dict(cfg, seed=0)
+    model = ref_shim.build_reference_xfm(cfg, O.expand_tied(sd, cfg))
+    g = torch.Generator().manual_seed(7)
+    B, E = 12, cfg["embed_dim"]
+    fi = torch.nn.functional.normalize(torch.randn(B, E, generator=g), dim=-1)
+    ft = torch.nn.functional.normalize(torch.randn(B, E, generator=g), dim=-1)
+    idx = torch.randint(0, 5, (B,), generator=g)
+    calls = []
+    orig = torch.multinomial
+
+    def fake(w, n, *a, **k):
+        calls.append(w.detach().clone())
+        return torch.argmax(w).view(1)
+
+    torch.multinomial = fake
+    try:
+        with torch.no_grad():
+            loss_idx = model.get_contrastive_loss(fi, ft, idx=idx)
+            loss_plain = model.get_contrastive_loss(fi, ft)
+            model.get_hard_negatives(fi, ft, idx=idx)
+    finally:
+        torch.multinomial = orig
+    return dict(image_feat=fi, text_feat=ft, idx=idx, temp=float(model.temp), loss_idx=float(loss_idx),
+                loss_plain=float(loss_plain), weights_t2i=torch.stack(calls[:B]), weights_i2t=torch.stack(calls[B:]))
+
+
+def masks_golden():
+    ref_shim.install()
+    from models.masking_generator import MaskingGenerator
+
+    out = {}
+    for (size, n, mn) in ((14, 75, 16), (24, 225, 16), (4, 6, 2)):
+        for seed in (0, 1, 42):
+            random.seed(seed)
+            np.random.seed(seed)
+            gen = MaskingGenerator(size, num_masking_patches=n, min_num_patches=mn)
+            out[(size, n, mn, seed)] = torch.from_numpy(np.stack([gen() for _ in range(6)]))
+    return out
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    torch.save(masks_golden(), os.path.join(GOLD, "masks.pt"))
+    torch.save(itc_idx_golden(), os.path.join(GOLD, "itc_idx.pt"))
+    tv = run_reference(O.tiny_config(use_vision_tokenizer=True), B=4, L=24, M=6, image_uniform=True, want_grads=True)
+    torch.save(tv, os.path.join(GOLD, "tiny_vq.pt"))
+    print("tiny_vq", tv["losses"])
+    tm = run_reference(O.tiny_config(), B=4, L=24, M=6, image_uniform=False, want_grads=True, full=False)
+    tm.pop("acts_summary"), tm.pop("finals_summary")
+    torch.save(tm, os.path.join(GOLD, "tiny_mse.pt"))
+    print("tiny_mse", tm["losses"])
+    if "--skip-base" not in sys.argv:
+        bm = run_reference(O.base_config(), B=2, L=40, M=15, image_uniform=False, full=False)
+        torch.save(bm, os.path.join(GOLD, "base_mse.pt"))
+        print("base_mse", bm["losses"])
+        bv = run_reference(O.base_config(use_vision_tokenizer=True), B=2, L=40, M=15, image_uniform=True, full=False)
+        torch.save(bv, os.path.join(GOLD, "base_vq.pt"))
+        print("base_vq", bv["losses"])
+    for f in sorted(os.listdir(GOLD)):
+        print(f, os.path.getsize(os.path.join(GOLD, f)))
+
+
+if __name__ == "__main__":
+    main()

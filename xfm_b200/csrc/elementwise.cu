@@ -1,0 +1,694 @@
+// HBM-bound kernels of the XFM hot path: LayerNorm fwd/bwd, LayerScale backward, column sums (bias
+// gradients), embeddings, patch im2col / token assembly, mean-pool, casts, row gather / scatter.
+// All use 128-bit coalesced accesses and warp-shuffle reductions; one warp owns one row of D features.
+#include "common.cuh"
+#include "internal.h"
+
+namespace xfm {
+
+// ---- dtype-generic 4-element accessors (dtype: 0 = bf16, 1 = f32); idx is an ELEMENT index, multiple of 4
+XFM_DEVINL float4 ld4(const void* p, int dtype, size_t idx) {
+  if (dtype == 1) return *(const float4*)((const float*)p + idx);
+  uint2 u = *(const uint2*)((const bf16*)p + idx);
+  float2 a = __bfloat1622float2(*(const __nv_bfloat162*)&u.x);
+  float2 b = __bfloat1622float2(*(const __nv_bfloat162*)&u.y);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+XFM_DEVINL void st4(void* p, int dtype, size_t idx, float4 v) {
+  if (dtype == 1) {
+    *(float4*)((float*)p + idx) = v;
+  } else {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u;
+    u.x = *(uint32_t*)&a;
+    u.y = *(uint32_t*)&b;
+    *(uint2*)((bf16*)p + idx) = u;
+  }
+}
+
+constexpr int LN_MAX_VEC = 16;  // per-lane float4 slots: D <= 32 * 4 * 16 = 2048
+constexpr int LN_WARPS = 8;
+
+// -------------------------------------------------------------------------------- LayerNorm forward
+// y = (x - mean) * rstd * w + b.  Reference: torch layer_norm at beit2.py:201-205, xroberta.py:135,303,384,1328.
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm_fwd_kernel(const void* __restrict__ x, int x_dtype, const float* __restrict__ w, const float* __restrict__ b,
+                     void* __restrict__ y, int y_dtype, float* __restrict__ y2_f32, float* __restrict__ stats, int M,
+                     int D, float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * LN_WARPS + warp;
+  if (row >= M) return;
+  const size_t base = (size_t)row * D;
+  float4 v[LN_MAX_VEC];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_VEC; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < D) {
+      v[i] = ld4(x, x_dtype, base + c);
+      sum += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
+  }
+  const float mean = warp_sum(sum) / (float)D;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_VEC; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < D) {
+      const float a = v[i].x - mean, bb = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+      sq += a * a + bb * bb + cc * cc + d * d;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / (float)D + eps);
+#pragma unroll
+  for (int i = 0; i < LN_MAX_VEC; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < D) {
+      const float4 ww = *(const float4*)(w + c), bb = *(const float4*)(b + c);
+      float4 o;
+      o.x = (v[i].x - mean) * rstd * ww.x + bb.x;
+      o.y = (v[i].y - mean) * rstd * ww.y + bb.y;
+      o.z = (v[i].z - mean) * rstd * ww.z + bb.z;
+      o.w = (v[i].w - mean) * rstd * ww.w + bb.w;
+      st4(y, y_dtype, base + c, o);
+      if (y2_f32) *(float4*)(y2_f32 + base + c) = o;
+    }
+  }
+  if (lane == 0 && stats) {
+    stats[2 * row] = mean;
+    stats[2 * row + 1] = rstd;
+  }
+}
+
+// -------------------------------------------------------------------------------- LayerNorm backward
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * w;  dw += sum dy * xhat;  db += sum dy.
+// Optional add_in (residual-path gradient) is added to dx.  dw / db are accumulated with one fp32 atomic per
+// column per CTA (each CTA first reduces its rows in registers + shared memory).
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm_bwd_kernel(const void* __restrict__ dy, int dy_dtype, const void* __restrict__ x, int x_dtype,
+                     const float* __restrict__ stats, const float* __restrict__ w, const void* __restrict__ add_in,
+                     int add_dtype, void* __restrict__ dx, int dx_dtype, float* __restrict__ dw, float* __restrict__ db,
+                     int M, int D, int rows_per_cta) {
+  extern __shared__ float red[];  // [2][LN_WARPS][D]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4 aw[LN_MAX_VEC], ab[LN_MAX_VEC];
+#pragma unroll
+  for (int i = 0; i < LN_MAX_VEC; ++i) aw[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int row0 = blockIdx.x * rows_per_cta;
+  const int row1 = min(M, row0 + rows_per_cta);
+  for (int row = row0 + warp; row < row1; row += LN_WARPS) {
+    const size_t base = (size_t)row * D;
+    const float mean = stats[2 * row], rstd = stats[2 * row + 1];
+    float4 g[LN_MAX_VEC], xh[LN_MAX_VEC];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_VEC; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < D) {
+        const float4 d = ld4(dy, dy_dtype, base + c);
+        const float4 xv = ld4(x, x_dtype, base + c);
+        const float4 ww = *(const float4*)(w + c);
+        xh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
+        g[i] = make_float4(d.x * ww.x, d.y * ww.y, d.z * ww.z, d.w * ww.w);
+        s1 += g[i].x + g[i].y + g[i].z + g[i].w;
+        s2 += g[i].x * xh[i].x + g[i].y * xh[i].y + g[i].z * xh[i].z + g[i].w * xh[i].w;
+        aw[i].x += d.x * xh[i].x; aw[i].y += d.y * xh[i].y; aw[i].z += d.z * xh[i].z; aw[i].w += d.w * xh[i].w;
+        ab[i].x += d.x; ab[i].y += d.y; ab[i].z += d.z; ab[i].w += d.w;
+      }
+    }
+    s1 = warp_sum(s1) / (float)D;
+    s2 = warp_sum(s2) / (float)D;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_VEC; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < D) {
+        float4 o;
+        o.x = rstd * (g[i].x - s1 - xh[i].x * s2);
+        o.y = rstd * (g[i].y - s1 - xh[i].y * s2);
+        o.z = rstd * (g[i].z - s1 - xh[i].z * s2);
+        o.w = rstd * (g[i].w - s1 - xh[i].w * s2);
+        if (add_in) {
+          const float4 a = ld4(add_in, add_dtype, base + c);
+          o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+        }
+        st4(dx, dx_dtype, base + c, o);
+      }
+    }
+  }
+  if (!dw) return;
+  float* rw = red;
+  float* rb = red + LN_WARPS * D;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_VEC; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < D) {
+      *(float4*)(rw + warp * D + c) = aw[i];
+      *(float4*)(rb + warp * D + c) = ab[i];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float sw = 0.f, sb = 0.f;
+#pragma unroll
+    for (int k = 0; k < LN_WARPS; ++k) {
+      sw += rw[k * D + c];
+      sb += rb[k * D + c];
+    }
+    atomicAdd(dw + c, sw);
+    atomicAdd(db + c, sb);
+  }
+}
+
+// -------------------------------------------------------------------------------- LayerScale backward
+// Forward (GEMM epilogue): x_out = x_in + rs[row/rpg] * gamma * z, z = acc + bias (saved as bf16).
+// Backward: dz = dx_out * gamma * rs (bf16 out), dgamma += sum_rows dx_out * rs * z, dbias += sum_rows dz.
+// Reference: beit2.py:204-205 (gamma_1 / gamma_2, DropPath).
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layerscale_bwd_kernel(const float* __restrict__ dxo, const bf16* __restrict__ z, const float* __restrict__ gamma,
+                      const float* __restrict__ rs, int rpg, bf16* __restrict__ dz, float* __restrict__ dgamma,
+                      float* __restrict__ dbias, int M, int D, int rows_per_cta) {
+  extern __shared__ float red[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4 ag[LN_MAX_VEC], ab[LN_MAX_VEC];
+#pragma unroll
+  for (int i = 0; i < LN_MAX_VEC; ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int row0 = blockIdx.x * rows_per_cta;
+  const int row1 = min(M, row0 + rows_per_cta);
+  for (int row = row0 + warp; row < row1; row += LN_WARPS) {
+    const size_t base = (size_t)row * D;
+    const float s = rs ? rs[row / rpg] : 1.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_VEC; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < D) {
+        const float4 d = *(const float4*)(dxo + base + c);
+        const float4 zz = ld4(z, 0, base + c);
+        const float4 gm = *(const float4*)(gamma + c);
+        const float4 ds = make_float4(d.x * s, d.y * s, d.z * s, d.w * s);
+        const float4 o = make_float4(ds.x * gm.x, ds.y * gm.y, ds.z * gm.z, ds.w * gm.w);
+        st4(dz, 0, base + c, o);
+        ag[i].x += ds.x * zz.x; ag[i].y += ds.y * zz.y; ag[i].z += ds.z * zz.z; ag[i].w += ds.w * zz.w;
+        ab[i].x += o.x; ab[i].y += o.y; ab[i].z += o.z; ab[i].w += o.w;
+      }
+    }
+  }
+  float* rg = red;
+  float* rb = red + LN_WARPS * D;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_VEC; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < D) {
+      *(float4*)(rg + warp * D + c) = ag[i];
+      *(float4*)(rb + warp * D + c) = ab[i];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float sg = 0.f, sb = 0.f;
+#pragma unroll
+    for (int k = 0; k < LN_WARPS; ++k) {
+      sg += rg[k * D + c];
+      sb += rb[k * D + c];
+    }
+    atomicAdd(dgamma + c, sg);
+    if (dbias) atomicAdd(dbias + c, sb);
+  }
+}
+
+// -------------------------------------------------------------------------------- column sum (bias grads)
+// out[c] += sum_rows in[row, c]; in is bf16 [M, N] with leading dimension ld.  blockDim = (32, 8):
+// each thread owns 8 consecutive columns (one 16-byte load), 8 row-lanes per CTA, rows strided over grid.y.
+__global__ void __launch_bounds__(256)
+colsum_kernel(const bf16* __restrict__ in, int64_t ld, float* __restrict__ out, int M, int N, int rows_per_cta) {
+  __shared__ float red[8][256 + 8];
+  const int c = (blockIdx.x * 32 + threadIdx.x) * 8;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  const int row0 = blockIdx.y * rows_per_cta;
+  const int row1 = min(M, row0 + rows_per_cta);
+  if (c < N) {
+    for (int r = row0 + threadIdx.y; r < row1; r += 8) {
+      const uint4 u = *(const uint4*)(in + (int64_t)r * ld + c);
+      const __nv_bfloat162* h = (const __nv_bfloat162*)&u;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 f = __bfloat1622float2(h[q]);
+        acc[2 * q] += f.x;
+        acc[2 * q + 1] += f.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[threadIdx.y][threadIdx.x * 8 + j] = acc[j];
+  __syncthreads();
+  const int t = threadIdx.y * 32 + threadIdx.x;  // 0..255 -> one column each
+  const int col = blockIdx.x * 256 + t;
+  if (col < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += red[k][t];
+    atomicAdd(out + col, s);
+  }
+}
+
+// -------------------------------------------------------------------------------- casts / fills
+__global__ void cast_f32_to_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, size_t n4) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = *(const float4*)(in + 4 * i);
+    st4(out, 0, 4 * i, v);
+  }
+}
+__global__ void cast_bf16_to_f32_kernel(const bf16* __restrict__ in, float* __restrict__ out, size_t n4) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
+    *(float4*)(out + 4 * i) = ld4(in, 0, 4 * i);
+}
+// out = in * (*scalar) ; in/out same dtype (used to apply the upstream loss gradient to fused-loss gradients)
+__global__ void scale_by_scalar_kernel(void* __restrict__ data, int dtype, const float* __restrict__ scalar, size_t n4) {
+  const float s = *scalar;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 v = ld4(data, dtype, 4 * i);
+    v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+    st4(data, dtype, 4 * i, v);
+  }
+}
+
+// -------------------------------------------------------------------------------- RoBERTa embeddings
+// pos_ids = cumsum(ids != pad) * (ids != pad) + pad (xroberta.py:1747-1757); emb = word + type0 + pos; LayerNorm.
+// One CTA per sequence, one warp per token (round-robin).  Saves pos_ids and LN stats for the backward.
+__global__ void __launch_bounds__(LN_WARPS * 32)
+roberta_embed_fwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ word, const float* __restrict__ pos,
+                         const float* __restrict__ type0, const float* __restrict__ w, const float* __restrict__ b,
+                         bf16* __restrict__ y, float* __restrict__ pre_ln, float* __restrict__ stats,
+                         int32_t* __restrict__ pos_ids, int L, int D, int pad_id, float eps) {
+  extern __shared__ int s_pos[];  // [L]
+  const int seq = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0) {
+    int carry = 0;
+    for (int t0 = 0; t0 < L; t0 += 32) {
+      const int t = t0 + lane;
+      const int m = (t < L && ids[(size_t)seq * L + t] != pad_id) ? 1 : 0;
+      int inc = m;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+      }
+      if (t < L) {
+        const int p = (carry + inc) * m + pad_id;
+        s_pos[t] = p;
+        pos_ids[(size_t)seq * L + t] = p;
+      }
+      carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+  }
+  __syncthreads();
+  for (int t = warp; t < L; t += LN_WARPS) {
+    const size_t row = (size_t)seq * L + t;
+    const int64_t id = ids[row];
+    const float* wr = word + (size_t)id * D;
+    const float* pr = pos + (size_t)s_pos[t] * D;
+    float4 v[LN_MAX_VEC];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_VEC; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < D) {
+        const float4 a = *(const float4*)(wr + c), t4 = *(const float4*)(type0 + c), p4 = *(const float4*)(pr + c);
+        v[i] = make_float4((a.x + t4.x) + p4.x, (a.y + t4.y) + p4.y, (a.z + t4.z) + p4.z, (a.w + t4.w) + p4.w);
+        sum += v[i].x + v[i].y + v[i].z + v[i].w;
+        if (pre_ln) *(float4*)(pre_ln + row * D + c) = v[i];
+      }
+    }
+    const float mean = warp_sum(sum) / (float)D;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_VEC; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < D) {
+        const float a = v[i].x - mean, bb = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+        sq += a * a + bb * bb + cc * cc + d * d;
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / (float)D + eps);
+#pragma unroll
+    for (int i = 0; i < LN_MAX_VEC; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < D) {
+        const float4 ww = *(const float4*)(w + c), bb = *(const float4*)(b + c);
+        float4 o;
+        o.x = (v[i].x - mean) * rstd * ww.x + bb.x;
+        o.y = (v[i].y - mean) * rstd * ww.y + bb.y;
+        o.z = (v[i].z - mean) * rstd * ww.z + bb.z;
+        o.w = (v[i].w - mean) * rstd * ww.w + bb.w;
+        st4(y, 0, row * D + c, o);
+      }
+    }
+    if (lane == 0 && stats) {
+      stats[2 * row] = mean;
+      stats[2 * row + 1] = rstd;
+    }
+  }
+}
+
+// Scatter-add the (pre-LayerNorm) embedding gradient into the word / position / token-type tables.
+// Padding rows receive gradients exactly like torch's nn.Embedding without padding_idx masking would NOT:
+// nn.Embedding(padding_idx=pad) zeroes the gradient of row `pad` (xroberta.py:80,100-102), reproduced here.
+__global__ void __launch_bounds__(256)
+roberta_embed_bwd_kernel(const float* __restrict__ dpre, const int64_t* __restrict__ ids,
+                         const int32_t* __restrict__ pos_ids, float* __restrict__ dword, float* __restrict__ dpos,
+                         float* __restrict__ dtype0, int rows, int D, int pad_id) {
+  const int row = blockIdx.x;
+  if (row >= rows) return;
+  const int64_t id = ids[row];
+  const int p = pos_ids[row];
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    const float g = dpre[(size_t)row * D + c];
+    if (id != pad_id) atomicAdd(dword + (size_t)id * D + c, g);
+    if (p != pad_id) atomicAdd(dpos + (size_t)p * D + c, g);
+    atomicAdd(dtype0 + c, g);
+  }
+}
+
+// -------------------------------------------------------------------------------- ViT patch pipeline
+// im2col for the 16x16 stride-16 conv (beit2.py:229): out[b*np + p, c*P*P + py*P + px] = image[b, c, gy*P+py, gx*P+px].
+// `pre` applies the VQ-KD pre-processing x * mul / 127.5 - 1 (model_vqkd.py:125-131) when pre_mul != 0.
+__global__ void __launch_bounds__(256)
+im2col_kernel(const float* __restrict__ img, bf16* __restrict__ out, int B, int C, int H, int W, int P,
+              float pre_mul) {
+  const int gw = W / P, gh = H / P;
+  const int K = C * P * P;
+  const size_t total4 = (size_t)B * gh * gw * K / 4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t e = i * 4;
+    const int k = (int)(e % K);
+    const size_t rowp = e / K;
+    const int p = (int)(rowp % (gh * gw));
+    const int b = (int)(rowp / (gh * gw));
+    const int c = k / (P * P), py = (k / P) % P, px = k % P;  // px multiple of 4
+    const int gy = p / gw, gx = p % gw;
+    float4 v = *(const float4*)(img + (((size_t)b * C + c) * H + gy * P + py) * W + gx * P + px);
+    if (pre_mul != 0.f) {
+      v.x = v.x * pre_mul / 127.5f - 1.0f; v.y = v.y * pre_mul / 127.5f - 1.0f;
+      v.z = v.z * pre_mul / 127.5f - 1.0f; v.w = v.w * pre_mul / 127.5f - 1.0f;
+    }
+    st4(out, 0, e, v);
+  }
+}
+
+// x[b, 0] = cls (+ pos[0]); x[b, 1+p] = (mask[b,p] ? mask_token : patch[b,p]) (+ pos[1+p]).  (beit2.py:438-449,
+// vqkd_vit.py:378-385).  patch is the f32 conv output [B*np, D]; x is the f32 residual stream [B*(np+1), D].
+__global__ void __launch_bounds__(256)
+assemble_tokens_kernel(const float* __restrict__ patch, const float* __restrict__ cls, const float* __restrict__ mask_token,
+                       const uint8_t* __restrict__ mask, const float* __restrict__ pos, float* __restrict__ x, int B,
+                       int np, int D) {
+  const int row = blockIdx.x;  // b * (np + 1) + t
+  const int b = row / (np + 1), t = row % (np + 1);
+  const float* src;
+  if (t == 0) src = cls;
+  else if (mask && mask[(size_t)b * np + t - 1]) src = mask_token;
+  else src = patch + ((size_t)b * np + t - 1) * D;
+  for (int c = threadIdx.x * 4; c < D; c += blockDim.x * 4) {
+    float4 v = *(const float4*)(src + c);
+    if (pos) {
+      const float4 p4 = *(const float4*)(pos + (size_t)t * D + c);
+      v.x += p4.x; v.y += p4.y; v.z += p4.z; v.w += p4.w;
+    }
+    *(float4*)(x + (size_t)row * D + c) = v;
+  }
+}
+
+// Backward of assemble: dpatch[b,p] = mask ? 0 : dx[b,1+p] (bf16, feeds the conv wgrad GEMM);
+// dcls += sum_b dx[b,0]; dmask_token += sum over masked positions.
+__global__ void __launch_bounds__(256)
+assemble_tokens_bwd_kernel(const float* __restrict__ dx, const uint8_t* __restrict__ mask, bf16* __restrict__ dpatch,
+                           float* __restrict__ dcls, float* __restrict__ dmask_token, int B, int np, int D) {
+  const int row = blockIdx.x;
+  const int b = row / (np + 1), t = row % (np + 1);
+  const bool masked = (t > 0) && mask && mask[(size_t)b * np + t - 1];
+  for (int c = threadIdx.x * 4; c < D; c += blockDim.x * 4) {
+    const float4 v = *(const float4*)(dx + (size_t)row * D + c);
+    if (t == 0) {
+      atomicAdd(dcls + c, v.x); atomicAdd(dcls + c + 1, v.y); atomicAdd(dcls + c + 2, v.z); atomicAdd(dcls + c + 3, v.w);
+    } else {
+      if (masked) {
+        atomicAdd(dmask_token + c, v.x); atomicAdd(dmask_token + c + 1, v.y);
+        atomicAdd(dmask_token + c + 2, v.z); atomicAdd(dmask_token + c + 3, v.w);
+      }
+      st4(dpatch, 0, ((size_t)b * np + t - 1) * D + c, masked ? make_float4(0.f, 0.f, 0.f, 0.f) : v);
+    }
+  }
+}
+
+// Mean-pool pseudo-CLS (beit2.py:456-466): y[b,0,:] = mean_p y[b,1+p,:], written to the bf16 and f32 copies.
+__global__ void __launch_bounds__(256)
+meanpool_fwd_kernel(bf16* __restrict__ y, float* __restrict__ y32, int np, int D) {
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float s = 0.f;
+    for (int p = 1; p <= np; ++p) s += y32[((size_t)b * (np + 1) + p) * D + c];
+    s /= (float)np;
+    y32[(size_t)b * (np + 1) * D + c] = s;
+    y[(size_t)b * (np + 1) * D + c] = __float2bfloat16(s);
+  }
+}
+// dy_ln[b,t,:] = t == 0 ? 0 : dout[b,t,:] + dout[b,0,:] / np
+__global__ void __launch_bounds__(256)
+meanpool_bwd_kernel(const float* __restrict__ dout, float* __restrict__ dy, int np, int D) {
+  const int row = blockIdx.x;
+  const int b = row / (np + 1), t = row % (np + 1);
+  for (int c = threadIdx.x * 4; c < D; c += blockDim.x * 4) {
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t > 0) {
+      const float4 a = *(const float4*)(dout + (size_t)row * D + c);
+      const float4 m = *(const float4*)(dout + (size_t)b * (np + 1) * D + c);
+      const float inv = 1.0f / (float)np;
+      o = make_float4(a.x + m.x * inv, a.y + m.y * inv, a.z + m.z * inv, a.w + m.w * inv);
+    }
+    *(float4*)(dy + (size_t)row * D + c) = o;
+  }
+}
+
+// -------------------------------------------------------------------------------- row gather / scatter-add
+// out[i, :] = in[index[i], :]   (dtype generic; D multiple of 4)
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const void* __restrict__ in, int in_dtype, const int64_t* __restrict__ index, void* __restrict__ out,
+                   int out_dtype, int D) {
+  const size_t src = (size_t)index[blockIdx.x] * D, dst = (size_t)blockIdx.x * D;
+  for (int c = threadIdx.x * 4; c < D; c += blockDim.x * 4) st4(out, out_dtype, dst + c, ld4(in, in_dtype, src + c));
+}
+// out[index[i], :] += in[i, :]   (out f32, atomics: several i may share a destination)
+__global__ void __launch_bounds__(256)
+scatter_add_rows_kernel(const void* __restrict__ in, int in_dtype, const int64_t* __restrict__ index,
+                        float* __restrict__ out, int D) {
+  const size_t dst = (size_t)index[blockIdx.x] * D, src = (size_t)blockIdx.x * D;
+  for (int c = threadIdx.x * 4; c < D; c += blockDim.x * 4) {
+    const float4 v = ld4(in, in_dtype, src + c);
+    atomicAdd(out + dst + c, v.x); atomicAdd(out + dst + c + 1, v.y);
+    atomicAdd(out + dst + c + 2, v.z); atomicAdd(out + dst + c + 3, v.w);
+  }
+}
+
+// Relative-position bias: bias[h, i, j] = table[index[i, j], h] (beit2.py:139-144), and its scatter-add backward.
+// bias / dbias rows have leading dimension ld (>= N) so the attention kernels can use aligned rows.
+__global__ void __launch_bounds__(256)
+relpos_bias_fwd_kernel(const float* __restrict__ table, const int64_t* __restrict__ index, float* __restrict__ bias,
+                       int N, int ld, int H) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * N) return;
+  const int64_t r = index[i];
+  const size_t o = (size_t)(i / N) * ld + (i % N);
+  for (int h = 0; h < H; ++h) bias[(size_t)h * N * ld + o] = table[r * H + h];
+}
+__global__ void __launch_bounds__(256)
+relpos_bias_bwd_kernel(const float* __restrict__ dbias, const int64_t* __restrict__ index, float* __restrict__ dtable,
+                       int N, int ld, int H) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * N) return;
+  const int64_t r = index[i];
+  const size_t o = (size_t)(i / N) * ld + (i % N);
+  for (int h = 0; h < H; ++h) atomicAdd(dtable + r * H + h, dbias[(size_t)h * N * ld + o]);
+}
+
+// Sum over the batch of the bf16 dS dump from attention backward: out[h,i,j] = sum_b ds[b,h,i,j].
+__global__ void __launch_bounds__(256)
+batch_sum_bf16_kernel(const bf16* __restrict__ in, float* __restrict__ out, int B, size_t per) {
+  const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= per) return;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int b = 0; b < B; ++b) {
+    const float4 v = ld4(in, 0, (size_t)b * per + i);
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  }
+  *(float4*)(out + i) = s;
+}
+
+// ------------------------------------------------------------------------------------------ host
+static int ln_check(int D) {
+  if (D % 4 != 0 || D > 32 * 4 * LN_MAX_VEC) {
+    set_error("feature dim %d unsupported (need multiple of 4, <= %d)", D, 32 * 4 * LN_MAX_VEC);
+    return XFM_ERR_BAD_ARG;
+  }
+  return 0;
+}
+static int grid_1d(size_t n, int block) {
+  size_t g = (n + block - 1) / block;
+  const size_t cap = (size_t)num_sms() * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+#define LAUNCH_END()  \
+  count_launch();     \
+  return (int)cudaGetLastError();
+
+int layernorm_fwd(const void* x, int x_dtype, const float* w, const float* b, void* y, int y_dtype, float* y2, float* stats,
+                  int M, int D, float eps, cudaStream_t s) {
+  if (ln_check(D)) return XFM_ERR_BAD_ARG;
+  if (M <= 0) return 0;
+  layernorm_fwd_kernel<<<(M + LN_WARPS - 1) / LN_WARPS, LN_WARPS * 32, 0, s>>>(x, x_dtype, w, b, y, y_dtype, y2, stats, M, D, eps);
+  LAUNCH_END();
+}
+
+static int rows_per_cta_for(int M) {
+  // ~2 CTAs per SM; each CTA reduces its rows before touching the global dw/db atomics
+  int ctas = num_sms() * 2;
+  int r = (M + ctas - 1) / ctas;
+  r = ((r + LN_WARPS - 1) / LN_WARPS) * LN_WARPS;
+  return r < LN_WARPS ? LN_WARPS : r;
+}
+
+int layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* stats, const float* w,
+                  const void* add_in, int add_dtype, void* dx, int dx_dtype, float* dw, float* db, int M, int D,
+                  cudaStream_t s) {
+  if (ln_check(D)) return XFM_ERR_BAD_ARG;
+  if (M <= 0) return 0;
+  const int rpc = rows_per_cta_for(M);
+  const int grid = (M + rpc - 1) / rpc;
+  const size_t smem = dw ? (size_t)2 * LN_WARPS * D * sizeof(float) : 0;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(layernorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * LN_WARPS * 2048 * 4);
+    attr = true;
+  }
+  layernorm_bwd_kernel<<<grid, LN_WARPS * 32, smem, s>>>(dy, dy_dtype, x, x_dtype, stats, w, add_in, add_dtype, dx, dx_dtype, dw,
+                                                         db, M, D, rpc);
+  LAUNCH_END();
+}
+
+int layerscale_bwd(const float* dxo, const bf16* z, const float* gamma, const float* rs, int rpg, bf16* dz, float* dgamma,
+                   float* dbias, int M, int D, cudaStream_t s) {
+  if (ln_check(D)) return XFM_ERR_BAD_ARG;
+  if (M <= 0) return 0;
+  const int rpc = rows_per_cta_for(M);
+  const int grid = (M + rpc - 1) / rpc;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(layerscale_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * LN_WARPS * 2048 * 4);
+    attr = true;
+  }
+  layerscale_bwd_kernel<<<grid, LN_WARPS * 32, (size_t)2 * LN_WARPS * D * sizeof(float), s>>>(dxo, z, gamma, rs, rpg > 0 ? rpg : 1,
+                                                                                              dz, dgamma, dbias, M, D, rpc);
+  LAUNCH_END();
+}
+
+int colsum_bf16(const bf16* in, int64_t ld, float* out, int M, int N, cudaStream_t s) {
+  if ((N & 7) || (ld & 7)) {
+    set_error("colsum: N and ld must be multiples of 8");
+    return XFM_ERR_BAD_ARG;
+  }
+  if (M <= 0) return 0;
+  const int gx = (N + 255) / 256;
+  int gy = (num_sms() * 2 + gx - 1) / gx;
+  int rpc = (M + gy - 1) / gy;
+  rpc = ((rpc + 7) / 8) * 8;
+  gy = (M + rpc - 1) / rpc;
+  colsum_kernel<<<dim3(gx, gy), dim3(32, 8), 0, s>>>(in, ld, out, M, N, rpc);
+  LAUNCH_END();
+}
+
+int cast_f32_to_bf16(const float* in, bf16* out, size_t n, cudaStream_t s) {
+  if (n & 3) { set_error("cast: n must be a multiple of 4"); return XFM_ERR_BAD_ARG; }
+  if (!n) return 0;
+  cast_f32_to_bf16_kernel<<<grid_1d(n / 4, 256), 256, 0, s>>>(in, out, n / 4);
+  LAUNCH_END();
+}
+int cast_bf16_to_f32(const bf16* in, float* out, size_t n, cudaStream_t s) {
+  if (n & 3) { set_error("cast: n must be a multiple of 4"); return XFM_ERR_BAD_ARG; }
+  if (!n) return 0;
+  cast_bf16_to_f32_kernel<<<grid_1d(n / 4, 256), 256, 0, s>>>(in, out, n / 4);
+  LAUNCH_END();
+}
+int scale_by_scalar(void* data, int dtype, const float* scalar, size_t n, cudaStream_t s) {
+  if (n & 3) { set_error("scale: n must be a multiple of 4"); return XFM_ERR_BAD_ARG; }
+  if (!n) return 0;
+  scale_by_scalar_kernel<<<grid_1d(n / 4, 256), 256, 0, s>>>(data, dtype, scalar, n / 4);
+  LAUNCH_END();
+}
+
+int roberta_embed_fwd(const int64_t* ids, const float* word, const float* pos, const float* type0, const float* w,
+                      const float* b, bf16* y, float* pre_ln, float* stats, int32_t* pos_ids, int B, int L, int D,
+                      int pad_id, float eps, cudaStream_t s) {
+  if (ln_check(D)) return XFM_ERR_BAD_ARG;
+  if (B <= 0) return 0;
+  roberta_embed_fwd_kernel<<<B, LN_WARPS * 32, L * sizeof(int), s>>>(ids, word, pos, type0, w, b, y, pre_ln, stats, pos_ids, L, D,
+                                                                   pad_id, eps);
+  LAUNCH_END();
+}
+int roberta_embed_bwd(const float* dpre, const int64_t* ids, const int32_t* pos_ids, float* dword, float* dpos,
+                      float* dtype0, int rows, int D, int pad_id, cudaStream_t s) {
+  if (rows <= 0) return 0;
+  roberta_embed_bwd_kernel<<<rows, 256, 0, s>>>(dpre, ids, pos_ids, dword, dpos, dtype0, rows, D, pad_id);
+  LAUNCH_END();
+}
+
+int im2col(const float* img, bf16* out, int B, int C, int H, int W, int P, float pre_mul, cudaStream_t s) {
+  if (P % 4 || H % P || W % P) { set_error("im2col: bad geometry"); return XFM_ERR_BAD_ARG; }
+  const size_t n4 = (size_t)B * C * H * W / 4;
+  im2col_kernel<<<grid_1d(n4, 256), 256, 0, s>>>(img, out, B, C, H, W, P, pre_mul);
+  LAUNCH_END();
+}
+int assemble_tokens(const float* patch, const float* cls, const float* mask_token, const uint8_t* mask, const float* pos,
+                    float* x, int B, int np, int D, cudaStream_t s) {
+  assemble_tokens_kernel<<<B * (np + 1), 256, 0, s>>>(patch, cls, mask_token, mask, pos, x, B, np, D);
+  LAUNCH_END();
+}
+int assemble_tokens_bwd(const float* dx, const uint8_t* mask, bf16* dpatch, float* dcls, float* dmask_token, int B, int np,
+                        int D, cudaStream_t s) {
+  assemble_tokens_bwd_kernel<<<B * (np + 1), 256, 0, s>>>(dx, mask, dpatch, dcls, dmask_token, B, np, D);
+  LAUNCH_END();
+}
+int meanpool_fwd(bf16* y, float* y32, int B, int np, int D, cudaStream_t s) {
+  meanpool_fwd_kernel<<<B, 256, 0, s>>>(y, y32, np, D);
+  LAUNCH_END();
+}
+int meanpool_bwd(const float* dout, float* dy, int B, int np, int D, cudaStream_t s) {
+  meanpool_bwd_kernel<<<B * (np + 1), 256, 0, s>>>(dout, dy, np, D);
+  LAUNCH_END();
+}
+int gather_rows(const void* in, int in_dtype, const int64_t* index, void* out, int out_dtype, int n, int D, cudaStream_t s) {
+  if (D & 3) { set_error("gather: D must be a multiple of 4"); return XFM_ERR_BAD_ARG; }
+  if (n <= 0) return 0;
+  gather_rows_kernel<<<n, 256, 0, s>>>(in, in_dtype, index, out, out_dtype, D);
+  LAUNCH_END();
+}
+int scatter_add_rows(const void* in, int in_dtype, const int64_t* index, float* out, int n, int D, cudaStream_t s) {
+  if (D & 3) { set_error("scatter: D must be a multiple of 4"); return XFM_ERR_BAD_ARG; }
+  if (n <= 0) return 0;
+  scatter_add_rows_kernel<<<n, 256, 0, s>>>(in, in_dtype, index, out, D);
+  LAUNCH_END();
+}
+int relpos_bias_fwd(const float* table, const int64_t* index, float* bias, int N, int ld, int H, cudaStream_t s) {
+  relpos_bias_fwd_kernel<<<(N * N + 255) / 256, 256, 0, s>>>(table, index, bias, N, ld, H);
+  LAUNCH_END();
+}
+int relpos_bias_bwd(const float* dbias, const int64_t* index, float* dtable, int N, int ld, int H, cudaStream_t s) {
+  relpos_bias_bwd_kernel<<<(N * N + 255) / 256, 256, 0, s>>>(dbias, index, dtable, N, ld, H);
+  LAUNCH_END();
+}
+int batch_sum_bf16(const bf16* in, float* out, int B, size_t per, cudaStream_t s) {
+  if (per & 3) { set_error("batch_sum: per must be a multiple of 4"); return XFM_ERR_BAD_ARG; }
+  batch_sum_bf16_kernel<<<(unsigned)((per / 4 + 255) / 256), 256, 0, s>>>(in, out, B, per);
+  LAUNCH_END();
+}
+
+}  // namespace xfm
