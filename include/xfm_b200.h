@@ -89,6 +89,116 @@ typedef struct xfm_gemm_params {
 
 int xfm_gemm_bf16(const xfm_gemm_params* p, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * K2/K3/K4 — flash-style attention, head_dim 64 (scores never written to HBM).
+ * Replaces beit2.py:133-159 (q*scale, q@k^T, + relative_position_bias, softmax, @v),
+ * xroberta.py:237-284 (q/sqrt(d), + (1-m)*-1e4 mask, softmax, dropout, @v) and the cross-attention
+ * call at xroberta.py:448-455, plus their autograd backward.
+ *   q rows of sample b: q + (b*Lq + i)*q_stride + h*64;  k/v rows: k + (kv_row*Lk + j)*k_stride + h*64,
+ *   kv_row = kv_index ? kv_index[b] : b  (several samples may attend to one image's K/V).
+ *   logits = scale * q.k + bias[h,i,j] + kmask[b,j]
+ * Backward needs lse (saved by the forward), a [B,H,Lq] f32 scratch `delta`, and writes bf16 dq/dk/dv.
+ * ds_dump (optional, bf16 [B,H,Lq,ds_ld]) receives dS for the relative-position-bias gradient.
+ * kv_offsets/kv_samples: CSR inverse of kv_index over the Bkv K/V rows (null = identity).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct xfm_attn_params {
+  const void *q, *k, *v;
+  void* out;
+  float* lse;
+  const float* bias;
+  const float* kmask;
+  const int32_t* kv_index;
+  int64_t q_stride, k_stride, v_stride, o_stride, bias_ld;
+  int32_t B, H, Lq, Lk, head_dim, Bkv;
+  float scale, dropout_p;
+  uint64_t dropout_seed;
+  /* backward */
+  const void* dout;
+  float* delta;
+  void *dq, *dk, *dv, *ds_dump;
+  int64_t do_stride, dq_stride, dk_stride, dv_stride, ds_ld;
+  const int32_t* kv_offsets;
+  const int32_t* kv_samples;
+} xfm_attn_params;
+
+int xfm_attention_fwd(const xfm_attn_params* p, void* stream);
+int xfm_attention_bwd(const xfm_attn_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K6 — LayerNorm (torch layer_norm at beit2.py:201-205,458; xroberta.py:135,303,384,1328; xfm.py:118).
+ * dtype codes: 0 = bf16, 1 = f32.  stats = [M,2] f32 (mean, rstd).  y2_f32: optional second f32 copy.
+ * bwd: dx = LN'(dy) (+ add_in); dw/db accumulate (+=) with f32 atomics.
+ * ---------------------------------------------------------------------------------------------- */
+int xfm_layernorm_fwd(const void* x, int x_dtype, const float* w, const float* b, void* y, int y_dtype, float* y2_f32,
+                      float* stats, int M, int D, float eps, void* stream);
+int xfm_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* stats, const float* w,
+                      const void* add_in, int add_dtype, void* dx, int dx_dtype, float* dw, float* db, int M, int D,
+                      void* stream);
+/* LayerScale / DropPath backward (beit2.py:204-205): dz = dx_out*gamma*rs; dgamma += sum dx_out*rs*z; dbias += sum dz. */
+int xfm_layerscale_bwd(const float* dx_out, const void* z_bf16, const float* gamma, const float* row_group_scale,
+                       int rows_per_group, void* dz_bf16, float* dgamma, float* dbias, int M, int D, void* stream);
+/* out[c] += sum_rows in[row,c]  (bias gradients of every Linear). */
+int xfm_colsum_bf16(const void* in, int64_t ld, float* out, int M, int N, void* stream);
+int xfm_cast_f32_to_bf16(const float* in, void* out, size_t n, void* stream);
+int xfm_cast_bf16_to_f32(const void* in, float* out, size_t n, void* stream);
+int xfm_scale_by_scalar(void* data, int dtype, const float* scalar, size_t n, void* stream);
+
+/* Stand-alone GELU(erf) forward / backward (xfm.py:115-121 ITM head; xroberta.py:1325-1328 LM head) and the
+ * dropout mask re-application used by the backward of the GEMM dropout epilogue (same (seed, row*N+col) stream). */
+int xfm_gelu_fwd(const void* x, int x_dtype, void* y_bf16, size_t n, void* stream);
+int xfm_gelu_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, void* dx_bf16, size_t n, void* stream);
+int xfm_dropout_apply(const void* x, int x_dtype, void* y_bf16, size_t n, float p, uint64_t seed, void* stream);
+
+/* K7 — RoBERTa embeddings + position ids + LayerNorm (xroberta.py:104-137, :1747-1757) and the scatter-add backward. */
+int xfm_roberta_embed_fwd(const int64_t* ids, const float* word, const float* pos, const float* type0, const float* ln_w,
+                          const float* ln_b, void* y_bf16, float* pre_ln, float* stats, int32_t* pos_ids, int B, int L,
+                          int D, int pad_id, float eps, void* stream);
+int xfm_roberta_embed_bwd(const float* dpre, const int64_t* ids, const int32_t* pos_ids, float* dword, float* dpos,
+                          float* dtype0, int rows, int D, int pad_id, void* stream);
+
+/* K8/K9 — patch-embed im2col (beit2.py:229), token assembly with mask-token blend + CLS (+ abs pos) (beit2.py:438-449),
+ * mean-pool pseudo-CLS (beit2.py:456-466) and their backward. */
+int xfm_im2col(const float* image, void* out_bf16, int B, int C, int H, int W, int P, float pre_mul, void* stream);
+int xfm_assemble_tokens(const float* patch, const float* cls, const float* mask_token, const uint8_t* mask, const float* pos,
+                        float* x, int B, int np, int D, void* stream);
+int xfm_assemble_tokens_bwd(const float* dx, const uint8_t* mask, void* dpatch_bf16, float* dcls, float* dmask_token, int B,
+                            int np, int D, void* stream);
+int xfm_meanpool_fwd(void* y_bf16, float* y_f32, int B, int np, int D, void* stream);
+int xfm_meanpool_bwd(const float* dout, float* dy, int B, int np, int D, void* stream);
+
+/* K12 — row gather / scatter-add (xfm.py:758-786 negatives, xroberta.py:1215-1216 masked positions, xfm.py:629 masked patches). */
+int xfm_gather_rows(const void* in, int in_dtype, const int64_t* index, void* out, int out_dtype, int n, int D, void* stream);
+int xfm_scatter_add_rows(const void* in, int in_dtype, const int64_t* index, float* out, int n, int D, void* stream);
+
+/* Relative position bias gather (beit2.py:139-144) and its backward; batch reduction of the attention dS dump. */
+int xfm_relpos_bias_fwd(const float* table, const int64_t* index, float* bias, int N, int ld, int H, void* stream);
+int xfm_relpos_bias_bwd(const float* dbias, const int64_t* index, float* dtable, int N, int ld, int H, void* stream);
+int xfm_batch_sum_bf16(const void* in, float* out, int B, size_t per, void* stream);
+
+/* K13/K14 — softmax cross-entropy with ignore_index=-100 (xroberta.py:1298-1299; xfm.py:629,800-802).
+ * fwd: row_loss[R], lse[R], *loss = mean over valid rows, *count = #valid.  bwd: dlogits (bf16, ld = ldd) =
+ * (softmax - onehot) * (*upstream) / count. */
+int xfm_ce_fwd(const float* logits, int64_t ld, const int64_t* labels, int R, int V, float* row_loss, float* lse, float* loss,
+               float* count, void* stream);
+int xfm_ce_bwd(const float* logits, int64_t ld, const int64_t* labels, const float* lse, const float* count,
+               const float* upstream, void* dlogits_bf16, int64_t ldd, int R, int V, void* stream);
+
+/* K10 — ITC (xfm.py:683-715) on gathered features [n,E] f32: loss and, in the same call, the gradients wrt the LOCAL
+ * slice [local_off, local_off+local_n) of image/text features (AllGather.backward, xfm.py:93-98) and wrt temp, for an
+ * upstream gradient of 1.  work: f32 scratch of xfm_itc_workspace(n) elements. */
+size_t xfm_itc_workspace(int n);
+int xfm_itc_loss_fused(const float* image_all, const float* text_all, int n, int E, const int64_t* idx_all, const float* temp,
+                       int local_off, int local_n, float* work, float* loss, float* d_image_local, float* d_text_local,
+                       float* dtemp, void* stream);
+
+/* K11 — ITM hard negatives (xfm.py:717-746): weights (optional outputs, [B,B] f32) and one on-device draw per row. */
+int xfm_hard_negatives(const float* image_feat, const float* text_feat, int B, int E, const float* temp, const int64_t* idx,
+                       uint64_t seed, float* w_i2t, float* w_t2i, int64_t* text_neg_idx, int64_t* image_neg_idx, void* stream);
+
+/* K15 — VQ-KD codebook argmin (norm_ema_quantizer.py:149-162): z [R,32] f32 (un-normalised), codebook [K,32] f32,
+ * ids [R] int64.  Bit-exact contract: exact fp32 arithmetic, first index on ties. */
+int xfm_vq_argmin(const float* z, const float* codebook, int64_t* ids, int R, int K, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

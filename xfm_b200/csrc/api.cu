@@ -51,6 +51,98 @@ int xfm_init(void) {
 int64_t xfm_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 const char* xfm_last_error(void) { return g_err; }
 
-int xfm_gemm_bf16(const xfm_gemm_params* p, void* stream) { return gemm_bf16(p, (cudaStream_t)stream); }
+#define ST ((cudaStream_t)stream)
+#define BF(p) ((bf16_t*)(p))
+#define CBF(p) ((const bf16_t*)(p))
+
+int xfm_gemm_bf16(const xfm_gemm_params* p, void* stream) { return gemm_bf16(p, ST); }
+int xfm_attention_fwd(const xfm_attn_params* p, void* stream) { return attention_fwd(p, ST); }
+int xfm_attention_bwd(const xfm_attn_params* p, void* stream) { return attention_bwd(p, ST); }
+
+int xfm_layernorm_fwd(const void* x, int x_dtype, const float* w, const float* b, void* y, int y_dtype, float* y2_f32,
+                      float* stats, int M, int D, float eps, void* stream) {
+  return layernorm_fwd(x, x_dtype, w, b, y, y_dtype, y2_f32, stats, M, D, eps, ST);
+}
+int xfm_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* stats, const float* w,
+                      const void* add_in, int add_dtype, void* dx, int dx_dtype, float* dw, float* db, int M, int D,
+                      void* stream) {
+  return layernorm_bwd(dy, dy_dtype, x, x_dtype, stats, w, add_in, add_dtype, dx, dx_dtype, dw, db, M, D, ST);
+}
+int xfm_layerscale_bwd(const float* dx_out, const void* z, const float* gamma, const float* rs, int rpg, void* dz, float* dgamma,
+                       float* dbias, int M, int D, void* stream) {
+  return layerscale_bwd(dx_out, CBF(z), gamma, rs, rpg, BF(dz), dgamma, dbias, M, D, ST);
+}
+int xfm_colsum_bf16(const void* in, int64_t ld, float* out, int M, int N, void* stream) {
+  return colsum_bf16(CBF(in), ld, out, M, N, ST);
+}
+int xfm_cast_f32_to_bf16(const float* in, void* out, size_t n, void* stream) { return cast_f32_to_bf16(in, BF(out), n, ST); }
+int xfm_cast_bf16_to_f32(const void* in, float* out, size_t n, void* stream) { return cast_bf16_to_f32(CBF(in), out, n, ST); }
+int xfm_scale_by_scalar(void* data, int dtype, const float* scalar, size_t n, void* stream) {
+  return scale_by_scalar(data, dtype, scalar, n, ST);
+}
+int xfm_gelu_fwd(const void* x, int x_dtype, void* y, size_t n, void* stream) { return gelu_fwd(x, x_dtype, BF(y), n, ST); }
+int xfm_gelu_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, void* dx, size_t n, void* stream) {
+  return gelu_bwd(dy, dy_dtype, x, x_dtype, BF(dx), n, ST);
+}
+int xfm_dropout_apply(const void* x, int x_dtype, void* y, size_t n, float p, uint64_t seed, void* stream) {
+  return dropout_apply(x, x_dtype, BF(y), n, p, seed, ST);
+}
+int xfm_roberta_embed_fwd(const int64_t* ids, const float* word, const float* pos, const float* type0, const float* ln_w,
+                          const float* ln_b, void* y, float* pre_ln, float* stats, int32_t* pos_ids, int B, int L, int D,
+                          int pad_id, float eps, void* stream) {
+  return roberta_embed_fwd(ids, word, pos, type0, ln_w, ln_b, BF(y), pre_ln, stats, pos_ids, B, L, D, pad_id, eps, ST);
+}
+int xfm_roberta_embed_bwd(const float* dpre, const int64_t* ids, const int32_t* pos_ids, float* dword, float* dpos,
+                          float* dtype0, int rows, int D, int pad_id, void* stream) {
+  return roberta_embed_bwd(dpre, ids, pos_ids, dword, dpos, dtype0, rows, D, pad_id, ST);
+}
+int xfm_im2col(const float* image, void* out, int B, int C, int H, int W, int P, float pre_mul, void* stream) {
+  return im2col(image, BF(out), B, C, H, W, P, pre_mul, ST);
+}
+int xfm_assemble_tokens(const float* patch, const float* cls, const float* mask_token, const uint8_t* mask, const float* pos,
+                        float* x, int B, int np, int D, void* stream) {
+  return assemble_tokens(patch, cls, mask_token, mask, pos, x, B, np, D, ST);
+}
+int xfm_assemble_tokens_bwd(const float* dx, const uint8_t* mask, void* dpatch, float* dcls, float* dmask_token, int B, int np,
+                            int D, void* stream) {
+  return assemble_tokens_bwd(dx, mask, BF(dpatch), dcls, dmask_token, B, np, D, ST);
+}
+int xfm_meanpool_fwd(void* y, float* y_f32, int B, int np, int D, void* stream) { return meanpool_fwd(BF(y), y_f32, B, np, D, ST); }
+int xfm_meanpool_bwd(const float* dout, float* dy, int B, int np, int D, void* stream) { return meanpool_bwd(dout, dy, B, np, D, ST); }
+int xfm_gather_rows(const void* in, int in_dtype, const int64_t* index, void* out, int out_dtype, int n, int D, void* stream) {
+  return gather_rows(in, in_dtype, index, out, out_dtype, n, D, ST);
+}
+int xfm_scatter_add_rows(const void* in, int in_dtype, const int64_t* index, float* out, int n, int D, void* stream) {
+  return scatter_add_rows(in, in_dtype, index, out, n, D, ST);
+}
+int xfm_relpos_bias_fwd(const float* table, const int64_t* index, float* bias, int N, int ld, int H, void* stream) {
+  return relpos_bias_fwd(table, index, bias, N, ld, H, ST);
+}
+int xfm_relpos_bias_bwd(const float* dbias, const int64_t* index, float* dtable, int N, int ld, int H, void* stream) {
+  return relpos_bias_bwd(dbias, index, dtable, N, ld, H, ST);
+}
+int xfm_batch_sum_bf16(const void* in, float* out, int B, size_t per, void* stream) { return batch_sum_bf16(CBF(in), out, B, per, ST); }
+int xfm_ce_fwd(const float* logits, int64_t ld, const int64_t* labels, int R, int V, float* row_loss, float* lse, float* loss,
+               float* count, void* stream) {
+  return ce_fwd(logits, ld, labels, R, V, row_loss, lse, loss, count, ST);
+}
+int xfm_ce_bwd(const float* logits, int64_t ld, const int64_t* labels, const float* lse, const float* count,
+               const float* upstream, void* dlogits, int64_t ldd, int R, int V, void* stream) {
+  return ce_bwd(logits, ld, labels, lse, count, upstream, BF(dlogits), ldd, R, V, ST);
+}
+size_t xfm_itc_workspace(int n) { return (size_t)2 * n * n + (size_t)3 * n; }
+int xfm_itc_loss_fused(const float* image_all, const float* text_all, int n, int E, const int64_t* idx_all, const float* temp,
+                       int local_off, int local_n, float* work, float* loss, float* d_image_local, float* d_text_local,
+                       float* dtemp, void* stream) {
+  return itc_loss_fused(image_all, text_all, n, E, idx_all, temp, local_off, local_n, work, loss, d_image_local, d_text_local,
+                        dtemp, ST);
+}
+int xfm_hard_negatives(const float* image_feat, const float* text_feat, int B, int E, const float* temp, const int64_t* idx,
+                       uint64_t seed, float* w_i2t, float* w_t2i, int64_t* text_neg_idx, int64_t* image_neg_idx, void* stream) {
+  return hard_negatives(image_feat, text_feat, B, E, temp, idx, seed, w_i2t, w_t2i, text_neg_idx, image_neg_idx, ST);
+}
+int xfm_vq_argmin(const float* z, const float* codebook, int64_t* ids, int R, int K, int C, void* stream) {
+  return vq_argmin(z, codebook, ids, R, K, C, ST);
+}
 
 }  // extern "C"

@@ -273,6 +273,38 @@ __global__ void scale_by_scalar_kernel(void* __restrict__ data, int dtype, const
   }
 }
 
+// y = gelu(x) (bf16 -> bf16) and dx = dy * gelu'(x): the two GELU sites that do not sit behind a GEMM epilogue
+// (ITM head: Linear -> LayerNorm -> GELU, xfm.py:115-121; LM head backward: dense -> GELU -> LayerNorm, xroberta.py:1325-1328).
+__global__ void gelu_fwd_kernel(const void* __restrict__ x, int x_dtype, bf16* __restrict__ y, size_t n4) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 v = ld4(x, x_dtype, 4 * i);
+    v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
+    st4(y, 0, 4 * i, v);
+  }
+}
+__global__ void gelu_bwd_kernel(const void* __restrict__ dy, int dy_dtype, const void* __restrict__ x, int x_dtype,
+                                bf16* __restrict__ dx, size_t n4) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 g = ld4(dy, dy_dtype, 4 * i), v = ld4(x, x_dtype, 4 * i);
+    st4(dx, 0, 4 * i, make_float4(g.x * gelu_erf_grad(v.x), g.y * gelu_erf_grad(v.y), g.z * gelu_erf_grad(v.z),
+                                  g.w * gelu_erf_grad(v.w)));
+  }
+}
+// y[i] = keep(seed, i) ? x[i] / (1-p) : 0 with the SAME (seed, row * N + col) indexing as the GEMM dropout epilogue, so
+// the backward pass re-applies the forward mask to the incoming gradient without storing it (xroberta.py:302,383).
+__global__ void dropout_apply_kernel(const void* __restrict__ x, int x_dtype, bf16* __restrict__ y, size_t n4, float p,
+                                     uint64_t seed) {
+  const float inv_keep = 1.0f / (1.0f - p);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 v = ld4(x, x_dtype, 4 * i);
+    v.x = hash_uniform(seed, 4 * i) >= p ? v.x * inv_keep : 0.f;
+    v.y = hash_uniform(seed, 4 * i + 1) >= p ? v.y * inv_keep : 0.f;
+    v.z = hash_uniform(seed, 4 * i + 2) >= p ? v.z * inv_keep : 0.f;
+    v.w = hash_uniform(seed, 4 * i + 3) >= p ? v.w * inv_keep : 0.f;
+    st4(y, 0, 4 * i, v);
+  }
+}
+
 // -------------------------------------------------------------------------------- RoBERTa embeddings
 // pos_ids = cumsum(ids != pad) * (ids != pad) + pad (xroberta.py:1747-1757); emb = word + type0 + pos; LayerNorm.
 // One CTA per sequence, one warp per token (round-robin).  Saves pos_ids and LN stats for the backward.
@@ -622,6 +654,25 @@ int scale_by_scalar(void* data, int dtype, const float* scalar, size_t n, cudaSt
   if (n & 3) { set_error("scale: n must be a multiple of 4"); return XFM_ERR_BAD_ARG; }
   if (!n) return 0;
   scale_by_scalar_kernel<<<grid_1d(n / 4, 256), 256, 0, s>>>(data, dtype, scalar, n / 4);
+  LAUNCH_END();
+}
+
+int gelu_fwd(const void* x, int x_dtype, bf16* y, size_t n, cudaStream_t s) {
+  if (n & 3) { set_error("gelu: n must be a multiple of 4"); return XFM_ERR_BAD_ARG; }
+  if (!n) return 0;
+  gelu_fwd_kernel<<<grid_1d(n / 4, 256), 256, 0, s>>>(x, x_dtype, y, n / 4);
+  LAUNCH_END();
+}
+int gelu_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, bf16* dx, size_t n, cudaStream_t s) {
+  if (n & 3) { set_error("gelu: n must be a multiple of 4"); return XFM_ERR_BAD_ARG; }
+  if (!n) return 0;
+  gelu_bwd_kernel<<<grid_1d(n / 4, 256), 256, 0, s>>>(dy, dy_dtype, x, x_dtype, dx, n / 4);
+  LAUNCH_END();
+}
+int dropout_apply(const void* x, int x_dtype, bf16* y, size_t n, float p, uint64_t seed, cudaStream_t s) {
+  if (n & 3) { set_error("dropout: n must be a multiple of 4"); return XFM_ERR_BAD_ARG; }
+  if (!n) return 0;
+  dropout_apply_kernel<<<grid_1d(n / 4, 256), 256, 0, s>>>(x, x_dtype, y, n / 4, p, seed);
   LAUNCH_END();
 }
 

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
 #include <stdint.h>
 #include "../../include/xfm_b200.h"
 
@@ -16,5 +17,50 @@ int num_sms();
 void count_launch(int n = 1);
 
 int gemm_bf16(const xfm_gemm_params* p, cudaStream_t stream);
+int attention_fwd(const xfm_attn_params* p, cudaStream_t s);
+int attention_bwd(const xfm_attn_params* p, cudaStream_t s);
+
+typedef __nv_bfloat16 bf16_t;
+int layernorm_fwd(const void* x, int x_dtype, const float* w, const float* b, void* y, int y_dtype, float* y2, float* stats,
+                  int M, int D, float eps, cudaStream_t s);
+int layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* stats, const float* w,
+                  const void* add_in, int add_dtype, void* dx, int dx_dtype, float* dw, float* db, int M, int D,
+                  cudaStream_t s);
+int layerscale_bwd(const float* dxo, const bf16_t* z, const float* gamma, const float* rs, int rpg, bf16_t* dz, float* dgamma,
+                   float* dbias, int M, int D, cudaStream_t s);
+int colsum_bf16(const bf16_t* in, int64_t ld, float* out, int M, int N, cudaStream_t s);
+int cast_f32_to_bf16(const float* in, bf16_t* out, size_t n, cudaStream_t s);
+int cast_bf16_to_f32(const bf16_t* in, float* out, size_t n, cudaStream_t s);
+int scale_by_scalar(void* data, int dtype, const float* scalar, size_t n, cudaStream_t s);
+int gelu_fwd(const void* x, int x_dtype, bf16_t* y, size_t n, cudaStream_t s);
+int gelu_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, bf16_t* dx, size_t n, cudaStream_t s);
+int dropout_apply(const void* x, int x_dtype, bf16_t* y, size_t n, float p, uint64_t seed, cudaStream_t s);
+int roberta_embed_fwd(const int64_t* ids, const float* word, const float* pos, const float* type0, const float* w,
+                      const float* b, bf16_t* y, float* pre_ln, float* stats, int32_t* pos_ids, int B, int L, int D,
+                      int pad_id, float eps, cudaStream_t s);
+int roberta_embed_bwd(const float* dpre, const int64_t* ids, const int32_t* pos_ids, float* dword, float* dpos,
+                      float* dtype0, int rows, int D, int pad_id, cudaStream_t s);
+int im2col(const float* img, bf16_t* out, int B, int C, int H, int W, int P, float pre_mul, cudaStream_t s);
+int assemble_tokens(const float* patch, const float* cls, const float* mask_token, const uint8_t* mask, const float* pos,
+                    float* x, int B, int np, int D, cudaStream_t s);
+int assemble_tokens_bwd(const float* dx, const uint8_t* mask, bf16_t* dpatch, float* dcls, float* dmask_token, int B, int np,
+                        int D, cudaStream_t s);
+int meanpool_fwd(bf16_t* y, float* y32, int B, int np, int D, cudaStream_t s);
+int meanpool_bwd(const float* dout, float* dy, int B, int np, int D, cudaStream_t s);
+int gather_rows(const void* in, int in_dtype, const int64_t* index, void* out, int out_dtype, int n, int D, cudaStream_t s);
+int scatter_add_rows(const void* in, int in_dtype, const int64_t* index, float* out, int n, int D, cudaStream_t s);
+int relpos_bias_fwd(const float* table, const int64_t* index, float* bias, int N, int ld, int H, cudaStream_t s);
+int relpos_bias_bwd(const float* dbias, const int64_t* index, float* dtable, int N, int ld, int H, cudaStream_t s);
+int batch_sum_bf16(const bf16_t* in, float* out, int B, size_t per, cudaStream_t s);
+int ce_fwd(const float* logits, int64_t ld, const int64_t* labels, int R, int V, float* row_loss, float* lse, float* loss,
+           float* count, cudaStream_t s);
+int ce_bwd(const float* logits, int64_t ld, const int64_t* labels, const float* lse, const float* count, const float* upstream,
+           bf16_t* dlogits, int64_t ldd, int R, int V, cudaStream_t s);
+int itc_loss_fused(const float* image_all, const float* text_all, int n, int E, const int64_t* idx_all, const float* temp,
+                   int local_off, int local_n, float* work, float* loss, float* d_image_local, float* d_text_local,
+                   float* dtemp, cudaStream_t s);
+int hard_negatives(const float* image_feat, const float* text_feat, int B, int E, const float* temp, const int64_t* idx,
+                   uint64_t seed, float* w_i2t, float* w_t2i, int64_t* text_neg, int64_t* image_neg, cudaStream_t s);
+int vq_argmin(const float* z, const float* codebook, int64_t* ids, int R, int K, int C, cudaStream_t s);
 
 }  // namespace xfm

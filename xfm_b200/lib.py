@@ -137,3 +137,309 @@ def gemm(a, b, *, a_t=False, b_t=False, out=None, out_dtype=torch.bfloat16, bias
     p.dropout_seed = dropout_seed
     check(lib().xfm_gemm_bf16(C.byref(p), stream_ptr()), "xfm_gemm_bf16")
     return out
+
+
+# ------------------------------------------------------------------------------------------------------
+# attention
+# ------------------------------------------------------------------------------------------------------
+class AttnParams(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("out", C.c_void_p), ("lse", C.c_void_p),
+        ("bias", C.c_void_p), ("kmask", C.c_void_p), ("kv_index", C.c_void_p),
+        ("q_stride", C.c_int64), ("k_stride", C.c_int64), ("v_stride", C.c_int64), ("o_stride", C.c_int64),
+        ("bias_ld", C.c_int64),
+        ("B", C.c_int32), ("H", C.c_int32), ("Lq", C.c_int32), ("Lk", C.c_int32), ("head_dim", C.c_int32),
+        ("Bkv", C.c_int32),
+        ("scale", C.c_float), ("dropout_p", C.c_float), ("dropout_seed", C.c_uint64),
+        ("dout", C.c_void_p), ("delta", C.c_void_p),
+        ("dq", C.c_void_p), ("dk", C.c_void_p), ("dv", C.c_void_p), ("ds_dump", C.c_void_p),
+        ("do_stride", C.c_int64), ("dq_stride", C.c_int64), ("dk_stride", C.c_int64), ("dv_stride", C.c_int64),
+        ("ds_ld", C.c_int64),
+        ("kv_offsets", C.c_void_p), ("kv_samples", C.c_void_p),
+    ]
+
+
+def _attn_common(p, q, k, v, B, H, Lq, Lk, Bkv, scale, bias, kmask, kv_index, dropout_p, dropout_seed):
+    for t in (q, k, v):
+        assert t.dtype == torch.bfloat16 and t.dim() == 2 and t.stride(1) == 1
+    assert q.shape[0] == B * Lq and k.shape[0] == Bkv * Lk and v.shape[0] == Bkv * Lk
+    p.q, p.k, p.v = q.data_ptr(), k.data_ptr(), v.data_ptr()
+    p.q_stride, p.k_stride, p.v_stride = q.stride(0), k.stride(0), v.stride(0)
+    p.B, p.H, p.Lq, p.Lk, p.head_dim, p.Bkv = B, H, Lq, Lk, 64, Bkv
+    p.scale, p.dropout_p, p.dropout_seed = scale, dropout_p, dropout_seed
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.dim() == 3 and bias.shape[0] == H and bias.shape[1] == Lq
+        assert bias.stride(2) == 1 and bias.stride(0) == Lq * bias.stride(1)
+        p.bias, p.bias_ld = bias.data_ptr(), bias.stride(1)
+    if kmask is not None:
+        assert kmask.dtype == torch.float32 and kmask.shape == (B, Lk) and kmask.is_contiguous()
+        p.kmask = kmask.data_ptr()
+    if kv_index is not None:
+        assert kv_index.dtype == torch.int32 and kv_index.numel() == B
+        p.kv_index = kv_index.data_ptr()
+
+
+def attention_fwd(q, k, v, B, H, Lq, Lk, scale, *, Bkv=None, bias=None, kmask=None, kv_index=None, dropout_p=0.0,
+                  dropout_seed=0, out=None):
+    """q: bf16 [B*Lq, >=H*64] view; k, v: bf16 [Bkv*Lk, ...] views.  Returns (out bf16 [B*Lq, H*64], lse f32 [B,H,Lq])."""
+    Bkv = B if Bkv is None else Bkv
+    if out is None:
+        out = torch.empty((B * Lq, H * 64), dtype=torch.bfloat16, device=q.device)
+    lse = torch.empty((B, H, Lq), dtype=torch.float32, device=q.device)
+    p = AttnParams()
+    _attn_common(p, q, k, v, B, H, Lq, Lk, Bkv, scale, bias, kmask, kv_index, dropout_p, dropout_seed)
+    p.out, p.o_stride, p.lse = out.data_ptr(), out.stride(0), lse.data_ptr()
+    check(lib().xfm_attention_fwd(C.byref(p), stream_ptr()), "xfm_attention_fwd")
+    return out, lse
+
+
+def attention_bwd(dout, q, k, v, out, lse, B, H, Lq, Lk, scale, dq, dk, dv, *, Bkv=None, bias=None, kmask=None,
+                  kv_index=None, kv_offsets=None, kv_samples=None, dropout_p=0.0, dropout_seed=0, ds_dump=None):
+    """Writes bf16 dq [B*Lq, ...], dk / dv [Bkv*Lk, ...] (views with row strides).  ds_dump: bf16 [B,H,Lq,ld]."""
+    Bkv = B if Bkv is None else Bkv
+    p = AttnParams()
+    _attn_common(p, q, k, v, B, H, Lq, Lk, Bkv, scale, bias, kmask, kv_index, dropout_p, dropout_seed)
+    delta = torch.empty((B, H, Lq), dtype=torch.float32, device=q.device)
+    assert dout.dtype == torch.bfloat16 and dout.stride(1) == 1 and out.stride(1) == 1
+    p.out, p.o_stride, p.lse = out.data_ptr(), out.stride(0), lse.data_ptr()
+    p.dout, p.do_stride, p.delta = dout.data_ptr(), dout.stride(0), delta.data_ptr()
+    for t in (dq, dk, dv):
+        assert t.dtype == torch.bfloat16 and t.stride(1) == 1
+    p.dq, p.dk, p.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
+    p.dq_stride, p.dk_stride, p.dv_stride = dq.stride(0), dk.stride(0), dv.stride(0)
+    if ds_dump is not None:
+        assert ds_dump.dtype == torch.bfloat16 and ds_dump.is_contiguous() and ds_dump.shape[:3] == (B, H, Lq)
+        p.ds_dump, p.ds_ld = ds_dump.data_ptr(), ds_dump.shape[3]
+    if kv_samples is not None:
+        assert kv_offsets.dtype == torch.int32 and kv_samples.dtype == torch.int32
+        p.kv_offsets, p.kv_samples = kv_offsets.data_ptr(), kv_samples.data_ptr()
+    check(lib().xfm_attention_bwd(C.byref(p), stream_ptr()), "xfm_attention_bwd")
+
+
+# ------------------------------------------------------------------------------------------------------
+# thin wrappers over the remaining entry points
+# ------------------------------------------------------------------------------------------------------
+def _p(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _dt(t):
+    return _DT[t.dtype]
+
+
+def layernorm_fwd(x, w, b, eps, out_dtype=torch.bfloat16, want_f32_copy=False, want_stats=True):
+    M, D = x.shape
+    assert x.is_contiguous()
+    y = torch.empty((M, D), dtype=out_dtype, device=x.device)
+    y2 = torch.empty((M, D), dtype=torch.float32, device=x.device) if want_f32_copy else None
+    stats = torch.empty((M, 2), dtype=torch.float32, device=x.device) if want_stats else None
+    check(lib().xfm_layernorm_fwd(_p(x), _dt(x), _p(w), _p(b), _p(y), _dt(y), _p(y2), _p(stats), M, D, C.c_float(eps),
+                                  stream_ptr()), "xfm_layernorm_fwd")
+    return y, stats, y2
+
+
+def layernorm_bwd(dy, x, stats, w, dw, db, add_in=None, out_dtype=torch.float32):
+    M, D = x.shape
+    assert dy.is_contiguous() and x.is_contiguous() and dy.shape == x.shape
+    dx = torch.empty((M, D), dtype=out_dtype, device=x.device)
+    check(lib().xfm_layernorm_bwd(_p(dy), _dt(dy), _p(x), _dt(x), _p(stats), _p(w), _p(add_in),
+                                  0 if add_in is None else _dt(add_in), _p(dx), _dt(dx), _p(dw), _p(db), M, D,
+                                  stream_ptr()), "xfm_layernorm_bwd")
+    return dx
+
+
+def layerscale_bwd(dx_out, z, gamma, dgamma, dbias, row_group_scale=None, rows_per_group=1):
+    M, D = dx_out.shape
+    assert dx_out.dtype == torch.float32 and z.dtype == torch.bfloat16 and dx_out.is_contiguous() and z.is_contiguous()
+    dz = torch.empty((M, D), dtype=torch.bfloat16, device=z.device)
+    check(lib().xfm_layerscale_bwd(_p(dx_out), _p(z), _p(gamma), _p(row_group_scale), rows_per_group, _p(dz), _p(dgamma),
+                                   _p(dbias), M, D, stream_ptr()), "xfm_layerscale_bwd")
+    return dz
+
+
+def colsum_into(x, out):
+    """out[c] += sum_rows x[:, c]; x bf16 2-D (row stride allowed)."""
+    assert x.dtype == torch.bfloat16 and x.stride(1) == 1 and out.dtype == torch.float32
+    check(lib().xfm_colsum_bf16(_p(x), C.c_int64(x.stride(0)), _p(out), x.shape[0], x.shape[1], stream_ptr()),
+          "xfm_colsum_bf16")
+
+
+def cast_to_bf16(src, dst):
+    assert src.dtype == torch.float32 and dst.dtype == torch.bfloat16 and src.numel() == dst.numel()
+    assert src.is_contiguous() and dst.is_contiguous()
+    check(lib().xfm_cast_f32_to_bf16(_p(src), _p(dst), C.c_size_t(src.numel()), stream_ptr()), "xfm_cast_f32_to_bf16")
+
+
+def cast_to_f32(src, dst):
+    assert src.dtype == torch.bfloat16 and dst.dtype == torch.float32 and src.numel() == dst.numel()
+    check(lib().xfm_cast_bf16_to_f32(_p(src), _p(dst), C.c_size_t(src.numel()), stream_ptr()), "xfm_cast_bf16_to_f32")
+
+
+def scale_by_scalar_(t, scalar):
+    assert t.is_contiguous() and scalar.dtype == torch.float32
+    check(lib().xfm_scale_by_scalar(_p(t), _dt(t), _p(scalar), C.c_size_t(t.numel()), stream_ptr()), "xfm_scale_by_scalar")
+
+
+def roberta_embed_fwd(ids, word, pos, type_emb, ln_w, ln_b, pad_id, eps, want_pre=True):
+    B, L = ids.shape
+    D = word.shape[1]
+    assert ids.dtype == torch.int64 and ids.is_contiguous()
+    y = torch.empty((B * L, D), dtype=torch.bfloat16, device=ids.device)
+    pre = torch.empty((B * L, D), dtype=torch.float32, device=ids.device) if want_pre else None
+    stats = torch.empty((B * L, 2), dtype=torch.float32, device=ids.device)
+    pos_ids = torch.empty((B, L), dtype=torch.int32, device=ids.device)
+    check(lib().xfm_roberta_embed_fwd(_p(ids), _p(word), _p(pos), _p(type_emb), _p(ln_w), _p(ln_b), _p(y), _p(pre),
+                                      _p(stats), _p(pos_ids), B, L, D, pad_id, C.c_float(eps), stream_ptr()),
+          "xfm_roberta_embed_fwd")
+    return y, pre, stats, pos_ids
+
+
+def roberta_embed_bwd(dpre, ids, pos_ids, dword, dpos, dtype0, pad_id):
+    rows, D = dpre.shape
+    check(lib().xfm_roberta_embed_bwd(_p(dpre), _p(ids), _p(pos_ids), _p(dword), _p(dpos), _p(dtype0), rows, D, pad_id,
+                                      stream_ptr()), "xfm_roberta_embed_bwd")
+
+
+def im2col(image, P, pre_mul=0.0):
+    B, Cc, H, W = image.shape
+    assert image.dtype == torch.float32 and image.is_contiguous()
+    out = torch.empty((B * (H // P) * (W // P), Cc * P * P), dtype=torch.bfloat16, device=image.device)
+    check(lib().xfm_im2col(_p(image), _p(out), B, Cc, H, W, P, C.c_float(pre_mul), stream_ptr()), "xfm_im2col")
+    return out
+
+
+def assemble_tokens(patch, cls, mask_token, mask_u8, pos, B, npatch):
+    D = patch.shape[1]
+    x = torch.empty((B * (npatch + 1), D), dtype=torch.float32, device=patch.device)
+    check(lib().xfm_assemble_tokens(_p(patch), _p(cls), _p(mask_token), _p(mask_u8), _p(pos), _p(x), B, npatch, D,
+                                    stream_ptr()), "xfm_assemble_tokens")
+    return x
+
+
+def assemble_tokens_bwd(dx, mask_u8, dcls, dmask_token, B, npatch):
+    D = dx.shape[1]
+    dpatch = torch.empty((B * npatch, D), dtype=torch.bfloat16, device=dx.device)
+    check(lib().xfm_assemble_tokens_bwd(_p(dx), _p(mask_u8), _p(dpatch), _p(dcls), _p(dmask_token), B, npatch, D,
+                                        stream_ptr()), "xfm_assemble_tokens_bwd")
+    return dpatch
+
+
+def meanpool_fwd_(y_bf16, y_f32, B, npatch):
+    check(lib().xfm_meanpool_fwd(_p(y_bf16), _p(y_f32), B, npatch, y_f32.shape[-1], stream_ptr()), "xfm_meanpool_fwd")
+
+
+def meanpool_bwd(dout, B, npatch):
+    dy = torch.empty_like(dout)
+    check(lib().xfm_meanpool_bwd(_p(dout), _p(dy), B, npatch, dout.shape[-1], stream_ptr()), "xfm_meanpool_bwd")
+    return dy
+
+
+def gather_rows(src, index, out_dtype=None):
+    assert src.dim() == 2 and src.is_contiguous() and index.dtype == torch.int64
+    out = torch.empty((index.numel(), src.shape[1]), dtype=out_dtype or src.dtype, device=src.device)
+    check(lib().xfm_gather_rows(_p(src), _dt(src), _p(index), _p(out), _dt(out), index.numel(), src.shape[1],
+                                stream_ptr()), "xfm_gather_rows")
+    return out
+
+
+def scatter_add_rows_(dst, index, src):
+    assert dst.dtype == torch.float32 and dst.is_contiguous() and src.is_contiguous() and index.dtype == torch.int64
+    check(lib().xfm_scatter_add_rows(_p(src), _dt(src), _p(index), _p(dst), index.numel(), src.shape[1], stream_ptr()),
+          "xfm_scatter_add_rows")
+
+
+def relpos_bias_fwd(table, index, N, H, ld):
+    bias = torch.zeros((H, N, ld), dtype=torch.float32, device=table.device)
+    check(lib().xfm_relpos_bias_fwd(_p(table), _p(index), _p(bias), N, ld, H, stream_ptr()), "xfm_relpos_bias_fwd")
+    return bias
+
+
+def relpos_bias_bwd(dbias, index, dtable, N, H, ld):
+    check(lib().xfm_relpos_bias_bwd(_p(dbias), _p(index), _p(dtable), N, ld, H, stream_ptr()), "xfm_relpos_bias_bwd")
+
+
+def batch_sum_bf16(x):
+    """x bf16 [B, ...] -> f32 [...] summed over dim 0."""
+    B = x.shape[0]
+    per = x[0].numel()
+    out = torch.empty(x.shape[1:], dtype=torch.float32, device=x.device)
+    check(lib().xfm_batch_sum_bf16(_p(x), _p(out), B, C.c_size_t(per), stream_ptr()), "xfm_batch_sum_bf16")
+    return out
+
+
+def ce_fwd(logits, labels, V):
+    """logits f32 [R, ld>=V]; labels int64 [R] (-100 = ignore).  Returns (loss[1], count[1], lse[R])."""
+    R = logits.shape[0]
+    assert logits.dtype == torch.float32 and logits.stride(1) == 1 and labels.dtype == torch.int64
+    dev = logits.device
+    row_loss = torch.empty(R, dtype=torch.float32, device=dev)
+    lse = torch.empty(R, dtype=torch.float32, device=dev)
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    count = torch.empty(1, dtype=torch.float32, device=dev)
+    check(lib().xfm_ce_fwd(_p(logits), C.c_int64(logits.stride(0)), _p(labels), R, V, _p(row_loss), _p(lse), _p(loss),
+                           _p(count), stream_ptr()), "xfm_ce_fwd")
+    return loss, count, lse
+
+
+def ce_bwd(logits, labels, lse, count, upstream, V, ldd):
+    R = logits.shape[0]
+    d = torch.empty((R, ldd), dtype=torch.bfloat16, device=logits.device)
+    check(lib().xfm_ce_bwd(_p(logits), C.c_int64(logits.stride(0)), _p(labels), _p(lse), _p(count), _p(upstream), _p(d),
+                           C.c_int64(ldd), R, V, stream_ptr()), "xfm_ce_bwd")
+    return d
+
+
+def itc_loss_fused(image_all, text_all, temp, local_off, local_n, idx_all=None):
+    n, E = image_all.shape
+    dev = image_all.device
+    l = lib()
+    l.xfm_itc_workspace.restype = C.c_size_t
+    work = torch.empty(l.xfm_itc_workspace(n), dtype=torch.float32, device=dev)
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    dtemp = torch.empty(1, dtype=torch.float32, device=dev)
+    di = torch.empty((local_n, E), dtype=torch.float32, device=dev)
+    dt = torch.empty((local_n, E), dtype=torch.float32, device=dev)
+    assert image_all.is_contiguous() and text_all.is_contiguous() and image_all.dtype == torch.float32
+    check(l.xfm_itc_loss_fused(_p(image_all), _p(text_all), n, E, _p(idx_all), _p(temp), local_off, local_n, _p(work),
+                               _p(loss), _p(di), _p(dt), _p(dtemp), stream_ptr()), "xfm_itc_loss_fused")
+    return loss, di, dt, dtemp
+
+
+def hard_negatives(image_feat, text_feat, temp, seed, idx=None, want_weights=False):
+    B, E = image_feat.shape
+    dev = image_feat.device
+    w1 = torch.empty((B, B), dtype=torch.float32, device=dev) if want_weights else None
+    w2 = torch.empty((B, B), dtype=torch.float32, device=dev) if want_weights else None
+    tneg = torch.empty(B, dtype=torch.int64, device=dev)
+    ineg = torch.empty(B, dtype=torch.int64, device=dev)
+    check(lib().xfm_hard_negatives(_p(image_feat), _p(text_feat), B, E, _p(temp), _p(idx), C.c_uint64(seed), _p(w1),
+                                   _p(w2), _p(tneg), _p(ineg), stream_ptr()), "xfm_hard_negatives")
+    return ineg, tneg, w1, w2
+
+
+def vq_argmin(z, codebook):
+    R, Cd = z.shape
+    assert z.dtype == torch.float32 and z.is_contiguous() and codebook.is_contiguous()
+    ids = torch.empty(R, dtype=torch.int64, device=z.device)
+    check(lib().xfm_vq_argmin(_p(z), _p(codebook), _p(ids), R, codebook.shape[0], Cd, stream_ptr()), "xfm_vq_argmin")
+    return ids
+
+
+def gelu_fwd(x):
+    y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    check(lib().xfm_gelu_fwd(_p(x), _dt(x), _p(y), C.c_size_t(x.numel()), stream_ptr()), "xfm_gelu_fwd")
+    return y
+
+
+def gelu_bwd(dy, x):
+    dx = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    check(lib().xfm_gelu_bwd(_p(dy), _dt(dy), _p(x), _dt(x), _p(dx), C.c_size_t(x.numel()), stream_ptr()), "xfm_gelu_bwd")
+    return dx
+
+
+def dropout_apply(x, p, seed):
+    assert x.is_contiguous()
+    y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    check(lib().xfm_dropout_apply(_p(x), _dt(x), _p(y), C.c_size_t(x.numel()), C.c_float(p), C.c_uint64(seed),
+                                  stream_ptr()), "xfm_dropout_apply")
+    return y
