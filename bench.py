@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py — XFM-base pre-training step (ITC + ITM + MLM + MIM with VQ-KD targets) on synthetic 224 px / 40-token
+batches (BASELINE.json configs[1]), one process per GPU.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --steps K --warmup W      # the reference algorithm on the host CPU cores
+
+One "step" = forward (vision x2, text x2, fusion over 4B pairs, VQ-KD tokenizer, heads) + backward + gradient
+all-reduce + clip + AdamW on B pairs per GPU.  `value` is timed with the batches already resident in HBM; `e2e` repeats
+the same K steps with each step's inputs copied from pinned host memory and the loss read back to the host inside the
+timed region.  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# algorithmic FLOPs per image-text pair, fwd+bwd, measured on the reference with FlopCounterMode:
+# 406.94 GFLOP (ITC+ITM+MLM+MSE-MIM) + VQ-KD tokenizer fwd 35.47 + codebook 0.10 + lm_head 768->8192 on 75 rows 2.83
+GFLOP_PER_PAIR = 445.3
+METRIC = "image-text pairs/sec/step"
+UNIT = "pairs/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# synthetic workload
+# ----------------------------------------------------------------------------------------------------------------------
+def base_config():
+    return dict(image_res=224, patch_size=16, use_vision_tokenizer=True, codebook_size=8192, codebook_dim=32, embed_dim=256,
+                temp=0.07, num_masking_patches=75, min_num_patches=16, use_bbox=True)
+
+
+def gpu_init(device, seed):
+    """Random-init weights of the XFM-base architecture, generated on the device (O(1) activations through depth)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+
+    def init(name, shape):
+        leaf = name.rsplit(".", 1)[-1]
+        if name == "temp":
+            return torch.tensor(0.07)
+        if leaf in ("gamma_1", "gamma_2"):
+            return torch.full(shape, 0.1, device=device)
+        if ("norm" in name.lower() and leaf == "weight") or (name.endswith(".1.weight") and len(shape) == 1):
+            return torch.ones(shape, device=device)
+        if len(shape) <= 1 and leaf != "relative_position_bias_table":
+            return 0.02 * torch.randn(shape, device=device, generator=g)
+        if "quantize.embedding" in name:
+            return torch.nn.functional.normalize(torch.randn(shape, device=device, generator=g), dim=-1)
+        if "embeddings" in name or "pos_embed" in name or "patch_embed" in name or leaf == "relative_position_bias_table":
+            return 0.05 * torch.randn(shape, device=device, generator=g)
+        return (0.6 / shape[-1] ** 0.5) * torch.randn(shape, device=device, generator=g)
+    return init
+
+
+def make_host_batch(B, L, M, vocab, res, seed):
+    g = torch.Generator().manual_seed(seed)
+    image = torch.rand(B, 3, res, res, generator=g)
+    ids = torch.randint(3, vocab - 1, (B, L), generator=g)
+    ids[:, 0] = 0
+    atts = torch.ones(B, L, dtype=torch.long)
+    n_real = torch.randint(L // 2, L + 1, (B,), generator=g)
+    ar = torch.arange(L).view(1, L)
+    pad = ar >= n_real.view(B, 1)
+    atts[pad] = 0
+    ids[pad] = 1
+    masked_pos = torch.zeros(B, M, dtype=torch.long)
+    masked_ids = torch.full((B, M), -100, dtype=torch.long)
+    ids_masked = ids.clone()
+    for b in range(B):
+        k = min(M, max(1, (int(n_real[b]) - 1) // 2))
+        pos = torch.sort(torch.randperm(int(n_real[b]) - 1, generator=g)[:k] + 1).values
+        masked_pos[b, :k] = pos
+        masked_ids[b, :k] = ids[b, pos]
+        ids_masked[b, pos] = vocab - 1
+    out = dict(image=image, text_ids=ids, text_atts=atts, text_ids_masked=ids_masked, masked_pos=masked_pos, masked_ids=masked_ids)
+    return {k: v.pin_memory() for k, v in out.items()}
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from xfm_b200 import lib as L
+    from xfm_b200.accelerator import B200DDPAccelerator, FlatAdamW
+    from xfm_b200.model_pretrain import XFM
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, Lt, M = args.batch, 40, 15
+    import random
+    import numpy as np
+    random.seed(1234 + rank)
+    np.random.seed(1234 + rank)
+    torch.manual_seed(1234 + rank)
+    cfg = base_config()
+    model = XFM(cfg, init=gpu_init(dev, 0), device=dev).train()
+    opt = FlatAdamW(model, lr=1e-4, weight_decay=0.01, lr_mult=2.0)
+    acc = B200DDPAccelerator(dict(CLIP_GRAD_NORM=1.0, AUTO_CAST=False))
+    wrapped, opt, _ = acc.set_up(model, opt, None, local, world, rank)
+    n_pool = 4
+    host = [make_host_batch(B, Lt, M, model.cfg["vocab_size"], 224, 100 + 17 * rank + i) for i in range(n_pool)]
+    h2d = sum(v.numel() * v.element_size() for v in host[0].values())
+
+    def to_dev(hb):
+        return {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
+
+    def step(b):
+        out = wrapped(b["image"], b["text_ids"], b["text_atts"], text_ids_masked=b["text_ids_masked"], masked_pos=b["masked_pos"],
+                      masked_ids=b["masked_ids"], ret_mim_loss=True, data_source="image")
+        loss = out["loss_itc"] + out["loss_itm"] + out["loss_mlm"] + out["loss_mim"]
+        acc.backward_step(loss, opt)
+        acc.optimizer_step(opt, wrapped)
+        return loss.detach(), out
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    resident = [to_dev(hb) for hb in host]
+    for i in range(args.warmup):
+        loss, out = step(resident[i % n_pool])
+    barrier()
+    clocks = ClockSampler(local) if rank == 0 else None
+    if clocks:
+        clocks.start()
+
+    def timed(fn):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = L.launch_count()
+        e0.record()
+        for i in range(args.steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / args.steps, L.launch_count() - n0
+
+    last = {}
+
+    def resident_step(i):
+        last["loss"], last["out"] = step(resident[i % n_pool])
+
+    def e2e_step(i):
+        loss, _ = step(to_dev(host[i % n_pool]))
+        last["host_loss"] = float(loss)  # D2H read of the step's result
+
+    ms_step, launches = timed(resident_step)
+    ms_e2e, _ = timed(e2e_step)
+    clk = clocks.stop() if clocks else None
+
+    # ---- roofline leg: one more step with CUDA events around every launch of the dominant kernel (the tcgen05 GEMM)
+    L.gemm_profile = []
+    step(resident[0])
+    torch.cuda.synchronize()
+    prof, L.gemm_profile = L.gemm_profile, None
+    g_flops = sum(p[0] for p in prof)
+    g_ms = sum(p[1].elapsed_time(p[2]) for p in prof)
+    pk, pk_kind = peaks()
+    peak = pk.get("bf16_tflops_sustained", 1400.0)
+    ach = g_flops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
+    losses = {k: float(v) for k, v in last["out"].items() if k in ("loss_itc", "loss_itm", "loss_mlm", "loss_mim")}
+
+    pairs = B * world
+    line = {
+        "metric": METRIC, "value": pairs / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic (uniform images, random token ids; random-init XFM-base weights)",
+        "config": {"workload": "XFM-base pretraining step ITC+ITM+MLM+MIM(VQ-KD), 224px / 40 tokens / 15 masked, "
+                               "fwd+bwd+allreduce+clip+AdamW", "pairs_per_gpu": B, "global_pairs": pairs,
+                   "parallelism": f"dp{world}", "l2": "inputs and activations exceed L2 (>= 58 MB per activation tensor)",
+                   "train_mode": True},
+        "e2e": {"value": pairs / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4},
+        "gpu_launches": launches,
+        "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                     "traffic": None, "kernel": "gemm_tcgen05_kernel", "launches_per_step": len(prof),
+                     "gemm_ms_per_step": g_ms, "peak_source": f"{pk_kind} bf16_tflops_sustained",
+                     "step_tflops_algorithmic": GFLOP_PER_PAIR * B / ms_step,
+                     "step_frac_of_peak": GFLOP_PER_PAIR * B / ms_step / peak},
+        "clocks": clk, "losses_last_step": losses,
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline(args, quick=True)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm (oracle port, pinned to the reference's outputs by tests/test_oracle_golden.py)
+# ----------------------------------------------------------------------------------------------------------------------
+def _oracle_step_fn(B):
+    from oracle import xfm_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    cfg = O.base_config(use_vision_tokenizer=True)
+    sd = O.make_state_dict(cfg, seed=0)
+    train = [v.requires_grad_(True) for k, v in sd.items() if not k.startswith("vqkd.")]
+    optim = torch.optim.AdamW(train, lr=1e-4, betas=(0.9, 0.98), eps=1e-8, weight_decay=0.01)
+    batch = O.make_batch(cfg, B, L=40, M=15, seed=1, image_uniform=True)
+    import random
+    import numpy as np
+    random.seed(1234)
+    np.random.seed(1234)
+
+    def step():
+        ids_mask = O.sample_mim_masks(cfg, B)
+        ineg = torch.roll(torch.arange(B), 1)
+        tneg = torch.roll(torch.arange(B), -1)
+        out = O.pretrain_forward(sd, cfg, batch, ineg, tneg, ids_mask=ids_mask)
+        loss = out["loss_itc"] + out["loss_itm"] + out["loss_mlm"] + out["loss_mim"]
+        optim.zero_grad(set_to_none=True)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(train, 1.0)
+        optim.step()
+        return float(loss)
+    return step
+
+
+def cpu_baseline(args, quick):
+    B = 2
+    step = _oracle_step_fn(B)
+    step()
+    n = 2 if quick else args.steps
+    t0 = time.perf_counter()
+    for _ in range(n):
+        step()
+    dt = (time.perf_counter() - t0) / n
+    return {"value": B / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "s_per_step": dt,
+            "sample": f"{n} fwd+bwd+AdamW steps of the same workload at {B} pairs/step (oracle/xfm_oracle.py, fp32, eval-mode "
+                      f"dropout), after 1 warm-up step"}
+
+
+def run_reference(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    B = 2 if (args.steps + args.warmup) <= 24 else 1
+    step = _oracle_step_fn(B)
+    for _ in range(max(1, args.warmup)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    v = B / dt
+    sample = (f"each step = fwd+bwd+clip+AdamW of the same workload on {B} pairs (oracle port of the reference algorithm, fp32, "
+              f"{os.cpu_count()} host threads)")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "XFM-base pretraining step ITC+ITM+MLM+MIM(VQ-KD), 224px / 40 tokens / 15 masked, "
+                               "fwd+bwd+clip+AdamW", "pairs_per_step": B, "parallelism": "cpu"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("XFM_BENCH_PAIRS", "96")), help="pairs per GPU (yaml: 96)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -199,6 +199,40 @@ int xfm_hard_negatives(const float* image_feat, const float* text_feat, int B, i
  * ids [R] int64.  Bit-exact contract: exact fp32 arithmetic, first index on ties. */
 int xfm_vq_argmin(const float* z, const float* codebook, int64_t* ids, int R, int K, int C, void* stream);
 
+/* Exact-fp32 small GEMM with element strides: C[m,n] (+)= sum_k A[m*sam + k*sak] * B[n*sbn + k*sbk] (+ bias[n]).
+ * Used for the latency-bound [B,768]x[768,256] ITC projections (xfm.py:614-621, self.vision_proj / self.text_proj) and
+ * their backward, where bf16 operand rounding would be amplified by 1/temp in the contrastive logits. */
+int xfm_sgemm_f32(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbn, int64_t sbk, float* C, int64_t ldc,
+                  int M, int N, int K, const float* bias, int accumulate, void* stream);
+
+/* ITC feature normalisation (F.normalize, xfm.py:614-621): y = x / max(||x||_2, 1e-12), inv_norm[R] saved for the
+ * backward dx = (dy - y <y,dy>) * inv_norm. */
+int xfm_l2norm_fwd(const float* x, float* y, float* inv_norm, int R, int E, void* stream);
+int xfm_l2norm_bwd(const float* dy, const float* y, const float* inv_norm, float* dx, int R, int E, void* stream);
+
+/* K14 — MIM loss, MSE variant (xfm.py:631-635): x, t f32 [B, np+1, D]; mask u8 [B, np].  Writes *loss, *count (number
+ * of masked patches) and dx = dloss/dx for an upstream gradient of 1 (zero outside the selected rows). */
+int xfm_mim_mse(const float* x, const float* t, const uint8_t* mask, int B, int np, int D, int with_cls, float* count,
+                float* loss, float* dx, void* stream);
+
+/* Flat-buffer optimizer step (accelerators/ddp_accelerator.py:89-98 clip_grad_norm_ + optimizer.step with the
+ * transformers AdamW of optim.py:4-50).  P/G/M/V: f32 buffers of nchunks*64 elements, S: bf16 shadow (may be null);
+ * chunk_group[nchunks]: hyper-parameter group 0..3 of each 64-element chunk, 255 = skip (frozen or no gradient).
+ * xfm_grad_sumsq: *out = sum of g^2 over non-skipped chunks.  xfm_adamw_flat: if sumsq != null the gradient is
+ * scaled by grad_mul and clipped to max_grad_norm (total norm written to *norm_out when non-null). */
+typedef struct xfm_adamw_params {
+  float lr[4];
+  float weight_decay[4];
+  float beta1, beta2, eps;
+  float max_grad_norm; /* <= 0: no clipping */
+  float grad_mul;      /* gradient pre-scale (1/world_size for DDP averaging) */
+  int32_t step;        /* 1-based */
+  int32_t correct_bias;
+} xfm_adamw_params;
+int xfm_grad_sumsq(const float* g, const uint8_t* chunk_group, size_t nchunks, float* out, void* stream);
+int xfm_adamw_flat(float* P, const float* G, float* M, float* V, void* S_bf16, const uint8_t* chunk_group, size_t nchunks,
+                   const float* sumsq, float* norm_out, const xfm_adamw_params* hp, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

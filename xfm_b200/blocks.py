@@ -40,34 +40,35 @@ def vit_block_fwd(x, w, B, N, H, eps, relbias=None, drop_scale=None, save=True):
     qkv = L.gemm(xn1, w["qkv_w16"], bias=w["qkv_b"])
     attn, lse = L.attention_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], B, H, N, N, 0.125, bias=relbias)
     gamma1, gamma2 = w.get("g1"), w.get("g2")
+    ds1, ds2 = drop_scale if isinstance(drop_scale, tuple) else (drop_scale, drop_scale)  # one DropPath draw per branch
     z1 = torch.empty_like(attn) if (save and gamma1 is not None) else None
-    x1 = L.gemm(attn, w["proj_w16"], bias=w["proj_b"], col_scale=gamma1, row_group_scale=drop_scale, rows_per_group=N,
+    x1 = L.gemm(attn, w["proj_w16"], bias=w["proj_b"], col_scale=gamma1, row_group_scale=ds1, rows_per_group=N,
                 residual=x, aux_out=z1, out_dtype=torch.float32)
     xn2, st2, _ = L.layernorm_fwd(x1, w["n2w"], w["n2b"], eps, want_stats=save)
     Fh = w["fc1_w16"].shape[0]
     h1 = torch.empty((x.shape[0], Fh), dtype=torch.bfloat16, device=x.device) if save else None
     a1 = L.gemm(xn2, w["fc1_w16"], bias=w["fc1_b"], act=1, aux_out=h1)
     z2 = torch.empty_like(attn) if (save and gamma2 is not None) else None
-    x2 = L.gemm(a1, w["fc2_w16"], bias=w["fc2_b"], col_scale=gamma2, row_group_scale=drop_scale, rows_per_group=N,
+    x2 = L.gemm(a1, w["fc2_w16"], bias=w["fc2_b"], col_scale=gamma2, row_group_scale=ds2, rows_per_group=N,
                 residual=x1, aux_out=z2, out_dtype=torch.float32)
     if save:
         s.x, s.st1, s.xn1, s.qkv, s.attn, s.lse, s.z1 = x, st1, xn1, qkv, attn, lse, z1
         s.x1, s.st2, s.xn2, s.h1, s.a1, s.z2 = x1, st2, xn2, h1, a1, z2
-        s.relbias, s.drop_scale = relbias, drop_scale
+        s.relbias, s.ds1, s.ds2 = relbias, ds1, ds2
     return x2, s
 
 
 def vit_block_bwd(dx2, s, w, g, B, N, H, rel_index=None):
     """dx2: fp32 [B*N, D] gradient of the block output.  g: callable name -> fp32 grad view.  Returns dx (fp32)."""
     D = dx2.shape[1]
-    dz2 = L.layerscale_bwd(dx2, s.z2, w["g2"], g("g2"), g("fc2_b"), s.drop_scale, N)
+    dz2 = L.layerscale_bwd(dx2, s.z2, w["g2"], g("g2"), g("fc2_b"), s.ds2, N)
     wgrad(g("fc2_w"), dz2, s.a1)
     dh1 = L.gemm(dz2, w["fc2_w16"], b_t=True, act=2, aux_in=s.h1)
     L.colsum_into(dh1, g("fc1_b"))
     wgrad(g("fc1_w"), dh1, s.xn2)
     dxn2 = L.gemm(dh1, w["fc1_w16"], b_t=True)
     dx1 = L.layernorm_bwd(dxn2, s.x1, s.st2, w["n2w"], g("n2w"), g("n2b"), add_in=dx2)
-    dz1 = L.layerscale_bwd(dx1, s.z1, w["g1"], g("g1"), g("proj_b"), s.drop_scale, N)
+    dz1 = L.layerscale_bwd(dx1, s.z1, w["g1"], g("g1"), g("proj_b"), s.ds1, N)
     wgrad(g("proj_w"), dz1, s.attn)
     dattn = L.gemm(dz1, w["proj_w16"], b_t=True)
     dqkv = torch.empty_like(s.qkv)
@@ -107,20 +108,23 @@ NO_DROP = DropCfg()
 
 
 def _attn_out_fwd(ctx, w, pre, resid, eps, drop, s, tag):
-    """RobertaSelfOutput (xroberta.py:300-304): LayerNorm(dropout(dense(ctx)) + resid)."""
+    """RobertaSelfOutput (xroberta.py:300-304): LayerNorm(dropout(dense(ctx)) + resid).  Returns (bf16, f32) copies of the
+    LayerNorm output: the bf16 one feeds the next GEMM, the f32 one is the next residual."""
     seed = drop.next_seed() if drop.p_hidden > 0 else 0
     pre_ln = L.gemm(ctx, w[pre + "o_w16"], bias=w[pre + "o_b"], dropout_p=drop.p_hidden, dropout_seed=seed, residual=resid,
                     out_dtype=torch.float32)
-    h, st, _ = L.layernorm_fwd(pre_ln, w[pre + "ln_w"], w[pre + "ln_b"], eps, want_stats=s is not None)
+    h, st, h32 = L.layernorm_fwd(pre_ln, w[pre + "ln_w"], w[pre + "ln_b"], eps, want_f32_copy=True, want_stats=s is not None)
     if s is not None:
         setattr(s, tag + "_pre_ln", pre_ln)
         setattr(s, tag + "_st", st)
         setattr(s, tag + "_seed", seed)
-    return h
+    return h, h32
 
 
-def roberta_layer_fwd(h, w, Bt, Lt, H, eps, kmask, enc=None, Benc=0, Lenc=0, kv_index=None, drop=NO_DROP, save=True):
-    """h: bf16 [Bt*Lt, D].  enc: bf16 [Benc*Lenc, Denc] image tokens (cross-attention) or None."""
+def roberta_layer_fwd(h, w, Bt, Lt, H, eps, kmask, enc=None, Benc=0, Lenc=0, kv_index=None, drop=NO_DROP, save=True,
+                      h32=None):
+    """h: bf16 [Bt*Lt, D] (h32: the same hidden state in f32, used as the residual when given).
+    enc: bf16 [Benc*Lenc, Denc] image tokens (cross-attention) or None.  Returns (h_out bf16, h_out f32, saved)."""
     D = h.shape[1]
     s = Saved() if save else None
     scale = 1.0 / math.sqrt(64)
@@ -128,37 +132,45 @@ def roberta_layer_fwd(h, w, Bt, Lt, H, eps, kmask, enc=None, Benc=0, Lenc=0, kv_
     seed_a = drop.next_seed() if drop.p_attn > 0 else 0
     ctx, lse = L.attention_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], Bt, H, Lt, Lt, scale, kmask=kmask,
                                dropout_p=drop.p_attn, dropout_seed=seed_a)
-    h1 = _attn_out_fwd(ctx, w, "a_", h, eps, drop, s, "a")
+    h1, h1_32 = _attn_out_fwd(ctx, w, "a_", h if h32 is None else h32, eps, drop, s, "a")
     if save:
         s.h, s.qkv, s.ctx, s.lse, s.seed_a, s.h1 = h, qkv, ctx, lse, seed_a, h1
         s.p_hidden, s.p_attn = drop.p_hidden, drop.p_attn
-    h2 = h1
+    h2, h2_32 = h1, h1_32
     if enc is not None:
         qc = L.gemm(h1, w["c_q_w16"], bias=w["c_q_b"])
         kvc = L.gemm(enc, w["c_kv_w16"], bias=w["c_kv_b"])
         seed_c = drop.next_seed() if drop.p_attn > 0 else 0
         cctx, clse = L.attention_fwd(qc, kvc[:, :D], kvc[:, D:], Bt, H, Lt, Lenc, scale, Bkv=Benc, kv_index=kv_index,
                                      dropout_p=drop.p_attn, dropout_seed=seed_c)
-        h2 = _attn_out_fwd(cctx, w, "c_", h1, eps, drop, s, "c")
+        h2, h2_32 = _attn_out_fwd(cctx, w, "c_", h1_32, eps, drop, s, "c")
         if save:
             s.qc, s.kvc, s.cctx, s.clse, s.seed_c, s.h2, s.enc = qc, kvc, cctx, clse, seed_c, h2, enc
     Fh = w["i_w16"].shape[0]
     pre = torch.empty((h.shape[0], Fh), dtype=torch.bfloat16, device=h.device) if save else None
     act = L.gemm(h2, w["i_w16"], bias=w["i_b"], act=1, aux_out=pre)
     seed_f = drop.next_seed() if drop.p_hidden > 0 else 0
-    pre_ln = L.gemm(act, w["f_w16"], bias=w["f_b"], dropout_p=drop.p_hidden, dropout_seed=seed_f, residual=h2,
+    pre_ln = L.gemm(act, w["f_w16"], bias=w["f_b"], dropout_p=drop.p_hidden, dropout_seed=seed_f, residual=h2_32,
                     out_dtype=torch.float32)
-    h3, st3, _ = L.layernorm_fwd(pre_ln, w["f_ln_w"], w["f_ln_b"], eps, want_stats=save)
+    h3, st3, h3_32 = L.layernorm_fwd(pre_ln, w["f_ln_w"], w["f_ln_b"], eps, want_f32_copy=True, want_stats=save)
     if save:
         s.pre, s.act, s.f_pre_ln, s.f_st, s.f_seed, s.has_cross = pre, act, pre_ln, st3, seed_f, enc is not None
-    return h3, s
+    return h3, h3_32, s
+
+
+def _bf16_copy(x32):
+    x16 = torch.empty(x32.shape, dtype=torch.bfloat16, device=x32.device)
+    L.cast_to_bf16(x32, x16)
+    return x16
 
 
 def _attn_out_bwd(dh, s, w, g, pre, tag, ctx):
-    """Backward of LayerNorm(dropout(dense(ctx)) + resid).  Returns (d_pre_ln bf16 = grad wrt resid, d_ctx bf16)."""
+    """Backward of LayerNorm(dropout(dense(ctx)) + resid).  Returns (d_pre_ln f32 = grad wrt resid, d_ctx bf16).
+    The residual-stream gradient stays fp32 between layers: LayerNorm backward cancels the large mean / x-hat components
+    of dy, so bf16 rounding of dy would dominate the small components that survive."""
     d_pre = L.layernorm_bwd(dh, getattr(s, tag + "_pre_ln"), getattr(s, tag + "_st"), w[pre + "ln_w"], g(pre + "ln_w"),
-                            g(pre + "ln_b"), out_dtype=torch.bfloat16)
-    d_dense = d_pre if s.p_hidden == 0 else L.dropout_apply(d_pre, s.p_hidden, getattr(s, tag + "_seed"))
+                            g(pre + "ln_b"), out_dtype=torch.float32)
+    d_dense = _bf16_copy(d_pre) if s.p_hidden == 0 else L.dropout_apply(d_pre, s.p_hidden, getattr(s, tag + "_seed"))
     L.colsum_into(d_dense, g(pre + "o_b"))
     wgrad(g(pre + "o_w"), d_dense, ctx)
     d_ctx = L.gemm(d_dense, w[pre + "o_w16"], b_t=True)
@@ -167,19 +179,21 @@ def _attn_out_bwd(dh, s, w, g, pre, tag, ctx):
 
 def roberta_layer_bwd(dh3, s, w, g, Bt, Lt, H, kmask, Benc=0, Lenc=0, kv_index=None, kv_offsets=None, kv_samples=None,
                       d_enc=None, need_dh=True):
-    """dh3: bf16 or fp32 [Bt*Lt, D].  d_enc: fp32 [Benc*Lenc, Denc] accumulator for the image-token gradient."""
+    """dh3: bf16 or fp32 [Bt*Lt, D].  d_enc: fp32 [Benc*Lenc, Denc] accumulator for the image-token gradient.
+    Returns the fp32 gradient wrt the layer input (or None)."""
     D = s.h.shape[1]
     scale = 1.0 / math.sqrt(64)
+    f32 = torch.float32
     # ---- FFN
-    d_pre_ln = L.layernorm_bwd(dh3, s.f_pre_ln, s.f_st, w["f_ln_w"], g("f_ln_w"), g("f_ln_b"), out_dtype=torch.bfloat16)
-    d_dense = d_pre_ln if s.p_hidden == 0 else L.dropout_apply(d_pre_ln, s.p_hidden, s.f_seed)
+    d_pre_ln = L.layernorm_bwd(dh3, s.f_pre_ln, s.f_st, w["f_ln_w"], g("f_ln_w"), g("f_ln_b"), out_dtype=f32)
+    d_dense = _bf16_copy(d_pre_ln) if s.p_hidden == 0 else L.dropout_apply(d_pre_ln, s.p_hidden, s.f_seed)
     L.colsum_into(d_dense, g("f_b"))
     wgrad(g("f_w"), d_dense, s.act)
     d_i = L.gemm(d_dense, w["f_w16"], b_t=True, act=2, aux_in=s.pre)
     L.colsum_into(d_i, g("i_b"))
     h2 = s.h2 if s.has_cross else s.h1
     wgrad(g("i_w"), d_i, h2)
-    dh2 = L.gemm(d_i, w["i_w16"], b_t=True, residual=d_pre_ln)
+    dh2 = L.gemm(d_i, w["i_w16"], b_t=True, residual=d_pre_ln, out_dtype=f32)
     # ---- cross-attention
     dh1 = dh2
     if s.has_cross:
@@ -191,7 +205,7 @@ def roberta_layer_bwd(dh3, s, w, g, Bt, Lt, H, kmask, Benc=0, Lenc=0, kv_index=N
                         dropout_p=s.p_attn, dropout_seed=s.seed_c)
         L.colsum_into(dqc, g("c_q_b"))
         wgrad(g("c_q_w"), dqc, s.h1)
-        dh1 = L.gemm(dqc, w["c_q_w16"], b_t=True, residual=d_res)
+        dh1 = L.gemm(dqc, w["c_q_w16"], b_t=True, residual=d_res, out_dtype=f32)
         L.colsum_into(dkvc, g("c_kv_b"))
         wgrad(g("c_kv_w"), dkvc, s.enc)
         if d_enc is not None:
@@ -205,4 +219,4 @@ def roberta_layer_bwd(dh3, s, w, g, Bt, Lt, H, kmask, Benc=0, Lenc=0, kv_index=N
     wgrad(g("qkv_w"), dqkv, s.h)
     if not need_dh:
         return None
-    return L.gemm(dqkv, w["qkv_w16"], b_t=True, residual=d_res)
+    return L.gemm(dqkv, w["qkv_w16"], b_t=True, residual=d_res, out_dtype=f32)

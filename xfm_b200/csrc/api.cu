@@ -144,5 +144,26 @@ int xfm_hard_negatives(const float* image_feat, const float* text_feat, int B, i
 int xfm_vq_argmin(const float* z, const float* codebook, int64_t* ids, int R, int K, int C, void* stream) {
   return vq_argmin(z, codebook, ids, R, K, C, ST);
 }
+int xfm_sgemm_f32(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbn, int64_t sbk, float* C, int64_t ldc,
+                  int M, int N, int K, const float* bias, int accumulate, void* stream) {
+  return sgemm_f32(A, sam, sak, B, sbn, sbk, C, ldc, M, N, K, bias, accumulate, ST);
+}
+int xfm_l2norm_fwd(const float* x, float* y, float* inv_norm, int R, int E, void* stream) {
+  return l2norm_fwd(x, y, inv_norm, R, E, ST);
+}
+int xfm_l2norm_bwd(const float* dy, const float* y, const float* inv_norm, float* dx, int R, int E, void* stream) {
+  return l2norm_bwd(dy, y, inv_norm, dx, R, E, ST);
+}
+int xfm_mim_mse(const float* x, const float* t, const uint8_t* mask, int B, int np, int D, int with_cls, float* count,
+                float* loss, float* dx, void* stream) {
+  return mim_mse(x, t, mask, B, np, D, with_cls, count, loss, dx, ST);
+}
+int xfm_grad_sumsq(const float* g, const uint8_t* chunk_group, size_t nchunks, float* out, void* stream) {
+  return grad_sumsq(g, chunk_group, nchunks, out, ST);
+}
+int xfm_adamw_flat(float* P, const float* G, float* M, float* V, void* S, const uint8_t* chunk_group, size_t nchunks,
+                   const float* sumsq, float* norm_out, const xfm_adamw_params* hp, void* stream) {
+  return adamw_flat(P, G, M, V, BF(S), chunk_group, nchunks, sumsq, norm_out, hp, ST);
+}
 
 }  // extern "C"

@@ -62,5 +62,14 @@ int itc_loss_fused(const float* image_all, const float* text_all, int n, int E, 
 int hard_negatives(const float* image_feat, const float* text_feat, int B, int E, const float* temp, const int64_t* idx,
                    uint64_t seed, float* w_i2t, float* w_t2i, int64_t* text_neg, int64_t* image_neg, cudaStream_t s);
 int vq_argmin(const float* z, const float* codebook, int64_t* ids, int R, int K, int C, cudaStream_t s);
+int sgemm_f32(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbn, int64_t sbk, float* C, int64_t ldc,
+              int M, int N, int K, const float* bias, int accumulate, cudaStream_t s);
+int l2norm_fwd(const float* x, float* y, float* inv_norm, int R, int E, cudaStream_t s);
+int l2norm_bwd(const float* dy, const float* y, const float* inv_norm, float* dx, int R, int E, cudaStream_t s);
+int mim_mse(const float* x, const float* t, const uint8_t* mask, int B, int np, int D, int with_cls, float* count,
+            float* loss, float* dx, cudaStream_t s);
+int grad_sumsq(const float* g, const uint8_t* chunk_group, size_t nchunks, float* out, cudaStream_t s);
+int adamw_flat(float* P, const float* G, float* M, float* V, bf16_t* S, const uint8_t* chunk_group, size_t nchunks,
+               const float* sumsq, float* norm_out, const xfm_adamw_params* hp, cudaStream_t s);
 
 }  // namespace xfm

@@ -111,7 +111,7 @@ ce_bwd_kernel(const float* __restrict__ logits, int64_t ld, const int64_t* __res
 __global__ void __launch_bounds__(256)
 sgemm_small_kernel(const float* __restrict__ A, int64_t sam, int64_t sak, const float* __restrict__ B, int64_t sbn,
                    int64_t sbk, float* __restrict__ C, int64_t ldc, int M, int N, int K, const float* __restrict__ alpha_ptr,
-                   float alpha_mul, int alpha_div) {
+                   float alpha_mul, int alpha_div, const float* __restrict__ bias, int accumulate) {
   __shared__ float sA[32][33], sB[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
@@ -138,16 +138,27 @@ sgemm_small_kernel(const float* __restrict__ A, int64_t sam, int64_t sak, const 
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
     const int m = m0 + ty + 8 * r, n = n0 + tx;
-    if (m < M && n < N) C[(int64_t)m * ldc + n] = acc[r] * alpha;
+    if (m < M && n < N) {
+      float v = acc[r] * alpha + (bias ? bias[n] : 0.f);
+      if (accumulate) v += C[(int64_t)m * ldc + n];
+      C[(int64_t)m * ldc + n] = v;
+    }
   }
 }
 
 static void sgemm_small(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbn, int64_t sbk, float* C,
                         int64_t ldc, int M, int N, int K, const float* alpha_ptr, float alpha_mul, int alpha_div,
-                        cudaStream_t s) {
+                        cudaStream_t s, const float* bias = nullptr, int accumulate = 0) {
   sgemm_small_kernel<<<dim3((N + 31) / 32, (M + 31) / 32), 256, 0, s>>>(A, sam, sak, B, sbn, sbk, C, ldc, M, N, K, alpha_ptr,
-                                                                       alpha_mul, alpha_div);
+                                                                       alpha_mul, alpha_div, bias, accumulate);
   count_launch();
+}
+// Exact-fp32 small GEMM for latency-bound heads (ITC projections, xfm.py:614-621): C (+)= A.B^T + bias.
+int sgemm_f32(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbn, int64_t sbk, float* C, int64_t ldc,
+              int M, int N, int K, const float* bias, int accumulate, cudaStream_t s) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  sgemm_small(A, sam, sak, B, sbn, sbk, C, ldc, M, N, K, nullptr, 1.f, 0, s, bias, accumulate);
+  return (int)cudaGetLastError();
 }
 
 // ======================================================================================== ITC (xfm.py:683-715)
@@ -406,6 +417,102 @@ int ce_bwd(const float* logits, int64_t ld, const int64_t* labels, const float* 
            bf16* dlogits, int64_t ldd, int R, int V, cudaStream_t s) {
   if (R <= 0) return 0;
   ce_bwd_kernel<<<R, CE_THREADS, 0, s>>>(logits, ld, labels, lse, count, upstream, dlogits, ldd, V);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+}  // namespace xfm
+
+// ======================================================================================== feature normalisation
+// F.normalize(x, dim=-1) of the ITC projections (xfm.py:614-621): y = x / max(||x||, 1e-12); one warp per row.
+namespace xfm {
+
+__global__ void __launch_bounds__(256)
+l2norm_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ inv_norm, int R, int E) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= R) return;
+  const float* xr = x + (size_t)row * E;
+  float s = 0.f;
+  for (int k = lane; k < E; k += 32) s = fmaf(xr[k], xr[k], s);
+  s = warp_sum(s);
+  const float inv = 1.0f / fmaxf(sqrtf(s), 1e-12f);
+  for (int k = lane; k < E; k += 32) y[(size_t)row * E + k] = xr[k] * inv;
+  if (lane == 0) inv_norm[row] = inv;
+}
+// dx = (dy - y * <y, dy>) * inv_norm
+__global__ void __launch_bounds__(256)
+l2norm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ inv_norm,
+                  float* __restrict__ dx, int R, int E) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= R) return;
+  const float* dr = dy + (size_t)row * E;
+  const float* yr = y + (size_t)row * E;
+  float s = 0.f;
+  for (int k = lane; k < E; k += 32) s = fmaf(yr[k], dr[k], s);
+  s = warp_sum(s);
+  const float inv = inv_norm[row];
+  for (int k = lane; k < E; k += 32) dx[(size_t)row * E + k] = (dr[k] - yr[k] * s) * inv;
+}
+
+int l2norm_fwd(const float* x, float* y, float* inv_norm, int R, int E, cudaStream_t s) {
+  if (R <= 0) return 0;
+  l2norm_fwd_kernel<<<(R + 7) / 8, 256, 0, s>>>(x, y, inv_norm, R, E);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+int l2norm_bwd(const float* dy, const float* y, const float* inv_norm, float* dx, int R, int E, cudaStream_t s) {
+  if (R <= 0) return 0;
+  l2norm_bwd_kernel<<<(R + 7) / 8, 256, 0, s>>>(dy, y, inv_norm, dx, R, E);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+// ======================================================================================== MIM (MSE variant)
+// xfm.py:631-635: loss = mse(x[:,1:][mask], t[:,1:][mask]) (+ mse(x[:,0], t[:,0]) unless mim_cls_only).
+// Forward and the gradient for an upstream of 1 in one pass over x / t (f32 [B, np+1, D]); rows outside the
+// selection get a zero gradient.  *count = number of masked patches (device-side, no host sync).
+__global__ void __launch_bounds__(256)
+mask_count_kernel(const uint8_t* __restrict__ mask, size_t n, float* __restrict__ count) {
+  __shared__ float sh[32];
+  float c = 0.f;
+  for (size_t i = threadIdx.x; i < n; i += 256) c += mask[i] ? 1.f : 0.f;
+  c = block_sum<256>(c, sh);
+  if (threadIdx.x == 0) *count = c;
+}
+__global__ void __launch_bounds__(256)
+mim_mse_kernel(const float* __restrict__ x, const float* __restrict__ t, const uint8_t* __restrict__ mask,
+               const float* __restrict__ count, int B, int np, int D, int with_cls, float* __restrict__ loss,
+               float* __restrict__ dx) {
+  __shared__ float sh[32];
+  const int row = blockIdx.x;
+  const int b = row / (np + 1), tok = row % (np + 1);
+  float w = 0.f;
+  if (tok == 0) w = with_cls ? 1.0f / ((float)B * (float)D) : 0.f;
+  else if (mask[(size_t)b * np + tok - 1]) w = 1.0f / (*count * (float)D);
+  float acc = 0.f;
+  for (int c = threadIdx.x * 4; c < D; c += 256 * 4) {
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (w != 0.f) {
+      const float4 a = *(const float4*)(x + (size_t)row * D + c);
+      const float4 r = *(const float4*)(t + (size_t)row * D + c);
+      const float d0 = a.x - r.x, d1 = a.y - r.y, d2 = a.z - r.z, d3 = a.w - r.w;
+      acc += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+      g = make_float4(2.f * w * d0, 2.f * w * d1, 2.f * w * d2, 2.f * w * d3);
+    }
+    *(float4*)(dx + (size_t)row * D + c) = g;
+  }
+  if (w != 0.f) {  // block-uniform
+    acc = block_sum<256>(acc, sh);
+    if (threadIdx.x == 0) atomicAdd(loss, acc * w);
+  }
+}
+int mim_mse(const float* x, const float* t, const uint8_t* mask, int B, int np, int D, int with_cls, float* count,
+            float* loss, float* dx, cudaStream_t s) {
+  if (D & 3) { set_error("mim_mse: D must be a multiple of 4"); return XFM_ERR_BAD_ARG; }
+  cudaMemsetAsync(loss, 0, sizeof(float), s);
+  mask_count_kernel<<<1, 256, 0, s>>>(mask, (size_t)B * np, count);
+  count_launch();
+  mim_mse_kernel<<<B * (np + 1), 256, 0, s>>>(x, t, mask, count, B, np, D, with_cls, loss, dx);
   count_launch();
   return (int)cudaGetLastError();
 }

@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libxfm_b200.so")
 
 _lib = None
 _inited_devices = set()
+gemm_profile = None  # set to a list to time every GEMM launch with CUDA events (bench.py)
 
 
 class GemmParams(C.Structure):
@@ -135,6 +136,13 @@ def gemm(a, b, *, a_t=False, b_t=False, out=None, out_dtype=torch.bfloat16, bias
         p.residual, p.ld_res, p.res_dtype = residual.data_ptr(), residual.stride(0), _DT[residual.dtype]
     p.dropout_p = dropout_p
     p.dropout_seed = dropout_seed
+    if gemm_profile is not None:  # bench.py roofline leg: CUDA events around every launch of the dominant kernel
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(lib().xfm_gemm_bf16(C.byref(p), stream_ptr()), "xfm_gemm_bf16")
+        e1.record()
+        gemm_profile.append((2.0 * M * N * K, e0, e1, (M, N, K, int(a_t), int(b_t))))
+        return out
     check(lib().xfm_gemm_bf16(C.byref(p), stream_ptr()), "xfm_gemm_bf16")
     return out
 
@@ -443,3 +451,66 @@ def dropout_apply(x, p, seed):
     check(lib().xfm_dropout_apply(_p(x), _dt(x), _p(y), C.c_size_t(x.numel()), C.c_float(p), C.c_uint64(seed),
                                   stream_ptr()), "xfm_dropout_apply")
     return y
+
+
+def l2norm_fwd(x):
+    R, E = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    y = torch.empty_like(x)
+    inv = torch.empty(R, dtype=torch.float32, device=x.device)
+    check(lib().xfm_l2norm_fwd(_p(x), _p(y), _p(inv), R, E, stream_ptr()), "xfm_l2norm_fwd")
+    return y, inv
+
+
+def l2norm_bwd(dy, y, inv):
+    R, E = y.shape
+    assert dy.dtype == torch.float32 and dy.is_contiguous()
+    dx = torch.empty_like(y)
+    check(lib().xfm_l2norm_bwd(_p(dy), _p(y), _p(inv), _p(dx), R, E, stream_ptr()), "xfm_l2norm_bwd")
+    return dx
+
+
+def mim_mse(x, t, mask_u8, with_cls=True):
+    """x, t: f32 [B, np+1, D]; mask u8 [B, np].  Returns (loss[1], dx) for an upstream gradient of 1."""
+    B, N, D = x.shape
+    assert x.dtype == torch.float32 and t.dtype == torch.float32 and x.is_contiguous() and t.is_contiguous()
+    assert mask_u8.dtype == torch.uint8 and mask_u8.is_contiguous() and mask_u8.shape == (B, N - 1)
+    loss = torch.empty(1, dtype=torch.float32, device=x.device)
+    count = torch.empty(1, dtype=torch.float32, device=x.device)
+    dx = torch.empty_like(x)
+    check(lib().xfm_mim_mse(_p(x), _p(t), _p(mask_u8), B, N - 1, D, int(with_cls), _p(count), _p(loss), _p(dx),
+                            stream_ptr()), "xfm_mim_mse")
+    return loss, dx
+
+
+class AdamWParams(C.Structure):
+    _fields_ = [("lr", C.c_float * 4), ("weight_decay", C.c_float * 4), ("beta1", C.c_float), ("beta2", C.c_float),
+                ("eps", C.c_float), ("max_grad_norm", C.c_float), ("grad_mul", C.c_float), ("step", C.c_int32),
+                ("correct_bias", C.c_int32)]
+
+
+def grad_sumsq(G, chunk_group, out):
+    n = G.numel() // 64
+    check(lib().xfm_grad_sumsq(_p(G), _p(chunk_group), C.c_size_t(n), _p(out), stream_ptr()), "xfm_grad_sumsq")
+
+
+def adamw_flat(P, G, M, V, S, chunk_group, hp, sumsq=None, norm_out=None):
+    n = P.numel() // 64
+    assert P.numel() % 64 == 0 and chunk_group.numel() == n and chunk_group.dtype == torch.uint8
+    check(lib().xfm_adamw_flat(_p(P), _p(G), _p(M), _p(V), _p(S), _p(chunk_group), C.c_size_t(n), _p(sumsq), _p(norm_out),
+                               C.byref(hp), stream_ptr()), "xfm_adamw_flat")
+
+
+def sgemm_f32(a, b, out=None, bias=None, accumulate=False):
+    """Exact fp32 C[M,N] (+)= A[M,K] . B[N,K]^T (+ bias); a / b may be arbitrary-stride 2-D views (pass .t() for a transpose)."""
+    assert a.dtype == torch.float32 and b.dtype == torch.float32 and a.dim() == 2 and b.dim() == 2
+    M, K = a.shape
+    N, Kb = b.shape
+    assert K == Kb
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    assert out.shape == (M, N) and out.stride(1) == 1 and out.dtype == torch.float32
+    check(lib().xfm_sgemm_f32(_p(a), C.c_int64(a.stride(0)), C.c_int64(a.stride(1)), _p(b), C.c_int64(b.stride(0)),
+                              C.c_int64(b.stride(1)), _p(out), C.c_int64(out.stride(0)), M, N, K, _p(bias), int(accumulate),
+                              stream_ptr()), "xfm_sgemm_f32")
+    return out

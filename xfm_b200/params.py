@@ -89,6 +89,14 @@ class FlatParams:
         self.touched.add(name)
         return self._view(self.G, name)
 
+    def grad_padded(self, name, n):
+        """1-D gradient view of `n` >= numel elements starting at the segment (the tail is alignment padding that
+        nothing reads): lets column-sum kernels that need a multiple-of-8 width write odd-sized bias gradients."""
+        s = self.segments[name]
+        assert n >= s.numel and n <= (s.numel + ALIGN - 1) // ALIGN * ALIGN, (name, n)
+        self.touched.add(name)
+        return self.G[s.offset:s.offset + n]
+
     def _span(self, buf, first, last, shape):
         a, b = self.segments[first], self.segments[last]
         n = 1
