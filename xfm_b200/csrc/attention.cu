@@ -69,14 +69,19 @@ XFM_DEVINL uint32_t pack_bf16(float lo, float hi) {
 }
 
 // Copy `total` rows x 64 bf16 (row stride `stride` elements) into a swizzled tile; rows >= valid are zero-filled.
+// Asynchronous (LDGSTS, 16 B per thread per op): every load of the tile is in flight at once instead of one
+// global round trip per loop iteration; the caller waits with cp_async_wait_all() + __syncthreads().
 XFM_DEVINL void load_tile(uint8_t* tile, const bf16* g, int64_t stride, int valid, int total) {
+  const uint32_t base = smem_u32(tile);
   for (int i = threadIdx.x; i < total * 8; i += blockDim.x) {
     const int r = i >> 3, ch = i & 7;
-    uint4 val = make_uint4(0u, 0u, 0u, 0u);
-    if (r < valid) val = *(const uint4*)(g + (int64_t)r * stride + ch * 8);
-    *(uint4*)(tile + r * ROW_BYTES + ((ch ^ (r & 7)) << 4)) = val;
+    const bool ok = r < valid;
+    const bf16* src = g + (int64_t)(ok ? r : 0) * stride + ch * 8;
+    const uint32_t dst = base + r * ROW_BYTES + ((ch ^ (r & 7)) << 4);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0) : "memory");
   }
 }
+XFM_DEVINL void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
 
 // A-operand fragments (16 rows x 64 cols) of a swizzled tile: f[kk][0..3], rows row0..row0+15.
 XFM_DEVINL void load_a_frags(uint32_t tile_addr, int row0, int lane, uint32_t (&f)[4][4]) {
@@ -149,6 +154,46 @@ XFM_DEVINL float logit(const AttnArgs& a, float raw, int b, int h, int row, int 
   return v;
 }
 
+// Additive term (relative-position bias + key mask) of the 16 x 64 score fragment this thread owns, fetched BEFORE the
+// score MMAs are issued so the global-load latency hides under them.  rows = query rows r0 / r1, keys kb + nt*8 + 2t (+1).
+// Requires an even bias_ld (the host checks), so the float2 never straddles a row.
+XFM_DEVINL void load_addend_rows(const AttnArgs& a, int b, int h, int r0, int r1, int kb, int t, float (&bb)[8][4]) {
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    const int key = kb + nt * 8 + 2 * t;
+    float2 v0 = make_float2(0.f, 0.f), v1 = make_float2(0.f, 0.f);
+    if (a.bias && key < a.bias_ld) {
+      if (r0 < a.Lq) v0 = __ldg((const float2*)(a.bias + ((int64_t)h * a.Lq + r0) * a.bias_ld + key));
+      if (r1 < a.Lq) v1 = __ldg((const float2*)(a.bias + ((int64_t)h * a.Lq + r1) * a.bias_ld + key));
+    }
+    if (a.kmask) {
+      const float m0 = key < a.Lk ? __ldg(a.kmask + (int64_t)b * a.Lk + key) : 0.f;
+      const float m1 = key + 1 < a.Lk ? __ldg(a.kmask + (int64_t)b * a.Lk + key + 1) : 0.f;
+      v0.x += m0; v0.y += m1; v1.x += m0; v1.y += m1;
+    }
+    bb[nt][0] = v0.x; bb[nt][1] = v0.y; bb[nt][2] = v1.x; bb[nt][3] = v1.y;
+  }
+}
+// Transposed ownership (dK/dV kernel): rows = keys key0 / key1, columns = queries qb + nt*8 + 2t (+1).
+XFM_DEVINL void load_addend_cols(const AttnArgs& a, int b, int h, int key0, int key1, int qb, int t, float (&bb)[8][4]) {
+  const float m0 = (a.kmask && key0 < a.Lk) ? __ldg(a.kmask + (int64_t)b * a.Lk + key0) : 0.f;
+  const float m1 = (a.kmask && key1 < a.Lk) ? __ldg(a.kmask + (int64_t)b * a.Lk + key1) : 0.f;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int key = (e < 2) ? key0 : key1;
+      const int qi = qb + nt * 8 + 2 * t + (e & 1);
+      float v = (e < 2) ? m0 : m1;
+      if (a.bias && qi < a.Lq && key < a.Lk) v += __ldg(a.bias + ((int64_t)h * a.Lq + qi) * a.bias_ld + key);
+      bb[nt][e] = v;
+    }
+  }
+}
+XFM_DEVINL float logit2(const AttnArgs& a, float raw, float addend, int key) {
+  return key < a.Lk ? raw * a.scale + addend : -INFINITY;
+}
+
 // ================================================================================================ forward
 __global__ void __launch_bounds__(AT_WARPS * 32)
 attn_fwd_kernel(const AttnArgs a) {
@@ -163,6 +208,7 @@ attn_fwd_kernel(const AttnArgs a) {
   load_tile(sQ, a.q + ((int64_t)b * a.Lq + q0) * a.q_stride + h * HD, a.q_stride, min(AT_TILE, a.Lq - q0), AT_TILE);
   load_tile(sK, a.k + (int64_t)kvb * a.Lk * a.k_stride + h * HD, a.k_stride, a.Lk, LkP);
   load_tile(sV, a.v + (int64_t)kvb * a.Lk * a.v_stride + h * HD, a.v_stride, a.Lk, LkP);
+  cp_async_wait_all();
   __syncthreads();
   if (q0 + warp * 16 >= a.Lq) return;  // warp-uniform; no later block-wide barrier
   const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV);
@@ -179,15 +225,17 @@ attn_fwd_kernel(const AttnArgs a) {
     float s[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+    float bb[8][4];
+    load_addend_rows(a, b, h, r0, r1, kb, t, bb);
     mma_rows_nt(s, qf, aK, kb, lane);
     float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       const int key = kb + nt * 8 + 2 * t;
-      s[nt][0] = logit(a, s[nt][0], b, h, r0, key);
-      s[nt][1] = logit(a, s[nt][1], b, h, r0, key + 1);
-      s[nt][2] = logit(a, s[nt][2], b, h, r1, key);
-      s[nt][3] = logit(a, s[nt][3], b, h, r1, key + 1);
+      s[nt][0] = logit2(a, s[nt][0], bb[nt][0], key);
+      s[nt][1] = logit2(a, s[nt][1], bb[nt][1], key + 1);
+      s[nt][2] = logit2(a, s[nt][2], bb[nt][2], key);
+      s[nt][3] = logit2(a, s[nt][3], bb[nt][3], key + 1);
       mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
       mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
     }
@@ -281,6 +329,7 @@ attn_bwd_dq_kernel(const AttnArgs a) {
   load_tile(sdO, a.dout + ((int64_t)b * a.Lq + q0) * a.do_stride + h * HD, a.do_stride, nq, AT_TILE);
   load_tile(sK, a.k + (int64_t)kvb * a.Lk * a.k_stride + h * HD, a.k_stride, a.Lk, LkP);
   load_tile(sV, a.v + (int64_t)kvb * a.Lk * a.v_stride + h * HD, a.v_stride, a.Lk, LkP);
+  cp_async_wait_all();
   __syncthreads();
   if (q0 + warp * 16 >= a.Lq) return;
   const uint32_t aQ = smem_u32(sQ), adO = smem_u32(sdO), aK = smem_u32(sK), aV = smem_u32(sV);
@@ -303,6 +352,8 @@ attn_bwd_dq_kernel(const AttnArgs a) {
       s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
       dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
     }
+    float bb[8][4];
+    load_addend_rows(a, b, h, r0, r1, kb, t, bb);
     mma_rows_nt(s, qf, aK, kb, lane);    // S  = Q K^T
     mma_rows_nt(dp, dof, aV, kb, lane);  // dP = dO V^T
 #pragma unroll
@@ -311,7 +362,7 @@ attn_bwd_dq_kernel(const AttnArgs a) {
       for (int e = 0; e < 4; ++e) {
         const int row = (e < 2) ? r0 : r1;
         const int key = kb + nt * 8 + 2 * t + (e & 1);
-        const float p = __expf(logit(a, s[nt][e], b, h, row, key) - ((e < 2) ? lse0 : lse1));  // 0 for key >= Lk
+        const float p = __expf(logit2(a, s[nt][e], bb[nt][e], key) - ((e < 2) ? lse0 : lse1));  // 0 for key >= Lk
         float dpe = dp[nt][e];
         if (a.dropout_p > 0.f) dpe = (key < a.Lk && drop_keep(a, b, h, row, key)) ? dpe * inv_keep : 0.f;
         const float ds = (row < a.Lq) ? p * (dpe - ((e < 2) ? dl0 : dl1)) : 0.f;
@@ -380,6 +431,7 @@ attn_bwd_dkv_kernel(const AttnArgs a) {
       sLse[i] = i < a.Lq ? a.lse[st + i] : 0.f;
       sDelta[i] = i < a.Lq ? a.delta[st + i] : 0.f;
     }
+    cp_async_wait_all();
     __syncthreads();
     if (!warp_active) continue;
     if (si == s_begin) {
@@ -393,6 +445,8 @@ attn_bwd_dkv_kernel(const AttnArgs a) {
         s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
         dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
       }
+      float bb[8][4];
+      load_addend_cols(a, b, h, key0, key1, qb, t, bb);
       mma_rows_nt(s, kf, aQ, qb, lane);    // S^T  = K Q^T
       mma_rows_nt(dp, vf, adO, qb, lane);  // dP^T = V dO^T
       float pd[8][4];
@@ -403,7 +457,7 @@ attn_bwd_dkv_kernel(const AttnArgs a) {
           const int key = (e < 2) ? key0 : key1;
           const int qi = qb + nt * 8 + 2 * t + (e & 1);
           float p = 0.f;
-          if (qi < a.Lq && key < a.Lk) p = __expf(logit(a, s[nt][e], b, h, qi, key) - sLse[qi]);
+          if (qi < a.Lq && key < a.Lk) p = __expf(s[nt][e] * a.scale + bb[nt][e] - sLse[qi]);
           float keep = 1.f;
           if (a.dropout_p > 0.f) keep = (qi < a.Lq && key < a.Lk && drop_keep(a, b, h, qi, key)) ? inv_keep : 0.f;
           pd[nt][e] = p * keep;
@@ -440,6 +494,10 @@ static int attn_check(const xfm_attn_params* p) {
   }
   if (p->head_dim != HD) {
     set_error("attention: head_dim must be 64 (got %d)", p->head_dim);
+    return XFM_ERR_BAD_ARG;
+  }
+  if (p->bias && (p->bias_ld & 1)) {
+    set_error("attention: bias_ld must be even");
     return XFM_ERR_BAD_ARG;
   }
   if ((p->q_stride | p->k_stride | p->v_stride) & 7) {
