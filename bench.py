@@ -15,7 +15,6 @@ timed region.  Prints ONE JSON line (rank 0).
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -42,34 +41,45 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region through NVML (the same counters the
+    `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` line of B200_PROFILING.md prints).  NVML calls release the
+    GIL and take microseconds; forking nvidia-smi from a thread stalled the launching thread for tens of ms per step."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.index, self.sm, self.bits, self.max_mhz, self._stop_evt = index, [], 0, None, threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
 
     def run(self):
+        if self.nv is None:
+            return
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                self.sm.append(int(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                self.bits |= int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
             except Exception:
-                pass
-            self._stop_evt.wait(0.2)
+                try:
+                    self.bits |= int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                except Exception:
+                    pass
+            self._stop_evt.wait(0.05)
 
     def stop(self):
         self._stop_evt.set()
-        self.join(timeout=6)
-        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
-        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.rows)}
+        self.join(timeout=2)
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": [n for bit, n in self.REASONS.items() if self.bits & bit], "samples": len(sm), "source": "nvml"}
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -211,6 +221,18 @@ def run_ours(args):
     step(resident[0])
     torch.cuda.synchronize()
     prof, L.gemm_profile = L.gemm_profile, None
+    shapes = {}
+    for p in prof:
+        d = shapes.setdefault(p[3], [0, 0.0, 0.0])
+        d[0] += 1
+        d[1] += p[1].elapsed_time(p[2])
+        d[2] += p[0]
+    if rank == 0 and os.path.isdir(os.path.join(ROOT, "gpurun_out")):
+        rows = [dict(M=k[0], N=k[1], K=k[2], a_t=k[3], b_t=k[4], count=v[0], ms=round(v[1], 4),
+                     tflops=round(v[2] / (v[1] * 1e-3) / 1e12, 1) if v[1] > 0 else 0.0) for k, v in shapes.items()]
+        rows.sort(key=lambda r: -r["ms"])
+        with open(os.path.join(ROOT, "gpurun_out", "gemm_shapes.json"), "w") as f:
+            json.dump(rows, f, indent=0)
     g_flops = sum(p[0] for p in prof)
     g_ms = sum(p[1].elapsed_time(p[2]) for p in prof)
     pk, pk_kind = peaks()

@@ -31,6 +31,7 @@ constexpr int LN_WARPS = 8;
 
 // -------------------------------------------------------------------------------- LayerNorm forward
 // y = (x - mean) * rstd * w + b.  Reference: torch layer_norm at beit2.py:201-205, xroberta.py:135,303,384,1328.
+template <int NV>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_fwd_kernel(const void* __restrict__ x, int x_dtype, const float* __restrict__ w, const float* __restrict__ b,
                      void* __restrict__ y, int y_dtype, float* __restrict__ y2_f32, float* __restrict__ stats, int M,
@@ -39,10 +40,10 @@ layernorm_fwd_kernel(const void* __restrict__ x, int x_dtype, const float* __res
   const int row = blockIdx.x * LN_WARPS + warp;
   if (row >= M) return;
   const size_t base = (size_t)row * D;
-  float4 v[LN_MAX_VEC];
+  float4 v[NV];
   float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAX_VEC; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int c = (i * 32 + lane) * 4;
     if (c < D) {
       v[i] = ld4(x, x_dtype, base + c);
@@ -52,7 +53,7 @@ layernorm_fwd_kernel(const void* __restrict__ x, int x_dtype, const float* __res
   const float mean = warp_sum(sum) / (float)D;
   float sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAX_VEC; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int c = (i * 32 + lane) * 4;
     if (c < D) {
       const float a = v[i].x - mean, bb = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
@@ -61,7 +62,7 @@ layernorm_fwd_kernel(const void* __restrict__ x, int x_dtype, const float* __res
   }
   const float rstd = rsqrtf(warp_sum(sq) / (float)D + eps);
 #pragma unroll
-  for (int i = 0; i < LN_MAX_VEC; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int c = (i * 32 + lane) * 4;
     if (c < D) {
       const float4 ww = *(const float4*)(w + c), bb = *(const float4*)(b + c);
@@ -84,25 +85,26 @@ layernorm_fwd_kernel(const void* __restrict__ x, int x_dtype, const float* __res
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * w;  dw += sum dy * xhat;  db += sum dy.
 // Optional add_in (residual-path gradient) is added to dx.  dw / db are accumulated with one fp32 atomic per
 // column per CTA (each CTA first reduces its rows in registers + shared memory).
-__global__ void __launch_bounds__(LN_WARPS * 32)
+template <int NV>
+__global__ void __launch_bounds__(LN_WARPS * 32, NV <= 6 ? 2 : 1)
 layernorm_bwd_kernel(const void* __restrict__ dy, int dy_dtype, const void* __restrict__ x, int x_dtype,
                      const float* __restrict__ stats, const float* __restrict__ w, const void* __restrict__ add_in,
                      int add_dtype, void* __restrict__ dx, int dx_dtype, float* __restrict__ dw, float* __restrict__ db,
                      int M, int D, int rows_per_cta) {
   extern __shared__ float red[];  // [2][LN_WARPS][D]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float4 aw[LN_MAX_VEC], ab[LN_MAX_VEC];
+  float4 aw[NV], ab[NV];
 #pragma unroll
-  for (int i = 0; i < LN_MAX_VEC; ++i) aw[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < NV; ++i) aw[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   const int row0 = blockIdx.x * rows_per_cta;
   const int row1 = min(M, row0 + rows_per_cta);
   for (int row = row0 + warp; row < row1; row += LN_WARPS) {
     const size_t base = (size_t)row * D;
     const float mean = stats[2 * row], rstd = stats[2 * row + 1];
-    float4 g[LN_MAX_VEC], xh[LN_MAX_VEC];
+    float4 g[NV], xh[NV];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_VEC; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int c = (i * 32 + lane) * 4;
       if (c < D) {
         const float4 d = ld4(dy, dy_dtype, base + c);
@@ -119,7 +121,7 @@ layernorm_bwd_kernel(const void* __restrict__ dy, int dy_dtype, const void* __re
     s1 = warp_sum(s1) / (float)D;
     s2 = warp_sum(s2) / (float)D;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_VEC; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int c = (i * 32 + lane) * 4;
       if (c < D) {
         float4 o;
@@ -139,7 +141,7 @@ layernorm_bwd_kernel(const void* __restrict__ dy, int dy_dtype, const void* __re
   float* rw = red;
   float* rb = red + LN_WARPS * D;
 #pragma unroll
-  for (int i = 0; i < LN_MAX_VEC; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int c = (i * 32 + lane) * 4;
     if (c < D) {
       *(float4*)(rw + warp * D + c) = aw[i];
@@ -163,22 +165,23 @@ layernorm_bwd_kernel(const void* __restrict__ dy, int dy_dtype, const void* __re
 // Forward (GEMM epilogue): x_out = x_in + rs[row/rpg] * gamma * z, z = acc + bias (saved as bf16).
 // Backward: dz = dx_out * gamma * rs (bf16 out), dgamma += sum_rows dx_out * rs * z, dbias += sum_rows dz.
 // Reference: beit2.py:204-205 (gamma_1 / gamma_2, DropPath).
+template <int NV>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 layerscale_bwd_kernel(const float* __restrict__ dxo, const bf16* __restrict__ z, const float* __restrict__ gamma,
                       const float* __restrict__ rs, int rpg, bf16* __restrict__ dz, float* __restrict__ dgamma,
                       float* __restrict__ dbias, int M, int D, int rows_per_cta) {
   extern __shared__ float red[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float4 ag[LN_MAX_VEC], ab[LN_MAX_VEC];
+  float4 ag[NV], ab[NV];
 #pragma unroll
-  for (int i = 0; i < LN_MAX_VEC; ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < NV; ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   const int row0 = blockIdx.x * rows_per_cta;
   const int row1 = min(M, row0 + rows_per_cta);
   for (int row = row0 + warp; row < row1; row += LN_WARPS) {
     const size_t base = (size_t)row * D;
     const float s = rs ? rs[row / rpg] : 1.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_VEC; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int c = (i * 32 + lane) * 4;
       if (c < D) {
         const float4 d = *(const float4*)(dxo + base + c);
@@ -195,7 +198,7 @@ layerscale_bwd_kernel(const float* __restrict__ dxo, const bf16* __restrict__ z,
   float* rg = red;
   float* rb = red + LN_WARPS * D;
 #pragma unroll
-  for (int i = 0; i < LN_MAX_VEC; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int c = (i * 32 + lane) * 4;
     if (c < D) {
       *(float4*)(rg + warp * D + c) = ag[i];
@@ -569,6 +572,19 @@ static int grid_1d(size_t n, int block) {
   const size_t cap = (size_t)num_sms() * 16;
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
+// Per-lane float4 slots actually needed for D features: kernels are instantiated per slot count so the register
+// arrays match D (a single 16-slot instantiation needed 255 registers and spilled in the backward kernel).
+#define LN_DISPATCH(D, ...)                          \
+  do {                                               \
+    const int nv_ = ((D) + 127) / 128;               \
+    if (nv_ <= 2) { constexpr int NV = 2; __VA_ARGS__; }        \
+    else if (nv_ <= 4) { constexpr int NV = 4; __VA_ARGS__; }   \
+    else if (nv_ <= 6) { constexpr int NV = 6; __VA_ARGS__; }   \
+    else if (nv_ <= 8) { constexpr int NV = 8; __VA_ARGS__; }   \
+    else if (nv_ <= 12) { constexpr int NV = 12; __VA_ARGS__; } \
+    else { constexpr int NV = 16; __VA_ARGS__; }                \
+  } while (0)
+
 #define LAUNCH_END()  \
   count_launch();     \
   return (int)cudaGetLastError();
@@ -577,13 +593,14 @@ int layernorm_fwd(const void* x, int x_dtype, const float* w, const float* b, vo
                   int M, int D, float eps, cudaStream_t s) {
   if (ln_check(D)) return XFM_ERR_BAD_ARG;
   if (M <= 0) return 0;
-  layernorm_fwd_kernel<<<(M + LN_WARPS - 1) / LN_WARPS, LN_WARPS * 32, 0, s>>>(x, x_dtype, w, b, y, y_dtype, y2, stats, M, D, eps);
+  LN_DISPATCH(D, (layernorm_fwd_kernel<NV><<<(M + LN_WARPS - 1) / LN_WARPS, LN_WARPS * 32, 0, s>>>(x, x_dtype, w, b, y, y_dtype, y2,
+                                                                                               stats, M, D, eps)));
   LAUNCH_END();
 }
 
 static int rows_per_cta_for(int M) {
-  // ~2 CTAs per SM; each CTA reduces its rows before touching the global dw/db atomics
-  int ctas = num_sms() * 2;
+  // ~3 CTAs per SM; each CTA reduces its rows before touching the global dw/db atomics
+  int ctas = num_sms() * 3;
   int r = (M + ctas - 1) / ctas;
   r = ((r + LN_WARPS - 1) / LN_WARPS) * LN_WARPS;
   return r < LN_WARPS ? LN_WARPS : r;
@@ -597,13 +614,15 @@ int layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, cons
   const int rpc = rows_per_cta_for(M);
   const int grid = (M + rpc - 1) / rpc;
   const size_t smem = dw ? (size_t)2 * LN_WARPS * D * sizeof(float) : 0;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(layernorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * LN_WARPS * 2048 * 4);
-    attr = true;
-  }
-  layernorm_bwd_kernel<<<grid, LN_WARPS * 32, smem, s>>>(dy, dy_dtype, x, x_dtype, stats, w, add_in, add_dtype, dx, dx_dtype, dw,
-                                                         db, M, D, rpc);
+  LN_DISPATCH(D, {
+    static bool attr = false;  // one per instantiation
+    if (!attr) {
+      cudaFuncSetAttribute(layernorm_bwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * LN_WARPS * NV * 128 * 4);
+      attr = true;
+    }
+    layernorm_bwd_kernel<NV><<<grid, LN_WARPS * 32, smem, s>>>(dy, dy_dtype, x, x_dtype, stats, w, add_in, add_dtype, dx, dx_dtype,
+                                                               dw, db, M, D, rpc);
+  });
   LAUNCH_END();
 }
 
@@ -613,13 +632,15 @@ int layerscale_bwd(const float* dxo, const bf16* z, const float* gamma, const fl
   if (M <= 0) return 0;
   const int rpc = rows_per_cta_for(M);
   const int grid = (M + rpc - 1) / rpc;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(layerscale_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * LN_WARPS * 2048 * 4);
-    attr = true;
-  }
-  layerscale_bwd_kernel<<<grid, LN_WARPS * 32, (size_t)2 * LN_WARPS * D * sizeof(float), s>>>(dxo, z, gamma, rs, rpg > 0 ? rpg : 1,
-                                                                                              dz, dgamma, dbias, M, D, rpc);
+  LN_DISPATCH(D, {
+    static bool attr = false;
+    if (!attr) {
+      cudaFuncSetAttribute(layerscale_bwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * LN_WARPS * NV * 128 * 4);
+      attr = true;
+    }
+    layerscale_bwd_kernel<NV><<<grid, LN_WARPS * 32, (size_t)2 * LN_WARPS * D * sizeof(float), s>>>(
+        dxo, z, gamma, rs, rpg > 0 ? rpg : 1, dz, dgamma, dbias, M, D, rpc);
+  });
   LAUNCH_END();
 }
 

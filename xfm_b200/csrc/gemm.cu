@@ -2,8 +2,8 @@
 //
 //   C[M,N] = epilogue(A[M,K] · B[N,K]^T), bf16 operands, fp32 accumulation in TMEM.
 //
-// CTA = 192 threads: warp 0 = TMA producer, warp 1 = TMEM owner + single-thread UMMA issuer,
-// warps 2..5 = epilogue (one TMEM lane quadrant each).  Operands are staged by TMA into a
+// CTA = 320 threads: warp 0 = TMA producer, warp 1 = TMEM owner + single-thread UMMA issuer,
+// warps 2..9 = epilogue (two per TMEM lane quadrant, each taking half of the tile's columns).  Operands are staged by TMA into a
 // multi-stage ring of SWIZZLE_128B tiles (128 x 64 for A, BLOCK_N x 64 for B); the accumulator
 // is double-buffered in TMEM (2 x BLOCK_N columns) so the epilogue of tile i overlaps the MMAs
 // of tile i+1.  Both operands may be K-major (torch Linear forward) or MN-major (the operand's
@@ -17,7 +17,7 @@ namespace xfm {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 64 + 8 * 32;  // TMA warp, MMA warp, 8 epilogue warps
 
 struct GemmArgs {
   int M, N, K;
@@ -33,7 +33,8 @@ struct GemmArgs {
   const void* residual;
   float dropout_p;
   uint64_t dropout_seed;
-  int vec_ok;  // all row pointers 16-byte aligned for 32-column chunks
+  int vec_ok;    // every epilogue pointer / leading dimension allows 2-element vector access at even columns
+  int epi_mode;  // see epilogue_block
 };
 
 template <int BLOCK_N>
@@ -43,144 +44,207 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
   static constexpr int TMEM_COLS = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int EPI_BYTES = 8 * 32 * 34 * 4;  // 8 epilogue warps x [32][EPI_LD] fp32 transposition blocks
+  // 227 KB (232448 B) is the per-CTA limit; the BLOCK_N = 256 configuration uses all of it (768 B of alignment slack:
+  // dynamic shared memory starts 1024-aligned when the kernel has no static shared memory, checked in the kernel).
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 768 + 256 /*barriers*/;
 };
 
-XFM_DEVINL void store_chunk(const GemmArgs& g, int row, int n, int ncols, float (&v)[32]) {
-  // v[0..ncols) are final values for C[row, n .. n+ncols)
-  if (g.c_dtype == 0) {
-    bf16* dst = (bf16*)g.C + (int64_t)row * g.ldc + n;
-    if (ncols == 32 && g.vec_ok) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        uint4 u;
-        __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]);
-        __nv_bfloat162 t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-        __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
-        __nv_bfloat162 t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-        u.x = *(uint32_t*)&t0; u.y = *(uint32_t*)&t1; u.z = *(uint32_t*)&t2; u.w = *(uint32_t*)&t3;
-        *(uint4*)(dst + j) = u;
-      }
-    } else {
-      for (int j = 0; j < ncols; ++j) dst[j] = __float2bfloat16(v[j]);
-    }
+// ---------------------------------------------------------------------------------------------- epilogue
+// Each epilogue warp owns 32 accumulator rows (one TMEM lane quadrant).  tcgen05.ld hands thread t the row t, i.e. a
+// row-per-thread layout whose direct global stores touch 32 different rows per instruction (16 B each).  The tile is
+// therefore transposed through a per-warp shared-memory block of 32 rows x 64 columns (fp32, leading dimension 66 words:
+// 8-byte accesses are bank-conflict free in both directions) so that phase 2 runs with lane = column pair: every global
+// load / store / reduction of the fused epilogue (output, saved pre-activation, residual, dGELU input) is one fully
+// coalesced 128-byte (bf16) or 256-byte (fp32) row segment per warp instruction.
+constexpr int EPI_WARPS = 8;   // two per TMEM lane quadrant, each taking half of the tile's columns
+constexpr int EPI_COLS = 32;
+constexpr int EPI_LD = 34;     // words; 136 B rows: float2 accesses are 8-byte aligned and conflict free per half warp
+constexpr int EPI_WARP_FLOATS = 32 * EPI_LD;
+
+XFM_DEVINL float2 ld2_bf16(const bf16* p, bool vec, bool c1) {
+  if (vec) return __bfloat1622float2(*(const __nv_bfloat162*)p);
+  return make_float2(__bfloat162float(p[0]), c1 ? __bfloat162float(p[1]) : 0.f);
+}
+XFM_DEVINL void st2_bf16(bf16* p, float2 v, bool vec, bool c1) {
+  if (vec) {
+    *(__nv_bfloat162*)p = __floats2bfloat162_rn(v.x, v.y);
   } else {
-    float* dst = (float*)g.C + (int64_t)row * g.ldc + n;
-    if (g.accumulate) {
-      if (ncols == 32 && g.vec_ok) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(v[j]), "f"(v[j + 1]),
-                       "f"(v[j + 2]), "f"(v[j + 3])
-                       : "memory");
-        }
-      } else {
-        for (int j = 0; j < ncols; ++j) atomicAdd(dst + j, v[j]);
-      }
-    } else {
-      if (ncols == 32 && g.vec_ok) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) *(float4*)(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-      } else {
-        for (int j = 0; j < ncols; ++j) dst[j] = v[j];
-      }
-    }
+    p[0] = __float2bfloat16(v.x);
+    if (c1) p[1] = __float2bfloat16(v.y);
   }
 }
 
-XFM_DEVINL void load_bf16_chunk(const bf16* src, int ncols, bool vec, float (&o)[32]) {
-  if (ncols == 32 && vec) {
-#pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-      uint4 u = *(const uint4*)(src + j);
-      const __nv_bfloat162* h = (const __nv_bfloat162*)&u;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float2 f = __bfloat1622float2(h[q]);
-        o[j + 2 * q] = f.x;
-        o[j + 2 * q + 1] = f.y;
-      }
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) o[j] = (j < ncols) ? __bfloat162float(src[j]) : 0.f;
-  }
-}
-
-XFM_DEVINL void epilogue_chunk(const GemmArgs& g, int row, int n, uint32_t (&r)[32]) {
-  const int ncols = min(32, g.N - n);
-  float v[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+// Phase 2 for one 32 x 32 block: rows row_base .. +31, columns n .. n+31.  Lane l owns columns n + 2*(l%16), +1 of rows
+// (l/16), (l/16)+2, ...: one warp instruction moves two 32-column row segments (64 B bf16 / 128 B fp32 each).
+// The 16 row steps run as two batches of 8: all global loads of a batch (dGELU pre-activation, residual) are issued
+// first, then the arithmetic, then the stores, so 8 loads per lane are in flight and no load waits behind a store
+// that might alias it.
+// MODE 0: C = bf16(act(acc + bias)), act in {none, GELU}, optional saved pre-activation  (forward Linear layers)
+// MODE 1: C = bf16((acc + bias) * gelu'(aux_in))                                        (dgrad through GELU)
+// MODE 2: everything (tanh, LayerScale / DropPath scales, dropout, residual, fp32 output, split-K reduction)
+// FULL: the block lies inside the matrix and every pointer allows vector access, so all bounds predicates fold away.
+template <int MODE, bool FULL>
+XFM_DEVINL void epilogue_block(const GemmArgs& g, const float* stage, int row_base, int n, int lane) {
+  const int col = n + 2 * (lane & 15);
+  if (!FULL && col >= g.N) return;
+  const bool c1 = FULL ? true : (col + 1 < g.N);
+  const bool vec = FULL ? true : (g.vec_ok && c1);
+  float2 bias = make_float2(0.f, 0.f), cs = make_float2(1.f, 1.f);
   if (g.bias) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] += (j < ncols) ? __ldg(g.bias + n + j) : 0.f;
+    bias.x = __ldg(g.bias + col);
+    if (c1) bias.y = __ldg(g.bias + col + 1);
   }
-  if (g.aux_out) {
-    bf16* dst = g.aux_out + (int64_t)row * g.ld_aux_out + n;
-    if (ncols == 32 && g.vec_ok) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        uint4 u;
-        __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]);
-        __nv_bfloat162 t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-        __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
-        __nv_bfloat162 t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-        u.x = *(uint32_t*)&t0; u.y = *(uint32_t*)&t1; u.z = *(uint32_t*)&t2; u.w = *(uint32_t*)&t3;
-        *(uint4*)(dst + j) = u;
-      }
-    } else {
-      for (int j = 0; j < ncols; ++j) dst[j] = __float2bfloat16(v[j]);
-    }
+  if (MODE == 2 && g.col_scale) {
+    cs.x = __ldg(g.col_scale + col);
+    if (c1) cs.y = __ldg(g.col_scale + col + 1);
   }
-  if (g.act == 1) {
+  const float inv_keep = (MODE == 2 && g.dropout_p > 0.f) ? 1.0f / (1.0f - g.dropout_p) : 1.0f;
+  const int nrows = FULL ? 32 : min(32, g.M - row_base);
+  const bool has_aux_out = MODE != 1 && g.aux_out != nullptr;
+  const int act = g.act;
+  const bool want_aux = MODE == 1 || (MODE == 2 && act == 2);
+  const bool want_res = MODE == 2 && g.residual != nullptr;
+  const int ldc = (int)g.ldc, ld_ai = (int)g.ld_aux_in, ld_ao = (int)g.ld_aux_out, ld_r = (int)g.ld_res;
+  const int64_t rb = row_base;
+  const bf16* aux_in0 = want_aux ? g.aux_in + rb * g.ld_aux_in + col : nullptr;
+  bf16* aux_out0 = has_aux_out ? g.aux_out + rb * g.ld_aux_out + col : nullptr;
+  const char* res0 = want_res ? (const char*)g.residual + (rb * g.ld_res + col) * (g.res_dtype == 0 ? 2 : 4) : nullptr;
+  char* c0 = (char*)g.C + (rb * g.ldc + col) * (g.c_dtype == 0 ? 2 : 4);
+  const float* st0 = stage + 2 * (lane & 15);
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    const int rr0 = (lane >> 4) + 16 * half;
+    if (rr0 >= nrows) break;
+    uint32_t aux[8];
+    float2 res[8], v[8];
+    if (want_aux) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-  } else if (g.act == 2) {
-    float a[32];
-    load_bf16_chunk(g.aux_in + (int64_t)row * g.ld_aux_in + n, ncols, g.vec_ok, a);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] *= gelu_erf_grad(a[j]);
-  } else if (g.act == 3) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
-  }
-  if (g.col_scale) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] *= (j < ncols) ? __ldg(g.col_scale + n + j) : 0.f;
-  }
-  if (g.row_group_scale) {
-    const float s = __ldg(g.row_group_scale + row / g.rows_per_group);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] *= s;
-  }
-  if (g.dropout_p > 0.f) {
-    const float inv_keep = 1.0f / (1.0f - g.dropout_p);
-    const uint64_t base = (uint64_t)row * (uint64_t)g.N + (uint64_t)n;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = (hash_uniform(g.dropout_seed, base + j) >= g.dropout_p) ? v[j] * inv_keep : 0.f;
-  }
-  if (g.residual) {
-    if (g.res_dtype == 0) {
-      float a[32];
-      load_bf16_chunk((const bf16*)g.residual + (int64_t)row * g.ld_res + n, ncols, g.vec_ok, a);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] += a[j];
-    } else {
-      const float* src = (const float*)g.residual + (int64_t)row * g.ld_res + n;
-      if (ncols == 32 && g.vec_ok) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 f = *(const float4*)(src + j);
-          v[j] += f.x; v[j + 1] += f.y; v[j + 2] += f.z; v[j + 3] += f.w;
+      for (int i = 0; i < 8; ++i) {
+        const int rr = rr0 + 2 * i;
+        aux[i] = 0u;
+        if (rr < nrows) {
+          const bf16* p = aux_in0 + rr * ld_ai;
+          if (vec) aux[i] = *(const uint32_t*)p;
+          else aux[i] = (uint32_t) * (const uint16_t*)p | (c1 ? ((uint32_t) * (const uint16_t*)(p + 1) << 16) : 0u);
         }
-      } else {
+      }
+    }
+    if (want_res) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += (j < ncols) ? src[j] : 0.f;
+      for (int i = 0; i < 8; ++i) {
+        const int rr = rr0 + 2 * i;
+        res[i] = make_float2(0.f, 0.f);
+        if (rr < nrows) {
+          if (g.res_dtype == 0) {
+            const bf16* p = (const bf16*)res0 + rr * ld_r;
+            res[i] = ld2_bf16(p, vec, c1);
+          } else {
+            const float* p = (const float*)res0 + rr * ld_r;
+            res[i] = vec ? *(const float2*)p : make_float2(p[0], c1 ? p[1] : 0.f);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      v[i] = *(const float2*)(st0 + (rr0 + 2 * i) * EPI_LD);
+      v[i].x += bias.x;
+      v[i].y += bias.y;
+    }
+    if (has_aux_out) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (rr0 + 2 * i < nrows) st2_bf16(aux_out0 + (rr0 + 2 * i) * ld_ao, v[i], vec, c1);
+    }
+    if (MODE != 1 && act == 1) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        v[i].x = gelu_fast(v[i].x);
+        v[i].y = gelu_fast(v[i].y);
+      }
+    }
+    if (want_aux) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float2 a = __bfloat1622float2(*(const __nv_bfloat162*)&aux[i]);
+        v[i].x *= gelu_grad_fast(a.x);
+        v[i].y *= gelu_grad_fast(a.y);
+      }
+    }
+    if (MODE == 2) {
+      if (act == 3) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          v[i].x = tanhf(v[i].x);
+          v[i].y = tanhf(v[i].y);
+        }
+      }
+      if (g.col_scale || g.row_group_scale) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float s = 1.f;
+          if (g.row_group_scale) s = __ldg(g.row_group_scale + min(row_base + rr0 + 2 * i, g.M - 1) / g.rows_per_group);
+          v[i].x *= cs.x * s;
+          v[i].y *= cs.y * s;
+        }
+      }
+      if (g.dropout_p > 0.f) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint64_t base = (uint64_t)(row_base + rr0 + 2 * i) * (uint64_t)g.N + (uint64_t)col;
+          v[i].x = (hash_uniform(g.dropout_seed, base) >= g.dropout_p) ? v[i].x * inv_keep : 0.f;
+          v[i].y = (hash_uniform(g.dropout_seed, base + 1) >= g.dropout_p) ? v[i].y * inv_keep : 0.f;
+        }
+      }
+      if (want_res) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          v[i].x += res[i].x;
+          v[i].y += res[i].y;
+        }
+      }
+    }
+    if (MODE != 2 || g.c_dtype == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (rr0 + 2 * i < nrows) st2_bf16((bf16*)c0 + (rr0 + 2 * i) * ldc, v[i], vec, c1);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (rr0 + 2 * i >= nrows) continue;
+        float* dst = (float*)c0 + (rr0 + 2 * i) * ldc;
+        if (g.accumulate) {
+          if (vec) {
+            asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dst), "f"(v[i].x), "f"(v[i].y) : "memory");
+          } else {
+            atomicAdd(dst, v[i].x);
+            if (c1) atomicAdd(dst + 1, v[i].y);
+          }
+        } else if (vec) {
+          *(float2*)dst = v[i];
+        } else {
+          dst[0] = v[i].x;
+          if (c1) dst[1] = v[i].y;
+        }
       }
     }
   }
-  store_chunk(g, row, n, ncols, v);
+}
+
+template <int MODE>
+XFM_DEVINL void epilogue_one(const GemmArgs& g, float* stage, uint32_t taddr, int row_base, int n, int lane, bool has_work) {
+  uint32_t r[32];
+  tmem_ld_32x32(taddr, r);
+  tmem_ld_wait();
+  if (!has_work) return;
+  __syncwarp();  // phase 2 of the previous block has finished reading the staging block
+#pragma unroll
+  for (int j = 0; j < 32; j += 2)
+    *(float2*)(stage + lane * EPI_LD + j) = make_float2(__uint_as_float(r[j]), __uint_as_float(r[j + 1]));
+  __syncwarp();
+  if (g.vec_ok && row_base + 32 <= g.M && n + 32 <= g.N) epilogue_block<MODE, true>(g, stage, row_base, n, lane);
+  else epilogue_block<MODE, false>(g, stage, row_base, n, lane);
 }
 
 template <int BLOCK_N, int A_MN, int B_MN>
@@ -191,9 +255,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  if ((int)(smem - smem_raw) + STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES + 256 > Cfg::SMEM_BYTES) __trap();
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
-  uint64_t* bars = (uint64_t*)(smem + STAGES * Cfg::STAGE_BYTES);
+  float* epi_stage = (float*)(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* bars = (uint64_t*)(smem + STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES);
   uint64_t* full_bar = bars;                    // [STAGES]
   uint64_t* empty_bar = bars + STAGES;          // [STAGES]
   uint64_t* tmem_full = bars + 2 * STAGES;      // [2]
@@ -212,7 +278,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 4);
+      mbar_init(&tmem_empty[s], EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -240,7 +306,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int kb0 = ks * kb_per_split;
         const int kb1 = min(g.kb_total, kb0 + kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           uint8_t* sa = smem_a + stage * Cfg::A_BYTES;
           uint8_t* sb = smem_b + stage * Cfg::B_BYTES;
@@ -273,7 +339,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int ks = t % g.split_k;
         const int kb0 = ks * kb_per_split;
         const int kb1 = min(g.kb_total, kb0 + kb_per_split);
-        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        mbar_wait_relaxed(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * BLOCK_N);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -300,7 +366,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
     __syncwarp();
   } else {
-    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    const int q = warp & 3;          // TMEM lane quadrant this warp may access
+    const int ew = warp - 2;         // 0..7
+    const int c_begin = (ew >> 2) * (BLOCK_N / (2 * EPI_COLS));  // first 32-column block of this warp's column half
+    constexpr int C_PER_WARP = BLOCK_N / (2 * EPI_COLS);
+    float* stage = epi_stage + ew * EPI_WARP_FLOATS;
     int as = 0;
     uint32_t aphase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -310,19 +380,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       const int ks = t % g.split_k;
       const int kb0 = ks * kb_per_split;
       const int kb1 = min(g.kb_total, kb0 + kb_per_split);
-      mbar_wait(&tmem_full[as], aphase);
+      mbar_wait_relaxed(&tmem_full[as], aphase);
       tc_fence_after();
-      const int row = m0 + q * 32 + lane;
+      const int row_base = m0 + q * 32;
       const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BLOCK_N);
-      const bool has_work = kb1 > kb0;  // empty split slices contribute nothing
+      const bool has_work = kb1 > kb0 && row_base < g.M;  // empty split slices contribute nothing
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        const int n = n0 + c * 32;
+      for (int c = c_begin; c < c_begin + C_PER_WARP; ++c) {
+        const int n = n0 + c * EPI_COLS;
         if (n >= g.N) break;
-        uint32_t r[32];
-        tmem_ld_32x32(t_base + c * 32, r);
-        tmem_ld_wait();
-        if (row < g.M && has_work) epilogue_chunk(g, row, n, r);
+        const uint32_t taddr = t_base + c * EPI_COLS;
+        if (g.epi_mode == 0) epilogue_one<0>(g, stage, taddr, row_base, n, lane, has_work);
+        else if (g.epi_mode == 1) epilogue_one<1>(g, stage, taddr, row_base, n, lane, has_work);
+        else epilogue_one<2>(g, stage, taddr, row_base, n, lane, has_work);
       }
       tc_fence_before();
       __syncwarp();
@@ -440,11 +510,13 @@ int gemm_bf16(const xfm_gemm_params* p, cudaStream_t stream) {
   g.C = p->C; g.bias = p->bias; g.aux_in = (const bf16*)p->aux_in; g.aux_out = (bf16*)p->aux_out;
   g.col_scale = p->col_scale; g.row_group_scale = p->row_group_scale; g.residual = p->residual;
   g.dropout_p = p->dropout_p; g.dropout_seed = p->dropout_seed;
-  const int c_al = p->c_dtype == 0 ? 7 : 3;
-  bool vec = aligned16(p->C) && (p->ldc & c_al) == 0;
-  if (p->aux_in) vec = vec && aligned16(p->aux_in) && (p->ld_aux_in & 7) == 0;
-  if (p->aux_out) vec = vec && aligned16(p->aux_out) && (p->ld_aux_out & 7) == 0;
-  if (p->residual) vec = vec && aligned16(p->residual) && (p->ld_res & (p->res_dtype == 0 ? 7 : 3)) == 0;
+  auto al = [](const void* q, size_t bytes) { return ((uintptr_t)q & (bytes - 1)) == 0; };
+  bool vec = al(p->C, p->c_dtype == 0 ? 4 : 8) && (p->ldc & 1) == 0;
+  if (p->aux_in) vec = vec && al(p->aux_in, 4) && (p->ld_aux_in & 1) == 0;
+  if (p->aux_out) vec = vec && al(p->aux_out, 4) && (p->ld_aux_out & 1) == 0;
+  if (p->residual) vec = vec && al(p->residual, p->res_dtype == 0 ? 4 : 8) && (p->ld_res & 1) == 0;
+  const bool plain = p->c_dtype == 0 && !p->col_scale && !p->row_group_scale && !p->residual && !(p->dropout_p > 0.f);
+  g.epi_mode = (plain && p->act <= 1) ? 0 : ((plain && p->act == 2 && !p->aux_out) ? 1 : 2);
   g.vec_ok = vec ? 1 : 0;
   switch (bn) {
     case 64: return dispatch_major<64>(p, g, stream);

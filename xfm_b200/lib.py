@@ -54,8 +54,16 @@ def check(rc, what):
         raise RuntimeError(f"xfm_b200: {what} failed with code {rc}: {msg}")
 
 
+_cur_dev = torch._C._cuda_getDevice if hasattr(torch._C, "_cuda_getDevice") else None
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def lib():
-    """Library handle, initialised for the current CUDA device."""
+    """Library handle, initialised for the current CUDA device (hot path: one C call + a set lookup)."""
+    if _lib is not None and _inited_devices:
+        dev = _cur_dev() if _cur_dev is not None else torch.cuda.current_device()
+        if dev in _inited_devices:
+            return _lib
     l = load()
     if not torch.cuda.is_available():
         raise RuntimeError("xfm_b200 needs a CUDA device (sm_100a); there is no CPU path")
@@ -73,6 +81,9 @@ def launch_count():
 
 
 def stream_ptr():
+    """Raw cudaStream_t of torch's current stream on the current device."""
+    if _raw_stream is not None and _cur_dev is not None:
+        return C.c_void_p(_raw_stream(_cur_dev()))
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
