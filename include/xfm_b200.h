@@ -119,6 +119,12 @@ typedef struct xfm_attn_params {
   int64_t do_stride, dq_stride, dk_stride, dv_stride, ds_ld;
   const int32_t* kv_offsets;
   const int32_t* kv_samples;
+  /* BEiT relative position bias in closed form (beit2.py:94-116): table [ (2W-1)^2 + 3, H ] f32 and the window side W
+   * (Lq = Lk = W*W + 1).  When given (and no mask / dropout / kv_index is), the forward runs on the tcgen05 kernel and
+   * gathers the bias from the table instead of reading `bias`; `bias` must then hold the same values (backward). */
+  const float* rel_table;
+  int32_t rel_window;
+  int32_t allow_tc; /* 1: use the tcgen05 / TMEM kernel when the problem fits it (self-attention, Lk <= 208) */
 } xfm_attn_params;
 
 int xfm_attention_fwd(const xfm_attn_params* p, void* stream);

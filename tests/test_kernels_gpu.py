@@ -311,6 +311,43 @@ def test_attention_fwd_bwd(lib, B, H, Lq, Lk, mode):
         assert e < 2e-2 * max(1.0, float(bias_r.grad.abs().max())), e
 
 
+@pytest.mark.parametrize("B,H,ws,with_table", [(3, 12, 14, True), (10, 12, 14, False), (2, 2, 4, True), (5, 3, 7, True),
+                                               (1, 1, 12, True)])
+def test_vit_attention_tcgen05_forward(lib, B, H, ws, with_table):
+    """tcgen05 / TMEM forward (attention_tc.cu): relative-position bias gathered from the table in closed form
+    (beit2.py:94-116,139-145) must equal softmax((q*scale) k^T + table[index]) v; also checked against the mma.sync
+    kernel fed with the materialised bias, and lse against torch.logsumexp."""
+    from xfm_b200.encoders import closed_form_rel_index
+    g = G(ws * 100 + B)
+    L, D = ws * ws + 1, H * 64
+    qkv = bf(torch.randn(B * L, 3 * D, generator=g))
+    c = qkv.cuda()
+    q, k, v = c[:, :D], c[:, D:2 * D], c[:, 2 * D:]
+    f = qkv.float().view(B, L, 3, H, 64).permute(2, 0, 3, 1, 4)
+    table = bias = bias_dev = None
+    if with_table:
+        T = (2 * ws - 1) ** 2 + 3
+        table = torch.randn(T, H, generator=g)
+        idx = closed_form_rel_index(ws)
+        bias = table[idx.view(-1)].view(L, L, H).permute(2, 0, 1).contiguous()  # beit2.py:139-145
+        ld = (L + 7) // 8 * 8
+        bias_dev = torch.zeros(H, L, ld)
+        bias_dev[:, :, :L] = bias
+        bias_dev = bias_dev.cuda()
+    s = (f[0] * 0.125) @ f[1].transpose(-1, -2)
+    if bias is not None:
+        s = s + bias
+    ref = (torch.softmax(s, -1) @ f[2]).permute(0, 2, 1, 3).reshape(B * L, D)
+    lse_ref = torch.logsumexp(s, -1)
+    kw = dict(bias=bias_dev, rel_table=None if table is None else table.cuda(), rel_window=ws if with_table else 0)
+    out, lse = lib.attention_fwd(q, k, v, B, H, L, L, 0.125, **kw)
+    out2, lse2 = lib.attention_fwd(q, k, v, B, H, L, L, 0.125, allow_tc=False, **kw)
+    assert float((out.float().cpu() - ref).abs().max()) < 2e-2
+    assert float((lse.cpu() - lse_ref).abs().max()) < 2e-3
+    assert float((out.float() - out2.float()).abs().max()) < 2e-2
+    assert float((lse - lse2).abs().max()) < 2e-3
+
+
 def test_attention_dropout_is_consistent(lib):
     """Same (seed, index) mask in forward and both backward kernels: check dQ/dK/dV against autograd through the
     forward's own (recovered) mask."""

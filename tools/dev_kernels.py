@@ -61,18 +61,21 @@ def attn_case(name, B, H, Lq, Lk, mode, Bkv=None, p=0.0, nbuf=3):
             dq, dk, dv = dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:]
             kv_index = order = offs = None
         ld = (Lk + 7) // 8 * 8
-        bias = torch.randn(H, Lq, ld, device=dev, generator=g) if mode == "vit" else None
+        bias = torch.randn(H, Lq, ld, device=dev, generator=g) if mode in ("vit", "vit_tc") else None
+        table = torch.randn(732, H, device=dev, generator=g) if mode == "vit_tc" else None
         kmask = torch.zeros(B, Lk, device=dev) if mode == "text" else None
         dout = torch.randn(B * Lq, D, device=dev, generator=g).bfloat16()
-        ds = torch.empty(B, H, Lq, ld, device=dev, dtype=torch.bfloat16) if mode == "vit" else None
+        ds = torch.empty(B, H, Lq, ld, device=dev, dtype=torch.bfloat16) if mode in ("vit", "vit_tc") else None
         out = torch.empty(B * Lq, D, device=dev, dtype=torch.bfloat16)
         sets.append(dict(q=q, k=k, v=v, dq=dq, dk=dk, dv=dv, kv_index=kv_index, order=order, offs=offs, bias=bias, kmask=kmask,
+                         table=table,
                          dout=dout, ds=ds, out=out))
     lses = []
 
     def fwd(s):
         o, lse = L.attention_fwd(s["q"], s["k"], s["v"], B, H, Lq, Lk, 0.125, Bkv=Bkv, bias=s["bias"], kmask=s["kmask"],
-                                 kv_index=s["kv_index"], dropout_p=p, dropout_seed=7, out=s["out"])
+                                 kv_index=s["kv_index"], dropout_p=p, dropout_seed=7, out=s["out"], rel_table=s["table"],
+                                 rel_window=14 if s["table"] is not None else 0, allow_tc=mode in ("vit_tc", "plain_tc"))
         s["lse"] = lse
 
     def bwd(s):
@@ -123,6 +126,8 @@ if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     torch.cuda.set_device(0)
     if what in ("attn", "all"):
+        attn_case("vit_self_tcgen05", 96, 12, 197, 197, "vit_tc")
+        attn_case("vqkd_self_tcgen05", 96, 12, 197, 197, "plain_tc")
         attn_case("vit_self", 96, 12, 197, 197, "vit")
         attn_case("vqkd_self", 96, 12, 197, 197, "plain")
         attn_case("text_self", 96, 12, 40, 40, "text", p=0.1)

@@ -32,13 +32,14 @@ def wgrad(fp_grad, dy, x):
 # =====================================================================================================
 # BEiT / ViT block
 # =====================================================================================================
-def vit_block_fwd(x, w, B, N, H, eps, relbias=None, drop_scale=None, save=True):
+def vit_block_fwd(x, w, B, N, H, eps, relbias=None, drop_scale=None, save=True, rel=None):
     """x: fp32 [B*N, D] residual stream.  w: dict of views for this block (see vision.py).  Returns (x_out, saved)."""
     D = x.shape[1]
     s = Saved() if save else None
     xn1, st1, _ = L.layernorm_fwd(x, w["n1w"], w["n1b"], eps, want_stats=save)
     qkv = L.gemm(xn1, w["qkv_w16"], bias=w["qkv_b"])
-    attn, lse = L.attention_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], B, H, N, N, 0.125, bias=relbias)
+    attn, lse = L.attention_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], B, H, N, N, 0.125, bias=relbias,
+                                rel_table=None if rel is None else rel[0], rel_window=0 if rel is None else rel[1])
     gamma1, gamma2 = w.get("g1"), w.get("g2")
     ds1, ds2 = drop_scale if isinstance(drop_scale, tuple) else (drop_scale, drop_scale)  # one DropPath draw per branch
     z1 = torch.empty_like(attn) if (save and gamma1 is not None) else None

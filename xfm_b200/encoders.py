@@ -25,6 +25,19 @@ def _f32(t):
     return t if t.dtype == torch.float32 else t.float()
 
 
+def closed_form_rel_index(ws):
+    """idx(i, j) of beit2.py:104-114 as arithmetic: what attention_tc.cu evaluates per score element."""
+    T = (2 * ws - 1) ** 2 + 3
+    n = ws * ws + 1
+    t = torch.arange(n) - 1
+    r, c = torch.div(t, ws, rounding_mode="floor"), t % ws
+    idx = (r[:, None] - r[None, :] + ws - 1) * (2 * ws - 1) + (c[:, None] - c[None, :] + ws - 1)
+    idx[0, :] = T - 3
+    idx[:, 0] = T - 2
+    idx[0, 0] = T - 1
+    return idx.to(torch.int64)
+
+
 # =====================================================================================================
 # parameter layout
 # =====================================================================================================
@@ -142,6 +155,11 @@ class VisionEncoder:
         self.N = self.np + 1
         self.eps = cfg["vision_ln_eps"] if prefix == "vision_encoder." else 1e-6  # model_vqkd.py:245
         self.rel_index = rel_index  # int64 [N, N] device tensor
+        # The tcgen05 attention kernel gathers the bias through the closed form of beit2.py:104-114; use it only when the
+        # buffer really is that index (a checkpoint could in principle carry another one).
+        self.ws = cfg["image_res"] // self.P
+        self.rel_closed_form = bool(relbias and rel_index is not None and
+                                    torch.equal(rel_index.cpu(), closed_form_rel_index(self.ws)))
         self.bias_ld = (self.N + 7) // 8 * 8
         self.drop_path = [float(x) for x in torch.linspace(0, cfg["drop_path_rate"], self.depth)] if layerscale else \
             [0.0] * self.depth  # beit2.py:309; the frozen tokenizer runs in eval mode
@@ -203,7 +221,8 @@ class VisionEncoder:
             if train and self.drop_path[i] > 0:
                 keep = 1.0 - self.drop_path[i]
                 ds = tuple((torch.rand(B, device=x.device) < keep).float() / keep for _ in range(2))
-            x, s = BK.vit_block_fwd(x, w, B, N, self.H, self.eps, relbias=rb, drop_scale=ds, save=save)
+            rel = (w["rel_table"], self.ws) if (self.relbias and self.rel_closed_form) else None
+            x, s = BK.vit_block_fwd(x, w, B, N, self.H, self.eps, relbias=rb, drop_scale=ds, save=save, rel=rel)
             st.blocks.append(s)
             if self.collect is not None:
                 self.collect.append(x.view(B, N, D).clone())

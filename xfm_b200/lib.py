@@ -175,6 +175,7 @@ class AttnParams(C.Structure):
         ("do_stride", C.c_int64), ("dq_stride", C.c_int64), ("dk_stride", C.c_int64), ("dv_stride", C.c_int64),
         ("ds_ld", C.c_int64),
         ("kv_offsets", C.c_void_p), ("kv_samples", C.c_void_p),
+        ("rel_table", C.c_void_p), ("rel_window", C.c_int32), ("allow_tc", C.c_int32),
     ]
 
 
@@ -199,8 +200,10 @@ def _attn_common(p, q, k, v, B, H, Lq, Lk, Bkv, scale, bias, kmask, kv_index, dr
 
 
 def attention_fwd(q, k, v, B, H, Lq, Lk, scale, *, Bkv=None, bias=None, kmask=None, kv_index=None, dropout_p=0.0,
-                  dropout_seed=0, out=None):
-    """q: bf16 [B*Lq, >=H*64] view; k, v: bf16 [Bkv*Lk, ...] views.  Returns (out bf16 [B*Lq, H*64], lse f32 [B,H,Lq])."""
+                  dropout_seed=0, out=None, rel_table=None, rel_window=0, allow_tc=True):
+    """q: bf16 [B*Lq, >=H*64] view; k, v: bf16 [Bkv*Lk, ...] views.  Returns (out bf16 [B*Lq, H*64], lse f32 [B,H,Lq]).
+    rel_table / rel_window: BEiT relative-position table [(2W-1)^2+3, H] f32 whose closed-form gather equals `bias`
+    (tcgen05 path); allow_tc=False forces the mma.sync kernel."""
     Bkv = B if Bkv is None else Bkv
     if out is None:
         out = torch.empty((B * Lq, H * 64), dtype=torch.bfloat16, device=q.device)
@@ -208,6 +211,11 @@ def attention_fwd(q, k, v, B, H, Lq, Lk, scale, *, Bkv=None, bias=None, kmask=No
     p = AttnParams()
     _attn_common(p, q, k, v, B, H, Lq, Lk, Bkv, scale, bias, kmask, kv_index, dropout_p, dropout_seed)
     p.out, p.o_stride, p.lse = out.data_ptr(), out.stride(0), lse.data_ptr()
+    p.allow_tc = int(allow_tc)
+    if rel_table is not None:
+        assert rel_table.dtype == torch.float32 and rel_table.is_contiguous() and rel_table.shape[1] == H
+        assert rel_table.shape[0] == (2 * rel_window - 1) ** 2 + 3
+        p.rel_table, p.rel_window = rel_table.data_ptr(), rel_window
     check(lib().xfm_attention_fwd(C.byref(p), stream_ptr()), "xfm_attention_fwd")
     return out, lse
 
