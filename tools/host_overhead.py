@@ -50,4 +50,34 @@ if os.environ.get("XFM_PYPROF"):
     step()
     pr.disable()
     torch.cuda.synchronize()
-    pstats.Stats(pr).sort_stats("cumulative").print_stats(45)
+    pstats.Stats(pr).sort_stats("tottime").print_stats(40)
+
+# ---- does running un-synchronised (host ahead of the GPU) change the step time?
+def loop(n, sync_each):
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(n):
+        l = step()
+        if sync_each:
+            float(l.detach())
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n, 1e3 * (time.perf_counter() - t0) / n
+
+
+if os.environ.get("XFM_PRERESERVE"):
+    gib = int(os.environ["XFM_PRERESERVE"])
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    x = torch.empty(gib << 30, dtype=torch.uint8, device=dev)
+    del x
+    print("pre-reserved", gib, "GiB; reserved now", torch.cuda.memory_reserved() / 2**30)
+for mode in (False, True, False, True, False, True):
+    d0 = torch.cuda.memory_stats().get("num_device_alloc")
+    ms, wall = loop(6, mode)
+    st = torch.cuda.memory_stats()
+    print(f"sync_each={mode}: {ms:.1f} ms/step (events), {wall:.1f} ms/step (wall); device_allocs +{st.get('num_device_alloc') - d0}, "
+          f"reserved={torch.cuda.memory_reserved() / 2**30:.1f} GiB, peak_alloc={torch.cuda.max_memory_allocated() / 2**30:.1f} GiB",
+          flush=True)

@@ -16,6 +16,28 @@ import torch.distributed as dist
 
 from . import lib as L
 
+def reserve_arena(nbytes=None, factor=1.5, device=None):
+    """Make the caching allocator own one large segment so steady-state steps never reach cudaMalloc.
+
+    A pre-training step allocates ~2000 activation tensors with staggered lifetimes; the allocator keeps growing by a
+    few hundred MB for dozens of steps, and every cudaMalloc that lands while the GPU is busy stalls the launching
+    thread (measured on B200: 175 ms/step with 9 device allocations in a 6-step loop vs 111 ms/step with none).  Call
+    after one warm-up step: reserves factor x the peak seen so far (or nbytes) in a single block and returns it to the
+    cache, from which later allocations are carved."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+    torch.cuda.synchronize(dev)
+    if nbytes is None:
+        nbytes = int(torch.cuda.max_memory_allocated(dev) * factor)
+    free, _ = torch.cuda.mem_get_info(dev)
+    torch.cuda.empty_cache()
+    free, _ = torch.cuda.mem_get_info(dev)
+    nbytes = min(nbytes, int(free * 0.9))
+    if nbytes > (1 << 20):
+        x = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        del x
+    return nbytes
+
+
 NO_DECAY = ("bias", "LayerNorm.bias", "LayerNorm.weight", "norm.bias", "norm.weight", "norm1.bias", "norm1.weight",
             "norm2.bias", "norm2.weight")  # optim.py:17-25
 

@@ -408,9 +408,8 @@ class XFMBase(nn.Module):
             return image_feat.contiguous(), text_feat.contiguous(), idx, 0
         W, r = dist.get_world_size(), dist.get_rank()
         msg = torch.cat([image_feat, text_feat], 1).contiguous()  # one message per rank: [B, 2E]
-        allm = torch.empty((W, B, 2 * Ed), dtype=msg.dtype, device=msg.device)
+        allm = torch.empty((W * B, 2 * Ed), dtype=msg.dtype, device=msg.device)  # rank-major concatenation along dim 0
         dist.all_gather_into_tensor(allm, msg)
-        allm = allm.view(W * B, 2 * Ed)
         idx_all = None
         if idx is not None:
             idx_all = torch.empty((W * B,), dtype=idx.dtype, device=idx.device)
