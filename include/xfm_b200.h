@@ -124,7 +124,9 @@ typedef struct xfm_attn_params {
    * gathers the bias from the table instead of reading `bias`; `bias` must then hold the same values (backward). */
   const float* rel_table;
   int32_t rel_window;
-  int32_t allow_tc; /* 1: use the tcgen05 / TMEM kernel when the problem fits it (self-attention, Lk <= 208) */
+  int32_t allow_tc;
+  float* rel_dtable; /* backward: gradient of rel_table, accumulated (+=) by the tcgen05 dQ kernel; when null or when the
+                      * tcgen05 path is not taken the caller derives it from ds_dump */ /* 1: use the tcgen05 / TMEM kernel when the problem fits it (self-attention, Lk <= 208) */
 } xfm_attn_params;
 
 int xfm_attention_fwd(const xfm_attn_params* p, void* stream);

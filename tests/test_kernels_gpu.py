@@ -348,6 +348,47 @@ def test_vit_attention_tcgen05_forward(lib, B, H, ws, with_table):
     assert float((lse - lse2).abs().max()) < 2e-3
 
 
+@pytest.mark.parametrize("B,H,ws,with_table", [(3, 12, 14, True), (2, 2, 14, False), (2, 2, 4, True), (5, 3, 7, True),
+                                               (2, 1, 12, True), (30, 12, 14, True)])
+def test_vit_attention_tcgen05_backward(lib, B, H, ws, with_table):
+    """tcgen05 dQ / dK / dV kernels and the in-kernel relative-position-table gradient against torch autograd."""
+    from xfm_b200.encoders import closed_form_rel_index
+    g = G(ws * 1000 + B)
+    L, D = ws * ws + 1, H * 64
+    qkv = bf(torch.randn(B * L, 3 * D, generator=g) * 0.7)
+    dout = bf(torch.randn(B * L, D, generator=g))
+    f = qkv.float().view(B, L, 3, H, 64).permute(2, 0, 3, 1, 4)
+    qf, kf, vf = (t.clone().requires_grad_(True) for t in (f[0], f[1], f[2]))
+    table = None
+    s = (qf * 0.125) @ kf.transpose(-1, -2)
+    if with_table:
+        T = (2 * ws - 1) ** 2 + 3
+        table = (torch.randn(T, H, generator=g)).requires_grad_(True)
+        idx = closed_form_rel_index(ws)
+        s = s + table[idx.view(-1)].view(L, L, H).permute(2, 0, 1)
+    ref = torch.softmax(s, -1) @ vf
+    ref.backward(dout.float().view(B, L, H, 64).permute(0, 2, 1, 3))
+    want = torch.stack([qf.grad, kf.grad, vf.grad]).permute(1, 3, 0, 2, 4).reshape(B * L, 3 * D)
+    c, do = qkv.cuda(), dout.cuda()
+    q, k, v = c[:, :D], c[:, D:2 * D], c[:, 2 * D:]
+    tdev = None if table is None else table.detach().cuda()
+    kw = dict(rel_table=tdev, rel_window=ws if with_table else 0)
+    out, lse = lib.attention_fwd(q, k, v, B, H, L, L, 0.125, **kw)
+    dqkv = torch.full_like(c, float("nan"))
+    dtab = None if table is None else torch.zeros_like(tdev)
+    lib.attention_bwd(do, q, k, v, out, lse, B, H, L, L, 0.125, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:],
+                      rel_dtable=dtab, **kw)
+    got = dqkv.float().cpu()
+    assert torch.isfinite(got).all()
+    scale = float(want.abs().max())
+    for name, sl in (("dq", slice(0, D)), ("dk", slice(D, 2 * D)), ("dv", slice(2 * D, 3 * D))):
+        err = float((got[:, sl] - want[:, sl]).abs().max())
+        assert err < 2.5e-2 * max(1.0, scale), (name, err, scale)
+    if table is not None:
+        err = float((dtab.cpu() - table.grad).abs().max())
+        assert err < 2e-2 * max(1.0, float(table.grad.abs().max())), ("dtable", err, float(table.grad.abs().max()))
+
+
 def test_attention_dropout_is_consistent(lib):
     """Same (seed, index) mask in forward and both backward kernels: check dQ/dK/dV against autograd through the
     forward's own (recovered) mask."""

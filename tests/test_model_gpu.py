@@ -201,3 +201,25 @@ def test_train_mode_runs_and_dropout_changes_losses(golden_dir):
     gsum = sum(float(p.grad.abs().sum()) for p in model.parameters() if p.grad is not None)
     assert gsum > 0 and np.isfinite(gsum)
     assert abs(float(out["loss_mlm"]) - g["losses"]["loss_mlm"]) > 1e-6  # dropout active
+
+
+def test_build_mlp_head_matches_torch():
+    """build_mlp (xfm.py:115-121), as used by model_nlvr.py:25 on the concatenated CLS rows: forward and all gradients
+    against the same nn.Sequential evaluated by torch in fp32."""
+    from xfm_b200.xfm import build_mlp
+    torch.manual_seed(3)
+    head = build_mlp(256, 2).cuda()
+    ref = torch.nn.Sequential(torch.nn.Linear(256, 512), torch.nn.LayerNorm(512), torch.nn.GELU(), torch.nn.Linear(512, 2))
+    ref.load_state_dict({k: v.detach().cpu() for k, v in head.state_dict().items()})
+    x = torch.randn(24, 256)
+    xr = x.clone().requires_grad_(True)
+    xg = x.cuda().requires_grad_(True)
+    tgt = torch.randint(0, 2, (24,))
+    lr = torch.nn.functional.cross_entropy(ref(xr), tgt)
+    lg = torch.nn.functional.cross_entropy(head(xg), tgt.cuda())
+    lr.backward()
+    lg.backward()
+    assert abs(float(lg) - float(lr)) < 5e-3
+    assert float((xg.grad.cpu() - xr.grad).abs().max()) < 2e-2 * float(xr.grad.abs().max()) + 1e-5
+    for (n, p), (_, q) in zip(head.named_parameters(), ref.named_parameters()):
+        assert float((p.grad.cpu() - q.grad).abs().max()) < 3e-2 * float(q.grad.abs().max()) + 1e-5, n

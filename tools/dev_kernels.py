@@ -68,7 +68,7 @@ def attn_case(name, B, H, Lq, Lk, mode, Bkv=None, p=0.0, nbuf=3):
         ds = torch.empty(B, H, Lq, ld, device=dev, dtype=torch.bfloat16) if mode in ("vit", "vit_tc") else None
         out = torch.empty(B * Lq, D, device=dev, dtype=torch.bfloat16)
         sets.append(dict(q=q, k=k, v=v, dq=dq, dk=dk, dv=dv, kv_index=kv_index, order=order, offs=offs, bias=bias, kmask=kmask,
-                         table=table,
+                         table=table, dtab=None if table is None else torch.zeros_like(table),
                          dout=dout, ds=ds, out=out))
     lses = []
 
@@ -78,10 +78,14 @@ def attn_case(name, B, H, Lq, Lk, mode, Bkv=None, p=0.0, nbuf=3):
                                  rel_window=14 if s["table"] is not None else 0, allow_tc=mode in ("vit_tc", "plain_tc"))
         s["lse"] = lse
 
+    tc = mode in ("vit_tc", "plain_tc")
+
     def bwd(s):
         L.attention_bwd(s["dout"], s["q"], s["k"], s["v"], s["out"], s["lse"], B, H, Lq, Lk, 0.125, s["dq"], s["dk"], s["dv"],
                         Bkv=Bkv, bias=s["bias"], kmask=s["kmask"], kv_index=s["kv_index"], kv_offsets=s["offs"],
-                        kv_samples=s["order"], dropout_p=p, dropout_seed=7, ds_dump=s["ds"])
+                        kv_samples=s["order"], dropout_p=p, dropout_seed=7, ds_dump=None if tc else s["ds"],
+                        rel_table=s["table"], rel_window=14 if s["table"] is not None else 0,
+                        rel_dtable=s["dtab"] if tc else None, allow_tc=tc)
 
     us_f = timeit([lambda s=s: fwd(s) for s in sets])
     us_b = timeit([lambda s=s: bwd(s) for s in sets])

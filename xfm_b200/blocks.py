@@ -55,7 +55,7 @@ def vit_block_fwd(x, w, B, N, H, eps, relbias=None, drop_scale=None, save=True, 
     if save:
         s.x, s.st1, s.xn1, s.qkv, s.attn, s.lse, s.z1 = x, st1, xn1, qkv, attn, lse, z1
         s.x1, s.st2, s.xn2, s.h1, s.a1, s.z2 = x1, st2, xn2, h1, a1, z2
-        s.relbias, s.ds1, s.ds2 = relbias, ds1, ds2
+        s.relbias, s.ds1, s.ds2, s.rel = relbias, ds1, ds2, rel
     return x2, s
 
 
@@ -74,13 +74,15 @@ def vit_block_bwd(dx2, s, w, g, B, N, H, rel_index=None):
     dattn = L.gemm(dz1, w["proj_w16"], b_t=True)
     dqkv = torch.empty_like(s.qkv)
     ds = None
-    if s.relbias is not None:
+    tc = s.rel is not None and L.vit_attention_tc_ok(N)  # tcgen05 path: table gradient accumulated in-kernel
+    if s.relbias is not None and not tc:
         ds = torch.empty((B, H, N, s.relbias.shape[2]), dtype=torch.bfloat16, device=dx2.device)
         if s.relbias.shape[2] != N:
             ds[..., N:].zero_()
     q, k, v = s.qkv[:, :D], s.qkv[:, D:2 * D], s.qkv[:, 2 * D:]
     L.attention_bwd(dattn, q, k, v, s.attn, s.lse, B, H, N, N, 0.125, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:],
-                    bias=s.relbias, ds_dump=ds)
+                    bias=s.relbias, ds_dump=ds, rel_table=s.rel[0] if tc else None, rel_window=s.rel[1] if tc else 0,
+                    rel_dtable=g("rel_table") if tc else None)
     if ds is not None:
         dbias = L.batch_sum_bf16(ds)
         L.relpos_bias_bwd(dbias, rel_index, g("rel_table"), N, H, s.relbias.shape[2])

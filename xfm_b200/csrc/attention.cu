@@ -560,6 +560,9 @@ int attention_bwd(const xfm_attn_params* p, cudaStream_t s) {
     attn_delta_kernel<<<(a.B * a.Lq + 3) / 4, blk, 0, s>>>(a.dout, a.do_stride, a.out, a.o_stride, (float*)p->delta, a.B, a.H, a.Lq);
     count_launch();
   }
+  // tcgen05 path: needs the closed-form table whenever there is a bias (its gradient goes to rel_dtable, not ds_dump)
+  if (p->allow_tc && vit_attention_tc_supported(p) && (!p->bias || (p->rel_table && !p->ds_dump)))
+    return vit_attention_bwd_tc(p, s);
   const size_t smem_a = (size_t)(2 * AT_TILE + 2 * LkP) * ROW_BYTES;
   const size_t smem_b = (size_t)(2 * AT_TILE + 2 * LqP) * ROW_BYTES + 2 * LqP * sizeof(float);
   if (smem_a > 220 * 1024 || smem_b > 220 * 1024) {

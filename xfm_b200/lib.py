@@ -175,7 +175,7 @@ class AttnParams(C.Structure):
         ("do_stride", C.c_int64), ("dq_stride", C.c_int64), ("dk_stride", C.c_int64), ("dv_stride", C.c_int64),
         ("ds_ld", C.c_int64),
         ("kv_offsets", C.c_void_p), ("kv_samples", C.c_void_p),
-        ("rel_table", C.c_void_p), ("rel_window", C.c_int32), ("allow_tc", C.c_int32),
+        ("rel_table", C.c_void_p), ("rel_window", C.c_int32), ("allow_tc", C.c_int32), ("rel_dtable", C.c_void_p),
     ]
 
 
@@ -221,8 +221,11 @@ def attention_fwd(q, k, v, B, H, Lq, Lk, scale, *, Bkv=None, bias=None, kmask=No
 
 
 def attention_bwd(dout, q, k, v, out, lse, B, H, Lq, Lk, scale, dq, dk, dv, *, Bkv=None, bias=None, kmask=None,
-                  kv_index=None, kv_offsets=None, kv_samples=None, dropout_p=0.0, dropout_seed=0, ds_dump=None):
-    """Writes bf16 dq [B*Lq, ...], dk / dv [Bkv*Lk, ...] (views with row strides).  ds_dump: bf16 [B,H,Lq,ld]."""
+                  kv_index=None, kv_offsets=None, kv_samples=None, dropout_p=0.0, dropout_seed=0, ds_dump=None,
+                  rel_table=None, rel_window=0, rel_dtable=None, allow_tc=True):
+    """Writes bf16 dq [B*Lq, ...], dk / dv [Bkv*Lk, ...] (views with row strides).  ds_dump: bf16 [B,H,Lq,ld] (mma.sync path:
+    the caller reduces it into the bias-table gradient).  rel_table / rel_window / rel_dtable: closed-form relative-position
+    bias and its f32 gradient accumulator [(2W-1)^2+3, H] (tcgen05 path; needs ds_dump=None)."""
     Bkv = B if Bkv is None else Bkv
     p = AttnParams()
     _attn_common(p, q, k, v, B, H, Lq, Lk, Bkv, scale, bias, kmask, kv_index, dropout_p, dropout_seed)
@@ -240,7 +243,20 @@ def attention_bwd(dout, q, k, v, out, lse, B, H, Lq, Lk, scale, dq, dk, dv, *, B
     if kv_samples is not None:
         assert kv_offsets.dtype == torch.int32 and kv_samples.dtype == torch.int32
         p.kv_offsets, p.kv_samples = kv_offsets.data_ptr(), kv_samples.data_ptr()
+    p.allow_tc = int(allow_tc)
+    if rel_table is not None:
+        assert rel_table.dtype == torch.float32 and rel_table.is_contiguous() and rel_table.shape[1] == H
+        assert rel_table.shape[0] == (2 * rel_window - 1) ** 2 + 3
+        p.rel_table, p.rel_window = rel_table.data_ptr(), rel_window
+        if rel_dtable is not None:
+            assert rel_dtable.dtype == torch.float32 and rel_dtable.is_contiguous() and rel_dtable.shape == rel_table.shape
+            p.rel_dtable = rel_dtable.data_ptr()
     check(lib().xfm_attention_bwd(C.byref(p), stream_ptr()), "xfm_attention_bwd")
+
+
+def vit_attention_tc_ok(n_tokens):
+    """Token counts (W*W + 1) with an instantiated tcgen05 self-attention kernel (attention_tc.cu::window_for)."""
+    return n_tokens in (197, 145, 50, 17)
 
 
 # ------------------------------------------------------------------------------------------------------

@@ -109,6 +109,89 @@ def _to_f32(t16):
     return out
 
 
+class _MlpFn(torch.autograd.Function):
+    """Linear - LayerNorm - GELU(erf) - Linear on the C-ABI kernels, for heads a task model adds on top of XFMBase."""
+
+    @staticmethod
+    def forward(ctx, x, w0, b0, lw, lb, w3, b3):
+        x16 = x.detach().to(torch.bfloat16).contiguous()
+        w0_16, w3_16 = w0.detach().to(torch.bfloat16), w3.detach().to(torch.bfloat16)
+        z = L.gemm(x16, w0_16, bias=b0.detach(), out_dtype=torch.float32)
+        zn, stats, _ = L.layernorm_fwd(z, lw.detach(), lb.detach(), 1e-5, out_dtype=torch.float32)
+        a = L.gelu_fwd(zn)
+        n_out = w3.shape[0]
+        pad = (n_out + 7) // 8 * 8
+        y = torch.empty((x16.shape[0], pad), dtype=torch.float32, device=x.device)
+        L.gemm(a, w3_16, bias=b3.detach(), out=y[:, :n_out])
+        ctx.save_for_backward(x16, w0_16, z, zn, stats, a, w3_16, lw.detach())
+        ctx.n_out = n_out
+        return y[:, :n_out]
+
+    @staticmethod
+    def backward(ctx, dy):
+        x16, w0_16, z, zn, stats, a, w3_16, lw = ctx.saved_tensors
+        R, n_out = dy.shape
+        pad = (n_out + 7) // 8 * 8
+        dy16 = torch.zeros((R, pad), dtype=torch.bfloat16, device=dy.device)
+        dy16[:, :n_out] = dy
+        db3 = torch.zeros(pad, dtype=torch.float32, device=dy.device)
+        L.colsum_into(dy16, db3)
+        dw3 = torch.zeros(w3_16.shape, dtype=torch.float32, device=dy.device)
+        BK.wgrad(dw3, dy16[:, :n_out], a)
+        da = L.gemm(dy16[:, :n_out], w3_16, b_t=True)
+        dzn = L.gelu_bwd(da, zn)
+        dlw, dlb = torch.zeros_like(lw), torch.zeros_like(lw)
+        dz = L.layernorm_bwd(dzn, z, stats, lw, dlw, dlb, out_dtype=torch.bfloat16)
+        db0 = torch.zeros(w0_16.shape[0], dtype=torch.float32, device=dy.device)
+        L.colsum_into(dz, db0)
+        dw0 = torch.zeros(w0_16.shape, dtype=torch.float32, device=dy.device)
+        BK.wgrad(dw0, dz, x16)
+        dx = L.gemm(dz, w0_16, b_t=True, out_dtype=torch.float32)
+        return dx, dw0, db0, dlw, dlb, dw3, db3[:n_out]
+
+
+class _Mlp(nn.Sequential):
+    """Same parameter names as the reference's nn.Sequential (0.weight, 0.bias, 1.weight, 1.bias, 3.weight, 3.bias)."""
+
+    def forward(self, x):
+        shape = x.shape
+        y = _MlpFn.apply(x.reshape(-1, shape[-1]), self[0].weight, self[0].bias, self[1].weight, self[1].bias, self[3].weight,
+                         self[3].bias)
+        return y.reshape(*shape[:-1], y.shape[-1])
+
+
+def build_mlp(input_dim, output_dim):
+    """xfm.py:115-121 — heads built by task models (model_nlvr.py:25 cls_head); forward / backward run on the C-ABI kernels."""
+    return _Mlp(nn.Linear(input_dim, input_dim * 2), nn.LayerNorm(input_dim * 2), nn.GELU(), nn.Linear(input_dim * 2, output_dim))
+
+
+def load_pretrained(model, ckpt_rpath, config, is_eval=False, load_text=False):
+    """xfm.py:408-468 for the BEiT-v2 configurations: returns the state_dict to load.  Relative-position tables are passed
+    through when the checkpoint resolution equals config['image_res']; the geometric interpolation of beit2.py:753-849
+    (resolution change at fine-tune time) is checkpoint tooling outside the hot path and is not re-implemented."""
+    checkpoint = torch.load(ckpt_rpath, map_location="cpu")
+    state_dict = checkpoint["model"] if "model" in checkpoint.keys() else checkpoint
+    if is_eval:
+        return state_dict
+    if not config.get("use_beit_v2", True):
+        raise ValueError("only the BEiT-v2 vision encoder is built (every shipped config selects it)")
+    own = model.state_dict()
+    for k in list(state_dict.keys()):
+        if k.startswith("vision_encoder.") and "relative_position_bias_table" in k and k in own and \
+                state_dict[k].shape != own[k].shape:
+            raise NotImplementedError(f"{k}: checkpoint table {tuple(state_dict[k].shape)} vs model {tuple(own[k].shape)}; "
+                                      "interpolate the checkpoint with the reference's beit2.interpolate_pos_embed first")
+        if "relative_position_index" in k:
+            del state_dict[k]
+    if load_text:
+        for key in list(state_dict.keys()):
+            if key.startswith("text_encoder."):
+                name = "roberta." if "roberta" in str(config.get("text_encoder", "roberta")) else "bert."
+                if name in key:
+                    state_dict[key.replace(name, "")] = state_dict.pop(key)
+    return state_dict
+
+
 class XFMBase(nn.Module):
     def __init__(self, config=None, load_vision_params=False, load_text_params=False, use_contrastive_loss=False,
                  use_matching_loss=False, use_mlm_loss=False, use_bbox_loss=False, config_text=None, init=None,
