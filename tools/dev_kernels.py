@@ -83,9 +83,9 @@ def attn_case(name, B, H, Lq, Lk, mode, Bkv=None, p=0.0, nbuf=3):
     def bwd(s):
         L.attention_bwd(s["dout"], s["q"], s["k"], s["v"], s["out"], s["lse"], B, H, Lq, Lk, 0.125, s["dq"], s["dk"], s["dv"],
                         Bkv=Bkv, bias=s["bias"], kmask=s["kmask"], kv_index=s["kv_index"], kv_offsets=s["offs"],
-                        kv_samples=s["order"], dropout_p=p, dropout_seed=7, ds_dump=None if tc else s["ds"],
+                        kv_samples=s["order"], dropout_p=p, dropout_seed=7, ds_dump=s["ds"],
                         rel_table=s["table"], rel_window=14 if s["table"] is not None else 0,
-                        rel_dtable=s["dtab"] if tc else None, allow_tc=tc)
+                        allow_tc=tc)
 
     us_f = timeit([lambda s=s: fwd(s) for s in sets])
     us_b = timeit([lambda s=s: bwd(s) for s in sets])

@@ -74,15 +74,14 @@ def vit_block_bwd(dx2, s, w, g, B, N, H, rel_index=None):
     dattn = L.gemm(dz1, w["proj_w16"], b_t=True)
     dqkv = torch.empty_like(s.qkv)
     ds = None
-    tc = s.rel is not None and L.vit_attention_tc_ok(N)  # tcgen05 path: table gradient accumulated in-kernel
-    if s.relbias is not None and not tc:
+    tc = s.rel is not None and L.vit_attention_tc_ok(N)  # tcgen05 backward kernels (closed-form bias)
+    if s.relbias is not None:
         ds = torch.empty((B, H, N, s.relbias.shape[2]), dtype=torch.bfloat16, device=dx2.device)
         if s.relbias.shape[2] != N:
             ds[..., N:].zero_()
     q, k, v = s.qkv[:, :D], s.qkv[:, D:2 * D], s.qkv[:, 2 * D:]
     L.attention_bwd(dattn, q, k, v, s.attn, s.lse, B, H, N, N, 0.125, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:],
-                    bias=s.relbias, ds_dump=ds, rel_table=s.rel[0] if tc else None, rel_window=s.rel[1] if tc else 0,
-                    rel_dtable=g("rel_table") if tc else None)
+                    bias=s.relbias, ds_dump=ds, rel_table=s.rel[0] if tc else None, rel_window=s.rel[1] if tc else 0)
     if ds is not None:
         dbias = L.batch_sum_bf16(ds)
         L.relpos_bias_bwd(dbias, rel_index, g("rel_table"), N, H, s.relbias.shape[2])

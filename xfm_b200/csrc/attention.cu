@@ -142,7 +142,7 @@ XFM_DEVINL float quad_sum(float v) {
 
 XFM_DEVINL bool drop_keep(const AttnArgs& a, int b, int h, int q, int key) {
   const uint64_t idx = (((uint64_t)b * a.H + h) * a.Lq + q) * (uint64_t)a.Lk + key;
-  return hash_uniform(a.seed, idx) >= a.dropout_p;
+  return drop_keep_idx(a.seed, idx, a.dropout_p);
 }
 
 // Logit of (query row, key) after scale / bias / mask; -inf outside [0,Lk).
@@ -560,8 +560,9 @@ int attention_bwd(const xfm_attn_params* p, cudaStream_t s) {
     attn_delta_kernel<<<(a.B * a.Lq + 3) / 4, blk, 0, s>>>(a.dout, a.do_stride, a.out, a.o_stride, (float*)p->delta, a.B, a.H, a.Lq);
     count_launch();
   }
-  // tcgen05 path: needs the closed-form table whenever there is a bias (its gradient goes to rel_dtable, not ds_dump)
-  if (p->allow_tc && vit_attention_tc_supported(p) && (!p->bias || (p->rel_table && !p->ds_dump)))
+  // tcgen05 path: needs the closed-form table whenever there is a bias; the table gradient either comes out of the bf16
+  // dS dump (reduced by the caller) or is accumulated in-kernel into rel_dtable (shared-memory atomics: slower)
+  if (p->allow_tc && vit_attention_tc_supported(p) && (!p->bias || p->rel_table))
     return vit_attention_bwd_tc(p, s);
   const size_t smem_a = (size_t)(2 * AT_TILE + 2 * LkP) * ROW_BYTES;
   const size_t smem_b = (size_t)(2 * AT_TILE + 2 * LqP) * ROW_BYTES + 2 * LqP * sizeof(float);

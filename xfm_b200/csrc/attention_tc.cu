@@ -338,6 +338,8 @@ struct VitBwdArgs {
   const float* delta;    // [B, H, L]
   const float* table;    // [T, H] or null
   float* dtable;         // [T, H] accumulated (+=) or null
+  bf16* ds_dump;         // [B, H, L, ds_ld] bf16 dS (natural-logit gradient) or null: cheaper than dtable's smem atomics
+  int64_t ds_ld;
   bf16 *dq, *dk, *dv;
   int64_t dq_stride, dk_stride, dv_stride;
   int B, H;
@@ -523,9 +525,9 @@ vit_attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
       float* gb = gtab + rb_off;
       const int c0_idx = Cfg::OFFMAX + 1 + (qc >= 1 ? Cfg::T - 2 : Cfg::T - 1);
       const float bias_c0 = tab[c0_idx];
-      const int64_t st = ((int64_t)b * a.H + h) * L + qc;
-      const float lse2 = __ldg(a.lse + st) * 1.4426950408889634f;
-      const float dl = __ldg(a.delta + st);
+      const int64_t st_row = ((int64_t)b * a.H + h) * L + qc;
+      const float lse2 = __ldg(a.lse + st_row) * 1.4426950408889634f;
+      const float dl = __ldg(a.delta + st_row);
       mbar_wait(sd_full, (uint32_t)tau & 1u);
       tc_fence_after();
       const int cb = wg == 0 ? C_BEGIN0 : C_END0, ce = wg == 0 ? C_END0 : C_END1;
@@ -579,6 +581,8 @@ vit_attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
             }
           }
           st_bf16x8(dst8, ds);
+          if (a.ds_dump && row_ok && col8 < a.ds_ld)   // ds_ld is a multiple of 8: whole 16-byte chunks
+            st_bf16x8((uint8_t*)(a.ds_dump + (st_row * a.ds_ld + col8)), ds);
         }
       }
       fence_proxy_async();
@@ -917,6 +921,7 @@ static int launch_vit_bwd(const xfm_attn_params* p, cudaStream_t s) {
   using Cfg = VitBwdCfg<W>;
   VitBwdArgs a;
   a.lse = p->lse; a.delta = p->delta; a.table = p->rel_table; a.dtable = p->rel_dtable;
+  a.ds_dump = (bf16*)p->ds_dump; a.ds_ld = p->ds_ld;
   a.dq = (bf16*)p->dq; a.dk = (bf16*)p->dk; a.dv = (bf16*)p->dv;
   a.dq_stride = p->dq_stride; a.dk_stride = p->dk_stride; a.dv_stride = p->dv_stride;
   a.B = p->B; a.H = p->H; a.scale = p->scale;

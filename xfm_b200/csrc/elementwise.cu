@@ -300,10 +300,10 @@ __global__ void dropout_apply_kernel(const void* __restrict__ x, int x_dtype, bf
   const float inv_keep = 1.0f / (1.0f - p);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     float4 v = ld4(x, x_dtype, 4 * i);
-    v.x = hash_uniform(seed, 4 * i) >= p ? v.x * inv_keep : 0.f;
-    v.y = hash_uniform(seed, 4 * i + 1) >= p ? v.y * inv_keep : 0.f;
-    v.z = hash_uniform(seed, 4 * i + 2) >= p ? v.z * inv_keep : 0.f;
-    v.w = hash_uniform(seed, 4 * i + 3) >= p ? v.w * inv_keep : 0.f;
+    v.x = drop_keep_idx(seed, 4 * i, p) ? v.x * inv_keep : 0.f;
+    v.y = drop_keep_idx(seed, 4 * i + 1, p) ? v.y * inv_keep : 0.f;
+    v.z = drop_keep_idx(seed, 4 * i + 2, p) ? v.z * inv_keep : 0.f;
+    v.w = drop_keep_idx(seed, 4 * i + 3, p) ? v.w * inv_keep : 0.f;
     st4(y, 0, 4 * i, v);
   }
 }

@@ -193,8 +193,8 @@ XFM_DEVINL void epilogue_block(const GemmArgs& g, const float* stage, int row_ba
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const uint64_t base = (uint64_t)(row_base + rr0 + 2 * i) * (uint64_t)g.N + (uint64_t)col;
-          v[i].x = (hash_uniform(g.dropout_seed, base) >= g.dropout_p) ? v[i].x * inv_keep : 0.f;
-          v[i].y = (hash_uniform(g.dropout_seed, base + 1) >= g.dropout_p) ? v[i].y * inv_keep : 0.f;
+          v[i].x = drop_keep_idx(g.dropout_seed, base, g.dropout_p) ? v[i].x * inv_keep : 0.f;
+          v[i].y = drop_keep_idx(g.dropout_seed, base + 1, g.dropout_p) ? v[i].y * inv_keep : 0.f;
         }
       }
       if (want_res) {

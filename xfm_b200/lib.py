@@ -225,7 +225,8 @@ def attention_bwd(dout, q, k, v, out, lse, B, H, Lq, Lk, scale, dq, dk, dv, *, B
                   rel_table=None, rel_window=0, rel_dtable=None, allow_tc=True):
     """Writes bf16 dq [B*Lq, ...], dk / dv [Bkv*Lk, ...] (views with row strides).  ds_dump: bf16 [B,H,Lq,ld] (mma.sync path:
     the caller reduces it into the bias-table gradient).  rel_table / rel_window / rel_dtable: closed-form relative-position
-    bias and its f32 gradient accumulator [(2W-1)^2+3, H] (tcgen05 path; needs ds_dump=None)."""
+    bias and (optionally) its f32 gradient accumulator [(2W-1)^2+3, H] (tcgen05 path; ds_dump + the caller's reduction is
+    the faster way to get the table gradient)."""
     Bkv = B if Bkv is None else Bkv
     p = AttnParams()
     _attn_common(p, q, k, v, B, H, Lq, Lk, Bkv, scale, bias, kmask, kv_index, dropout_p, dropout_seed)
