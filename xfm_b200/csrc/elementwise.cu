@@ -85,30 +85,81 @@ layernorm_fwd_kernel(const void* __restrict__ x, int x_dtype, const float* __res
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * w;  dw += sum dy * xhat;  db += sum dy.
 // Optional add_in (residual-path gradient) is added to dx.  dw / db are accumulated with one fp32 atomic per
 // column per CTA (each CTA first reduces its rows in registers + shared memory).
+//
+// One warp owns one row at a time, but its inputs (dy, x, add_in, the row's mean / rstd) are staged through a per-warp
+// two-slot shared-memory ring with cp.async: the loads of rows k+1 and k+2 are in flight while row k is reduced, at no
+// register cost (the dgamma / dbeta accumulators already take 48 registers).  Loading straight into registers left one
+// exposed DRAM round trip (two with add_in) per row and 17 % of DRAM bandwidth (ncu, profiles/r01_ln_bwd_*).
+XFM_DEVINL void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+XFM_DEVINL void cp_async8(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+XFM_DEVINL void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+XFM_DEVINL void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+XFM_DEVINL float4 lds4(const uint8_t* slot, int dtype, int c) {  // 4 elements at column c of a staged row
+  if (dtype == 1) return *(const float4*)(slot + (size_t)c * 4);
+  const uint2 u = *(const uint2*)(slot + (size_t)c * 2);
+  const float2 a = __bfloat1622float2(*(const __nv_bfloat162*)&u.x), b = __bfloat1622float2(*(const __nv_bfloat162*)&u.y);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
 template <int NV>
-__global__ void __launch_bounds__(LN_WARPS * 32, NV <= 6 ? 2 : 1)
+__global__ void __launch_bounds__(LN_WARPS * 32, 1)
 layernorm_bwd_kernel(const void* __restrict__ dy, int dy_dtype, const void* __restrict__ x, int x_dtype,
                      const float* __restrict__ stats, const float* __restrict__ w, const void* __restrict__ add_in,
                      int add_dtype, void* __restrict__ dx, int dx_dtype, float* __restrict__ dw, float* __restrict__ db,
-                     int M, int D, int rows_per_cta) {
-  extern __shared__ float red[];  // [2][LN_WARPS][D]
+                     int M, int D, int rows_per_cta, int nw) {   // nw: warps that own a staging ring (<= LN_WARPS)
+  extern __shared__ __align__(16) uint8_t ln_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int dy_b = D * (dy_dtype == 1 ? 4 : 2), x_b = D * (x_dtype == 1 ? 4 : 2);
+  const int add_b = add_in ? D * (add_dtype == 1 ? 4 : 2) : 0;
+  const int slot_b = dy_b + x_b + add_b + 16;   // + the row's (mean, rstd)
+  uint8_t* ring = ln_smem + (size_t)warp * 2 * slot_b;
+  const uint32_t ring_a = smem_u32(ring);
   float4 aw[NV], ab[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) aw[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   const int row0 = blockIdx.x * rows_per_cta;
-  const int row1 = min(M, row0 + rows_per_cta);
-  for (int row = row0 + warp; row < row1; row += LN_WARPS) {
+  const int row1 = (warp < nw) ? min(M, row0 + rows_per_cta) : 0;   // ring-less warps only join the final reduction
+
+  auto issue = [&](int row, int slot) {   // stage one row; always commits a group so the wait counts stay uniform
+    if (row < row1) {
+      const uint32_t dst = ring_a + slot * slot_b;
+      const uint8_t* s_dy = (const uint8_t*)dy + (size_t)row * dy_b;
+      const uint8_t* s_x = (const uint8_t*)x + (size_t)row * x_b;
+      for (int o = lane * 16; o < dy_b; o += 512) cp_async16(dst + o, s_dy + o);
+      for (int o = lane * 16; o < x_b; o += 512) cp_async16(dst + dy_b + o, s_x + o);
+      if (add_in) {
+        const uint8_t* s_a = (const uint8_t*)add_in + (size_t)row * add_b;
+        for (int o = lane * 16; o < add_b; o += 512) cp_async16(dst + dy_b + x_b + o, s_a + o);
+      }
+      if (lane == 0) cp_async8(dst + dy_b + x_b + add_b, stats + 2 * (size_t)row);
+    }
+    cp_async_commit();
+  };
+
+  int row = row0 + warp;
+  issue(row, 0);
+  issue(row + nw, 1);
+  for (int k = 0; row < row1; ++k, row += nw) {
+    cp_async_wait<1>();
+    __syncwarp();
+    const uint8_t* slot = ring + (k & 1) * slot_b;
+    const float2 mr = *(const float2*)(slot + dy_b + x_b + add_b);
+    const float mean = mr.x, rstd = mr.y;
     const size_t base = (size_t)row * D;
-    const float mean = stats[2 * row], rstd = stats[2 * row + 1];
     float4 g[NV], xh[NV];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = (i * 32 + lane) * 4;
       if (c < D) {
-        const float4 d = ld4(dy, dy_dtype, base + c);
-        const float4 xv = ld4(x, x_dtype, base + c);
+        const float4 d = lds4(slot, dy_dtype, c);
+        const float4 xv = lds4(slot + dy_b, x_dtype, c);
         const float4 ww = *(const float4*)(w + c);
         xh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
         g[i] = make_float4(d.x * ww.x, d.y * ww.y, d.z * ww.z, d.w * ww.w);
@@ -130,16 +181,20 @@ layernorm_bwd_kernel(const void* __restrict__ dy, int dy_dtype, const void* __re
         o.z = rstd * (g[i].z - s1 - xh[i].z * s2);
         o.w = rstd * (g[i].w - s1 - xh[i].w * s2);
         if (add_in) {
-          const float4 a = ld4(add_in, add_dtype, base + c);
+          const float4 a = lds4(slot + dy_b + x_b, add_dtype, c);
           o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
         }
         st4(dx, dx_dtype, base + c, o);
       }
     }
+    __syncwarp();                                   // every lane is done reading this slot
+    issue(row + 2 * nw, k & 1);                     // refill it with the row after next
   }
+  cp_async_wait<0>();
   if (!dw) return;
-  float* rw = red;
-  float* rb = red + LN_WARPS * D;
+  __syncthreads();                                   // the rings are dead: reuse shared memory for the cross-warp reduction
+  float* rw = (float*)ln_smem;
+  float* rb = rw + LN_WARPS * D;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = (i * 32 + lane) * 4;
@@ -610,18 +665,36 @@ int layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, cons
                   const void* add_in, int add_dtype, void* dx, int dx_dtype, float* dw, float* db, int M, int D,
                   cudaStream_t s) {
   if (ln_check(D)) return XFM_ERR_BAD_ARG;
+  if (D & 7) {
+    set_error("layernorm_bwd: feature dim %d must be a multiple of 8 (16-byte cp.async rows)", D);
+    return XFM_ERR_BAD_ARG;
+  }
   if (M <= 0) return 0;
-  const int rpc = rows_per_cta_for(M);
+  // one CTA per SM (the staging rings take ~100-150 KB), >= 2 rows per warp so the ring actually pipelines
+  int ctas = num_sms();
+  int rpc = (M + ctas - 1) / ctas;
+  rpc = ((rpc + LN_WARPS - 1) / LN_WARPS) * LN_WARPS;
+  if (rpc < 2 * LN_WARPS) rpc = 2 * LN_WARPS;
   const int grid = (M + rpc - 1) / rpc;
-  const size_t smem = dw ? (size_t)2 * LN_WARPS * D * sizeof(float) : 0;
+  const size_t slot = (size_t)D * ((dy_dtype == 1 ? 4 : 2) + (x_dtype == 1 ? 4 : 2) + (add_in ? (add_dtype == 1 ? 4 : 2) : 0)) + 16;
+  int nw = LN_WARPS;   // wide fp32 rows: fewer warps get a staging ring so the rings fit shared memory
+  while (nw > 1 && (size_t)nw * 2 * slot > 200 * 1024) --nw;
+  size_t smem = (size_t)nw * 2 * slot;
+  const size_t red = (size_t)2 * LN_WARPS * D * sizeof(float);
+  if (smem < red) smem = red;
+  if (smem > 220 * 1024) {
+    set_error("layernorm_bwd: D=%d needs %zu bytes of shared memory", D, smem);
+    return XFM_ERR_BAD_ARG;
+  }
   LN_DISPATCH(D, {
-    static bool attr = false;  // one per instantiation
-    if (!attr) {
-      cudaFuncSetAttribute(layernorm_bwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * LN_WARPS * NV * 128 * 4);
-      attr = true;
+    static size_t attr = 0;  // one per instantiation
+    if (smem > attr) {
+      cudaError_t e = cudaFuncSetAttribute(layernorm_bwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      attr = smem;
     }
     layernorm_bwd_kernel<NV><<<grid, LN_WARPS * 32, smem, s>>>(dy, dy_dtype, x, x_dtype, stats, w, add_in, add_dtype, dx, dx_dtype,
-                                                               dw, db, M, D, rpc);
+                                                               dw, db, M, D, rpc, nw);
   });
   LAUNCH_END();
 }
