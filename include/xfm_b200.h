@@ -166,7 +166,9 @@ int xfm_roberta_embed_bwd(const float* dpre, const int64_t* ids, const int32_t* 
 
 /* K8/K9 — patch-embed im2col (beit2.py:229), token assembly with mask-token blend + CLS (+ abs pos) (beit2.py:438-449),
  * mean-pool pseudo-CLS (beit2.py:456-466) and their backward. */
-int xfm_im2col(const float* image, void* out_bf16, int B, int C, int H, int W, int P, float pre_mul, void* stream);
+/* pre_mul: null, or a DEVICE scalar m: pixels become x * m / 127.5 - 1 before the cast (model_vqkd.py:125-131; m is the
+ * result of the reference's data-dependent `if data.max() <= 1` rule, evaluated on the device). */
+int xfm_im2col(const float* image, void* out_bf16, int B, int C, int H, int W, int P, const float* pre_mul, void* stream);
 int xfm_assemble_tokens(const float* patch, const float* cls, const float* mask_token, const uint8_t* mask, const float* pos,
                         float* x, int B, int np, int D, void* stream);
 int xfm_assemble_tokens_bwd(const float* dx, const uint8_t* mask, void* dpatch_bf16, float* dcls, float* dmask_token, int B,

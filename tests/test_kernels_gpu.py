@@ -183,7 +183,7 @@ def test_patch_pipeline(lib):
     assert rel_err(dpatch.view(B, npatch, D), d3[:, 1:] * (1 - w)) < 5e-3
     # VQ-KD pre-processing folded into im2col
     img01 = torch.rand(B, 3, res, res, generator=g)
-    c2 = lib.im2col(img01.cuda(), P, pre_mul=255.0)
+    c2 = lib.im2col(img01.cuda(), P, pre_mul=torch.tensor([255.0], device="cuda"))
     ref2 = F.unfold(O.vqkd_preprocess(img01), P, stride=P).transpose(1, 2).reshape(-1, 3 * P * P)
     assert rel_err(c2, ref2) < 5e-3
 

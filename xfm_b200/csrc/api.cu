@@ -96,7 +96,7 @@ int xfm_roberta_embed_bwd(const float* dpre, const int64_t* ids, const int32_t* 
                           float* dtype0, int rows, int D, int pad_id, void* stream) {
   return roberta_embed_bwd(dpre, ids, pos_ids, dword, dpos, dtype0, rows, D, pad_id, ST);
 }
-int xfm_im2col(const float* image, void* out, int B, int C, int H, int W, int P, float pre_mul, void* stream) {
+int xfm_im2col(const float* image, void* out, int B, int C, int H, int W, int P, const float* pre_mul, void* stream) {
   return im2col(image, BF(out), B, C, H, W, P, pre_mul, ST);
 }
 int xfm_assemble_tokens(const float* patch, const float* cls, const float* mask_token, const uint8_t* mask, const float* pos,

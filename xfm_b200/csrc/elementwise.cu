@@ -463,10 +463,11 @@ roberta_embed_bwd_kernel(const float* __restrict__ dpre, const int64_t* __restri
 
 // -------------------------------------------------------------------------------- ViT patch pipeline
 // im2col for the 16x16 stride-16 conv (beit2.py:229): out[b*np + p, c*P*P + py*P + px] = image[b, c, gy*P+py, gx*P+px].
-// `pre` applies the VQ-KD pre-processing x * mul / 127.5 - 1 (model_vqkd.py:125-131) when pre_mul != 0.
+// With pre_mul_ptr (a device scalar m) the VQ-KD pre-processing x * m / 127.5 - 1 (model_vqkd.py:125-131) is applied.
 __global__ void __launch_bounds__(256)
 im2col_kernel(const float* __restrict__ img, bf16* __restrict__ out, int B, int C, int H, int W, int P,
-              float pre_mul) {
+              const float* __restrict__ pre_mul_ptr) {
+  const float pre_mul = pre_mul_ptr ? __ldg(pre_mul_ptr) : 0.f;
   const int gw = W / P, gh = H / P;
   const int K = C * P * P;
   const size_t total4 = (size_t)B * gh * gw * K / 4;
@@ -786,7 +787,7 @@ int roberta_embed_bwd(const float* dpre, const int64_t* ids, const int32_t* pos_
   LAUNCH_END();
 }
 
-int im2col(const float* img, bf16* out, int B, int C, int H, int W, int P, float pre_mul, cudaStream_t s) {
+int im2col(const float* img, bf16* out, int B, int C, int H, int W, int P, const float* pre_mul, cudaStream_t s) {
   if (P % 4 || H % P || W % P) { set_error("im2col: bad geometry"); return XFM_ERR_BAD_ARG; }
   const size_t n4 = (size_t)B * C * H * W / 4;
   im2col_kernel<<<grid_1d(n4, 256), 256, 0, s>>>(img, out, B, C, H, W, P, pre_mul);

@@ -43,7 +43,7 @@ int roberta_embed_fwd(const int64_t* ids, const float* word, const float* pos, c
                       int pad_id, float eps, cudaStream_t s);
 int roberta_embed_bwd(const float* dpre, const int64_t* ids, const int32_t* pos_ids, float* dword, float* dpos,
                       float* dtype0, int rows, int D, int pad_id, cudaStream_t s);
-int im2col(const float* img, bf16_t* out, int B, int C, int H, int W, int P, float pre_mul, cudaStream_t s);
+int im2col(const float* img, bf16_t* out, int B, int C, int H, int W, int P, const float* pre_mul, cudaStream_t s);
 int assemble_tokens(const float* patch, const float* cls, const float* mask_token, const uint8_t* mask, const float* pos,
                     float* x, int B, int np, int D, cudaStream_t s);
 int assemble_tokens_bwd(const float* dx, const uint8_t* mask, bf16_t* dpatch, float* dcls, float* dmask_token, int B, int np,

@@ -201,7 +201,7 @@ class VisionEncoder:
         gm, fp = self.gmap[i], self.fp
         return lambda k: fp.grad(gm[k])
 
-    def forward(self, image, mask_u8=None, train=False, save=True, pre_mul=0.0, pool=True):
+    def forward(self, image, mask_u8=None, train=False, save=True, pre_mul=None, pool=True):
         """image f32 [B,3,R,R] -> (y32 [B,N,D] f32, y16 bf16 same shape, state).  pool=False (tokenizer) leaves
         token 0 un-pooled."""
         if self.w is None:
@@ -365,7 +365,8 @@ class RobertaStack:
 def csr_inverse(kv_index, Bkv):
     """CSR inverse of a sample -> K/V row map (int32 device tensors): rows of kv_samples grouped by K/V row."""
     order = torch.argsort(kv_index.long(), stable=True).to(torch.int32)
-    counts = torch.bincount(kv_index.long(), minlength=Bkv)
+    counts = torch.zeros(Bkv, dtype=torch.int64, device=kv_index.device)  # bincount would sync to size its output
+    counts.scatter_add_(0, kv_index.long(), torch.ones_like(kv_index, dtype=torch.int64))
     offsets = torch.zeros(Bkv + 1, dtype=torch.int32, device=kv_index.device)
     offsets[1:] = torch.cumsum(counts, 0).to(torch.int32)
     return offsets, order

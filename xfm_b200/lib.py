@@ -344,11 +344,13 @@ def roberta_embed_bwd(dpre, ids, pos_ids, dword, dpos, dtype0, pad_id):
                                       stream_ptr()), "xfm_roberta_embed_bwd")
 
 
-def im2col(image, P, pre_mul=0.0):
+def im2col(image, P, pre_mul=None):
+    """pre_mul: None, or a 1-element f32 DEVICE tensor m: pixels become x * m / 127.5 - 1 (model_vqkd.py:125-131)."""
     B, Cc, H, W = image.shape
     assert image.dtype == torch.float32 and image.is_contiguous()
+    assert pre_mul is None or (pre_mul.dtype == torch.float32 and pre_mul.is_cuda and pre_mul.numel() == 1)
     out = torch.empty((B * (H // P) * (W // P), Cc * P * P), dtype=torch.bfloat16, device=image.device)
-    check(lib().xfm_im2col(_p(image), _p(out), B, Cc, H, W, P, C.c_float(pre_mul), stream_ptr()), "xfm_im2col")
+    check(lib().xfm_im2col(_p(image), _p(out), B, Cc, H, W, P, _p(pre_mul), stream_ptr()), "xfm_im2col")
     return out
 
 

@@ -403,7 +403,9 @@ class XFMBase(nn.Module):
                 rows = torch.from_numpy(__import__("numpy").flatnonzero(m.numpy()).astype("int64"))
             else:
                 m, rows = sample_batch(self._sampler, B)
-            mask_dev = m.to(image.device, non_blocking=True)
+            # pinned staging: a pageable source would make the "non_blocking" copy synchronise with the device
+            mask_dev = m.pin_memory().to(image.device, non_blocking=True)
+            rows = rows.pin_memory().to(image.device, non_blocking=True)
         model = self
 
         class Impl:
@@ -630,7 +632,8 @@ class XFMBase(nn.Module):
         kmask = E.RobertaStack.additive_mask(text_atts.index_select(0, txt_index))
         img16, t16 = _twin(image_embeds), _twin(text_embeds)
         need_dtext = not is_pretrain
-        labels = torch.cat([torch.ones(B, dtype=torch.long), torch.zeros(2 * B, dtype=torch.long)]).to(image_embeds.device)
+        labels = torch.zeros(3 * B, dtype=torch.long, device=image_embeds.device)
+        labels[:B] = 1
 
         class Impl:
             def fwd(self, ctx, img, txt):
@@ -726,7 +729,9 @@ class XFMBase(nn.Module):
         self._prep()
         fp, vq = self.flat, self._vq
         B = image.shape[0]
-        pre_mul = 255.0 if float(image.max()) <= 1.0 else 1.0  # model_vqkd.py:125-131 (same host branch as the reference)
+        # model_vqkd.py:125-131 `if data.max() <= 1: data *= 255`: same data-dependent rule, decided on the device (the
+        # reference's host branch costs a device->host sync per step)
+        pre_mul = torch.where(image.max() <= 1.0, 255.0, 1.0).to(torch.float32).reshape(1)
         _, y16, _ = vq.forward(image, train=False, save=False, pre_mul=pre_mul, pool=False)
         N, D = vq.N, vq.D
         t = L.gemm(y16.view(B * N, D), fp.view16("vqkd.encode_task_layer.0.weight"),
