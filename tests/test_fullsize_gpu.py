@@ -1,0 +1,126 @@
+"""Full-size (BASELINE configs[1]: 96 pairs/GPU, 197 image tokens, 40 text tokens, D=768) checks of the hot kernels through
+size-independent properties and a torch fp32/bf16 reference where one fits in seconds."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+B, H, N, D, F = 96, 12, 197, 768, 3072
+M = B * N
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from xfm_b200 import lib as L
+    L.lib()
+    return L
+
+
+def G(seed):
+    return torch.Generator(device="cuda").manual_seed(seed)
+
+
+def test_gemm_full_size_fused_epilogues(lib):
+    """fc1 (bias + GELU(erf) + saved pre-activation) and the LayerScale residual projection at M = 18912, against torch."""
+    g = G(1)
+    x = (torch.randn(M, D, device="cuda", generator=g) * 0.5).bfloat16()
+    w = (torch.randn(F, D, device="cuda", generator=g) * 0.03).bfloat16()
+    b = torch.randn(F, device="cuda", generator=g) * 0.1
+    pre = torch.empty(M, F, device="cuda", dtype=torch.bfloat16)
+    y = lib.gemm(x, w, bias=b, act=1, aux_out=pre)
+    ref_pre = x.float() @ w.float().t() + b
+    ref = torch.nn.functional.gelu(ref_pre)
+    assert float((pre.float() - ref_pre).abs().max()) < 2e-2 * float(ref_pre.abs().max())
+    assert float((y.float() - ref).abs().max()) < 2e-2 * float(ref.abs().max())
+    # linearity in A: gemm(2x) - 2 gemm(x) = 0 up to bf16 rounding of the operands (exact: scaling by 2 is exact in bf16)
+    y1 = lib.gemm(x, w, out_dtype=torch.float32)
+    y2 = lib.gemm((x.float() * 2).bfloat16(), w, out_dtype=torch.float32)
+    assert torch.equal(y2, 2 * y1)
+    # LayerScale + residual epilogue in fp32
+    res = torch.randn(M, D, device="cuda", generator=g)
+    w2 = (torch.randn(D, D, device="cuda", generator=g) * 0.03).bfloat16()
+    gam = torch.randn(D, device="cuda", generator=g) * 0.1
+    out = lib.gemm(x, w2, col_scale=gam, residual=res, out_dtype=torch.float32)
+    ref2 = res + gam * (x.float() @ w2.float().t())
+    assert float((out - ref2).abs().max()) < 1e-3 * float(ref2.abs().max()) + 1e-3
+    # wgrad: split-K fp32 accumulation equals the unsplit product
+    dy = (torch.randn(M, D, device="cuda", generator=g) * 0.1).bfloat16()
+    a1 = torch.zeros(D, D, device="cuda")
+    a8 = torch.zeros(D, D, device="cuda")
+    lib.gemm(dy, x, a_t=True, b_t=True, out=a1, accumulate=True, split_k=1)
+    lib.gemm(dy, x, a_t=True, b_t=True, out=a8, accumulate=True, split_k=8)
+    ref3 = dy.float().t() @ x.float()
+    assert float((a1 - ref3).abs().max()) < 2e-3 * float(ref3.abs().max())
+    assert float((a8 - a1).abs().max()) < 1e-4 * float(ref3.abs().max())
+
+
+def test_vit_attention_full_size_properties(lib):
+    """tcgen05 attention at B=96: rows of P sum to 1 (V = ones -> output ones), lse = logsumexp, forward equals the
+    mma.sync kernel, and the backward satisfies sum_j dS_ij = 0 (dQ.q - dK.k balance: sum(dq*q) = sum(dk*k))."""
+    g = G(2)
+    qkv = (torch.randn(M, 3 * D, device="cuda", generator=g) * 0.6).bfloat16()
+    table = torch.randn(732, H, device="cuda", generator=g)
+    q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
+    ones = qkv.clone()
+    ones[:, 2 * D:] = 1.0
+    o1, _ = lib.attention_fwd(ones[:, :D], ones[:, D:2 * D], ones[:, 2 * D:], B, H, N, N, 0.125, rel_table=table, rel_window=14)
+    assert float((o1.float() - 1).abs().max()) < 1e-2
+    out, lse = lib.attention_fwd(q, k, v, B, H, N, N, 0.125, rel_table=table, rel_window=14)
+    from xfm_b200.encoders import closed_form_rel_index
+    idx = closed_form_rel_index(14).cuda()
+    bias = table[idx.view(-1)].view(N, N, H).permute(2, 0, 1).contiguous()
+    ld = (N + 7) // 8 * 8
+    bias_p = torch.zeros(H, N, ld, device="cuda")
+    bias_p[:, :, :N] = bias
+    out2, lse2 = lib.attention_fwd(q, k, v, B, H, N, N, 0.125, bias=bias_p, allow_tc=False)
+    assert float((out.float() - out2.float()).abs().max()) < 2e-2
+    assert float((lse - lse2).abs().max()) < 2e-3
+    # two samples against torch
+    f = qkv[:2 * N].float().view(2, N, 3, H, 64).permute(2, 0, 3, 1, 4)
+    s = (f[0] * 0.125) @ f[1].transpose(-1, -2) + bias
+    assert float((lse[:2] - torch.logsumexp(s, -1)).abs().max()) < 2e-3
+    dout = (torch.randn(M, D, device="cuda", generator=g)).bfloat16()
+    dqkv = torch.empty_like(qkv)
+    lib.attention_bwd(dout, q, k, v, out, lse, B, H, N, N, 0.125, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], rel_table=table,
+                      rel_window=14)
+    # dS = P o (dP - delta) has zero row sums, hence sum(dQ o Q) = sum_ij dS_ij s_ij scale = sum(dK o K)
+    a = float((dqkv[:, :D].float() * q.float()).sum())
+    b_ = float((dqkv[:, D:2 * D].float() * k.float()).sum())
+    assert abs(a - b_) < 2e-2 * max(1.0, abs(a))
+    assert torch.isfinite(dqkv.float()).all()
+
+
+def test_layernorm_full_size(lib):
+    g = G(3)
+    x = torch.randn(M, D, device="cuda", generator=g) * 2 + 0.5
+    w = torch.randn(D, device="cuda", generator=g)
+    b = torch.randn(D, device="cuda", generator=g)
+    y, stats, y32 = lib.layernorm_fwd(x, w, b, 1e-6, want_f32_copy=True)
+    ref = torch.nn.functional.layer_norm(x, (D,), w, b, 1e-6)
+    assert float((y32 - ref).abs().max()) < 1e-4
+    dy = torch.randn(M, D, device="cuda", generator=g).bfloat16()
+    add = torch.randn(M, D, device="cuda", generator=g)
+    dw, db = torch.zeros(D, device="cuda"), torch.zeros(D, device="cuda")
+    dx = lib.layernorm_bwd(dy, x, stats, w, dw, db, add_in=add)
+    xr = x.clone().requires_grad_(True)
+    wr, br = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    torch.nn.functional.layer_norm(xr, (D,), wr, br, 1e-6).backward(dy.float())
+    assert float((dx - (xr.grad + add)).abs().max()) < 1e-3
+    assert float((dw - wr.grad).abs().max()) < 2e-3 * float(wr.grad.abs().max())
+    assert float((db - br.grad).abs().max()) < 2e-3 * float(br.grad.abs().max())
+
+
+def test_vq_argmin_full_size_matches_fp64_argmin(lib):
+    """K15 at 96 x 196 rows x 8192 codes: ids equal the fp64 argmin wherever the fp32 winner's margin is not a rounding tie
+    (norm_ema_quantizer.py:152-162)."""
+    g = G(4)
+    z = torch.nn.functional.normalize(torch.randn(B * 196, 32, device="cuda", generator=g), dim=-1)
+    cb = torch.nn.functional.normalize(torch.randn(8192, 32, device="cuda", generator=g), dim=-1)
+    ids = lib.vq_argmin(z, cb)
+    d = (z.double() ** 2).sum(1, keepdim=True) + (cb.double() ** 2).sum(1) - 2 * z.double() @ cb.double().t()
+    best = d.argmin(1)
+    mism = ids != best
+    if mism.any():
+        gap = (d[mism, ids[mism]] - d[mism, best[mism]]).abs()
+        assert float(gap.max()) < 1e-6
+    assert float(mism.float().mean()) < 1e-3
