@@ -23,9 +23,13 @@ def wgrad(fp_grad, dy, x):
     """fp_grad[Nout, Kin] += dy[T, Nout]^T · x[T, Kin]  (fp32 accumulate; split-K when few output tiles)."""
     T = dy.shape[0]
     n_out, k_in = fp_grad.shape
-    tiles = ((n_out + 127) // 128) * ((k_in + 255) // 256)
     kb = (T + 63) // 64
-    split = max(1, min(296 // max(tiles, 1), kb // 8))
+    if n_out >= L.PAIR_MIN_M and k_in >= 256:   # CTA-pair kernel: 256 x 256 tiles over 74 SM pairs
+        tiles = ((n_out + 255) // 256) * ((k_in + 255) // 256)
+        split = max(1, min(148 // max(tiles, 1), kb // 8))
+    else:
+        tiles = ((n_out + 127) // 128) * ((k_in + 255) // 256)
+        split = max(1, min(296 // max(tiles, 1), kb // 8))
     L.gemm(dy, x, a_t=True, b_t=True, out=fp_grad, accumulate=True, split_k=max(split, 1))
 
 

@@ -409,6 +409,180 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   }
 }
 
+// ================================================================================================ CTA-pair GEMM
+// Same pipeline with tcgen05 cta_group::2: a cluster of two CTAs (one TPC) computes one 256 x 256 tile.  Each CTA stages
+// its own 128 rows of A and HALF of the B tile (128 of the 256 N rows), the leader's single thread issues M=256 MMAs that
+// read both halves, and each CTA's TMEM receives its 128 x 256 accumulator.  Per CTA a k-block costs 32 KB of L2->SM
+// traffic instead of 48 KB: the single-CTA kernel is capped by exactly that ingest rate (~47 B/clk/SM measured, tensor pipe
+// 49 % busy), which is where cuBLAS's 1.5 PF on these shapes comes from.
+constexpr int PAIR_STAGES = 5;
+constexpr int PAIR_STAGE_BYTES = 2 * 16384;  // A 128 x 64 + B 128 x 64 (bf16)
+constexpr int PAIR_SMEM_BYTES = PAIR_STAGES * PAIR_STAGE_BYTES + 8 * 32 * 34 * 4 + 256;
+
+template <int A_MN, int B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                         const GemmArgs g) {
+  constexpr int STAGES = PAIR_STAGES;
+  constexpr int BLOCK_N = 256;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if (smem_u32(smem) & 1023) __trap();
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * 16384;
+  float* epi_stage = (float*)(smem + STAGES * PAIR_STAGE_BYTES);
+  uint64_t* bars = (uint64_t*)(smem + STAGES * PAIR_STAGE_BYTES + 8 * 32 * 34 * 4);
+  uint64_t* full_bar = bars;                    // [STAGES]  used in the leader CTA only
+  uint64_t* empty_bar = bars + STAGES;          // [STAGES]  one per CTA, arrived by the leader's multicast commit
+  uint64_t* tmem_full = bars + 2 * STAGES;      // [2]       one per CTA, multicast commit
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2; // [2]       leader's copy: 2 x EPI_WARPS arrivals (peer arrives remotely)
+  uint32_t* tmem_ptr = (uint32_t*)(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();     // 0 = leader
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 2 * EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2sm(tmem_ptr, 512);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int num_m_pairs = (g.num_m_tiles + 1) / 2;
+  const int num_tiles = num_m_pairs * g.num_n_tiles * g.split_k;
+  const int kb_per_split = (g.kb_total + g.split_k - 1) / g.split_k;
+  const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = pair_id; t < num_tiles; t += num_pairs) {
+        const int ks = t % g.split_k;
+        const int rest = t / g.split_k;
+        const int m0 = ((rest % num_m_pairs) * 2 + (int)rank) * BLOCK_M;      // this CTA's 128 rows of the 256-row tile
+        const int n0 = (rest / num_m_pairs) * BLOCK_N + (int)rank * 128;      // this CTA's half of the tile's N range
+        const int kb0 = ks * kb_per_split;
+        const int kb1 = min(g.kb_total, kb0 + kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * PAIR_STAGE_BYTES);  // both CTAs' boxes land on this barrier
+          uint8_t* sa = smem_a + stage * 16384;
+          uint8_t* sb = smem_b + stage * 16384;
+          if (A_MN) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) tma_load_2d_2sm(sa + j * 8192, &map_a, &full_bar[stage], m0 + 64 * j, kb * BLOCK_K);
+          } else {
+            tma_load_2d_2sm(sa, &map_a, &full_bar[stage], kb * BLOCK_K, m0);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) tma_load_2d_2sm(sb + j * 8192, &map_b, &full_bar[stage], n0 + 64 * j, kb * BLOCK_K);
+          } else {
+            tma_load_2d_2sm(sb, &map_b, &full_bar[stage], kb * BLOCK_K, n0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(256, BLOCK_N, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int t = pair_id; t < num_tiles; t += num_pairs) {
+        const int ks = t % g.split_k;
+        const int kb0 = ks * kb_per_split;
+        const int kb1 = min(g.kb_total, kb0 + kb_per_split);
+        mbar_wait_relaxed(&tmem_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BLOCK_N);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + stage * 16384);
+          const uint32_t b_addr = smem_u32(smem_b + stage * 16384);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t a_desc = A_MN ? make_smem_desc(a_addr + k * 2048, 64 * BLOCK_K * 2, 1024)
+                                         : make_smem_desc(a_addr + k * 32, 16, 1024);
+            const uint64_t b_desc = B_MN ? make_smem_desc(b_addr + k * 2048, 64 * BLOCK_K * 2, 1024)
+                                         : make_smem_desc(b_addr + k * 32, 16, 1024);
+            umma_bf16_2sm(d_tmem, a_desc, b_desc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_2sm(&empty_bar[stage], 3);   // frees this stage in both CTAs
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm(&tmem_full[as], 3);        // accumulator ready in both CTAs
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int ew = warp - 2;
+    constexpr int C_PER_WARP = BLOCK_N / (2 * EPI_COLS);
+    const int c_begin = (ew >> 2) * C_PER_WARP;
+    float* stage = epi_stage + ew * EPI_WARP_FLOATS;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int t = pair_id; t < num_tiles; t += num_pairs) {
+      const int rest = t / g.split_k;
+      const int m0 = ((rest % num_m_pairs) * 2 + (int)rank) * BLOCK_M;
+      const int n0 = (rest / num_m_pairs) * BLOCK_N;
+      const int ks = t % g.split_k;
+      const int kb0 = ks * kb_per_split;
+      const int kb1 = min(g.kb_total, kb0 + kb_per_split);
+      mbar_wait_relaxed(&tmem_full[as], aphase);
+      tc_fence_after();
+      const int row_base = m0 + q * 32;
+      const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BLOCK_N);
+      const bool has_work = kb1 > kb0 && row_base < g.M;
+#pragma unroll 1
+      for (int c = c_begin; c < c_begin + C_PER_WARP; ++c) {
+        const int n = n0 + c * EPI_COLS;
+        if (n >= g.N) break;
+        const uint32_t taddr = t_base + c * EPI_COLS;
+        if (g.epi_mode == 0) epilogue_one<0>(g, stage, taddr, row_base, n, lane, has_work);
+        else if (g.epi_mode == 1) epilogue_one<1>(g, stage, taddr, row_base, n, lane, has_work);
+        else epilogue_one<2>(g, stage, taddr, row_base, n, lane, has_work);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(&tmem_empty[as]);
+        else mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[as]), 0));
+      }
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();   // neither CTA may exit (or free TMEM) while the other can still signal it or read its operands
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ host
 static int encode_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
                      uint32_t box_inner, uint32_t box_outer) {
@@ -455,6 +629,40 @@ static int launch_gemm(const xfm_gemm_params* p, const GemmArgs& g, cudaStream_t
   return (int)cudaGetLastError();
 }
 
+template <int A_MN, int B_MN>
+static int launch_gemm_pair(const xfm_gemm_params* p, const GemmArgs& g, cudaStream_t stream) {
+  CUtensorMap map_a, map_b;
+  int rc;
+  if (A_MN) rc = encode_2d(&map_a, p->A, p->M, p->K, p->lda, 64, BLOCK_K);
+  else rc = encode_2d(&map_a, p->A, p->K, p->M, p->lda, BLOCK_K, BLOCK_M);
+  if (rc) return rc;
+  if (B_MN) rc = encode_2d(&map_b, p->B, p->N, p->K, p->ldb, 64, BLOCK_K);
+  else rc = encode_2d(&map_b, p->B, p->K, p->N, p->ldb, BLOCK_K, 128);   // half of the 256-wide tile per CTA
+  if (rc) return rc;
+  auto kern = gemm_tcgen05_pair_kernel<A_MN, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const int num_tiles = ((g.num_m_tiles + 1) / 2) * g.num_n_tiles * g.split_k;
+  const int max_pairs = num_sms() / 2;
+  const int pairs = num_tiles < max_pairs ? num_tiles : max_pairs;
+  kern<<<2 * pairs, GEMM_THREADS, PAIR_SMEM_BYTES, stream>>>(map_a, map_b, g);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+static int dispatch_pair(const xfm_gemm_params* p, const GemmArgs& g, cudaStream_t s) {
+  if (p->a_mn_major) {
+    if (p->b_mn_major) return launch_gemm_pair<1, 1>(p, g, s);
+    return launch_gemm_pair<1, 0>(p, g, s);
+  }
+  if (p->b_mn_major) return launch_gemm_pair<0, 1>(p, g, s);
+  return launch_gemm_pair<0, 0>(p, g, s);
+}
+
 template <int BLOCK_N>
 static int dispatch_major(const xfm_gemm_params* p, const GemmArgs& g, cudaStream_t s) {
   if (p->a_mn_major) {
@@ -489,7 +697,7 @@ int gemm_bf16(const xfm_gemm_params* p, cudaStream_t stream) {
     set_error("gemm: act=2 (dgelu) needs aux_in");
     return XFM_ERR_BAD_ARG;
   }
-  int bn = p->block_n;
+  int bn = p->block_n == 512 ? 256 : p->block_n;
   if (bn == 0) {
     // Largest tile that still yields >= ~1 wave of CTAs; small problems fall to narrower tiles.
     const int mt = (p->M + BLOCK_M - 1) / BLOCK_M;
@@ -518,6 +726,10 @@ int gemm_bf16(const xfm_gemm_params* p, cudaStream_t stream) {
   const bool plain = p->c_dtype == 0 && !p->col_scale && !p->row_group_scale && !p->residual && !(p->dropout_p > 0.f);
   g.epi_mode = (plain && p->act <= 1) ? 0 : ((plain && p->act == 2 && !p->aux_out) ? 1 : 2);
   g.vec_ok = vec ? 1 : 0;
+  if (p->block_n == 512) {   // CTA-pair (cta_group::2) kernel: 256 x 256 tiles; num_n_tiles counted in 256-wide tiles
+    g.num_n_tiles = (p->N + 255) / 256;
+    return dispatch_pair(p, g, stream);
+  }
   switch (bn) {
     case 64: return dispatch_major<64>(p, g, stream);
     case 128: return dispatch_major<128>(p, g, stream);

@@ -14,6 +14,8 @@ LIB_PATH = os.path.join(_HERE, "libxfm_b200.so")
 _lib = None
 _inited_devices = set()
 gemm_profile = None  # set to a list to time every GEMM launch with CUDA events (bench.py)
+# block_n = 0 (auto) picks the CTA-pair (cta_group::2, 256 x 256 tiles) kernel for problems with at least this many rows
+PAIR_MIN_M = int(os.environ.get("XFM_GEMM_PAIR_MIN_M", "2048"))
 
 
 class GemmParams(C.Structure):
@@ -125,6 +127,8 @@ def gemm(a, b, *, a_t=False, b_t=False, out=None, out_dtype=torch.bfloat16, bias
     p.split_k = split_k
     p.accumulate = int(accumulate)
     p.act = act
+    if block_n == 0 and M >= PAIR_MIN_M and N >= 256:
+        block_n = 512
     p.block_n = block_n
     p.rows_per_group = rows_per_group
     if bias is not None:
