@@ -73,15 +73,15 @@ def test_tiny_vq_activations_losses_against_reference(golden_dir):
         out = _run(model, g, batch)
     nv, nt, nf = cfg["vision_depth"], cfg["text_layers"], cfg["fusion_layers"]
     vis, txt, fus = model._vis.collect, model._txt.collect, model._fus.collect
-    # call order: vision | text | fusion(3B ITM pass) | text(masked) | fusion(MLM) | vision(masked)
-    assert len(vis) == 2 * nv and len(txt) == 2 * nt and len(fus) == 2 * nf
+    # call order: vision | text | text(masked) | fusion(4B pass: 3B ITM rows + B MLM rows) | vision(masked)
+    assert len(vis) == 2 * nv and len(txt) == 2 * nt and len(fus) == nf
     B = g["B"]
     for i in range(nv):
         assert _maxabs(vis[i], g["acts"]["vision"][i]) <= 2e-2, ("vision", i)
         assert _maxabs(vis[nv + i], g["acts"]["vision_masked"][i]) <= 2e-2, ("vision_masked", i)
     for i in range(nt):
         assert _maxabs(txt[i], g["acts"]["text"][i]) <= 2e-2, ("text", i)
-    for i in range(nf):  # first B samples of the 3B pass are the positive pairs
+    for i in range(nf):  # first B samples of the fusion pass are the positive pairs
         assert _maxabs(fus[i][:B], g["acts"]["fusion_pos"][i]) <= 2e-2, ("fusion", i)
     for k, v in g["losses"].items():
         tol = 5e-3 if k == "loss_mim" else 1e-3
@@ -223,3 +223,24 @@ def test_build_mlp_head_matches_torch():
     assert float((xg.grad.cpu() - xr.grad).abs().max()) < 2e-2 * float(xr.grad.abs().max()) + 1e-5
     for (n, p), (_, q) in zip(head.named_parameters(), ref.named_parameters()):
         assert float((p.grad.cpu() - q.grad).abs().max()) < 3e-2 * float(q.grad.abs().max()) + 1e-5, n
+
+
+def test_fused_itm_mlm_pass_equals_separate_calls(golden_dir):
+    """model_pretrain's single 4B-sample fusion pass (get_matching_and_fuse_mlm_loss) against the reference call pattern
+    get_matching_loss + get_fuse_mlm_loss (xfm.py:749-802, 638-656): same losses, same parameter gradients."""
+    g = _load(golden_dir, "tiny_vq.pt")
+    res = {}
+    for fused in (True, False):
+        model, cfg = _build(g)
+        model.fuse_itm_mlm = fused
+        batch = _batch(g, cfg)
+        out = _run(model, g, batch)
+        (out["loss_itm"] + out["loss_mlm"]).backward()
+        res[fused] = (float(out["loss_itm"]), float(out["loss_mlm"]),
+                      {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None})
+    a, b = res[True], res[False]
+    assert abs(a[0] - b[0]) < 1e-5 and abs(a[1] - b[1]) < 1e-5, (a[:2], b[:2])
+    assert set(a[2]) == set(b[2])
+    for n in a[2]:
+        scale = max(float(b[2][n].abs().max()), 1e-8)
+        assert _maxabs(a[2][n], b[2][n]) <= 2e-2 * scale, n  # bf16 gradient tensors summed in a different grouping

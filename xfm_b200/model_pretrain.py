@@ -20,6 +20,7 @@ class XFM(XFMBase):
                             "aux": config.get("waux", 1.0)}
         self.do_image_mask = config.get("do_image_mask", True)
         self.use_mm_mim_loss = config.get("use_mm_mim_loss", True)
+        self.fuse_itm_mlm = config.get("fuse_itm_mlm", True)  # xfm_b200 only: ITM + MLM in one fusion-encoder pass
         self.min_temp = config.get("min_temp", 0.001)
         self.max_temp = config.get("max_temp", 0.5)
 
@@ -41,6 +42,14 @@ class XFM(XFMBase):
                 loss_itc = self.get_contrastive_loss(image_feat, text_feat)
                 if data_source in wmap:
                     loss_itc = loss_itc * wmap[data_source]
+            if ret_match_loss and ret_mlm_loss and self.fuse_itm_mlm:
+                # same two losses as the branches below, from one 4B-sample pass of the fusion encoder
+                loss_itm, loss_mlm = self.get_matching_and_fuse_mlm_loss(
+                    image_embeds, image_atts, image_feat, text_ids, text_atts, text_feat, text_ids_masked, masked_pos,
+                    masked_ids, text_embeds=text_embeds)
+                if data_source in wmap:
+                    loss_itm, loss_mlm = loss_itm * wmap[data_source], loss_mlm * wmap[data_source]
+                ret_match_loss = ret_mlm_loss = False
             if ret_match_loss:
                 loss_itm = self.get_matching_loss(image_embeds, image_atts, image_feat, text_ids, text_atts, text_feat,
                                                   text_embeds=text_embeds)

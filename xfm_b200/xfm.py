@@ -669,6 +669,83 @@ class XFMBase(nn.Module):
             return loss, impl.cross_pos
         return loss
 
+    def get_matching_and_fuse_mlm_loss(self, image_embeds, image_atts, image_feat, text_ids, text_atts, text_feat,
+                                       text_ids_masked, masked_pos, masked_ids, idx=None, text_embeds=None, is_pretrain=True):
+        """get_matching_loss (xfm.py:749-802) and get_fuse_mlm_loss (xfm.py:638-656) as ONE 4B-sample pass of the fusion
+        encoder: rows [0,B) positives, [B,2B) (image_neg, text), [2B,3B) (image, text_neg), [3B,4B) the masked-LM texts.  All
+        four groups attend to the same B images, so every layer's cross-attention K/V projection (and its backward) runs
+        once instead of twice and the text-side GEMMs see M = 4·B·L rows.  Per-sample arithmetic is unchanged; returns
+        (loss_itm, loss_mlm) equal to the two separate calls (tests/test_model_gpu.py)."""
+        assert text_embeds is not None and text_ids.dim() == 2
+        self._prep()
+        model = self
+        B, Ni, _ = image_embeds.shape
+        Lt = text_atts.shape[1]
+        dev = image_embeds.device
+        with torch.no_grad():
+            image_neg, text_neg = self.get_hard_negatives(image_feat, text_feat, idx=idx)
+        ar = torch.arange(B, device=dev)
+        txt_index = torch.cat([ar, ar, text_neg.long()])
+        kv_index = torch.cat([ar, image_neg.long(), ar, ar]).to(torch.int32)
+        kmask_mlm = E.RobertaStack.additive_mask(text_atts)
+        kmask = torch.cat([kmask_mlm.index_select(0, txt_index), kmask_mlm]).contiguous()
+        img16, t16 = _twin(image_embeds), _twin(text_embeds)
+        need_dtext = not is_pretrain
+        detach = self.detach_text_forMLM
+        itm_labels = torch.zeros(3 * B, dtype=torch.long, device=dev)
+        itm_labels[:B] = 1
+        rows = (torch.arange(B, device=dev).view(B, 1) * Lt + masked_pos).reshape(-1).contiguous() + 3 * B * Lt
+        mlm_labels = masked_ids.reshape(-1).contiguous()
+        head = self._mlm_fus
+
+        class Impl:
+            def fwd(self, ctx, img, txt):
+                D = t16.shape[-1]
+                drop = model._drop()
+                keep_text = self.save and not detach
+                hm, hm32, est = model._txt.embed(text_ids_masked, drop, save=keep_text)
+                hm, hm32, tst = model._txt.layers_fwd(hm, B, Lt, kmask_mlm, drop=drop, save=keep_text, h32=hm32)
+                tall = torch.empty((4 * B * Lt, D), dtype=torch.bfloat16, device=dev)
+                tall32 = torch.empty((4 * B * Lt, D), dtype=torch.float32, device=dev)
+                tall[:3 * B * Lt] = L.gather_rows(t16.reshape(B, Lt * D), txt_index).view(3 * B * Lt, D)
+                tall32[:3 * B * Lt] = L.gather_rows(txt.detach().float().reshape(B, Lt * D).contiguous(), txt_index).view(3 * B * Lt, D)
+                tall[3 * B * Lt:] = hm
+                tall32[3 * B * Lt:] = hm32
+                h, _, st = model._fusion_run(tall, 4 * B, Lt, kmask, img16, B, kv_index, self.save, text32=tall32)
+                x0 = E.cls_rows(h, 4 * B, Lt)[:3 * B]
+                logits, hst = model._itm.logits(x0, save=self.save)
+                loss_itm, count, lse = L.ce_fwd(logits, itm_labels, 2)
+                x = L.gather_rows(h, rows)
+                loss_mlm, mst = head.loss(x, mlm_labels)
+                if ctx is not None:
+                    ctx.st, ctx.hst, ctx.ce, ctx.mst, ctx.est, ctx.tst = st, hst, (logits, count, lse), mst, est, tst
+                return loss_itm.view(()), loss_mlm.view(())
+
+            def bwd(self, ctx, g_itm, g_mlm):
+                D = t16.shape[-1]
+                dh = torch.zeros((4 * B * Lt, D), dtype=torch.float32, device=dev)
+                if g_itm is not None:
+                    logits, count, lse = ctx.ce
+                    dlog = L.ce_bwd(logits, itm_labels, lse, count, _up(g_itm), 2, 8)
+                    model._itm.backward(ctx.hst, dlog, E.cls_rows(dh, 4 * B, Lt)[:3 * B])
+                if g_mlm is not None:
+                    dx = head.backward(ctx.mst, _up(g_mlm))
+                    L.scatter_add_rows_(dh, rows, dx)
+                need_any = need_dtext or not detach
+                d_tall, d_img = model._fusion_back(ctx.st, dh, B, Ni, need_any, kv_index)
+                d_txt = None
+                if need_dtext:
+                    d_txt = torch.zeros((B, Lt * D), dtype=torch.float32, device=dev)
+                    L.scatter_add_rows_(d_txt, txt_index, d_tall[:3 * B * Lt].reshape(3 * B, Lt * D).contiguous())
+                    d_txt = d_txt.view(B, Lt, D)
+                if not detach:
+                    d = model._txt.layers_bwd(ctx.tst, d_tall[3 * B * Lt:].contiguous(), need_dh=True)
+                    model._txt.embed_bwd(ctx.est, d)
+                ctx.st = ctx.hst = ctx.ce = ctx.mst = ctx.est = ctx.tst = None
+                return d_img, d_txt
+        impl = Impl()
+        return self._call(impl, image_embeds, text_embeds)
+
     # ------------------------------------------------------------------ MLM
     def _mlm(self, text_ids_masked, text_atts, image_embeds, masked_pos, masked_ids, fused):
         self._prep()
