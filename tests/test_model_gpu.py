@@ -243,4 +243,5 @@ def test_fused_itm_mlm_pass_equals_separate_calls(golden_dir):
     assert set(a[2]) == set(b[2])
     for n in a[2]:
         scale = max(float(b[2][n].abs().max()), 1e-8)
-        assert _maxabs(a[2][n], b[2][n]) <= 2e-2 * scale, n  # bf16 gradient tensors summed in a different grouping
+        # bf16 gradient tensors summed in a different grouping; key biases have a theoretically zero gradient (pure noise)
+        assert _maxabs(a[2][n], b[2][n]) <= 2e-2 * scale + 1e-5, n
