@@ -389,6 +389,49 @@ def test_vit_attention_tcgen05_backward(lib, B, H, ws, with_table):
         assert err < 2e-2 * max(1.0, float(table.grad.abs().max())), ("dtable", err, float(table.grad.abs().max()))
 
 
+def _cross_case(B, Bkv, H, g, kv_index):
+    Lq, Lk, D = 40, 197, H * 64
+    q2 = bf(torch.randn(B * Lq, D, generator=g))
+    kv2 = bf(torch.randn(Bkv * Lk, 2 * D, generator=g))
+    order = torch.argsort(kv_index.long(), stable=True).to(torch.int32)
+    offs = torch.zeros(Bkv + 1, dtype=torch.int32)
+    offs[1:] = torch.cumsum(torch.bincount(kv_index.long(), minlength=Bkv), 0).to(torch.int32)
+    return Lq, Lk, D, q2, kv2, order, offs
+
+
+@pytest.mark.parametrize("B,Bkv,H,pattern", [(8, 2, 2, "even"), (24, 6, 12, "random"), (14, 2, 3, "big_groups"), (6, 6, 2, "identity")])
+def test_cross_attention_tcgen05_forward(lib, B, Bkv, H, pattern):
+    """tcgen05 cross-attention (attention_xtc.cu): samples stacked per image (1..>GMAX samples per image) against torch and
+    against the mma.sync kernel; with dropout the two kernels must produce the same mask (same (seed, index) hash)."""
+    g = G(B * 31 + Bkv)
+    if pattern == "even":
+        kv_index = (torch.arange(B) % Bkv).to(torch.int32)
+    elif pattern == "identity":
+        kv_index = torch.arange(B, dtype=torch.int32)
+    elif pattern == "big_groups":
+        kv_index = torch.tensor([0] * 9 + [1] * 5, dtype=torch.int32)   # 9 > GMAX = 6: two chunks
+    else:
+        kv_index = torch.randint(0, Bkv, (B,), generator=g).to(torch.int32)
+        kv_index[:Bkv] = torch.arange(Bkv, dtype=torch.int32)
+    Lq, Lk, D, q2, kv2, order, offs = _cross_case(B, Bkv, H, g, kv_index)
+    qf = q2.float().view(B, Lq, H, 64).permute(0, 2, 1, 3)
+    kf = kv2.float()[:, :D].reshape(Bkv, Lk, H, 64).permute(0, 2, 1, 3)[kv_index.long()]
+    vf = kv2.float()[:, D:].reshape(Bkv, Lk, H, 64).permute(0, 2, 1, 3)[kv_index.long()]
+    s = (qf * 0.125) @ kf.transpose(-1, -2)
+    ref = (torch.softmax(s, -1) @ vf).permute(0, 2, 1, 3).reshape(B * Lq, D)
+    qd, kvd = q2.cuda(), kv2.cuda()
+    kw = dict(Bkv=Bkv, kv_index=kv_index.cuda(), kv_offsets=offs.cuda(), kv_samples=order.cuda())
+    out, lse = lib.attention_fwd(qd, kvd[:, :D], kvd[:, D:], B, H, Lq, Lk, 0.125, **kw)
+    out2, lse2 = lib.attention_fwd(qd, kvd[:, :D], kvd[:, D:], B, H, Lq, Lk, 0.125, allow_tc=False, **kw)
+    assert float((out.float().cpu() - ref).abs().max()) < 2e-2
+    assert float((lse.cpu() - torch.logsumexp(s, -1)).abs().max()) < 2e-3
+    assert float((out.float() - out2.float()).abs().max()) < 2e-2
+    od, _ = lib.attention_fwd(qd, kvd[:, :D], kvd[:, D:], B, H, Lq, Lk, 0.125, dropout_p=0.2, dropout_seed=11, **kw)
+    od2, _ = lib.attention_fwd(qd, kvd[:, :D], kvd[:, D:], B, H, Lq, Lk, 0.125, dropout_p=0.2, dropout_seed=11, allow_tc=False, **kw)
+    assert float((od.float() - od2.float()).abs().max()) < 3e-2
+    assert float((od.float() - out.float()).abs().max()) > 1e-2   # dropout did something
+
+
 def test_attention_dropout_is_consistent(lib):
     """Same (seed, index) mask in forward and both backward kernels: check dQ/dK/dV against autograd through the
     forward's own (recovered) mask."""

@@ -75,10 +75,11 @@ def attn_case(name, B, H, Lq, Lk, mode, Bkv=None, p=0.0, nbuf=3):
     def fwd(s):
         o, lse = L.attention_fwd(s["q"], s["k"], s["v"], B, H, Lq, Lk, 0.125, Bkv=Bkv, bias=s["bias"], kmask=s["kmask"],
                                  kv_index=s["kv_index"], dropout_p=p, dropout_seed=7, out=s["out"], rel_table=s["table"],
-                                 rel_window=14 if s["table"] is not None else 0, allow_tc=mode in ("vit_tc", "plain_tc"))
+                                 rel_window=14 if s["table"] is not None else 0, allow_tc=mode in ("vit_tc", "plain_tc", "cross"),
+                                 kv_offsets=s["offs"], kv_samples=s["order"])
         s["lse"] = lse
 
-    tc = mode in ("vit_tc", "plain_tc")
+    tc = mode in ("vit_tc", "plain_tc", "cross")
 
     def bwd(s):
         L.attention_bwd(s["dout"], s["q"], s["k"], s["v"], s["out"], s["lse"], B, H, Lq, Lk, 0.125, s["dq"], s["dk"], s["dv"],

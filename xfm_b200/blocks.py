@@ -128,7 +128,7 @@ def _attn_out_fwd(ctx, w, pre, resid, eps, drop, s, tag):
 
 
 def roberta_layer_fwd(h, w, Bt, Lt, H, eps, kmask, enc=None, Benc=0, Lenc=0, kv_index=None, drop=NO_DROP, save=True,
-                      h32=None):
+                      h32=None, kv_offsets=None, kv_samples=None):
     """h: bf16 [Bt*Lt, D] (h32: the same hidden state in f32, used as the residual when given).
     enc: bf16 [Benc*Lenc, Denc] image tokens (cross-attention) or None.  Returns (h_out bf16, h_out f32, saved)."""
     D = h.shape[1]
@@ -148,7 +148,7 @@ def roberta_layer_fwd(h, w, Bt, Lt, H, eps, kmask, enc=None, Benc=0, Lenc=0, kv_
         kvc = L.gemm(enc, w["c_kv_w16"], bias=w["c_kv_b"])
         seed_c = drop.next_seed() if drop.p_attn > 0 else 0
         cctx, clse = L.attention_fwd(qc, kvc[:, :D], kvc[:, D:], Bt, H, Lt, Lenc, scale, Bkv=Benc, kv_index=kv_index,
-                                     dropout_p=drop.p_attn, dropout_seed=seed_c)
+                                     dropout_p=drop.p_attn, dropout_seed=seed_c, kv_offsets=kv_offsets, kv_samples=kv_samples)
         h2, h2_32 = _attn_out_fwd(cctx, w, "c_", h1_32, eps, drop, s, "c")
         if save:
             s.qc, s.kvc, s.cctx, s.clse, s.seed_c, s.h2, s.enc = qc, kvc, cctx, clse, seed_c, h2, enc

@@ -525,6 +525,7 @@ static void fill_args(const xfm_attn_params* p, AttnArgs& a) {
 int attention_fwd(const xfm_attn_params* p, cudaStream_t s) {
   if (attn_check(p)) return XFM_ERR_BAD_ARG;
   if (p->allow_tc && vit_attention_tc_supported(p)) return vit_attention_fwd_tc(p, s);
+  if (p->allow_tc && cross_attention_tc_supported(p)) return cross_attention_fwd_tc(p, s);
   AttnArgs a;
   fill_args(p, a);
   const int LkP = (a.Lk + AT_TILE - 1) / AT_TILE * AT_TILE;

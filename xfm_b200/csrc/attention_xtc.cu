@@ -1,0 +1,370 @@
+// K4 — cross-attention (xroberta.py:223-226,243-284 called from :448-455) on tcgen05 + TMEM + TMA.
+//
+// Text queries attend to the image tokens of ONE image; several text samples share the same image (the ITM positives, the
+// hard negatives that re-use that image, the MLM pass: kv_index / its CSR inverse kv_offsets, kv_samples).  The samples of
+// one image are therefore STACKED along the query axis: up to GMAX samples x LQS (= 40) rows form the rows of two 128-row
+// query tiles (slot g -> tile g % 2, rows (g / 2) * LQS ..), and the image's K / V tile is loaded once for all of them.
+// Same pipeline as attention_tc.cu: warp 0 TMA, warp 1 single-thread tcgen05.mma (S = Q K^T into two TMEM score buffers,
+// O = P V into a third region), two softmax warpgroups (one per query tile, thread = query row).  No bias; dropout on the
+// probabilities uses the stateless (seed, (b, h, q, key)) hash shared with the mma.sync kernels, so forward and backward
+// kernels of either family regenerate the same mask.  Images referenced by more than GMAX samples are processed in
+// several chunks of GMAX.
+#include "common.cuh"
+#include "internal.h"
+
+namespace xfm {
+
+constexpr int XT_HD = 64;
+constexpr int XT_THREADS = 64 + 256;
+
+struct XAttnArgs {
+  bf16* out;
+  int64_t o_stride;
+  float* lse;                 // [B, H, LQS]
+  const int32_t* kv_offsets;  // [Bkv + 1]
+  const int32_t* kv_samples;  // [B] sample ids grouped by K/V row
+  int B, Bkv, H;
+  float scale, dropout_p;
+  uint64_t seed;
+  int items_per_cta;
+  // backward
+  const float* delta;         // [B, H, LQS]
+  bf16 *dq, *dk, *dv;
+  int64_t dq_stride, dk_stride, dv_stride;
+};
+
+template <int LQS_, int LK_, int GMAX_>
+struct XCfg {
+  static constexpr int LQS = LQS_, LK = LK_, GMAX = GMAX_;
+  static constexpr int PER_TILE = (GMAX + 1) / 2;            // sample slots per 128-row query tile
+  static_assert(PER_TILE * LQS <= 128, "slots of one tile must fit 128 rows");
+  static_assert((LQS * 128) % 1024 == 0, "a sample's rows must start on a swizzle-atom boundary (LQS multiple of 8)");
+  static constexpr int LPAD = (LK + 15) / 16 * 16;
+  static constexpr int NKB = (LPAD + 63) / 64;
+  static constexpr int Q_BYTES = 2 * 128 * 128;
+  static constexpr int KV_BYTES = LPAD * 128;
+  static constexpr int P_BYTES = NKB * 16384;
+  static constexpr int SMEM_FWD = Q_BYTES + 2 * KV_BYTES + 2 * P_BYTES + 128;
+  static constexpr int TMEM_O = 2 * LPAD;
+  static_assert(2 * LPAD + 64 <= 512, "TMEM");
+};
+
+XFM_DEVINL void xt_ld32(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld_32x32(taddr, r); }
+XFM_DEVINL void xt_ld16(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+XFM_DEVINL void xt_st_bf16x8(uint8_t* dst, const float (&p)[8]) {
+  uint4 u;
+  __nv_bfloat162 t0 = __floats2bfloat162_rn(p[0], p[1]), t1 = __floats2bfloat162_rn(p[2], p[3]);
+  __nv_bfloat162 t2 = __floats2bfloat162_rn(p[4], p[5]), t3 = __floats2bfloat162_rn(p[6], p[7]);
+  u.x = *(uint32_t*)&t0; u.y = *(uint32_t*)&t1; u.z = *(uint32_t*)&t2; u.w = *(uint32_t*)&t3;
+  *(uint4*)dst = u;
+}
+
+// One "unit" = (K/V row, head, chunk of <= GMAX samples).  Every role walks the same unit sequence.
+struct XUnit {
+  int r, h, first, ns;   // K/V row, head, index of the chunk's first entry in kv_samples, samples in the chunk
+};
+template <int GMAX>
+struct XWalker {
+  const XAttnArgs& a;
+  int it, it_end, chunk, nchunks, off0, cnt;
+  XFM_DEVINL XWalker(const XAttnArgs& a_, int it0, int it1) : a(a_), it(it0 - 1), it_end(it1), chunk(0), nchunks(0), off0(0), cnt(0) {}
+  XFM_DEVINL bool next(XUnit& u) {
+    ++chunk;
+    while (chunk >= nchunks) {
+      if (++it >= it_end) return false;
+      const int r = it % a.Bkv;
+      off0 = a.kv_offsets[r];
+      cnt = a.kv_offsets[r + 1] - off0;
+      nchunks = (cnt + GMAX - 1) / GMAX;
+      chunk = 0;
+    }
+    u.r = it % a.Bkv;
+    u.h = it / a.Bkv;
+    u.first = off0 + chunk * GMAX;
+    u.ns = min(GMAX, cnt - chunk * GMAX);
+    return true;
+  }
+};
+
+template <int LQS, int LK, int GMAX>
+__global__ void __launch_bounds__(XT_THREADS, 1)
+xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                    const __grid_constant__ CUtensorMap map_v, const XAttnArgs a) {
+  using Cfg = XCfg<LQS, LK, GMAX>;
+  constexpr int LPAD = Cfg::LPAD, PER_TILE = Cfg::PER_TILE;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if (smem_u32(smem) & 1023) __trap();
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Cfg::Q_BYTES;
+  uint8_t* sV = sK + Cfg::KV_BYTES;
+  uint8_t* sP = sV + Cfg::KV_BYTES;   // [2][P_BYTES]
+  uint64_t* bars = (uint64_t*)(sP + 2 * Cfg::P_BYTES);
+  uint64_t *qk_full = bars, *qk_empty = bars + 1, *v_full = bars + 2, *v_empty = bars + 3;
+  uint64_t *s_full = bars + 4, *p_full = bars + 6, *o_full = bars + 8, *o_empty = bars + 10;
+  uint32_t* tmem_ptr = (uint32_t*)(bars + 11);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < Cfg::Q_BYTES / 16; i += blockDim.x) ((uint4*)sQ)[i] = make_uint4(0u, 0u, 0u, 0u);  // unused slots stay finite
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_q);
+    tma_prefetch_desc(&map_k);
+    tma_prefetch_desc(&map_v);
+    mbar_init(qk_full, 1);
+    mbar_init(qk_empty, 1);
+    mbar_init(v_full, 1);
+    mbar_init(v_empty, 1);
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&s_full[t], 1);
+      mbar_init(&p_full[t], 4);
+      mbar_init(&o_full[t], 1);
+    }
+    mbar_init(o_empty, 4);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int n_items = a.Bkv * a.H;
+  const int item0 = blockIdx.x * a.items_per_cta;
+  const int item1 = min(n_items, item0 + a.items_per_cta);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      XWalker<GMAX> w(a, item0, item1);
+      XUnit u;
+      uint32_t ph = 0;
+      while (w.next(u)) {
+        mbar_wait_relaxed(qk_empty, ph ^ 1);
+        mbar_arrive_expect_tx(qk_full, u.ns * LQS * 128 + Cfg::KV_BYTES);
+        for (int g = 0; g < u.ns; ++g) {
+          const int b = a.kv_samples[u.first + g];
+          tma_load_2d(sQ + (g & 1) * 16384 + (g >> 1) * (LQS * 128), &map_q, qk_full, u.h * XT_HD, b * LQS);
+        }
+        tma_load_2d(sK, &map_k, qk_full, u.h * XT_HD, u.r * LK);
+        mbar_wait_relaxed(v_empty, ph ^ 1);
+        mbar_arrive_expect_tx(v_full, Cfg::KV_BYTES);
+        tma_load_2d(sV, &map_v, v_full, u.h * XT_HD, u.r * LK);
+        ph ^= 1;
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, LPAD, 0, 0);
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, XT_HD, 0, 1);
+      const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
+      XWalker<GMAX> w(a, item0, item1);
+      XUnit u;
+      uint32_t ph = 0;        // unit parity (qk_full / v_full / s_full / p_full / o_full[t] complete once per unit)
+      uint32_t oe = 1;        // o_empty wait parity (completes once per tile)
+      while (w.next(u)) {
+        mbar_wait(qk_full, ph);
+        tc_fence_after();
+        for (int t = 0; t < 2; ++t) {   // S buffers are free: the previous unit's p_full[t] was consumed below
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + t * LPAD, make_smem_desc(aQ + t * 16384 + k * 32, 16, 1024),
+                      make_smem_desc(aK + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+          umma_commit(&s_full[t]);
+        }
+        umma_commit(qk_empty);
+        mbar_wait(v_full, ph);
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(&p_full[t], ph);
+          mbar_wait(o_empty, oe);
+          oe ^= 1;
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < LPAD / 16; ++k)
+            umma_bf16(tmem_base + Cfg::TMEM_O, make_smem_desc(aP + t * Cfg::P_BYTES + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                      make_smem_desc(aV + k * 2048, 8192, 1024), idesc_o, k > 0 ? 1u : 0u);
+          umma_commit(&o_full[t]);
+        }
+        umma_commit(v_empty);
+        ph ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    const int t = (warp - 2) >> 2;             // query tile of this warpgroup
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;            // row inside the tile
+    const int slot_in_tile = r / LQS, q = r % LQS;
+    const int g = 2 * slot_in_tile + t;        // sample slot of this row
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const uint32_t t_s = lane_base + (uint32_t)(t * LPAD), t_o = lane_base + (uint32_t)Cfg::TMEM_O;
+    const float scale2 = a.scale * 1.4426950408889634f;
+    const float inv_keep = a.dropout_p > 0.f ? 1.0f / (1.0f - a.dropout_p) : 1.0f;
+    uint8_t* myP = sP + t * Cfg::P_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
+    const int sw = r & 7;
+    XWalker<GMAX> w(a, item0, item1);
+    XUnit u;
+    uint32_t ph = 0;
+    while (w.next(u)) {
+      const bool valid = slot_in_tile < PER_TILE && g < u.ns;
+      const bool wv = __any_sync(0xffffffffu, valid);   // tcgen05.ld is warp-collective: decide per warp, mask per thread
+      const int b = valid ? a.kv_samples[u.first + g] : 0;
+      const uint64_t drop_base = (((uint64_t)b * a.H + u.h) * LQS + q) * (uint64_t)LK;
+      mbar_wait(&s_full[t], ph);
+      tc_fence_after();
+      float m = -INFINITY, sum = 0.f;
+      if (wv) {
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int c0 = 0; c0 < LPAD; c0 += 32) {
+          uint32_t v[32];
+          if (c0 + 32 <= LPAD) xt_ld32(t_s + c0, v);
+          else xt_ld16(t_s + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (c0 + e < LK) m4[e & 3] = fmaxf(m4[e & 3], __uint_as_float(v[e]));
+        }
+        m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * scale2;   // scale2 > 0: max commutes with the scaling
+      }
+      float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c0 = 0; c0 < LPAD; c0 += 32) {
+        uint32_t v[32];
+        if (wv) {
+          if (c0 + 32 <= LPAD) xt_ld32(t_s + c0, v);
+          else xt_ld16(t_s + c0, v);
+          tmem_ld_wait();
+        }
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+          if (c0 + g8 * 8 < LPAD) {
+            float p[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int j = c0 + g8 * 8 + e;
+              float pe = 0.f;
+              if (valid && j < LK) {
+                pe = ex2_approx(fmaf(__uint_as_float(v[g8 * 8 + e]), scale2, -m));
+                s4[e & 3] += pe;
+                if (a.dropout_p > 0.f) pe = drop_keep_idx(a.seed, drop_base + j, a.dropout_p) ? pe * inv_keep : 0.f;
+              }
+              p[e] = pe;
+            }
+            const int col8 = c0 + g8 * 8;
+            xt_st_bf16x8(myP + (col8 >> 6) * 16384 + ((((col8 & 63) >> 3) ^ sw) << 4), p);
+          }
+        }
+      }
+      sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[t]);
+      mbar_wait(&o_full[t], ph);
+      tc_fence_after();
+      uint32_t o[2][32];
+      if (wv) {
+        tmem_ld_32x32(t_o, o[0]);
+        tmem_ld_32x32(t_o + 32, o[1]);
+        tmem_ld_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_empty);
+      if (valid) {
+        const float inv = 1.0f / sum;
+        bf16* orow = a.out + ((int64_t)b * LQS + q) * a.o_stride + u.h * XT_HD;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+          for (int e = 0; e < 32; e += 8) {
+            float vv[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) vv[k] = __uint_as_float(o[hh][e + k]) * inv;
+            xt_st_bf16x8((uint8_t*)(orow + hh * 32 + e), vv);
+          }
+        if (a.lse) a.lse[((int64_t)b * a.H + u.h) * LQS + q] = (m + log2f(sum)) * 0.6931471805599453f;
+      }
+      ph ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+static int xt_encode_rows(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint64_t ld_elems, uint32_t box_rows) {
+  auto fn = get_tensor_map_encoder();
+  if (!fn) return XFM_ERR_NO_DRIVER;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {XT_HD, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cross attention: cuTensorMapEncodeTiled failed: %d", (int)r);
+    return XFM_ERR_BAD_ARG;
+  }
+  return 0;
+}
+
+// Instantiated shape: 40 text tokens attending to 197 image tokens (BASELINE configs[1]), up to 6 samples per chunk.
+bool cross_attention_tc_supported(const xfm_attn_params* p) {
+  return p->head_dim == XT_HD && p->Lq == 40 && p->Lk == 197 && !p->kmask && !p->bias && p->kv_offsets && p->kv_samples &&
+         p->Bkv > 0 && ((uintptr_t)p->q & 15) == 0 && ((uintptr_t)p->k & 15) == 0 && ((uintptr_t)p->v & 15) == 0 &&
+         ((p->q_stride | p->k_stride | p->v_stride | p->o_stride) & 7) == 0;
+}
+
+static void xt_fill(const xfm_attn_params* p, XAttnArgs& a) {
+  a.out = (bf16*)p->out; a.o_stride = p->o_stride; a.lse = p->lse;
+  a.kv_offsets = p->kv_offsets; a.kv_samples = p->kv_samples;
+  a.B = p->B; a.Bkv = p->Bkv; a.H = p->H; a.scale = p->scale; a.dropout_p = p->dropout_p; a.seed = p->dropout_seed;
+  a.delta = p->delta;
+  a.dq = (bf16*)p->dq; a.dk = (bf16*)p->dk; a.dv = (bf16*)p->dv;
+  a.dq_stride = p->dq_stride; a.dk_stride = p->dk_stride; a.dv_stride = p->dv_stride;
+  const int n_items = a.Bkv * a.H;
+  const int ctas = n_items < num_sms() ? n_items : num_sms();
+  a.items_per_cta = (n_items + ctas - 1) / ctas;
+}
+
+int cross_attention_fwd_tc(const xfm_attn_params* p, cudaStream_t s) {
+  constexpr int LQS = 40, LK = 197, GMAX = 6;
+  using Cfg = XCfg<LQS, LK, GMAX>;
+  XAttnArgs a;
+  xt_fill(p, a);
+  const uint64_t cols = (uint64_t)a.H * XT_HD;
+  CUtensorMap mq, mk, mv;
+  int rc = xt_encode_rows(&mq, p->q, cols, (uint64_t)a.B * LQS, p->q_stride, LQS);
+  if (!rc) rc = xt_encode_rows(&mk, p->k, cols, (uint64_t)a.Bkv * LK, p->k_stride, Cfg::LPAD);
+  if (!rc) rc = xt_encode_rows(&mv, p->v, cols, (uint64_t)a.Bkv * LK, p->v_stride, Cfg::LPAD);
+  if (rc) return rc;
+  auto kern = xattn_fwd_tc_kernel<LQS, LK, GMAX>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_FWD);
+    if (e != cudaSuccess) return (int)e;
+    attr = true;
+  }
+  const int n_items = a.Bkv * a.H;
+  const int grid = (n_items + a.items_per_cta - 1) / a.items_per_cta;
+  kern<<<grid, XT_THREADS, Cfg::SMEM_FWD, s>>>(mq, mk, mv, a);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+}  // namespace xfm

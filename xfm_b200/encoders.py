@@ -343,9 +343,17 @@ class RobertaStack:
             self.refresh()
         st = State()
         st.layers, st.Bt, st.Lt, st.kmask, st.Benc, st.Lenc, st.kv_index = [], Bt, Lt, kmask, Benc, Lenc, kv_index
+        st.kv_offsets = st.kv_samples = None
+        if enc is not None:  # CSR inverse of the sample -> image map: the tcgen05 cross-attention kernels stack an image's samples
+            if kv_index is None:
+                st.kv_offsets = torch.arange(Benc + 1, dtype=torch.int32, device=h.device)
+                st.kv_samples = torch.arange(Bt, dtype=torch.int32, device=h.device)
+            else:
+                st.kv_offsets, st.kv_samples = csr_inverse(kv_index, Benc)
         for i in range(self.layers):
             h, h32, s = BK.roberta_layer_fwd(h, self.w[i], Bt, Lt, self.H, self.eps, kmask, enc=enc, Benc=Benc, Lenc=Lenc,
-                                             kv_index=kv_index, drop=drop, save=save, h32=h32)
+                                             kv_index=kv_index, drop=drop, save=save, h32=h32, kv_offsets=st.kv_offsets,
+                                             kv_samples=st.kv_samples)
             st.layers.append(s)
             if self.collect is not None:
                 self.collect.append(h32.view(Bt, Lt, -1).clone())
@@ -353,6 +361,8 @@ class RobertaStack:
 
     def layers_bwd(self, st, dh, d_enc=None, need_dh=True, kv_offsets=None, kv_samples=None):
         """dh: bf16 / f32 [Bt*Lt, D].  d_enc: f32 [Benc*Lenc, Denc] accumulator (cross-attention K/V input gradient)."""
+        if kv_samples is None and st.kv_index is not None:
+            kv_offsets, kv_samples = st.kv_offsets, st.kv_samples
         for i in reversed(range(self.layers)):
             last = i == 0
             dh = BK.roberta_layer_bwd(dh, st.layers[i], self.w[i], self._g(i), st.Bt, st.Lt, self.H, st.kmask, Benc=st.Benc,

@@ -204,7 +204,7 @@ def _attn_common(p, q, k, v, B, H, Lq, Lk, Bkv, scale, bias, kmask, kv_index, dr
 
 
 def attention_fwd(q, k, v, B, H, Lq, Lk, scale, *, Bkv=None, bias=None, kmask=None, kv_index=None, dropout_p=0.0,
-                  dropout_seed=0, out=None, rel_table=None, rel_window=0, allow_tc=True):
+                  dropout_seed=0, out=None, rel_table=None, rel_window=0, allow_tc=True, kv_offsets=None, kv_samples=None):
     """q: bf16 [B*Lq, >=H*64] view; k, v: bf16 [Bkv*Lk, ...] views.  Returns (out bf16 [B*Lq, H*64], lse f32 [B,H,Lq]).
     rel_table / rel_window: BEiT relative-position table [(2W-1)^2+3, H] f32 whose closed-form gather equals `bias`
     (tcgen05 path); allow_tc=False forces the mma.sync kernel."""
@@ -220,6 +220,10 @@ def attention_fwd(q, k, v, B, H, Lq, Lk, scale, *, Bkv=None, bias=None, kmask=No
         assert rel_table.dtype == torch.float32 and rel_table.is_contiguous() and rel_table.shape[1] == H
         assert rel_table.shape[0] == (2 * rel_window - 1) ** 2 + 3
         p.rel_table, p.rel_window = rel_table.data_ptr(), rel_window
+    if kv_samples is not None:  # CSR inverse of kv_index: lets the tcgen05 cross-attention kernel stack the samples of an image
+        assert kv_offsets.dtype == torch.int32 and kv_samples.dtype == torch.int32
+        assert kv_offsets.numel() == Bkv + 1 and kv_samples.numel() == B
+        p.kv_offsets, p.kv_samples = kv_offsets.data_ptr(), kv_samples.data_ptr()
     check(lib().xfm_attention_fwd(C.byref(p), stream_ptr()), "xfm_attention_fwd")
     return out, lse
 

@@ -560,10 +560,7 @@ class XFMBase(nn.Module):
 
     def _fusion_back(self, st, dh, Bi, Ni, need_dtext, kv_index):
         d_enc = torch.zeros((Bi * Ni, self.vision_width), dtype=torch.float32, device=dh.device)
-        off = smp = None
-        if kv_index is not None:
-            off, smp = E.csr_inverse(kv_index, Bi)
-        d_text = self._fus.layers_bwd(st, dh, d_enc=d_enc, need_dh=need_dtext, kv_offsets=off, kv_samples=smp)
+        d_text = self._fus.layers_bwd(st, dh, d_enc=d_enc, need_dh=need_dtext)  # CSR of kv_index: built once in layers_fwd
         return d_text, d_enc.view(Bi, Ni, -1)
 
     def get_cross_embeds(self, image_embeds, image_atts, text_ids=None, text_embeds=None, text_atts=None, is_pretrain=True):
