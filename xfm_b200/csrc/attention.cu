@@ -141,7 +141,9 @@ XFM_DEVINL float quad_sum(float v) {
 }
 
 XFM_DEVINL bool drop_keep(const AttnArgs& a, int b, int h, int q, int key) {
-  const uint64_t idx = (((uint64_t)b * a.H + h) * a.Lq + q) * (uint64_t)a.Lk + key;
+  // element index with an EVEN row stride: keys (2k, 2k+1) of a row share one hash pair (the tcgen05 kernels evaluate the
+  // mask pair-wise; both kernel families must index identically so forward and backward regenerate the same mask)
+  const uint64_t idx = (((uint64_t)b * a.H + h) * a.Lq + q) * (uint64_t)((a.Lk + 1) & ~1) + key;
   return drop_keep_idx(a.seed, idx, a.dropout_p);
 }
 

@@ -207,7 +207,9 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
     const uint32_t t_s = lane_base + (uint32_t)(t * LPAD), t_o = lane_base + (uint32_t)Cfg::TMEM_O;
     const float scale2 = a.scale * 1.4426950408889634f;
-    const float inv_keep = a.dropout_p > 0.f ? 1.0f / (1.0f - a.dropout_p) : 1.0f;
+    const bool drop_on = a.dropout_p > 0.f;
+    const float inv_keep = drop_on ? 1.0f / (1.0f - a.dropout_p) : 1.0f;
+    const uint32_t seed_mix = drop_seed_mix(a.seed), thr = drop_threshold(a.dropout_p);
     uint8_t* myP = sP + t * Cfg::P_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
     const int sw = r & 7;
     XWalker<GMAX> w(a, item0, item1);
@@ -217,7 +219,10 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       const bool valid = slot_in_tile < PER_TILE && g < u.ns;
       const bool wv = __any_sync(0xffffffffu, valid);   // tcgen05.ld is warp-collective: decide per warp, mask per thread
       const int b = valid ? a.kv_samples[u.first + g] : 0;
-      const uint64_t drop_base = (((uint64_t)b * a.H + u.h) * LQS + q) * (uint64_t)LK;
+      // dropout mask: element index ((b, h, q) row) * LKE + key with the even row stride LKE (attention.cu::drop_keep)
+      constexpr int LKE = (LK + 1) & ~1;
+      const uint64_t pair_base = ((((uint64_t)b * a.H + u.h) * LQS + q) * (uint64_t)LKE) >> 1;
+      const uint32_t pb_lo = (uint32_t)pair_base, pb_hi = (uint32_t)(pair_base >> 32);
       mbar_wait(&s_full[t], ph);
       tc_fence_after();
       float m = -INFINITY, sum = 0.f;
@@ -249,15 +254,23 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
           if (c0 + g8 * 8 < LPAD) {
             float p[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int j = c0 + g8 * 8 + e;
-              float pe = 0.f;
+            for (int e = 0; e < 8; e += 2) {
+              const int j = c0 + g8 * 8 + e;   // even
+              float p0 = 0.f, p1 = 0.f;
               if (valid && j < LK) {
-                pe = ex2_approx(fmaf(__uint_as_float(v[g8 * 8 + e]), scale2, -m));
-                s4[e & 3] += pe;
-                if (a.dropout_p > 0.f) pe = drop_keep_idx(a.seed, drop_base + j, a.dropout_p) ? pe * inv_keep : 0.f;
+                p0 = ex2_approx(fmaf(__uint_as_float(v[g8 * 8 + e]), scale2, -m));
+                if (j + 1 < LK) p1 = ex2_approx(fmaf(__uint_as_float(v[g8 * 8 + e + 1]), scale2, -m));
+                s4[e & 3] += p0;
+                s4[(e + 1) & 3] += p1;
+                if (drop_on) {
+                  const uint32_t lo = pb_lo + (uint32_t)(j >> 1);
+                  const uint32_t keep = drop_keep_pair(seed_mix, lo, pb_hi + (lo < pb_lo ? 1u : 0u), thr);
+                  p0 = (keep & 1u) ? p0 * inv_keep : 0.f;
+                  p1 = (keep & 2u) ? p1 * inv_keep : 0.f;
+                }
               }
-              p[e] = pe;
+              p[e] = p0;
+              p[e + 1] = p1;
             }
             const int col8 = c0 + g8 * 8;
             xt_st_bf16x8(myP + (col8 >> 6) * 16384 + ((((col8 & 63) >> 3) ^ sw) << 4), p);

@@ -274,6 +274,14 @@ XFM_DEVINL bool drop_keep_idx(uint64_t seed, uint64_t idx, float p) {
   const uint32_t bits = (idx & 1) ? (x >> 16) : (x & 0xFFFFu);
   return bits >= thr;
 }
+// The same decision for the two elements of pair index `pair` (= element index >> 1) at once: bit 0 = even element kept,
+// bit 1 = odd element kept.  seed_mix = drop_seed_mix(seed), thr = drop_threshold(p).
+XFM_DEVINL uint32_t drop_seed_mix(uint64_t seed) { return (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x85EBCA6Bu); }
+XFM_DEVINL uint32_t drop_threshold(float p) { return (uint32_t)(p * 65536.0f + 0.5f); }
+XFM_DEVINL uint32_t drop_keep_pair(uint32_t seed_mix, uint32_t pair_lo, uint32_t pair_hi, uint32_t thr) {
+  const uint32_t x = mix32((pair_lo + pair_hi * 0x9E3779B1u) ^ seed_mix);
+  return ((x & 0xFFFFu) >= thr ? 1u : 0u) | ((x >> 16) >= thr ? 2u : 0u);
+}
 XFM_DEVINL float hash_uniform(uint64_t seed, uint64_t idx) { return (float)(hash_u32(seed, idx) >> 8) * (1.0f / 16777216.0f); }
 
 }  // namespace xfm
