@@ -432,6 +432,52 @@ def test_cross_attention_tcgen05_forward(lib, B, Bkv, H, pattern):
     assert float((od.float() - out.float()).abs().max()) > 1e-2   # dropout did something
 
 
+@pytest.mark.parametrize("B,Bkv,H,pattern", [(8, 2, 2, "even"), (24, 6, 12, "random"), (14, 2, 3, "big_groups"), (6, 6, 2, "identity")])
+def test_cross_attention_tcgen05_backward(lib, B, Bkv, H, pattern):
+    """tcgen05 cross-attention dQ / dK / dV against torch autograd (no dropout) and against the mma.sync kernels with the
+    shared dropout mask (p = 0.2)."""
+    g = G(B * 17 + Bkv)
+    if pattern == "even":
+        kv_index = (torch.arange(B) % Bkv).to(torch.int32)
+    elif pattern == "identity":
+        kv_index = torch.arange(B, dtype=torch.int32)
+    elif pattern == "big_groups":
+        kv_index = torch.tensor([0] * 9 + [1] * 5, dtype=torch.int32)
+    else:
+        kv_index = torch.randint(0, Bkv, (B,), generator=g).to(torch.int32)
+        kv_index[:Bkv] = torch.arange(Bkv, dtype=torch.int32)
+    Lq, Lk, D, q2, kv2, order, offs = _cross_case(B, Bkv, H, g, kv_index)
+    dout = bf(torch.randn(B * Lq, D, generator=g))
+    qf = q2.float().view(B, Lq, H, 64).permute(0, 2, 1, 3).clone().requires_grad_(True)
+    kb = kv2.float()[:, :D].reshape(Bkv, Lk, H, 64).permute(0, 2, 1, 3).clone().requires_grad_(True)
+    vb = kv2.float()[:, D:].reshape(Bkv, Lk, H, 64).permute(0, 2, 1, 3).clone().requires_grad_(True)
+    s = (qf * 0.125) @ kb[kv_index.long()].transpose(-1, -2)
+    ref = torch.softmax(s, -1) @ vb[kv_index.long()]
+    ref.backward(dout.float().view(B, Lq, H, 64).permute(0, 2, 1, 3))
+    want_dq = qf.grad.permute(0, 2, 1, 3).reshape(B * Lq, D)
+    want_dk = kb.grad.permute(0, 2, 1, 3).reshape(Bkv * Lk, D)
+    want_dv = vb.grad.permute(0, 2, 1, 3).reshape(Bkv * Lk, D)
+    qd, kvd, do = q2.cuda(), kv2.cuda(), dout.cuda()
+    kw = dict(Bkv=Bkv, kv_index=kv_index.cuda(), kv_offsets=offs.cuda(), kv_samples=order.cuda())
+
+    def run(tc, p):
+        out, lse = lib.attention_fwd(qd, kvd[:, :D], kvd[:, D:], B, H, Lq, Lk, 0.125, dropout_p=p, dropout_seed=9, allow_tc=tc, **kw)
+        dq = torch.full_like(qd, float("nan"))
+        dkv = torch.full_like(kvd, float("nan"))
+        lib.attention_bwd(do, qd, kvd[:, :D], kvd[:, D:], out, lse, B, H, Lq, Lk, 0.125, dq, dkv[:, :D], dkv[:, D:],
+                          dropout_p=p, dropout_seed=9, allow_tc=tc, **kw)
+        return dq.float().cpu(), dkv[:, :D].float().cpu(), dkv[:, D:].float().cpu()
+
+    dq, dk, dv = run(True, 0.0)
+    for name, got, want in (("dq", dq, want_dq), ("dk", dk, want_dk), ("dv", dv, want_dv)):
+        assert torch.isfinite(got).all(), name
+        assert float((got - want).abs().max()) < 2.5e-2 * max(1.0, float(want.abs().max())), name
+    a, b_ = run(True, 0.2), run(False, 0.2)
+    for name, x, y in zip(("dq", "dk", "dv"), a, b_):
+        assert torch.isfinite(x).all(), name
+        assert float((x - y).abs().max()) < 3e-2 * max(1.0, float(y.abs().max())), name
+
+
 def test_attention_dropout_is_consistent(lib):
     """Same (seed, index) mask in forward and both backward kernels: check dQ/dK/dV against autograd through the
     forward's own (recovered) mask."""

@@ -6,7 +6,7 @@ What is recorded (all produced by the reference's own code, through oracle/ref_s
   * tiny_vq.pt   — tiny config with the VQ-KD tokenizer: every per-layer activation, features, hard-negative
                    weights, VQ ids, MIM masks, the four losses, gradients of a few parameters.
   * tiny_mse.pt  — tiny config with the default MSE MIM loss: the four losses.
-  * base_vq.pt / base_mse.pt — XFM-base (224 px, 40 tokens, B=2): losses, VQ ids, masks and sampled slices
+  * base_vq.pt / base_mse.pt — XFM-base (224 px, 40 tokens, B=8): losses, VQ ids, masks and sampled slices
                    of every layer's activations (full tensors would be ~100 MB).
   * itc_idx.pt   — get_contrastive_loss / get_hard_negatives with `idx` (retrieval soft labels).
   * masks.pt     — MaskingGenerator outputs for fixed (random, np.random) seeds.
@@ -197,8 +197,20 @@ def masks_golden():
     return out
 
 
+BASE_B = 8
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
+    if "--only-base" in sys.argv:
+        torch.set_num_threads(os.cpu_count())
+        bm = run_reference(O.base_config(), B=BASE_B, L=40, M=15, image_uniform=False, full=False)
+        torch.save(bm, os.path.join(GOLD, "base_mse.pt"))
+        print("base_mse", bm["losses"])
+        bv = run_reference(O.base_config(use_vision_tokenizer=True), B=BASE_B, L=40, M=15, image_uniform=True, full=False)
+        torch.save(bv, os.path.join(GOLD, "base_vq.pt"))
+        print("base_vq", bv["losses"])
+        return
     torch.set_num_threads(os.cpu_count())
     torch.save(masks_golden(), os.path.join(GOLD, "masks.pt"))
     torch.save(itc_idx_golden(), os.path.join(GOLD, "itc_idx.pt"))
@@ -210,10 +222,12 @@ def main():
     torch.save(tm, os.path.join(GOLD, "tiny_mse.pt"))
     print("tiny_mse", tm["losses"])
     if "--skip-base" not in sys.argv:
-        bm = run_reference(O.base_config(), B=2, L=40, M=15, image_uniform=False, full=False)
+        # B = 8: the ITM loss is a mean over 3B fusion samples; at B = 2 (6 samples) two equally accurate bf16 kernels differ
+        # by ~1e-3 in it, which is the tolerance itself
+        bm = run_reference(O.base_config(), B=BASE_B, L=40, M=15, image_uniform=False, full=False)
         torch.save(bm, os.path.join(GOLD, "base_mse.pt"))
         print("base_mse", bm["losses"])
-        bv = run_reference(O.base_config(use_vision_tokenizer=True), B=2, L=40, M=15, image_uniform=True, full=False)
+        bv = run_reference(O.base_config(use_vision_tokenizer=True), B=BASE_B, L=40, M=15, image_uniform=True, full=False)
         torch.save(bv, os.path.join(GOLD, "base_vq.pt"))
         print("base_vq", bv["losses"])
     for f in sorted(os.listdir(GOLD)):

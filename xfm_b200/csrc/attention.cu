@@ -567,6 +567,7 @@ int attention_bwd(const xfm_attn_params* p, cudaStream_t s) {
   // dS dump (reduced by the caller) or is accumulated in-kernel into rel_dtable (shared-memory atomics: slower)
   if (p->allow_tc && vit_attention_tc_supported(p) && (!p->bias || p->rel_table))
     return vit_attention_bwd_tc(p, s);
+  if (p->allow_tc && cross_attention_tc_supported(p) && !p->ds_dump) return cross_attention_bwd_tc(p, s);
   const size_t smem_a = (size_t)(2 * AT_TILE + 2 * LkP) * ROW_BYTES;
   const size_t smem_b = (size_t)(2 * AT_TILE + 2 * LqP) * ROW_BYTES + 2 * LqP * sizeof(float);
   if (smem_a > 220 * 1024 || smem_b > 220 * 1024) {
