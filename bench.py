@@ -237,6 +237,11 @@ def run_ours(args):
             json.dump(rows, f, indent=0)
     g_flops = sum(p[0] for p in prof)
     g_ms = sum(p[1].elapsed_time(p[2]) for p in prof)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+    if os.path.exists(tpath):  # dram__bytes_read + write per launch from the committed ncu --set full capture of this command
+        with open(tpath) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
     pk, pk_kind = peaks()
     peak = pk.get("bf16_tflops_sustained", 1400.0)
     ach = g_flops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
@@ -255,7 +260,8 @@ def run_ours(args):
                 "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                     "traffic": None, "kernel": "gemm_tcgen05_kernel", "launches_per_step": len(prof),
+                     "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write, mean of the profiled launches)",
+                     "kernel": "gemm_tcgen05_pair_kernel / gemm_tcgen05_kernel", "launches_per_step": len(prof),
                      "gemm_ms_per_step": g_ms, "peak_source": f"{pk_kind} bf16_tflops_sustained",
                      "step_tflops_algorithmic": GFLOP_PER_PAIR * B / ms_step,
                      "step_frac_of_peak": GFLOP_PER_PAIR * B / ms_step / peak},
