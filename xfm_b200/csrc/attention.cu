@@ -92,11 +92,14 @@ XFM_DEVINL void load_a_frags(uint32_t tile_addr, int row0, int lane, uint32_t (&
 
 // acc[nt] (16 x 64 block, 8 n-tiles) += A(16 x 64 over d) * Bt, where tile rows n0..n0+63 are the "n" index and the
 // contraction runs over the 64 columns (d):  acc[row][n] = sum_d A[row][d] * tile[n0 + n][d].
-XFM_DEVINL void mma_rows_nt(float (&acc)[8][4], const uint32_t (&a)[4][4], uint32_t tile_addr, int n0, int lane) {
+// `lim`: rows n0 .. n0+lim-1 of the tile are real; 16-row groups beyond are skipped (their accumulators stay 0), which is
+// most of the work for the 40-token text sequences inside 64-row tiles.
+XFM_DEVINL void mma_rows_nt(float (&acc)[8][4], const uint32_t (&a)[4][4], uint32_t tile_addr, int n0, int lane, int lim = 64) {
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) {
 #pragma unroll
     for (int ntp = 0; ntp < 4; ++ntp) {
+      if (ntp * 16 >= lim) continue;
       uint32_t b00, b01, b10, b11;
       const int n = n0 + ntp * 16 + (lane & 7) + (lane >> 4) * 8;
       ldsm_x4(tile_addr + swz(n, kk * 16 + ((lane >> 3) & 1) * 8), b00, b01, b10, b11);
@@ -107,9 +110,10 @@ XFM_DEVINL void mma_rows_nt(float (&acc)[8][4], const uint32_t (&a)[4][4], uint3
 }
 
 // acc (16 x 64 over d) += P(16 x 64 over k) * tile[k0 + k][d]; P given as 4 k-step A fragments.
-XFM_DEVINL void mma_rows_kd(float (&acc)[8][4], const uint32_t (&p)[4][4], uint32_t tile_addr, int k0, int lane) {
+XFM_DEVINL void mma_rows_kd(float (&acc)[8][4], const uint32_t (&p)[4][4], uint32_t tile_addr, int k0, int lane, int lim = 64) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
+    if (j * 16 >= lim) continue;   // the P / dS fragment of these k rows is all zero
 #pragma unroll
     for (int dtp = 0; dtp < 4; ++dtp) {
       uint32_t r0, r1, r2, r3;
@@ -145,6 +149,15 @@ XFM_DEVINL bool drop_keep(const AttnArgs& a, int b, int h, int q, int key) {
   // mask pair-wise; both kernel families must index identically so forward and backward regenerate the same mask)
   const uint64_t idx = (((uint64_t)b * a.H + h) * a.Lq + q) * (uint64_t)((a.Lk + 1) & ~1) + key;
   return drop_keep_idx(a.seed, idx, a.dropout_p);
+}
+
+// Pair-wise evaluation of the same mask: pair base of a (b, h, q) row, then both keys (key, key+1), key even, at once.
+XFM_DEVINL uint64_t drop_row_pair_base(const AttnArgs& a, int b, int h, int q) {
+  return ((((uint64_t)b * a.H + h) * a.Lq + q) * (uint64_t)((a.Lk + 1) & ~1)) >> 1;
+}
+XFM_DEVINL uint32_t drop_pair_row(uint64_t pair_base, int key_even, uint32_t seed_mix, uint32_t thr) {
+  const uint64_t pair = pair_base + (uint64_t)(key_even >> 1);
+  return drop_keep_pair(seed_mix, (uint32_t)pair, (uint32_t)(pair >> 32), thr);
 }
 
 // Logit of (query row, key) after scale / bias / mask; -inf outside [0,Lk).
@@ -223,16 +236,20 @@ attn_fwd_kernel(const AttnArgs a) {
   for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
   const float inv_keep = a.dropout_p > 0.f ? 1.0f / (1.0f - a.dropout_p) : 1.0f;
+  const uint32_t seed_mix = drop_seed_mix(a.seed), thr = drop_threshold(a.dropout_p);
+  const uint64_t dp0 = drop_row_pair_base(a, b, h, r0), dp1 = drop_row_pair_base(a, b, h, r1);
   for (int kb = 0; kb < LkP; kb += AT_TILE) {
     float s[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
     float bb[8][4];
     load_addend_rows(a, b, h, r0, r1, kb, t, bb);
-    mma_rows_nt(s, qf, aK, kb, lane);
+    const int lim = a.Lk - kb;   // valid keys in this block
+    mma_rows_nt(s, qf, aK, kb, lane, lim);
     float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
+      if (nt * 8 >= lim) continue;   // all-padding key group: s stays 0 = probability 0
       const int key = kb + nt * 8 + 2 * t;
       s[nt][0] = logit2(a, s[nt][0], bb[nt][0], key);
       s[nt][1] = logit2(a, s[nt][1], bb[nt][1], key + 1);
@@ -248,29 +265,32 @@ attn_fwd_kernel(const AttnArgs a) {
     float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
+      o[nt][0] *= c0; o[nt][1] *= c0; o[nt][2] *= c1; o[nt][3] *= c1;
+      if (nt * 8 >= lim) continue;
       s[nt][0] = __expf(s[nt][0] - mn0);
       s[nt][1] = __expf(s[nt][1] - mn0);
       s[nt][2] = __expf(s[nt][2] - mn1);
       s[nt][3] = __expf(s[nt][3] - mn1);
       sum0 += s[nt][0] + s[nt][1];
       sum1 += s[nt][2] + s[nt][3];
-      o[nt][0] *= c0; o[nt][1] *= c0; o[nt][2] *= c1; o[nt][3] *= c1;
     }
     l0 = l0 * c0 + sum0;
     l1 = l1 * c1 + sum1;
     if (a.dropout_p > 0.f) {
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
-        const int key = kb + nt * 8 + 2 * t;
-        s[nt][0] = drop_keep(a, b, h, r0, key) ? s[nt][0] * inv_keep : 0.f;
-        s[nt][1] = drop_keep(a, b, h, r0, key + 1) ? s[nt][1] * inv_keep : 0.f;
-        s[nt][2] = drop_keep(a, b, h, r1, key) ? s[nt][2] * inv_keep : 0.f;
-        s[nt][3] = drop_keep(a, b, h, r1, key + 1) ? s[nt][3] * inv_keep : 0.f;
+        if (nt * 8 >= lim) continue;
+        const int key = kb + nt * 8 + 2 * t;   // even: (key, key+1) is one hash pair of each row
+        const uint32_t k0 = drop_pair_row(dp0, key, seed_mix, thr), k1 = drop_pair_row(dp1, key, seed_mix, thr);
+        s[nt][0] = (k0 & 1u) ? s[nt][0] * inv_keep : 0.f;
+        s[nt][1] = (k0 & 2u) ? s[nt][1] * inv_keep : 0.f;
+        s[nt][2] = (k1 & 1u) ? s[nt][2] * inv_keep : 0.f;
+        s[nt][3] = (k1 & 2u) ? s[nt][3] * inv_keep : 0.f;
       }
     }
     uint32_t pf[4][4];
     c_to_a_frags(s, pf);
-    mma_rows_kd(o, pf, aV, kb, lane);
+    mma_rows_kd(o, pf, aV, kb, lane, lim);
   }
   l0 = quad_sum(l0);
   l1 = quad_sum(l1);
@@ -343,6 +363,8 @@ attn_bwd_dq_kernel(const AttnArgs a) {
   const int64_t st = ((int64_t)b * a.H + h) * a.Lq;
   const float lse0 = r0 < a.Lq ? a.lse[st + r0] : 0.f, lse1 = r1 < a.Lq ? a.lse[st + r1] : 0.f;
   const float dl0 = r0 < a.Lq ? a.delta[st + r0] : 0.f, dl1 = r1 < a.Lq ? a.delta[st + r1] : 0.f;
+  const uint32_t seed_mix = drop_seed_mix(a.seed), thr = drop_threshold(a.dropout_p);
+  const uint64_t dpb0 = drop_row_pair_base(a, b, h, r0), dpb1 = drop_row_pair_base(a, b, h, r1);
   const float inv_keep = a.dropout_p > 0.f ? 1.0f / (1.0f - a.dropout_p) : 1.0f;
   float dq[8][4];
 #pragma unroll
@@ -356,17 +378,25 @@ attn_bwd_dq_kernel(const AttnArgs a) {
     }
     float bb[8][4];
     load_addend_rows(a, b, h, r0, r1, kb, t, bb);
-    mma_rows_nt(s, qf, aK, kb, lane);    // S  = Q K^T
-    mma_rows_nt(dp, dof, aV, kb, lane);  // dP = dO V^T
+    const int lim = a.Lk - kb;
+    mma_rows_nt(s, qf, aK, kb, lane, lim);    // S  = Q K^T
+    mma_rows_nt(dp, dof, aV, kb, lane, lim);  // dP = dO V^T
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
+      if (nt * 8 >= lim) continue;   // all-padding key group: dS stays 0 (ds_dump beyond Lk is pre-zeroed by the caller)
+      uint32_t keep[2] = {3u, 3u};
+      if (a.dropout_p > 0.f) {
+        const int key_even = kb + nt * 8 + 2 * t;
+        keep[0] = drop_pair_row(dpb0, key_even, seed_mix, thr);
+        keep[1] = drop_pair_row(dpb1, key_even, seed_mix, thr);
+      }
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int row = (e < 2) ? r0 : r1;
         const int key = kb + nt * 8 + 2 * t + (e & 1);
         const float p = __expf(logit2(a, s[nt][e], bb[nt][e], key) - ((e < 2) ? lse0 : lse1));  // 0 for key >= Lk
         float dpe = dp[nt][e];
-        if (a.dropout_p > 0.f) dpe = (key < a.Lk && drop_keep(a, b, h, row, key)) ? dpe * inv_keep : 0.f;
+        if (a.dropout_p > 0.f) dpe = (key < a.Lk && ((keep[e >> 1] >> (e & 1)) & 1u)) ? dpe * inv_keep : 0.f;
         const float ds = (row < a.Lq) ? p * (dpe - ((e < 2) ? dl0 : dl1)) : 0.f;
         s[nt][e] = ds;
       }
@@ -380,7 +410,7 @@ attn_bwd_dq_kernel(const AttnArgs a) {
     }
     uint32_t dsf[4][4];
     c_to_a_frags(s, dsf);
-    mma_rows_kd(dq, dsf, aK, kb, lane);  // dQ += dS K
+    mma_rows_kd(dq, dsf, aK, kb, lane, lim);  // dQ += dS K
   }
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) {
@@ -449,11 +479,17 @@ attn_bwd_dkv_kernel(const AttnArgs a) {
       }
       float bb[8][4];
       load_addend_cols(a, b, h, key0, key1, qb, t, bb);
-      mma_rows_nt(s, kf, aQ, qb, lane);    // S^T  = K Q^T
-      mma_rows_nt(dp, vf, adO, qb, lane);  // dP^T = V dO^T
+      const int lim = a.Lq - qb;   // valid queries in this block
+      mma_rows_nt(s, kf, aQ, qb, lane, lim);    // S^T  = K Q^T
+      mma_rows_nt(dp, vf, adO, qb, lane, lim);  // dP^T = V dO^T
       float pd[8][4];
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
+        if (nt * 8 >= lim) {   // all-padding query group
+#pragma unroll
+          for (int e = 0; e < 4; ++e) pd[nt][e] = s[nt][e] = 0.f;
+          continue;
+        }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int key = (e < 2) ? key0 : key1;
@@ -469,8 +505,8 @@ attn_bwd_dkv_kernel(const AttnArgs a) {
       uint32_t pf[4][4], dsf[4][4];
       c_to_a_frags(pd, pf);
       c_to_a_frags(s, dsf);
-      mma_rows_kd(dv, pf, adO, qb, lane);  // dV += P^T dO
-      mma_rows_kd(dk, dsf, aQ, qb, lane);  // dK += dS^T Q
+      mma_rows_kd(dv, pf, adO, qb, lane, lim);  // dV += P^T dO
+      mma_rows_kd(dk, dsf, aQ, qb, lane, lim);  // dK += dS^T Q
     }
   }
   if (!warp_active) return;
