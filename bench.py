@@ -190,6 +190,7 @@ def run_ours(args):
         loss, out = step(resident[i % n_pool])
         if i == 0:
             arena = reserve_arena(factor=1.5)  # no cudaMalloc inside the timed regions (see accelerator.reserve_arena)
+            t_warm = time.perf_counter()       # the 2 s start after the one-off initialisation of the first step
         if i % 4 == 3:
             torch.cuda.synchronize()
         i += 1
@@ -218,8 +219,32 @@ def run_ours(args):
     def resident_step(i):
         last["loss"], last["out"] = step(resident[i % n_pool])
 
+    # End-to-end loop: every step's inputs come from pinned host memory and its loss is read back.  The copy of step i+1 is
+    # issued on a side stream while step i computes (what a prefetching loader does); both copies and the read-back are
+    # inside the timed region.
+    copy_stream = torch.cuda.Stream(device=dev)
+    slots = [{k: torch.empty_like(v, device=dev) for k, v in host[0].items()} for _ in range(2)]  # static double buffer
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    staged = {"next": None}
+
+    def stage(i):
+        s = i & 1
+        copy_stream.wait_event(consumed[s])  # the step that last used this slot has finished with it
+        with torch.cuda.stream(copy_stream):
+            for k, v in host[i % n_pool].items():
+                slots[s][k].copy_(v, non_blocking=True)
+            ready[s].record(copy_stream)
+        staged["next"] = i
+
     def e2e_step(i):
-        loss, _ = step(to_dev(host[i % n_pool]))
+        if staged["next"] != i:
+            stage(i)
+        s = i & 1
+        torch.cuda.current_stream().wait_event(ready[s])
+        stage(i + 1)
+        loss, _ = step(slots[s])
+        consumed[s].record(torch.cuda.current_stream())
         last["host_loss"] = float(loss)  # D2H read of the step's result
 
     ms_step, launches = timed(resident_step)
