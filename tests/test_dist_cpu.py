@@ -63,7 +63,11 @@ def _worker(rank, world, port, q):
             res[use_idx] = (float(loss) - float(big), float((ia.grad[sl] - a.grad[sl]).abs().max()),
                             float((ta.grad[sl] - b.grad[sl]).abs().max()))
 
-        # ---- gradient all-reduce of a flat buffer in buckets
+        # ---- gradient all-reduce of the trainable part of a flat buffer in buckets (frozen tail untouched)
+        from collections import OrderedDict
+
+        from xfm_b200.params import Segment
+
         class Flat:
             pass
 
@@ -72,12 +76,21 @@ def _worker(rank, world, port, q):
 
         m = Model()
         m.flat = Flat()
-        n = 64 * 37 + 64  # not a multiple of the bucket count
+        n = 64 * 37 + 64
+        segs = OrderedDict()
+        segs["temp"] = Segment("temp", (), 0, 1, True)
+        segs["vision_encoder.a"] = Segment("vision_encoder.a", (64 * 10,), 64, 64 * 10, True)
+        segs["text_encoder.b"] = Segment("text_encoder.b", (64 * 25 + 3,), 64 * 11, 64 * 25 + 3, True)
+        segs["vqkd.frozen"] = Segment("vqkd.frozen", (64,), 64 * 37, 64, False)
+        m.flat.segments = segs
         m.flat.G = torch.arange(n, dtype=torch.float32) * (rank + 1)
         acc = B200DDPAccelerator(dict(CLIP_GRAD_NORM=1.0, ALLREDUCE_BUCKETS=4))
         acc.world, acc.rank = world, rank
+        acc._layout(m)
+        assert acc._train_end == 64 * 37 and acc._vis == (64, 64 * 11)
         acc.all_reduce_grads(m)
         want = torch.arange(n, dtype=torch.float32) * sum(r + 1 for r in range(world))
+        want[64 * 37:] = torch.arange(64 * 37, n, dtype=torch.float32) * (rank + 1)   # frozen segment: not reduced
         res["allreduce"] = float((m.flat.G - want).abs().max())
         q.put((rank, res, None))
         dist.barrier()

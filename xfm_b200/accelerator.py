@@ -142,31 +142,85 @@ class B200DDPAccelerator:
         self.clip = float(getattr(self.cfg, "CLIP_GRAD_NORM", 0.0) or 0.0)
         self.world, self.rank = 1, 0
         self.buckets = int(getattr(self.cfg, "ALLREDUCE_BUCKETS", 4))
+        self.overlap = bool(getattr(self.cfg, "OVERLAP_ALLREDUCE", True))
         self._comm_stream = None
+        self._early = None
+        self._vis = None
 
     def set_up(self, model, optimizer, lr_scheduler, local_rank=0, world_size=1, rank=0):
         self.world, self.rank = world_size, rank
+        self._layout(model)
         if world_size > 1:
             assert dist.is_initialized(), "init torch.distributed (nccl) before set_up"
             flat = model.flat
             dist.broadcast(flat.P, src=0)  # one flat broadcast replaces ~750 per-tensor ones (ddp_accelerator.py:69-74)
             flat.sync_shadow(force=True)
+            if self.overlap and self._vis is not None and flat.G.is_cuda:
+                self._model = model
+                self._comm_stream = torch.cuda.Stream(device=flat.G.device)
+                model._last_node_hook = self._early_reduce
         return _Wrapped(model), optimizer, lr_scheduler
 
+    def _layout(self, model):
+        """Ranges of the flat gradient buffer: [0, train_end) holds every trainable segment (the frozen VQ-KD tokenizer sits
+        behind it and is never reduced); [v0, v1) is the vision encoder, whose gradients are the last ones produced."""
+        segs = model.flat.segments
+        al = lambda n: (n + 63) // 64 * 64
+        self._train_end = max([s.offset + al(s.numel) for s in segs.values() if s.trainable] or [0])
+        vis = [s for s in segs.values() if s.name.startswith("vision_encoder.")]
+        self._vis = None
+        if vis:
+            v0, v1 = min(s.offset for s in vis), max(s.offset + al(s.numel) for s in vis)
+            inside = [s for s in segs.values() if v0 <= s.offset < v1]
+            if len(inside) == len(vis):   # contiguous
+                self._vis = (v0, v1)
+
     def backward_step(self, loss, optimizer):
+        if self._early is not None:
+            raise RuntimeError("B200DDPAccelerator: a second backward ran before optimizer_step after gradients were reduced "
+                               "early; set OVERLAP_ALLREDUCE: false when accumulating several backward passes per step")
         loss.backward()
 
-    def all_reduce_grads(self, model):
-        """SUM all-reduce of the flat gradient buffer in a few large NVLink messages (averaging is folded into the
-        optimizer kernel's grad_mul)."""
-        if self.world == 1:
+    def _reduce_range(self, G, a, b):
+        n = b - a
+        if n <= 0:
             return
-        G = (model.module if hasattr(model, "module") else model).flat.G
-        n = G.numel()
         per = (n + self.buckets - 1) // self.buckets
         per = (per + 63) // 64 * 64
-        for i in range(0, n, per):
-            dist.all_reduce(G[i:i + per], op=dist.ReduceOp.SUM)
+        for i in range(a, b, per):
+            dist.all_reduce(G[i:min(b, i + per)], op=dist.ReduceOp.SUM)
+
+    def _early_reduce(self):
+        """Called at the start of the last backward node (vision encoder): reduce everything but the vision range on a side
+        stream while the vision backward runs (the reference's DDP overlaps bucket by bucket, ddp_accelerator.py:65)."""
+        G = self._model.flat.G
+        v0, v1 = self._vis
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream())
+        self._comm_stream.wait_event(ready)
+        with torch.cuda.stream(self._comm_stream):
+            self._reduce_range(G, 0, v0)
+            self._reduce_range(G, v1, self._train_end)
+            done = torch.cuda.Event()
+            done.record(self._comm_stream)
+        self._early = done
+
+    def all_reduce_grads(self, model):
+        """SUM all-reduce of the trainable part of the flat gradient buffer in a few large NVLink messages (averaging is
+        folded into the optimizer kernel's grad_mul).  When the non-vision ranges were already reduced under the vision
+        backward (_early_reduce) only the vision range is left."""
+        if self.world == 1:
+            return
+        m = model.module if hasattr(model, "module") else model
+        G = m.flat.G
+        if not hasattr(self, "_train_end"):
+            self._layout(m)
+        if self._early is not None:
+            torch.cuda.current_stream().wait_event(self._early)
+            self._early = None
+            self._reduce_range(G, self._vis[0], self._vis[1])
+        else:
+            self._reduce_range(G, 0, self._train_end)
 
     def optimizer_step(self, optimizer, model):
         """clip_grad_norm_(CLIP_GRAD_NORM) + AdamW step + zero_grad (ddp_accelerator.py:89-98).  Returns the total gradient

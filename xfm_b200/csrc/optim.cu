@@ -12,7 +12,13 @@ namespace xfm {
 
 constexpr int OPT_THREADS = 256;
 
-// out[0] += sum g^2 over chunks whose group != 255.
+// out[0] = sum g^2 over chunks whose group != 255.  DETERMINISTIC: every block writes its partial sum, the block that
+// arrives last adds the partials in index order.  (An atomicAdd per block made the clip factor differ in the last bits
+// between data-parallel ranks that hold identical gradients, and the replicas drifted apart by ulps per step.)
+constexpr int SUMSQ_MAX_BLOCKS = 4096;
+__device__ float g_sumsq_partials[SUMSQ_MAX_BLOCKS];
+__device__ unsigned int g_sumsq_arrived = 0;
+
 __global__ void __launch_bounds__(OPT_THREADS)
 sumsq_kernel(const float* __restrict__ g, const uint8_t* __restrict__ chunk_group, size_t nchunks, float* __restrict__ out) {
   __shared__ float sh[OPT_THREADS / 32];
@@ -29,7 +35,28 @@ sumsq_kernel(const float* __restrict__ g, const uint8_t* __restrict__ chunk_grou
   if (threadIdx.x < 32) {
     float r = threadIdx.x < OPT_THREADS / 32 ? sh[threadIdx.x] : 0.f;
     r = warp_sum(r);
-    if (threadIdx.x == 0) atomicAdd(out, r);
+    if (threadIdx.x == 0) g_sumsq_partials[blockIdx.x] = r;
+  }
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    last = atomicAdd(&g_sumsq_arrived, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  float t = 0.f;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += OPT_THREADS) t += ((volatile float*)g_sumsq_partials)[i];
+  t = warp_sum(t);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float r = threadIdx.x < OPT_THREADS / 32 ? sh[threadIdx.x] : 0.f;
+    r = warp_sum(r);
+    if (threadIdx.x == 0) {
+      *out = r;
+      g_sumsq_arrived = 0;
+    }
   }
 }
 
@@ -81,8 +108,8 @@ adamw_flat_kernel(float* __restrict__ P, const float* __restrict__ G, float* __r
 }
 
 int grad_sumsq(const float* g, const uint8_t* chunk_group, size_t nchunks, float* out, cudaStream_t s) {
-  cudaMemsetAsync(out, 0, sizeof(float), s);
-  const int grid = num_sms() * 8;
+  int grid = num_sms() * 8;
+  if (grid > SUMSQ_MAX_BLOCKS) grid = SUMSQ_MAX_BLOCKS;
   sumsq_kernel<<<grid, OPT_THREADS, 0, s>>>(g, chunk_group, nchunks, out);
   count_launch();
   return (int)cudaGetLastError();

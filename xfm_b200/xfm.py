@@ -77,12 +77,19 @@ class _Op(torch.autograd.Function):
     @staticmethod
     def forward(ctx, impl, anchor, *tensors):
         ctx.impl = impl
+        impl.model._pending_nodes += 1
         out = impl.fwd(ctx, *tensors)
         return out
 
     @staticmethod
     def backward(ctx, *grads):
-        ctx.impl.model._backward_begin()
+        model = ctx.impl.model
+        model._backward_begin()
+        model._pending_nodes -= 1
+        # Last node of this backward pass and it only produces vision-encoder gradients: every other gradient is final,
+        # so a data-parallel accelerator may start reducing those ranges now, under the vision backward.
+        if model._pending_nodes == 0 and getattr(ctx.impl, "kind", None) == "vision" and model._last_node_hook is not None:
+            model._last_node_hook()
         gin = ctx.impl.bwd(ctx, *grads)
         return (None, None) + tuple(gin)
 
@@ -347,6 +354,7 @@ class XFMBase(nn.Module):
 
     def _backward_end(self):
         self._in_backward = False
+        self._pending_nodes = 0
         G = self.flat
         att = []
         for name in G.touched:
@@ -380,6 +388,9 @@ class XFMBase(nn.Module):
             return BK.NO_DROP
         self._drop_calls += 1
         return BK.DropCfg(self.cfg["hidden_dropout"], self.cfg["attn_dropout"], self._seed * 131 + self._drop_calls)
+
+    _pending_nodes = 0
+    _last_node_hook = None
 
     def _call(self, impl, *tensors):
         impl.model = self
@@ -422,6 +433,7 @@ class XFMBase(nn.Module):
                 ctx.st = None
                 return (None,)
         impl = Impl()
+        impl.kind = "vision"
         y = self._call(impl, image)
         y._xfm16 = impl.y16
         atts = torch.ones(y.shape[:-1], dtype=torch.long, device=image.device)
