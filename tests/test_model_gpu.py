@@ -245,3 +245,78 @@ def test_fused_itm_mlm_pass_equals_separate_calls(golden_dir):
         scale = max(float(b[2][n].abs().max()), 1e-8)
         # bf16 gradient tensors summed in a different grouping; key biases have a theoretically zero gradient (pure noise)
         assert _maxabs(a[2][n], b[2][n]) <= 2e-2 * scale + 1e-5, n
+
+
+def _grad_check(model, ref_grads, names, tol=6e-2):
+    params = dict(model.named_parameters())
+    for n in names:
+        mine, ref = params[n].grad, ref_grads[n]
+        assert mine is not None, n
+        assert _maxabs(mine, ref) <= tol * max(float(ref.abs().max()), 1e-8), n
+
+
+def test_retrieval_model_against_oracle():
+    """models/model_retrieval.py:26-37 (BASELINE config #3 shape, tiny widths): ITC with idx soft labels + idx-masked
+    hard-negative ITM, text gradients through the fusion encoder (is_pretrain=False)."""
+    from xfm_b200.model_retrieval import XFMForRetrieval
+    cfg = O.tiny_config()
+    B, Lt = 6, 24
+    sd = O.make_state_dict(cfg, 0)
+    for v in sd.values():
+        if v.dtype.is_floating_point:
+            v.requires_grad_(True)
+    batch = O.make_batch(cfg, B, L=Lt, M=6, seed=3)
+    idx = torch.tensor([0, 1, 0, 2, 1, 3])
+    ie = O.vision_forward(batch["image"], sd, cfg)
+    ia = torch.ones(ie.shape[:2], dtype=torch.long)
+    te = O.text_forward(batch["text_ids"], batch["text_atts"], sd, cfg)
+    fi, ft = O.get_features(ie, te, sd)
+    w_i2t, w_t2i = O.hard_negative_weights(fi.detach(), ft.detach(), sd["temp"].detach(), idx)
+    tneg, ineg = w_i2t.argmax(1), w_t2i.argmax(1)   # deterministic stand-in for torch.multinomial (xfm.py:736-746)
+    itc = O.contrastive_loss(fi, ft, sd["temp"], idx)
+    itm, _ = O.matching_loss(ie, ia, te, batch["text_atts"], ineg, tneg, sd, cfg, is_pretrain=False)
+    (itc + itm).backward()
+    model = XFMForRetrieval(dict(cfg), init=lambda n, s: O.make_tensor(n, s, 0), device="cuda").eval()
+    model._forced_negatives = (ineg, tneg)
+    b = {k: v.cuda() for k, v in batch.items()}
+    l_itc, l_itm = model(b["image"], b["text_ids"], b["text_atts"], idx=idx.cuda())
+    assert abs(float(l_itc) - float(itc)) <= 2e-3 * max(1.0, abs(float(itc))), (float(l_itc), float(itc))
+    assert abs(float(l_itm) - float(itm)) <= 1e-3 * max(1.0, abs(float(itm))), (float(l_itm), float(itm))
+    (l_itc + l_itm).backward()
+    ref = {k: v.grad for k, v in sd.items() if v.dtype.is_floating_point and v.grad is not None}
+    _grad_check(model, ref, ["itm_head.0.weight", "fusion_encoder.roberta.encoder.layer.1.crossattention.self.key.weight",
+                             "text_encoder.roberta.encoder.layer.0.intermediate.dense.weight", "vision_proj.weight",
+                             "vision_encoder.blocks.1.mlp.fc2.weight"])
+
+
+def test_nlvr_model_against_oracle():
+    """models/model_nlvr.py:28-44 (BASELINE config #4 shape, tiny widths): two images per text, two fusion passes sharing
+    the text, concatenated CLS -> build_mlp -> CE."""
+    from xfm_b200.model_nlvr import XFMForNLVR
+    cfg = O.tiny_config()
+    B, Lt = 4, 24
+    sd = O.make_state_dict(cfg, 0)
+    batch = O.make_batch(cfg, 2 * B, L=Lt, M=6, seed=5)
+    image = batch["image"]
+    text_ids, text_atts = batch["text_ids"][:B], batch["text_atts"][:B]
+    targets = torch.tensor([0, 1, 1, 0])
+    model = XFMForNLVR(dict(cfg), init=lambda n, s: O.make_tensor(n, s, 0), device="cuda").eval()
+    head = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in model.cls_head.state_dict().items()}
+    ie = O.vision_forward(image, sd, cfg)
+    ia = torch.ones(ie.shape[:2], dtype=torch.long)
+    te = O.text_forward(text_ids, text_atts, sd, cfg)
+    c1 = O.fusion_forward(te, text_atts, ie[:B], ia[:B], sd, cfg)[:, 0]
+    c2 = O.fusion_forward(te, text_atts, ie[B:], ia[B:], sd, cfg)[:, 0]
+    x = torch.cat([c1, c2], -1)
+    x = torch.nn.functional.linear(x, head["0.weight"], head["0.bias"])
+    x = torch.nn.functional.gelu(torch.nn.functional.layer_norm(x, (x.shape[-1],), head["1.weight"], head["1.bias"], 1e-5))
+    pred = torch.nn.functional.linear(x, head["3.weight"], head["3.bias"])
+    ref_loss = torch.nn.functional.cross_entropy(pred, targets)
+    ref_loss.backward()
+    loss = model(image.cuda(), text_ids.cuda(), text_atts.cuda(), targets.cuda())
+    assert abs(float(loss) - float(ref_loss)) <= 2e-3 * max(1.0, abs(float(ref_loss))), (float(loss), float(ref_loss))
+    loss.backward()
+    for n, p in model.cls_head.named_parameters():
+        assert _maxabs(p.grad, head[n].grad) <= 6e-2 * max(float(head[n].grad.abs().max()), 1e-8), n
+    pred_gpu = model(image.cuda(), text_ids.cuda(), text_atts.cuda(), targets.cuda(), train=False)
+    assert _maxabs(pred_gpu, pred.detach()) <= 2e-2
