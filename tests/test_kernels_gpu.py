@@ -478,6 +478,53 @@ def test_cross_attention_tcgen05_backward(lib, B, Bkv, H, pattern):
         assert float((x - y).abs().max()) < 3e-2 * max(1.0, float(y.abs().max())), name
 
 
+@pytest.mark.parametrize("B,H,masked", [(3, 2, False), (7, 12, True), (96, 12, True), (1, 1, True), (11, 3, False)])
+def test_self_attention_tcgen05(lib, B, H, masked):
+    """tcgen05 text / fusion self-attention (attention_stc.cu): three 40-token samples packed per 128-row tile, additive key
+    mask (xroberta.py:966-970), B not a multiple of 3, q/k/v as strided views of one qkv matrix.  Forward and the fused
+    backward against torch autograd without dropout, and against the mma.sync kernels with the shared dropout mask."""
+    g = G(B * 13 + H)
+    L, D = 40, H * 64
+    qkv = bf(torch.randn(B * L, 3 * D, generator=g))
+    dout = bf(torch.randn(B * L, D, generator=g))
+    km = None
+    if masked:
+        lens = torch.randint(3, L + 1, (B,), generator=g)
+        km = torch.where(torch.arange(L)[None, :] < lens[:, None], 0.0, -10000.0)
+    f = qkv.float().view(B, L, 3, H, 64).permute(2, 0, 3, 1, 4)
+    qf, kf, vf = (t.clone().requires_grad_(True) for t in (f[0], f[1], f[2]))
+    s = (qf * 0.125) @ kf.transpose(-1, -2)
+    if masked:
+        s = s + km[:, None, None, :]
+    ref = torch.softmax(s, -1) @ vf
+    ref.backward(dout.float().view(B, L, H, 64).permute(0, 2, 1, 3))
+    want = [t.grad.permute(0, 2, 1, 3).reshape(B * L, D) for t in (qf, kf, vf)]
+    qd, do = qkv.cuda(), dout.cuda()
+    kmd = None if km is None else km.cuda().contiguous()
+    q, k, v = qd[:, :D], qd[:, D:2 * D], qd[:, 2 * D:]
+
+    def run(tc, p):
+        out, lse = lib.attention_fwd(q, k, v, B, H, L, L, 0.125, kmask=kmd, dropout_p=p, dropout_seed=21, allow_tc=tc)
+        dqkv = torch.full_like(qd, float("nan"))
+        lib.attention_bwd(do, q, k, v, out, lse, B, H, L, L, 0.125, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:],
+                          kmask=kmd, dropout_p=p, dropout_seed=21, allow_tc=tc)
+        return out.float().cpu(), lse.cpu(), dqkv.float().cpu()
+
+    out, lse, dqkv = run(True, 0.0)
+    assert float((out - ref.detach().permute(0, 2, 1, 3).reshape(B * L, D)).abs().max()) < 2e-2
+    assert float((lse - torch.logsumexp(s.detach(), -1)).abs().max()) < 2e-3
+    assert torch.isfinite(dqkv).all()
+    for i, name in enumerate(("dq", "dk", "dv")):
+        got, w = dqkv[:, i * D:(i + 1) * D], want[i]
+        assert float((got - w).abs().max()) < 2.5e-2 * max(1.0, float(w.abs().max())), name
+    a, b_ = run(True, 0.2), run(False, 0.2)
+    assert float((a[0] - out).abs().max()) > 1e-2          # dropout did something
+    assert float((a[0] - b_[0]).abs().max()) < 3e-2        # same mask in both kernel families
+    assert float((a[1] - b_[1]).abs().max()) < 2e-3
+    assert torch.isfinite(a[2]).all()
+    assert float((a[2] - b_[2]).abs().max()) < 3e-2 * max(1.0, float(b_[2].abs().max()))
+
+
 def test_attention_dropout_is_consistent(lib):
     """Same (seed, index) mask in forward and both backward kernels: check dQ/dK/dV against autograd through the
     forward's own (recovered) mask."""

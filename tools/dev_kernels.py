@@ -63,7 +63,7 @@ def attn_case(name, B, H, Lq, Lk, mode, Bkv=None, p=0.0, nbuf=3):
         ld = (Lk + 7) // 8 * 8
         bias = torch.randn(H, Lq, ld, device=dev, generator=g) if mode in ("vit", "vit_tc") else None
         table = torch.randn(732, H, device=dev, generator=g) if mode == "vit_tc" else None
-        kmask = torch.zeros(B, Lk, device=dev) if mode == "text" else None
+        kmask = torch.zeros(B, Lk, device=dev) if mode in ("text", "text_tc") else None
         dout = torch.randn(B * Lq, D, device=dev, generator=g).bfloat16()
         ds = torch.empty(B, H, Lq, ld, device=dev, dtype=torch.bfloat16) if mode in ("vit", "vit_tc") else None
         out = torch.empty(B * Lq, D, device=dev, dtype=torch.bfloat16)
@@ -75,11 +75,11 @@ def attn_case(name, B, H, Lq, Lk, mode, Bkv=None, p=0.0, nbuf=3):
     def fwd(s):
         o, lse = L.attention_fwd(s["q"], s["k"], s["v"], B, H, Lq, Lk, 0.125, Bkv=Bkv, bias=s["bias"], kmask=s["kmask"],
                                  kv_index=s["kv_index"], dropout_p=p, dropout_seed=7, out=s["out"], rel_table=s["table"],
-                                 rel_window=14 if s["table"] is not None else 0, allow_tc=mode in ("vit_tc", "plain_tc", "cross"),
+                                 rel_window=14 if s["table"] is not None else 0, allow_tc=mode in ("vit_tc", "plain_tc", "cross", "text_tc"),
                                  kv_offsets=s["offs"], kv_samples=s["order"])
         s["lse"] = lse
 
-    tc = mode in ("vit_tc", "plain_tc", "cross")
+    tc = mode in ("vit_tc", "plain_tc", "cross", "text_tc")
 
     def bwd(s):
         L.attention_bwd(s["dout"], s["q"], s["k"], s["v"], s["out"], s["lse"], B, H, Lq, Lk, 0.125, s["dq"], s["dk"], s["dv"],
@@ -130,6 +130,14 @@ def misc_case(M=18912, D=768):
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     torch.cuda.set_device(0)
+    if what == "tc":
+        attn_case("vit_self_tcgen05", 96, 12, 197, 197, "vit_tc")
+        attn_case("fusion_cross", 384, 12, 40, 197, "cross", Bkv=96, p=0.1)
+    if what == "self":
+        attn_case("text_self", 96, 12, 40, 40, "text", p=0.1)
+        attn_case("fusion_self", 384, 12, 40, 40, "text", p=0.1)
+        attn_case("text_self_tcgen05", 96, 12, 40, 40, "text_tc", p=0.1)
+        attn_case("fusion_self_tcgen05", 384, 12, 40, 40, "text_tc", p=0.1)
     if what in ("attn", "all"):
         attn_case("vit_self_tcgen05", 96, 12, 197, 197, "vit_tc")
         attn_case("vqkd_self_tcgen05", 96, 12, 197, 197, "plain_tc")
@@ -137,6 +145,8 @@ if __name__ == "__main__":
         attn_case("vqkd_self", 96, 12, 197, 197, "plain")
         attn_case("text_self", 96, 12, 40, 40, "text", p=0.1)
         attn_case("fusion_self", 384, 12, 40, 40, "text", p=0.1)
+        attn_case("text_self_tcgen05", 96, 12, 40, 40, "text_tc", p=0.1)
+        attn_case("fusion_self_tcgen05", 384, 12, 40, 40, "text_tc", p=0.1)
         attn_case("fusion_cross", 384, 12, 40, 197, "cross", Bkv=96, p=0.1)
     if what in ("ln", "all"):
         ln_case(18912)

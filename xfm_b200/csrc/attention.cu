@@ -564,6 +564,7 @@ int attention_fwd(const xfm_attn_params* p, cudaStream_t s) {
   if (attn_check(p)) return XFM_ERR_BAD_ARG;
   if (p->allow_tc && vit_attention_tc_supported(p)) return vit_attention_fwd_tc(p, s);
   if (p->allow_tc && cross_attention_tc_supported(p)) return cross_attention_fwd_tc(p, s);
+  if (p->allow_tc && self_attention_tc_supported(p)) return self_attention_fwd_tc(p, s);
   AttnArgs a;
   fill_args(p, a);
   const int LkP = (a.Lk + AT_TILE - 1) / AT_TILE * AT_TILE;
@@ -604,6 +605,7 @@ int attention_bwd(const xfm_attn_params* p, cudaStream_t s) {
   if (p->allow_tc && vit_attention_tc_supported(p) && (!p->bias || p->rel_table))
     return vit_attention_bwd_tc(p, s);
   if (p->allow_tc && cross_attention_tc_supported(p) && !p->ds_dump) return cross_attention_bwd_tc(p, s);
+  if (p->allow_tc && self_attention_tc_supported(p) && !p->ds_dump) return self_attention_bwd_tc(p, s);
   const size_t smem_a = (size_t)(2 * AT_TILE + 2 * LkP) * ROW_BYTES;
   const size_t smem_b = (size_t)(2 * AT_TILE + 2 * LqP) * ROW_BYTES + 2 * LqP * sizeof(float);
   if (smem_a > 220 * 1024 || smem_b > 220 * 1024) {

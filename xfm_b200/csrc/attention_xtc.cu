@@ -453,6 +453,7 @@ xattn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     XUnit u;
     uint32_t tp = 0;
     while (w.next(u)) {
+#pragma unroll 1
       for (int t = 0; t < 2; ++t) {
         const int g = 2 * slot_in_tile + t;
         const bool valid = slot_in_tile < PER_TILE && g < u.ns;
@@ -465,6 +466,7 @@ xattn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         const uint32_t pb_lo = (uint32_t)pair_base, pb_hi = (uint32_t)(pair_base >> 32);
         mbar_wait(sd_full, tp);
         tc_fence_after();
+#pragma unroll 1
         for (int c0 = cb; c0 < ce; c0 += 32) {
           const bool full = c0 + 32 <= ce;
           uint32_t vs[32], vp[32];
@@ -721,11 +723,13 @@ xattn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
         pbh[c] = (uint32_t)(pb >> 32);
       }
       xt_named_bar(1, 256);
+#pragma unroll 1
       for (int t = 0; t < 2; ++t) {
         const int key = t * 128 + r;
         const bool row_ok = key < LK;
         mbar_wait(sd_full, tp);
         tc_fence_after();
+#pragma unroll 1
         for (int c0 = cb; c0 < ce; c0 += 32) {
           const bool full = c0 + 32 <= ce;
           uint32_t vs[32], vp[32];

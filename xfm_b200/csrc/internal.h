@@ -25,6 +25,9 @@ int vit_attention_bwd_tc(const xfm_attn_params* p, cudaStream_t s);
 bool cross_attention_tc_supported(const xfm_attn_params* p);
 int cross_attention_fwd_tc(const xfm_attn_params* p, cudaStream_t s);
 int cross_attention_bwd_tc(const xfm_attn_params* p, cudaStream_t s);
+bool self_attention_tc_supported(const xfm_attn_params* p);
+int self_attention_fwd_tc(const xfm_attn_params* p, cudaStream_t s);
+int self_attention_bwd_tc(const xfm_attn_params* p, cudaStream_t s);
 
 typedef __nv_bfloat16 bf16_t;
 int layernorm_fwd(const void* x, int x_dtype, const float* w, const float* b, void* y, int y_dtype, float* y2, float* stats,
