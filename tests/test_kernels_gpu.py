@@ -79,6 +79,51 @@ def test_gemm_epilogues(lib):
     assert rel_err(out, ref) < 1e-5
 
 
+@pytest.mark.parametrize("M,N,K", [(2560, 768, 256), (2500, 304, 200), (2049, 1000, 64)])
+def test_gemm_cta_pair_epilogues(lib, M, N, K):
+    """CTA-pair (cta_group::2) kernel (selected for M >= 2048, N >= 256): every epilogue mode on
+    full and ragged tiles (M, N not multiples of the 256 x 256 tile / the 32 x 32 epilogue block), against the single-CTA
+    kernel (block_n = 128) and against fp32 torch."""
+    g = G(M + N + K)
+    A, B = bf(torch.randn(M, K, generator=g)), bf(torch.randn(N, K, generator=g) * 0.1)
+    bias, gamma = torch.randn(N, generator=g), torch.randn(N, generator=g)
+    rpg = 197
+    rs = torch.rand((M + rpg - 1) // rpg, generator=g)
+    res = torch.randn(M, N, generator=g)
+    z = A.float() @ B.float().t() + bias
+    ref = res + z * gamma * rs.repeat_interleave(rpg)[:M, None]
+    Ad, Bd = A.cuda(), B.cuda()
+    for bn in (0, 128):   # 0 = automatic: the pair kernel at these sizes
+        aux = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+        out = lib.gemm(Ad, Bd, bias=bias.cuda(), col_scale=gamma.cuda(), row_group_scale=rs.cuda(), rows_per_group=rpg,
+                       residual=res.cuda(), aux_out=aux, out_dtype=torch.float32, block_n=bn)
+        assert rel_err(out, ref) < 1e-5, bn
+        assert rel_err(aux, z) < 5e-3, bn
+        out = lib.gemm(Ad, Bd, bias=bias.cuda(), act=1, aux_out=aux, block_n=bn)
+        assert rel_err(out, F.gelu(z)) < 5e-3, bn
+        assert rel_err(aux, z) < 5e-3, bn
+        h = bf(torch.randn(M, N, generator=G(7)))
+        hf = h.float()
+        dgelu = 0.5 * (1 + torch.erf(hf / math.sqrt(2))) + hf * torch.exp(-0.5 * hf * hf) / math.sqrt(2 * math.pi)
+        out = lib.gemm(Ad, Bd, act=2, aux_in=h.cuda(), block_n=bn)
+        assert rel_err(out, (A.float() @ B.float().t()) * dgelu) < 5e-3, bn
+        # dropout + f32 residual -> f32 (text layers); the two kernels must drop the same elements
+        d = lib.gemm(Ad, Bd, bias=bias.cuda(), dropout_p=0.1, dropout_seed=3, residual=res.cuda(), out_dtype=torch.float32,
+                     block_n=bn)
+        kept = (d - res.cuda()) != 0
+        assert abs(float(kept.float().mean()) - 0.9) < 0.01
+        assert rel_err((d - res.cuda())[kept], (z.cuda() / 0.9)[kept]) < 1e-4
+        if bn == 0:
+            d_pair = d
+        else:
+            assert torch.equal(d_pair != res.cuda(), d != res.cuda())
+    acc = torch.randn(N, K, generator=g)
+    X = bf(torch.randn(M, N, generator=g))
+    out = acc.clone().cuda()
+    lib.gemm(X.cuda(), Ad, a_t=True, b_t=True, out=out, accumulate=True, split_k=3)
+    assert rel_err(out, acc + X.float().t() @ A.float()) < 1e-5
+
+
 def test_gemm_dropout_statistics_and_determinism(lib):
     g = G(5)
     A, B = bf(torch.randn(512, 64, generator=g)), bf(torch.randn(256, 64, generator=g))

@@ -101,6 +101,18 @@ XFM_DEVINL void epilogue_block(const GemmArgs& g, const float* stage, int row_ba
   }
   const float inv_keep = (MODE == 2 && g.dropout_p > 0.f) ? 1.0f / (1.0f - g.dropout_p) : 1.0f;
   const int nrows = FULL ? 32 : min(32, g.M - row_base);
+  // Per-sample (DropPath) scale: a 32-row block touches at most two row groups when a group has >= 32 rows, so the two
+  // scales are fetched once per block instead of one divide + dependent load per row inside the arithmetic.
+  float rgs_lo = 1.f, rgs_hi = 1.f;
+  int rgs_split = 32;
+  const bool rgs_fast = MODE == 2 && g.row_group_scale != nullptr && g.rows_per_group >= 32;
+  if (rgs_fast) {
+    const int g0 = row_base / g.rows_per_group;
+    const int g1 = (row_base + nrows - 1) / g.rows_per_group;
+    rgs_lo = __ldg(g.row_group_scale + g0);
+    rgs_hi = __ldg(g.row_group_scale + g1);
+    rgs_split = (g0 + 1) * g.rows_per_group - row_base;   // first row offset of the second group
+  }
   const bool has_aux_out = MODE != 1 && g.aux_out != nullptr;
   const int act = g.act;
   const bool want_aux = MODE == 1 || (MODE == 2 && act == 2);
@@ -184,7 +196,8 @@ XFM_DEVINL void epilogue_block(const GemmArgs& g, const float* stage, int row_ba
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           float s = 1.f;
-          if (g.row_group_scale) s = __ldg(g.row_group_scale + min(row_base + rr0 + 2 * i, g.M - 1) / g.rows_per_group);
+          if (rgs_fast) s = (rr0 + 2 * i < rgs_split) ? rgs_lo : rgs_hi;
+          else if (g.row_group_scale) s = __ldg(g.row_group_scale + min(row_base + rr0 + 2 * i, g.M - 1) / g.rows_per_group);
           v[i].x *= cs.x * s;
           v[i].y *= cs.y * s;
         }
