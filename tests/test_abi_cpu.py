@@ -79,3 +79,32 @@ def test_masking_sampler_consumes_rng_like_the_reference(golden_dir):
     s = BlockMaskSampler(size, n, mn)
     got = np.stack([s() for _ in range(want.shape[0])])
     assert np.array_equal(got, want.numpy())
+
+
+def test_itm_eval_metrics():
+    """Retrieval.py:186-231 recall metrics against a literal restatement of the reference's loops."""
+    import numpy as np
+    from xfm_b200.retrieval_eval import itm_eval
+    rng = np.random.default_rng(0)
+    n_img, per = 40, 5
+    n_txt = n_img * per
+    s_i2t, s_t2i = rng.standard_normal((n_img, n_txt)), rng.standard_normal((n_txt, n_img))
+    img2txt = {i: list(range(i * per, (i + 1) * per)) for i in range(n_img)}
+    txt2img = {j: j // per for j in range(n_txt)}
+    for i in range(n_img):      # make the task non-trivial but solvable
+        s_i2t[i, img2txt[i]] += 1.5
+    for j in range(n_txt):
+        s_t2i[j, txt2img[j]] += 1.5
+    got = itm_eval(s_i2t, s_t2i, txt2img, img2txt)
+    ranks = np.zeros(n_img)
+    for index, score in enumerate(s_i2t):
+        inds = np.argsort(score)[::-1]
+        ranks[index] = min(np.where(inds == i)[0][0] for i in img2txt[index])
+    tr = [100.0 * len(np.where(ranks < n)[0]) / len(ranks) for n in (1, 5, 10)]
+    ranks = np.zeros(n_txt)
+    for index, score in enumerate(s_t2i):
+        inds = np.argsort(score)[::-1]
+        ranks[index] = np.where(inds == txt2img[index])[0][0]
+    ir = [100.0 * len(np.where(ranks < n)[0]) / len(ranks) for n in (1, 5, 10)]
+    assert [got["txt_r1"], got["txt_r5"], got["txt_r10"]] == tr and [got["img_r1"], got["img_r5"], got["img_r10"]] == ir
+    assert abs(got["r_mean"] - (sum(tr) / 3 + sum(ir) / 3) / 2) < 1e-12

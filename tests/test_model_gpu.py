@@ -320,3 +320,47 @@ def test_nlvr_model_against_oracle():
         assert _maxabs(p.grad, head[n].grad) <= 6e-2 * max(float(head[n].grad.abs().max()), 1e-8), n
     pred_gpu = model(image.cuda(), text_ids.cuda(), text_atts.cuda(), targets.cuda(), train=False)
     assert _maxabs(pred_gpu, pred.detach()) <= 2e-2
+
+
+def test_retrieval_evaluation_rerank_against_oracle():
+    """Retrieval.py:76-184: ITC top-k candidates re-scored by the fusion encoder + itm_head, both
+    directions.  Oracle: the reference's per-row loop restated on the CPU functions (every (image, text) pair scored, so the
+    comparison does not depend on which near-tied candidates a side picks).  Also the rank sharding of the loop."""
+    from xfm_b200.model_retrieval import XFMForRetrieval
+    from xfm_b200 import retrieval_eval as RE
+    cfg = O.tiny_config()
+    n_img, n_txt, Lt, k = 5, 11, 24, 3
+    sd = O.make_state_dict(cfg, 0)
+    bi = O.make_batch(cfg, n_img, L=Lt, M=6, seed=11)
+    bt = O.make_batch(cfg, n_txt, L=Lt, M=6, seed=12)
+    with torch.no_grad():
+        ie = O.vision_forward(bi["image"], sd, cfg)
+        te = O.text_forward(bt["text_ids"], bt["text_atts"], sd, cfg)
+        fi, ft = O.get_features(ie, te, sd)
+        sims = fi @ ft.t()
+        full = torch.empty(n_img, n_txt)
+        for i in range(n_img):   # Retrieval.py:139-147 with every text as a candidate
+            enc = ie[i].repeat(n_txt, 1, 1)
+            out = O.fusion_forward(te, bt["text_atts"], enc, torch.ones(enc.shape[:2], dtype=torch.long), sd, cfg)
+            full[i] = O.itm_head(out[:, 0, :], sd)[:, 1]
+    model = XFMForRetrieval(dict(cfg), init=lambda n, s: O.make_tensor(n, s, 0), device="cuda").eval()
+    s_i2t, s_t2i = RE.evaluation(model, [bi["image"][:2].cuda(), bi["image"][2:].cuda()], bt["text_ids"].cuda(),
+                                 bt["text_atts"].cuda(), {"k_test": k, "batch_size_test_text": 4})
+    assert s_i2t.shape == (n_img, n_txt) and s_t2i.shape == (n_txt, n_img)
+    tol = 2e-2 * max(1.0, float(full.abs().max()))
+    for mat, ref, ref_sims in ((s_i2t, full, sims), (s_t2i, full.t(), sims.t())):
+        mat = torch.from_numpy(mat)
+        scored = mat != -100.0
+        assert (scored.sum(1) == k).all()
+        assert float((mat - ref)[scored].abs().max()) <= tol
+        # the scored candidates are the ITC top-k (ties at the k-th similarity may resolve either way)
+        kth = ref_sims.topk(k, dim=1).values[:, -1:]
+        assert bool((ref_sims[scored].view(-1, k) >= kth - 2e-3).all())
+    # rank sharding (Retrieval.py:133-136,153-155): the two ranks' matrices sum to the single-rank result - 100
+    t32, t16, temb = RE.encode_texts(model, bt["text_ids"].cuda(), bt["text_atts"].cuda())
+    i16, iemb = RE.encode_images(model, [bi["image"].cuda()])
+    parts = [RE.rerank(model, i16, iemb, t32, t16, temb, bt["text_atts"].cuda(), k, pairs_per_pass=7, shard=(r, 2)) for r in (0, 1)]
+    one = RE.rerank(model, i16, iemb, t32, t16, temb, bt["text_atts"].cuda(), k)
+    for d in (0, 1):
+        assert float((parts[0][d] + parts[1][d] - (one[d] - 100.0)).abs().max()) <= 2e-2
+
