@@ -411,6 +411,7 @@ def test_vit_attention_tcgen05_backward(lib, B, H, ws, with_table):
         table = (torch.randn(T, H, generator=g)).requires_grad_(True)
         idx = closed_form_rel_index(ws)
         s = s + table[idx.view(-1)].view(L, L, H).permute(2, 0, 1)
+    s.retain_grad()
     ref = torch.softmax(s, -1) @ vf
     ref.backward(dout.float().view(B, L, H, 64).permute(0, 2, 1, 3))
     want = torch.stack([qf.grad, kf.grad, vf.grad]).permute(1, 3, 0, 2, 4).reshape(B * L, 3 * D)
@@ -432,6 +433,18 @@ def test_vit_attention_tcgen05_backward(lib, B, H, ws, with_table):
     if table is not None:
         err = float((dtab.cpu() - table.grad).abs().max())
         assert err < 2e-2 * max(1.0, float(table.grad.abs().max())), ("dtable", err, float(table.grad.abs().max()))
+    # the fused dQ/dK/dV kernel (taken when the table gradient is NOT accumulated in-kernel) with the bf16 dS dump
+    ld = (L + 7) // 8 * 8
+    ds = torch.zeros(B, H, L, ld, dtype=torch.bfloat16, device="cuda")
+    dqkv2 = torch.full_like(c, float("nan"))
+    lib.attention_bwd(do, q, k, v, out, lse, B, H, L, L, 0.125, dqkv2[:, :D], dqkv2[:, D:2 * D], dqkv2[:, 2 * D:], ds_dump=ds, **kw)
+    got2 = dqkv2.float().cpu()
+    assert torch.isfinite(got2).all()
+    for name, sl in (("dq", slice(0, D)), ("dk", slice(D, 2 * D)), ("dv", slice(2 * D, 3 * D))):
+        err = float((got2[:, sl] - want[:, sl]).abs().max())
+        assert err < 2.5e-2 * max(1.0, scale), ("fused " + name, err, scale)
+    err = float((ds[..., :L].float().cpu() - s.grad).abs().max())
+    assert err < 1e-2 * max(1.0, float(s.grad.abs().max())), ("ds_dump", err)
 
 
 def _cross_case(B, Bkv, H, g, kv_index):

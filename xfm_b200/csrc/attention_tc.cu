@@ -855,6 +855,305 @@ vit_attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __gr
   }
 }
 
+// ================================================================================================ fused backward
+// One kernel for dQ, dK and dV (used when the table gradient comes from the bf16 dS dump, i.e. always in the training step):
+// per query tile S = Q K^T and dP = dO V^T are computed ONCE, the two warpgroups write P and dS to shared memory once, and
+// three products are issued from those buffers — dQ = dS K (dS read K-major), dK = dS^T Q and dV = P^T dO (the same buffers
+// read MN-major: keys become the M dimension, 64-key blocks are 16 KB apart).  The elementwise stage, which bounds these
+// kernels, therefore runs once per (query, key) pair instead of once in a dQ kernel and again in a dK/dV kernel.  The outputs
+// re-use the TMEM columns of S / dP; the second query tile of a (sample, head) adds its dK / dV to the first tile's rows in
+// global memory (same thread, same rows: no synchronisation needed).
+template <int W>
+struct VitFusedCfg : VitCfg<W> {
+  using Base = VitCfg<W>;
+  static constexpr int SPLIT = ((Base::LPAD / 2 + 15) / 16) * 16;
+  static constexpr int NM = (Base::LPAD + 127) / 128;             // 128-key M tiles of dK / dV
+  static constexpr int PD_BYTES = 2 * NM * 16384;                  // P / dS operand: whole 64-key blocks for every M tile
+  static constexpr int SMEM = 2 * 16384 + 2 * Base::KV_BYTES + 2 * PD_BYTES + Base::TAB_FLOATS * 4 + 128;
+  static constexpr int TM_DQ = 0, TM_DK = 64, TM_DV = 64 + 64 * NM, TM_END = 64 + 128 * NM;
+  static constexpr int UNITS = TM_END / 32;                        // 32-column drain units, split between the warpgroups
+  static_assert(2 * Base::LPAD <= 512 && TM_END <= 512, "TMEM");
+  static_assert(SMEM <= 232448, "shared memory");
+};
+
+template <int W>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+vit_attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
+                             const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
+                             const VitBwdArgs a) {
+  using Cfg = VitFusedCfg<W>;
+  constexpr int L = Cfg::L, LPAD = Cfg::LPAD, NT = Cfg::NT, SPLIT = Cfg::SPLIT, NM = Cfg::NM;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if (smem_u32(smem) & 1023) __trap();
+  uint8_t* sQ = smem;                       // one 128-row query tile
+  uint8_t* sdO = sQ + 16384;
+  uint8_t* sK = sdO + 16384;                // LPAD keys
+  uint8_t* sV = sK + Cfg::KV_BYTES;
+  uint8_t* sdS = sV + Cfg::KV_BYTES;
+  uint8_t* sP = sdS + Cfg::PD_BYTES;
+  float* tab = (float*)(sP + Cfg::PD_BYTES);    // [OFFMAX+1 copies of table[T-3]] ++ [table], log2 domain
+  uint64_t* bars = (uint64_t*)(tab + Cfg::TAB_FLOATS);
+  uint64_t *kv_full = bars, *kv_empty = bars + 1, *qdo_full = bars + 2, *qdo_empty = bars + 3, *sd_full = bars + 4,
+           *ds_full = bars + 5, *out_full = bars + 6, *out_empty = bars + 7;
+  uint32_t* tmem_ptr = (uint32_t*)(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_q);
+    tma_prefetch_desc(&map_do);
+    tma_prefetch_desc(&map_k);
+    tma_prefetch_desc(&map_v);
+    mbar_init(kv_full, 1);
+    mbar_init(kv_empty, 1);
+    mbar_init(qdo_full, 1);
+    mbar_init(qdo_empty, 1);
+    mbar_init(sd_full, 1);
+    mbar_init(ds_full, 8);
+    mbar_init(out_full, 1);
+    mbar_init(out_empty, 8);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  constexpr uint32_t TM_S = 0, TM_DP = LPAD;
+
+  const int n_items = a.B * a.H;
+  const int item0 = blockIdx.x * a.items_per_cta;
+  const int item1 = min(n_items, item0 + a.items_per_cta);
+  const int n_tiles = (item1 - item0) * NT;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int tau = 0; tau < n_tiles; ++tau) {
+        const int item = item0 + tau / NT, t = tau % NT;
+        const int h = item / a.B, b = item % a.B;
+        if (t == 0) {
+          mbar_wait_relaxed(kv_empty, ((uint32_t)(tau / NT) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(kv_full, 2 * Cfg::KV_BYTES);
+          tma_load_2d(sK, &map_k, kv_full, h * TC_HD, b * L);
+          tma_load_2d(sV, &map_v, kv_full, h * TC_HD, b * L);
+        }
+        mbar_wait_relaxed(qdo_empty, ((uint32_t)tau & 1u) ^ 1u);
+        mbar_arrive_expect_tx(qdo_full, 2 * 16384);
+        tma_load_2d(sQ, &map_q, qdo_full, h * TC_HD, b * L + t * 128);
+        tma_load_2d(sdO, &map_do, qdo_full, h * TC_HD, b * L + t * 128);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, LPAD, 0, 0);
+      constexpr uint32_t idesc_dq = make_idesc_bf16(128, TC_HD, 0, 1);
+      constexpr uint32_t idesc_dkv = make_idesc_bf16(128, TC_HD, 1, 1);
+      const uint32_t aQ = smem_u32(sQ), adO = smem_u32(sdO), aK = smem_u32(sK), aV = smem_u32(sV), adS = smem_u32(sdS),
+                     aP = smem_u32(sP);
+      for (int tau = 0; tau < n_tiles; ++tau) {
+        const int t = tau % NT;
+        const uint32_t par = (uint32_t)tau & 1u;
+        if (t == 0) mbar_wait(kv_full, (uint32_t)(tau / NT) & 1u);
+        mbar_wait(qdo_full, par);
+        mbar_wait(out_empty, par ^ 1u);        // the previous tile's outputs (which alias S / dP) are drained
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base + TM_S, make_smem_desc(aQ + k * 32, 16, 1024), make_smem_desc(aK + k * 32, 16, 1024), idesc_s,
+                    k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base + TM_DP, make_smem_desc(adO + k * 32, 16, 1024), make_smem_desc(aV + k * 32, 16, 1024), idesc_s,
+                    k > 0 ? 1u : 0u);
+        umma_commit(sd_full);
+        mbar_wait(ds_full, par);                // P / dS in shared memory, S / dP read out
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < LPAD / 16; ++k)     // dQ = dS K
+          umma_bf16(tmem_base + Cfg::TM_DQ, make_smem_desc(adS + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                    make_smem_desc(aK + k * 2048, 8192, 1024), idesc_dq, k > 0 ? 1u : 0u);
+        const int rows = min(128, L - t * 128);
+        const int nk = (rows + 15) / 16;        // query k-steps: rows beyond the tile's live queries hold zeros in P / dS
+#pragma unroll
+        for (int m = 0; m < NM; ++m) {
+          for (int k = 0; k < nk; ++k)          // dK = dS^T Q
+            umma_bf16(tmem_base + Cfg::TM_DK + m * 64, make_smem_desc(adS + m * 32768 + k * 2048, 16384, 1024),
+                      make_smem_desc(aQ + k * 2048, 8192, 1024), idesc_dkv, k > 0 ? 1u : 0u);
+          for (int k = 0; k < nk; ++k)          // dV = P^T dO
+            umma_bf16(tmem_base + Cfg::TM_DV + m * 64, make_smem_desc(aP + m * 32768 + k * 2048, 16384, 1024),
+                      make_smem_desc(adO + k * 2048, 8192, 1024), idesc_dkv, k > 0 ? 1u : 0u);
+        }
+        umma_commit(out_full);
+        umma_commit(qdo_empty);
+        if (t == NT - 1) umma_commit(kv_empty);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int wg = (warp - 2) >> 2;
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    const int wgt = threadIdx.x - 64;          // 0..255
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const float scale2 = a.scale * 1.4426950408889634f;
+    uint8_t* myS = sdS + (r >> 3) * 1024 + (r & 7) * 128;
+    uint8_t* myP = sP + (r >> 3) * 1024 + (r & 7) * 128;
+    const int sw = r & 7;
+    constexpr int C_END0 = SPLIT, C_END1 = LPAD;
+    int cur_h = -1;
+    for (int tau = 0; tau < n_tiles; ++tau) {
+      const int item = item0 + tau / NT, t = tau % NT;
+      const int h = item / a.B, b = item % a.B;
+      const uint32_t par = (uint32_t)tau & 1u;
+      const int qi = t * 128 + r;
+      if (h != cur_h) {
+        named_bar_sync(1, 256);
+        for (int i = wgt; i < Cfg::T; i += 256)
+          tab[Cfg::OFFMAX + 1 + i] = a.table ? __ldg(a.table + (int64_t)i * a.H + h) * 1.4426950408889634f : 0.f;
+        const float row0 = a.table ? __ldg(a.table + (int64_t)(Cfg::T - 3) * a.H + h) * 1.4426950408889634f : 0.f;
+        for (int i = wgt; i <= Cfg::OFFMAX; i += 256) tab[i] = row0;
+        named_bar_sync(1, 256);
+        cur_h = h;
+      }
+      const int qc = qi < L ? qi : L - 1;
+      const bool row_ok = qi < L;
+      const bool wv = __any_sync(0xffffffffu, row_ok);
+      const int rb_off = qc >= 1 ? Cfg::OFFMAX + 1 + (((qc - 1) / W) + W - 1) * (2 * W - 1) + ((qc - 1) % W) + W - 1
+                                 : Cfg::OFFMAX;
+      const float* rb = tab + rb_off;
+      const int c0_idx = Cfg::OFFMAX + 1 + (qc >= 1 ? Cfg::T - 2 : Cfg::T - 1);
+      const float bias_c0 = tab[c0_idx];
+      const int64_t st_row = ((int64_t)b * a.H + h) * L + qc;
+      const float lse2 = __ldg(a.lse + st_row) * 1.4426950408889634f;
+      const float dl = __ldg(a.delta + st_row);
+      mbar_wait(sd_full, par);
+      tc_fence_after();
+      const int cb = wg == 0 ? 0 : C_END0, ce = wg == 0 ? C_END0 : C_END1;
+#pragma unroll
+      for (int cc = 0; cc < LPAD; cc += 32) {
+        if (cc >= (SPLIT > LPAD - SPLIT ? SPLIT : LPAD - SPLIT)) continue;
+        const int c0 = cb + cc;
+        if (c0 >= ce) continue;
+        const bool full = c0 + 32 <= ce;
+        if (!wv) {   // every row of this warp lies beyond the last query (second tile): only clear its operand rows
+#pragma unroll
+          for (int g8 = 0; g8 < 4; ++g8) {
+            if (!full && g8 >= 2) continue;
+            const int col8 = c0 + g8 * 8;
+            const int off8 = (col8 >> 6) * 16384 + ((((col8 & 63) >> 3) ^ sw) << 4);
+            *(uint4*)(myS + off8) = make_uint4(0u, 0u, 0u, 0u);
+            *(uint4*)(myP + off8) = make_uint4(0u, 0u, 0u, 0u);
+          }
+          continue;
+        }
+        uint32_t vs[32], vp[32];
+        if (full) {
+          tmem_ld_32x32(lane_base + TM_S + c0, vs);
+          tmem_ld_32x32(lane_base + TM_DP + c0, vp);
+        } else {
+          tmem_ld_32x32_16(lane_base + TM_S + c0, vs);
+          tmem_ld_32x32_16(lane_base + TM_DP + c0, vp);
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+          if (!full && g8 >= 2) continue;
+          const int col8 = c0 + g8 * 8;
+          const int off8 = (col8 >> 6) * 16384 + ((((col8 & 63) >> 3) ^ sw) << 4);
+          float ds[8], pp[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int j = c0 + g8 * 8 + e;
+            float bias2;
+            if (wg == 0) {
+              const int jc = cc + g8 * 8 + e;
+              bias2 = jc == 0 ? bias_c0 : *(rb - rel_off<W>(jc));
+            } else {
+              const int jc = SPLIT + cc + g8 * 8 + e;
+              bias2 = *(rb - rel_off<W>(jc));
+            }
+            float p = ex2_approx(fmaf(__uint_as_float(vs[g8 * 8 + e]), scale2, bias2) - lse2);
+            if (j >= L || !row_ok) p = 0.f;
+            pp[e] = p;
+            ds[e] = p * (__uint_as_float(vp[g8 * 8 + e]) - dl);
+          }
+          st_bf16x8(myS + off8, ds);
+          st_bf16x8(myP + off8, pp);
+          if (a.ds_dump && row_ok && col8 < a.ds_ld)
+            st_bf16x8((uint8_t*)(a.ds_dump + (st_row * a.ds_ld + col8)), ds);
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ds_full);
+      // ---- outputs: 32-column units [dQ | dK tiles | dV tiles]; warpgroup 0 drains the first half, warpgroup 1 the rest
+      mbar_wait(out_full, par);
+      tc_fence_after();
+      constexpr int UH = Cfg::UNITS / 2;
+#pragma unroll
+      for (int i0 = 0; i0 < UH; i0 += 2) {      // two units (64 registers) at a time
+        uint32_t o[2][32];
+        tmem_ld_32x32(lane_base + (uint32_t)((wg * UH + i0) * 32), o[0]);
+        if (i0 + 1 < UH) tmem_ld_32x32(lane_base + (uint32_t)((wg * UH + i0 + 1) * 32), o[1]);
+        tmem_ld_wait();
+        if (i0 + 2 >= UH) {                      // last read of this tile's outputs: TMEM may be overwritten
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(out_empty);
+        }
+#pragma unroll
+        for (int ii = 0; ii < 2; ++ii) {
+          if (i0 + ii >= UH) continue;
+          const int u = wg * UH + i0 + ii;      // unit -> (tensor, key tile, column half)
+          bf16* dst = nullptr;
+          float mul = a.scale;
+          bool add = false;
+          if (u < 2) {
+            if (row_ok) dst = a.dq + ((int64_t)b * L + qi) * a.dq_stride + h * TC_HD + u * 32;
+          } else {
+            const bool is_dv = u >= 2 + 2 * NM;
+            const int uu = is_dv ? u - 2 - 2 * NM : u - 2;
+            const int key = (uu >> 1) * 128 + r;
+            if (key < L)
+              dst = (is_dv ? a.dv + ((int64_t)b * L + key) * a.dv_stride : a.dk + ((int64_t)b * L + key) * a.dk_stride) +
+                    h * TC_HD + (uu & 1) * 32;
+            if (is_dv) mul = 1.0f;
+            add = t > 0;
+          }
+          if (dst) {
+#pragma unroll
+            for (int e = 0; e < 32; e += 8) {
+              float v[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) v[k] = __uint_as_float(o[ii][e + k]) * mul;
+              if (add) {
+                const uint4 prev = *(const uint4*)(dst + e);
+                const __nv_bfloat162* p2 = (const __nv_bfloat162*)&prev;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const float2 f = __bfloat1622float2(p2[k]);
+                  v[2 * k] += f.x;
+                  v[2 * k + 1] += f.y;
+                }
+              }
+              st_bf16x8((uint8_t*)(dst + e), v);
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ host
 static int encode_rows(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint64_t ld_elems, uint32_t box_rows) {
   auto fn = get_tensor_map_encoder();
@@ -936,6 +1235,26 @@ static int launch_vit_bwd(const xfm_attn_params* p, cudaStream_t s) {
   if (!rc) rc = encode_rows(&mk_t, p->k, cols, rows, p->k_stride, 128);
   if (!rc) rc = encode_rows(&mv_t, p->v, cols, rows, p->v_stride, 128);
   if (rc) return rc;
+  const int n_items_f = a.B * a.H;
+  if (!a.dtable) {   // table gradient (if any) comes from the dS dump: one fused kernel for dQ, dK and dV
+    using FCfg = VitFusedCfg<W>;
+    CUtensorMap mq1, mdo1;
+    rc = encode_rows(&mq1, p->q, cols, rows, p->q_stride, 128);
+    if (!rc) rc = encode_rows(&mdo1, p->dout, cols, rows, p->do_stride, 128);
+    if (rc) return rc;
+    static bool fattr = false;
+    if (!fattr) {
+      cudaError_t e = cudaFuncSetAttribute(vit_attn_bwd_fused_tc_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, FCfg::SMEM);
+      if (e != cudaSuccess) return (int)e;
+      fattr = true;
+    }
+    const int ctas = n_items_f < num_sms() ? n_items_f : num_sms();
+    a.items_per_cta = (n_items_f + ctas - 1) / ctas;
+    const int grid = (n_items_f + a.items_per_cta - 1) / a.items_per_cta;
+    vit_attn_bwd_fused_tc_kernel<W><<<grid, TC_THREADS, FCfg::SMEM, s>>>(mq1, mdo1, mk_l, mv_l, a);
+    count_launch();
+    return (int)cudaGetLastError();
+  }
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(vit_attn_bwd_dq_tc_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::DQ_SMEM);

@@ -826,6 +826,316 @@ xattn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
   }
 }
 
+// ================================================================================================ fused backward
+// One kernel for dQ, dK and dV.  A unit is (image, head, chunk of <= 3 samples): ONE 128-row query tile (three 40-row slots).
+// S = Q K^T and dP = dO V^T are computed once, P~ (dropout mask and 1/(1-p) applied) and dS are written to shared memory
+// once, and dQ = dS K (dS read K-major), dK = dS^T Q, dV = P~^T dO (the same buffers read MN-major, keys as the M dimension
+// in two 128-key tiles) are issued from them into the TMEM columns S / dP occupied.  The elementwise stage runs once per
+// (query, key) pair instead of once in a dQ and once more in a dK/dV kernel.  Later chunks of the same image add their
+// dK / dV to the rows the first chunk stored (same CTA, same thread per row: ordered without synchronisation).
+template <int LQS, int LK>
+struct XFusedCfg {
+  static constexpr int GMAX = 3;
+  static_assert(GMAX * LQS <= 128, "three samples per query tile");
+  static constexpr int LPAD = (LK + 15) / 16 * 16;
+  static constexpr int NM = (LPAD + 127) / 128;
+  static constexpr int KV_BYTES = LPAD * 128;
+  static constexpr int PD_BYTES = 2 * NM * 16384;
+  static constexpr int SMEM = 2 * 16384 + 2 * KV_BYTES + 2 * PD_BYTES + 128;
+  static constexpr int SPLIT = ((LPAD / 2 + 15) / 16) * 16;
+  static constexpr int TM_DQ = 0, TM_DK = 64, TM_DV = 64 + 64 * NM, TM_END = 64 + 128 * NM;
+  static constexpr int UNITS = TM_END / 32;
+  static_assert(2 * LPAD <= 512 && TM_END <= 512, "TMEM");
+  static_assert(SMEM <= 232448, "shared memory");
+};
+
+template <int LQS, int LK>
+__global__ void __launch_bounds__(XT_THREADS, 1)
+xattn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
+                          const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v, const XAttnArgs a) {
+  using Cfg = XFusedCfg<LQS, LK>;
+  constexpr int LPAD = Cfg::LPAD, GMAX = Cfg::GMAX, NM = Cfg::NM, SPLIT = Cfg::SPLIT;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if (smem_u32(smem) & 1023) __trap();
+  uint8_t* sQ = smem;
+  uint8_t* sdO = sQ + 16384;
+  uint8_t* sK = sdO + 16384;
+  uint8_t* sV = sK + Cfg::KV_BYTES;
+  uint8_t* sdS = sV + Cfg::KV_BYTES;
+  uint8_t* sP = sdS + Cfg::PD_BYTES;
+  uint64_t* bars = (uint64_t*)(sP + Cfg::PD_BYTES);
+  uint64_t *kv_full = bars, *kv_empty = bars + 1, *qdo_full = bars + 2, *qdo_empty = bars + 3, *sd_full = bars + 4,
+           *ds_full = bars + 5, *out_full = bars + 6, *out_empty = bars + 7;
+  uint32_t* tmem_ptr = (uint32_t*)(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 2 * 16384 / 16; i += blockDim.x) ((uint4*)sQ)[i] = make_uint4(0u, 0u, 0u, 0u);  // unused slots stay finite
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_q);
+    tma_prefetch_desc(&map_do);
+    tma_prefetch_desc(&map_k);
+    tma_prefetch_desc(&map_v);
+    mbar_init(kv_full, 1);
+    mbar_init(kv_empty, 1);
+    mbar_init(qdo_full, 1);
+    mbar_init(qdo_empty, 1);
+    mbar_init(sd_full, 1);
+    mbar_init(ds_full, 8);
+    mbar_init(out_full, 1);
+    mbar_init(out_empty, 8);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  constexpr uint32_t TM_S = 0, TM_DP = LPAD;
+
+  const int n_items = a.Bkv * a.H;
+  const int item0 = blockIdx.x * a.items_per_cta;
+  const int item1 = min(n_items, item0 + a.items_per_cta);
+
+  // Every role walks the same unit sequence; K / V are loaded once per item (image, head), Q / dO once per unit.
+  if (warp == 0) {
+    if (lane == 0) {
+      XWalker<GMAX> w(a, item0, item1);
+      XUnit u;
+      uint32_t up = 0, ip = 0;   // unit parity, item parity
+      int cur = -1;
+      while (w.next(u)) {
+        const int id = u.h * a.Bkv + u.r;
+        if (id != cur) {
+          mbar_wait_relaxed(kv_empty, ip ^ 1);
+          mbar_arrive_expect_tx(kv_full, 2 * Cfg::KV_BYTES);
+          tma_load_2d(sK, &map_k, kv_full, u.h * XT_HD, u.r * LK);
+          tma_load_2d(sV, &map_v, kv_full, u.h * XT_HD, u.r * LK);
+          ip ^= 1;
+          cur = id;
+        }
+        mbar_wait_relaxed(qdo_empty, up ^ 1);
+        mbar_arrive_expect_tx(qdo_full, 2 * u.ns * LQS * 128);
+        for (int g = 0; g < u.ns; ++g) {
+          const int b = a.kv_samples[u.first + g];
+          tma_load_2d(sQ + g * (LQS * 128), &map_q, qdo_full, u.h * XT_HD, b * LQS);
+          tma_load_2d(sdO + g * (LQS * 128), &map_do, qdo_full, u.h * XT_HD, b * LQS);
+        }
+        up ^= 1;
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, LPAD, 0, 0);
+      constexpr uint32_t idesc_dq = make_idesc_bf16(128, XT_HD, 0, 1);
+      constexpr uint32_t idesc_dkv = make_idesc_bf16(128, XT_HD, 1, 1);
+      const uint32_t aQ = smem_u32(sQ), adO = smem_u32(sdO), aK = smem_u32(sK), aV = smem_u32(sV), adS = smem_u32(sdS),
+                     aP = smem_u32(sP);
+      XWalker<GMAX> w(a, item0, item1);
+      XUnit u;
+      uint32_t up = 0, ip = 1;
+      int cur = -1;
+      bool have = w.next(u);
+      while (have) {
+        const int id = u.h * a.Bkv + u.r;
+        if (id != cur) {
+          ip ^= 1;
+          mbar_wait(kv_full, ip);
+          cur = id;
+        }
+        const int ns = u.ns;
+        XUnit nu;
+        have = w.next(nu);
+        const bool last_of_item = !have || (nu.h * a.Bkv + nu.r) != id;
+        mbar_wait(qdo_full, up);
+        mbar_wait(out_empty, up ^ 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base + TM_S, make_smem_desc(aQ + k * 32, 16, 1024), make_smem_desc(aK + k * 32, 16, 1024), idesc_s,
+                    k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base + TM_DP, make_smem_desc(adO + k * 32, 16, 1024), make_smem_desc(aV + k * 32, 16, 1024), idesc_s,
+                    k > 0 ? 1u : 0u);
+        umma_commit(sd_full);
+        mbar_wait(ds_full, up);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < LPAD / 16; ++k)
+          umma_bf16(tmem_base + Cfg::TM_DQ, make_smem_desc(adS + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                    make_smem_desc(aK + k * 2048, 8192, 1024), idesc_dq, k > 0 ? 1u : 0u);
+        const int nk = (ns * LQS + 15) / 16;
+#pragma unroll
+        for (int m = 0; m < NM; ++m) {
+          for (int k = 0; k < nk; ++k)
+            umma_bf16(tmem_base + Cfg::TM_DK + m * 64, make_smem_desc(adS + m * 32768 + k * 2048, 16384, 1024),
+                      make_smem_desc(aQ + k * 2048, 8192, 1024), idesc_dkv, k > 0 ? 1u : 0u);
+          for (int k = 0; k < nk; ++k)
+            umma_bf16(tmem_base + Cfg::TM_DV + m * 64, make_smem_desc(aP + m * 32768 + k * 2048, 16384, 1024),
+                      make_smem_desc(adO + k * 2048, 8192, 1024), idesc_dkv, k > 0 ? 1u : 0u);
+        }
+        umma_commit(out_full);
+        umma_commit(qdo_empty);
+        if (last_of_item) umma_commit(kv_empty);
+        up ^= 1;
+        u = nu;
+      }
+    }
+    __syncwarp();
+  } else {
+    const int wg = (warp - 2) >> 2;
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    const int slot = r / LQS, q = r % LQS;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const float scale2 = a.scale * 1.4426950408889634f;
+    const bool drop_on = a.dropout_p > 0.f;
+    const float inv_keep = drop_on ? 1.0f / (1.0f - a.dropout_p) : 1.0f;
+    const uint32_t seed_mix = drop_seed_mix(a.seed), thr = drop_threshold(a.dropout_p);
+    uint8_t* myS = sdS + (r >> 3) * 1024 + (r & 7) * 128;
+    uint8_t* myP = sP + (r >> 3) * 1024 + (r & 7) * 128;
+    const int sw = r & 7;
+    const int cb = wg == 0 ? 0 : SPLIT, ce = wg == 0 ? SPLIT : LPAD;
+    constexpr int LKE = (LK + 1) & ~1;
+    XWalker<GMAX> w(a, item0, item1);
+    XUnit u;
+    uint32_t up = 0;
+    int cur = -1, chunk_of_item = 0;
+    while (w.next(u)) {
+      const int id = u.h * a.Bkv + u.r;
+      chunk_of_item = id == cur ? chunk_of_item + 1 : 0;
+      cur = id;
+      const bool valid = slot < GMAX && slot < u.ns;
+      const bool wv = __any_sync(0xffffffffu, valid);
+      const int b = valid ? a.kv_samples[u.first + slot] : 0;
+      const int64_t st_row = ((int64_t)b * a.H + u.h) * LQS + q;
+      const float lse2 = valid ? __ldg(a.lse + st_row) * 1.4426950408889634f : 0.f;
+      const float dl = valid ? __ldg(a.delta + st_row) : 0.f;
+      const uint64_t pair_base = ((uint64_t)st_row * (uint64_t)LKE) >> 1;
+      const uint32_t pb_lo = (uint32_t)pair_base, pb_hi = (uint32_t)(pair_base >> 32);
+      mbar_wait(sd_full, up);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = cb; c0 < ce; c0 += 32) {
+        const bool full = c0 + 32 <= ce;
+        uint32_t vs[32], vp[32];
+        if (wv) {   // tcgen05.ld is warp-collective: decide per warp, mask per thread
+          if (full) {
+            xt_ld32(lane_base + TM_S + c0, vs);
+            xt_ld32(lane_base + TM_DP + c0, vp);
+          } else {
+            xt_ld16(lane_base + TM_S + c0, vs);
+            xt_ld16(lane_base + TM_DP + c0, vp);
+          }
+          tmem_ld_wait();
+        }
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+          if (!full && g8 >= 2) continue;
+          float ds[8], pp[8];
+#pragma unroll
+          for (int e = 0; e < 8; e += 2) {
+            const int j = c0 + g8 * 8 + e;   // even
+            float d0 = 0.f, d1 = 0.f, p0 = 0.f, p1 = 0.f;
+            if (valid && j < LK) {
+              p0 = ex2_approx(fmaf(__uint_as_float(vs[g8 * 8 + e]), scale2, -lse2));
+              p1 = j + 1 < LK ? ex2_approx(fmaf(__uint_as_float(vs[g8 * 8 + e + 1]), scale2, -lse2)) : 0.f;
+              float k0 = 1.f, k1 = 1.f;
+              if (drop_on) {
+                const uint32_t lo = pb_lo + (uint32_t)(j >> 1);
+                const uint32_t keep = drop_keep_pair(seed_mix, lo, pb_hi + (lo < pb_lo ? 1u : 0u), thr);
+                k0 = (keep & 1u) ? inv_keep : 0.f;
+                k1 = (keep & 2u) ? inv_keep : 0.f;
+              }
+              d0 = p0 * (__uint_as_float(vp[g8 * 8 + e]) * k0 - dl);
+              d1 = p1 * (__uint_as_float(vp[g8 * 8 + e + 1]) * k1 - dl);
+              p0 *= k0;
+              p1 *= k1;
+            }
+            ds[e] = d0;
+            ds[e + 1] = d1;
+            pp[e] = p0;
+            pp[e + 1] = p1;
+          }
+          const int col8 = c0 + g8 * 8;
+          const int off8 = (col8 >> 6) * 16384 + ((((col8 & 63) >> 3) ^ sw) << 4);
+          xt_st_bf16x8(myS + off8, ds);
+          xt_st_bf16x8(myP + off8, pp);
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ds_full);
+      mbar_wait(out_full, up);
+      tc_fence_after();
+      constexpr int UH = Cfg::UNITS / 2;
+#pragma unroll
+      for (int i0 = 0; i0 < UH; i0 += 2) {
+        uint32_t o[2][32];
+        xt_ld32(lane_base + (uint32_t)((wg * UH + i0) * 32), o[0]);
+        if (i0 + 1 < UH) xt_ld32(lane_base + (uint32_t)((wg * UH + i0 + 1) * 32), o[1]);
+        tmem_ld_wait();
+        if (i0 + 2 >= UH) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(out_empty);
+        }
+#pragma unroll
+        for (int ii = 0; ii < 2; ++ii) {
+          if (i0 + ii >= UH) continue;
+          const int un = wg * UH + i0 + ii;
+          bf16* dst = nullptr;
+          float mul = a.scale;
+          bool add = false;
+          if (un < 2) {
+            if (valid) dst = a.dq + ((int64_t)b * LQS + q) * a.dq_stride + u.h * XT_HD + un * 32;
+          } else {
+            const bool is_dv = un >= 2 + 2 * NM;
+            const int uu = is_dv ? un - 2 - 2 * NM : un - 2;
+            const int key = (uu >> 1) * 128 + r;
+            if (key < LK)
+              dst = (is_dv ? a.dv + ((int64_t)u.r * LK + key) * a.dv_stride : a.dk + ((int64_t)u.r * LK + key) * a.dk_stride) +
+                    u.h * XT_HD + (uu & 1) * 32;
+            if (is_dv) mul = 1.0f;
+            add = chunk_of_item > 0;
+          }
+          if (dst) {
+#pragma unroll
+            for (int e = 0; e < 32; e += 8) {
+              float vv[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) vv[k] = __uint_as_float(o[ii][e + k]) * mul;
+              if (add) {
+                const uint4 prev = *(const uint4*)(dst + e);
+                const __nv_bfloat162* p2 = (const __nv_bfloat162*)&prev;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const float2 f = __bfloat1622float2(p2[k]);
+                  vv[2 * k] += f.x;
+                  vv[2 * k + 1] += f.y;
+                }
+              }
+              xt_st_bf16x8((uint8_t*)(dst + e), vv);
+            }
+          }
+        }
+      }
+      up ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ host
 static int xt_encode_rows(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint64_t ld_elems, uint32_t box_rows) {
   auto fn = get_tensor_map_encoder();
@@ -908,6 +1218,21 @@ int cross_attention_bwd_tc(const xfm_attn_params* p, cudaStream_t s) {
   if (!rc) rc = xt_encode_rows(&mk_t, p->k, cols, (uint64_t)a.Bkv * LK, p->k_stride, 128);
   if (!rc) rc = xt_encode_rows(&mv_t, p->v, cols, (uint64_t)a.Bkv * LK, p->v_stride, 128);
   if (rc) return rc;
+  if (!p->ds_dump) {   // one fused kernel for dQ, dK and dV
+    using FCfg = XFusedCfg<LQS, LK>;
+    auto kf = xattn_bwd_fused_tc_kernel<LQS, LK>;
+    static bool fattr = false;
+    if (!fattr) {
+      cudaError_t e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, FCfg::SMEM);
+      if (e != cudaSuccess) return (int)e;
+      fattr = true;
+    }
+    const int n_items_f = a.Bkv * a.H;
+    const int grid_f = (n_items_f + a.items_per_cta - 1) / a.items_per_cta;
+    kf<<<grid_f, XT_THREADS, FCfg::SMEM, s>>>(mq, mdo, mk_l, mv_l, a);
+    count_launch();
+    return (int)cudaGetLastError();
+  }
   constexpr int DQ_SMEM = 2 * Cfg::Q_BYTES + 2 * Cfg::KV_BYTES + Cfg::P_BYTES + 128;
   auto kdq = xattn_bwd_dq_tc_kernel<LQS, LK, GMAX>;
   auto kdkv = xattn_bwd_dkv_tc_kernel<LQS, LK, GMAX>;
