@@ -66,6 +66,19 @@ XFM_DEVINL void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* ba
       : "memory");
 }
 
+// TMA store (shared -> global, bulk-group completion).  The source tile must be written with generic-proxy stores followed
+// by fence.proxy.async before the issuing thread executes the copy; out-of-range rows / columns of the box are clipped.
+XFM_DEVINL void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+XFM_DEVINL void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+XFM_DEVINL void tma_store_wait_read() {   // at most N of this thread's bulk groups may still be READING shared memory
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+
 // ----------------------------------------------------------------------------- tcgen05 / TMEM
 XFM_DEVINL void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)

@@ -35,6 +35,7 @@ struct GemmArgs {
   uint64_t dropout_seed;
   int vec_ok;    // every epilogue pointer / leading dimension allows 2-element vector access at even columns
   int epi_mode;  // see epilogue_block
+  int tma_epi;   // CTA-pair kernel: modes 0 / 1 store bf16 tiles with TMA (epilogue_tma_block)
 };
 
 template <int BLOCK_N>
@@ -260,6 +261,98 @@ XFM_DEVINL void epilogue_one(const GemmArgs& g, float* stage, uint32_t taddr, in
   else epilogue_block<MODE, false>(g, stage, row_base, n, lane);
 }
 
+// ---------------------------------------------------------------------------------------------- TMA-store epilogue
+// Modes 0 and 1 of the CTA-pair kernel (bf16 outputs).  The accumulator block stays in its tcgen05.ld layout (lane = row,
+// 32 consecutive columns): bias / GELU / dGELU are applied in registers, the bf16 row (64 bytes) goes to a dense 32 x 32
+// staging tile in shared memory and ONE thread hands the tile to the TMA engine, which writes full 64-byte row segments and
+// clips rows / columns beyond the matrix.  No transposition pass, no per-row address arithmetic, no bounds predicates: about
+// 70 instructions per lane and block instead of ~500, which is what the fused epilogues are bound by.
+// Four staging tiles per warp (8 KB): the saved pre-activation and the output of a block use two, so the copies of block i
+// still read shared memory while block i + 1 is computed (cp.async.bulk.wait_group.read keeps at most one block in flight).
+constexpr int TMA_EPI_TILE_BYTES = 32 * 32 * 2;
+constexpr int TMA_EPI_WARP_BYTES = 4 * TMA_EPI_TILE_BYTES;
+
+XFM_DEVINL void st_row_bf16x32(uint8_t* row, const float (&v)[32]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint4 u;
+    __nv_bfloat162 t0 = __floats2bfloat162_rn(v[8 * c], v[8 * c + 1]), t1 = __floats2bfloat162_rn(v[8 * c + 2], v[8 * c + 3]);
+    __nv_bfloat162 t2 = __floats2bfloat162_rn(v[8 * c + 4], v[8 * c + 5]), t3 = __floats2bfloat162_rn(v[8 * c + 6], v[8 * c + 7]);
+    u.x = *(uint32_t*)&t0; u.y = *(uint32_t*)&t1; u.z = *(uint32_t*)&t2; u.w = *(uint32_t*)&t3;
+    *(uint4*)(row + 16 * c) = u;
+  }
+}
+
+template <int MODE>
+XFM_DEVINL void epilogue_tma_block(const GemmArgs& g, const CUtensorMap* map_c, const CUtensorMap* map_aux, uint8_t* tiles,
+                                   int& slot, uint32_t taddr, int row_base, int n, int lane, bool has_work) {
+  uint32_t r[32];
+  tmem_ld_32x32(taddr, r);
+  // dGELU operand: this lane's row, 64 contiguous bytes; issued before the TMEM wait so the two latencies overlap
+  uint4 aux[4] = {};
+  const int row = row_base + lane;
+  if (MODE == 1 && has_work && row < g.M) {
+    const bf16* ap = g.aux_in + (int64_t)row * g.ld_aux_in + n;
+    if (n + 32 <= g.N) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) aux[c] = *(const uint4*)(ap + 8 * c);
+    } else {
+      bf16* a16 = (bf16*)aux;
+      for (int j = 0; j < 32 && n + j < g.N; ++j) a16[j] = ap[j];
+    }
+  }
+  tmem_ld_wait();
+  if (!has_work) return;
+  float v[32];
+  if (g.bias) {
+    if (n + 32 <= g.N) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float4 b4 = __ldg((const float4*)(g.bias + n) + c);
+        v[4 * c] = __uint_as_float(r[4 * c]) + b4.x;
+        v[4 * c + 1] = __uint_as_float(r[4 * c + 1]) + b4.y;
+        v[4 * c + 2] = __uint_as_float(r[4 * c + 2]) + b4.z;
+        v[4 * c + 3] = __uint_as_float(r[4 * c + 3]) + b4.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + (n + j < g.N ? __ldg(g.bias + n + j) : 0.f);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  }
+  // the copies issued two blocks ago have finished reading their staging tiles
+  if (lane == 0) tma_store_wait_read<1>();
+  __syncwarp();
+  const bool has_aux_out = MODE == 0 && g.aux_out != nullptr;
+  uint8_t* t_aux = tiles + slot * TMA_EPI_TILE_BYTES;
+  uint8_t* t_c = tiles + (slot ^ 1) * TMA_EPI_TILE_BYTES;
+  if (has_aux_out) st_row_bf16x32(t_aux + lane * 64, v);
+  if (MODE == 0 && g.act == 1) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+  }
+  if (MODE == 1) {
+    const __nv_bfloat162* a2 = (const __nv_bfloat162*)aux;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float2 af = __bfloat1622float2(a2[j]);
+      v[2 * j] *= gelu_grad_fast(af.x);
+      v[2 * j + 1] *= gelu_grad_fast(af.y);
+    }
+  }
+  st_row_bf16x32(t_c + lane * 64, v);
+  fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) {
+    if (has_aux_out) tma_store_2d(map_aux, t_aux, n, row_base);
+    tma_store_2d(map_c, t_c, n, row_base);
+    tma_store_commit();
+  }
+  slot ^= 2;
+}
+
 template <int BLOCK_N, int A_MN, int B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -430,12 +523,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 // 49 % busy), which is where cuBLAS's 1.5 PF on these shapes comes from.
 constexpr int PAIR_STAGES = 5;
 constexpr int PAIR_STAGE_BYTES = 2 * 16384;  // A 128 x 64 + B 128 x 64 (bf16)
-constexpr int PAIR_SMEM_BYTES = PAIR_STAGES * PAIR_STAGE_BYTES + 8 * 32 * 34 * 4 + 256;
+constexpr int PAIR_EPI_BYTES = 8 * TMA_EPI_WARP_BYTES;   // 64 KB: TMA staging tiles; the fp32 transposition blocks of mode 2 alias it
+static_assert(PAIR_EPI_BYTES >= 8 * 32 * 34 * 4, "mode-2 staging must fit");
+constexpr int PAIR_SMEM_BYTES = PAIR_STAGES * PAIR_STAGE_BYTES + PAIR_EPI_BYTES + 256;
+static_assert(PAIR_SMEM_BYTES <= 232448, "shared memory");
 
 template <int A_MN, int B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                         const GemmArgs g) {
+                         const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_aux, const GemmArgs g) {
   constexpr int STAGES = PAIR_STAGES;
   constexpr int BLOCK_N = 256;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -443,7 +539,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * 16384;
   float* epi_stage = (float*)(smem + STAGES * PAIR_STAGE_BYTES);
-  uint64_t* bars = (uint64_t*)(smem + STAGES * PAIR_STAGE_BYTES + 8 * 32 * 34 * 4);
+  uint64_t* bars = (uint64_t*)(smem + STAGES * PAIR_STAGE_BYTES + PAIR_EPI_BYTES);
   uint64_t* full_bar = bars;                    // [STAGES]  used in the leader CTA only
   uint64_t* empty_bar = bars + STAGES;          // [STAGES]  one per CTA, arrived by the leader's multicast commit
   uint64_t* tmem_full = bars + 2 * STAGES;      // [2]       one per CTA, multicast commit
@@ -555,6 +651,8 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     constexpr int C_PER_WARP = BLOCK_N / (2 * EPI_COLS);
     const int c_begin = (ew >> 2) * C_PER_WARP;
     float* stage = epi_stage + ew * EPI_WARP_FLOATS;
+    uint8_t* tma_tiles = (uint8_t*)epi_stage + ew * TMA_EPI_WARP_BYTES;
+    int tma_slot = 0;
     int as = 0;
     uint32_t aphase = 0;
     for (int t = pair_id; t < num_tiles; t += num_pairs) {
@@ -574,7 +672,10 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
         const int n = n0 + c * EPI_COLS;
         if (n >= g.N) break;
         const uint32_t taddr = t_base + c * EPI_COLS;
-        if (g.epi_mode == 0) epilogue_one<0>(g, stage, taddr, row_base, n, lane, has_work);
+        if (g.tma_epi) {
+          if (g.epi_mode == 0) epilogue_tma_block<0>(g, &map_c, &map_aux, tma_tiles, tma_slot, taddr, row_base, n, lane, has_work);
+          else epilogue_tma_block<1>(g, &map_c, &map_aux, tma_tiles, tma_slot, taddr, row_base, n, lane, has_work);
+        } else if (g.epi_mode == 0) epilogue_one<0>(g, stage, taddr, row_base, n, lane, has_work);
         else if (g.epi_mode == 1) epilogue_one<1>(g, stage, taddr, row_base, n, lane, has_work);
         else epilogue_one<2>(g, stage, taddr, row_base, n, lane, has_work);
       }
@@ -586,6 +687,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
       }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
+    if (g.tma_epi && lane == 0) tma_store_wait_read<0>();   // shared memory must outlive the last copies
   }
 
   tc_fence_before();
@@ -612,6 +714,26 @@ static int encode_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_
     set_error("cuTensorMapEncodeTiled failed: %d (inner=%llu outer=%llu ld=%llu box=%u,%u base=%p)", (int)r,
               (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld_elems, box_inner, box_outer,
               base);
+    return XFM_ERR_BAD_ARG;
+  }
+  return 0;
+}
+
+// bf16 [outer, inner] tile map without swizzle (TMA-store epilogue: dense 64-byte rows in shared memory)
+static int encode_2d_plain(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
+                           uint32_t box_inner, uint32_t box_outer) {
+  auto fn = get_tensor_map_encoder();
+  if (!fn) return XFM_ERR_NO_DRIVER;
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (output) failed: %d (inner=%llu outer=%llu ld=%llu base=%p)", (int)r,
+              (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld_elems, base);
     return XFM_ERR_BAD_ARG;
   }
   return 0;
@@ -662,7 +784,19 @@ static int launch_gemm_pair(const xfm_gemm_params* p, const GemmArgs& g, cudaStr
   const int num_tiles = ((g.num_m_tiles + 1) / 2) * g.num_n_tiles * g.split_k;
   const int max_pairs = num_sms() / 2;
   const int pairs = num_tiles < max_pairs ? num_tiles : max_pairs;
-  kern<<<2 * pairs, GEMM_THREADS, PAIR_SMEM_BYTES, stream>>>(map_a, map_b, g);
+  CUtensorMap map_c = map_a, map_aux = map_a;   // placeholders when the TMA-store epilogue is not used
+  GemmArgs g2 = g;
+  g2.tma_epi = 0;
+  if ((g.epi_mode == 0 || g.epi_mode == 1) && g.split_k == 1 && ((uintptr_t)p->C & 15) == 0 && (p->ldc & 7) == 0 &&
+      (!p->aux_out || (((uintptr_t)p->aux_out & 15) == 0 && (p->ld_aux_out & 7) == 0)) &&
+      (!p->aux_in || (((uintptr_t)p->aux_in & 15) == 0 && (p->ld_aux_in & 7) == 0)) &&
+      (!p->bias || ((uintptr_t)p->bias & 15) == 0)) {
+    rc = encode_2d_plain(&map_c, p->C, p->N, p->M, p->ldc, 32, 32);
+    if (!rc && g.epi_mode == 0 && p->aux_out) rc = encode_2d_plain(&map_aux, p->aux_out, p->N, p->M, p->ld_aux_out, 32, 32);
+    if (rc) return rc;
+    g2.tma_epi = 1;
+  }
+  kern<<<2 * pairs, GEMM_THREADS, PAIR_SMEM_BYTES, stream>>>(map_a, map_b, map_c, map_aux, g2);
   count_launch();
   return (int)cudaGetLastError();
 }
