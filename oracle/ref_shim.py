@@ -205,3 +205,63 @@ def build_reference_xfm(cfg, sd_full):
     model.load_state_dict(load, strict=False)
     model.eval()
     return model
+
+
+def build_reference_vqa(cfg, sd_full):
+    """Build the reference's `models.model_generation.XFMForVQA` (BASELINE config #5) with dims from `cfg`
+    (`dec_layers` decoder layers, decoder_fusion_start_at 0) and load `sd_full` (reference key layout)."""
+    install()
+    import contextlib
+    import yaml
+
+    if "dataset" not in sys.modules:
+        # model_generation.py:17 imports build_tokenizer from the data package, which needs pycocotools etc.; XFMForVQA
+        # never calls it.
+        _mod("dataset", build_tokenizer=lambda *a, **k: None)
+    cwd = os.getcwd()
+    os.chdir(REF_ROOT)
+    try:
+        config = yaml.safe_load(open("configs/xfm-ft/VQA.yaml"))
+        config["text_encoder"] = roberta_config_dir(cfg)
+        config["image_res"] = cfg["image_res"]
+        vdir = tempfile.mkdtemp(prefix="beit2-base-")
+        with open(os.path.join(vdir, "config_beit2_base.json"), "w") as f:
+            json.dump(dict(ckpt="", vision_width=cfg["vision_width"], patch_size=cfg["patch_size"]), f)
+        config.update(vision_config=os.path.join(vdir, "config_beit2_base.json"), patch_size=cfg["patch_size"],
+                      text_num_hidden_layers=cfg["text_layers"], text_fusion_start_at=cfg["text_layers"],
+                      fusion_num_hidden_layers=cfg["fusion_layers"], num_dec_layers=cfg["dec_layers"],
+                      decoder_fusion_start_at=0, pad_token_id=cfg["pad_id"])
+        import models.beit2 as beit2
+        from functools import partial
+
+        orig_factory = beit2.beit_base_patch16
+        if cfg["vision_width"] != 768 or cfg["vision_depth"] != 12:
+            def small(img_size, **kw):
+                return beit2.VisionTransformer(img_size=img_size, patch_size=cfg["patch_size"],
+                                               embed_dim=cfg["vision_width"], depth=cfg["vision_depth"],
+                                               num_heads=cfg["vision_heads"],
+                                               mlp_ratio=cfg["vision_mlp"] / cfg["vision_width"],
+                                               norm_layer=partial(nn.LayerNorm, eps=1e-6), **kw)
+
+            beit2.beit_base_patch16 = small
+        try:
+            with contextlib.redirect_stdout(open(os.devnull, "w")):
+                from models.model_generation import XFMForVQA
+
+                model = XFMForVQA(config)
+        finally:
+            beit2.beit_base_patch16 = orig_factory
+    finally:
+        os.chdir(cwd)
+    own = model.state_dict()
+    # fine-tuning models hold a bare RobertaModel as text_encoder (xfm.py:397-403): keys lose the 'roberta.' level
+    sd_full = {(k.replace("text_encoder.roberta.", "text_encoder.") if k.startswith("text_encoder.roberta.") else k): v
+               for k, v in sd_full.items()}
+    missing = [k for k in own if k not in sd_full]
+    assert not missing, f"synthetic state_dict misses reference keys: {missing[:8]}"
+    load = {k: v for k, v in sd_full.items() if k in own}
+    for k, v in load.items():
+        assert tuple(own[k].shape) == tuple(v.shape), (k, own[k].shape, v.shape)
+    model.load_state_dict(load, strict=True)
+    model.eval()
+    return model

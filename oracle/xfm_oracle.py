@@ -114,7 +114,7 @@ def param_shapes(cfg):
     s[v + "fc_norm.weight"] = (D,)
     s[v + "fc_norm.bias"] = (D,)
 
-    def roberta(prefix, layers, cross):
+    def roberta(prefix, layers, cross, kin=D, heads=("lm_head", "lm_cap_head")):
         e = prefix + "roberta.embeddings."
         s[e + "word_embeddings.weight"] = (V, H)
         s[e + "position_embeddings.weight"] = (cfg["max_pos"], H)
@@ -123,7 +123,7 @@ def param_shapes(cfg):
         s[e + "LayerNorm.bias"] = (H,)
         for i in range(layers):
             l = f"{prefix}roberta.encoder.layer.{i}."
-            for att, kin in (("attention", H),) + ((("crossattention", D),) if cross else ()):
+            for att, kin in (("attention", H),) + ((("crossattention", kin),) if cross else ()):
                 s[l + att + ".self.query.weight"] = (H, H)
                 s[l + att + ".self.query.bias"] = (H,)
                 s[l + att + ".self.key.weight"] = (H, kin)
@@ -140,7 +140,7 @@ def param_shapes(cfg):
             s[l + "output.dense.bias"] = (H,)
             s[l + "output.LayerNorm.weight"] = (H,)
             s[l + "output.LayerNorm.bias"] = (H,)
-        for head in ("lm_head", "lm_cap_head"):
+        for head in heads:
             h = prefix + head + "."
             s[h + "bias"] = (V,)
             s[h + "dense.weight"] = (H, H)
@@ -152,6 +152,10 @@ def param_shapes(cfg):
 
     roberta("text_encoder.", cfg["text_layers"], cross=False)
     roberta("fusion_encoder.", cfg["fusion_layers"], cross=True)
+    if cfg.get("dec_layers", 0) > 0:
+        # XFMForVQA.text_decoder = RobertaForCausalLM (models/model_generation.py:41-54): cross-attention over the
+        # question states (encoder_width = hidden) in every layer (decoder_fusion_start_at 0), one tied LM head
+        roberta("text_decoder.", cfg["dec_layers"], cross=True, kin=H, heads=("lm_head",))
     E = cfg["embed_dim"]
     s["vision_proj.weight"] = (E, D)
     s["vision_proj.bias"] = (E,)
@@ -263,6 +267,11 @@ def expand_tied(sd, cfg):
         out[p + "lm_head.decoder.weight"] = out[p + "roberta.embeddings.word_embeddings.weight"]
         out[p + "lm_head.decoder.bias"] = out[p + "lm_head.bias"]
         out[p + "lm_cap_head.decoder.bias"] = out[p + "lm_cap_head.bias"]
+    if cfg.get("dec_layers", 0) > 0:
+        p = "text_decoder."
+        out[p + "roberta.embeddings.position_ids"] = torch.arange(cfg["max_pos"]).expand((1, -1)).clone()
+        out[p + "lm_head.decoder.weight"] = out[p + "roberta.embeddings.word_embeddings.weight"]
+        out[p + "lm_head.decoder.bias"] = out[p + "lm_head.bias"]
     return out
 
 
@@ -695,6 +704,108 @@ def mim_loss_vqkd(image_embeds_masked, image, mask, sd, cfg):
         ids = vqkd_codebook_indices(image, sd, cfg)
     logits = F.linear(image_embeds_masked[:, 1:, :][mask], sd["lm_head.weight"], sd["lm_head.bias"])
     return F.cross_entropy(logits, ids[mask])
+
+
+# ----------------------------------------------------------------------------------------------
+# VQA: cross-modal causal decoder (models/model_generation.py:23-202, models/xroberta.py:963-1123)
+# ----------------------------------------------------------------------------------------------
+
+
+def causal_extended_mask(atts):
+    """models/xroberta.py:771-806 with is_decoder=True: (1 - causal[i,j] * atts[b,j]) * -10000, [B,1,L,L]."""
+    L = atts.shape[1]
+    ids = torch.arange(L)
+    causal = (ids[None, :] <= ids[:, None]).to(torch.float32)  # [i, j]: key j visible from query i
+    ext = causal[None, None, :, :] * atts[:, None, None, :].to(torch.float32)
+    return (1.0 - ext) * -10000.0
+
+
+def decoder_forward(input_ids, atts, enc_states, enc_atts, sd, cfg, prefix="text_decoder."):
+    """RobertaForCausalLM.forward up to the LM head (models/xroberta.py:1079-1097): embeddings, then every layer =
+    causal self-attention -> cross-attention over `enc_states` (mask: invert_attention_mask, :903-909) -> FFN.
+    Returns the vocabulary logits [B, L, V]."""
+    h = roberta_embeddings(input_ids, sd, prefix, cfg)
+    m = causal_extended_mask(atts)
+    em = inverted_mask(enc_atts)
+    for i in range(cfg["dec_layers"]):
+        h = roberta_layer(h, m, sd, f"{prefix}roberta.encoder.layer.{i}.", cfg, enc_states, em)
+    return lm_head(h, sd, prefix, cfg)
+
+
+def causal_lm_loss(logits, labels):
+    """models/xroberta.py:1104-1110 with reduction='none': next-token CE (ignore_index -100), summed per sequence."""
+    V = logits.shape[-1]
+    loss = F.cross_entropy(logits[:, :-1, :].reshape(-1, V), labels[:, 1:].reshape(-1), reduction="none")
+    return loss.view(logits.shape[0], -1).sum(1)
+
+
+def vqa_question_states(image, q_ids, q_atts, sd, cfg):
+    """models/model_generation.py:94-109: vision encoder, text encoder, fusion encoder (is_pretrain=False)."""
+    image_embeds = vision_forward(image, sd, cfg)
+    image_atts = torch.ones(image_embeds.shape[:-1], dtype=torch.long)
+    text_embeds = text_forward(q_ids, q_atts, sd, cfg)
+    return fusion_forward(text_embeds, q_atts, image_embeds, image_atts, sd, cfg)
+
+
+def vqa_train_loss(image, q_ids, q_atts, a_ids, a_atts, k, weights, sd, cfg, collect=None):
+    """XFMForVQA.forward(train=True) (models/model_generation.py:96-131): every answer of question b attends to
+    question_output[b]; loss = sum(weights * per-answer loss) / batch."""
+    q_out = vqa_question_states(image, q_ids, q_atts, sd, cfg)
+    rep = torch.repeat_interleave(torch.arange(len(k)), torch.as_tensor(k))
+    targets = a_ids.masked_fill(a_ids == cfg["pad_id"], -100)
+    logits = decoder_forward(a_ids, a_atts, q_out[rep], q_atts[rep], sd, cfg)
+    per_answer = causal_lm_loss(logits, targets)
+    if collect is not None:
+        collect.update(question_output=q_out, answer_loss=per_answer, logits=logits)
+    return (weights * per_answer).sum() / image.shape[0]
+
+
+def vqa_rank_answer(q_states, q_atts, answer_ids, answer_atts, k, sd, cfg):
+    """XFMForVQA.rank_answer (models/model_generation.py:146-202): first-token probabilities of every candidate,
+    top-k, full-sequence log-likelihood of those k, softmax re-rank."""
+    nq = q_states.shape[0]
+    start = answer_ids[0, 0].repeat(nq, 1)
+    logits = decoder_forward(start, torch.ones_like(start), q_states, q_atts, sd, cfg)[:, 0, :]
+    p_first = torch.softmax(logits, dim=1).index_select(1, answer_ids[:, 1])
+    topk_probs, topk_ids = p_first.topk(k, dim=1)
+    ids = answer_ids[topk_ids.reshape(-1)]
+    atts = answer_atts[topk_ids.reshape(-1)]
+    targets = ids.masked_fill(ids == cfg["pad_id"], -100)
+    rep = torch.repeat_interleave(torch.arange(nq), k)
+    loss = causal_lm_loss(decoder_forward(ids, atts, q_states[rep], q_atts[rep], sd, cfg), targets)
+    log_probs = torch.cat([topk_probs.view(-1, 1).log(), -loss.view(-1, 1)], dim=1).sum(1).view(nq, k)
+    probs, rerank = torch.softmax(log_probs, dim=-1).topk(k, dim=1)
+    return torch.gather(topk_ids, 1, rerank), probs
+
+
+def vqa_rank(image, q_ids, q_atts, answer_ids, answer_atts, k, sd, cfg):
+    """XFMForVQA.forward(train=False) (models/model_generation.py:133-144); question_atts is all-ones there (:141)."""
+    q_out = vqa_question_states(image, q_ids, q_atts, sd, cfg)
+    return vqa_rank_answer(q_out, torch.ones(q_out.shape[:-1], dtype=torch.long), answer_ids, answer_atts, k, sd, cfg)
+
+
+def make_vqa_batch(cfg, B=3, L=12, La=6, n_cand=7, seed=11):
+    """Synthetic VQA batch: questions (odd rows padded), 1-3 answers per question with weights, a candidate list."""
+    g = torch.Generator().manual_seed(seed)
+    base = make_batch(cfg, B, L=L, M=2, seed=seed)
+    V = cfg["vocab_size"]
+    k = [(b % 3) + 1 for b in range(B)]
+
+    def answers(n):
+        ids = torch.randint(3, V - 1, (n, La), generator=g)
+        ids[:, 0] = 0
+        atts = torch.ones(n, La, dtype=torch.long)
+        for a in range(n):
+            n_real = 3 + (a % (La - 2))        # 3 .. La tokens incl. BOS / EOS
+            ids[a, n_real - 1] = 2
+            ids[a, n_real:] = cfg["pad_id"]
+            atts[a, n_real:] = 0
+        return ids, atts
+    a_ids, a_atts = answers(sum(k))
+    weights = torch.rand(sum(k), generator=g) * 0.8 + 0.2
+    c_ids, c_atts = answers(n_cand)
+    return dict(image=base["image"], q_ids=base["text_ids"], q_atts=base["text_atts"], a_ids=a_ids, a_atts=a_atts, k=k,
+                weights=weights, cand_ids=c_ids, cand_atts=c_atts)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -121,3 +121,27 @@ def test_base_config_against_reference(golden_dir, name):
         amb = O.quantizer_ambiguous(O.vqkd_features(O.vqkd_preprocess(batch["image"]), sd, cfg),
                                     sd["vqkd.quantize.embedding.weight"]).view(ids.shape)
         assert torch.equal(ids[~amb], g["vq_ids"][~amb])
+
+
+def test_vqa_decoder_against_reference(golden_dir):
+    """XFMForVQA (models/model_generation.py:93-202): training loss, per-answer losses, question states, gradients and the
+    rank_answer re-ranking of the oracle against the unmodified reference."""
+    g = _load(golden_dir, "tiny_vqa.pt")
+    cfg = g["cfg"]
+    sd = O.make_state_dict(cfg, seed=0)
+    for v in sd.values():
+        v.requires_grad_(True)
+    b = O.make_vqa_batch(cfg)
+    col = {}
+    loss = O.vqa_train_loss(b["image"], b["q_ids"], b["q_atts"], b["a_ids"], b["a_atts"], b["k"], b["weights"], sd, cfg,
+                            collect=col)
+    assert abs(float(loss) - g["loss"]) <= 2e-5 * abs(g["loss"])
+    torch.testing.assert_close(col["answer_loss"], g["answer_loss"], rtol=2e-5, atol=1e-5)
+    torch.testing.assert_close(col["question_output"], g["question_output"], rtol=1e-4, atol=2e-5)
+    loss.backward()
+    for n, gr in g["grads"].items():
+        torch.testing.assert_close(sd[n].grad, gr, rtol=2e-4, atol=2e-6, msg=lambda m, n=n: f"{n}: {m}")
+    with torch.no_grad():
+        ids, probs = O.vqa_rank(b["image"], b["q_ids"], b["q_atts"], b["cand_ids"], b["cand_atts"], g["k_test"], sd, cfg)
+    assert torch.equal(ids, g["topk_ids"])
+    torch.testing.assert_close(probs, g["topk_probs"], rtol=1e-4, atol=1e-7)

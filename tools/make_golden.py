@@ -10,6 +10,9 @@ What is recorded (all produced by the reference's own code, through oracle/ref_s
                    of every layer's activations (full tensors would be ~100 MB).
   * itc_idx.pt   — get_contrastive_loss / get_hard_negatives with `idx` (retrieval soft labels).
   * masks.pt     — MaskingGenerator outputs for fixed (random, np.random) seeds.
+  * tiny_vqa.pt  — XFMForVQA (models/model_generation.py), tiny config with a 2-layer causal decoder: training loss,
+                   per-answer losses, question states, parameter gradients; rank_answer ids / probabilities.
+                   `python tools/make_golden.py --only-vqa` regenerates just this file.
 Synthetic weights come from oracle.xfm_oracle.make_state_dict (a pure function of parameter names), so the
 fixtures stay small: tests regenerate the same weights instead of loading them.
 """
@@ -197,11 +200,65 @@ def masks_golden():
     return out
 
 
+VQA_GRADS = ["text_decoder.roberta.encoder.layer.0.attention.self.query.weight",
+             "text_decoder.roberta.encoder.layer.1.crossattention.self.key.weight",
+             "text_decoder.roberta.encoder.layer.1.output.dense.weight",
+             "text_decoder.lm_head.dense.weight", "text_decoder.lm_head.bias",
+             "text_decoder.roberta.embeddings.word_embeddings.weight",
+             "fusion_encoder.roberta.encoder.layer.1.crossattention.self.value.weight",
+             "text_encoder.roberta.encoder.layer.0.intermediate.dense.weight",
+             "vision_encoder.blocks.1.mlp.fc2.weight"]
+
+
+def vqa_golden():
+    """XFMForVQA.forward train / rank paths of the UNMODIFIED reference (models/model_generation.py:93-202)."""
+    import types
+
+    cfg = O.tiny_config(dec_layers=2, use_bbox=False)
+    sd = O.make_state_dict(cfg, seed=0)
+    model = ref_shim.build_reference_vqa(cfg, O.expand_tied(sd, cfg))
+    b = O.make_vqa_batch(cfg)
+    q = types.SimpleNamespace(input_ids=b["q_ids"], attention_mask=b["q_atts"])
+    a = types.SimpleNamespace(input_ids=b["a_ids"], attention_mask=b["a_atts"])
+    c = types.SimpleNamespace(input_ids=b["cand_ids"], attention_mask=b["cand_atts"])
+    seen = {}
+    orig_dec, orig_cross = model.text_decoder.forward, model.get_cross_embeds
+
+    def spy_dec(*args, **kw):
+        out = orig_dec(*args, **kw)
+        seen["answer_loss"] = out.loss.detach().clone()
+        return out
+
+    def spy_cross(*args, **kw):
+        out = orig_cross(*args, **kw)
+        seen["question_output"] = out.detach().clone()
+        return out
+
+    model.text_decoder.forward, model.get_cross_embeds = spy_dec, spy_cross
+    loss = model(b["image"], q, a, k=b["k"], weights=b["weights"], train=True)
+    loss.backward()
+    params = dict(model.named_parameters())
+    grads = {}
+    for n in VQA_GRADS:
+        rn = n.replace("text_encoder.roberta.", "text_encoder.")
+        grads[n] = params[rn].grad.detach().clone()
+    model.text_decoder.forward = orig_dec
+    with torch.no_grad():
+        topk_ids, topk_probs = model(b["image"], q, c, k=3, train=False)
+    return dict(cfg=cfg, loss=float(loss), answer_loss=seen["answer_loss"], question_output=seen["question_output"],
+                grads=grads, k_test=3, topk_ids=topk_ids, topk_probs=topk_probs)
+
+
 BASE_B = 8
 
 
 def main():
     os.makedirs(GOLD, exist_ok=True)
+    if "--only-vqa" in sys.argv:
+        v = vqa_golden()
+        torch.save(v, os.path.join(GOLD, "tiny_vqa.pt"))
+        print("tiny_vqa", v["loss"], v["topk_ids"].tolist())
+        return
     if "--only-base" in sys.argv:
         torch.set_num_threads(os.cpu_count())
         bm = run_reference(O.base_config(), B=BASE_B, L=40, M=15, image_uniform=False, full=False)
@@ -214,6 +271,7 @@ def main():
     torch.set_num_threads(os.cpu_count())
     torch.save(masks_golden(), os.path.join(GOLD, "masks.pt"))
     torch.save(itc_idx_golden(), os.path.join(GOLD, "itc_idx.pt"))
+    torch.save(vqa_golden(), os.path.join(GOLD, "tiny_vqa.pt"))
     tv = run_reference(O.tiny_config(use_vision_tokenizer=True), B=4, L=24, M=6, image_uniform=True, want_grads=True)
     torch.save(tv, os.path.join(GOLD, "tiny_vq.pt"))
     print("tiny_vq", tv["losses"])
