@@ -192,6 +192,10 @@ int xfm_ce_fwd(const float* logits, int64_t ld, const int64_t* labels, int R, in
                float* count, void* stream);
 int xfm_ce_bwd(const float* logits, int64_t ld, const int64_t* labels, const float* lse, const float* count,
                const float* upstream, void* dlogits_bf16, int64_t ldd, int R, int V, void* stream);
+/* CrossEntropyLoss(reduction='none') followed by a weighted sum over rows — the VQA answer loss (xroberta.py:1104-1110,
+ * model_generation.py:130-131): dlogits = (softmax - onehot) * row_scale[row] * (*upstream); rows with label < 0 get 0. */
+int xfm_ce_bwd_rows(const float* logits, int64_t ld, const int64_t* labels, const float* lse, const float* row_scale,
+                    const float* upstream, void* dlogits_bf16, int64_t ldd, int R, int V, void* stream);
 
 /* K10 — ITC (xfm.py:683-715) on gathered features [n,E] f32: loss and, in the same call, the gradients wrt the LOCAL
  * slice [local_off, local_off+local_n) of image/text features (AllGather.backward, xfm.py:93-98) and wrt temp, for an

@@ -364,3 +364,85 @@ def test_retrieval_evaluation_rerank_against_oracle():
     for d in (0, 1):
         assert float((parts[0][d] + parts[1][d] - (one[d] - 100.0)).abs().max()) <= 2e-2
 
+
+
+def _vqa_inputs(b):
+    import types
+    c = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in b.items()}
+    q = types.SimpleNamespace(input_ids=c["q_ids"], attention_mask=c["q_atts"])
+    a = types.SimpleNamespace(input_ids=c["a_ids"], attention_mask=c["a_atts"])
+    cand = types.SimpleNamespace(input_ids=c["cand_ids"], attention_mask=c["cand_atts"])
+    return c, q, a, cand
+
+
+def test_vqa_model_against_reference(golden_dir):
+    """models/model_generation.py:93-202 (BASELINE config #5 shape, tiny widths) against the fixture produced by the
+    UNMODIFIED reference: question states, per-answer causal-decoder losses, the weighted loss, parameter gradients through
+    decoder / fusion / text / vision, and the rank_answer re-ranking."""
+    from xfm_b200.model_generation import XFMForVQA
+    g = _load(golden_dir, "tiny_vqa.pt")
+    cfg = g["cfg"]
+    b = O.make_vqa_batch(cfg)
+    model = XFMForVQA(dict(cfg, num_dec_layers=cfg["dec_layers"], decoder_fusion_start_at=0, pad_token_id=cfg["pad_id"]),
+                      init=lambda n, s: O.make_tensor(n, s, 0), device="cuda").eval()
+    c, q, a, cand = _vqa_inputs(b)
+    with torch.no_grad():
+        ie, ia = model.get_vision_embeds(c["image"])
+        te = model.get_text_embeds(q.input_ids, q.attention_mask)
+        qo = model.get_cross_embeds(ie, ia, text_embeds=te, text_atts=q.attention_mask, is_pretrain=False)
+    assert _maxabs(qo, g["question_output"]) <= 2e-2
+    loss = model(c["image"], q, a, k=b["k"], weights=c["weights"], train=True)
+    assert _maxabs(model.last_answer_loss, g["answer_loss"]) <= 1e-3 * float(g["answer_loss"].abs().max())
+    assert abs(float(loss) - g["loss"]) <= 1e-3 * abs(g["loss"]), (float(loss), g["loss"])
+    loss.backward()
+    _grad_check(model, g["grads"], list(g["grads"]))
+    ids, probs = model(c["image"], q, cand, k=g["k_test"], train=False)
+    assert torch.equal(ids.cpu(), g["topk_ids"])
+    torch.testing.assert_close(probs.cpu(), g["topk_probs"], rtol=0.1, atol=1e-4)
+    # state_dict carries the reference's decoder names, incl. the tied head
+    sd = model.state_dict()
+    for n in ("text_decoder.roberta.encoder.layer.1.crossattention.self.key.weight", "text_decoder.lm_head.decoder.weight",
+              "text_decoder.lm_head.decoder.bias", "text_decoder.roberta.embeddings.position_ids"):
+        assert n in sd, n
+    assert sd["text_decoder.lm_head.decoder.weight"].data_ptr() == sd["text_decoder.roberta.embeddings.word_embeddings.weight"].data_ptr()
+
+
+def test_vqa_base_width_against_oracle():
+    """Same path at the XFM-base widths (768 wide, vocabulary 50265, 40-token questions, 8-token answers; 2 layers per
+    stack so the CPU oracle finishes in seconds), train mode off: loss, gradients, ranking."""
+    from xfm_b200.model_generation import XFMForVQA
+    cfg = O.base_config(vision_depth=2, text_layers=2, fusion_layers=2, dec_layers=2, use_bbox=False)
+    sd = O.make_state_dict(cfg, 0)
+    for v in sd.values():
+        if v.dtype.is_floating_point:
+            v.requires_grad_(True)
+    b = O.make_vqa_batch(cfg, B=4, L=40, La=8, n_cand=9, seed=17)
+    col = {}
+    ref = O.vqa_train_loss(b["image"], b["q_ids"], b["q_atts"], b["a_ids"], b["a_atts"], b["k"], b["weights"], sd, cfg,
+                           collect=col)
+    ref.backward()
+    with torch.no_grad():
+        ref_ids, ref_probs = O.vqa_rank(b["image"], b["q_ids"], b["q_atts"], b["cand_ids"], b["cand_atts"], 4, sd, cfg)
+    model = XFMForVQA(dict(cfg, num_dec_layers=2, pad_token_id=cfg["pad_id"]), init=lambda n, s: O.make_tensor(n, s, 0),
+                      device="cuda").eval()
+    c, q, a, cand = _vqa_inputs(b)
+    loss = model(c["image"], q, a, k=b["k"], weights=c["weights"], train=True)
+    assert _maxabs(model.last_answer_loss, col["answer_loss"].detach()) <= 2e-3 * float(col["answer_loss"].abs().max())
+    assert abs(float(loss) - float(ref)) <= 1e-3 * abs(float(ref)), (float(loss), float(ref))
+    loss.backward()
+    grads = {k: v.grad for k, v in sd.items() if v.dtype.is_floating_point and v.grad is not None}
+    _grad_check(model, grads, ["text_decoder.roberta.encoder.layer.0.crossattention.self.value.weight",
+                               "text_decoder.roberta.encoder.layer.1.attention.self.key.weight",
+                               "text_decoder.lm_head.layer_norm.weight",
+                               "fusion_encoder.roberta.encoder.layer.1.output.dense.weight",
+                               "text_encoder.roberta.encoder.layer.0.attention.self.query.weight",
+                               "vision_encoder.blocks.0.attn.qkv.weight"])
+    ids, probs = model(c["image"], q, cand, k=4, train=False)
+    # candidates whose probabilities are within bf16 noise of each other may swap places: compare as sets + sorted values
+    assert torch.equal(ids.cpu().sort(1).values, ref_ids.sort(1).values)
+    # 50265-way random-init logits make the re-ranked probabilities span 27 decades: compare them in log space
+    torch.testing.assert_close(probs.cpu().double().log(), ref_probs.double().log(), rtol=0, atol=0.3)
+    model.train()
+    l2 = model(c["image"], q, a, k=b["k"], weights=c["weights"], train=True)
+    l2.backward()
+    assert torch.isfinite(l2) and abs(float(l2) - float(loss)) > 0

@@ -128,15 +128,17 @@ def _attn_out_fwd(ctx, w, pre, resid, eps, drop, s, tag):
 
 
 def roberta_layer_fwd(h, w, Bt, Lt, H, eps, kmask, enc=None, Benc=0, Lenc=0, kv_index=None, drop=NO_DROP, save=True,
-                      h32=None, kv_offsets=None, kv_samples=None):
+                      h32=None, kv_offsets=None, kv_samples=None, self_bias=None, enc_kmask=None):
     """h: bf16 [Bt*Lt, D] (h32: the same hidden state in f32, used as the residual when given).
-    enc: bf16 [Benc*Lenc, Denc] image tokens (cross-attention) or None.  Returns (h_out bf16, h_out f32, saved)."""
+    enc: bf16 [Benc*Lenc, Denc] image tokens (cross-attention) or None.  Returns (h_out bf16, h_out f32, saved).
+    self_bias: f32 [H, Lt, ld] additive self-attention term (the decoder's causal mask, xroberta.py:771-806);
+    enc_kmask: f32 [Bt, Lenc] additive key mask of the cross-attention (xroberta.py:903-909)."""
     D = h.shape[1]
     s = Saved() if save else None
     scale = 1.0 / math.sqrt(64)
     qkv = L.gemm(h, w["qkv_w16"], bias=w["qkv_b"])
     seed_a = drop.next_seed() if drop.p_attn > 0 else 0
-    ctx, lse = L.attention_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], Bt, H, Lt, Lt, scale, kmask=kmask,
+    ctx, lse = L.attention_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], Bt, H, Lt, Lt, scale, kmask=kmask, bias=self_bias,
                                dropout_p=drop.p_attn, dropout_seed=seed_a)
     h1, h1_32 = _attn_out_fwd(ctx, w, "a_", h if h32 is None else h32, eps, drop, s, "a")
     if save:
@@ -148,7 +150,8 @@ def roberta_layer_fwd(h, w, Bt, Lt, H, eps, kmask, enc=None, Benc=0, Lenc=0, kv_
         kvc = L.gemm(enc, w["c_kv_w16"], bias=w["c_kv_b"])
         seed_c = drop.next_seed() if drop.p_attn > 0 else 0
         cctx, clse = L.attention_fwd(qc, kvc[:, :D], kvc[:, D:], Bt, H, Lt, Lenc, scale, Bkv=Benc, kv_index=kv_index,
-                                     dropout_p=drop.p_attn, dropout_seed=seed_c, kv_offsets=kv_offsets, kv_samples=kv_samples)
+                                     kmask=enc_kmask, dropout_p=drop.p_attn, dropout_seed=seed_c, kv_offsets=kv_offsets,
+                                     kv_samples=kv_samples)
         h2, h2_32 = _attn_out_fwd(cctx, w, "c_", h1_32, eps, drop, s, "c")
         if save:
             s.qc, s.kvc, s.cctx, s.clse, s.seed_c, s.h2, s.enc = qc, kvc, cctx, clse, seed_c, h2, enc
@@ -184,7 +187,7 @@ def _attn_out_bwd(dh, s, w, g, pre, tag, ctx):
 
 
 def roberta_layer_bwd(dh3, s, w, g, Bt, Lt, H, kmask, Benc=0, Lenc=0, kv_index=None, kv_offsets=None, kv_samples=None,
-                      d_enc=None, need_dh=True):
+                      d_enc=None, need_dh=True, self_bias=None, enc_kmask=None):
     """dh3: bf16 or fp32 [Bt*Lt, D].  d_enc: fp32 [Benc*Lenc, Denc] accumulator for the image-token gradient.
     Returns the fp32 gradient wrt the layer input (or None)."""
     D = s.h.shape[1]
@@ -208,7 +211,7 @@ def roberta_layer_bwd(dh3, s, w, g, Bt, Lt, H, kmask, Benc=0, Lenc=0, kv_index=N
         dkvc = torch.empty_like(s.kvc)
         L.attention_bwd(d_cctx, s.qc, s.kvc[:, :D], s.kvc[:, D:], s.cctx, s.clse, Bt, H, Lt, Lenc, scale, dqc, dkvc[:, :D],
                         dkvc[:, D:], Bkv=Benc, kv_index=kv_index, kv_offsets=kv_offsets, kv_samples=kv_samples,
-                        dropout_p=s.p_attn, dropout_seed=s.seed_c)
+                        kmask=enc_kmask, dropout_p=s.p_attn, dropout_seed=s.seed_c)
         L.colsum_into(dqc, g("c_q_b"))
         wgrad(g("c_q_w"), dqc, s.h1)
         dh1 = L.gemm(dqc, w["c_q_w16"], b_t=True, residual=d_res, out_dtype=f32)
@@ -220,7 +223,7 @@ def roberta_layer_bwd(dh3, s, w, g, Bt, Lt, H, kmask, Benc=0, Lenc=0, kv_index=N
     d_res, d_ctx = _attn_out_bwd(dh1, s, w, g, "a_", "a", s.ctx)
     dqkv = torch.empty_like(s.qkv)
     L.attention_bwd(d_ctx, s.qkv[:, :D], s.qkv[:, D:2 * D], s.qkv[:, 2 * D:], s.ctx, s.lse, Bt, H, Lt, Lt, scale, dqkv[:, :D],
-                    dqkv[:, D:2 * D], dqkv[:, 2 * D:], kmask=kmask, dropout_p=s.p_attn, dropout_seed=s.seed_a)
+                    dqkv[:, D:2 * D], dqkv[:, 2 * D:], kmask=kmask, bias=self_bias, dropout_p=s.p_attn, dropout_seed=s.seed_a)
     L.colsum_into(dqkv, g("qkv_b"))
     wgrad(g("qkv_w"), dqkv, s.h)
     if not need_dh:

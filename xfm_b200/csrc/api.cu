@@ -130,6 +130,10 @@ int xfm_ce_bwd(const float* logits, int64_t ld, const int64_t* labels, const flo
                const float* upstream, void* dlogits, int64_t ldd, int R, int V, void* stream) {
   return ce_bwd(logits, ld, labels, lse, count, upstream, BF(dlogits), ldd, R, V, ST);
 }
+int xfm_ce_bwd_rows(const float* logits, int64_t ld, const int64_t* labels, const float* lse, const float* row_scale,
+                    const float* upstream, void* dlogits, int64_t ldd, int R, int V, void* stream) {
+  return ce_bwd_rows(logits, ld, labels, lse, row_scale, upstream, BF(dlogits), ldd, R, V, ST);
+}
 size_t xfm_itc_workspace(int n) { return (size_t)2 * n * n + (size_t)3 * n; }
 int xfm_itc_loss_fused(const float* image_all, const float* text_all, int n, int E, const int64_t* idx_all, const float* temp,
                        int local_off, int local_n, float* work, float* loss, float* d_image_local, float* d_text_local,

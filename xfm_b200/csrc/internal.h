@@ -65,6 +65,8 @@ int ce_fwd(const float* logits, int64_t ld, const int64_t* labels, int R, int V,
            float* count, cudaStream_t s);
 int ce_bwd(const float* logits, int64_t ld, const int64_t* labels, const float* lse, const float* count, const float* upstream,
            bf16_t* dlogits, int64_t ldd, int R, int V, cudaStream_t s);
+int ce_bwd_rows(const float* logits, int64_t ld, const int64_t* labels, const float* lse, const float* row_scale,
+                const float* upstream, bf16_t* dlogits, int64_t ldd, int R, int V, cudaStream_t s);
 int itc_loss_fused(const float* image_all, const float* text_all, int n, int E, const int64_t* idx_all, const float* temp,
                    int local_off, int local_n, float* work, float* loss, float* d_image_local, float* d_text_local,
                    float* dtemp, cudaStream_t s);

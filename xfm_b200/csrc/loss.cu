@@ -86,8 +86,8 @@ ce_reduce_kernel(const float* __restrict__ row_loss, const int64_t* __restrict__
 
 __global__ void __launch_bounds__(CE_THREADS)
 ce_bwd_kernel(const float* __restrict__ logits, int64_t ld, const int64_t* __restrict__ labels, const float* __restrict__ lse,
-              const float* __restrict__ count, const float* __restrict__ upstream, bf16* __restrict__ dlogits, int64_t ldd,
-              int V) {
+              const float* __restrict__ count, const float* __restrict__ row_scale, const float* __restrict__ upstream,
+              bf16* __restrict__ dlogits, int64_t ldd, int V) {
   const int row = blockIdx.x;
   const int64_t label = labels[row];
   bf16* d = dlogits + (int64_t)row * ldd;
@@ -95,7 +95,8 @@ ce_bwd_kernel(const float* __restrict__ logits, int64_t ld, const int64_t* __res
     for (int j = threadIdx.x; j < (int)ldd; j += CE_THREADS) d[j] = __float2bfloat16(0.f);
     return;
   }
-  const float g = (upstream ? *upstream : 1.f) / *count;
+  // mean reduction: 1 / count; reduction='none' followed by a weighted sum (model_generation.py:130-131): row_scale[row]
+  const float g = (upstream ? *upstream : 1.f) * (row_scale ? row_scale[row] : 1.f / *count);
   const float l = lse[row];
   const float* x = logits + (int64_t)row * ld;
   for (int j = threadIdx.x; j < (int)ldd; j += CE_THREADS) {
@@ -416,7 +417,15 @@ int ce_fwd(const float* logits, int64_t ld, const int64_t* labels, int R, int V,
 int ce_bwd(const float* logits, int64_t ld, const int64_t* labels, const float* lse, const float* count, const float* upstream,
            bf16* dlogits, int64_t ldd, int R, int V, cudaStream_t s) {
   if (R <= 0) return 0;
-  ce_bwd_kernel<<<R, CE_THREADS, 0, s>>>(logits, ld, labels, lse, count, upstream, dlogits, ldd, V);
+  ce_bwd_kernel<<<R, CE_THREADS, 0, s>>>(logits, ld, labels, lse, count, nullptr, upstream, dlogits, ldd, V);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+int ce_bwd_rows(const float* logits, int64_t ld, const int64_t* labels, const float* lse, const float* row_scale,
+                const float* upstream, bf16* dlogits, int64_t ldd, int R, int V, cudaStream_t s) {
+  if (R <= 0) return 0;
+  if (!row_scale) { set_error("ce_bwd_rows: row_scale is required"); return XFM_ERR_BAD_ARG; }
+  ce_bwd_kernel<<<R, CE_THREADS, 0, s>>>(logits, ld, labels, lse, nullptr, row_scale, upstream, dlogits, ldd, V);
   count_launch();
   return (int)cudaGetLastError();
 }

@@ -82,7 +82,7 @@ def add_vision(fp, cfg, init, prefix="vision_encoder.", layerscale=True, relbias
     add("fc_norm.bias", (D,))
 
 
-def add_roberta(fp, cfg, init, prefix, layers, cross, enc_width):
+def add_roberta(fp, cfg, init, prefix, layers, cross, enc_width, heads=("lm_head", "lm_cap_head")):
     H, Ff, V = cfg["hidden"], cfg["ffn"], cfg["vocab_size"]
 
     def add(name, shape):
@@ -124,7 +124,7 @@ def add_roberta(fp, cfg, init, prefix, layers, cross, enc_width):
         add(l + "output.dense.bias", (H,))
         add(l + "output.LayerNorm.weight", (H,))
         add(l + "output.LayerNorm.bias", (H,))
-    for head in ("lm_head", "lm_cap_head"):
+    for head in heads:
         h = head + "."
         add(h + "bias", (V,))
         add(h + "dense.weight", (H, H))
@@ -337,13 +337,15 @@ class RobertaStack:
         L.roberta_embed_bwd(dpre, st.ids.reshape(-1), st.pos_ids, fp.grad(e + "word_embeddings.weight"),
                             fp.grad(e + "position_embeddings.weight"), fp.grad(e + "token_type_embeddings.weight"), self.pad)
 
-    def layers_fwd(self, h, Bt, Lt, kmask, enc=None, Benc=0, Lenc=0, kv_index=None, drop=BK.NO_DROP, save=True, h32=None):
-        """Returns (h bf16 [Bt*Lt, D], h f32 same shape, state)."""
+    def layers_fwd(self, h, Bt, Lt, kmask, enc=None, Benc=0, Lenc=0, kv_index=None, drop=BK.NO_DROP, save=True, h32=None,
+                   self_bias=None, enc_kmask=None):
+        """Returns (h bf16 [Bt*Lt, D], h f32 same shape, state).  self_bias / enc_kmask: see blocks.roberta_layer_fwd."""
         if self.w is None:
             self.refresh()
         st = State()
         st.layers, st.Bt, st.Lt, st.kmask, st.Benc, st.Lenc, st.kv_index = [], Bt, Lt, kmask, Benc, Lenc, kv_index
         st.kv_offsets = st.kv_samples = None
+        st.self_bias, st.enc_kmask = self_bias, enc_kmask
         if enc is not None:  # CSR inverse of the sample -> image map: the tcgen05 cross-attention kernels stack an image's samples
             if kv_index is None:
                 st.kv_offsets = torch.arange(Benc + 1, dtype=torch.int32, device=h.device)
@@ -353,7 +355,7 @@ class RobertaStack:
         for i in range(self.layers):
             h, h32, s = BK.roberta_layer_fwd(h, self.w[i], Bt, Lt, self.H, self.eps, kmask, enc=enc, Benc=Benc, Lenc=Lenc,
                                              kv_index=kv_index, drop=drop, save=save, h32=h32, kv_offsets=st.kv_offsets,
-                                             kv_samples=st.kv_samples)
+                                             kv_samples=st.kv_samples, self_bias=self_bias, enc_kmask=enc_kmask)
             st.layers.append(s)
             if self.collect is not None:
                 self.collect.append(h32.view(Bt, Lt, -1).clone())
@@ -367,7 +369,8 @@ class RobertaStack:
             last = i == 0
             dh = BK.roberta_layer_bwd(dh, st.layers[i], self.w[i], self._g(i), st.Bt, st.Lt, self.H, st.kmask, Benc=st.Benc,
                                       Lenc=st.Lenc, kv_index=st.kv_index, kv_offsets=kv_offsets, kv_samples=kv_samples,
-                                      d_enc=d_enc, need_dh=(need_dh or not last))
+                                      d_enc=d_enc, need_dh=(need_dh or not last), self_bias=st.self_bias,
+                                      enc_kmask=st.enc_kmask)
             st.layers[i] = None
         return dh
 
@@ -461,8 +464,8 @@ class LMHead:
         self.V, self.eps = cfg["vocab_size"], cfg["ln_eps"]
         self.ldv = (self.V + 7) // 8 * 8
 
-    def loss(self, x, labels):
-        """x bf16 [R, D] gathered hidden rows; labels int64 [R]."""
+    def logits(self, x, st=None):
+        """x bf16 [R, D] -> f32 logits [R, ldv] (columns >= V are padding)."""
         fp, p = self.fp, self.p
         R = x.shape[0]
         pre = torch.empty_like(x)
@@ -472,15 +475,34 @@ class LMHead:
         logits = torch.empty((R, self.ldv), dtype=torch.float32, device=x.device)
         L.gemm(y, fp.view16(p + "roberta.embeddings.word_embeddings.weight"), bias=fp.view32(p + "lm_head.bias"),
                out=logits[:, :self.V])
-        loss, count, lse = L.ce_fwd(logits, labels, self.V)
+        if st is not None:
+            st.x, st.pre, st.a, st.y, st.stats, st.logits = x, pre, a, y, stats, logits
+        return logits
+
+    def loss(self, x, labels):
+        """x bf16 [R, D] gathered hidden rows; labels int64 [R]."""
         st = State()
-        st.x, st.pre, st.a, st.y, st.stats, st.logits, st.labels, st.count, st.lse = x, pre, a, y, stats, logits, labels, count, lse
+        logits = self.logits(x, st)
+        loss, count, lse = L.ce_fwd(logits, labels, self.V)
+        st.labels, st.count, st.lse = labels, count, lse
         return loss, st
 
-    def backward(self, st, upstream):
-        """upstream: f32 [1] device scalar.  Returns d_x bf16 [R, D]."""
+    def loss_rows(self, x, labels):
+        """CrossEntropyLoss(reduction='none') (xroberta.py:1108-1109): per-row losses f32 [R] (0 where label = -100)."""
+        st = State()
+        logits = self.logits(x, st)
+        _, count, lse, rows = L.ce_fwd(logits, labels, self.V, want_rows=True)
+        st.labels, st.count, st.lse = labels, count, lse
+        return rows, st
+
+    def backward(self, st, upstream, row_scale=None):
+        """upstream: f32 [1] device scalar (or None = 1); row_scale: f32 [R] gradient of the scalar loss wrt each row loss
+        (loss_rows), else the mean reduction of loss().  Returns d_x bf16 [R, D]."""
         fp, p, V = self.fp, self.p, self.V
-        dlog = L.ce_bwd(st.logits, st.labels, st.lse, st.count, upstream, V, self.ldv)
+        if row_scale is not None:
+            dlog = L.ce_bwd_rows(st.logits, st.labels, st.lse, row_scale, upstream, V, self.ldv)
+        else:
+            dlog = L.ce_bwd(st.logits, st.labels, st.lse, st.count, upstream, V, self.ldv)
         st.logits = None
         L.colsum_into(dlog, fp.grad_padded(p + "lm_head.bias", self.ldv))
         BK.wgrad(fp.grad(p + "roberta.embeddings.word_embeddings.weight"), dlog[:, :V], st.y)

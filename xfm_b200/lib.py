@@ -421,8 +421,9 @@ def batch_sum_bf16(x):
     return out
 
 
-def ce_fwd(logits, labels, V):
-    """logits f32 [R, ld>=V]; labels int64 [R] (-100 = ignore).  Returns (loss[1], count[1], lse[R])."""
+def ce_fwd(logits, labels, V, want_rows=False):
+    """logits f32 [R, ld>=V]; labels int64 [R] (-100 = ignore).  Returns (loss[1], count[1], lse[R]) and, with want_rows,
+    the per-row losses [R] (0 for ignored rows) as a fourth value."""
     R = logits.shape[0]
     assert logits.dtype == torch.float32 and logits.stride(1) == 1 and labels.dtype == torch.int64
     dev = logits.device
@@ -432,6 +433,8 @@ def ce_fwd(logits, labels, V):
     count = torch.empty(1, dtype=torch.float32, device=dev)
     check(lib().xfm_ce_fwd(_p(logits), C.c_int64(logits.stride(0)), _p(labels), R, V, _p(row_loss), _p(lse), _p(loss),
                            _p(count), stream_ptr()), "xfm_ce_fwd")
+    if want_rows:
+        return loss, count, lse, row_loss
     return loss, count, lse
 
 
@@ -440,6 +443,16 @@ def ce_bwd(logits, labels, lse, count, upstream, V, ldd):
     d = torch.empty((R, ldd), dtype=torch.bfloat16, device=logits.device)
     check(lib().xfm_ce_bwd(_p(logits), C.c_int64(logits.stride(0)), _p(labels), _p(lse), _p(count), _p(upstream), _p(d),
                            C.c_int64(ldd), R, V, stream_ptr()), "xfm_ce_bwd")
+    return d
+
+
+def ce_bwd_rows(logits, labels, lse, row_scale, upstream, V, ldd):
+    """dlogits bf16 [R, ldd] = (softmax - onehot) * row_scale[row] * upstream (reduction='none' + weighted sum)."""
+    R = logits.shape[0]
+    assert row_scale.dtype == torch.float32 and row_scale.numel() == R and row_scale.is_contiguous()
+    d = torch.empty((R, ldd), dtype=torch.bfloat16, device=logits.device)
+    check(lib().xfm_ce_bwd_rows(_p(logits), C.c_int64(logits.stride(0)), _p(labels), _p(lse), _p(row_scale), _p(upstream),
+                                _p(d), C.c_int64(ldd), R, V, stream_ptr()), "xfm_ce_bwd_rows")
     return d
 
 

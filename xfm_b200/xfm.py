@@ -250,6 +250,7 @@ class XFMBase(nn.Module):
                 fp.add(n, shape, init=init(n, shape), trainable=False)
         if not self.learnable_temp and use_contrastive_loss:
             self.init_params.remove("temp")
+        self._extend_params(fp, cfg, init, config)
         dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         fp.finalize(dev)
 
@@ -287,6 +288,7 @@ class XFMBase(nn.Module):
             self._vq = E.VisionEncoder(fp, cfg, prefix="vqkd.encoder.", layerscale=False, relbias=False, abs_pos=True)
             self._mim_head = E.LinearCE(fp, "lm_head", cfg["codebook_size"])
         self._sampler = BlockMaskSampler(ws, cfg["num_masking_patches"], cfg["min_num_patches"])
+        self._extend_modules(fp, cfg, config)
         if use_matching_loss:
             object.__setattr__(self.itm_head, "_owner", lambda s=self: s)
         self._anchor = torch.zeros((), requires_grad=True)
@@ -297,6 +299,13 @@ class XFMBase(nn.Module):
         self._drop_calls = 0
         self._seed = int(torch.initial_seed()) & 0x7FFFFFFF
         self.last_hard_negative_weights = None
+
+    # ------------------------------------------------------------------ subclass hooks
+    def _extend_params(self, fp, cfg, init, config):
+        """Task models add their parameters to the flat buffers here (before the buffers are allocated)."""
+
+    def _extend_modules(self, fp, cfg, config):
+        """Task models register tied aliases / buffers and build their runners here."""
 
     # ------------------------------------------------------------------ module plumbing
     def _node(self, path, leaf_cls=_Holder):
@@ -328,6 +337,11 @@ class XFMBase(nn.Module):
         return self
 
     def load_state_dict(self, state_dict, strict=True, assign=False):
+        # fine-tuning models of the reference hold a bare RobertaModel as text_encoder (xfm.py:397-403), so their
+        # checkpoints name it text_encoder.<x>; this module always keeps the pre-training layout text_encoder.roberta.<x>
+        state_dict = {(("text_encoder.roberta." + k[len("text_encoder."):])
+                       if k.startswith(("text_encoder.embeddings.", "text_encoder.encoder.")) else k): v
+                      for k, v in state_dict.items()}
         out = super().load_state_dict(state_dict, strict=strict, assign=False)
         self.flat.sync_shadow(force=True)
         return out
