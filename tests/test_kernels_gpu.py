@@ -124,6 +124,43 @@ def test_gemm_cta_pair_epilogues(lib, M, N, K):
     assert rel_err(out, acc + X.float().t() @ A.float()) < 1e-5
 
 
+@pytest.mark.parametrize("M,N,K", [(2560, 768, 256), (2500, 288, 200), (4000, 1536, 128), (18912, 768, 768)])
+def test_gemm_cta_pair_f32_tma_epilogue(lib, M, N, K):
+    """f32 TMA epilogue of the CTA-pair kernel (f32 residual in through TMA, f32 out through TMA, N % 32 == 0): LayerScale /
+    DropPath scales, dropout, plain f32 output and the MN-major (dgrad) operand, on full and ragged M / N tiles, against
+    fp32 torch and against the single-CTA kernel's generic epilogue (same dropout decisions)."""
+    g = G(3 * M + N + K)
+    A, B = bf(torch.randn(M, K, generator=g)), bf(torch.randn(N, K, generator=g) * 0.1)
+    bias, gamma = torch.randn(N, generator=g), torch.randn(N, generator=g)
+    rpg = 197
+    rs = torch.rand((M + rpg - 1) // rpg, generator=g)
+    res = torch.randn(M, N, generator=g)
+    z = A.float() @ B.float().t()
+    Ad, Bd, resd = A.cuda(), B.cuda(), res.cuda()
+    out = lib.gemm(Ad, Bd, bias=bias.cuda(), col_scale=gamma.cuda(), row_group_scale=rs.cuda(), rows_per_group=rpg,
+                   residual=resd, out_dtype=torch.float32)
+    assert rel_err(out, res + (z + bias) * gamma * rs.repeat_interleave(rpg)[:M, None]) < 1e-5
+    out = lib.gemm(Ad, Bd, out_dtype=torch.float32)                      # no bias, no residual
+    assert rel_err(out, z) < 1e-5
+    out = lib.gemm(Ad, Bd, bias=bias.cuda(), residual=resd, out_dtype=torch.float32)
+    assert rel_err(out, z + bias + res) < 1e-5
+    d_pair = lib.gemm(Ad, Bd, bias=bias.cuda(), dropout_p=0.1, dropout_seed=11, residual=resd, out_dtype=torch.float32)
+    d_one = lib.gemm(Ad, Bd, bias=bias.cuda(), dropout_p=0.1, dropout_seed=11, residual=resd, out_dtype=torch.float32,
+                     block_n=128)
+    kept = (d_pair - resd) != 0
+    assert abs(float(kept.float().mean()) - 0.9) < 0.01
+    assert torch.equal(kept, (d_one - resd) != 0)
+    assert rel_err(d_pair, d_one) < 1e-6
+    # dgrad form: B stored [K, N] (MN-major), f32 residual = gradient of the skip connection
+    Bt = B.t().contiguous().cuda()
+    out = lib.gemm(Ad, Bt, b_t=True, residual=resd, out_dtype=torch.float32)
+    assert rel_err(out, z + res) < 1e-5
+    # output written into a strided view (row stride > N)
+    wide = torch.zeros(M, N + 64, dtype=torch.float32, device="cuda")
+    lib.gemm(Ad, Bd, bias=bias.cuda(), residual=resd, out=wide[:, :N])
+    assert rel_err(wide[:, :N], z + bias + res) < 1e-5 and float(wide[:, N:].abs().max()) == 0.0
+
+
 def test_gemm_dropout_statistics_and_determinism(lib):
     g = G(5)
     A, B = bf(torch.randn(512, 64, generator=g)), bf(torch.randn(256, 64, generator=g))

@@ -521,30 +521,44 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 // read both halves, and each CTA's TMEM receives its 128 x 256 accumulator.  Per CTA a k-block costs 32 KB of L2->SM
 // traffic instead of 48 KB: the single-CTA kernel is capped by exactly that ingest rate (~47 B/clk/SM measured, tensor pipe
 // 49 % busy), which is where cuBLAS's 1.5 PF on these shapes comes from.
-constexpr int PAIR_STAGES = 5;
 constexpr int PAIR_STAGE_BYTES = 2 * 16384;  // A 128 x 64 + B 128 x 64 (bf16)
-constexpr int PAIR_EPI_BYTES = 8 * TMA_EPI_WARP_BYTES;   // 64 KB: TMA staging tiles; the fp32 transposition blocks of mode 2 alias it
-static_assert(PAIR_EPI_BYTES >= 8 * 32 * 34 * 4, "mode-2 staging must fit");
-constexpr int PAIR_SMEM_BYTES = PAIR_STAGES * PAIR_STAGE_BYTES + PAIR_EPI_BYTES + 256;
-static_assert(PAIR_SMEM_BYTES <= 232448, "shared memory");
+// Shared-memory plan of the two variants.  F32_EPI = false: 5 operand stages + 64 KB of bf16 TMA staging tiles (the fp32
+// transposition blocks of the generic mode 2 alias them).  F32_EPI = true (fp32 residual in / fp32 out, see
+// the f32 TMA epilogue below): 4 operand stages + a ring of three 4 KB fp32 tiles per epilogue warp (96 KB).
+constexpr int F32_EPI_TILE_BYTES = 32 * 32 * 4;
+constexpr int F32_EPI_RING = 3;
+template <bool F32_EPI>
+struct PairCfg {
+  static constexpr int STAGES = F32_EPI ? 4 : 5;
+  static constexpr int EPI_BYTES = F32_EPI ? 8 * F32_EPI_RING * F32_EPI_TILE_BYTES : 8 * TMA_EPI_WARP_BYTES;
+  static constexpr int BAR_BYTES = 512;
+  static constexpr int SMEM_BYTES = STAGES * PAIR_STAGE_BYTES + EPI_BYTES + BAR_BYTES;
+  static_assert(EPI_BYTES >= 8 * 32 * 34 * 4, "mode-2 staging must fit");
+  static_assert(SMEM_BYTES <= 232448, "shared memory");
+};
 
-template <int A_MN, int B_MN>
+// Swizzle-128B position of 16-byte chunk `k` of row `r` in a TMA tile with 128-byte rows (tile base 1024-aligned).
+XFM_DEVINL uint32_t swz128(int r, int k) { return (uint32_t)(r * 128 + ((k ^ (r & 7)) << 4)); }
+
+template <int A_MN, int B_MN, bool F32_EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                          const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_aux, const GemmArgs g) {
-  constexpr int STAGES = PAIR_STAGES;
+  using PC = PairCfg<F32_EPI>;
+  constexpr int STAGES = PC::STAGES;
   constexpr int BLOCK_N = 256;
   extern __shared__ __align__(1024) uint8_t smem[];
   if (smem_u32(smem) & 1023) __trap();
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * 16384;
   float* epi_stage = (float*)(smem + STAGES * PAIR_STAGE_BYTES);
-  uint64_t* bars = (uint64_t*)(smem + STAGES * PAIR_STAGE_BYTES + PAIR_EPI_BYTES);
+  uint64_t* bars = (uint64_t*)(smem + STAGES * PAIR_STAGE_BYTES + PC::EPI_BYTES);
   uint64_t* full_bar = bars;                    // [STAGES]  used in the leader CTA only
   uint64_t* empty_bar = bars + STAGES;          // [STAGES]  one per CTA, arrived by the leader's multicast commit
   uint64_t* tmem_full = bars + 2 * STAGES;      // [2]       one per CTA, multicast commit
   uint64_t* tmem_empty = bars + 2 * STAGES + 2; // [2]       leader's copy: 2 x EPI_WARPS arrivals (peer arrives remotely)
   uint32_t* tmem_ptr = (uint32_t*)(bars + 2 * STAGES + 4);
+  uint64_t* res_bar = bars + 2 * STAGES + 5;    // [EPI_WARPS][F32_EPI_RING]  residual tiles of the f32 TMA epilogue
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -561,6 +575,11 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], 2 * EPI_WARPS);
+    }
+    if (F32_EPI) {
+      tma_prefetch_desc(&map_c);
+      tma_prefetch_desc(&map_aux);
+      for (int s = 0; s < EPI_WARPS * F32_EPI_RING; ++s) mbar_init(&res_bar[s], 1);
     }
     fence_barrier_init();
   }
@@ -645,6 +664,133 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
       }
     }
     __syncwarp();
+  } else if (F32_EPI) {
+    // ---- f32 TMA epilogue: C(f32) = dropout((acc + bias) * col_scale * row_group_scale) + residual(f32).
+    // The generic mode-2 path moves the residual and the output through a transposition block with 16 row steps of
+    // dependent global accesses per 32 x 32 block and is latency bound (65 us for the 18912 x 768 x 768 ViT projection,
+    // whose operands + residual + output take 22 us of HBM time).  Here every epilogue warp owns a ring of three
+    // swizzled 4 KB tiles: the TMA engine prefetches the residual block two blocks ahead, the lane (= accumulator row)
+    // reads its 128-byte row conflict-free, combines it with the accumulator in registers, writes the result IN PLACE and
+    // one thread hands the tile back to the TMA engine for the store (edges are clipped / zero-filled by the tensor maps).
+    const int q = warp & 3;
+    const int ew = warp - 2;
+    constexpr int C_PER_WARP = BLOCK_N / (2 * EPI_COLS);
+    const int c_begin = (ew >> 2) * C_PER_WARP, c_end = c_begin + C_PER_WARP;
+    uint8_t* ring = (uint8_t*)epi_stage + ew * F32_EPI_RING * F32_EPI_TILE_BYTES;
+    uint64_t* rbar = res_bar + ew * F32_EPI_RING;
+    const bool want_res = g.residual != nullptr;
+    const bool has_scale = g.col_scale != nullptr || g.row_group_scale != nullptr;
+    const bool has_drop = g.dropout_p > 0.f;
+    const float inv_keep = has_drop ? 1.0f / (1.0f - g.dropout_p) : 1.0f;
+    const uint32_t seed_mix = drop_seed_mix(g.dropout_seed), thr = drop_threshold(g.dropout_p);
+    // block sequence of this warp: tiles t = pair_id, pair_id + num_pairs, ...; blocks c_begin .. c_end-1 while inside N
+    auto block_at = [&](int t, int c, int& rb, int& n) -> bool {
+      if (t >= num_tiles) return false;
+      rb = ((t % num_m_pairs) * 2 + (int)rank) * BLOCK_M + q * 32;
+      n = (t / num_m_pairs) * BLOCK_N + c * EPI_COLS;
+      return n < g.N;
+    };
+    int pf_t = pair_id, pf_c = c_begin, pf_k = 0;   // prefetch cursor (lane 0): next residual block to request
+    auto prefetch = [&]() {
+      int rb, n;
+      if (!block_at(pf_t, pf_c, rb, n)) return;
+      const int slot = pf_k % F32_EPI_RING;
+      mbar_arrive_expect_tx(&rbar[slot], F32_EPI_TILE_BYTES);
+      tma_load_2d(ring + slot * F32_EPI_TILE_BYTES, &map_aux, &rbar[slot], n, rb);
+      ++pf_k;
+      if (++pf_c >= c_end || !block_at(pf_t, pf_c, rb, n)) { pf_t += num_pairs; pf_c = c_begin; }
+    };
+    if (want_res && lane == 0) { prefetch(); prefetch(); }
+    int blk = 0;   // blocks consumed so far
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int t = pair_id; t < num_tiles; t += num_pairs) {
+      mbar_wait_relaxed(&tmem_full[as], aphase);
+      tc_fence_after();
+      const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BLOCK_N);
+#pragma unroll 1
+      for (int c = c_begin; c < c_end; ++c) {
+        int row_base, n;
+        if (!block_at(t, c, row_base, n)) break;
+        const int slot = blk % F32_EPI_RING;
+        uint8_t* tile = ring + slot * F32_EPI_TILE_BYTES;
+        uint32_t r[32];
+        tmem_ld_32x32(t_base + c * EPI_COLS, r);
+        float4 res[8];
+        if (want_res) {
+          mbar_wait(&rbar[slot], (uint32_t)(blk / F32_EPI_RING) & 1u);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) res[k] = *(const float4*)(tile + swz128(lane, k));
+        }
+        const int row = row_base + lane;
+        float rs = 1.f;
+        if (g.row_group_scale) rs = __ldg(g.row_group_scale + min(row, g.M - 1) / g.rows_per_group);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (g.bias) b4 = __ldg((const float4*)(g.bias + n) + k);
+          v[4 * k] = __uint_as_float(r[4 * k]) + b4.x;
+          v[4 * k + 1] = __uint_as_float(r[4 * k + 1]) + b4.y;
+          v[4 * k + 2] = __uint_as_float(r[4 * k + 2]) + b4.z;
+          v[4 * k + 3] = __uint_as_float(r[4 * k + 3]) + b4.w;
+        }
+        if (has_scale) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            float4 c4 = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (g.col_scale) c4 = __ldg((const float4*)(g.col_scale + n) + k);
+            v[4 * k] *= c4.x * rs;
+            v[4 * k + 1] *= c4.y * rs;
+            v[4 * k + 2] *= c4.z * rs;
+            v[4 * k + 3] *= c4.w * rs;
+          }
+        }
+        if (has_drop) {
+          const uint64_t pair0 = ((uint64_t)row * (uint64_t)g.N + (uint64_t)n) >> 1;   // N and n are even
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const uint64_t pr = pair0 + j;
+            const uint32_t keep = drop_keep_pair(seed_mix, (uint32_t)pr, (uint32_t)(pr >> 32), thr);
+            v[2 * j] = (keep & 1u) ? v[2 * j] * inv_keep : 0.f;
+            v[2 * j + 1] = (keep & 2u) ? v[2 * j + 1] * inv_keep : 0.f;
+          }
+        }
+        if (want_res) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            v[4 * k] += res[k].x;
+            v[4 * k + 1] += res[k].y;
+            v[4 * k + 2] += res[k].z;
+            v[4 * k + 3] += res[k].w;
+          }
+        }
+        // in place: this lane overwrites exactly the chunks it read; without a residual the tile was last read by the
+        // store of block blk - 3, which the wait_read<1> at the end of block blk - 2 has retired
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          *(float4*)(tile + swz128(lane, k)) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&map_c, tile, n, row_base);
+          tma_store_commit();
+          tma_store_wait_read<1>();            // the store of block blk - 1 has finished reading its tile ...
+          if (want_res) prefetch();            // ... which is the slot of block blk + 2
+        }
+        __syncwarp();
+        ++blk;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(&tmem_empty[as]);
+        else mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[as]), 0));
+      }
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+    if (lane == 0) tma_store_wait_read<0>();   // shared memory must outlive the last copies
   } else {
     const int q = warp & 3;
     const int ew = warp - 2;
@@ -739,6 +885,25 @@ static int encode_2d_plain(CUtensorMap* map, const void* base, uint64_t inner, u
   return 0;
 }
 
+// f32 [outer, inner] tile map, 32 x 32 boxes with 128-byte rows, SWIZZLE_128B (f32 TMA epilogue: residual in, C out)
+static int encode_2d_f32(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems) {
+  auto fn = get_tensor_map_encoder();
+  if (!fn) return XFM_ERR_NO_DRIVER;
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld_elems * 4};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (f32 epilogue) failed: %d (inner=%llu outer=%llu ld=%llu base=%p)", (int)r,
+              (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld_elems, base);
+    return XFM_ERR_BAD_ARG;
+  }
+  return 0;
+}
+
 template <int BLOCK_N, int A_MN, int B_MN>
 static int launch_gemm(const xfm_gemm_params* p, const GemmArgs& g, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N>;
@@ -774,19 +939,41 @@ static int launch_gemm_pair(const xfm_gemm_params* p, const GemmArgs& g, cudaStr
   if (B_MN) rc = encode_2d(&map_b, p->B, p->N, p->K, p->ldb, 64, BLOCK_K);
   else rc = encode_2d(&map_b, p->B, p->K, p->N, p->ldb, BLOCK_K, 128);   // half of the 256-wide tile per CTA
   if (rc) return rc;
-  auto kern = gemm_tcgen05_pair_kernel<A_MN, B_MN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
-  }
   const int num_tiles = ((g.num_m_tiles + 1) / 2) * g.num_n_tiles * g.split_k;
   const int max_pairs = num_sms() / 2;
   const int pairs = num_tiles < max_pairs ? num_tiles : max_pairs;
   CUtensorMap map_c = map_a, map_aux = map_a;   // placeholders when the TMA-store epilogue is not used
   GemmArgs g2 = g;
   g2.tma_epi = 0;
+  auto a16 = [](const void* q) { return ((uintptr_t)q & 15) == 0; };
+  static const bool f32_epi_on = getenv("XFM_GEMM_F32_EPI") == nullptr || atoi(getenv("XFM_GEMM_F32_EPI")) != 0;
+  if (f32_epi_on && g.epi_mode == 2 && p->c_dtype == 1 && !p->accumulate && g.split_k == 1 && p->act == 0 && !p->aux_out &&
+      (p->N % 32) == 0 && a16(p->C) && (p->ldc & 3) == 0 &&
+      (!p->residual || (p->res_dtype == 1 && a16(p->residual) && (p->ld_res & 3) == 0)) && (!p->bias || a16(p->bias)) &&
+      (!p->col_scale || a16(p->col_scale))) {
+    // f32 TMA epilogue variant (4 operand stages, residual / output tiles through the TMA engine)
+    rc = encode_2d_f32(&map_c, p->C, p->N, p->M, p->ldc);
+    if (!rc && p->residual) rc = encode_2d_f32(&map_aux, p->residual, p->N, p->M, p->ld_res);
+    if (rc) return rc;
+    g2.tma_epi = 2;
+    auto kern32 = gemm_tcgen05_pair_kernel<A_MN, B_MN, true>;
+    static bool attr32_set = false;
+    if (!attr32_set) {
+      cudaError_t e = cudaFuncSetAttribute(kern32, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<true>::SMEM_BYTES);
+      if (e != cudaSuccess) return (int)e;
+      attr32_set = true;
+    }
+    kern32<<<2 * pairs, GEMM_THREADS, PairCfg<true>::SMEM_BYTES, stream>>>(map_a, map_b, map_c, map_aux, g2);
+    count_launch();
+    return (int)cudaGetLastError();
+  }
+  auto kern = gemm_tcgen05_pair_kernel<A_MN, B_MN, false>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<false>::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
   if ((g.epi_mode == 0 || g.epi_mode == 1) && g.split_k == 1 && ((uintptr_t)p->C & 15) == 0 && (p->ldc & 7) == 0 &&
       (!p->aux_out || (((uintptr_t)p->aux_out & 15) == 0 && (p->ld_aux_out & 7) == 0)) &&
       (!p->aux_in || (((uintptr_t)p->aux_in & 15) == 0 && (p->ld_aux_in & 7) == 0)) &&
@@ -796,7 +983,7 @@ static int launch_gemm_pair(const xfm_gemm_params* p, const GemmArgs& g, cudaStr
     if (rc) return rc;
     g2.tma_epi = 1;
   }
-  kern<<<2 * pairs, GEMM_THREADS, PAIR_SMEM_BYTES, stream>>>(map_a, map_b, map_c, map_aux, g2);
+  kern<<<2 * pairs, GEMM_THREADS, PairCfg<false>::SMEM_BYTES, stream>>>(map_a, map_b, map_c, map_aux, g2);
   count_launch();
   return (int)cudaGetLastError();
 }
