@@ -140,6 +140,10 @@ def test_gemm_cta_pair_f32_tma_epilogue(lib, M, N, K):
     out = lib.gemm(Ad, Bd, bias=bias.cuda(), col_scale=gamma.cuda(), row_group_scale=rs.cuda(), rows_per_group=rpg,
                    residual=resd, out_dtype=torch.float32)
     assert rel_err(out, res + (z + bias) * gamma * rs.repeat_interleave(rpg)[:M, None]) < 1e-5
+    aux = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device="cuda")   # ViT blocks: saved pre-scale value
+    out2 = lib.gemm(Ad, Bd, bias=bias.cuda(), col_scale=gamma.cuda(), row_group_scale=rs.cuda(), rows_per_group=rpg,
+                    residual=resd, aux_out=aux, out_dtype=torch.float32)
+    assert torch.equal(out, out2) and rel_err(aux, z + bias) < 5e-3
     out = lib.gemm(Ad, Bd, out_dtype=torch.float32)                      # no bias, no residual
     assert rel_err(out, z) < 1e-5
     out = lib.gemm(Ad, Bd, bias=bias.cuda(), residual=resd, out_dtype=torch.float32)

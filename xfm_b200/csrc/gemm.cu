@@ -522,14 +522,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 // traffic instead of 48 KB: the single-CTA kernel is capped by exactly that ingest rate (~47 B/clk/SM measured, tensor pipe
 // 49 % busy), which is where cuBLAS's 1.5 PF on these shapes comes from.
 constexpr int PAIR_STAGE_BYTES = 2 * 16384;  // A 128 x 64 + B 128 x 64 (bf16)
-// Shared-memory plan of the two variants.  F32_EPI = false: 5 operand stages + 64 KB of bf16 TMA staging tiles (the fp32
-// transposition blocks of the generic mode 2 alias them).  F32_EPI = true (fp32 residual in / fp32 out, see
-// the f32 TMA epilogue below): 4 operand stages + a ring of three 4 KB fp32 tiles per epilogue warp (96 KB).
+// Shared-memory plan of the two variants: 5 operand stages + 64 KB of epilogue staging.  F32_EPI = false: bf16 TMA staging
+// tiles (the fp32 transposition blocks of the generic mode 2 alias them).  F32_EPI = true (fp32 residual in / fp32 out, see
+// the f32 TMA epilogue below): a ring of two 4 KB fp32 tiles per epilogue warp.  (A three-tile ring with 4 operand stages
+// was measured first: the K = 3072 GEMMs lost in the main loop what the epilogue gained.)
 constexpr int F32_EPI_TILE_BYTES = 32 * 32 * 4;
-constexpr int F32_EPI_RING = 3;
+constexpr int F32_EPI_RING = 2;
 template <bool F32_EPI>
 struct PairCfg {
-  static constexpr int STAGES = F32_EPI ? 4 : 5;
+  static constexpr int STAGES = 5;
   static constexpr int EPI_BYTES = F32_EPI ? 8 * F32_EPI_RING * F32_EPI_TILE_BYTES : 8 * TMA_EPI_WARP_BYTES;
   static constexpr int BAR_BYTES = 512;
   static constexpr int SMEM_BYTES = STAGES * PAIR_STAGE_BYTES + EPI_BYTES + BAR_BYTES;
@@ -668,8 +669,8 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     // ---- f32 TMA epilogue: C(f32) = dropout((acc + bias) * col_scale * row_group_scale) + residual(f32).
     // The generic mode-2 path moves the residual and the output through a transposition block with 16 row steps of
     // dependent global accesses per 32 x 32 block and is latency bound (65 us for the 18912 x 768 x 768 ViT projection,
-    // whose operands + residual + output take 22 us of HBM time).  Here every epilogue warp owns a ring of three
-    // swizzled 4 KB tiles: the TMA engine prefetches the residual block two blocks ahead, the lane (= accumulator row)
+    // whose operands + residual + output take 22 us of HBM time).  Here every epilogue warp owns a ring of two
+    // swizzled 4 KB tiles: the TMA engine prefetches the residual block one block ahead, the lane (= accumulator row)
     // reads its 128-byte row conflict-free, combines it with the accumulator in registers, writes the result IN PLACE and
     // one thread hands the tile back to the TMA engine for the store (edges are clipped / zero-filled by the tensor maps).
     const int q = warp & 3;
@@ -700,7 +701,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
       ++pf_k;
       if (++pf_c >= c_end || !block_at(pf_t, pf_c, rb, n)) { pf_t += num_pairs; pf_c = c_begin; }
     };
-    if (want_res && lane == 0) { prefetch(); prefetch(); }
+    if (want_res && lane == 0) prefetch();
     int blk = 0;   // blocks consumed so far
     int as = 0;
     uint32_t aphase = 0;
@@ -721,6 +722,10 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
           mbar_wait(&rbar[slot], (uint32_t)(blk / F32_EPI_RING) & 1u);
 #pragma unroll
           for (int k = 0; k < 8; ++k) res[k] = *(const float4*)(tile + swz128(lane, k));
+          if (lane == 0) {
+            tma_store_wait_read<0>();          // the store of block blk - 1 has finished reading the other tile ...
+            prefetch();                        // ... which now receives the residual of block blk + 1
+          }
         }
         const int row = row_base + lane;
         float rs = 1.f;
@@ -735,6 +740,19 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
           v[4 * k + 1] = __uint_as_float(r[4 * k + 1]) + b4.y;
           v[4 * k + 2] = __uint_as_float(r[4 * k + 2]) + b4.z;
           v[4 * k + 3] = __uint_as_float(r[4 * k + 3]) + b4.w;
+        }
+        if (g.aux_out && row < g.M) {
+          // saved pre-scale value z = acc + bias (bf16; LayerScale backward needs it): this lane's 64-byte row segment,
+          // written straight from registers (no shared-memory tile left for it; the stores are fire-and-forget)
+          uint4* ap = (uint4*)(g.aux_out + (int64_t)row * g.ld_aux_out + n);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            uint4 u;
+            __nv_bfloat162 t0 = __floats2bfloat162_rn(v[8 * k], v[8 * k + 1]), t1 = __floats2bfloat162_rn(v[8 * k + 2], v[8 * k + 3]);
+            __nv_bfloat162 t2 = __floats2bfloat162_rn(v[8 * k + 4], v[8 * k + 5]), t3 = __floats2bfloat162_rn(v[8 * k + 6], v[8 * k + 7]);
+            u.x = *(uint32_t*)&t0; u.y = *(uint32_t*)&t1; u.z = *(uint32_t*)&t2; u.w = *(uint32_t*)&t3;
+            ap[k] = u;
+          }
         }
         if (has_scale) {
 #pragma unroll
@@ -767,7 +785,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
           }
         }
         // in place: this lane overwrites exactly the chunks it read; without a residual the tile was last read by the
-        // store of block blk - 3, which the wait_read<1> at the end of block blk - 2 has retired
+        // store of block blk - 2, which the wait_read<1> at the end of block blk - 1 has retired
 #pragma unroll
         for (int k = 0; k < 8; ++k)
           *(float4*)(tile + swz128(lane, k)) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
@@ -776,8 +794,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
         if (lane == 0) {
           tma_store_2d(&map_c, tile, n, row_base);
           tma_store_commit();
-          tma_store_wait_read<1>();            // the store of block blk - 1 has finished reading its tile ...
-          if (want_res) prefetch();            // ... which is the slot of block blk + 2
+          if (!want_res) tma_store_wait_read<1>();
         }
         __syncwarp();
         ++blk;
@@ -947,8 +964,8 @@ static int launch_gemm_pair(const xfm_gemm_params* p, const GemmArgs& g, cudaStr
   g2.tma_epi = 0;
   auto a16 = [](const void* q) { return ((uintptr_t)q & 15) == 0; };
   static const bool f32_epi_on = getenv("XFM_GEMM_F32_EPI") == nullptr || atoi(getenv("XFM_GEMM_F32_EPI")) != 0;
-  if (f32_epi_on && g.epi_mode == 2 && p->c_dtype == 1 && !p->accumulate && g.split_k == 1 && p->act == 0 && !p->aux_out &&
-      (p->N % 32) == 0 && a16(p->C) && (p->ldc & 3) == 0 &&
+  if (f32_epi_on && g.epi_mode == 2 && p->c_dtype == 1 && !p->accumulate && g.split_k == 1 && p->act == 0 &&
+      (!p->aux_out || (a16(p->aux_out) && (p->ld_aux_out & 7) == 0)) && (p->N % 32) == 0 && a16(p->C) && (p->ldc & 3) == 0 &&
       (!p->residual || (p->res_dtype == 1 && a16(p->residual) && (p->ld_res & 3) == 0)) && (!p->bias || a16(p->bias)) &&
       (!p->col_scale || a16(p->col_scale))) {
     // f32 TMA epilogue variant (4 operand stages, residual / output tiles through the TMA engine)
