@@ -35,7 +35,9 @@ struct GemmArgs {
   uint64_t dropout_seed;
   int vec_ok;    // every epilogue pointer / leading dimension allows 2-element vector access at even columns
   int epi_mode;  // see epilogue_block
-  int tma_epi;   // CTA-pair kernel: modes 0 / 1 store bf16 tiles with TMA (epilogue_tma_block)
+  int tma_epi;   // CTA-pair kernel: modes 0 / 1 store bf16 tiles with TMA (epilogue_tma_block); 2 = f32 TMA epilogue
+  int n_fastest; // CTA-pair kernel: consecutive tiles walk N first (all N tiles of an M tile run concurrently: A is read from
+                 // HBM once even when it is far larger than L2; the weight operand B stays L2 resident either way)
 };
 
 template <int BLOCK_N>
@@ -272,14 +274,17 @@ XFM_DEVINL void epilogue_one(const GemmArgs& g, float* stage, uint32_t taddr, in
 constexpr int TMA_EPI_TILE_BYTES = 32 * 32 * 2;
 constexpr int TMA_EPI_WARP_BYTES = 4 * TMA_EPI_TILE_BYTES;
 
-XFM_DEVINL void st_row_bf16x32(uint8_t* row, const float (&v)[32]) {
+// `sw` = (row >> 1) & 3: SWIZZLE_64B position of the row's 16-byte chunks (tile base 512-byte aligned), which makes the
+// lane = row stores of a quarter warp hit 8 different bank groups (dense 64-byte rows: 4-way conflicts, 6.0 M conflict
+// cycles per fc1 GEMM in ncu, on the pipe the UMMA operand reads already keep ~60 % busy).
+XFM_DEVINL void st_row_bf16x32(uint8_t* row, const float (&v)[32], int sw) {
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     uint4 u;
     __nv_bfloat162 t0 = __floats2bfloat162_rn(v[8 * c], v[8 * c + 1]), t1 = __floats2bfloat162_rn(v[8 * c + 2], v[8 * c + 3]);
     __nv_bfloat162 t2 = __floats2bfloat162_rn(v[8 * c + 4], v[8 * c + 5]), t3 = __floats2bfloat162_rn(v[8 * c + 6], v[8 * c + 7]);
     u.x = *(uint32_t*)&t0; u.y = *(uint32_t*)&t1; u.z = *(uint32_t*)&t2; u.w = *(uint32_t*)&t3;
-    *(uint4*)(row + 16 * c) = u;
+    *(uint4*)(row + 16 * (c ^ sw)) = u;
   }
 }
 
@@ -328,7 +333,8 @@ XFM_DEVINL void epilogue_tma_block(const GemmArgs& g, const CUtensorMap* map_c, 
   const bool has_aux_out = MODE == 0 && g.aux_out != nullptr;
   uint8_t* t_aux = tiles + slot * TMA_EPI_TILE_BYTES;
   uint8_t* t_c = tiles + (slot ^ 1) * TMA_EPI_TILE_BYTES;
-  if (has_aux_out) st_row_bf16x32(t_aux + lane * 64, v);
+  const int sw = (lane >> 1) & 3;
+  if (has_aux_out) st_row_bf16x32(t_aux + lane * 64, v, sw);
   if (MODE == 0 && g.act == 1) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
@@ -342,7 +348,7 @@ XFM_DEVINL void epilogue_tma_block(const GemmArgs& g, const CUtensorMap* map_c, 
       v[2 * j + 1] *= gelu_grad_fast(af.y);
     }
   }
-  st_row_bf16x32(t_c + lane * 64, v);
+  st_row_bf16x32(t_c + lane * 64, v, sw);
   fence_proxy_async();
   __syncwarp();
   if (lane == 0) {
@@ -605,8 +611,10 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
       for (int t = pair_id; t < num_tiles; t += num_pairs) {
         const int ks = t % g.split_k;
         const int rest = t / g.split_k;
-        const int m0 = ((rest % num_m_pairs) * 2 + (int)rank) * BLOCK_M;      // this CTA's 128 rows of the 256-row tile
-        const int n0 = (rest / num_m_pairs) * BLOCK_N + (int)rank * 128;      // this CTA's half of the tile's N range
+        const int mt = g.n_fastest ? rest / g.num_n_tiles : rest % num_m_pairs;
+        const int nt = g.n_fastest ? rest % g.num_n_tiles : rest / num_m_pairs;
+        const int m0 = (mt * 2 + (int)rank) * BLOCK_M;      // this CTA's 128 rows of the 256-row tile
+        const int n0 = nt * BLOCK_N + (int)rank * 128;      // this CTA's half of the tile's N range
         const int kb0 = ks * kb_per_split;
         const int kb1 = min(g.kb_total, kb0 + kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -687,8 +695,10 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     // block sequence of this warp: tiles t = pair_id, pair_id + num_pairs, ...; blocks c_begin .. c_end-1 while inside N
     auto block_at = [&](int t, int c, int& rb, int& n) -> bool {
       if (t >= num_tiles) return false;
-      rb = ((t % num_m_pairs) * 2 + (int)rank) * BLOCK_M + q * 32;
-      n = (t / num_m_pairs) * BLOCK_N + c * EPI_COLS;
+      const int mt = g.n_fastest ? t / g.num_n_tiles : t % num_m_pairs;
+      const int nt = g.n_fastest ? t % g.num_n_tiles : t / num_m_pairs;
+      rb = (mt * 2 + (int)rank) * BLOCK_M + q * 32;
+      n = nt * BLOCK_N + c * EPI_COLS;
       return n < g.N;
     };
     int pf_t = pair_id, pf_c = c_begin, pf_k = 0;   // prefetch cursor (lane 0): next residual block to request
@@ -820,8 +830,10 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     uint32_t aphase = 0;
     for (int t = pair_id; t < num_tiles; t += num_pairs) {
       const int rest = t / g.split_k;
-      const int m0 = ((rest % num_m_pairs) * 2 + (int)rank) * BLOCK_M;
-      const int n0 = (rest / num_m_pairs) * BLOCK_N;
+      const int mt = g.n_fastest ? rest / g.num_n_tiles : rest % num_m_pairs;
+      const int nt = g.n_fastest ? rest % g.num_n_tiles : rest / num_m_pairs;
+      const int m0 = (mt * 2 + (int)rank) * BLOCK_M;
+      const int n0 = nt * BLOCK_N;
       const int ks = t % g.split_k;
       const int kb0 = ks * kb_per_split;
       const int kb1 = min(g.kb_total, kb0 + kb_per_split);
@@ -882,7 +894,7 @@ static int encode_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_
   return 0;
 }
 
-// bf16 [outer, inner] tile map without swizzle (TMA-store epilogue: dense 64-byte rows in shared memory)
+// bf16 [outer, inner] tile map, SWIZZLE_64B (TMA-store epilogue: 64-byte rows in shared memory, see st_row_bf16x32)
 static int encode_2d_plain(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
                            uint32_t box_inner, uint32_t box_outer) {
   auto fn = get_tensor_map_encoder();
@@ -892,7 +904,7 @@ static int encode_2d_plain(CUtensorMap* map, const void* base, uint64_t inner, u
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled (output) failed: %d (inner=%llu outer=%llu ld=%llu base=%p)", (int)r,
@@ -962,6 +974,13 @@ static int launch_gemm_pair(const xfm_gemm_params* p, const GemmArgs& g, cudaStr
   CUtensorMap map_c = map_a, map_aux = map_a;   // placeholders when the TMA-store epilogue is not used
   GemmArgs g2 = g;
   g2.tma_epi = 0;
+  // Tile order.  M-fastest (default) keeps a B tile hot while the grid sweeps M; each wave then touches ALL of A, so an A
+  // larger than L2 is re-read from HBM once per N tile (ncu: 407 MB read for the 18912 x 768 x 3072 fc2 GEMM whose
+  // operands + residual are 174 MB).  N-fastest runs the N tiles of an M tile side by side instead.
+  static const int raster_env = getenv("XFM_GEMM_RASTER") ? atoi(getenv("XFM_GEMM_RASTER")) : -1;
+  const int64_t a_bytes = (int64_t)p->M * p->K * 2, b_bytes = (int64_t)p->N * p->K * 2;
+  g2.n_fastest = (g.split_k == 1 && g.num_n_tiles > 1 && a_bytes > (40ll << 20) && b_bytes <= (16ll << 20)) ? 1 : 0;
+  if (raster_env >= 0) g2.n_fastest = (raster_env != 0 && g.split_k == 1) ? 1 : 0;
   auto a16 = [](const void* q) { return ((uintptr_t)q & 15) == 0; };
   static const bool f32_epi_on = getenv("XFM_GEMM_F32_EPI") == nullptr || atoi(getenv("XFM_GEMM_F32_EPI")) != 0;
   if (f32_epi_on && g.epi_mode == 2 && p->c_dtype == 1 && !p->accumulate && g.split_k == 1 && p->act == 0 &&
@@ -1058,6 +1077,7 @@ int gemm_bf16(const xfm_gemm_params* p, cudaStream_t stream) {
     else if (p->N <= 128 && bn > 128) bn = 128;
   }
   GemmArgs g;
+  g.tma_epi = 0; g.n_fastest = 0;
   g.M = p->M; g.N = p->N; g.K = p->K;
   g.num_m_tiles = (p->M + BLOCK_M - 1) / BLOCK_M;
   g.num_n_tiles = (p->N + bn - 1) / bn;
