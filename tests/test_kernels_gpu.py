@@ -159,6 +159,13 @@ def test_gemm_cta_pair_f32_tma_epilogue(lib, M, N, K):
     Bt = B.t().contiguous().cuda()
     out = lib.gemm(Ad, Bt, b_t=True, residual=resd, out_dtype=torch.float32)
     assert rel_err(out, z + res) < 1e-5
+    # dGELU TMA epilogue (pre-activation tile in through TMA, bf16 result written in place and stored by TMA)
+    h = bf(torch.randn(M, N, generator=G(7)))
+    hf = h.float()
+    dgelu = 0.5 * (1 + torch.erf(hf / math.sqrt(2))) + hf * torch.exp(-0.5 * hf * hf) / math.sqrt(2 * math.pi)
+    out = lib.gemm(Ad, Bt, b_t=True, act=2, aux_in=h.cuda())
+    assert rel_err(out, z * dgelu) < 5e-3
+    assert torch.equal(out, lib.gemm(Ad, Bt, b_t=True, act=2, aux_in=h.cuda(), block_n=128))
     # output written into a strided view (row stride > N)
     wide = torch.zeros(M, N + 64, dtype=torch.float32, device="cuda")
     lib.gemm(Ad, Bd, bias=bias.cuda(), residual=resd, out=wide[:, :N])

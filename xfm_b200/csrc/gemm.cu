@@ -528,30 +528,34 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 // traffic instead of 48 KB: the single-CTA kernel is capped by exactly that ingest rate (~47 B/clk/SM measured, tensor pipe
 // 49 % busy), which is where cuBLAS's 1.5 PF on these shapes comes from.
 constexpr int PAIR_STAGE_BYTES = 2 * 16384;  // A 128 x 64 + B 128 x 64 (bf16)
-// Shared-memory plan of the two variants: 5 operand stages + 64 KB of epilogue staging.  F32_EPI = false: bf16 TMA staging
-// tiles (the fp32 transposition blocks of the generic mode 2 alias them).  F32_EPI = true (fp32 residual in / fp32 out, see
+// Shared-memory plan of every variant: 5 operand stages + 64 KB of epilogue staging.  EPI = 0: bf16 TMA staging
+// tiles (the fp32 transposition blocks of the generic mode 2 alias them).  EPI = 1 (fp32 residual in / fp32 out, see
 // the f32 TMA epilogue below): a ring of two 4 KB fp32 tiles per epilogue warp.  (A three-tile ring with 4 operand stages
 // was measured first: the K = 3072 GEMMs lost in the main loop what the epilogue gained.)
 constexpr int F32_EPI_TILE_BYTES = 32 * 32 * 4;
 constexpr int F32_EPI_RING = 2;
-template <bool F32_EPI>
+template <int EPI>   // 0: classic / bf16 TMA-store epilogues, 1: f32 TMA epilogue, 2: dGELU (bf16 in / bf16 out) TMA epilogue
 struct PairCfg {
   static constexpr int STAGES = 5;
-  static constexpr int EPI_BYTES = F32_EPI ? 8 * F32_EPI_RING * F32_EPI_TILE_BYTES : 8 * TMA_EPI_WARP_BYTES;
+  static constexpr int EPI_BYTES = 8 * TMA_EPI_WARP_BYTES;   // >= the two-tile rings of the EPI = 1 / 2 variants
   static constexpr int BAR_BYTES = 512;
   static constexpr int SMEM_BYTES = STAGES * PAIR_STAGE_BYTES + EPI_BYTES + BAR_BYTES;
-  static_assert(EPI_BYTES >= 8 * 32 * 34 * 4, "mode-2 staging must fit");
+  static_assert(EPI_BYTES >= 8 * 32 * 34 * 4 && EPI_BYTES >= 8 * F32_EPI_RING * F32_EPI_TILE_BYTES, "staging must fit");
   static_assert(SMEM_BYTES <= 232448, "shared memory");
 };
 
-// Swizzle-128B position of 16-byte chunk `k` of row `r` in a TMA tile with 128-byte rows (tile base 1024-aligned).
+// Swizzle-128B position of 16-byte chunk `k` of row `r` in a TMA tile with 128-byte rows (tile base 1024-aligned), and the
+// Swizzle-64B one for 64-byte rows (tile base 512-aligned).
 XFM_DEVINL uint32_t swz128(int r, int k) { return (uint32_t)(r * 128 + ((k ^ (r & 7)) << 4)); }
+XFM_DEVINL uint32_t swz64(int r, int k) { return (uint32_t)(r * 64 + ((k ^ ((r >> 1) & 3)) << 4)); }
 
-template <int A_MN, int B_MN, bool F32_EPI>
+template <int A_MN, int B_MN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                          const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_aux, const GemmArgs g) {
-  using PC = PairCfg<F32_EPI>;
+  using PC = PairCfg<EPI>;
+  constexpr bool DG_EPI = EPI == 2;    // dGELU: bf16 pre-activation in / bf16 out (EPI == 1: f32 residual in / f32 out)
+  constexpr int RING_TILE_BYTES = DG_EPI ? 32 * 32 * 2 : F32_EPI_TILE_BYTES;
   constexpr int STAGES = PC::STAGES;
   constexpr int BLOCK_N = 256;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -583,7 +587,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], 2 * EPI_WARPS);
     }
-    if (F32_EPI) {
+    if (EPI != 0) {
       tma_prefetch_desc(&map_c);
       tma_prefetch_desc(&map_aux);
       for (int s = 0; s < EPI_WARPS * F32_EPI_RING; ++s) mbar_init(&res_bar[s], 1);
@@ -673,8 +677,10 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
       }
     }
     __syncwarp();
-  } else if (F32_EPI) {
+  } else if (EPI != 0) {
     // ---- f32 TMA epilogue: C(f32) = dropout((acc + bias) * col_scale * row_group_scale) + residual(f32).
+    // ---- dGELU TMA epilogue (EPI = 2): C(bf16) = (acc + bias) * gelu'(aux_in(bf16)); same ring with 2 KB SWIZZLE_64B tiles
+    //      (the operand used to be fetched with lane = row 16-byte global loads: 32 L1 wavefronts per instruction).
     // The generic mode-2 path moves the residual and the output through a transposition block with 16 row steps of
     // dependent global accesses per 32 x 32 block and is latency bound (65 us for the 18912 x 768 x 768 ViT projection,
     // whose operands + residual + output take 22 us of HBM time).  Here every epilogue warp owns a ring of two
@@ -685,9 +691,9 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     const int ew = warp - 2;
     constexpr int C_PER_WARP = BLOCK_N / (2 * EPI_COLS);
     const int c_begin = (ew >> 2) * C_PER_WARP, c_end = c_begin + C_PER_WARP;
-    uint8_t* ring = (uint8_t*)epi_stage + ew * F32_EPI_RING * F32_EPI_TILE_BYTES;
+    uint8_t* ring = (uint8_t*)epi_stage + ew * F32_EPI_RING * RING_TILE_BYTES;
     uint64_t* rbar = res_bar + ew * F32_EPI_RING;
-    const bool want_res = g.residual != nullptr;
+    const bool want_res = DG_EPI ? true : g.residual != nullptr;
     const bool has_scale = g.col_scale != nullptr || g.row_group_scale != nullptr;
     const bool has_drop = g.dropout_p > 0.f;
     const float inv_keep = has_drop ? 1.0f / (1.0f - g.dropout_p) : 1.0f;
@@ -706,8 +712,8 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
       int rb, n;
       if (!block_at(pf_t, pf_c, rb, n)) return;
       const int slot = pf_k % F32_EPI_RING;
-      mbar_arrive_expect_tx(&rbar[slot], F32_EPI_TILE_BYTES);
-      tma_load_2d(ring + slot * F32_EPI_TILE_BYTES, &map_aux, &rbar[slot], n, rb);
+      mbar_arrive_expect_tx(&rbar[slot], RING_TILE_BYTES);
+      tma_load_2d(ring + slot * RING_TILE_BYTES, &map_aux, &rbar[slot], n, rb);
       ++pf_k;
       if (++pf_c >= c_end || !block_at(pf_t, pf_c, rb, n)) { pf_t += num_pairs; pf_c = c_begin; }
     };
@@ -724,14 +730,19 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
         int row_base, n;
         if (!block_at(t, c, row_base, n)) break;
         const int slot = blk % F32_EPI_RING;
-        uint8_t* tile = ring + slot * F32_EPI_TILE_BYTES;
+        uint8_t* tile = ring + slot * RING_TILE_BYTES;
         uint32_t r[32];
         tmem_ld_32x32(t_base + c * EPI_COLS, r);
-        float4 res[8];
+        float4 res[DG_EPI ? 4 : 8];   // f32: the residual row; dGELU: the bf16 pre-activation row (4 x 8 values)
         if (want_res) {
           mbar_wait(&rbar[slot], (uint32_t)(blk / F32_EPI_RING) & 1u);
+          if (DG_EPI) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) res[k] = *(const float4*)(tile + swz128(lane, k));
+            for (int k = 0; k < 4; ++k) res[k] = *(const float4*)(tile + swz64(lane, k));
+          } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) res[k] = *(const float4*)(tile + swz128(lane, k));
+          }
           if (lane == 0) {
             tma_store_wait_read<0>();          // the store of block blk - 1 has finished reading the other tile ...
             prefetch();                        // ... which now receives the residual of block blk + 1
@@ -740,17 +751,35 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
         const int row = row_base + lane;
         float rs = 1.f;
         if (g.row_group_scale) rs = __ldg(g.row_group_scale + min(row, g.M - 1) / g.rows_per_group);
+        float4 b4[8];   // requested before the TMEM wait so the two latencies overlap
+#pragma unroll
+        for (int k = 0; k < 8; ++k) b4[k] = g.bias ? __ldg((const float4*)(g.bias + n) + k) : make_float4(0.f, 0.f, 0.f, 0.f);
         tmem_ld_wait();
         float v[32];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (g.bias) b4 = __ldg((const float4*)(g.bias + n) + k);
-          v[4 * k] = __uint_as_float(r[4 * k]) + b4.x;
-          v[4 * k + 1] = __uint_as_float(r[4 * k + 1]) + b4.y;
-          v[4 * k + 2] = __uint_as_float(r[4 * k + 2]) + b4.z;
-          v[4 * k + 3] = __uint_as_float(r[4 * k + 3]) + b4.w;
+          v[4 * k] = __uint_as_float(r[4 * k]) + b4[k].x;
+          v[4 * k + 1] = __uint_as_float(r[4 * k + 1]) + b4[k].y;
+          v[4 * k + 2] = __uint_as_float(r[4 * k + 2]) + b4[k].z;
+          v[4 * k + 3] = __uint_as_float(r[4 * k + 3]) + b4[k].w;
         }
+        if (DG_EPI) {
+          const __nv_bfloat162* a2 = (const __nv_bfloat162*)res;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float2 af = __bfloat1622float2(a2[j]);
+            v[2 * j] *= gelu_grad_fast(af.x);
+            v[2 * j + 1] *= gelu_grad_fast(af.y);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {   // in place: the bf16 result replaces the pre-activation row this lane read
+            uint4 u;
+            __nv_bfloat162 t0 = __floats2bfloat162_rn(v[8 * k], v[8 * k + 1]), t1 = __floats2bfloat162_rn(v[8 * k + 2], v[8 * k + 3]);
+            __nv_bfloat162 t2 = __floats2bfloat162_rn(v[8 * k + 4], v[8 * k + 5]), t3 = __floats2bfloat162_rn(v[8 * k + 6], v[8 * k + 7]);
+            u.x = *(uint32_t*)&t0; u.y = *(uint32_t*)&t1; u.z = *(uint32_t*)&t2; u.w = *(uint32_t*)&t3;
+            *(uint4*)(tile + swz64(lane, k)) = u;
+          }
+        } else {
         if (g.aux_out && row < g.M) {
           // saved pre-scale value z = acc + bias (bf16; LayerScale backward needs it): this lane's 64-byte row segment,
           // written straight from registers (no shared-memory tile left for it; the stores are fire-and-forget)
@@ -799,6 +828,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
 #pragma unroll
         for (int k = 0; k < 8; ++k)
           *(float4*)(tile + swz128(lane, k)) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+        }   // !DG_EPI
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
@@ -983,30 +1013,49 @@ static int launch_gemm_pair(const xfm_gemm_params* p, const GemmArgs& g, cudaStr
   if (raster_env >= 0) g2.n_fastest = (raster_env != 0 && g.split_k == 1) ? 1 : 0;
   auto a16 = [](const void* q) { return ((uintptr_t)q & 15) == 0; };
   static const bool f32_epi_on = getenv("XFM_GEMM_F32_EPI") == nullptr || atoi(getenv("XFM_GEMM_F32_EPI")) != 0;
+  static const bool dg_epi_on = getenv("XFM_GEMM_DG_EPI") == nullptr || atoi(getenv("XFM_GEMM_DG_EPI")) != 0;
   if (f32_epi_on && g.epi_mode == 2 && p->c_dtype == 1 && !p->accumulate && g.split_k == 1 && p->act == 0 &&
       (!p->aux_out || (a16(p->aux_out) && (p->ld_aux_out & 7) == 0)) && (p->N % 32) == 0 && a16(p->C) && (p->ldc & 3) == 0 &&
       (!p->residual || (p->res_dtype == 1 && a16(p->residual) && (p->ld_res & 3) == 0)) && (!p->bias || a16(p->bias)) &&
       (!p->col_scale || a16(p->col_scale))) {
-    // f32 TMA epilogue variant (4 operand stages, residual / output tiles through the TMA engine)
+    // f32 TMA epilogue variant (residual / output tiles through the TMA engine)
     rc = encode_2d_f32(&map_c, p->C, p->N, p->M, p->ldc);
     if (!rc && p->residual) rc = encode_2d_f32(&map_aux, p->residual, p->N, p->M, p->ld_res);
     if (rc) return rc;
     g2.tma_epi = 2;
-    auto kern32 = gemm_tcgen05_pair_kernel<A_MN, B_MN, true>;
+    auto kern32 = gemm_tcgen05_pair_kernel<A_MN, B_MN, 1>;
     static bool attr32_set = false;
     if (!attr32_set) {
-      cudaError_t e = cudaFuncSetAttribute(kern32, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<true>::SMEM_BYTES);
+      cudaError_t e = cudaFuncSetAttribute(kern32, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<1>::SMEM_BYTES);
       if (e != cudaSuccess) return (int)e;
       attr32_set = true;
     }
-    kern32<<<2 * pairs, GEMM_THREADS, PairCfg<true>::SMEM_BYTES, stream>>>(map_a, map_b, map_c, map_aux, g2);
+    kern32<<<2 * pairs, GEMM_THREADS, PairCfg<1>::SMEM_BYTES, stream>>>(map_a, map_b, map_c, map_aux, g2);
     count_launch();
     return (int)cudaGetLastError();
   }
-  auto kern = gemm_tcgen05_pair_kernel<A_MN, B_MN, false>;
+  if (dg_epi_on && g.epi_mode == 1 && p->c_dtype == 0 && g.split_k == 1 && (p->N % 32) == 0 && a16(p->C) && (p->ldc & 7) == 0 &&
+      p->aux_in && a16(p->aux_in) && (p->ld_aux_in & 7) == 0 && (!p->bias || a16(p->bias))) {
+    // dGELU TMA epilogue variant (pre-activation tiles in, bf16 result out through the TMA engine)
+    rc = encode_2d_plain(&map_c, p->C, p->N, p->M, p->ldc, 32, 32);
+    if (!rc) rc = encode_2d_plain(&map_aux, p->aux_in, p->N, p->M, p->ld_aux_in, 32, 32);
+    if (rc) return rc;
+    g2.tma_epi = 3;
+    auto kern_dg = gemm_tcgen05_pair_kernel<A_MN, B_MN, 2>;
+    static bool attr_dg_set = false;
+    if (!attr_dg_set) {
+      cudaError_t e = cudaFuncSetAttribute(kern_dg, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<2>::SMEM_BYTES);
+      if (e != cudaSuccess) return (int)e;
+      attr_dg_set = true;
+    }
+    kern_dg<<<2 * pairs, GEMM_THREADS, PairCfg<2>::SMEM_BYTES, stream>>>(map_a, map_b, map_c, map_aux, g2);
+    count_launch();
+    return (int)cudaGetLastError();
+  }
+  auto kern = gemm_tcgen05_pair_kernel<A_MN, B_MN, 0>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<false>::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<0>::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
@@ -1019,7 +1068,7 @@ static int launch_gemm_pair(const xfm_gemm_params* p, const GemmArgs& g, cudaStr
     if (rc) return rc;
     g2.tma_epi = 1;
   }
-  kern<<<2 * pairs, GEMM_THREADS, PairCfg<false>::SMEM_BYTES, stream>>>(map_a, map_b, map_c, map_aux, g2);
+  kern<<<2 * pairs, GEMM_THREADS, PairCfg<0>::SMEM_BYTES, stream>>>(map_a, map_b, map_c, map_aux, g2);
   count_launch();
   return (int)cudaGetLastError();
 }
