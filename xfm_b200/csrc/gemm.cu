@@ -768,8 +768,9 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float2 af = __bfloat1622float2(a2[j]);
-            v[2 * j] *= gelu_grad_fast(af.x);
-            v[2 * j + 1] *= gelu_grad_fast(af.y);
+            const float2 dg = gelu_grad_fast2(af.x, af.y);
+            v[2 * j] *= dg.x;
+            v[2 * j + 1] *= dg.y;
           }
 #pragma unroll
           for (int k = 0; k < 4; ++k) {   // in place: the bf16 result replaces the pre-activation row this lane read
