@@ -108,3 +108,34 @@ def test_itm_eval_metrics():
     ir = [100.0 * len(np.where(ranks < n)[0]) / len(ranks) for n in (1, 5, 10)]
     assert [got["txt_r1"], got["txt_r5"], got["txt_r10"]] == tr and [got["img_r1"], got["img_r5"], got["img_r10"]] == ir
     assert abs(got["r_mean"] - (sum(tr) / 3 + sum(ir) / 3) / 2) < 1e-12
+
+
+def test_wgrad_split_k_fills_whole_waves():
+    """blocks._split_k: the smallest factor that fills whole waves (<= 2 waves, >= 8 k-blocks per item)."""
+    from xfm_b200.blocks import _split_k
+    assert _split_k(18, 148, 296) == 8      # 768 x 768 outputs (128 x 256 tiles): 144 of 148 slots in one wave
+    assert _split_k(72, 148, 296) == 2      # 768 x 3072
+    assert _split_k(36, 74, 296) == 2       # 3072 x 768 on 74 SM pairs
+    assert _split_k(27, 74, 296) == 5       # 2304 x 768: 135 of 148 slots over two waves beats 54 of 74 in one
+    assert _split_k(591, 74, 23) == 1       # vocabulary-sized outputs never split
+    assert _split_k(18, 148, 60) == 7       # short reductions: at least 8 k-blocks per item
+    for tiles in (1, 3, 9, 18, 27, 36, 72, 100, 200):
+        for kb in (4, 23, 60, 296):
+            sk = _split_k(tiles, 148, kb)
+            assert 1 <= sk <= max(1, kb // 8) and tiles * sk <= max(2 * 148, tiles)
+
+
+def test_vqa_causal_bias_matches_the_reference_mask_rule():
+    """xroberta.py:771-806 with is_decoder=True: position i sees keys j <= i that are not padding.  The product adds a
+    causal [La, La] term and a key-padding term separately (-10000 each); after the softmax both forms give exact zeros."""
+    from oracle import xfm_oracle as O
+    atts = torch.tensor([[1, 1, 1, 1, 0, 0], [1, 1, 1, 1, 1, 1]])
+    ref = O.causal_extended_mask(atts)[:, 0]                                  # [B, L, L], one -10000 per masked pair
+    L = atts.shape[1]
+    ids = torch.arange(L)
+    causal = (ids[None, :] > ids[:, None]).float() * -10000.0                  # model_generation._causal_bias
+    key = (1.0 - atts.float()) * -10000.0                                      # RobertaStack.additive_mask
+    mine = causal[None] + key[:, None, :]
+    assert torch.equal(mine < 0, ref < 0)
+    s = torch.randn(2, L, L)
+    assert torch.equal(torch.softmax(s + mine, -1), torch.softmax(s + ref, -1))
