@@ -142,6 +142,13 @@ int xfm_layernorm_fwd(const void* x, int x_dtype, const float* w, const float* b
 int xfm_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* stats, const float* w,
                       const void* add_in, int add_dtype, void* dx, int dx_dtype, float* dw, float* db, int M, int D,
                       void* stream);
+/* LayerNorm backward of a RobertaSelfOutput / RobertaOutput site (xroberta.py:300-304,381-385: LayerNorm(dropout(dense(.)) +
+ * residual)) that also emits what the dense layer's own backward needs: dx16 = bf16(mask * dx / (1 - drop_p)) with the
+ * forward's dropout mask re-derived from (drop_seed, row * D + col) as in the GEMM epilogue, and dbias += column sums of
+ * dx16 (the dense bias gradient).  dx (f32 / bf16) is still written: it is the gradient of the residual branch. */
+int xfm_layernorm_bwd_dense(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* stats, const float* w,
+                            const void* add_in, int add_dtype, void* dx, int dx_dtype, float* dw, float* db, void* dx16_bf16,
+                            float* dbias, float drop_p, uint64_t drop_seed, int M, int D, void* stream);
 /* LayerScale / DropPath backward (beit2.py:204-205): dz = dx_out*gamma*rs; dgamma += sum dx_out*rs*z; dbias += sum dz. */
 int xfm_layerscale_bwd(const float* dx_out, const void* z_bf16, const float* gamma, const float* row_group_scale,
                        int rows_per_group, void* dz_bf16, float* dgamma, float* dbias, int M, int D, void* stream);

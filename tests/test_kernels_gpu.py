@@ -206,6 +206,32 @@ def test_layernorm_fwd_bwd(lib, D, xd):
     assert rel_err(dw, wr.grad) < 1e-5 and rel_err(db, br.grad) < 1e-5
 
 
+@pytest.mark.parametrize("M,p", [(333, 0.0), (3840, 0.1), (15360, 0.1)])
+def test_layernorm_bwd_dense_equals_the_three_pass_form(lib, M, p):
+    """xfm_layernorm_bwd_dense = layernorm_bwd, then dropout_apply (or the bf16 cast) of its output, then the bias column
+    sum of that: dx bit-equal, the bf16 copy bit-equal (same mask as the GEMM epilogue's), column sums to fp32 rounding."""
+    D = 768
+    g = G(M)
+    x = torch.randn(M, D, generator=g) * 2 + 0.5
+    w, b = 1 + 0.1 * torch.randn(D, generator=g), 0.1 * torch.randn(D, generator=g)
+    dy = torch.randn(M, D, generator=g)
+    _, stats, _ = lib.layernorm_fwd(x.cuda(), w.cuda(), b.cuda(), 1e-5)
+    dw0, db0 = torch.zeros(D, device="cuda"), torch.zeros(D, device="cuda")
+    dx0 = lib.layernorm_bwd(dy.cuda(), x.cuda(), stats, w.cuda(), dw0, db0)
+    if p > 0:
+        d16_0 = lib.dropout_apply(dx0, p, 77)
+    else:
+        d16_0 = dx0.to(torch.bfloat16)
+    bias0 = torch.zeros(D, device="cuda")
+    lib.colsum_into(d16_0, bias0)
+    dw1, db1, bias1 = torch.zeros(D, device="cuda"), torch.zeros(D, device="cuda"), torch.zeros(D, device="cuda")
+    dx1, d16_1 = lib.layernorm_bwd_dense(dy.cuda(), x.cuda(), stats, w.cuda(), dw1, db1, bias1, drop_p=p, drop_seed=77)
+    assert torch.equal(dx0, dx1) and torch.equal(d16_0, d16_1)
+    assert rel_err(dw1, dw0) < 1e-5 and rel_err(db1, db0) < 1e-5 and rel_err(bias1, bias0) < 1e-5
+    if p > 0:
+        assert abs(float((d16_1 != 0).float().mean()) - (1 - p)) < 0.01
+
+
 def test_layerscale_bwd_and_colsum(lib):
     g = G(9)
     M, D = 394, 768

@@ -190,10 +190,9 @@ def _attn_out_bwd(dh, s, w, g, pre, tag, ctx):
     """Backward of LayerNorm(dropout(dense(ctx)) + resid).  Returns (d_pre_ln f32 = grad wrt resid, d_ctx bf16).
     The residual-stream gradient stays fp32 between layers: LayerNorm backward cancels the large mean / x-hat components
     of dy, so bf16 rounding of dy would dominate the small components that survive."""
-    d_pre = L.layernorm_bwd(dh, getattr(s, tag + "_pre_ln"), getattr(s, tag + "_st"), w[pre + "ln_w"], g(pre + "ln_w"),
-                            g(pre + "ln_b"), out_dtype=torch.float32)
-    d_dense = _bf16_copy(d_pre) if s.p_hidden == 0 else L.dropout_apply(d_pre, s.p_hidden, getattr(s, tag + "_seed"))
-    L.colsum_into(d_dense, g(pre + "o_b"))
+    d_pre, d_dense = L.layernorm_bwd_dense(dh, getattr(s, tag + "_pre_ln"), getattr(s, tag + "_st"), w[pre + "ln_w"],
+                                           g(pre + "ln_w"), g(pre + "ln_b"), g(pre + "o_b"), drop_p=s.p_hidden,
+                                           drop_seed=getattr(s, tag + "_seed"))
     wgrad(g(pre + "o_w"), d_dense, ctx)
     d_ctx = L.gemm(d_dense, w[pre + "o_w16"], b_t=True)
     return d_pre, d_ctx
@@ -207,9 +206,8 @@ def roberta_layer_bwd(dh3, s, w, g, Bt, Lt, H, kmask, Benc=0, Lenc=0, kv_index=N
     scale = 1.0 / math.sqrt(64)
     f32 = torch.float32
     # ---- FFN
-    d_pre_ln = L.layernorm_bwd(dh3, s.f_pre_ln, s.f_st, w["f_ln_w"], g("f_ln_w"), g("f_ln_b"), out_dtype=f32)
-    d_dense = _bf16_copy(d_pre_ln) if s.p_hidden == 0 else L.dropout_apply(d_pre_ln, s.p_hidden, s.f_seed)
-    L.colsum_into(d_dense, g("f_b"))
+    d_pre_ln, d_dense = L.layernorm_bwd_dense(dh3, s.f_pre_ln, s.f_st, w["f_ln_w"], g("f_ln_w"), g("f_ln_b"), g("f_b"),
+                                              drop_p=s.p_hidden, drop_seed=s.f_seed)
     wgrad(g("f_w"), d_dense, s.act)
     d_i = L.gemm(d_dense, w["f_w16"], b_t=True, act=2, aux_in=s.pre)
     L.colsum_into(d_i, g("i_b"))

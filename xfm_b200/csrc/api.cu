@@ -68,6 +68,12 @@ int xfm_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, 
                       void* stream) {
   return layernorm_bwd(dy, dy_dtype, x, x_dtype, stats, w, add_in, add_dtype, dx, dx_dtype, dw, db, M, D, ST);
 }
+int xfm_layernorm_bwd_dense(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* stats, const float* w,
+                            const void* add_in, int add_dtype, void* dx, int dx_dtype, float* dw, float* db, void* dx16,
+                            float* dbias, float drop_p, uint64_t drop_seed, int M, int D, void* stream) {
+  return layernorm_bwd_dense(dy, dy_dtype, x, x_dtype, stats, w, add_in, add_dtype, dx, dx_dtype, dw, db, BF(dx16), dbias, drop_p,
+                             drop_seed, M, D, ST);
+}
 int xfm_layerscale_bwd(const float* dx_out, const void* z, const float* gamma, const float* rs, int rpg, void* dz, float* dgamma,
                        float* dbias, int M, int D, void* stream) {
   return layerscale_bwd(dx_out, CBF(z), gamma, rs, rpg, BF(dz), dgamma, dbias, M, D, ST);

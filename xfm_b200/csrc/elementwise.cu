@@ -107,12 +107,17 @@ XFM_DEVINL float4 lds4(const uint8_t* slot, int dtype, int c) {  // 4 elements a
   return make_float4(a.x, a.y, b.x, b.y);
 }
 
-template <int NV>
+// DENSE: also emit what the Linear in front of this LayerNorm needs for ITS backward (xroberta.py:300-304,381-385:
+// LayerNorm(dropout(dense(.)) + residual)): dx16 = bf16(dropout_mask * dx / (1 - p)) — the dgrad / wgrad operand, with the
+// forward's mask re-derived from (seed, row * D + col) like the GEMM epilogue that applied it — and dbias += its column
+// sums.  Replaces a dropout / cast pass and a column-sum pass over the same rows (2 launches per site, 60 sites per step).
+template <int NV, bool DENSE>
 __global__ void __launch_bounds__(LN_WARPS * 32, 1)
 layernorm_bwd_kernel(const void* __restrict__ dy, int dy_dtype, const void* __restrict__ x, int x_dtype,
                      const float* __restrict__ stats, const float* __restrict__ w, const void* __restrict__ add_in,
                      int add_dtype, void* __restrict__ dx, int dx_dtype, float* __restrict__ dw, float* __restrict__ db,
-                     int M, int D, int rows_per_cta, int nw) {   // nw: warps that own a staging ring (<= LN_WARPS)
+                     int M, int D, int rows_per_cta, int nw,   // nw: warps that own a staging ring (<= LN_WARPS)
+                     bf16* __restrict__ dx16, float* __restrict__ dbias, float drop_p, uint64_t drop_seed) {
   extern __shared__ __align__(16) uint8_t ln_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int dy_b = D * (dy_dtype == 1 ? 4 : 2), x_b = D * (x_dtype == 1 ? 4 : 2);
@@ -120,9 +125,13 @@ layernorm_bwd_kernel(const void* __restrict__ dy, int dy_dtype, const void* __re
   const int slot_b = dy_b + x_b + add_b + 16;   // + the row's (mean, rstd)
   uint8_t* ring = ln_smem + (size_t)warp * 2 * slot_b;
   const uint32_t ring_a = smem_u32(ring);
-  float4 aw[NV], ab[NV];
+  float4 aw[NV], ab[NV], ad[DENSE ? NV : 1];
 #pragma unroll
   for (int i = 0; i < NV; ++i) aw[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < (DENSE ? NV : 1); ++i) ad[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float inv_keep = (DENSE && drop_p > 0.f) ? 1.0f / (1.0f - drop_p) : 1.0f;
+  const uint32_t seed_mix = drop_seed_mix(drop_seed), thr = drop_threshold(drop_p);
   const int row0 = blockIdx.x * rows_per_cta;
   const int row1 = (warp < nw) ? min(M, row0 + rows_per_cta) : 0;   // ring-less warps only join the final reduction
 
@@ -185,34 +194,58 @@ layernorm_bwd_kernel(const void* __restrict__ dy, int dy_dtype, const void* __re
           o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
         }
         st4(dx, dx_dtype, base + c, o);
+        if (DENSE) {
+          if (drop_p > 0.f) {   // D is even and c a multiple of 4: the four elements are two whole hash pairs
+            const uint64_t pr = (uint64_t)(base + c) >> 1;
+            const uint32_t k0 = drop_keep_pair(seed_mix, (uint32_t)pr, (uint32_t)(pr >> 32), thr);
+            const uint32_t k1 = drop_keep_pair(seed_mix, (uint32_t)(pr + 1), (uint32_t)((pr + 1) >> 32), thr);
+            o.x = (k0 & 1u) ? o.x * inv_keep : 0.f;
+            o.y = (k0 & 2u) ? o.y * inv_keep : 0.f;
+            o.z = (k1 & 1u) ? o.z * inv_keep : 0.f;
+            o.w = (k1 & 2u) ? o.w * inv_keep : 0.f;
+          }
+          const __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+          uint2 u;
+          u.x = *(const uint32_t*)&lo;
+          u.y = *(const uint32_t*)&hi;
+          *(uint2*)(dx16 + base + c) = u;
+          const float2 flo = __bfloat1622float2(lo), fhi = __bfloat1622float2(hi);   // the column sums see the rounded values
+          ad[i].x += flo.x; ad[i].y += flo.y; ad[i].z += fhi.x; ad[i].w += fhi.y;
+        }
       }
     }
     __syncwarp();                                   // every lane is done reading this slot
     issue(row + 2 * nw, k & 1);                     // refill it with the row after next
   }
   cp_async_wait<0>();
-  if (!dw) return;
+  if (!dw && !DENSE) return;
   __syncthreads();                                   // the rings are dead: reuse shared memory for the cross-warp reduction
   float* rw = (float*)ln_smem;
   float* rb = rw + LN_WARPS * D;
+  float* rd = rb + LN_WARPS * D;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = (i * 32 + lane) * 4;
     if (c < D) {
       *(float4*)(rw + warp * D + c) = aw[i];
       *(float4*)(rb + warp * D + c) = ab[i];
+      if (DENSE) *(float4*)(rd + warp * D + c) = ad[i];
     }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < D; c += blockDim.x) {
-    float sw = 0.f, sb = 0.f;
+    float sw = 0.f, sb = 0.f, sd = 0.f;
 #pragma unroll
     for (int k = 0; k < LN_WARPS; ++k) {
       sw += rw[k * D + c];
       sb += rb[k * D + c];
+      if (DENSE) sd += rd[k * D + c];
     }
-    atomicAdd(dw + c, sw);
-    atomicAdd(db + c, sb);
+    if (dw) {
+      atomicAdd(dw + c, sw);
+      atomicAdd(db + c, sb);
+    }
+    if (DENSE && dbias) atomicAdd(dbias + c, sd);
   }
 }
 
@@ -665,7 +698,18 @@ static int rows_per_cta_for(int M) {
 int layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* stats, const float* w,
                   const void* add_in, int add_dtype, void* dx, int dx_dtype, float* dw, float* db, int M, int D,
                   cudaStream_t s) {
+  return layernorm_bwd_dense(dy, dy_dtype, x, x_dtype, stats, w, add_in, add_dtype, dx, dx_dtype, dw, db, nullptr, nullptr, 0.f, 0,
+                             M, D, s);
+}
+
+int layernorm_bwd_dense(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* stats, const float* w,
+                        const void* add_in, int add_dtype, void* dx, int dx_dtype, float* dw, float* db, bf16* dx16,
+                        float* dbias, float drop_p, uint64_t drop_seed, int M, int D, cudaStream_t s) {
   if (ln_check(D)) return XFM_ERR_BAD_ARG;
+  if (dx16 && (((uintptr_t)dx16 & 7) || (D & 3))) {
+    set_error("layernorm_bwd_dense: dx16 must be 8-byte aligned and D a multiple of 4");
+    return XFM_ERR_BAD_ARG;
+  }
   if (D & 7) {
     set_error("layernorm_bwd: feature dim %d must be a multiple of 8 (16-byte cp.async rows)", D);
     return XFM_ERR_BAD_ARG;
@@ -681,21 +725,34 @@ int layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, cons
   int nw = LN_WARPS;   // wide fp32 rows: fewer warps get a staging ring so the rings fit shared memory
   while (nw > 1 && (size_t)nw * 2 * slot > 200 * 1024) --nw;
   size_t smem = (size_t)nw * 2 * slot;
-  const size_t red = (size_t)2 * LN_WARPS * D * sizeof(float);
+  const size_t red = (size_t)(dx16 ? 3 : 2) * LN_WARPS * D * sizeof(float);
   if (smem < red) smem = red;
   if (smem > 220 * 1024) {
     set_error("layernorm_bwd: D=%d needs %zu bytes of shared memory", D, smem);
     return XFM_ERR_BAD_ARG;
   }
+  if (dx16) {
+    LN_DISPATCH(D, {
+      static size_t attr = 0;  // one per instantiation
+      if (smem > attr) {
+        cudaError_t e = cudaFuncSetAttribute(layernorm_bwd_kernel<NV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        attr = smem;
+      }
+      layernorm_bwd_kernel<NV, true><<<grid, LN_WARPS * 32, smem, s>>>(dy, dy_dtype, x, x_dtype, stats, w, add_in, add_dtype, dx,
+                                                                       dx_dtype, dw, db, M, D, rpc, nw, dx16, dbias, drop_p, drop_seed);
+    });
+    LAUNCH_END();
+  }
   LN_DISPATCH(D, {
     static size_t attr = 0;  // one per instantiation
     if (smem > attr) {
-      cudaError_t e = cudaFuncSetAttribute(layernorm_bwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaError_t e = cudaFuncSetAttribute(layernorm_bwd_kernel<NV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
       attr = smem;
     }
-    layernorm_bwd_kernel<NV><<<grid, LN_WARPS * 32, smem, s>>>(dy, dy_dtype, x, x_dtype, stats, w, add_in, add_dtype, dx, dx_dtype,
-                                                               dw, db, M, D, rpc, nw);
+    layernorm_bwd_kernel<NV, false><<<grid, LN_WARPS * 32, smem, s>>>(dy, dy_dtype, x, x_dtype, stats, w, add_in, add_dtype, dx,
+                                                                      dx_dtype, dw, db, M, D, rpc, nw, nullptr, nullptr, 0.f, 0);
   });
   LAUNCH_END();
 }

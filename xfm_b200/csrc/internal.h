@@ -35,6 +35,9 @@ int layernorm_fwd(const void* x, int x_dtype, const float* w, const float* b, vo
 int layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* stats, const float* w,
                   const void* add_in, int add_dtype, void* dx, int dx_dtype, float* dw, float* db, int M, int D,
                   cudaStream_t s);
+int layernorm_bwd_dense(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* stats, const float* w,
+                        const void* add_in, int add_dtype, void* dx, int dx_dtype, float* dw, float* db, bf16_t* dx16,
+                        float* dbias, float drop_p, uint64_t drop_seed, int M, int D, cudaStream_t s);
 int layerscale_bwd(const float* dxo, const bf16_t* z, const float* gamma, const float* rs, int rpg, bf16_t* dz, float* dgamma,
                    float* dbias, int M, int D, cudaStream_t s);
 int colsum_bf16(const bf16_t* in, int64_t ld, float* out, int M, int N, cudaStream_t s);

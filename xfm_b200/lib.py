@@ -300,6 +300,19 @@ def layernorm_bwd(dy, x, stats, w, dw, db, add_in=None, out_dtype=torch.float32)
     return dx
 
 
+def layernorm_bwd_dense(dy, x, stats, w, dw, db, dbias, drop_p=0.0, drop_seed=0, out_dtype=torch.float32):
+    """LayerNorm backward that also returns dx16 = bf16(dropout_mask * dx / (1 - p)) and accumulates its column sums into
+    `dbias` (see xfm_layernorm_bwd_dense).  Returns (dx, dx16)."""
+    M, D = x.shape
+    assert dy.is_contiguous() and x.is_contiguous() and dy.shape == x.shape and dbias.dtype == torch.float32
+    dx = torch.empty((M, D), dtype=out_dtype, device=x.device)
+    dx16 = torch.empty((M, D), dtype=torch.bfloat16, device=x.device)
+    check(lib().xfm_layernorm_bwd_dense(_p(dy), _dt(dy), _p(x), _dt(x), _p(stats), _p(w), _p(None), 0, _p(dx), _dt(dx), _p(dw),
+                                        _p(db), _p(dx16), _p(dbias), C.c_float(drop_p), C.c_uint64(drop_seed), M, D,
+                                        stream_ptr()), "xfm_layernorm_bwd_dense")
+    return dx, dx16
+
+
 def layerscale_bwd(dx_out, z, gamma, dgamma, dbias, row_group_scale=None, rows_per_group=1):
     M, D = dx_out.shape
     assert dx_out.dtype == torch.float32 and z.dtype == torch.bfloat16 and dx_out.is_contiguous() and z.is_contiguous()
