@@ -185,7 +185,8 @@ def test_gemm_dropout_statistics_and_determinism(lib):
 
 
 # ------------------------------------------------------------------------------------------------ LayerNorm
-@pytest.mark.parametrize("D,xd", [(768, torch.float32), (768, torch.bfloat16), (128, torch.float32), (1536, torch.float32)])
+@pytest.mark.parametrize("D,xd", [(768, torch.float32), (768, torch.bfloat16), (128, torch.float32), (1536, torch.float32),
+                                  (3072, torch.float32)])   # 3072: build_mlp on two concatenated CLS rows (model_nlvr.py:25)
 def test_layernorm_fwd_bwd(lib, D, xd):
     g = G(D)
     M = 333

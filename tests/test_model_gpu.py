@@ -446,3 +446,32 @@ def test_vqa_base_width_against_oracle():
     l2 = model(c["image"], q, a, k=b["k"], weights=c["weights"], train=True)
     l2.backward()
     assert torch.isfinite(l2) and abs(float(l2) - float(loss)) > 0
+
+
+def test_nlvr_base_width_head_against_torch():
+    """model_nlvr.py:25 at the XFM-base width: build_mlp(1536 -> 3072 -> 2) needs a 3072-wide LayerNorm (beyond the
+    2048-wide rows of every encoder LayerNorm).  2 layers per stack; loss and head gradients against torch on the module's
+    own concatenated CLS rows."""
+    from xfm_b200.model_nlvr import XFMForNLVR
+    cfg = O.base_config(vision_depth=2, text_layers=2, fusion_layers=2, use_bbox=False)
+    B = 4
+    batch = O.make_batch(cfg, 2 * B, L=40, M=2, seed=9)
+    model = XFMForNLVR(dict(cfg), init=lambda n, s: O.make_tensor(n, s, 0), device="cuda").eval()
+    image, ids, atts = batch["image"].cuda(), batch["text_ids"][:B].cuda(), batch["text_atts"][:B].cuda()
+    targets = torch.tensor([0, 1, 1, 0], device="cuda")
+    loss = model(image, ids, atts, targets)
+    loss.backward()
+    with torch.no_grad():
+        ie, ia = model.get_vision_embeds(image)
+        te = model.get_text_embeds(ids, atts)
+        c1 = model.get_cross_embeds(ie[:B], ia[:B], text_embeds=te, text_atts=atts, is_pretrain=False)[:, 0]
+        c2 = model.get_cross_embeds(ie[B:], ia[B:], text_embeds=te, text_atts=atts, is_pretrain=False)[:, 0]
+    x = torch.cat([c1, c2], -1).float().cpu()
+    head = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in model.cls_head.state_dict().items()}
+    h = torch.nn.functional.linear(x, head["0.weight"], head["0.bias"])
+    h = torch.nn.functional.gelu(torch.nn.functional.layer_norm(h, (h.shape[-1],), head["1.weight"], head["1.bias"], 1e-5))
+    ref = torch.nn.functional.cross_entropy(torch.nn.functional.linear(h, head["3.weight"], head["3.bias"]), targets.cpu())
+    ref.backward()
+    assert abs(float(loss) - float(ref)) <= 2e-3 * max(1.0, abs(float(ref))), (float(loss), float(ref))
+    for n, p in model.cls_head.named_parameters():
+        assert _maxabs(p.grad, head[n].grad) <= 6e-2 * max(float(head[n].grad.abs().max()), 1e-8), n

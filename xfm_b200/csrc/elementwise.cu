@@ -649,9 +649,11 @@ batch_sum_bf16_kernel(const bf16* __restrict__ in, float* __restrict__ out, int 
 }
 
 // ------------------------------------------------------------------------------------------ host
-static int ln_check(int D) {
-  if (D % 4 != 0 || D > 32 * 4 * LN_MAX_VEC) {
-    set_error("feature dim %d unsupported (need multiple of 4, <= %d)", D, 32 * 4 * LN_MAX_VEC);
+// LN_DISPATCH covers rows up to 4096 wide (NV = 32: the 3072-wide hidden layer of build_mlp on concatenated CLS rows,
+// model_nlvr.py:25); the embedding kernel keeps its row in LN_MAX_VEC registers (<= 2048).
+static int ln_check(int D, int max_vec = 32) {
+  if (D % 4 != 0 || D > 32 * 4 * max_vec) {
+    set_error("feature dim %d unsupported (need multiple of 4, <= %d)", D, 32 * 4 * max_vec);
     return XFM_ERR_BAD_ARG;
   }
   return 0;
@@ -671,7 +673,9 @@ static int grid_1d(size_t n, int block) {
     else if (nv_ <= 6) { constexpr int NV = 6; __VA_ARGS__; }   \
     else if (nv_ <= 8) { constexpr int NV = 8; __VA_ARGS__; }   \
     else if (nv_ <= 12) { constexpr int NV = 12; __VA_ARGS__; } \
-    else { constexpr int NV = 16; __VA_ARGS__; }                \
+    else if (nv_ <= 16) { constexpr int NV = 16; __VA_ARGS__; } \
+    else if (nv_ <= 24) { constexpr int NV = 24; __VA_ARGS__; } \
+    else { constexpr int NV = 32; __VA_ARGS__; }                \
   } while (0)
 
 #define LAUNCH_END()  \
@@ -831,7 +835,7 @@ int dropout_apply(const void* x, int x_dtype, bf16* y, size_t n, float p, uint64
 int roberta_embed_fwd(const int64_t* ids, const float* word, const float* pos, const float* type0, const float* w,
                       const float* b, bf16* y, float* pre_ln, float* stats, int32_t* pos_ids, int B, int L, int D,
                       int pad_id, float eps, cudaStream_t s) {
-  if (ln_check(D)) return XFM_ERR_BAD_ARG;
+  if (ln_check(D, LN_MAX_VEC)) return XFM_ERR_BAD_ARG;
   if (B <= 0) return 0;
   roberta_embed_fwd_kernel<<<B, LN_WARPS * 32, L * sizeof(int), s>>>(ids, word, pos, type0, w, b, y, pre_ln, stats, pos_ids, L, D,
                                                                    pad_id, eps);
