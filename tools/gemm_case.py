@@ -1,5 +1,6 @@
 """Time (and give ncu something short to profile) the fused-epilogue GEMM variants at the ViT-B shapes of the step.
     python tools/gemm_case.py [case ...]      cases: plain gelu dgelu proj fc2 wgrad ffn_out all
+                                              (+ gelu_noaux plain_aux plain_wide: the fc1 epilogue taken apart)
 """
 import json
 import os
@@ -26,6 +27,15 @@ def build(case):
     if case == "gelu":
         a, w, b, aux = rnd(M, D), rnd(F, D), rnd(F, dtype=torch.float32), torch.empty(M, F, device=dev, dtype=torch.bfloat16)
         return (lambda: L.gemm(a, w, bias=b, act=1, aux_out=aux)), 2.0 * M * F * D, M * F * 4
+    if case == "gelu_noaux":   # the GELU arithmetic without the second (saved pre-activation) store
+        a, w, b = rnd(M, D), rnd(F, D), rnd(F, dtype=torch.float32)
+        return (lambda: L.gemm(a, w, bias=b, act=1)), 2.0 * M * F * D, M * F * 2
+    if case == "plain_aux":    # the second store without the GELU arithmetic
+        a, w, b, aux = rnd(M, D), rnd(F, D), rnd(F, dtype=torch.float32), torch.empty(M, F, device=dev, dtype=torch.bfloat16)
+        return (lambda: L.gemm(a, w, bias=b, aux_out=aux)), 2.0 * M * F * D, M * F * 4
+    if case == "plain_wide":   # bias only, N = 3072 (same tile count as the GELU case)
+        a, w, b = rnd(M, D), rnd(F, D), rnd(F, dtype=torch.float32)
+        return (lambda: L.gemm(a, w, bias=b)), 2.0 * M * F * D, M * F * 2
     if case == "dgelu":
         a, w, aux = rnd(M, D), rnd(D, F), rnd(M, F)
         return (lambda: L.gemm(a, w, b_t=True, act=2, aux_in=aux)), 2.0 * M * F * D, M * F * 4
