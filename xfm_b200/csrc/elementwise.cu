@@ -548,19 +548,30 @@ assemble_tokens_kernel(const float* __restrict__ patch, const float* __restrict_
 __global__ void __launch_bounds__(256)
 assemble_tokens_bwd_kernel(const float* __restrict__ dx, const uint8_t* __restrict__ mask, bf16* __restrict__ dpatch,
                            float* __restrict__ dcls, float* __restrict__ dmask_token, int B, int np, int D) {
-  const int row = blockIdx.x;
-  const int b = row / (np + 1), t = row % (np + 1);
-  const bool masked = (t > 0) && mask && mask[(size_t)b * np + t - 1];
+  // grid (B, 4): a CTA walks every 4th token row of one image, thread = float4 column; the mask-token gradient is summed in
+  // registers and reaches global memory as ONE atomic per column and CTA (the first version issued one per masked element:
+  // 5.5 M atomics on 768 addresses at B = 96, 152 us).
+  const int b = blockIdx.x;
   for (int c = threadIdx.x * 4; c < D; c += blockDim.x * 4) {
-    const float4 v = *(const float4*)(dx + (size_t)row * D + c);
-    if (t == 0) {
-      atomicAdd(dcls + c, v.x); atomicAdd(dcls + c + 1, v.y); atomicAdd(dcls + c + 2, v.z); atomicAdd(dcls + c + 3, v.w);
-    } else {
-      if (masked) {
-        atomicAdd(dmask_token + c, v.x); atomicAdd(dmask_token + c + 1, v.y);
-        atomicAdd(dmask_token + c + 2, v.z); atomicAdd(dmask_token + c + 3, v.w);
+    float4 am = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool any = false;
+    for (int t = blockIdx.y; t <= np; t += gridDim.y) {
+      const size_t row = (size_t)b * (np + 1) + t;
+      const float4 v = *(const float4*)(dx + row * D + c);
+      if (t == 0) {
+        atomicAdd(dcls + c, v.x); atomicAdd(dcls + c + 1, v.y); atomicAdd(dcls + c + 2, v.z); atomicAdd(dcls + c + 3, v.w);
+      } else {
+        const bool masked = mask && mask[(size_t)b * np + t - 1];
+        if (masked) {
+          am.x += v.x; am.y += v.y; am.z += v.z; am.w += v.w;
+          any = true;
+        }
+        st4(dpatch, 0, ((size_t)b * np + t - 1) * D + c, masked ? make_float4(0.f, 0.f, 0.f, 0.f) : v);
       }
-      st4(dpatch, 0, ((size_t)b * np + t - 1) * D + c, masked ? make_float4(0.f, 0.f, 0.f, 0.f) : v);
+    }
+    if (any) {
+      atomicAdd(dmask_token + c, am.x); atomicAdd(dmask_token + c + 1, am.y);
+      atomicAdd(dmask_token + c + 2, am.z); atomicAdd(dmask_token + c + 3, am.w);
     }
   }
 }
@@ -881,7 +892,7 @@ int assemble_tokens(const float* patch, const float* cls, const float* mask_toke
 }
 int assemble_tokens_bwd(const float* dx, const uint8_t* mask, bf16* dpatch, float* dcls, float* dmask_token, int B, int np,
                         int D, cudaStream_t s) {
-  assemble_tokens_bwd_kernel<<<B * (np + 1), 256, 0, s>>>(dx, mask, dpatch, dcls, dmask_token, B, np, D);
+  assemble_tokens_bwd_kernel<<<dim3(B, 4), 256, 0, s>>>(dx, mask, dpatch, dcls, dmask_token, B, np, D);
   LAUNCH_END();
 }
 int meanpool_fwd(bf16* y, float* y32, int B, int np, int D, cudaStream_t s) {
