@@ -27,6 +27,9 @@ sys.path.insert(0, ROOT)
 # algorithmic FLOPs per image-text pair, fwd+bwd, measured on the reference with FlopCounterMode:
 # 406.94 GFLOP (ITC+ITM+MLM+MSE-MIM) + VQ-KD tokenizer fwd 35.47 + codebook 0.10 + lm_head 768->8192 on 75 rows 2.83
 GFLOP_PER_PAIR = 445.3
+# one fusion layer (self-attn + cross-attn over 197 image tokens + FFN), one sample-pass, L=40: 1.1545 GFLOP fwd, 3.46 fwd+bwd
+# (SURVEY.md §8d); a pre-training pair makes 4 passes (pos, 2 hard negatives, MLM) through 12 layers
+FUSION_GFLOP_PER_PAIR = 4 * 12 * 3.46
 METRIC = "image-text pairs/sec/step"
 UNIT = "pairs/s"
 
@@ -136,6 +139,69 @@ def make_host_batch(B, L, M, vocab, res, seed):
     return {k: v.pin_memory() for k, v in out.items()}
 
 
+def _eager_legs(dev, B, steps, out):
+    from oracle import xfm_oracle as O
+    cfg = O.base_config(use_vision_tokenizer=True)
+    init = gpu_init(dev, 0)
+    shapes = dict(O.param_shapes(cfg))
+    shapes.update(O.vqkd_param_shapes(cfg))
+    sd = {k: init(k, s).to(dev) for k, s in shapes.items()}
+    sd["temp"] = torch.tensor(0.07, device=dev)
+    train = [v.requires_grad_(True) for k, v in sd.items() if not k.startswith("vqkd.") and v.dtype.is_floating_point]
+    optim = torch.optim.AdamW(train, lr=1e-4, betas=(0.9, 0.98), eps=1e-8, weight_decay=0.01)
+    batch = {k: v.to(dev) for k, v in O.make_batch(cfg, B, L=40, M=15, seed=1, image_uniform=True).items()}
+    ineg, tneg = torch.roll(torch.arange(B, device=dev), 1), torch.roll(torch.arange(B, device=dev), -1)
+    import random
+    import numpy as np
+    random.seed(1234)
+    np.random.seed(1234)
+    ids_mask = O.sample_mim_masks(cfg, B).to(dev)
+
+    def step():
+        res = O.pretrain_forward(sd, cfg, batch, ineg, tneg, ids_mask=ids_mask)
+        loss = res["loss_itc"] + res["loss_itm"] + res["loss_mlm"] + res["loss_mim"]
+        optim.zero_grad(set_to_none=True)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(train, 1.0)
+        optim.step()
+        return loss
+
+    for name, autocast in (("bf16_autocast", True), ("fp32", False)):
+        def run():
+            if not autocast:
+                return step()
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                return step()
+        run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss = run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out[name] = {"value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "loss": float(loss.detach())}
+    out["peak_mem_gib"] = round(torch.cuda.max_memory_allocated(dev) / 2**30, 1)
+
+
+def gpu_eager_baseline(dev, B, steps=3):
+    """The comparator SURVEY.md §0.1 / §8d names: the reference algorithm as eager PyTorch library calls (cuBLAS / ATen
+    kernels; oracle/xfm_oracle.py is that op sequence) on the SAME B200, same workload and batch, fwd + bwd + clip +
+    torch.optim.AdamW, under bf16 autocast and in fp32.  Reported next to cpu_baseline; not the product path."""
+    import gc
+    out = {"pairs_per_step": B, "optimizer": "torch.optim.AdamW (foreach)", "steps": steps, "warmup": 1,
+           "what": "oracle/xfm_oracle.py op sequence (= the reference's ATen calls) on cuda:0, eval-mode dropout"}
+    try:
+        _eager_legs(dev, B, steps, out)
+    except Exception as e:  # an out-of-memory eager run is itself a result
+        out["error"] = f"{type(e).__name__}: {str(e)[:200]}"
+    gc.collect()
+    torch.cuda.empty_cache()
+    torch.cuda.reset_peak_memory_stats(dev)
+    return out
+
+
 def run_ours(args):
     import torch.distributed as dist
     from xfm_b200 import lib as L
@@ -158,9 +224,12 @@ def run_ours(args):
     np.random.seed(1234 + rank)
     torch.manual_seed(1234 + rank)
     cfg = base_config()
+    eager = None
+    if world == 1 and rank == 0 and not args.no_eager:
+        eager = gpu_eager_baseline(dev, B)
     model = XFM(cfg, init=gpu_init(dev, 0), device=dev).train()
     opt = FlatAdamW(model, lr=1e-4, weight_decay=0.01, lr_mult=2.0)
-    acc = B200DDPAccelerator(dict(CLIP_GRAD_NORM=1.0, AUTO_CAST=False))
+    acc = B200DDPAccelerator(dict(CLIP_GRAD_NORM=1.0, AUTO_CAST=False, OVERLAP_ALLREDUCE=args.overlap))
     wrapped, opt, _ = acc.set_up(model, opt, None, local, world, rank)
     n_pool = 4
     host = [make_host_batch(B, Lt, M, model.cfg["vocab_size"], 224, 100 + 17 * rank + i) for i in range(n_pool)]
@@ -255,8 +324,23 @@ def run_ours(args):
 
     # ---- roofline leg: one more step with CUDA events around every launch of the dominant kernel (the tcgen05 GEMM)
     L.gemm_profile = []
+    fus_ev = []
+
+    def timed_call(fn):
+        def wrapper(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a, **k)
+            e1.record()
+            fus_ev.append((e0, e1))
+            return r
+        return wrapper
+    fwd0, bwd0 = model._fus.layers_fwd, model._fus.layers_bwd
+    model._fus.layers_fwd, model._fus.layers_bwd = timed_call(fwd0), timed_call(bwd0)
     step(resident[0])
     torch.cuda.synchronize()
+    model._fus.layers_fwd, model._fus.layers_bwd = fwd0, bwd0
+    fus_ms = sum(a.elapsed_time(b) for a, b in fus_ev)
     prof, L.gemm_profile = L.gemm_profile, None
     shapes = {}
     for p in prof:
@@ -301,7 +385,15 @@ def run_ours(args):
                      "step_tflops_algorithmic": GFLOP_PER_PAIR * B / ms_step,
                      "step_frac_of_peak": GFLOP_PER_PAIR * B / ms_step / peak},
         "clocks": clk, "losses_last_step": losses,
+        # BASELINE.json's second figure: the 12 fusion layers (fwd + bwd of the 4B-sample pass), CUDA events around the
+        # fusion encoder in one profiled step.  "algorithmic" counts the reference's FLOPs (K/V projection of an image
+        # recomputed for each of its 4 passes); this implementation projects every image once per layer.
+        "fusion_layer": {"ms_per_step": fus_ms, "tflops_algorithmic": FUSION_GFLOP_PER_PAIR * B / fus_ms if fus_ms > 0 else None,
+                         "frac_of_peak": (FUSION_GFLOP_PER_PAIR * B / fus_ms / peak) if fus_ms > 0 else None,
+                         "gflop_per_pair_algorithmic": FUSION_GFLOP_PER_PAIR, "peak": peak},
     }
+    if eager is not None:
+        line["gpu_eager_baseline"] = eager
     if rank == 0:
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(args, quick=True)
@@ -358,7 +450,7 @@ def cpu_baseline(args, quick):
 def run_reference(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    B = 2 if (args.steps + args.warmup) <= 24 else 1
+    B = 2   # same pairs/step as the cpu_baseline leg of the GPU arm (ITC / ITM are degenerate at one pair)
     step = _oracle_step_fn(B)
     for _ in range(max(1, args.warmup)):
         step()
@@ -388,8 +480,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=int(os.environ.get("XFM_BENCH_PAIRS", "96")), help="pairs per GPU (yaml: 96)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-eager", action="store_true", help="skip the gpu_eager_baseline leg (eager PyTorch on the same GPU)")
+    ap.add_argument("--overlap", default="auto", help="accelerator OVERLAP_ALLREDUCE: auto | true | false")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    args.overlap = {"true": True, "false": False}.get(str(args.overlap).lower(), "auto")
     if args.impl == "reference":
         run_reference(args)
     else:

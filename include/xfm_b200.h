@@ -156,7 +156,13 @@ int xfm_layerscale_bwd(const float* dx_out, const void* z_bf16, const float* gam
 int xfm_colsum_bf16(const void* in, int64_t ld, float* out, int M, int N, void* stream);
 int xfm_cast_f32_to_bf16(const float* in, void* out, size_t n, void* stream);
 int xfm_cast_bf16_to_f32(const void* in, float* out, size_t n, void* stream);
-int xfm_scale_by_scalar(void* data, int dtype, const float* scalar, size_t n, void* stream);
+int xfm_scale_by_scalar(const void* in, void* out, int dtype, const float* scalar, size_t n, void* stream); /* out may alias in */
+/* fp32-grade GEMM operands for the bf16 tensor cores: every f32 row [K] becomes a bf16 row [6K] holding the three-term
+ * split x = h + m + l in the block order h,h,m,h,m,l (role 0, left operand) or h,m,h,l,m,h (role 1, right operand), so that
+ * xfm_gemm_bf16 over K' = 6K sums the six products of order <= 2 (relative error ~2^-24).  act: 0 none, 1 tanh first.
+ * Replaces the autocast(enabled=False) fp32 Linear-Tanh-Linear of model_vqkd.py:86-90,154-155 (encode_task_layer) and the
+ * fp32 similarity of xfm.py:696-697. */
+int xfm_split_bf16x3(const float* in_f32, void* out_bf16, int M, int K, int role, int act, void* stream);
 
 /* Stand-alone GELU(erf) forward / backward (xfm.py:115-121 ITM head; xroberta.py:1325-1328 LM head) and the
  * dropout mask re-application used by the backward of the GEMM dropout epilogue (same (seed, row*N+col) stream). */
@@ -237,22 +243,22 @@ int xfm_mim_mse(const float* x, const float* t, const uint8_t* mask, int B, int 
                 float* loss, float* dx, void* stream);
 
 /* Flat-buffer optimizer step (accelerators/ddp_accelerator.py:89-98 clip_grad_norm_ + optimizer.step with the
- * transformers AdamW of optim.py:4-50).  P/G/M/V: f32 buffers of nchunks*64 elements, S: bf16 shadow (may be null);
- * chunk_group[nchunks]: hyper-parameter group 0..3 of each 64-element chunk, 255 = skip (frozen or no gradient).
- * xfm_grad_sumsq: *out = sum of g^2 over non-skipped chunks.  xfm_adamw_flat: if sumsq != null the gradient is
- * scaled by grad_mul and clipped to max_grad_norm (total norm written to *norm_out when non-null). */
-typedef struct xfm_adamw_params {
-  float lr[4];
-  float weight_decay[4];
-  float beta1, beta2, eps;
-  float max_grad_norm; /* <= 0: no clipping */
-  float grad_mul;      /* gradient pre-scale (1/world_size for DDP averaging) */
-  int32_t step;        /* 1-based */
-  int32_t correct_bias;
-} xfm_adamw_params;
-int xfm_grad_sumsq(const float* g, const uint8_t* chunk_group, size_t nchunks, float* out, void* stream);
-int xfm_adamw_flat(float* P, const float* G, float* M, float* V, void* S_bf16, const uint8_t* chunk_group, size_t nchunks,
-                   const float* sumsq, float* norm_out, const xfm_adamw_params* hp, void* stream);
+ * transformers AdamW of optim.py:4-50).  P/G/M/V: f32 buffers of nchunks*64 elements, S: bf16 shadow (may be null).
+ *   chunk_seg[nchunks] int32  static: parameter segment of every 64-element chunk, -1 = frozen / padding (never touched)
+ *   seg_group[nseg]    uint8  per step: hyper-parameter group 0..3 of the segment ({decay, no-decay} x {lr, lr*mult},
+ *                             optim.py:10-46), 255 = no gradient since the last zero_grad (skipped like a None grad)
+ *   seg_step[nseg]     int32  device-resident per-parameter step counters (AdamW's state['step']), advanced by
+ *                             xfm_grad_sumsq for every live segment
+ *   seg_bc[nseg]       float2 bias corrections (1 - beta1^t, 1 - beta2^t) written by xfm_grad_sumsq, read by the update
+ *   hp                 16 f32 in DEVICE memory: lr[4] | weight_decay[4] | beta1 beta2 eps max_grad_norm | grad_mul
+ *                             correct_bias 0 0   (max_grad_norm <= 0: no clipping; grad_mul = 1/world for DDP averaging)
+ * xfm_grad_sumsq: *out (+)= sum of g^2 over live chunks (deterministic order).  xfm_adamw_flat: if sumsq != null the
+ * gradient is scaled by grad_mul and clipped to max_grad_norm (total norm written to *norm_out when non-null). */
+int xfm_grad_sumsq(const float* g, const int32_t* chunk_seg, const uint8_t* seg_group, size_t nchunks, int32_t* seg_step,
+                   float* seg_bc, int nseg, const float* hp, float* out, int accumulate, void* stream);
+int xfm_adamw_flat(float* P, const float* G, float* M, float* V, void* S_bf16, const int32_t* chunk_seg,
+                   const uint8_t* seg_group, const float* seg_bc, size_t nchunks, const float* sumsq, float* norm_out,
+                   const float* hp, void* stream);
 
 #ifdef __cplusplus
 }

@@ -91,6 +91,17 @@ def install():
     _mod("timm.data.constants", IMAGENET_DEFAULT_MEAN=(0.485, 0.456, 0.406), IMAGENET_DEFAULT_STD=(0.229, 0.224, 0.225),
          IMAGENET_INCEPTION_MEAN=(0.5, 0.5, 0.5), IMAGENET_INCEPTION_STD=(0.5, 0.5, 0.5))
     _mod("ftfy", fix_text=lambda s: s)
+    import scipy.interpolate as _si
+
+    # scipy >= 1.14 turned interp2d into a stub that raises (the reference's beit2.py:640 calls it).  On a rectilinear grid
+    # interp2d(x, y, z, kind='cubic') is FITPACK regrid_smth with s=0 = RectBivariateSpline(y, x, z, kx=3, ky=3, s=0)
+    # (scipy's interp2d migration guide).
+    def interp2d(x, y, z, kind="cubic"):
+        assert kind == "cubic"
+        f = _si.RectBivariateSpline(y, x, z, kx=3, ky=3, s=0)
+        return lambda xn, yn: f(yn, xn)
+
+    _si.interp2d = interp2d
     sys.path.insert(0, REF_ROOT)
     import torch.distributed as dist
 
@@ -115,9 +126,11 @@ def roberta_config_dir(cfg):
     return d
 
 
-def build_reference_xfm(cfg, sd_full):
+def build_reference_xfm(cfg, sd_full, load_vision_params=False, load_text_params=False, vision_ckpt="", text_dir=None):
     """Build the reference's `models.model_pretrain.XFM` with dims from `cfg` and load `sd_full`
-    (reference key layout, see oracle.xfm_oracle.expand_tied)."""
+    (reference key layout, see oracle.xfm_oracle.expand_tied).  With sd_full None the model is returned as constructed;
+    load_*_params / vision_ckpt / text_dir exercise the reference's constructor-time checkpoint import
+    (models/xfm.py:205-256,298-385)."""
     install()
     import yaml
 
@@ -125,11 +138,11 @@ def build_reference_xfm(cfg, sd_full):
     os.chdir(REF_ROOT)
     try:
         config = yaml.safe_load(open("configs/xfm-pt/Pretrain_XBrain_base_4m.yaml"))
-        config["text_encoder"] = roberta_config_dir(cfg)
+        config["text_encoder"] = text_dir or roberta_config_dir(cfg)
         config["image_res"] = cfg["image_res"]
         vdir = tempfile.mkdtemp(prefix="beit2-base-")
         with open(os.path.join(vdir, "config_beit2_base.json"), "w") as f:
-            json.dump(dict(ckpt="", vision_width=cfg["vision_width"], patch_size=cfg["patch_size"]), f)
+            json.dump(dict(ckpt=vision_ckpt, vision_width=cfg["vision_width"], patch_size=cfg["patch_size"]), f)
         config["vision_config"] = os.path.join(vdir, "config_beit2_base.json")
         config["patch_size"] = cfg["patch_size"]
         config["text_num_hidden_layers"] = cfg["text_layers"]
@@ -188,12 +201,14 @@ def build_reference_xfm(cfg, sd_full):
         try:
             from models.model_pretrain import XFM
 
-            model = XFM(config, load_vision_params=False, load_text_params=False)
+            model = XFM(config, load_vision_params=load_vision_params, load_text_params=load_text_params)
         finally:
             beit2.beit_base_patch16 = orig_factory
             model_vqkd.get_model_default_params = orig_defaults
     finally:
         os.chdir(cwd)
+    if sd_full is None:
+        return model
     own = model.state_dict()
     load = {k: v for k, v in sd_full.items() if not k.startswith("vqkd.")}
     missing = [k for k in own if k not in load and not k.startswith("vqkd.")]

@@ -567,7 +567,7 @@ def contrastive_loss(image_feat_all, text_feat_all, temp, idx_all=None):
     logits = image_feat_all @ text_feat_all.t() / temp
     n = logits.shape[0]
     if idx_all is None:
-        labels = torch.arange(n)
+        labels = torch.arange(n, device=logits.device)
         li = F.cross_entropy(logits, labels)
         lt = F.cross_entropy(logits.t(), labels)
     else:
@@ -619,7 +619,7 @@ def matching_loss(image_embeds, image_atts, text_embeds, text_atts, image_neg_id
     cross_pos = fusion_forward(det(text_embeds), text_atts, image_embeds, image_atts, sd, cfg, collect=collect)[:, 0]
     cross_neg = fusion_forward(det(te_all), ta_all, ie_all, ia_all, sd, cfg)[:, 0]
     out = itm_head(torch.cat([cross_pos, cross_neg], 0), sd)
-    labels = torch.cat([torch.ones(bs, dtype=torch.long), torch.zeros(2 * bs, dtype=torch.long)])
+    labels = torch.cat([torch.ones(bs, dtype=torch.long), torch.zeros(2 * bs, dtype=torch.long)]).to(out.device)
     return F.cross_entropy(out, labels), cross_pos
 
 
@@ -822,7 +822,7 @@ def pretrain_forward(sd, cfg, batch, image_neg_idx, text_neg_idx, ids_mask=None,
     c["vision"], c["text"], c["fusion_pos"], c["vision_masked"] = [], [], [], []
     image = batch["image"]
     image_embeds = vision_forward(image, sd, cfg, collect=c["vision"])
-    image_atts = torch.ones(image_embeds.shape[:-1], dtype=torch.long)
+    image_atts = torch.ones(image_embeds.shape[:-1], dtype=torch.long, device=image_embeds.device)
     text_embeds = text_forward(batch["text_ids"], batch["text_atts"], sd, cfg, collect=c["text"])
     image_feat, text_feat = get_features(image_embeds, text_embeds, sd)
     c["image_embeds"], c["text_embeds"], c["image_feat"], c["text_feat"] = image_embeds, text_embeds, image_feat, text_feat

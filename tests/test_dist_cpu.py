@@ -3,8 +3,10 @@
   * XFMBase._gather_world == the reference's AllGather (models/xfm.py:81-101): rank-ordered features, local offset;
     the loss every rank computes on the gathered features equals the single-process big-batch loss, and the local
     gradient slice equals the big-batch gradient rows (the reference keeps only that slice, xfm.py:93-98);
-  * B200DDPAccelerator.all_reduce_grads: bucketed SUM all-reduce of the flat gradient buffer (averaging is the optimizer
-    kernel's grad_mul = 1/W, i.e. DDP's mean).
+  * B200DDPAccelerator on a real tiny model: flat broadcast at set_up; bucketed SUM all-reduce of the flat gradient buffer
+    (averaging is the optimizer kernel's grad_mul = 1/W, i.e. DDP's mean) — plain, overlapped range by range, and with a
+    second backward pass arriving after an early reduction (exact through the stash); "auto" overlap; the live-parameter
+    table agreed over ranks.
 
 The arithmetic checker is the oracle (test infrastructure); the CUDA kernels are not involved here.
 """
@@ -63,35 +65,70 @@ def _worker(rank, world, port, q):
             res[use_idx] = (float(loss) - float(big), float((ia.grad[sl] - a.grad[sl]).abs().max()),
                             float((ta.grad[sl] - b.grad[sl]).abs().max()))
 
-        # ---- gradient all-reduce of the trainable part of a flat buffer in buckets (frozen tail untouched)
-        from collections import OrderedDict
+        # ---- gradient exchange of the accelerator on a real (tiny) model: plain, overlapped per range, and with a second
+        # backward pass arriving after ranges were reduced early (Pretrain.py:218-243 accumulates several per step)
+        from xfm_b200.accelerator import FlatAdamW
+        from xfm_b200.model_pretrain import XFM
+        cfg = O.tiny_config(use_vision_tokenizer=True)
+        model = XFM(dict(cfg), init=lambda n, s: O.make_tensor(n, s, rank), device="cpu")   # rank-dependent init ...
+        opt = FlatAdamW(model, lr=1e-4)
+        acc = B200DDPAccelerator(dict(CLIP_GRAD_NORM=1.0, ALLREDUCE_BUCKETS=3, OVERLAP_ALLREDUCE=True))
+        ref_P = XFM(dict(cfg), init=lambda n, s: O.make_tensor(n, s, 0), device="cpu").flat.P
+        acc.set_up(model, opt, None, 0, world, rank)
+        res["broadcast"] = float((model.flat.P - ref_P).abs().max())                           # ... equal after set_up
+        G, n = model.flat.G, model.flat.G.numel()
+        te = acc._train_end
+        assert 0 < te < n and len(acc._blocks) == cfg["vision_depth"] and acc._vis[0] < acc._blocks[0][0]
+        base = torch.arange(n, dtype=torch.float32) % 1000
+        tot = sum(r + 1 for r in range(world))
 
-        from xfm_b200.params import Segment
+        def frozen_ok():
+            return float((G[te:] - base[te:] * (rank + 1)).abs().max())
 
-        class Flat:
-            pass
-
-        class Model:
-            pass
-
-        m = Model()
-        m.flat = Flat()
-        n = 64 * 37 + 64
-        segs = OrderedDict()
-        segs["temp"] = Segment("temp", (), 0, 1, True)
-        segs["vision_encoder.a"] = Segment("vision_encoder.a", (64 * 10,), 64, 64 * 10, True)
-        segs["text_encoder.b"] = Segment("text_encoder.b", (64 * 25 + 3,), 64 * 11, 64 * 25 + 3, True)
-        segs["vqkd.frozen"] = Segment("vqkd.frozen", (64,), 64 * 37, 64, False)
-        m.flat.segments = segs
-        m.flat.G = torch.arange(n, dtype=torch.float32) * (rank + 1)
-        acc = B200DDPAccelerator(dict(CLIP_GRAD_NORM=1.0, ALLREDUCE_BUCKETS=4))
-        acc.world, acc.rank = world, rank
-        acc._layout(m)
-        assert acc._train_end == 64 * 37 and acc._vis == (64, 64 * 11)
-        acc.all_reduce_grads(m)
-        want = torch.arange(n, dtype=torch.float32) * sum(r + 1 for r in range(world))
-        want[64 * 37:] = torch.arange(64 * 37, n, dtype=torch.float32) * (rank + 1)   # frozen segment: not reduced
-        res["allreduce"] = float((m.flat.G - want).abs().max())
+        # (A) no overlap
+        G.copy_(base * (rank + 1))
+        acc._on_backward_begin()
+        acc.all_reduce_grads(model)
+        res["plain"] = float((G[:te] - base[:te] * tot).abs().max()) + frozen_ok()
+        # (B) overlapped: non-vision ranges at the last node, vision blocks as they finish, tail at optimizer_step
+        G.copy_(base * (rank + 1))
+        acc._on_backward_begin()
+        cb = acc._on_last_node()
+        for i in reversed(range(len(acc._blocks))):
+            cb(i)
+        v0 = acc._vis[0]
+        b0 = acc._blocks[0][0]
+        res["early_done"] = float((G[:v0] - base[:v0] * tot).abs().max())                      # already summed
+        res["tail_pending"] = float((G[v0:b0] - base[v0:b0] * (rank + 1)).abs().max())         # cls / patch embedding: not yet
+        acc.all_reduce_grads(model)
+        res["overlap"] = float((G[:te] - base[:te] * tot).abs().max()) + frozen_ok()
+        # (C) a second backward pass after the early reduction: reduced values are stashed, the result stays exact
+        G.copy_(base * (rank + 1))
+        acc._on_backward_begin()
+        cb = acc._on_last_node()
+        for i in reversed(range(len(acc._blocks))):
+            cb(i)
+        acc._on_backward_begin()                      # backward #2 begins
+        G[:te] += 0.5 * base[:te] * (rank + 2)        # ... and accumulates local gradients
+        cb = acc._on_last_node()
+        cb(len(acc._blocks) - 1)                      # only one block reduced early this time
+        acc.all_reduce_grads(model)
+        want = base[:te] * tot + 0.5 * base[:te] * sum(r + 2 for r in range(world))
+        res["stash"] = float((G[:te] - want).abs().max()) + frozen_ok()
+        # (D) "auto": learns the number of backward passes per optimizer step; the first step is never overlapped
+        auto = B200DDPAccelerator(dict(CLIP_GRAD_NORM=1.0))
+        auto.set_up(model, opt, None, 0, world, rank)
+        seen = []
+        for step in range(3):
+            for k in range(2):
+                auto._on_backward_begin()
+                seen.append(auto._on_last_node() is not None)
+            auto.all_reduce_grads(model)
+            auto._bw_per_step, auto._bw_seen = auto._bw_seen, 0
+        res["auto"] = seen
+        # (E) the live-parameter table is agreed over ranks (a parameter is updated if ANY rank has a gradient for it)
+        t = torch.tensor([0, 255, 3, 255] if rank == 0 else [255, 255, 3, 1], dtype=torch.uint8)
+        res["live"] = acc._sync_live(t).tolist()
         q.put((rank, res, None))
         dist.barrier()
         dist.destroy_process_group()
@@ -117,4 +154,7 @@ def test_two_rank_gather_and_allreduce():
         for use_idx in (False, True):
             dl, di, dt = res[use_idx]
             assert abs(dl) < 1e-6 and di < 1e-6 and dt < 1e-6, (rank, use_idx, res[use_idx])
-        assert res["allreduce"] == 0.0
+        for k in ("broadcast", "plain", "early_done", "tail_pending", "overlap", "stash"):
+            assert res[k] == 0.0, (rank, k, res[k])
+        assert res["auto"] == [False, False, False, True, False, True], res["auto"]
+        assert res["live"] == [0, 255, 3, 1]

@@ -124,3 +124,53 @@ def test_vq_argmin_full_size_matches_fp64_argmin(lib):
         gap = (d[mism, ids[mism]] - d[mism, best[mism]]).abs()
         assert float(gap.max()) < 1e-6
     assert float(mism.float().mean()) < 1e-3
+
+
+def test_split_precision_gemm_is_fp32_grade(lib):
+    """encode_task_layer at full size (model_vqkd.py:86-90,154-155: fp32 Linear-Tanh-Linear on 96 x 197 tokens): the three-term
+    bf16 operand split + one K' = 6K tcgen05 GEMM against an fp64 matmul — fp32-grade error, ~3 decades below plain bf16."""
+    g = G(5)
+    x = torch.randn(M, D, device="cuda", generator=g)
+    w = torch.randn(D, D, device="cuda", generator=g) * 0.04
+    b = torch.randn(D, device="cuda", generator=g) * 0.1
+    ref = x.double() @ w.double().t() + b.double()
+    y = lib.gemm(lib.split_bf16x3(x, 0), lib.split_bf16x3(w, 1), bias=b, out_dtype=torch.float32)
+    err = float((y.double() - ref).abs().max() / ref.abs().max())
+    y16 = lib.gemm(x.bfloat16(), w.bfloat16(), bias=b, out_dtype=torch.float32)
+    err16 = float((y16.double() - ref).abs().max() / ref.abs().max())
+    f32 = float(((x @ w.t() + b).double() - ref).abs().max() / ref.abs().max())   # torch fp32 (TF32 off by default)
+    assert err <= 2e-6 and err16 > 100 * err, (err, err16, f32)
+    # tanh on the way in (second Linear of the task layer, N = 32 codes dims)
+    w2 = torch.randn(32, D, device="cuda", generator=g) * 0.04
+    z = lib.gemm(lib.split_bf16x3(y, 0, act=1), lib.split_bf16x3(w2, 1), out_dtype=torch.float32)
+    ref2 = torch.tanh(y.double()) @ w2.double().t()
+    assert float((z.double() - ref2).abs().max() / ref2.abs().max()) <= 3e-6
+
+
+def test_vq_ids_at_bench_size_against_oracle(record):
+    """BASELINE configs[1] tokenizer at 96 images / GPU, XFM-base widths: get_codebook_indices against the CPU oracle
+    (models/model_vqkd.py:173-175).  Records the exact-match rate and the largest fp64 margin among differing ids."""
+    from oracle import xfm_oracle as O
+    from xfm_b200.xfm import XFMBase
+    cfg = O.base_config(use_vision_tokenizer=True, vision_depth=12, text_layers=1, fusion_layers=1, use_bbox=False)
+    model = XFMBase(dict(cfg), init=lambda n, s: O.make_tensor(n, s, 0), device="cuda").eval()
+    image = O.make_batch(cfg, B, L=40, M=15, seed=1, image_uniform=True)["image"]
+    with torch.no_grad():
+        ids = model.get_codebook_indices(image.cuda()).cpu()
+    sd = {k: O.make_tensor(k, s, 0) for k, s in O.vqkd_param_shapes(cfg).items()}
+    with torch.no_grad():
+        z = O.vqkd_features(O.vqkd_preprocess(image), sd, cfg)
+    zf = torch.nn.functional.normalize(z.permute(0, 2, 3, 1), dim=-1).reshape(-1, cfg["codebook_dim"])
+    cb = sd["vqkd.quantize.embedding.weight"]
+    want, gaps = [], []
+    for i in range(0, zf.shape[0], 2048):
+        want.append(torch.argmin(O.quantizer_distances(zf[i:i + 2048], cb), dim=1))
+        top2 = torch.topk(O.quantizer_distances(zf[i:i + 2048].double(), cb.double()), 2, dim=1, largest=False).values
+        gaps.append(top2[:, 1] - top2[:, 0])
+    want, gap = torch.cat(want).view(B, -1), torch.cat(gaps).view(B, -1)
+    match = ids == want
+    worst = float(gap[~match].max()) if (~match).any() else 0.0
+    record("vq_ids_b96", n=int(want.numel()), match=float(match.float().mean()), worst_missed_margin=worst,
+           distinct_codes=int(want.unique().numel()),
+           **{f"margin>{t}": float(match[gap > t].float().mean()) for t in (1e-3, 1e-2, 3e-2)})
+    assert worst <= 3e-2 and float(match.float().mean()) >= 0.93

@@ -103,18 +103,46 @@ def test_tiny_features_weights_and_vq_ids(golden_dir):
     assert _maxabs(ie, g["image_embeds"]) <= 2e-2 and _maxabs(te, g["text_embeds"]) <= 2e-2
     assert _maxabs(fi, g["image_feat"]) <= 5e-3 and _maxabs(ft, g["text_feat"]) <= 5e-3
     assert _maxabs(w_i2t, g["weights_i2t"]) <= 2e-2 and _maxabs(w_t2i, g["weights_t2i"]) <= 2e-2
-    # VQ ids: the quantizer itself is bit-exact on identical z (test_kernels_gpu.py::test_vq_argmin_bit_exact); end to
-    # end the bf16 tokenizer encoder perturbs z, so only rows whose fp64 margin exceeds that perturbation must agree.
-    sd = O.make_state_dict(cfg, 0)
-    img = O.make_batch(cfg, g["B"], L=g["L"], M=g["M"], seed=1, image_uniform=True)["image"]
-    z = O.vqkd_features(O.vqkd_preprocess(img), sd, cfg)
-    zf = torch.nn.functional.normalize(z.permute(0, 2, 3, 1), dim=-1).reshape(-1, cfg["codebook_dim"]).double()
-    d = O.quantizer_distances(zf, sd["vqkd.quantize.embedding.weight"].double())
-    top2 = torch.topk(d, 2, dim=1, largest=False).values
-    safe = ((top2[:, 1] - top2[:, 0]) > 0.05).view(g["vq_ids"].shape)
     assert ids.dtype == torch.int64 and ids.shape == g["vq_ids"].shape
-    assert torch.equal(ids.cpu()[safe], g["vq_ids"][safe])
-    assert float((ids.cpu() == g["vq_ids"]).float().mean()) > 0.9
+
+
+def _vq_margins(cfg, B, L, M):
+    """fp64 gap between the best and second-best codebook distance of every patch, from the oracle's fp32 z."""
+    sd = O.make_state_dict(cfg, 0)
+    img = O.make_batch(cfg, B, L=L, M=M, seed=1, image_uniform=True)["image"]
+    with torch.no_grad():
+        z = O.vqkd_features(O.vqkd_preprocess(img), sd, cfg)
+    zf = torch.nn.functional.normalize(z.permute(0, 2, 3, 1), dim=-1).reshape(-1, cfg["codebook_dim"]).double()
+    cb = sd["vqkd.quantize.embedding.weight"].double()
+    gaps = []
+    for i in range(0, zf.shape[0], 4096):
+        top2 = torch.topk(O.quantizer_distances(zf[i:i + 4096], cb), 2, dim=1, largest=False).values
+        gaps.append(top2[:, 1] - top2[:, 0])
+    return torch.cat(gaps)
+
+
+@pytest.mark.parametrize("name", ["tiny_vq.pt", "base_vq.pt"])
+def test_vq_ids_end_to_end_against_reference(golden_dir, record, name):
+    """VQKD.get_codebook_indices (model_vqkd.py:173-175) end to end against the ids the UNMODIFIED reference produced.
+    The quantizer is bit-exact on identical z (test_kernels_gpu.py::test_vq_argmin_bit_exact) and encode_task_layer runs at
+    fp32-grade precision like the reference (model_vqkd.py:154-155); what is left is the bf16 tokenizer ViT (the reference's
+    own GPU path runs it under fp16 autocast, xfm.py:627): its perturbation of z (~1e-2) can flip an argmin whose fp64 margin
+    is below that.  Every id whose margin exceeds the perturbation must match; the match rate is recorded."""
+    g = _load(golden_dir, name)
+    model, cfg = _build(g)
+    batch = _batch(g, cfg)
+    with torch.no_grad():
+        ids = model.get_codebook_indices(batch["image"]).cpu()
+    want = g["vq_ids"]
+    assert ids.shape == want.shape
+    gap = _vq_margins(cfg, g["B"], g["L"], g["M"]).view(want.shape)
+    match = ids == want
+    rates = {f"margin>{t}": float(match[gap > t].float().mean()) for t in (0.0, 1e-3, 1e-2, 3e-2)}
+    worst_missed = float(gap[~match].max()) if (~match).any() else 0.0
+    record("vq_ids", fixture=name, n=int(want.numel()), match=float(match.float().mean()), worst_missed_margin=worst_missed,
+           **rates)
+    assert worst_missed <= 3e-2, worst_missed          # no id with a margin above the bf16 perturbation differs
+    assert float(match.float().mean()) >= 0.93
 
 
 def test_mim_masks_bit_exact_through_the_module(golden_dir):
@@ -253,6 +281,42 @@ def _grad_check(model, ref_grads, names, tol=6e-2):
         mine, ref = params[n].grad, ref_grads[n]
         assert mine is not None, n
         assert _maxabs(mine, ref) <= tol * max(float(ref.abs().max()), 1e-8), n
+
+
+def test_text_only_mlm_stream_against_oracle(record):
+    """XFMBase.get_mlm_loss / XFM.forward_text (xfm.py:805-812, model_pretrain.py:93-98): the text-only stream — text encoder
+    on the masked ids, LM head on the gathered positions, CE(ignore -100) — loss and gradients, no image involved."""
+    from xfm_b200.model_pretrain import XFM
+    cfg = O.tiny_config()
+    B, Lt, Mm = 5, 24, 6
+    sd = O.make_state_dict(cfg, 0)
+    for v in sd.values():
+        if v.dtype.is_floating_point:
+            v.requires_grad_(True)
+    batch = O.make_batch(cfg, B, L=Lt, M=Mm, seed=21)
+    ref = O.text_mlm_loss(batch["text_ids_masked"], batch["text_atts"], batch["masked_pos"], batch["masked_ids"], sd, cfg)
+    ref.backward()
+    model = XFM(dict(cfg), init=lambda n, s: O.make_tensor(n, s, 0), device="cuda").eval()
+    b = {k: v.cuda() for k, v in batch.items()}
+    out = model(None, b["text_ids"], b["text_atts"], text_ids_masked=b["text_ids_masked"], masked_pos=b["masked_pos"],
+                masked_ids=b["masked_ids"])
+    assert set(out) == {"loss_mlm"}
+    rel = abs(float(out["loss_mlm"]) - float(ref)) / max(1.0, abs(float(ref)))
+    record("text_mlm", mine=float(out["loss_mlm"]), oracle=float(ref), rel=rel)
+    assert rel <= 1e-3, (float(out["loss_mlm"]), float(ref))
+    direct = model.get_mlm_loss(b["text_ids_masked"], b["text_atts"], None, None, b["masked_pos"], b["masked_ids"])
+    assert abs(float(direct) - float(out["loss_mlm"])) < 1e-6
+    out["loss_mlm"].backward()
+    grads = {k: v.grad for k, v in sd.items() if v.dtype.is_floating_point and v.grad is not None}
+    _grad_check(model, grads, ["text_encoder.lm_head.dense.weight", "text_encoder.lm_head.layer_norm.weight",
+                               "text_encoder.lm_head.bias", "text_encoder.roberta.embeddings.word_embeddings.weight",
+                               "text_encoder.roberta.encoder.layer.1.attention.self.query.weight",
+                               "text_encoder.roberta.encoder.layer.0.output.dense.weight",
+                               "text_encoder.roberta.embeddings.position_embeddings.weight"])
+    params = dict(model.named_parameters())
+    for n in ("vision_encoder.blocks.0.mlp.fc1.weight", "fusion_encoder.roberta.encoder.layer.0.output.dense.weight",
+              "itm_head.0.weight"):
+        assert params[n].grad is None, n     # nothing outside the text encoder takes part (xfm.py:805-812)
 
 
 def test_retrieval_model_against_oracle():

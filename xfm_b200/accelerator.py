@@ -42,80 +42,168 @@ NO_DECAY = ("bias", "LayerNorm.bias", "LayerNorm.weight", "norm.bias", "norm.wei
             "norm2.bias", "norm2.weight")  # optim.py:17-25
 
 
-class FlatAdamW:
-    """optim.py:4-50 (4 parameter groups: {decay, no-decay} x {lr, lr * lr_mult}) over the flat parameter buffer.
-    Exposes `param_groups` with an 'lr' entry per group so scheduler.py's LambdaLR-style schedulers can drive it."""
+def param_group_index(name, init_params):
+    """optim.py:31-46: {decay, no-decay} x {lr, lr * lr_mult}; the no-decay rule is a substring test on the name."""
+    return (1 if any(nd in name for nd in NO_DECAY) else 0) + (2 if name in init_params else 0)
+
+
+class _Buffer:
+    """Optimizer-side view of one FlatParams buffer: static chunk -> segment table, per-segment groups / step counters."""
+
+    def __init__(self, fp, group_of):
+        dev = fp.P.device
+        self.fp = fp
+        self.names = [n for n in fp.segments if n in group_of]
+        self.index = {n: i for i, n in enumerate(self.names)}
+        self.static_group = [group_of[n] for n in self.names]
+        nseg = max(len(self.names), 1)
+        host = torch.full((fp.P.numel() // 64,), -1, dtype=torch.int32)
+        for i, n in enumerate(self.names):
+            sg = fp.segments[n]
+            host[sg.offset // 64:(sg.offset + sg.numel + 63) // 64] = i
+        self.chunk_seg = host.to(dev)
+        self.seg_step = torch.zeros(nseg, dtype=torch.int32, device=dev)
+        self.seg_bc = torch.ones((nseg, 2), dtype=torch.float32, device=dev)
+        self.M = torch.zeros_like(fp.P)
+        self.V = torch.zeros_like(fp.P)
+        self._live = {}
+
+    def live_groups(self, always_all=False):
+        """uint8 [nseg] device tensor: group id of every segment that received a gradient since the last zero_grad, 255 for
+        the rest (the reference's optimizer skips grad-None parameters).  Cached per touched-set; never modified in place."""
+        key = None if always_all else frozenset(self.fp.touched)
+        t = self._live.get(key)
+        if t is None:
+            host = torch.tensor([g if (always_all or n in self.fp.touched) else 255
+                                 for n, g in zip(self.names, self.static_group)] or [255], dtype=torch.uint8)
+            if self.fp.P.is_cuda:
+                host = host.pin_memory()
+            t = host.to(self.fp.P.device, non_blocking=True)
+            if len(self._live) > 16:
+                self._live.clear()
+            self._live[key] = t
+        return t
+
+
+class FlatAdamW(torch.optim.Optimizer):
+    """optim.py:4-50 (transformers AdamW, 4 parameter groups: {decay, no-decay} x {lr, lr * lr_mult}) over the flat
+    parameter buffer.  A real torch.optim.Optimizer: `param_groups` hold the model's nn.Parameters (views into the flat
+    buffer) with the reference's group membership, so scheduler.py's LambdaLR drives `param_groups[i]['lr']` unchanged and
+    those values reach the kernel through its device-resident hyper-parameter block.  step() is two kernel launches per
+    buffer (xfm_grad_sumsq, xfm_adamw_flat); AdamW's per-parameter `step` counters live on the device.
+
+    Trainable parameters that a task model created outside the flat buffer (e.g. the reference's own
+    model_nlvr.py:25 `self.cls_head = build_mlp(...)`) are adopted into a second flat buffer first
+    (XFMBase.adopt_stray_parameters), so they are reduced, clipped, updated and zeroed like everything else."""
 
     def __init__(self, model, lr=1e-4, weight_decay=0.01, lr_mult=1.0, betas=(0.9, 0.98), eps=1e-8, correct_bias=True):
-        self.model, self.flat = model, model.flat
-        fp = self.flat
-        self.betas, self.eps, self.correct_bias = betas, eps, correct_bias
+        model = model.module if hasattr(model, "module") and hasattr(model.module, "flat") else model
+        self.model = model
+        model.adopt_stray_parameters()
         large = set(getattr(model, "init_params", []))
-        self.param_groups = [dict(lr=lr, weight_decay=weight_decay, initial_lr=lr, params=[]),
-                             dict(lr=lr, weight_decay=0.0, initial_lr=lr, params=[]),
-                             dict(lr=lr * lr_mult, weight_decay=weight_decay, initial_lr=lr * lr_mult, params=[]),
-                             dict(lr=lr * lr_mult, weight_decay=0.0, initial_lr=lr * lr_mult, params=[])]
-        self.defaults = dict(lr=lr)
+        groups = [dict(params=[], lr=lr, weight_decay=weight_decay), dict(params=[], lr=lr, weight_decay=0.0),
+                  dict(params=[], lr=lr * lr_mult, weight_decay=weight_decay), dict(params=[], lr=lr * lr_mult, weight_decay=0.0)]
         self._group_of = {}
-        for name, seg in fp.segments.items():
-            if not seg.trainable or name.rsplit(".", 1)[-1].startswith("_"):
-                continue
-            gi = (1 if any(nd in name for nd in NO_DECAY) else 0) + (2 if name in large else 0)
-            self._group_of[name] = gi
-        n = fp.P.numel()
-        self.M = torch.zeros(n, dtype=torch.float32, device=fp.P.device)
-        self.V = torch.zeros(n, dtype=torch.float32, device=fp.P.device)
-        self._chunks = {}
+        self._buffers = []
+        for fp, params in model.flat_buffers():
+            gof = {}
+            for name, seg in fp.segments.items():
+                if not seg.trainable or name.rsplit(".", 1)[-1].startswith("_") or name not in params:
+                    continue
+                gof[name] = param_group_index(name, large)
+                groups[gof[name]]["params"].append(params[name])
+            self._group_of.update(gof)
+            self._buffers.append(_Buffer(fp, gof))
+        super().__init__(groups, dict(lr=lr, weight_decay=weight_decay, betas=betas, eps=eps, correct_bias=correct_bias))
+        dev = model.flat.P.device
+        self.sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.norm = torch.zeros(1, dtype=torch.float32, device=dev)
         self.step_count = 0
-        self.sumsq = torch.zeros(1, dtype=torch.float32, device=fp.P.device)
-        self.norm = torch.zeros(1, dtype=torch.float32, device=fp.P.device)
-        self.state = {}
+        self.world_sync = None   # set by the accelerator: callable(uint8 tensor) -> tensor all-reduced with MIN over ranks
 
-    def _chunk_table(self):
-        """uint8 group id per 64-element chunk; 255 for frozen segments and for parameters that received no gradient
-        since the last zero_grad (the reference's optimizers skip grad-None parameters)."""
-        key = frozenset(self.flat.touched)
-        tab = self._chunks.get(key)
-        if tab is None:
-            fp = self.flat
-            host = torch.full((fp.P.numel() // 64,), 255, dtype=torch.uint8)
-            for name, gi in self._group_of.items():
-                if name in fp.touched:
-                    s = fp.segments[name]
-                    host[s.offset // 64:(s.offset + s.numel + 63) // 64] = gi
-            tab = host.to(fp.P.device)
-            self._chunks = {key: tab}
-        return tab
+    @property
+    def flat(self):
+        return self.model.flat
 
-    def step(self, max_grad_norm=0.0, grad_mul=1.0):
+    @property
+    def M(self):
+        return self._buffers[0].M
+
+    @property
+    def V(self):
+        return self._buffers[0].V
+
+    def hparams(self, max_grad_norm, grad_mul):
+        d = self.defaults
+        g = self.param_groups
+        return L.adamw_hparams([x["lr"] for x in g], [x["weight_decay"] for x in g], d["betas"][0], d["betas"][1], d["eps"],
+                               max_grad_norm, grad_mul, d["correct_bias"])
+
+    @torch.no_grad()
+    def step(self, closure=None, max_grad_norm=0.0, grad_mul=1.0):
+        loss = closure() if closure is not None else None
         self.step_count += 1
-        hp = L.AdamWParams()
-        for i, g in enumerate(self.param_groups):
-            hp.lr[i], hp.weight_decay[i] = g["lr"], g["weight_decay"]
-        hp.beta1, hp.beta2, hp.eps = self.betas[0], self.betas[1], self.eps
-        hp.max_grad_norm, hp.grad_mul, hp.step, hp.correct_bias = max_grad_norm, grad_mul, self.step_count, int(self.correct_bias)
-        tab = self._chunk_table()
-        fp = self.flat
-        fresh = fp._shadow_version == fp.P._version
-        L.grad_sumsq(fp.G, tab, self.sumsq)
-        L.adamw_flat(fp.P, fp.G, self.M, self.V, fp.S, tab, hp, sumsq=self.sumsq, norm_out=self.norm)
-        if fresh:
-            fp._shadow_version = fp.P._version  # the kernel refreshed the bf16 shadow of everything it changed
-        return self.norm
+        model = self.model
+        dev = model.flat.P.device
+        hp = self.hparams(max_grad_norm, grad_mul).to(dev, non_blocking=True)
+        model.collect_stray_grads()
+        live = []
+        for i, b in enumerate(self._buffers):
+            t = b.live_groups(always_all=(i > 0))
+            if self.world_sync is not None:   # ranks that touched different parameters must still take the same step
+                t = self.world_sync(t)
+            live.append(t)
+        for i, (b, t) in enumerate(zip(self._buffers, live)):
+            L.grad_sumsq(b.fp.G, b.chunk_seg, t, b.seg_step, b.seg_bc, hp, self.sumsq, accumulate=i > 0)
+        for i, (b, t) in enumerate(zip(self._buffers, live)):
+            fp = b.fp
+            fresh = fp._shadow_version == fp.P._version
+            L.adamw_flat(fp.P, fp.G, b.M, b.V, fp.S, b.chunk_seg, t, b.seg_bc, hp, sumsq=self.sumsq,
+                         norm_out=self.norm if i == 0 else None)
+            if fresh:
+                fp._shadow_version = fp.P._version  # the kernel refreshed the bf16 shadow of everything it changed
+        return self.norm if loss is None else loss
 
     def zero_grad(self, set_to_none=True):
         self.model.zero_grad()
 
+    # ---- checkpoints: torch.optim layout ({'state': {id: {step, exp_avg, exp_avg_sq}}, 'param_groups': [...]}) ----------
     def state_dict(self):
-        return dict(step=self.step_count, M=self.M, V=self.V, param_groups=[{k: v for k, v in g.items() if k != "params"}
-                                                                            for g in self.param_groups])
+        ids, pid = {}, 0
+        groups = []
+        for g in self.param_groups:
+            d = {k: v for k, v in g.items() if k != "params"}
+            d["params"] = list(range(pid, pid + len(g["params"])))
+            for p in g["params"]:
+                ids[id(p)] = pid
+                pid += 1
+            groups.append(d)
+        state = {}
+        for b, (fp, params) in zip(self._buffers, self.model.flat_buffers()):
+            steps = b.seg_step.cpu()
+            for n, i in b.index.items():
+                if int(steps[i]) > 0:
+                    state[ids[id(params[n])]] = dict(step=int(steps[i]), exp_avg=fp._view(b.M, n).clone(),
+                                                     exp_avg_sq=fp._view(b.V, n).clone())
+        return dict(state=state, param_groups=groups)
 
     def load_state_dict(self, sd):
-        self.step_count = sd["step"]
-        self.M.copy_(sd["M"])
-        self.V.copy_(sd["V"])
+        order = [p for g in self.param_groups for p in g["params"]]
+        where = {}
+        for b, (fp, params) in zip(self._buffers, self.model.flat_buffers()):
+            for n in b.names:
+                where[id(params[n])] = (b, fp, n)
         for g, s in zip(self.param_groups, sd["param_groups"]):
-            g.update(s)
+            g.update({k: v for k, v in s.items() if k != "params"})
+        for b in self._buffers:
+            b.seg_step.zero_()
+            b.M.zero_()
+            b.V.zero_()
+        for pid, st in sd["state"].items():
+            b, fp, n = where[id(order[int(pid)])]
+            fp._view(b.M, n).copy_(st["exp_avg"])
+            fp._view(b.V, n).copy_(st["exp_avg_sq"])
+            b.seg_step[b.index[n]] = int(st["step"])
 
 
 class _Cfg:
@@ -135,6 +223,15 @@ class _Wrapped(torch.nn.Module):
 
 
 class B200DDPAccelerator:
+    """OVERLAP_ALLREDUCE: "auto" (default) | true | false.  Overlap = while the LAST autograd node of a backward pass (the first
+    vision pass) runs, the finished ranges of the flat gradient buffer are all-reduced on a side stream: everything but
+    the vision encoder at the start of that node, then every vision block as soon as its backward is done (reverse
+    order), so only the patch-embedding tail (~3 MB) is left for optimizer_step.  With gradient accumulation (Pretrain.py
+    runs up to 5 backward passes per optimizer step, Pretrain.py:218-243) only the last backward of a step may reduce:
+    "auto" learns the number of backward passes per optimizer step from the previous step.  If a backward pass does begin
+    after ranges were reduced early, the reduced values are stashed and the ranges restart from zero, so the result stays
+    exact (one extra copy, only on a change of the accumulation pattern)."""
+
     def __init__(self, cfg, logger=None):
         self.cfg = cfg if hasattr(cfg, "CLIP_GRAD_NORM") or not isinstance(cfg, dict) else _Cfg(cfg)
         if not hasattr(self.cfg, "AUTO_CAST"):
@@ -142,44 +239,84 @@ class B200DDPAccelerator:
         self.clip = float(getattr(self.cfg, "CLIP_GRAD_NORM", 0.0) or 0.0)
         self.world, self.rank = 1, 0
         self.buckets = int(getattr(self.cfg, "ALLREDUCE_BUCKETS", 4))
-        self.overlap = bool(getattr(self.cfg, "OVERLAP_ALLREDUCE", True))
+        ov = getattr(self.cfg, "OVERLAP_ALLREDUCE", "auto")
+        self.overlap = "auto" if str(ov).lower() == "auto" else bool(ov)
         self._comm_stream = None
-        self._early = None
+        self._comm_done = None
+        self._early = []      # ranges of flat.G already summed over ranks in this optimizer step
+        self._stash = []      # (a, b, tensor): reduced values set aside because another backward pass followed
         self._vis = None
+        self._blocks = []
+        self._bw_seen = 0
+        self._bw_per_step = None
+        self._model = None
 
     def set_up(self, model, optimizer, lr_scheduler, local_rank=0, world_size=1, rank=0):
         self.world, self.rank = world_size, rank
+        self._model = model
         self._layout(model)
+        model._backward_begin_hook = self._on_backward_begin
         if world_size > 1:
-            assert dist.is_initialized(), "init torch.distributed (nccl) before set_up"
-            flat = model.flat
-            dist.broadcast(flat.P, src=0)  # one flat broadcast replaces ~750 per-tensor ones (ddp_accelerator.py:69-74)
-            flat.sync_shadow(force=True)
-            if self.overlap and self._vis is not None and flat.G.is_cuda:
-                self._model = model
-                self._comm_stream = torch.cuda.Stream(device=flat.G.device)
-                model._last_node_hook = self._early_reduce
+            assert dist.is_initialized(), "init torch.distributed before set_up"
+            for fp, _ in model.flat_buffers():
+                dist.broadcast(fp.P, src=0)  # one flat broadcast replaces ~750 per-tensor ones (ddp_accelerator.py:69-74)
+                fp.sync_shadow(force=True)
+            if optimizer is not None and hasattr(optimizer, "world_sync"):
+                optimizer.world_sync = self._sync_live
+            if self.overlap and self._vis is not None:
+                if model.flat.G.is_cuda:
+                    self._comm_stream = torch.cuda.Stream(device=model.flat.G.device)
+                model._last_node_hook = self._on_last_node
         return _Wrapped(model), optimizer, lr_scheduler
 
     def _layout(self, model):
         """Ranges of the flat gradient buffer: [0, train_end) holds every trainable segment (the frozen VQ-KD tokenizer sits
-        behind it and is never reduced); [v0, v1) is the vision encoder, whose gradients are the last ones produced."""
+        behind it and is never reduced); [v0, v1) is the vision encoder, whose gradients are the last ones produced, and
+        _blocks[i] the range of vision block i."""
         segs = model.flat.segments
         al = lambda n: (n + 63) // 64 * 64
         self._train_end = max([s.offset + al(s.numel) for s in segs.values() if s.trainable] or [0])
         vis = [s for s in segs.values() if s.name.startswith("vision_encoder.")]
-        self._vis = None
+        self._vis, self._blocks = None, []
         if vis:
             v0, v1 = min(s.offset for s in vis), max(s.offset + al(s.numel) for s in vis)
             inside = [s for s in segs.values() if v0 <= s.offset < v1]
             if len(inside) == len(vis):   # contiguous
                 self._vis = (v0, v1)
+                i = 0
+                while True:
+                    blk = [s for s in vis if s.name.startswith(f"vision_encoder.blocks.{i}.")]
+                    if not blk:
+                        break
+                    self._blocks.append((min(s.offset for s in blk), max(s.offset + al(s.numel) for s in blk)))
+                    i += 1
+
+    def _sync_live(self, t):
+        """Per-segment live/group table agreed over ranks: a parameter is updated if ANY rank produced a gradient for it."""
+        t = t.clone()
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return t
+
+    # ------------------------------------------------------------------ backward bookkeeping
+    def _on_backward_begin(self):
+        """First autograd node of a backward pass (called by the model; covers direct loss.backward() calls too)."""
+        self._bw_seen += 1
+        if self._early:   # gradients reduced early, and now more local gradients arrive: set the reduced values aside
+            G = self._model.flat.G
+            if self._comm_done is not None:
+                torch.cuda.current_stream().wait_event(self._comm_done)
+            for a, b in self._early:
+                self._stash.append((a, b, G[a:b].clone()))
+                G[a:b].zero_()
+            self._early = []
 
     def backward_step(self, loss, optimizer):
-        if self._early is not None:
-            raise RuntimeError("B200DDPAccelerator: a second backward ran before optimizer_step after gradients were reduced "
-                               "early; set OVERLAP_ALLREDUCE: false when accumulating several backward passes per step")
         loss.backward()
+
+    def _last_backward_expected(self):
+        if self.overlap is True:
+            return True
+        return self._bw_per_step is not None and self._bw_seen >= self._bw_per_step
 
     def _reduce_range(self, G, a, b):
         n = b - a
@@ -190,42 +327,65 @@ class B200DDPAccelerator:
         for i in range(a, b, per):
             dist.all_reduce(G[i:min(b, i + per)], op=dist.ReduceOp.SUM)
 
-    def _early_reduce(self):
-        """Called at the start of the last backward node (vision encoder): reduce everything but the vision range on a side
-        stream while the vision backward runs (the reference's DDP overlaps bucket by bucket, ddp_accelerator.py:65)."""
+    def _side(self, ranges):
+        """All-reduce `ranges` of flat.G on the side stream, ordered after everything issued so far on the compute stream."""
         G = self._model.flat.G
+        if self._comm_stream is None:   # host tensors (gloo tests of this logic): reduce in line
+            for a, b in ranges:
+                self._reduce_range(G, a, b)
+        else:
+            ready = torch.cuda.Event()
+            ready.record(torch.cuda.current_stream())
+            self._comm_stream.wait_event(ready)
+            with torch.cuda.stream(self._comm_stream):
+                for a, b in ranges:
+                    self._reduce_range(G, a, b)
+                done = torch.cuda.Event()
+                done.record(self._comm_stream)
+            self._comm_done = done
+        self._early.extend(r for r in ranges if r[1] > r[0])
+
+    def _on_last_node(self):
+        """Start of the last backward node (vision encoder): every other gradient is final.  Returns the per-block callback
+        the vision backward calls as each block's gradients become final (the reference's DDP overlaps bucket by bucket,
+        ddp_accelerator.py:65)."""
+        if not self._last_backward_expected():
+            return None
         v0, v1 = self._vis
-        ready = torch.cuda.Event()
-        ready.record(torch.cuda.current_stream())
-        self._comm_stream.wait_event(ready)
-        with torch.cuda.stream(self._comm_stream):
-            self._reduce_range(G, 0, v0)
-            self._reduce_range(G, v1, self._train_end)
-            done = torch.cuda.Event()
-            done.record(self._comm_stream)
-        self._early = done
+        self._side([(0, v0), (v1, self._train_end)])
+        return self._on_block_done if self._blocks else None
+
+    def _on_block_done(self, i):
+        self._side([self._blocks[i]])
 
     def all_reduce_grads(self, model):
         """SUM all-reduce of the trainable part of the flat gradient buffer in a few large NVLink messages (averaging is
-        folded into the optimizer kernel's grad_mul).  When the non-vision ranges were already reduced under the vision
-        backward (_early_reduce) only the vision range is left."""
+        folded into the optimizer kernel's grad_mul); ranges already reduced under the backward pass are skipped."""
         if self.world == 1:
             return
         m = model.module if hasattr(model, "module") else model
         G = m.flat.G
         if not hasattr(self, "_train_end"):
             self._layout(m)
-        if self._early is not None:
-            torch.cuda.current_stream().wait_event(self._early)
-            self._early = None
-            self._reduce_range(G, self._vis[0], self._vis[1])
-        else:
-            self._reduce_range(G, 0, self._train_end)
+        if self._early and self._comm_done is not None:
+            torch.cuda.current_stream().wait_event(self._comm_done)
+        pos = 0
+        for a, b in sorted(self._early):
+            self._reduce_range(G, pos, a)
+            pos = max(pos, b)
+        self._reduce_range(G, pos, self._train_end)
+        self._early = []
+        for a, b, t in self._stash:
+            G[a:b].add_(t)
+        self._stash = []
+        for fp, _ in list(m.flat_buffers())[1:]:
+            dist.all_reduce(fp.G, op=dist.ReduceOp.SUM)
 
     def optimizer_step(self, optimizer, model):
         """clip_grad_norm_(CLIP_GRAD_NORM) + AdamW step + zero_grad (ddp_accelerator.py:89-98).  Returns the total gradient
         norm as a 1-element device tensor (no host sync; float() it if a python number is needed)."""
         self.all_reduce_grads(model)
+        self._bw_per_step, self._bw_seen = self._bw_seen, 0
         norm = optimizer.step(max_grad_norm=self.clip, grad_mul=1.0 / self.world)
         optimizer.zero_grad()
         return norm

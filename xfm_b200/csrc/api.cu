@@ -83,8 +83,11 @@ int xfm_colsum_bf16(const void* in, int64_t ld, float* out, int M, int N, void* 
 }
 int xfm_cast_f32_to_bf16(const float* in, void* out, size_t n, void* stream) { return cast_f32_to_bf16(in, BF(out), n, ST); }
 int xfm_cast_bf16_to_f32(const void* in, float* out, size_t n, void* stream) { return cast_bf16_to_f32(CBF(in), out, n, ST); }
-int xfm_scale_by_scalar(void* data, int dtype, const float* scalar, size_t n, void* stream) {
-  return scale_by_scalar(data, dtype, scalar, n, ST);
+int xfm_scale_by_scalar(const void* in, void* out, int dtype, const float* scalar, size_t n, void* stream) {
+  return scale_by_scalar(in, out, dtype, scalar, n, ST);
+}
+int xfm_split_bf16x3(const float* in, void* out, int M, int K, int role, int act, void* stream) {
+  return split_bf16x3(in, BF(out), M, K, role, act, ST);
 }
 int xfm_gelu_fwd(const void* x, int x_dtype, void* y, size_t n, void* stream) { return gelu_fwd(x, x_dtype, BF(y), n, ST); }
 int xfm_gelu_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, void* dx, size_t n, void* stream) {
@@ -168,12 +171,13 @@ int xfm_mim_mse(const float* x, const float* t, const uint8_t* mask, int B, int 
                 float* loss, float* dx, void* stream) {
   return mim_mse(x, t, mask, B, np, D, with_cls, count, loss, dx, ST);
 }
-int xfm_grad_sumsq(const float* g, const uint8_t* chunk_group, size_t nchunks, float* out, void* stream) {
-  return grad_sumsq(g, chunk_group, nchunks, out, ST);
+int xfm_grad_sumsq(const float* g, const int32_t* chunk_seg, const uint8_t* seg_group, size_t nchunks, int32_t* seg_step,
+                   float* seg_bc, int nseg, const float* hp, float* out, int accumulate, void* stream) {
+  return grad_sumsq(g, chunk_seg, seg_group, nchunks, seg_step, seg_bc, nseg, hp, out, accumulate, ST);
 }
-int xfm_adamw_flat(float* P, const float* G, float* M, float* V, void* S, const uint8_t* chunk_group, size_t nchunks,
-                   const float* sumsq, float* norm_out, const xfm_adamw_params* hp, void* stream) {
-  return adamw_flat(P, G, M, V, BF(S), chunk_group, nchunks, sumsq, norm_out, hp, ST);
+int xfm_adamw_flat(float* P, const float* G, float* M, float* V, void* S, const int32_t* chunk_seg, const uint8_t* seg_group,
+                   const float* seg_bc, size_t nchunks, const float* sumsq, float* norm_out, const float* hp, void* stream) {
+  return adamw_flat(P, G, M, V, BF(S), chunk_seg, seg_group, seg_bc, nchunks, sumsq, norm_out, hp, ST);
 }
 
 }  // extern "C"

@@ -354,13 +354,52 @@ __global__ void cast_bf16_to_f32_kernel(const bf16* __restrict__ in, float* __re
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
     *(float4*)(out + 4 * i) = ld4(in, 0, 4 * i);
 }
-// out = in * (*scalar) ; in/out same dtype (used to apply the upstream loss gradient to fused-loss gradients)
-__global__ void scale_by_scalar_kernel(void* __restrict__ data, int dtype, const float* __restrict__ scalar, size_t n4) {
+// Split-precision operand for an fp32-grade GEMM on the bf16 tensor cores: x = h + m + l with h = bf16(x), m = bf16(x - h),
+// l = bf16(x - h - m) (24 mantissa bits in three bf16 terms).  Each f32 row [K] becomes a bf16 row [6K] of six K-blocks;
+// role 0 (left operand) lays out h,h,m,h,m,l and role 1 (right operand) h,m,h,l,m,h, so one K' = 6K GEMM sums the six
+// products of order <= 2 (hh, hm, mh, hl, mm, lh): relative error ~2^-24, fp32 accumulation in TMEM.
+// Used where the reference forces fp32 inside an otherwise reduced-precision region (model_vqkd.py:154-155).
+// act: 0 none, 1 tanh applied before the split (encode_task_layer's nn.Tanh, model_vqkd.py:86-90).
+__global__ void __launch_bounds__(256)
+split_bf16x3_kernel(const float* __restrict__ in, bf16* __restrict__ out, int M, int K, int role, int act) {
+  const size_t n4 = (size_t)M * (K / 4);
+  const int k4 = K / 4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = i / k4;
+    const int col = (int)(i - row * k4) * 4;
+    float4 v = *(const float4*)(in + row * K + col);
+    if (act == 1) { v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w); }
+    const float x[4] = {v.x, v.y, v.z, v.w};
+    bf16 t[3][4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const bf16 h = __float2bfloat16_rn(x[e]);
+      const float r1 = x[e] - __bfloat162float(h);
+      const bf16 m = __float2bfloat16_rn(r1);
+      const bf16 l = __float2bfloat16_rn(r1 - __bfloat162float(m));
+      t[0][e] = h; t[1][e] = m; t[2][e] = l;
+    }
+    const int sel0[6] = {0, 0, 1, 0, 1, 2}, sel1[6] = {0, 1, 0, 2, 1, 0};
+    bf16* o = out + row * (size_t)(6 * K) + col;
+#pragma unroll
+    for (int b = 0; b < 6; ++b) {
+      const int w = role == 0 ? sel0[b] : sel1[b];
+      uint2 u;
+      __nv_bfloat162 lo = __halves2bfloat162(t[w][0], t[w][1]), hi = __halves2bfloat162(t[w][2], t[w][3]);
+      u.x = *(uint32_t*)&lo; u.y = *(uint32_t*)&hi;
+      *(uint2*)(o + (size_t)b * K) = u;
+    }
+  }
+}
+
+// out = in * (*scalar) ; in/out same dtype, out may alias in (applies the upstream loss gradient to the gradients a fused
+// loss kernel prepared in its forward; out-of-place so that a retained graph can be back-propagated twice)
+__global__ void scale_by_scalar_kernel(const void* in, void* out, int dtype, const float* __restrict__ scalar, size_t n4) {
   const float s = *scalar;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
-    float4 v = ld4(data, dtype, 4 * i);
+    float4 v = ld4(in, dtype, 4 * i);
     v.x *= s; v.y *= s; v.z *= s; v.w *= s;
-    st4(data, dtype, 4 * i, v);
+    st4(out, dtype, 4 * i, v);
   }
 }
 
@@ -837,10 +876,16 @@ int cast_bf16_to_f32(const bf16* in, float* out, size_t n, cudaStream_t s) {
   cast_bf16_to_f32_kernel<<<grid_1d(n / 4, 256), 256, 0, s>>>(in, out, n / 4);
   LAUNCH_END();
 }
-int scale_by_scalar(void* data, int dtype, const float* scalar, size_t n, cudaStream_t s) {
+int split_bf16x3(const float* in, bf16* out, int M, int K, int role, int act, cudaStream_t s) {
+  if (K & 3 || M < 0 || (role != 0 && role != 1)) { set_error("split_bf16x3: K must be a multiple of 4, role 0/1"); return XFM_ERR_BAD_ARG; }
+  if (!M) return 0;
+  split_bf16x3_kernel<<<grid_1d((size_t)M * (K / 4), 256), 256, 0, s>>>(in, out, M, K, role, act);
+  LAUNCH_END();
+}
+int scale_by_scalar(const void* in, void* out, int dtype, const float* scalar, size_t n, cudaStream_t s) {
   if (n & 3) { set_error("scale: n must be a multiple of 4"); return XFM_ERR_BAD_ARG; }
   if (!n) return 0;
-  scale_by_scalar_kernel<<<grid_1d(n / 4, 256), 256, 0, s>>>(data, dtype, scalar, n / 4);
+  scale_by_scalar_kernel<<<grid_1d(n / 4, 256), 256, 0, s>>>(in, out, dtype, scalar, n / 4);
   LAUNCH_END();
 }
 

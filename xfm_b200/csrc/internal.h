@@ -43,7 +43,8 @@ int layerscale_bwd(const float* dxo, const bf16_t* z, const float* gamma, const 
 int colsum_bf16(const bf16_t* in, int64_t ld, float* out, int M, int N, cudaStream_t s);
 int cast_f32_to_bf16(const float* in, bf16_t* out, size_t n, cudaStream_t s);
 int cast_bf16_to_f32(const bf16_t* in, float* out, size_t n, cudaStream_t s);
-int scale_by_scalar(void* data, int dtype, const float* scalar, size_t n, cudaStream_t s);
+int scale_by_scalar(const void* in, void* out, int dtype, const float* scalar, size_t n, cudaStream_t s);
+int split_bf16x3(const float* in, bf16_t* out, int M, int K, int role, int act, cudaStream_t s);
 int gelu_fwd(const void* x, int x_dtype, bf16_t* y, size_t n, cudaStream_t s);
 int gelu_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, bf16_t* dx, size_t n, cudaStream_t s);
 int dropout_apply(const void* x, int x_dtype, bf16_t* y, size_t n, float p, uint64_t seed, cudaStream_t s);
@@ -82,8 +83,9 @@ int l2norm_fwd(const float* x, float* y, float* inv_norm, int R, int E, cudaStre
 int l2norm_bwd(const float* dy, const float* y, const float* inv_norm, float* dx, int R, int E, cudaStream_t s);
 int mim_mse(const float* x, const float* t, const uint8_t* mask, int B, int np, int D, int with_cls, float* count,
             float* loss, float* dx, cudaStream_t s);
-int grad_sumsq(const float* g, const uint8_t* chunk_group, size_t nchunks, float* out, cudaStream_t s);
-int adamw_flat(float* P, const float* G, float* M, float* V, bf16_t* S, const uint8_t* chunk_group, size_t nchunks,
-               const float* sumsq, float* norm_out, const xfm_adamw_params* hp, cudaStream_t s);
+int grad_sumsq(const float* g, const int32_t* chunk_seg, const uint8_t* seg_group, size_t nchunks, int32_t* seg_step,
+               float* seg_bc, int nseg, const float* hp, float* out, int accumulate, cudaStream_t s);
+int adamw_flat(float* P, const float* G, float* M, float* V, bf16_t* S, const int32_t* chunk_seg, const uint8_t* seg_group,
+               const float* seg_bc, size_t nchunks, const float* sumsq, float* norm_out, const float* hp, cudaStream_t s);
 
 }  // namespace xfm

@@ -233,14 +233,17 @@ class VisionEncoder:
             st.cols, st.mask, st.x_final, st.stats, st.B = cols, mask_u8, x, stats, B
         return y32.view(B, N, D), y16.view(B, N, D), (st if save else None)
 
-    def backward(self, st, dy32):
-        """dy32: f32 [B,N,D] gradient of the pooled output.  Accumulates every parameter gradient of the encoder."""
+    def backward(self, st, dy32, block_done=None):
+        """dy32: f32 [B,N,D] gradient of the pooled output.  Accumulates every parameter gradient of the encoder.
+        block_done(i), when given, is called as soon as block i's parameter gradients are final (kernels issued)."""
         B, N, D, npatch, p, fp = st.B, self.N, self.D, self.np, self.prefix, self.fp
         dy = L.meanpool_bwd(_f32(dy32).reshape(B * N, D).contiguous(), B, npatch)
         dx = L.layernorm_bwd(dy, st.x_final, st.stats, self.fcw, fp.grad(p + "fc_norm.weight"), fp.grad(p + "fc_norm.bias"))
         for i in reversed(range(self.depth)):
             dx = BK.vit_block_bwd(dx, st.blocks[i], self.w[i], self._g(i), B, N, self.H, rel_index=self.rel_index)
             st.blocks[i] = None  # free activations as we go
+            if block_done is not None:
+                block_done(i)
         dmask = fp.grad(p + "mask_token") if st.mask is not None else None
         dpatch = L.assemble_tokens_bwd(dx, st.mask, fp.grad(p + "cls_token"), dmask, B, npatch)
         L.colsum_into(dpatch, fp.grad(p + "patch_embed.proj.bias"))

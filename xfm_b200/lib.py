@@ -340,9 +340,22 @@ def cast_to_f32(src, dst):
     check(lib().xfm_cast_bf16_to_f32(_p(src), _p(dst), C.c_size_t(src.numel()), stream_ptr()), "xfm_cast_bf16_to_f32")
 
 
-def scale_by_scalar_(t, scalar):
+def split_bf16x3(x, role, act=0):
+    """f32 [M, K] -> bf16 [M, 6K]: three-term bf16 split laid out for an fp32-grade GEMM over K' = 6K (role 0 = left operand,
+    1 = right operand / weight; act=1 applies tanh first).  See xfm_split_bf16x3."""
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.is_contiguous()
+    M, K = x.shape
+    out = torch.empty((M, 6 * K), dtype=torch.bfloat16, device=x.device)
+    check(lib().xfm_split_bf16x3(_p(x), _p(out), M, K, role, act, stream_ptr()), "xfm_split_bf16x3")
+    return out
+
+
+def scale_by_scalar(t, scalar):
+    """t * scalar[0] as a NEW tensor (scalar: f32 [1] on the device)."""
     assert t.is_contiguous() and scalar.dtype == torch.float32
-    check(lib().xfm_scale_by_scalar(_p(t), _dt(t), _p(scalar), C.c_size_t(t.numel()), stream_ptr()), "xfm_scale_by_scalar")
+    out = torch.empty_like(t)
+    check(lib().xfm_scale_by_scalar(_p(t), _p(out), _dt(t), _p(scalar), C.c_size_t(t.numel()), stream_ptr()), "xfm_scale_by_scalar")
+    return out
 
 
 def roberta_embed_fwd(ids, word, pos, type_emb, ln_w, ln_b, pad_id, eps, want_pre=True):
@@ -555,22 +568,27 @@ def mim_mse(x, t, mask_u8, with_cls=True):
     return loss, dx
 
 
-class AdamWParams(C.Structure):
-    _fields_ = [("lr", C.c_float * 4), ("weight_decay", C.c_float * 4), ("beta1", C.c_float), ("beta2", C.c_float),
-                ("eps", C.c_float), ("max_grad_norm", C.c_float), ("grad_mul", C.c_float), ("step", C.c_int32),
-                ("correct_bias", C.c_int32)]
+def adamw_hparams(lrs, wds, beta1, beta2, eps, max_grad_norm, grad_mul, correct_bias):
+    """The 16-float hyper-parameter block of xfm_adamw_flat / xfm_grad_sumsq as a host tensor (pinned when CUDA is there)."""
+    t = torch.tensor(list(lrs) + list(wds) + [beta1, beta2, eps, max_grad_norm, grad_mul, 1.0 if correct_bias else 0.0, 0.0, 0.0],
+                     dtype=torch.float32)
+    return t.pin_memory() if torch.cuda.is_available() else t
 
 
-def grad_sumsq(G, chunk_group, out):
+def grad_sumsq(G, chunk_seg, seg_group, seg_step, seg_bc, hp, out, accumulate=False):
     n = G.numel() // 64
-    check(lib().xfm_grad_sumsq(_p(G), _p(chunk_group), C.c_size_t(n), _p(out), stream_ptr()), "xfm_grad_sumsq")
+    assert G.numel() % 64 == 0 and chunk_seg.numel() == n and chunk_seg.dtype == torch.int32
+    assert seg_group.dtype == torch.uint8 and seg_step.dtype == torch.int32 and seg_bc.dtype == torch.float32
+    assert seg_step.numel() == seg_group.numel() and seg_bc.numel() == 2 * seg_group.numel() and hp.numel() == 16
+    check(lib().xfm_grad_sumsq(_p(G), _p(chunk_seg), _p(seg_group), C.c_size_t(n), _p(seg_step), _p(seg_bc),
+                               seg_group.numel(), _p(hp), _p(out), int(accumulate), stream_ptr()), "xfm_grad_sumsq")
 
 
-def adamw_flat(P, G, M, V, S, chunk_group, hp, sumsq=None, norm_out=None):
+def adamw_flat(P, G, M, V, S, chunk_seg, seg_group, seg_bc, hp, sumsq=None, norm_out=None):
     n = P.numel() // 64
-    assert P.numel() % 64 == 0 and chunk_group.numel() == n and chunk_group.dtype == torch.uint8
-    check(lib().xfm_adamw_flat(_p(P), _p(G), _p(M), _p(V), _p(S), _p(chunk_group), C.c_size_t(n), _p(sumsq), _p(norm_out),
-                               C.byref(hp), stream_ptr()), "xfm_adamw_flat")
+    assert P.numel() % 64 == 0 and chunk_seg.numel() == n and chunk_seg.dtype == torch.int32 and seg_group.dtype == torch.uint8
+    check(lib().xfm_adamw_flat(_p(P), _p(G), _p(M), _p(V), _p(S), _p(chunk_seg), _p(seg_group), _p(seg_bc), C.c_size_t(n),
+                               _p(sumsq), _p(norm_out), _p(hp), stream_ptr()), "xfm_adamw_flat")
 
 
 def sgemm_f32(a, b, out=None, bias=None, accumulate=False):

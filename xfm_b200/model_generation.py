@@ -48,6 +48,10 @@ class XFMForVQA(XFMBase):
         self._dec_head = E.LMHead(fp, cfg, d)
         self._causal = {}
 
+    def _extra_runners(self):
+        self._causal = {}
+        return (self._dec,)
+
     def load_pretrained(self, ckpt_rpath, config, is_eval=False):
         """model_generation.py:62-91: the decoder starts from the pre-trained fusion encoder."""
         if is_eval:

@@ -119,6 +119,9 @@ class FlatParams:
     # ---- maintenance --------------------------------------------------------------------------------
     def sync_shadow(self, force=False):
         """bf16 shadow <- fp32 master, if the master changed (optimizer step, load_state_dict, manual edit)."""
+        if not self.P.is_cuda:   # model still on the host (constructed before .to(device)): cast on first use on the GPU
+            self._shadow_version = -1
+            return
         v = self.P._version
         if force or v != self._shadow_version:
             L.cast_to_bf16(self.P, self.S)

@@ -13,6 +13,7 @@ import numpy as np
 import torch
 
 from . import encoders as E
+from . import lib as L
 from .xfm import _twin
 
 
@@ -53,7 +54,7 @@ def _fusion_scores(model, text32, text16, text_atts, img16, kv_index):
     _, out32, _ = model._fusion_run(text16.contiguous(), Bt, Lt, kmask, img16, img16.shape[0], kv_index, False,
                                     text32=text32.contiguous())
     cls = out32.view(Bt, Lt, -1)[:, 0, :].contiguous()
-    return model._itm_logits(cls)[:, 1]
+    return model.itm_head(cls)[:, 1]
 
 
 @torch.no_grad()
@@ -67,7 +68,7 @@ def rerank(model, image_feats16, image_embeds, text_feats32, text_feats16, text_
     n_img, n_txt = image_embeds.shape[0], text_embeds.shape[0]
     k = min(k_test, n_txt)
     rank, world = _world() if shard is None else shard
-    sims = image_embeds @ text_embeds.t()
+    sims = L.sgemm_f32(image_embeds.float().contiguous(), text_embeds.float().contiguous())   # Retrieval.py:129 (fp32 exact)
     group = max(1, pairs_per_pass // k)
 
     score_i2t = torch.full((n_img, n_txt), -100.0, device=dev)

@@ -13,11 +13,13 @@ Differences a caller can observe (all documented in DESIGN.md):
   * parameters that took no part in a backward pass keep grad None, like the reference's unused parameters.
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
 
 from . import blocks as BK
+from . import checkpoint as CK
 from . import encoders as E
 from . import lib as L
 from .config import normalize_config
@@ -64,11 +66,12 @@ class _Holder(nn.Module):
         raise RuntimeError("xfm_b200 sub-modules are parameter holders; call the XFMBase methods")
 
 
-class _ItmHead(_Holder):
-    """Callable like the reference's nn.Sequential itm_head (Retrieval.py:147-150 calls model.itm_head(x))."""
+class _HeadModule(_Holder):
+    """Callable like the reference's nn.Sequential heads built by build_mlp (Retrieval.py:147-150 calls model.itm_head(x),
+    model_nlvr.py:42 self.cls_head(x)); differentiable wrt x and the head's parameters."""
 
     def forward(self, x):
-        return self._owner()._itm_logits(x)
+        return self._owner()._head_apply(self._head_name, x)
 
 
 class _Op(torch.autograd.Function):
@@ -87,9 +90,11 @@ class _Op(torch.autograd.Function):
         model._backward_begin()
         model._pending_nodes -= 1
         # Last node of this backward pass and it only produces vision-encoder gradients: every other gradient is final,
-        # so a data-parallel accelerator may start reducing those ranges now, under the vision backward.
+        # so a data-parallel accelerator may start reducing those ranges now, under the vision backward (the hook may
+        # return a callback that the vision backward invokes as each block's gradients become final).
+        ctx.impl.block_done = None
         if model._pending_nodes == 0 and getattr(ctx.impl, "kind", None) == "vision" and model._last_node_hook is not None:
-            model._last_node_hook()
+            ctx.impl.block_done = model._last_node_hook()
         gin = ctx.impl.bwd(ctx, *grads)
         return (None, None) + tuple(gin)
 
@@ -173,30 +178,17 @@ def build_mlp(input_dim, output_dim):
 
 
 def load_pretrained(model, ckpt_rpath, config, is_eval=False, load_text=False):
-    """xfm.py:408-468 for the BEiT-v2 configurations: returns the state_dict to load.  Relative-position tables are passed
-    through when the checkpoint resolution equals config['image_res']; the geometric interpolation of beit2.py:753-849
-    (resolution change at fine-tune time) is checkpoint tooling outside the hot path and is not re-implemented."""
+    """xfm.py:408-468 for the BEiT-v2 configurations: returns the state_dict to load.  Relative-position tables of another
+    resolution are resampled like beit2.py:753-808 (checkpoint.interpolate_rel_pos)."""
     checkpoint = torch.load(ckpt_rpath, map_location="cpu")
     state_dict = checkpoint["model"] if "model" in checkpoint.keys() else checkpoint
     if is_eval:
         return state_dict
     if not config.get("use_beit_v2", True):
         raise ValueError("only the BEiT-v2 vision encoder is built (every shipped config selects it)")
-    own = model.state_dict()
-    for k in list(state_dict.keys()):
-        if k.startswith("vision_encoder.") and "relative_position_bias_table" in k and k in own and \
-                state_dict[k].shape != own[k].shape:
-            raise NotImplementedError(f"{k}: checkpoint table {tuple(state_dict[k].shape)} vs model {tuple(own[k].shape)}; "
-                                      "interpolate the checkpoint with the reference's beit2.interpolate_pos_embed first")
-        if "relative_position_index" in k:
-            del state_dict[k]
-    if load_text:
-        for key in list(state_dict.keys()):
-            if key.startswith("text_encoder."):
-                name = "roberta." if "roberta" in str(config.get("text_encoder", "roberta")) else "bert."
-                if name in key:
-                    state_dict[key.replace(name, "")] = state_dict.pop(key)
-    return state_dict
+    print("### Loading pretrained vision encoder", flush=True)
+    own = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    return CK.finetune_state(state_dict, own, str(config.get("text_encoder", "roberta")), load_text=load_text)
 
 
 class XFMBase(nn.Module):
@@ -204,13 +196,12 @@ class XFMBase(nn.Module):
                  use_matching_loss=False, use_mlm_loss=False, use_bbox_loss=False, config_text=None, init=None,
                  device=None):
         super().__init__()
-        if load_vision_params or load_text_params:
-            raise NotImplementedError("checkpoint import goes through load_state_dict (reference key layout); "
-                                      "load_vision_params / load_text_params are not built")
         cfg = self.cfg = normalize_config(config)
         config = config or {}
         init = init or default_init()
         self.init_params = []
+        self._head_names = {"itm_head": 2, "bbox_head": 4}   # build_mlp heads callable as modules: name -> outputs
+        self._head_runners = {}
         fp = self.flat = FlatParams()
         D, Hd = cfg["vision_width"], cfg["hidden"]
         self.vision_width, self.text_width = D, Hd
@@ -251,15 +242,27 @@ class XFMBase(nn.Module):
         if not self.learnable_temp and use_contrastive_loss:
             self.init_params.remove("temp")
         self._extend_params(fp, cfg, init, config)
-        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        # default: the current CUDA device when there is one, else the host (the reference drivers construct on the host
+        # and call .to(device), Pretrain.py:413-417 — see _apply)
+        if device is not None:
+            dev = torch.device(device)
+        else:
+            dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
         fp.finalize(dev)
+        self.flat_extra, self._extra_params = None, {}
 
         # ---- module tree with the reference's names
         self._params = {}
         for name, seg in fp.segments.items():
             if name.rsplit(".", 1)[-1].startswith("_"):
                 continue
-            p = nn.Parameter(fp.view32(name), requires_grad=seg.trainable)
+            if name == "temp":
+                if not self.learnable_temp:   # xfm.py:505-507: a frozen temp is a python float, not a state_dict entry
+                    self.temp = float(cfg["temp"])
+                    continue
+                p = nn.Parameter(self._temp_alias(), requires_grad=True)
+            else:
+                p = nn.Parameter(fp.view32(name), requires_grad=seg.trainable)
             self._params[name] = p
             self._register(name, p)
         for enc in ("text_encoder.", "fusion_encoder."):  # weight tying (xroberta.py:1209-1210,1321-1323)
@@ -271,9 +274,6 @@ class XFMBase(nn.Module):
         rpi = relative_position_index(ws).to(dev)
         for i in range(cfg["vision_depth"]):
             self._register_buffer(f"vision_encoder.blocks.{i}.attn.relative_position_index", rpi)
-        if not self.learnable_temp and use_contrastive_loss:
-            pass  # temp stays a (frozen) parameter view so kernels can read it from device memory
-
         # ---- runners
         self._rpi = rpi
         self._vis = E.VisionEncoder(fp, cfg, rel_index=rpi)
@@ -289,8 +289,17 @@ class XFMBase(nn.Module):
             self._mim_head = E.LinearCE(fp, "lm_head", cfg["codebook_size"])
         self._sampler = BlockMaskSampler(ws, cfg["num_masking_patches"], cfg["min_num_patches"])
         self._extend_modules(fp, cfg, config)
-        if use_matching_loss:
-            object.__setattr__(self.itm_head, "_owner", lambda s=self: s)
+        import types
+        for enc, nl, fl in (("text_encoder", cfg["text_layers"], cfg["text_layers"]), ("fusion_encoder", cfg["fusion_layers"], 0)):
+            # the attributes of RobertaConfig the reference's task models read (model_retrieval.py:16, xfm.py:481-485)
+            object.__setattr__(self._modules[enc], "config", types.SimpleNamespace(
+                hidden_size=Hd, num_attention_heads=cfg["heads"], num_hidden_layers=nl, fusion_layer=fl, encoder_width=D,
+                vocab_size=cfg["vocab_size"], intermediate_size=cfg["ffn"], max_position_embeddings=cfg["max_pos"],
+                pad_token_id=cfg["pad_id"], layer_norm_eps=cfg["ln_eps"], type_vocab_size=cfg["type_vocab"]))
+        for hn in self._head_names:
+            if hn in self._modules:
+                object.__setattr__(self._modules[hn], "_owner", lambda s=self: s)
+                object.__setattr__(self._modules[hn], "_head_name", hn)
         self._anchor = torch.zeros((), requires_grad=True)
         self._in_backward = False
         self._attached = []
@@ -299,6 +308,15 @@ class XFMBase(nn.Module):
         self._drop_calls = 0
         self._seed = int(torch.initial_seed()) & 0x7FFFFFFF
         self.last_hard_negative_weights = None
+        self._task_ops = None
+        self._load_initial_params(config, load_vision_params, load_text_params and use_mlm_loss)
+        if not use_mlm_loss:
+            assert load_text_params is False  # xfm.py:387-388 (fine-tuning models never load the text checkpoint here)
+        named = set(n for n, _ in self.named_parameters())   # xfm.py:517-522
+        for n in set(self.init_params):
+            if n not in named:
+                print(f"warning: {n} not in named_parameters")
+                self.init_params.remove(n)
 
     # ------------------------------------------------------------------ subclass hooks
     def _extend_params(self, fp, cfg, init, config):
@@ -312,7 +330,7 @@ class XFMBase(nn.Module):
         mod = self
         for i, part in enumerate(path):
             if part not in mod._modules:
-                cls = _ItmHead if (i == 0 and part == "itm_head") else _Holder
+                cls = _HeadModule if (i == 0 and part in self._head_names) else _Holder
                 mod.add_module(part, cls())
             mod = mod._modules[part]
         return mod
@@ -328,13 +346,136 @@ class XFMBase(nn.Module):
         *path, leaf = name.split(".")
         self._node(path).register_buffer(leaf, t)
 
+    def _temp_alias(self):
+        """0-dim f32 tensor over the flat buffer's `temp` slot with its OWN version counter (not a view of P in autograd
+        terms): the reference's `self.temp.clamp_(...)` at the top of every forward (model_pretrain.py:35-37) then does not
+        look like an edit of the whole master buffer, which would force a full bf16 shadow recast per step."""
+        P = self.flat.P
+        off = self.flat.segments["temp"].offset
+        return torch.empty(0, dtype=P.dtype, device=P.device).set_(P.untyped_storage(), P.storage_offset() + off, (), ())
+
+    def _temp_dev(self):
+        """f32 [1] device view of temp for the kernels (a frozen temp is a python attribute the caller may edit)."""
+        t = self.flat.view32("temp").view(1)
+        if not self.learnable_temp and getattr(self, "_temp_written", None) != float(self.temp):
+            fresh = self.flat._shadow_version == self.flat.P._version
+            with torch.no_grad():
+                t.fill_(float(self.temp))
+            if fresh:
+                self.flat._shadow_version = self.flat.P._version
+            self._temp_written = float(self.temp)
+        return t
+
+    def flat_buffers(self):
+        """[(FlatParams, {segment name: nn.Parameter})]: the model's own buffer, then the adopted one (if any)."""
+        out = [(self.flat, self._params)]
+        if self.flat_extra is not None:
+            out.append((self.flat_extra, self._extra_params))
+        return out
+
+    def adopt_stray_parameters(self):
+        """Trainable parameters created outside the flat buffer — e.g. the reference's own model_nlvr.py:25
+        `self.cls_head = build_mlp(...)` assigned after XFMBase.__init__ — move into a second flat buffer (P/G/S), so the
+        flat optimizer and the accelerator reduce, clip, update and zero them like every other parameter.  Idempotent."""
+        known = {id(p) for p in self._params.values()} | {id(p) for p in self._extra_params.values()}
+        stray = [(n, p) for n, p in self.named_parameters() if p.requires_grad and id(p) not in known]
+        if not stray:
+            return
+        if self.flat_extra is not None:
+            raise RuntimeError("parameters were added after the optimizer was built: " + ", ".join(n for n, _ in stray[:4]))
+        fx = FlatParams()
+        for n, p in stray:
+            fx.add(n, tuple(p.shape), init=p.detach())
+        fx.finalize(self.flat.P.device)
+        with torch.no_grad():
+            for n, p in stray:
+                p.data = fx.view32(n)
+                p.grad = fx._view(fx.G, n)
+                fx.touched.add(n)
+        self.flat_extra, self._extra_params = fx, dict(stray)
+
+    def collect_stray_grads(self):
+        """Gradients of adopted parameters accumulate in place in the second buffer; if a driver dropped that .grad
+        (set_to_none) autograd allocated a fresh tensor — copy it in and re-attach the view."""
+        if self.flat_extra is None:
+            return
+        fx = self.flat_extra
+        for n, p in self._extra_params.items():
+            view = fx._view(fx.G, n)
+            if p.grad is None:
+                p.grad = view
+            elif p.grad.data_ptr() != view.data_ptr():
+                view.copy_(p.grad)
+                p.grad = view
+
     def _apply(self, fn, recurse=True):
+        """.to(device) / .cuda() move the flat buffers and re-point every parameter view (Pretrain.py:417 `model.to(device)`
+        after constructing on the host); dtype changes are refused (fp32 master weights, bf16 compute is internal)."""
         probe = fn(self.flat.P[:1])
         if probe.dtype != torch.float32:
             raise RuntimeError("xfm_b200 keeps fp32 master weights (bf16 compute is internal); .half()/.bfloat16() is not supported")
-        if probe.device != self.flat.P.device:
-            raise RuntimeError("construct XFMBase on its target device (device=...); moving the flat buffers is not supported")
+        known = {id(p) for p in self._params.values()} | {id(p) for p in self._extra_params.values()}
+        with torch.no_grad():   # modules a task model attached after construction (model_nlvr.py:25 cls_head)
+            for _, p in self.named_parameters():
+                if id(p) not in known:
+                    p.data = fn(p.data)
+                    if p.grad is not None:
+                        p.grad.data = fn(p.grad.data)
+        if probe.device == self.flat.P.device:
+            return self
+        for fp, params in self.flat_buffers():
+            fp.move(fn)
+            with torch.no_grad():
+                for name, p in params.items():
+                    p.data = self._temp_alias() if (name == "temp" and fp is self.flat) else fp.view32(name)
+                    p.grad = None
+        if self.flat_extra is not None:
+            for n, p in self._extra_params.items():
+                p.grad = self.flat_extra._view(self.flat_extra.G, n)
+        self._attached = []
+        for m in self.modules():
+            for k, b in list(m._buffers.items()):
+                if b is not None:
+                    m._buffers[k] = fn(b)
+        dev = self.flat.P.device
+        self._rpi = self._rpi.to(dev)
+        self._vis.rel_index = self._rpi
+        for r in (self._vis, self._txt, self._fus, getattr(self, "_vq", None)) + tuple(self._extra_runners()):
+            if r is not None:
+                r.w = None
+        self._task_ops = None
+        self._temp_written = None
         return self
+
+    def _extra_runners(self):
+        """Task models list the runners (objects caching parameter views in `.w`) they built in _extend_modules."""
+        return ()
+
+    def _load_initial_params(self, config, load_vision_params, load_text_params):
+        """Constructor-time checkpoint import of the reference (xfm.py:205-256 vision, :298-385 text, model_vqkd.py:315-333
+        tokenizer).  Adds the text-encoder keys the checkpoint lacks to init_params (xfm.py:385)."""
+        config = config or {}
+        own = None
+        if self.use_vision_tokenizer and config.get("tokenizer_weight") and os.path.exists(str(config["tokenizer_weight"])):
+            self.load_state_dict(CK.vqkd_state(config["tokenizer_weight"]), strict=False)
+        if load_vision_params:
+            from .config import _read_json
+            vis = _read_json(config.get("vision_config")) or {}
+            own = {k: tuple(v.shape) for k, v in self.state_dict().items()}
+            sd = CK.beit2_init_state(vis["ckpt"], own, self.cfg["vision_depth"])
+            msg = self.load_state_dict(sd, strict=False)
+            missing = [k for k in msg.missing_keys if k.startswith("vision_encoder.") and "relative_position_index" not in k]
+            if missing:
+                print("Weights of VisionTransformer not initialized from pretrained model: {}".format(missing))
+            if msg.unexpected_keys:
+                print("Weights from pretrained model not used in VisionTransformer: {}".format(msg.unexpected_keys))
+        if load_text_params:
+            sd = CK.roberta_init_state(str(config["text_encoder"]), self.cfg["text_layers"])
+            msg = self.load_state_dict(sd, strict=False)
+            missing = [k[len("text_encoder."):] for k in msg.missing_keys if k.startswith("text_encoder.")]
+            print("missing_keys: ", missing, flush=True)
+            print("unexpected_keys: ", [k[len("text_encoder."):] for k in msg.unexpected_keys], flush=True)
+            self.init_params += [f"text_encoder.{k}" for k in missing]
 
     def load_state_dict(self, state_dict, strict=True, assign=False):
         # fine-tuning models of the reference hold a bare RobertaModel as text_encoder (xfm.py:397-403), so their
@@ -343,7 +484,7 @@ class XFMBase(nn.Module):
                        if k.startswith(("text_encoder.embeddings.", "text_encoder.encoder.")) else k): v
                       for k, v in state_dict.items()}
         out = super().load_state_dict(state_dict, strict=strict, assign=False)
-        self.flat.sync_shadow(force=True)
+        self.flat.sync_shadow(force=True)   # (on the host: only marks the shadow stale, Pretrain.py:413-417)
         return out
 
     def load_pretrained(self, ckpt_rpath, config, is_eval=False, is_domain_pretrain=False):
@@ -361,6 +502,8 @@ class XFMBase(nn.Module):
         if self._in_backward:
             return
         self._in_backward = True
+        if self._backward_begin_hook is not None:
+            self._backward_begin_hook()
         if self._attached and self._attached[0].grad is None:  # optimizer.zero_grad(set_to_none=True) ran
             self.flat.zero_grad()
             self._attached = []
@@ -384,18 +527,19 @@ class XFMBase(nn.Module):
         for p in self._params.values():
             p.grad = None
         self._attached = []
+        if self.flat_extra is not None:   # adopted parameters keep their .grad views (autograd accumulates in place)
+            self.flat_extra.G.zero_()
+            for n, p in self._extra_params.items():
+                p.grad = self.flat_extra._view(self.flat_extra.G, n)
 
     def _prep(self):
         self.flat.sync_shadow()
 
     def clamp_temp(self, lo, hi):
-        """temp.clamp_(lo, hi) (model_pretrain.py:35-37) without invalidating the bf16 weight shadow (temp is only ever
-        read in fp32)."""
-        fresh = self.flat._shadow_version == self.flat.P._version
+        """temp.clamp_(lo, hi) (model_pretrain.py:35-37).  `temp` has its own version counter (_temp_alias), so neither this
+        nor the reference's own in-place clamp invalidates the bf16 weight shadow (temp is only ever read in fp32)."""
         with torch.no_grad():
-            self.flat.view32("temp").clamp_(lo, hi)
-        if fresh:
-            self.flat._shadow_version = self.flat.P._version
+            self._params["temp"].clamp_(lo, hi)
 
     def _drop(self):
         if not self.training:
@@ -405,6 +549,7 @@ class XFMBase(nn.Module):
 
     _pending_nodes = 0
     _last_node_hook = None
+    _backward_begin_hook = None
 
     def _call(self, impl, *tensors):
         impl.model = self
@@ -443,7 +588,7 @@ class XFMBase(nn.Module):
                 return y32
 
             def bwd(self, ctx, dy):
-                model._vis.backward(ctx.st, dy)
+                model._vis.backward(ctx.st, dy, block_done=getattr(self, "block_done", None))
                 ctx.st = None
                 return (None,)
         impl = Impl()
@@ -536,7 +681,7 @@ class XFMBase(nn.Module):
         if idx is not None:
             idx = idx.view(-1)
             assert idx.size(0) == B
-        temp = self.flat.view32("temp").view(1)
+        temp = self._temp_dev()
 
         class Impl:
             def fwd(self, ctx, fi, ft):
@@ -549,11 +694,9 @@ class XFMBase(nn.Module):
             def bwd(self, ctx, g):
                 di, dt, dtemp = ctx.g
                 up = _up(g)
-                L.scale_by_scalar_(di, up)
-                L.scale_by_scalar_(dt, up)
                 if model.learnable_temp:
                     model.flat.grad("temp").add_((dtemp * up).view(()))
-                return di, dt
+                return L.scale_by_scalar(di, up), L.scale_by_scalar(dt, up)
         return self._call(Impl(), image_feat, text_feat)
 
     # ------------------------------------------------------------------ ITM
@@ -565,13 +708,13 @@ class XFMBase(nn.Module):
         self._drop_calls += 1
         seed = (self._seed * 7919 + self._drop_calls * 104729) & 0x7FFFFFFFFFFFFFFF
         ineg, tneg, _, _ = L.hard_negatives(image_feat.detach().float().contiguous(), text_feat.detach().float().contiguous(),
-                                            self.flat.view32("temp").view(1), seed, idx=None if idx is None else idx.view(-1))
+                                            self._temp_dev(), seed, idx=None if idx is None else idx.view(-1))
         return ineg, tneg
 
     def hard_negative_weights(self, image_feat, text_feat, idx=None):
         """The deterministic part of get_hard_negatives (weights_i2t, weights_t2i), for parity checks."""
         _, _, w1, w2 = L.hard_negatives(image_feat.detach().float().contiguous(), text_feat.detach().float().contiguous(),
-                                        self.flat.view32("temp").view(1), 0, idx=None if idx is None else idx.view(-1),
+                                        self._temp_dev(), 0, idx=None if idx is None else idx.view(-1),
                                         want_weights=True)
         return w1, w2
 
@@ -628,12 +771,34 @@ class XFMBase(nn.Module):
         y._xfm16 = impl.h16
         return y
 
-    def _itm_logits(self, x):
-        """model.itm_head(x) for evaluation loops (Retrieval.py:147-150): x f32/bf16 [R, hidden] -> logits f32 [R, 2]."""
+    def _head_apply(self, name, x):
+        """model.<head>(x) for a build_mlp head living in the flat buffer: x f32/bf16 [..., din] -> logits f32 [..., nout]."""
         self._prep()
-        x16 = _twin(x) if x.dtype != torch.bfloat16 else x
-        logits, _ = self._itm.logits(x16.contiguous(), save=False)
-        return logits
+        model = self
+        runner = self._head_runners.get(name)
+        if runner is None:
+            runner = self._head_runners[name] = E.MlpHead(self.flat, name, self._head_names[name])
+        shape = x.shape
+        nout = self._head_names[name]
+
+        class Impl:
+            def fwd(self, ctx, x_):
+                x2 = x_.detach().reshape(-1, shape[-1])
+                x16 = (x2 if x2.dtype == torch.bfloat16 else _twin(x2)).contiguous()
+                logits, st = runner.logits(x16, save=self.save)
+                if ctx is not None:
+                    ctx.st = st
+                return logits.reshape(*shape[:-1], nout)
+
+            def bwd(self, ctx, dlog):
+                R = ctx.st.x0.shape[0]
+                d16 = torch.zeros((R, 8), dtype=torch.bfloat16, device=dlog.device)
+                d16[:, :nout] = dlog.reshape(R, nout)
+                dx = torch.empty((R, shape[-1]), dtype=torch.bfloat16, device=dlog.device)
+                runner.backward(ctx.st, d16, dx)
+                ctx.st = None
+                return (dx.to(x.dtype).reshape(shape),)
+        return self._call(Impl(), x)
 
     def get_matching_loss(self, image_embeds, image_atts, image_feat, text_ids, text_atts, text_feat, idx=None,
                           return_cross_embeds=False, text_embeds=None, is_pretrain=True):
@@ -832,16 +997,28 @@ class XFMBase(nn.Module):
         # model_vqkd.py:125-131 `if data.max() <= 1: data *= 255`: same data-dependent rule, decided on the device (the
         # reference's host branch costs a device->host sync per step)
         pre_mul = torch.where(image.max() <= 1.0, 255.0, 1.0).to(torch.float32).reshape(1)
-        _, y16, _ = vq.forward(image, train=False, save=False, pre_mul=pre_mul, pool=False)
+        y32, _, _ = vq.forward(image, train=False, save=False, pre_mul=pre_mul, pool=False)
         N, D = vq.N, vq.D
-        t = L.gemm(y16.view(B * N, D), fp.view16("vqkd.encode_task_layer.0.weight"),
-                   bias=fp.view32("vqkd.encode_task_layer.0.bias"), act=3)
-        z = L.gemm(t, fp.view16("vqkd.encode_task_layer.2.weight"), bias=fp.view32("vqkd.encode_task_layer.2.bias"),
+        # encode_task_layer (Linear - Tanh - Linear) runs in fp32 in the reference even under autocast
+        # (model_vqkd.py:154-155): fp32-grade products on the bf16 tensor cores through the three-term operand split
+        w0, w2 = self._task_layer_operands()
+        t = L.gemm(L.split_bf16x3(y32.reshape(B * N, D), 0), w0, bias=fp.view32("vqkd.encode_task_layer.0.bias"),
                    out_dtype=torch.float32)
+        z = L.gemm(L.split_bf16x3(t, 0, act=1), w2, bias=fp.view32("vqkd.encode_task_layer.2.bias"), out_dtype=torch.float32)
         prow = (torch.arange(B, device=image.device).view(B, 1) * N + 1 + torch.arange(N - 1, device=image.device)).reshape(-1)
         zp = L.gather_rows(z, prow.contiguous())
         ids = L.vq_argmin(zp, fp.view32("vqkd.quantize.embedding.weight"))
         return ids.view(B, N - 1)
+
+    def _task_layer_operands(self):
+        """Split-precision copies of the two encode_task_layer weights, rebuilt when the master buffer changes."""
+        fp = self.flat
+        ver = fp.P._version
+        if getattr(self, "_task_ops", None) is None or self._task_ops[0] != ver:
+            w0 = L.split_bf16x3(fp.view32("vqkd.encode_task_layer.0.weight").contiguous(), 1)
+            w2 = L.split_bf16x3(fp.view32("vqkd.encode_task_layer.2.weight").contiguous(), 1)
+            self._task_ops = (ver, w0, w2)
+        return self._task_ops[1], self._task_ops[2]
 
     def get_mim_loss(self, image_embeds_masked, targets, mask_tokens):
         """xfm.py:624-635: CE against VQ-KD ids of the raw image (targets = image), or MSE against the detached
@@ -886,6 +1063,5 @@ class XFMBase(nn.Module):
                 return loss.view(())
 
             def bwd(self, ctx, g):
-                L.scale_by_scalar_(ctx.dx, _up(g))
-                return (ctx.dx,)
+                return (L.scale_by_scalar(ctx.dx, _up(g)),)
         return self._call(ImplMSE(), image_embeds_masked)
