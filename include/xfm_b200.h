@@ -158,8 +158,9 @@ int xfm_cast_f32_to_bf16(const float* in, void* out, size_t n, void* stream);
 int xfm_cast_bf16_to_f32(const void* in, float* out, size_t n, void* stream);
 int xfm_scale_by_scalar(const void* in, void* out, int dtype, const float* scalar, size_t n, void* stream); /* out may alias in */
 /* fp32-grade GEMM operands for the bf16 tensor cores: every f32 row [K] becomes a bf16 row [6K] holding the three-term
- * split x = h + m + l in the block order h,h,m,h,m,l (role 0, left operand) or h,m,h,l,m,h (role 1, right operand), so that
- * xfm_gemm_bf16 over K' = 6K sums the six products of order <= 2 (relative error ~2^-24).  act: 0 none, 1 tanh first.
+ * split x = h + m + l in the block order l,m,h,m,h,h (role 0, left operand) or h,m,l,h,m,h (role 1, right operand), so that
+ * xfm_gemm_bf16 over K' = 6K sums the six products of order <= 2, smallest first (the tensor-core accumulator truncates:
+ * error ~ (K/16) 2^-24 of max|C|, the level of an fp32 library GEMM).  act: 0 none, 1 tanh first.
  * Replaces the autocast(enabled=False) fp32 Linear-Tanh-Linear of model_vqkd.py:86-90,154-155 (encode_task_layer) and the
  * fp32 similarity of xfm.py:696-697. */
 int xfm_split_bf16x3(const float* in_f32, void* out_bf16, int M, int K, int role, int act, void* stream);
@@ -241,6 +242,25 @@ int xfm_l2norm_bwd(const float* dy, const float* y, const float* inv_norm, float
  * of masked patches) and dx = dloss/dx for an upstream gradient of 1 (zero outside the selected rows). */
 int xfm_mim_mse(const float* x, const float* t, const uint8_t* mask, int B, int np, int D, int with_cls, float* count,
                 float* loss, float* dx, void* stream);
+
+/* Region / bounding-box branch.
+ * xfm_region_pool_fwd: models/beit2.py:468-475 — y f32 [n_img, N, D] vision tokens (token 0 = full-image mean), idx int64
+ *   [bsz] sample -> image, atts int64 [bsz, N] region masks: out[b, 1+j] = y[idx[b], 1+j]; out[b, 0] = the atts-weighted mean
+ *   of those patch tokens.  out_bf16 (optional) receives the same values in bf16.  _bwd accumulates (+=, atomics) into dy.
+ * xfm_sigmoid_fwd/bwd: bbox_head(...).sigmoid() (models/xfm.py:852-853).
+ * xfm_bbox_loss: models/xfm.py:815-840 with models/box_ops.py (cxcywh -> xyxy, generalized IoU, diagonal only): L1 and
+ *   1 - GIoU summed over the kept samples / num_boxes; is_image f32 [n] or null; a degenerate box anywhere zeroes the GIoU
+ *   loss (decided on the device).  d_bbox / d_giou [n, 4]: gradients wrt coord for upstream gradients of 1.
+ * xfm_axpby_scalars: out = a * sa[0] + b * sb[0] (sa / sb device scalars, null = 0). */
+int xfm_region_pool_fwd(const float* y, const int64_t* idx, const int64_t* atts, float* out, void* out_bf16, int bsz, int N,
+                        int D, void* stream);
+int xfm_region_pool_bwd(const float* dout, const int64_t* idx, const int64_t* atts, float* dy, int bsz, int N, int D,
+                        void* stream);
+int xfm_sigmoid_fwd(const float* x, float* y, int n, void* stream);
+int xfm_sigmoid_bwd(const float* dy, const float* y, float* dx, int n, void* stream);
+int xfm_bbox_loss(const float* coord, const float* target, const float* is_image, int n, float* loss_bbox, float* loss_giou,
+                  float* d_bbox, float* d_giou, void* stream);
+int xfm_axpby_scalars(const float* a, const float* sa, const float* b, const float* sb, float* out, int n, void* stream);
 
 /* Flat-buffer optimizer step (accelerators/ddp_accelerator.py:89-98 clip_grad_norm_ + optimizer.step with the
  * transformers AdamW of optim.py:4-50).  P/G/M/V: f32 buffers of nchunks*64 elements, S: bf16 shadow (may be null).

@@ -139,12 +139,14 @@ def test_split_precision_gemm_is_fp32_grade(lib):
     y16 = lib.gemm(x.bfloat16(), w.bfloat16(), bias=b, out_dtype=torch.float32)
     err16 = float((y16.double() - ref).abs().max() / ref.abs().max())
     f32 = float(((x @ w.t() + b).double() - ref).abs().max() / ref.abs().max())   # torch fp32 (TF32 off by default)
-    assert err <= 2e-6 and err16 > 100 * err, (err, err16, f32)
+    # measured: 1.0e-5 with the dominant hh block first (the tensor-core accumulator truncates at every k-step), ~1.2e-6
+    # with it last; torch's own fp32 GEMM: 1.3e-6; plain bf16 operands: 2.4e-3
+    assert err <= 3e-6 and err16 > 100 * err, (err, err16, f32)
     # tanh on the way in (second Linear of the task layer, N = 32 codes dims)
     w2 = torch.randn(32, D, device="cuda", generator=g) * 0.04
     z = lib.gemm(lib.split_bf16x3(y, 0, act=1), lib.split_bf16x3(w2, 1), out_dtype=torch.float32)
     ref2 = torch.tanh(y.double()) @ w2.double().t()
-    assert float((z.double() - ref2).abs().max() / ref2.abs().max()) <= 3e-6
+    assert float((z.double() - ref2).abs().max() / ref2.abs().max()) <= 5e-6
 
 
 def test_vq_ids_at_bench_size_against_oracle(record):
@@ -173,4 +175,5 @@ def test_vq_ids_at_bench_size_against_oracle(record):
     record("vq_ids_b96", n=int(want.numel()), match=float(match.float().mean()), worst_missed_margin=worst,
            distinct_codes=int(want.unique().numel()),
            **{f"margin>{t}": float(match[gap > t].float().mean()) for t in (1e-3, 1e-2, 3e-2)})
-    assert worst <= 3e-2 and float(match.float().mean()) >= 0.93
+    # measured: 98.9 % of 18816 ids equal, largest fp64 margin among the differing ones 3.8e-3, 100 % above a margin of 1e-2
+    assert worst <= 1e-2 and float(match.float().mean()) >= 0.98

@@ -141,8 +141,10 @@ def test_vq_ids_end_to_end_against_reference(golden_dir, record, name):
     worst_missed = float(gap[~match].max()) if (~match).any() else 0.0
     record("vq_ids", fixture=name, n=int(want.numel()), match=float(match.float().mean()), worst_missed_margin=worst_missed,
            **rates)
-    assert worst_missed <= 3e-2, worst_missed          # no id with a margin above the bf16 perturbation differs
-    assert float(match.float().mean()) >= 0.93
+    # measured (profiles/r02_parity_measurements.jsonl): tiny 64 / 64; base (B=8) 98.6 % with the largest margin among the
+    # differing ids 3.6e-3; every id whose margin exceeds 1e-2 matches
+    assert worst_missed <= 1e-2, worst_missed          # no id with a margin above the bf16 perturbation differs
+    assert float(match.float().mean()) >= 0.975
 
 
 def test_mim_masks_bit_exact_through_the_module(golden_dir):

@@ -123,10 +123,11 @@ def test_two_optimizer_steps_against_oracle(record):
         acc.backward_step(total, opt)
         norm = acc.optimizer_step(opt, wrapped)
         hist.append((float(total), float(ref_total), float(norm), float(ref_norm)))
-        # step 1: the north_star bound.  step 2: Adam's first update is lr * g / (|g| + eps) = lr * sign(g), so parameters
-        # whose gradient is bf16 noise move by +-lr in a direction the fp32 oracle need not share; measured and recorded.
-        tol = 2e-3 if step == 0 else 1e-2
+        # north_star: 1e-3 relative.  Measured (profiles/r02_parity_measurements.jsonl): step 1 itc 1.1e-3 (temp = 0.07
+        # multiplies the bf16 feature error by 14 on this 4-pair batch), itm 2.9e-4, mlm 5e-6, mim 6e-6; step 2 (after one
+        # clip + AdamW update on both sides) itc 4.4e-4, itm 5.3e-4, mlm 1.6e-4, mim 2.7e-5.
         for k in keys:
+            tol = 2e-3 if k == "loss_itc" else 1e-3
             rel = abs(float(out[k]) - float(ref[k])) / max(1.0, abs(float(ref[k])))
             record("loss_rel_err", step=step + 1, loss=k, mine=float(out[k]), oracle=float(ref[k]), rel=rel)
             assert rel <= tol, (step, k, float(out[k]), float(ref[k]))
@@ -147,7 +148,7 @@ def test_two_optimizer_steps_against_oracle(record):
     (t1, r1, _, _), (t2, r2, _, _) = hist
     record("total_loss", step1=t1, step1_oracle=r1, step2=t2, step2_oracle=r2)
     assert abs(r2 - r1) > 1e-2 and abs((t2 - t1) - (r2 - r1)) <= 0.1 * abs(r2 - r1), hist
-    assert abs(t2 - r2) <= 5e-3 * max(1.0, abs(r2)), hist
+    assert abs(t2 - r2) <= 1e-3 * max(1.0, abs(r2)), hist
 
 
 def test_nlvr_heads_are_updated_by_the_flat_optimizer():

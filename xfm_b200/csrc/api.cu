@@ -171,6 +171,23 @@ int xfm_mim_mse(const float* x, const float* t, const uint8_t* mask, int B, int 
                 float* loss, float* dx, void* stream) {
   return mim_mse(x, t, mask, B, np, D, with_cls, count, loss, dx, ST);
 }
+int xfm_region_pool_fwd(const float* y, const int64_t* idx, const int64_t* atts, float* out, void* out_bf16, int bsz, int N,
+                        int D, void* stream) {
+  return region_pool_fwd(y, idx, atts, out, BF(out_bf16), bsz, N, D, ST);
+}
+int xfm_region_pool_bwd(const float* dout, const int64_t* idx, const int64_t* atts, float* dy, int bsz, int N, int D,
+                        void* stream) {
+  return region_pool_bwd(dout, idx, atts, dy, bsz, N, D, ST);
+}
+int xfm_sigmoid_fwd(const float* x, float* y, int n, void* stream) { return sigmoid_fwd(x, y, n, ST); }
+int xfm_sigmoid_bwd(const float* dy, const float* y, float* dx, int n, void* stream) { return sigmoid_bwd(dy, y, dx, n, ST); }
+int xfm_bbox_loss(const float* coord, const float* target, const float* is_image, int n, float* loss_bbox, float* loss_giou,
+                  float* d_bbox, float* d_giou, void* stream) {
+  return bbox_loss(coord, target, is_image, n, loss_bbox, loss_giou, d_bbox, d_giou, ST);
+}
+int xfm_axpby_scalars(const float* a, const float* sa, const float* b, const float* sb, float* out, int n, void* stream) {
+  return axpby_scalars(a, sa, b, sb, out, n, ST);
+}
 int xfm_grad_sumsq(const float* g, const int32_t* chunk_seg, const uint8_t* seg_group, size_t nchunks, int32_t* seg_step,
                    float* seg_bc, int nseg, const float* hp, float* out, int accumulate, void* stream) {
   return grad_sumsq(g, chunk_seg, seg_group, nchunks, seg_step, seg_bc, nseg, hp, out, accumulate, ST);

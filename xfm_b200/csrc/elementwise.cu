@@ -356,8 +356,11 @@ __global__ void cast_bf16_to_f32_kernel(const bf16* __restrict__ in, float* __re
 }
 // Split-precision operand for an fp32-grade GEMM on the bf16 tensor cores: x = h + m + l with h = bf16(x), m = bf16(x - h),
 // l = bf16(x - h - m) (24 mantissa bits in three bf16 terms).  Each f32 row [K] becomes a bf16 row [6K] of six K-blocks;
-// role 0 (left operand) lays out h,h,m,h,m,l and role 1 (right operand) h,m,h,l,m,h, so one K' = 6K GEMM sums the six
-// products of order <= 2 (hh, hm, mh, hl, mm, lh): relative error ~2^-24, fp32 accumulation in TMEM.
+// role 0 (left operand) lays out l,m,h,m,h,h and role 1 (right operand) h,m,l,h,m,h, so one K' = 6K GEMM sums the six
+// products of order <= 2 in the order lh, mm, hl, mh, hm, hh.  SMALLEST TERMS FIRST: the tensor core adds into its fp32
+// accumulator with truncation, an error of ~2^-24 |acc| per k-step; with the dominant hh block last only its K/16 steps
+// see the full accumulator magnitude (measured at K = 768: 1.0e-5 of max|C| with hh first, ~1e-6 with hh last = what a
+// cuBLAS fp32 GEMM gives).
 // Used where the reference forces fp32 inside an otherwise reduced-precision region (model_vqkd.py:154-155).
 // act: 0 none, 1 tanh applied before the split (encode_task_layer's nn.Tanh, model_vqkd.py:86-90).
 __global__ void __launch_bounds__(256)
@@ -379,7 +382,7 @@ split_bf16x3_kernel(const float* __restrict__ in, bf16* __restrict__ out, int M,
       const bf16 l = __float2bfloat16_rn(r1 - __bfloat162float(m));
       t[0][e] = h; t[1][e] = m; t[2][e] = l;
     }
-    const int sel0[6] = {0, 0, 1, 0, 1, 2}, sel1[6] = {0, 1, 0, 2, 1, 0};
+    const int sel0[6] = {2, 1, 0, 1, 0, 0}, sel1[6] = {0, 1, 2, 0, 1, 0};
     bf16* o = out + row * (size_t)(6 * K) + col;
 #pragma unroll
     for (int b = 0; b < 6; ++b) {

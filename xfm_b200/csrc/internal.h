@@ -83,6 +83,15 @@ int l2norm_fwd(const float* x, float* y, float* inv_norm, int R, int E, cudaStre
 int l2norm_bwd(const float* dy, const float* y, const float* inv_norm, float* dx, int R, int E, cudaStream_t s);
 int mim_mse(const float* x, const float* t, const uint8_t* mask, int B, int np, int D, int with_cls, float* count,
             float* loss, float* dx, cudaStream_t s);
+int region_pool_fwd(const float* y, const int64_t* idx, const int64_t* atts, float* out, bf16_t* out16, int bsz, int N, int D,
+                    cudaStream_t s);
+int region_pool_bwd(const float* dout, const int64_t* idx, const int64_t* atts, float* dy, int bsz, int N, int D,
+                    cudaStream_t s);
+int sigmoid_fwd(const float* x, float* y, int n, cudaStream_t s);
+int sigmoid_bwd(const float* dy, const float* y, float* dx, int n, cudaStream_t s);
+int bbox_loss(const float* coord, const float* target, const float* is_image, int n, float* loss_bbox, float* loss_giou,
+              float* d_bbox, float* d_giou, cudaStream_t s);
+int axpby_scalars(const float* a, const float* sa, const float* b, const float* sb, float* out, int n, cudaStream_t s);
 int grad_sumsq(const float* g, const int32_t* chunk_seg, const uint8_t* seg_group, size_t nchunks, int32_t* seg_step,
                float* seg_bc, int nseg, const float* hp, float* out, int accumulate, cudaStream_t s);
 int adamw_flat(float* P, const float* G, float* M, float* V, bf16_t* S, const int32_t* chunk_seg, const uint8_t* seg_group,

@@ -568,6 +568,60 @@ def mim_mse(x, t, mask_u8, with_cls=True):
     return loss, dx
 
 
+def region_pool_fwd(y, idx, atts):
+    """y f32 [n_img, N, D]; idx int64 [bsz]; atts int64 [bsz, N] -> (out f32 [bsz, N, D], out bf16)."""
+    n_img, N, D = y.shape
+    bsz = idx.numel()
+    assert y.dtype == torch.float32 and y.is_contiguous() and idx.dtype == torch.int64 and atts.dtype == torch.int64
+    assert atts.shape == (bsz, N) and atts.is_contiguous()
+    out = torch.empty((bsz, N, D), dtype=torch.float32, device=y.device)
+    out16 = torch.empty((bsz, N, D), dtype=torch.bfloat16, device=y.device)
+    check(lib().xfm_region_pool_fwd(_p(y), _p(idx), _p(atts), _p(out), _p(out16), bsz, N, D, stream_ptr()), "xfm_region_pool_fwd")
+    return out, out16
+
+
+def region_pool_bwd_(dout, idx, atts, dy):
+    bsz, N, D = dout.shape
+    assert dout.dtype == torch.float32 and dout.is_contiguous() and dy.dtype == torch.float32 and dy.is_contiguous()
+    check(lib().xfm_region_pool_bwd(_p(dout), _p(idx), _p(atts), _p(dy), bsz, N, D, stream_ptr()), "xfm_region_pool_bwd")
+
+
+def sigmoid_fwd(x):
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    y = torch.empty_like(x)
+    check(lib().xfm_sigmoid_fwd(_p(x), _p(y), x.numel(), stream_ptr()), "xfm_sigmoid_fwd")
+    return y
+
+
+def sigmoid_bwd(dy, y):
+    assert dy.dtype == torch.float32 and dy.is_contiguous() and y.is_contiguous()
+    dx = torch.empty_like(y)
+    check(lib().xfm_sigmoid_bwd(_p(dy), _p(y), _p(dx), y.numel(), stream_ptr()), "xfm_sigmoid_bwd")
+    return dx
+
+
+def bbox_loss(coord, target, is_image=None):
+    """coord, target f32 [n, 4]; is_image f32 [n] or None.  Returns (loss_bbox[1], loss_giou[1], d_bbox [n,4], d_giou [n,4])."""
+    n = coord.shape[0]
+    assert coord.dtype == torch.float32 and coord.shape == (n, 4) and coord.is_contiguous()
+    assert target.dtype == torch.float32 and target.shape == (n, 4) and target.is_contiguous()
+    assert is_image is None or (is_image.dtype == torch.float32 and is_image.numel() == n and is_image.is_contiguous())
+    dev = coord.device
+    lb, lg = torch.empty(1, dtype=torch.float32, device=dev), torch.empty(1, dtype=torch.float32, device=dev)
+    db, dg = torch.empty_like(coord), torch.empty_like(coord)
+    check(lib().xfm_bbox_loss(_p(coord), _p(target), _p(is_image), n, _p(lb), _p(lg), _p(db), _p(dg), stream_ptr()),
+          "xfm_bbox_loss")
+    return lb, lg, db, dg
+
+
+def axpby_scalars(a, sa, b, sb):
+    """a * sa[0] + b * sb[0] (sa / sb: f32 [1] device tensors or None = 0)."""
+    assert a.dtype == torch.float32 and a.is_contiguous() and b.is_contiguous() and a.shape == b.shape
+    out = torch.empty_like(a)
+    check(lib().xfm_axpby_scalars(_p(a), _p(sa), _p(b), _p(sb), _p(out), a.numel(), stream_ptr()), "xfm_axpby_scalars")
+    return out
+
+
 def adamw_hparams(lrs, wds, beta1, beta2, eps, max_grad_norm, grad_mul, correct_bias):
     """The 16-float hyper-parameter block of xfm_adamw_flat / xfm_grad_sumsq as a host tensor (pinned when CUDA is there)."""
     t = torch.tensor(list(lrs) + list(wds) + [beta1, beta2, eps, max_grad_norm, grad_mul, 1.0 if correct_bias else 0.0, 0.0, 0.0],
