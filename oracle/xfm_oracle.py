@@ -809,6 +809,118 @@ def make_vqa_batch(cfg, B=3, L=12, La=6, n_cand=7, seed=11):
 
 
 # ----------------------------------------------------------------------------------------------
+# region / bounding-box branch (models/xfm.py:574-597,815-854, models/beit2.py:468-475, models/box_ops.py)
+# ----------------------------------------------------------------------------------------------
+
+
+def vision_forward_region(image, idx_to_group_img, image_atts, sd, cfg):
+    """beit2.py:468-475 + xfm.py:588-597: (region-pooled embeds [bsz, 1+np, D], full-image embeds gathered to [bsz, ...])."""
+    full = vision_forward(image, sd, cfg)
+    x = full[:, 1:]
+    x_bs = x[idx_to_group_img]
+    weights = image_atts[:, 1:].unsqueeze(2)
+    x_bs_cls = torch.sum(weights * x_bs, dim=1, keepdim=True) / torch.sum(weights, dim=1, keepdim=True)
+    return torch.cat([x_bs_cls, x_bs], dim=1), full[idx_to_group_img]
+
+
+def box_cxcywh_to_xyxy(x):
+    """box_ops.py:10-14."""
+    x_c, y_c, w, h = x.unbind(-1)
+    return torch.stack([x_c - 0.5 * w, y_c - 0.5 * h, x_c + 0.5 * w, y_c + 0.5 * h], dim=-1)
+
+
+def generalized_box_iou(boxes1, boxes2):
+    """box_ops.py:25-58 (pairwise [N, M])."""
+    area1 = (boxes1[:, 2] - boxes1[:, 0]) * (boxes1[:, 3] - boxes1[:, 1])
+    area2 = (boxes2[:, 2] - boxes2[:, 0]) * (boxes2[:, 3] - boxes2[:, 1])
+    lt = torch.max(boxes1[:, None, :2], boxes2[:, :2])
+    rb = torch.min(boxes1[:, None, 2:], boxes2[:, 2:])
+    wh = (rb - lt).clamp(min=0)
+    inter = wh[:, :, 0] * wh[:, :, 1]
+    union = area1[:, None] + area2 - inter
+    iou = inter / union
+    lt = torch.min(boxes1[:, None, :2], boxes2[:, :2])
+    rb = torch.max(boxes1[:, None, 2:], boxes2[:, 2:])
+    wh = (rb - lt).clamp(min=0)
+    area = wh[:, :, 0] * wh[:, :, 1]
+    return iou - (area - union) / area
+
+
+def bbox_loss(output_coord, target_bbox, is_image=None):
+    """models/xfm.py:815-840."""
+    loss_bbox = F.l1_loss(output_coord, target_bbox, reduction="none")
+    boxes1, boxes2 = box_cxcywh_to_xyxy(output_coord), box_cxcywh_to_xyxy(target_bbox)
+    if (boxes1[:, 2:] < boxes1[:, :2]).any() or (boxes2[:, 2:] < boxes2[:, :2]).any():
+        loss_giou = torch.zeros(output_coord.size(0), device=output_coord.device)
+    else:
+        loss_giou = 1 - torch.diag(generalized_box_iou(boxes1, boxes2))
+    if is_image is None:
+        num_boxes = target_bbox.size(0)
+    else:
+        num_boxes = torch.sum(1 - is_image)
+        loss_bbox = loss_bbox * (1 - is_image.view(-1, 1))
+        loss_giou = loss_giou * (1 - is_image)
+    return loss_bbox.sum() / num_boxes, loss_giou.sum() / num_boxes
+
+
+def predict_bbox(image_embeds_full, text_embeds, text_atts, sd, cfg, is_pretrain=True):
+    """models/xfm.py:843-854."""
+    ones = torch.ones(image_embeds_full.shape[:2], dtype=torch.long, device=image_embeds_full.device)
+    te = text_embeds.detach() if is_pretrain else text_embeds
+    cls = fusion_forward(te, text_atts, image_embeds_full, ones, sd, cfg)[:, 0, :]
+    return itm_head(cls, sd, name="bbox_head").sigmoid()
+
+
+def pretrain_forward_region(sd, cfg, batch, image_neg_idx, text_neg_idx, collect=None):
+    """models/model_pretrain.py:30-91 on a region batch (ret_bbox_loss = ret_bbox_giou = True, no MIM): batch carries
+    idx_to_group_img [bsz], image_atts [bsz, 1+np], target_bbox [bsz, 4], is_image [bsz] besides the text tensors."""
+    temp = sd["temp"].clamp(cfg["min_temp"], cfg["max_temp"])
+    c = collect if collect is not None else {}
+    image_atts = batch["image_atts"]
+    image_embeds, image_full = vision_forward_region(batch["image"], batch["idx_to_group_img"], image_atts, sd, cfg)
+    text_embeds = text_forward(batch["text_ids"], batch["text_atts"], sd, cfg)
+    image_feat, text_feat = get_features(image_embeds, text_embeds, sd)
+    c["image_embeds"], c["image_embeds_fullatts"], c["image_feat"] = image_embeds, image_full, image_feat
+    loss_itc = contrastive_loss(image_feat, text_feat, temp)
+    loss_itm, _ = matching_loss(image_embeds, image_atts, text_embeds, batch["text_atts"], image_neg_idx, text_neg_idx, sd, cfg)
+    loss_mlm = fuse_mlm_loss(batch["text_ids_masked"], batch["text_atts"], image_embeds, image_atts, batch["masked_pos"],
+                             batch["masked_ids"], sd, cfg)
+    coord = predict_bbox(image_full, text_embeds, batch["text_atts"], sd, cfg)
+    c["output_coord"] = coord
+    loss_bbox, loss_giou = bbox_loss(coord, batch["target_bbox"], batch.get("is_image"))
+    return dict(loss_itc=loss_itc, loss_itm=loss_itm, loss_mlm=loss_mlm, loss_bbox=loss_bbox, loss_giou=loss_giou)
+
+
+def make_region_batch(cfg, n_img=3, bsz=6, L=24, M=6, seed=31):
+    """Synthetic region batch in the layout of dataset/pretrain_dataset.py's region collate (Pretrain.py:93-99): several
+    samples per image, rectangular region masks over the patch grid (position 0 = cls, always visible), boxes in cxcywh."""
+    base = make_batch(cfg, bsz, L=L, M=M, seed=seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    ws = cfg["image_res"] // cfg["patch_size"]
+    image = torch.randn(n_img, 3, cfg["image_res"], cfg["image_res"], generator=g)
+    idx = torch.arange(bsz) * n_img // bsz
+    atts = torch.zeros(bsz, ws * ws + 1, dtype=torch.long)
+    atts[:, 0] = 1
+    target = torch.zeros(bsz, 4)
+    is_image = torch.zeros(bsz, dtype=torch.long)
+    for b in range(bsz):
+        if b % 3 == 2:   # a whole-image caption among the region samples
+            atts[b] = 1
+            target[b] = torch.tensor([0.5, 0.5, 1.0, 1.0])
+            is_image[b] = 1
+            continue
+        x0, y0 = int(torch.randint(0, ws - 1, (1,), generator=g)), int(torch.randint(0, ws - 1, (1,), generator=g))
+        x1, y1 = int(torch.randint(x0 + 1, ws + 1, (1,), generator=g)), int(torch.randint(y0 + 1, ws + 1, (1,), generator=g))
+        grid = torch.zeros(ws, ws, dtype=torch.long)
+        grid[y0:y1, x0:x1] = 1
+        atts[b, 1:] = grid.reshape(-1)
+        target[b] = torch.tensor([(x0 + x1) / 2 / ws, (y0 + y1) / 2 / ws, (x1 - x0) / ws, (y1 - y0) / ws])
+    out = dict(base)
+    out.update(image=image, idx_to_group_img=idx, image_atts=atts, target_bbox=target, is_image=is_image)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
 # whole pre-training forward (models/model_pretrain.py:30-91)
 # ----------------------------------------------------------------------------------------------
 

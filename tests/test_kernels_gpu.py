@@ -791,3 +791,51 @@ def test_vq_argmin_bit_exact(lib):
     # empty / ragged row counts
     assert lib.vq_argmin(zr[:1].contiguous().cuda(), code.cuda()).cpu()[0] == ids[0]
     assert torch.equal(lib.vq_argmin(zr[:131].contiguous().cuda(), code.cuda()).cpu(), ids[:131])
+
+
+def test_bbox_loss_and_region_pool_kernels_against_torch(lib):
+    """xfm_bbox_loss (xfm.py:815-840 + box_ops.py) values and gradients against autograd of the oracle's restatement — with
+    and without is_image, and the degenerate-box early-out; xfm_region_pool_fwd / _bwd (beit2.py:468-475) against torch."""
+    L = lib
+    g = torch.Generator().manual_seed(9)
+    n = 37
+    coord = torch.rand(n, 4, generator=g) * 0.5 + 0.2
+    target = torch.rand(n, 4, generator=g) * 0.5 + 0.2
+    is_image = (torch.rand(n, generator=g) < 0.3).float()
+    for keep in (None, is_image):
+        c = coord.clone().requires_grad_(True)
+        lb, lg = O.bbox_loss(c, target, keep)
+        gb, = torch.autograd.grad(lb, c, retain_graph=True)
+        gg, = torch.autograd.grad(lg, c)
+        mlb, mlg, db, dg = L.bbox_loss(coord.cuda(), target.cuda(), None if keep is None else keep.cuda())
+        assert abs(float(mlb) - float(lb)) <= 1e-5 and abs(float(mlg) - float(lg)) <= 1e-5
+        torch.testing.assert_close(db.cpu(), gb, rtol=1e-4, atol=1e-6)
+        torch.testing.assert_close(dg.cpu(), gg, rtol=1e-3, atol=1e-5)
+        up_b, up_g = torch.tensor([0.5], device="cuda"), torch.tensor([2.0], device="cuda")
+        torch.testing.assert_close(L.axpby_scalars(db, up_b, dg, up_g).cpu(), 0.5 * gb + 2.0 * gg, rtol=1e-3, atol=1e-5)
+    bad = coord.clone()
+    bad[5, 2] = -0.1
+    _, mlg, _, dg = L.bbox_loss(bad.cuda(), target.cuda(), None)
+    assert float(mlg) == 0.0 and float(dg.abs().max()) == 0.0
+    y = torch.sigmoid(coord)
+    torch.testing.assert_close(L.sigmoid_fwd(coord.cuda()).cpu(), y, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(L.sigmoid_bwd(target.cuda(), y.cuda()).cpu(), target * y * (1 - y), rtol=1e-5, atol=1e-6)
+    # region pooling
+    n_img, N, D, bsz = 3, 17, 128, 7
+    yv = torch.randn(n_img, N, D, generator=g)
+    idx = torch.tensor([0, 0, 1, 2, 2, 2, 1])
+    atts = (torch.rand(bsz, N, generator=g) < 0.5).long()
+    atts[:, 0] = 1
+    atts[:, 1] = 1
+    yr = yv.clone().requires_grad_(True)
+    x_bs = yr[:, 1:][idx]
+    w = atts[:, 1:].unsqueeze(2)
+    ref = torch.cat([(w * x_bs).sum(1, keepdim=True) / w.sum(1, keepdim=True), x_bs], 1)
+    out, out16 = L.region_pool_fwd(yv.cuda(), idx.cuda(), atts.cuda())
+    torch.testing.assert_close(out.cpu(), ref.detach(), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(out16.float().cpu(), ref.detach(), rtol=1e-2, atol=1e-2)
+    dout = torch.randn(bsz, N, D, generator=g)
+    ref.backward(dout)
+    dy = torch.zeros(n_img, N, D, device="cuda")
+    L.region_pool_bwd_(dout.cuda(), idx.cuda(), atts.cuda(), dy)
+    torch.testing.assert_close(dy.cpu(), yr.grad, rtol=1e-4, atol=1e-5)

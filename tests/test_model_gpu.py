@@ -321,6 +321,39 @@ def test_text_only_mlm_stream_against_oracle(record):
         assert params[n].grad is None, n     # nothing outside the text encoder takes part (xfm.py:805-812)
 
 
+def test_region_branch_against_reference(golden_dir, record):
+    """the region / bbox branch of the pre-training forward (model_pretrain.py:39-41,81-86) against the fixture
+    the UNMODIFIED reference produced — idx_to_group_img gather + region-weighted pooling (beit2.py:468-475), region masks as
+    cross-attention key masks, predict_bbox, L1 + GIoU (xfm.py:815-854) — losses, embeddings, boxes and gradients."""
+    from xfm_b200.model_pretrain import XFM
+    g = _load(golden_dir, "tiny_region.pt")
+    cfg = g["cfg"]
+    model = XFM(dict(cfg), init=lambda n, s: O.make_tensor(n, s, 0), device="cuda").eval()
+    b = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in O.make_region_batch(cfg).items()}
+    with torch.no_grad():
+        emb, atts, full = model.get_vision_embeds(b["image"], image_atts=b["image_atts"], idx_to_group_img=b["idx_to_group_img"])
+        only_full, ones = model.get_vision_embeds(b["image"], idx_to_group_img=b["idx_to_group_img"])
+    assert atts is b["image_atts"] and bool((ones == 1).all())
+    assert _maxabs(emb, g["image_embeds"]) <= 2e-2 and _maxabs(full, g["image_embeds_fullatts"]) <= 2e-2
+    assert _maxabs(only_full, g["image_embeds_fullatts"]) <= 2e-2
+    for fuse in (True, False):
+        model.zero_grad()
+        model.fuse_itm_mlm = fuse
+        model._forced_negatives = (g["image_neg_idx"], g["text_neg_idx"])
+        out = model(b["image"], b["text_ids"], b["text_atts"], text_ids_masked=b["text_ids_masked"], masked_pos=b["masked_pos"],
+                    masked_ids=b["masked_ids"], image_atts=b["image_atts"], idx_to_group_img=b["idx_to_group_img"],
+                    target_bbox=b["target_bbox"], is_image=b["is_image"], ret_mim_loss=True, ret_bbox_loss=True,
+                    ret_bbox_giou=True, data_source="region")
+        assert float(out["loss_mim"]) == 0.0
+        for k in ("loss_itc", "loss_itm", "loss_mlm", "loss_bbox", "loss_giou"):
+            rel = abs(float(out[k]) - g["losses"][k]) / max(1.0, abs(g["losses"][k]))
+            record("region_loss", fused=fuse, loss=k, mine=float(out[k]), reference=g["losses"][k], rel=rel)
+            assert rel <= (2e-3 if k == "loss_itc" else 1e-3), (fuse, k, float(out[k]), g["losses"][k])
+        total = out["loss_itc"] + out["loss_itm"] + out["loss_mlm"] + out["loss_bbox"] + out["loss_giou"]
+        total.backward()
+        _grad_check(model, g["grads"], list(g["grads"]))
+
+
 def test_retrieval_model_against_oracle():
     """models/model_retrieval.py:26-37 (BASELINE config #3 shape, tiny widths): ITC with idx soft labels + idx-masked
     hard-negative ITM, text gradients through the fusion encoder (is_pretrain=False)."""

@@ -145,3 +145,30 @@ def test_vqa_decoder_against_reference(golden_dir):
         ids, probs = O.vqa_rank(b["image"], b["q_ids"], b["q_atts"], b["cand_ids"], b["cand_atts"], g["k_test"], sd, cfg)
     assert torch.equal(ids, g["topk_ids"])
     torch.testing.assert_close(probs, g["topk_probs"], rtol=1e-4, atol=1e-7)
+
+
+def test_region_branch_against_reference(golden_dir):
+    """Region / bbox branch (model_pretrain.py:39-41,81-86; xfm.py:574-597,815-854; beit2.py:468-475; box_ops.py): the five
+    losses, region-pooled embeddings, predicted boxes and gradients of the restatement equal the reference's."""
+    g = _load(golden_dir, "tiny_region.pt")
+    cfg = g["cfg"]
+    sd = O.make_state_dict(cfg, seed=0)
+    for v in sd.values():
+        if v.dtype.is_floating_point:
+            v.requires_grad_(True)
+    batch = O.make_region_batch(cfg)
+    col = {}
+    out = O.pretrain_forward_region(sd, cfg, batch, g["image_neg_idx"], g["text_neg_idx"], collect=col)
+    for k, v in out.items():
+        assert abs(float(v) - g["losses"][k]) <= 2e-5 * max(1.0, abs(g["losses"][k])), (k, float(v), g["losses"][k])
+    assert g["losses"]["loss_mim"] == 0.0          # no MIM on region batches (model_pretrain.py:67)
+    torch.testing.assert_close(col["image_embeds"], g["image_embeds"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(col["image_embeds_fullatts"], g["image_embeds_fullatts"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(col["output_coord"], g["output_coord"], rtol=1e-5, atol=1e-6)
+    sum(out.values()).backward()
+    for n, ref in g["grads"].items():
+        assert float((sd[n].grad - ref).abs().max()) <= 1e-5 * float(ref.abs().max()) + 1e-9, n
+    # degenerate boxes zero the GIoU term for the whole batch (xfm.py:825-828); is_image rows are excluded from both terms
+    coord = torch.tensor([[0.5, 0.5, 0.2, 0.2], [0.3, 0.3, -0.1, 0.2]])
+    lb, lg = O.bbox_loss(coord, torch.tensor([[0.5, 0.5, 0.2, 0.2], [0.3, 0.3, 0.1, 0.2]]))
+    assert float(lg) == 0.0 and abs(float(lb) - 0.1) < 1e-7

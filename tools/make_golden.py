@@ -10,6 +10,8 @@ What is recorded (all produced by the reference's own code, through oracle/ref_s
                    of every layer's activations (full tensors would be ~100 MB).
   * itc_idx.pt   — get_contrastive_loss / get_hard_negatives with `idx` (retrieval soft labels).
   * masks.pt     — MaskingGenerator outputs for fixed (random, np.random) seeds.
+  * tiny_region.pt — the region / bbox branch of the pre-training forward (idx_to_group_img, region masks, L1 + GIoU):
+                   `python tools/make_golden.py --only-region`.
   * tiny_vqa.pt  — XFMForVQA (models/model_generation.py), tiny config with a 2-layer causal decoder: training loss,
                    per-answer losses, question states, parameter gradients; rank_answer ids / probabilities.
                    `python tools/make_golden.py --only-vqa` regenerates just this file.
@@ -252,12 +254,70 @@ def vqa_golden():
 BASE_B = 8
 
 
+def region_golden():
+    """Region / bbox branch (model_pretrain.py:39-41,81-86; xfm.py:574-597,815-854) on the tiny config: the five losses, the
+    region-pooled and full-image embeddings, predicted boxes, hard-negative picks and a few gradients."""
+    cfg = O.tiny_config()
+    sd = O.make_state_dict(cfg, seed=0)
+    model = ref_shim.build_reference_xfm(cfg, O.expand_tied(sd, cfg))
+    batch = O.make_region_batch(cfg)
+    rec, calls = {}, []
+    orig_multinomial = torch.multinomial
+
+    def fake_multinomial(w, n, *a, **k):
+        calls.append(w.detach().clone())
+        return torch.argmax(w).view(1)
+
+    orig_vis = model.get_vision_embeds
+
+    def spy_vis(*a, **k):
+        out = orig_vis(*a, **k)
+        if len(out) == 3 and k.get("idx_to_group_img") is not None:
+            rec["image_embeds"], rec["image_embeds_fullatts"] = out[0].detach().clone(), out[2].detach().clone()
+        return out
+
+    orig_pred = model.predict_bbox
+
+    def spy_pred(*a, **k):
+        out = orig_pred(*a, **k)
+        rec["output_coord"] = out.detach().clone()
+        return out
+
+    model.get_vision_embeds, model.predict_bbox = spy_vis, spy_pred
+    torch.multinomial = fake_multinomial
+    try:
+        model.zero_grad()
+        loss = model(batch["image"], batch["text_ids"], batch["text_atts"], text_ids_masked=batch["text_ids_masked"],
+                     masked_pos=batch["masked_pos"], masked_ids=batch["masked_ids"], image_atts=batch["image_atts"],
+                     idx_to_group_img=batch["idx_to_group_img"], target_bbox=batch["target_bbox"], is_image=batch["is_image"],
+                     ret_mim_loss=True, ret_bbox_loss=True, ret_bbox_giou=True, data_source="region")
+        total = loss["loss_itc"] + loss["loss_itm"] + loss["loss_mlm"] + loss["loss_bbox"] + loss["loss_giou"]
+        total.backward()
+    finally:
+        torch.multinomial = orig_multinomial
+    B = batch["text_ids"].shape[0]
+    w_t2i, w_i2t = torch.stack(calls[:B], 0), torch.stack(calls[B:2 * B], 0)
+    names = ["bbox_head.0.weight", "bbox_head.3.bias", "itm_head.0.weight", "vision_proj.weight", "temp",
+             "vision_encoder.blocks.1.mlp.fc2.weight", "vision_encoder.blocks.0.attn.qkv.weight", "vision_encoder.fc_norm.weight",
+             "fusion_encoder.roberta.encoder.layer.1.crossattention.self.key.weight",
+             "fusion_encoder.roberta.encoder.layer.0.crossattention.self.value.bias",
+             "text_encoder.roberta.encoder.layer.1.output.dense.weight"]
+    params = dict(model.named_parameters())
+    return dict(cfg=cfg, losses={k: float(v) for k, v in loss.items()}, image_neg_idx=torch.argmax(w_t2i, 1),
+                text_neg_idx=torch.argmax(w_i2t, 1), grads={n: params[n].grad.detach().clone() for n in names}, **rec)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     if "--only-vqa" in sys.argv:
         v = vqa_golden()
         torch.save(v, os.path.join(GOLD, "tiny_vqa.pt"))
         print("tiny_vqa", v["loss"], v["topk_ids"].tolist())
+        return
+    if "--only-region" in sys.argv:
+        r = region_golden()
+        torch.save(r, os.path.join(GOLD, "tiny_region.pt"))
+        print("tiny_region", r["losses"])
         return
     if "--only-base" in sys.argv:
         torch.set_num_threads(os.cpu_count())
@@ -272,6 +332,7 @@ def main():
     torch.save(masks_golden(), os.path.join(GOLD, "masks.pt"))
     torch.save(itc_idx_golden(), os.path.join(GOLD, "itc_idx.pt"))
     torch.save(vqa_golden(), os.path.join(GOLD, "tiny_vqa.pt"))
+    torch.save(region_golden(), os.path.join(GOLD, "tiny_region.pt"))
     tv = run_reference(O.tiny_config(use_vision_tokenizer=True), B=4, L=24, M=6, image_uniform=True, want_grads=True)
     torch.save(tv, os.path.join(GOLD, "tiny_vq.pt"))
     print("tiny_vq", tv["losses"])

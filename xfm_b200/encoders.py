@@ -366,7 +366,7 @@ class RobertaStack:
 
     def layers_bwd(self, st, dh, d_enc=None, need_dh=True, kv_offsets=None, kv_samples=None):
         """dh: bf16 / f32 [Bt*Lt, D].  d_enc: f32 [Benc*Lenc, Denc] accumulator (cross-attention K/V input gradient)."""
-        if kv_samples is None and st.kv_index is not None:
+        if kv_samples is None:   # CSR built in layers_fwd (identity when every sample has its own image)
             kv_offsets, kv_samples = st.kv_offsets, st.kv_samples
         for i in reversed(range(self.layers)):
             last = i == 0

@@ -3,7 +3,8 @@
 Same constructor, forward signature, loss dictionary and loss weighting as the reference class; the reference's own
 models/model_pretrain.py also runs unchanged against xfm_b200.XFMBase — this mirror exists so
 the package is usable where the reference tree is absent (the GPU box, bench.py, tests).
-The region / bbox branch (ret_bbox_loss, ret_bbox_giou) is outside the built hot path.
+The region / bbox branch (ret_bbox_loss, ret_bbox_giou: idx_to_group_img gather, region-weighted pooling, L1 + GIoU box
+losses) follows model_pretrain.py:39-41,81-86.
 """
 import torch
 
@@ -25,16 +26,20 @@ class XFM(XFMBase):
         self.max_temp = config.get("max_temp", 0.5)
 
     def forward_multimodal(self, image, text_ids, text_atts, text_ids_masked=None, masked_pos=None, masked_ids=None,
+                           text_ids_2=None, text_atts_2=None, text_ids_masked_2=None, masked_pos_2=None, masked_ids_2=None,
+                           image_atts=None, idx_to_group_img=None, target_bbox=None, is_image=None,
                            ret_mim_loss=False, ret_bbox_loss=False, ret_match_loss=True, ret_mlm_loss=True,
-                           ret_bbox_giou=False, ret_itc_loss=True, data_source=None, **unused):
-        if ret_bbox_loss or ret_bbox_giou:
-            raise NotImplementedError("region / bbox branch is outside the built hot path")
+                           ret_bbox_giou=False, ret_itc_loss=True, data_source=None):
         if self.learnable_temp:
             self.clamp_temp(self.min_temp, self.max_temp)
         wmap = self.weights_map
-        image_embeds, image_atts = self.get_vision_embeds(image)
+        if ret_bbox_loss:   # region data: fewer images than samples, per-sample region masks (model_pretrain.py:39-41)
+            image_embeds, image_atts, image_embeds_fullatts = \
+                self.get_vision_embeds(image, image_atts=image_atts, idx_to_group_img=idx_to_group_img)
+        else:
+            image_embeds, image_atts = self.get_vision_embeds(image)
         zero = torch.tensor(0.0)
-        loss_itc = loss_itm = loss_mlm = loss_mim = zero
+        loss_itc = loss_itm = loss_mlm = loss_mim = loss_bbox = loss_giou = zero
         if data_source != "imagenet":
             text_embeds = self.get_text_embeds(text_ids, text_atts)
             image_feat, text_feat = self.get_features(image_embeds, text_embeds)
@@ -59,15 +64,18 @@ class XFM(XFMBase):
                 loss_mlm = self.get_fuse_mlm_loss(text_ids_masked, text_atts, image_embeds, image_atts, masked_pos, masked_ids)
                 if data_source in wmap:
                     loss_mlm = loss_mlm * wmap[data_source]
-        if ret_mim_loss:
+        if ret_mim_loss and not ret_bbox_loss:
             image_embeds_masked, image_atts, ids_mask = self.get_vision_embeds(image, do_mask=self.do_image_mask)
             if data_source == "imagenet" or self.use_mm_mim_loss:
                 target = image if self.use_vision_tokenizer else image_embeds
                 loss_mim = self.get_mim_loss(image_embeds_masked, target, ids_mask)
                 if data_source in wmap:
                     loss_mim = loss_mim * wmap[data_source]
+        if ret_bbox_giou:   # model_pretrain.py:81-86
+            output_coord = self.predict_bbox(image_embeds_fullatts, text_ids, text_atts, text_embeds)
+            loss_bbox, loss_giou = self.get_bbox_loss(output_coord, target_bbox, is_image=is_image)
         return {"loss_itc": loss_itc, "loss_itm": loss_itm, "loss_mlm": loss_mlm, "loss_mim": loss_mim,
-                "loss_bbox": zero, "loss_giou": zero}
+                "loss_bbox": loss_bbox, "loss_giou": loss_giou}
 
     def forward_text(self, text_ids=None, text_atts=None, text_ids_masked=None, masked_pos=None, masked_ids=None):
         return {"loss_mlm": self.get_mlm_loss(text_ids_masked, text_atts, None, None, masked_pos, masked_ids)}

@@ -561,9 +561,11 @@ class XFMBase(nn.Module):
 
     # ------------------------------------------------------------------ vision
     def get_vision_embeds(self, image, image_atts=None, idx_to_group_img=None, do_mask=False):
-        """xfm.py:560-597 (idx_to_group_img / region branch is out of scope)."""
+        """xfm.py:560-597.  With idx_to_group_img (region data: fewer images than samples) the encoded images are gathered per
+        sample; with image_atts as well, token 0 becomes the region-weighted mean of the sample's patch tokens
+        (beit2.py:468-475) and the full-image embeddings are returned as a third value."""
         if idx_to_group_img is not None:
-            raise NotImplementedError("region / bbox branch (idx_to_group_img) is outside the built hot path")
+            return self._region_vision_embeds(image, image_atts, idx_to_group_img)
         self._prep()
         B = image.shape[0]
         mask_dev = None
@@ -596,10 +598,65 @@ class XFMBase(nn.Module):
         y = self._call(impl, image)
         y._xfm16 = impl.y16
         atts = torch.ones(y.shape[:-1], dtype=torch.long, device=image.device)
+        atts._xfm_all_ones = True   # lets the cross-attention skip the encoder mask (and stay on the tcgen05 kernel)
         if do_mask:
             mask_dev._xfm_rows = rows
             return y, atts, mask_dev
         return y, atts
+
+    def _region_vision_embeds(self, image, image_atts, idx_to_group_img):
+        """xfm.py:574-597 + beit2.py:468-475."""
+        y, _ = self.get_vision_embeds(image)
+        model = self
+        idx = idx_to_group_img.reshape(-1).long().contiguous()
+        n_img, N, D = y.shape
+        bsz = idx.numel()
+        y16 = _twin(y)
+        pooled = image_atts is not None
+        if pooled:
+            assert image_atts.size(0) == idx.size(0)
+            atts = image_atts.long().contiguous()
+
+        class Impl:
+            def fwd(self, ctx, y_):
+                y32 = y_.detach().float().contiguous()
+                full32 = L.gather_rows(y32.view(n_img, N * D), idx).view(bsz, N, D)
+                self.full16 = L.gather_rows(y16.reshape(n_img, N * D), idx).view(bsz, N, D)
+                if not pooled:
+                    return (full32,)
+                out32, self.out16 = L.region_pool_fwd(y32, idx, atts)
+                return out32, full32
+
+            def bwd(self, ctx, *grads):
+                dy = torch.zeros((n_img, N * D), dtype=torch.float32, device=y.device)
+                d_full = grads[-1]
+                if d_full is not None:
+                    L.scatter_add_rows_(dy, idx, d_full.float().reshape(bsz, N * D).contiguous())
+                if pooled and grads[0] is not None:
+                    L.region_pool_bwd_(grads[0].float().contiguous(), idx, atts, dy.view(n_img, N, D))
+                return (dy.view(n_img, N, D),)
+        impl = Impl()
+        outs = self._call(impl, y)
+        full = outs[-1]
+        full._xfm16 = impl.full16
+        if not pooled:
+            ones = torch.ones(full.shape[:-1], dtype=torch.long, device=image.device)
+            ones._xfm_all_ones = True
+            return full, ones
+        emb = outs[0]
+        emb._xfm16 = impl.out16
+        return emb, image_atts, full
+
+    @staticmethod
+    def _enc_kmask(image_atts, index=None):
+        """Additive key mask of the cross-attention, f32 [samples, image tokens]: (1 - m) * -1e9 (HF invert_attention_mask
+        for fp32, xroberta.py:903-909), or None for the all-ones masks get_vision_embeds produces.  index: sample -> mask row."""
+        if image_atts is None or getattr(image_atts, "_xfm_all_ones", False):
+            return None
+        m = ((1.0 - image_atts.to(torch.float32)) * -1e9)
+        if index is not None:
+            m = m.index_select(0, index.long())
+        return m.contiguous()
 
     # ------------------------------------------------------------------ text
     def get_text_embeds(self, text_ids, text_atts):
@@ -718,14 +775,15 @@ class XFMBase(nn.Module):
                                         want_weights=True)
         return w1, w2
 
-    def _fusion_run(self, text16, Bt, Lt, kmask, img16, Bi, kv_index, save, text32=None):
-        """fusion encoder over Bt text samples attending to Bi images (kv_index: sample -> image row, or None)."""
+    def _fusion_run(self, text16, Bt, Lt, kmask, img16, Bi, kv_index, save, text32=None, enc_kmask=None):
+        """fusion encoder over Bt text samples attending to Bi images (kv_index: sample -> image row, or None).
+        enc_kmask: additive key mask over the image tokens per text sample (region data), else all tokens are visible."""
         Ni = img16.shape[1]
         enc = img16.reshape(Bi * Ni, -1)
         if text32 is not None:
             text32 = text32.reshape(Bt * Lt, -1)
         return self._fus.layers_fwd(text16.reshape(Bt * Lt, -1), Bt, Lt, kmask, enc=enc, Benc=Bi, Lenc=Ni, kv_index=kv_index,
-                                    drop=self._drop(), save=save, h32=text32)
+                                    drop=self._drop(), save=save, h32=text32, enc_kmask=enc_kmask)
 
     def _fusion_back(self, st, dh, Bi, Ni, need_dtext, kv_index):
         d_enc = torch.zeros((Bi * Ni, self.vision_width), dtype=torch.float32, device=dh.device)
@@ -733,11 +791,13 @@ class XFMBase(nn.Module):
         return d_text, d_enc.view(Bi, Ni, -1)
 
     def get_cross_embeds(self, image_embeds, image_atts, text_ids=None, text_embeds=None, text_atts=None, is_pretrain=True):
-        """xfm.py:659-680.  image_atts is taken as all-ones (every BASELINE configuration)."""
+        """xfm.py:659-680.  image_atts other than get_vision_embeds' all-ones mask (region data) become an additive key mask of
+        the cross-attention."""
         self._prep()
         model = self
         Bi, Ni, _ = image_embeds.shape
         kmask = E.RobertaStack.additive_mask(text_atts)
+        ek = self._enc_kmask(image_atts)
         img16 = _twin(image_embeds)
         Bt, Lt = text_atts.shape
         assert Bt == Bi
@@ -751,7 +811,7 @@ class XFMBase(nn.Module):
                 h, h32 = t16, (None if from_ids else txt.detach().float().contiguous())
                 if from_ids:
                     h, h32, est = model._fus.embed(text_ids, model._drop(), save=self.save)
-                out, out32, st = model._fusion_run(h, Bt, Lt, kmask, img16, Bi, None, self.save, text32=h32)
+                out, out32, st = model._fusion_run(h, Bt, Lt, kmask, img16, Bi, None, self.save, text32=h32, enc_kmask=ek)
                 self.h16 = out.view(Bt, Lt, -1)
                 if ctx is not None:
                     ctx.st, ctx.est = st, est
@@ -818,6 +878,7 @@ class XFMBase(nn.Module):
         txt_index = torch.cat([ar, ar, text_neg.long()])
         kv_index = torch.cat([ar, image_neg.long(), ar]).to(torch.int32)
         kmask = E.RobertaStack.additive_mask(text_atts.index_select(0, txt_index))
+        ek = self._enc_kmask(image_atts, kv_index)
         img16, t16 = _twin(image_embeds), _twin(text_embeds)
         need_dtext = not is_pretrain
         labels = torch.zeros(3 * B, dtype=torch.long, device=image_embeds.device)
@@ -828,7 +889,7 @@ class XFMBase(nn.Module):
                 D = t16.shape[-1]
                 tall = L.gather_rows(t16.reshape(B, Lt * D), txt_index).view(3 * B * Lt, D)
                 tall32 = L.gather_rows(txt.detach().float().reshape(B, Lt * D).contiguous(), txt_index)
-                h, _, st = model._fusion_run(tall, 3 * B, Lt, kmask, img16, B, kv_index, self.save, text32=tall32)
+                h, _, st = model._fusion_run(tall, 3 * B, Lt, kmask, img16, B, kv_index, self.save, text32=tall32, enc_kmask=ek)
                 x0 = E.cls_rows(h, 3 * B, Lt)
                 logits, hst = model._itm.logits(x0, save=self.save)
                 loss, count, lse = L.ce_fwd(logits, labels, 2)
@@ -877,6 +938,7 @@ class XFMBase(nn.Module):
         kv_index = torch.cat([ar, image_neg.long(), ar, ar]).to(torch.int32)
         kmask_mlm = E.RobertaStack.additive_mask(text_atts)
         kmask = torch.cat([kmask_mlm.index_select(0, txt_index), kmask_mlm]).contiguous()
+        ek = self._enc_kmask(image_atts, kv_index)
         img16, t16 = _twin(image_embeds), _twin(text_embeds)
         need_dtext = not is_pretrain
         detach = self.detach_text_forMLM
@@ -899,7 +961,7 @@ class XFMBase(nn.Module):
                 tall32[:3 * B * Lt] = L.gather_rows(txt.detach().float().reshape(B, Lt * D).contiguous(), txt_index).view(3 * B * Lt, D)
                 tall[3 * B * Lt:] = hm
                 tall32[3 * B * Lt:] = hm32
-                h, _, st = model._fusion_run(tall, 4 * B, Lt, kmask, img16, B, kv_index, self.save, text32=tall32)
+                h, _, st = model._fusion_run(tall, 4 * B, Lt, kmask, img16, B, kv_index, self.save, text32=tall32, enc_kmask=ek)
                 x0 = E.cls_rows(h, 4 * B, Lt)[:3 * B]
                 logits, hst = model._itm.logits(x0, save=self.save)
                 loss_itm, count, lse = L.ce_fwd(logits, itm_labels, 2)
@@ -935,7 +997,7 @@ class XFMBase(nn.Module):
         return self._call(impl, image_embeds, text_embeds)
 
     # ------------------------------------------------------------------ MLM
-    def _mlm(self, text_ids_masked, text_atts, image_embeds, masked_pos, masked_ids, fused):
+    def _mlm(self, text_ids_masked, text_atts, image_embeds, masked_pos, masked_ids, fused, image_atts=None):
         self._prep()
         model = self
         B, Lt = text_ids_masked.shape
@@ -944,6 +1006,7 @@ class XFMBase(nn.Module):
         rows = (torch.arange(B, device=masked_pos.device).view(B, 1) * Lt + masked_pos).reshape(-1).contiguous()
         labels = masked_ids.reshape(-1).contiguous()
         img16 = _twin(image_embeds) if fused else None
+        ek = self._enc_kmask(image_atts) if fused else None
         detach = fused and self.detach_text_forMLM
         head = self._mlm_fus if fused else self._mlm_txt
 
@@ -955,7 +1018,8 @@ class XFMBase(nn.Module):
                 h, h32, tst = model._txt.layers_fwd(h, B, Lt, kmask, drop=drop, save=keep_text, h32=h32)
                 fst = None
                 if fused:
-                    h, h32, fst = model._fusion_run(h, B, Lt, kmask, img16, img16.shape[0], None, self.save, text32=h32)
+                    h, h32, fst = model._fusion_run(h, B, Lt, kmask, img16, img16.shape[0], None, self.save, text32=h32,
+                                                    enc_kmask=ek)
                 x = L.gather_rows(h, rows)
                 loss, hst = head.loss(x, labels)
                 if ctx is not None:
@@ -980,13 +1044,54 @@ class XFMBase(nn.Module):
 
     def get_fuse_mlm_loss(self, text_ids_masked, text_atts, image_embeds, image_atts, masked_pos, masked_ids):
         """xfm.py:638-656: text-encode the masked ids (detached), fuse with the image, LM head + CE on masked positions."""
-        return self._mlm(text_ids_masked, text_atts, image_embeds, masked_pos, masked_ids, fused=True)
+        return self._mlm(text_ids_masked, text_atts, image_embeds, masked_pos, masked_ids, fused=True, image_atts=image_atts)
 
     def get_mlm_loss(self, text_ids_masked, text_atts, image_embeds, image_atts, masked_pos, masked_ids):
         """xfm.py:805-812 on the text-only stream (model_pretrain.py:93-98 passes image_embeds=None)."""
         if image_embeds is not None:
             raise NotImplementedError("text_encoder has no cross-attention in the shipped layout; use get_fuse_mlm_loss")
         return self._mlm(text_ids_masked, text_atts, None, masked_pos, masked_ids, fused=False)
+
+    # ------------------------------------------------------------------ boxes (region data)
+    def predict_bbox(self, image_embeds, text_ids, text_atts, text_embeds, is_pretrain=True):
+        """xfm.py:843-854: fusion over the FULL image tokens, bbox_head on the CLS row, sigmoid -> (cx, cy, w, h) [bsz, 4]."""
+        assert image_embeds.size(0) == text_ids.size(0) == text_atts.size(0)
+        ones = torch.ones(image_embeds.shape[:2], dtype=torch.long, device=image_embeds.device)
+        ones._xfm_all_ones = True
+        output_cls = self.get_cross_embeds(image_embeds, ones, text_ids=text_ids, text_atts=text_atts, text_embeds=text_embeds,
+                                           is_pretrain=is_pretrain)[:, 0, :]
+        logits = self.bbox_head(output_cls)
+        model = self
+
+        class Impl:
+            def fwd(self, ctx, x):
+                y = L.sigmoid_fwd(x.detach().float().contiguous())
+                if ctx is not None:
+                    ctx.y = y
+                return y
+
+            def bwd(self, ctx, dy):
+                return (L.sigmoid_bwd(dy.float().contiguous(), ctx.y),)
+        return self._call(Impl(), logits)
+
+    def get_bbox_loss(self, output_coord, target_bbox, is_image=None):
+        """xfm.py:815-840: L1 and generalized-IoU losses over the region samples (is_image = 1 rows excluded), one kernel for
+        both losses and their gradients; the degenerate-box early-out (xfm.py:825-828) is decided on the device."""
+        model = self
+        tgt = target_bbox.detach().float().contiguous()
+        keep = None if is_image is None else is_image.detach().float().contiguous()
+
+        class Impl:
+            def fwd(self, ctx, coord):
+                lb, lg, db, dg = L.bbox_loss(coord.detach().float().contiguous(), tgt, keep)
+                if ctx is not None:
+                    ctx.g = (db, dg)
+                return lb.view(()), lg.view(())
+
+            def bwd(self, ctx, g_b, g_g):
+                db, dg = ctx.g
+                return (L.axpby_scalars(db, None if g_b is None else _up(g_b), dg, None if g_g is None else _up(g_g)),)
+        return self._call(Impl(), output_coord)
 
     # ------------------------------------------------------------------ MIM
     def get_codebook_indices(self, image):
