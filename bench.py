@@ -214,8 +214,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's "NCCL version ..." banner off stdout: rank 0 prints ONE JSON line
+        # rank 0 prints ONE JSON line on stdout: NCCL's own output (the "NCCL version ..." banner it prints at
+        # NCCL_DEBUG=VERSION / WARN, warnings) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     B, Lt, M = args.batch, 40, 15
     import random

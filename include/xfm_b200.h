@@ -171,12 +171,15 @@ int xfm_gelu_fwd(const void* x, int x_dtype, void* y_bf16, size_t n, void* strea
 int xfm_gelu_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, void* dx_bf16, size_t n, void* stream);
 int xfm_dropout_apply(const void* x, int x_dtype, void* y_bf16, size_t n, float p, uint64_t seed, void* stream);
 
-/* K7 — RoBERTa embeddings + position ids + LayerNorm (xroberta.py:104-137, :1747-1757) and the scatter-add backward. */
+/* K7 — text embeddings (word + token-type row 0 + position) + LayerNorm and the scatter-add backward.
+ * absolute_pos = 0: RoBERTa position ids cumsum(ids != pad) * (ids != pad) + pad (xroberta.py:104-137, :1747-1757);
+ * absolute_pos = 1: BERT position ids 0..L-1 (xbert.py:167-221).  word_pad / pos_pad: padding_idx rows of the word / position
+ * tables that receive no gradient (-1 = none): RoBERTa pad_id for both, BERT pad_token_id for the words only. */
 int xfm_roberta_embed_fwd(const int64_t* ids, const float* word, const float* pos, const float* type0, const float* ln_w,
                           const float* ln_b, void* y_bf16, float* pre_ln, float* stats, int32_t* pos_ids, int B, int L,
-                          int D, int pad_id, float eps, void* stream);
+                          int D, int pad_id, int absolute_pos, float eps, void* stream);
 int xfm_roberta_embed_bwd(const float* dpre, const int64_t* ids, const int32_t* pos_ids, float* dword, float* dpos,
-                          float* dtype0, int rows, int D, int pad_id, void* stream);
+                          float* dtype0, int rows, int D, int word_pad, int pos_pad, void* stream);
 
 /* K8/K9 — patch-embed im2col (beit2.py:229), token assembly with mask-token blend + CLS (+ abs pos) (beit2.py:438-449),
  * mean-pool pseudo-CLS (beit2.py:456-466) and their backward. */

@@ -124,7 +124,8 @@ def _worker(rank, world, port, q):
                 auto._on_backward_begin()
                 seen.append(auto._on_last_node() is not None)
             auto.all_reduce_grads(model)
-            auto._bw_per_step, auto._bw_seen = auto._bw_seen, 0
+            auto._bw_hist = (auto._bw_hist + [auto._bw_seen])[-4:]
+            auto._bw_per_step, auto._bw_seen = max(auto._bw_hist), 0
         res["auto"] = seen
         # (E) the live-parameter table is agreed over ranks (a parameter is updated if ANY rank has a gradient for it)
         t = torch.tensor([0, 255, 3, 255] if rank == 0 else [255, 255, 3, 1], dtype=torch.uint8)

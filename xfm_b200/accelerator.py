@@ -248,7 +248,8 @@ class B200DDPAccelerator:
         self._vis = None
         self._blocks = []
         self._bw_seen = 0
-        self._bw_per_step = None
+        self._bw_hist = []        # backward passes seen in each of the last optimizer steps ("auto" predicts their maximum:
+        self._bw_per_step = None  # Pretrain.py alternates a 1-backward text step with a k-backward multimodal step)
         self._model = None
 
     def set_up(self, model, optimizer, lr_scheduler, local_rank=0, world_size=1, rank=0):
@@ -385,7 +386,8 @@ class B200DDPAccelerator:
         """clip_grad_norm_(CLIP_GRAD_NORM) + AdamW step + zero_grad (ddp_accelerator.py:89-98).  Returns the total gradient
         norm as a 1-element device tensor (no host sync; float() it if a python number is needed)."""
         self.all_reduce_grads(model)
-        self._bw_per_step, self._bw_seen = self._bw_seen, 0
+        self._bw_hist = (self._bw_hist + [self._bw_seen])[-4:]
+        self._bw_per_step, self._bw_seen = max(self._bw_hist), 0
         norm = optimizer.step(max_grad_norm=self.clip, grad_mul=1.0 / self.world)
         optimizer.zero_grad()
         return norm

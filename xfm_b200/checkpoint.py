@@ -3,7 +3,7 @@ producing state_dicts in the reference key layout that XFMBase.load_state_dict c
 
     beit2_init_state        models/beit2.py:572-673   load_pretrained_beit2 (BEiT-v2 checkpoint -> vision_encoder.*)
     interpolate_rel_pos     models/beit2.py:611-652 / 753-808  relative-position table for another window size
-    roberta_init_state      models/xfm.py:298-312,382-385      text encoder from <text_encoder>/pytorch_model.bin
+    text_init_state         models/xfm.py:298-385      text encoder (RoBERTa or BERT class) from <text_encoder>/pytorch_model.bin
     finetune_state          models/xfm.py:408-468     load_pretrained(): XFM checkpoint -> fine-tuning model (BEiT-v2 branch)
     vqkd_state              models/model_vqkd.py:315-333       tokenizer weight file -> vqkd.*
 
@@ -121,17 +121,37 @@ def choose_layers(prefix, state, mapper):
     return state
 
 
-def roberta_init_state(text_encoder_dir, num_layers):
-    """xfm.py:298-314: <dir>/pytorch_model.bin (a RobertaForMaskedLM checkpoint: roberta.*, lm_head.*) -> the same keys
-    under 'text_encoder.'; the large checkpoints contribute every second layer when 12 layers are built."""
+def rename_tf_layernorm(state):
+    """xfm.py:53-61: TensorFlow-era BERT checkpoints call the LayerNorm parameters gamma / beta."""
+    for k in list(state.keys()):
+        if "LayerNorm." in k:
+            new_k = k.strip().replace("LayerNorm.beta", "LayerNorm.bias").replace("LayerNorm.gamma", "LayerNorm.weight")
+            if new_k != k:
+                state[new_k] = state.pop(k)
+
+
+def text_init_state(text_encoder_dir, num_layers, arch="roberta"):
+    """xfm.py:298-385: <dir>/pytorch_model.bin (a RobertaForMaskedLM checkpoint: roberta.*, lm_head.*; or a BertForMaskedLM one:
+    bert.*, cls.predictions.*) -> the same keys under 'text_encoder.'.  Layer-picking rules of the layouts this package
+    builds (text encoder without cross-attention): roberta-large / xlm-roberta-large and bert-large-uncased contribute every
+    second layer when 12 layers are built; bert-base-uncased with 6 layers takes layers 1, 3, ... 11."""
     path = os.path.join(text_encoder_dir, "pytorch_model.bin")
     print("### Initializing text encoder from ", path)
     state = dict(torch.load(path, map_location="cpu"))
-    if "roberta" not in text_encoder_dir:
-        raise NotImplementedError("xfm_b200 builds the RoBERTa text encoder (models/xroberta.py); BERT checkpoints "
-                                  "(models/xbert.py layouts, xfm.py:316-380) are not imported")
-    if ("roberta-large" in text_encoder_dir) and num_layers == 12:
-        choose_layers("roberta.encoder.layer", state, LAYER_PICK_24_TO_12)
+    if arch == "roberta":
+        if ("roberta-large" in text_encoder_dir) and num_layers == 12:   # covers xlm-roberta-large too (xfm.py:303-314)
+            choose_layers("roberta.encoder.layer", state, LAYER_PICK_24_TO_12)
+    else:
+        if "bert-large-uncased" in text_encoder_dir and "-12l" not in text_encoder_dir and "-18l" not in text_encoder_dir:
+            rename_tf_layernorm(state)                                   # xfm.py:353-358
+            if num_layers == 12:
+                choose_layers("bert.encoder.layer", state, LAYER_PICK_24_TO_12)
+        elif "bert-base-uncased" in text_encoder_dir and "-6l" not in text_encoder_dir and "-18l" not in text_encoder_dir:
+            rename_tf_layernorm(state)                                   # xfm.py:326-330
+            if num_layers == 6:
+                choose_layers("bert.encoder.layer", state, {1: 0, 3: 1, 5: 2, 7: 3, 9: 4, 11: 5})
+        elif "chinese-roberta-wwm-ext" in text_encoder_dir and num_layers == 6:   # xfm.py:371-374 (a BERT-class checkpoint)
+            choose_layers("bert.encoder.layer", state, {1: 0, 3: 1, 5: 2, 7: 3, 9: 4, 11: 5})
     return {"text_encoder." + k: v for k, v in state.items()}
 
 

@@ -17,6 +17,7 @@ _DEFAULTS = dict(
     num_masking_patches=75, min_num_patches=16,
     use_vision_tokenizer=False, codebook_size=8192, codebook_dim=32,
     use_bbox=True, detach_text_forMLM=True, mim_cls_only=False,
+    text_arch="roberta",   # "bert": models/xbert.py text encoder (selected by a text_encoder path without "roberta", xfm.py:260-265)
 )
 
 # keys of the internal dict that a caller may pass directly (tests / bench use them for the tiny configuration)
@@ -41,11 +42,19 @@ def normalize_config(config):
         cfg["vision_width"] = vis.get("vision_width", cfg["vision_width"])
         cfg["patch_size"] = vis.get("patch_size", cfg["patch_size"])
     if "text_encoder" in config:
+        te = str(config["text_encoder"])
+        if "roberta" in te:     # xfm.py:260-265
+            cfg["text_arch"] = "roberta"
+        elif "bert" in te:
+            cfg["text_arch"] = "bert"
+        else:
+            raise ValueError(f"text_encoder {te!r}: neither a roberta nor a bert checkpoint directory")
         txt = _read_json(os.path.join(config["text_encoder"], "config.json"))
         if txt:
             cfg.update(vocab_size=txt["vocab_size"], hidden=txt["hidden_size"], heads=txt["num_attention_heads"],
                        ffn=txt["intermediate_size"], max_pos=txt["max_position_embeddings"],
-                       type_vocab=txt["type_vocab_size"], pad_id=txt.get("pad_token_id", 1),
+                       type_vocab=txt["type_vocab_size"],
+                       pad_id=txt.get("pad_token_id", 1 if cfg["text_arch"] == "roberta" else 0),
                        ln_eps=txt["layer_norm_eps"], hidden_dropout=txt["hidden_dropout_prob"],
                        attn_dropout=txt["attention_probs_dropout_prob"])
     if "text_num_hidden_layers" in config:

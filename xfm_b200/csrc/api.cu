@@ -98,12 +98,12 @@ int xfm_dropout_apply(const void* x, int x_dtype, void* y, size_t n, float p, ui
 }
 int xfm_roberta_embed_fwd(const int64_t* ids, const float* word, const float* pos, const float* type0, const float* ln_w,
                           const float* ln_b, void* y, float* pre_ln, float* stats, int32_t* pos_ids, int B, int L, int D,
-                          int pad_id, float eps, void* stream) {
-  return roberta_embed_fwd(ids, word, pos, type0, ln_w, ln_b, BF(y), pre_ln, stats, pos_ids, B, L, D, pad_id, eps, ST);
+                          int pad_id, int absolute_pos, float eps, void* stream) {
+  return roberta_embed_fwd(ids, word, pos, type0, ln_w, ln_b, BF(y), pre_ln, stats, pos_ids, B, L, D, pad_id, absolute_pos, eps, ST);
 }
 int xfm_roberta_embed_bwd(const float* dpre, const int64_t* ids, const int32_t* pos_ids, float* dword, float* dpos,
-                          float* dtype0, int rows, int D, int pad_id, void* stream) {
-  return roberta_embed_bwd(dpre, ids, pos_ids, dword, dpos, dtype0, rows, D, pad_id, ST);
+                          float* dtype0, int rows, int D, int word_pad, int pos_pad, void* stream) {
+  return roberta_embed_bwd(dpre, ids, pos_ids, dword, dpos, dtype0, rows, D, word_pad, pos_pad, ST);
 }
 int xfm_im2col(const float* image, void* out, int B, int C, int H, int W, int P, const float* pre_mul, void* stream) {
   return im2col(image, BF(out), B, C, H, W, P, pre_mul, ST);

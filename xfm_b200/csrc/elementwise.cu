@@ -445,7 +445,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
 roberta_embed_fwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ word, const float* __restrict__ pos,
                          const float* __restrict__ type0, const float* __restrict__ w, const float* __restrict__ b,
                          bf16* __restrict__ y, float* __restrict__ pre_ln, float* __restrict__ stats,
-                         int32_t* __restrict__ pos_ids, int L, int D, int pad_id, float eps) {
+                         int32_t* __restrict__ pos_ids, int L, int D, int pad_id, int absolute_pos, float eps) {
   extern __shared__ int s_pos[];  // [L]
   const int seq = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -461,7 +461,8 @@ roberta_embed_fwd_kernel(const int64_t* __restrict__ ids, const float* __restric
         if (lane >= o) inc += n;
       }
       if (t < L) {
-        const int p = (carry + inc) * m + pad_id;
+        // RoBERTa: cumsum(ids != pad) * (ids != pad) + pad (xroberta.py:1747-1757); BERT: position_ids[:, :L] (xbert.py:199-200)
+        const int p = absolute_pos ? t : (carry + inc) * m + pad_id;
         s_pos[t] = p;
         pos_ids[(size_t)seq * L + t] = p;
       }
@@ -523,15 +524,15 @@ roberta_embed_fwd_kernel(const int64_t* __restrict__ ids, const float* __restric
 __global__ void __launch_bounds__(256)
 roberta_embed_bwd_kernel(const float* __restrict__ dpre, const int64_t* __restrict__ ids,
                          const int32_t* __restrict__ pos_ids, float* __restrict__ dword, float* __restrict__ dpos,
-                         float* __restrict__ dtype0, int rows, int D, int pad_id) {
+                         float* __restrict__ dtype0, int rows, int D, int word_pad, int pos_pad) {
   const int row = blockIdx.x;
   if (row >= rows) return;
   const int64_t id = ids[row];
   const int p = pos_ids[row];
   for (int c = threadIdx.x; c < D; c += blockDim.x) {
     const float g = dpre[(size_t)row * D + c];
-    if (id != pad_id) atomicAdd(dword + (size_t)id * D + c, g);
-    if (p != pad_id) atomicAdd(dpos + (size_t)p * D + c, g);
+    if (id != word_pad) atomicAdd(dword + (size_t)id * D + c, g);   // nn.Embedding(padding_idx) rows get no gradient
+    if (p != pos_pad) atomicAdd(dpos + (size_t)p * D + c, g);
     atomicAdd(dtype0 + c, g);
   }
 }
@@ -913,17 +914,17 @@ int dropout_apply(const void* x, int x_dtype, bf16* y, size_t n, float p, uint64
 
 int roberta_embed_fwd(const int64_t* ids, const float* word, const float* pos, const float* type0, const float* w,
                       const float* b, bf16* y, float* pre_ln, float* stats, int32_t* pos_ids, int B, int L, int D,
-                      int pad_id, float eps, cudaStream_t s) {
+                      int pad_id, int absolute_pos, float eps, cudaStream_t s) {
   if (ln_check(D, LN_MAX_VEC)) return XFM_ERR_BAD_ARG;
   if (B <= 0) return 0;
   roberta_embed_fwd_kernel<<<B, LN_WARPS * 32, L * sizeof(int), s>>>(ids, word, pos, type0, w, b, y, pre_ln, stats, pos_ids, L, D,
-                                                                   pad_id, eps);
+                                                                   pad_id, absolute_pos, eps);
   LAUNCH_END();
 }
 int roberta_embed_bwd(const float* dpre, const int64_t* ids, const int32_t* pos_ids, float* dword, float* dpos,
-                      float* dtype0, int rows, int D, int pad_id, cudaStream_t s) {
+                      float* dtype0, int rows, int D, int word_pad, int pos_pad, cudaStream_t s) {
   if (rows <= 0) return 0;
-  roberta_embed_bwd_kernel<<<rows, 256, 0, s>>>(dpre, ids, pos_ids, dword, dpos, dtype0, rows, D, pad_id);
+  roberta_embed_bwd_kernel<<<rows, 256, 0, s>>>(dpre, ids, pos_ids, dword, dpos, dtype0, rows, D, word_pad, pos_pad);
   LAUNCH_END();
 }
 

@@ -50,9 +50,9 @@ int gelu_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, bf16_t* d
 int dropout_apply(const void* x, int x_dtype, bf16_t* y, size_t n, float p, uint64_t seed, cudaStream_t s);
 int roberta_embed_fwd(const int64_t* ids, const float* word, const float* pos, const float* type0, const float* w,
                       const float* b, bf16_t* y, float* pre_ln, float* stats, int32_t* pos_ids, int B, int L, int D,
-                      int pad_id, float eps, cudaStream_t s);
+                      int pad_id, int absolute_pos, float eps, cudaStream_t s);
 int roberta_embed_bwd(const float* dpre, const int64_t* ids, const int32_t* pos_ids, float* dword, float* dpos,
-                      float* dtype0, int rows, int D, int pad_id, cudaStream_t s);
+                      float* dtype0, int rows, int D, int word_pad, int pos_pad, cudaStream_t s);
 int im2col(const float* img, bf16_t* out, int B, int C, int H, int W, int P, const float* pre_mul, cudaStream_t s);
 int assemble_tokens(const float* patch, const float* cls, const float* mask_token, const uint8_t* mask, const float* pos,
                     float* x, int B, int np, int D, cudaStream_t s);

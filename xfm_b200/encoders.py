@@ -82,20 +82,46 @@ def add_vision(fp, cfg, init, prefix="vision_encoder.", layerscale=True, relbias
     add("fc_norm.bias", (D,))
 
 
-def add_roberta(fp, cfg, init, prefix, layers, cross, enc_width, heads=("lm_head", "lm_cap_head")):
+class TextNames:
+    """Parameter naming of a text stack: models/xroberta.py (RobertaForMaskedLM: roberta.*, lm_head.*, lm_cap_head.*) or
+    models/xbert.py (BertForMaskedLM: bert.*, cls.predictions.*, xbert.py:663-707,1523-1540).  The arithmetic of the two is
+    the same post-LN layer; they differ in the embeddings (BERT: absolute position ids, xbert.py:167-221) and in where the
+    1/sqrt(d) sits (xbert.py:296-301,329-330: on q when config.fp16, else on the scores) — at head_dim 64 the factor is
+    0.125, a power of two, so both orders give bit-identical results and one kernel serves both."""
+
+    def __init__(self, arch="roberta"):
+        assert arch in ("roberta", "bert"), arch
+        self.arch = arch
+        self.stem = arch + "."
+
+    def head(self, head="lm_head"):
+        if self.arch == "roberta":
+            h = head + "."
+            return dict(bias=h + "bias", dense_w=h + "dense.weight", dense_b=h + "dense.bias", ln_w=h + "layer_norm.weight",
+                        ln_b=h + "layer_norm.bias", dec_w=h + "decoder.weight", dec_b=h + "decoder.bias")
+        h = "cls.predictions."
+        return dict(bias=h + "bias", dense_w=h + "transform.dense.weight", dense_b=h + "transform.dense.bias",
+                    ln_w=h + "transform.LayerNorm.weight", ln_b=h + "transform.LayerNorm.bias", dec_w=h + "decoder.weight",
+                    dec_b=h + "decoder.bias")
+
+
+def add_roberta(fp, cfg, init, prefix, layers, cross, enc_width, heads=("lm_head", "lm_cap_head"), arch="roberta"):
     H, Ff, V = cfg["hidden"], cfg["ffn"], cfg["vocab_size"]
+    names = TextNames(arch)
+    if arch == "bert":
+        heads = ("lm_head",) if heads else ()   # BertForMaskedLM has the one prediction head
 
     def add(name, shape):
         fp.add(prefix + name, shape, init=init(prefix + name, shape))
 
-    e = "roberta.embeddings."
+    e = names.stem + "embeddings."
     add(e + "word_embeddings.weight", (V, H))
     add(e + "position_embeddings.weight", (cfg["max_pos"], H))
     add(e + "token_type_embeddings.weight", (cfg["type_vocab"], H))
     add(e + "LayerNorm.weight", (H,))
     add(e + "LayerNorm.bias", (H,))
     for i in range(layers):
-        l = f"roberta.encoder.layer.{i}."
+        l = f"{names.stem}encoder.layer.{i}."
         a = l + "attention."
         # query | key | value back to back: one fused [3H, H] operand (xroberta.py:170-176 keeps three Linears)
         for n in ("query", "key", "value"):
@@ -125,14 +151,14 @@ def add_roberta(fp, cfg, init, prefix, layers, cross, enc_width, heads=("lm_head
         add(l + "output.LayerNorm.weight", (H,))
         add(l + "output.LayerNorm.bias", (H,))
     for head in heads:
-        h = head + "."
-        add(h + "bias", (V,))
-        add(h + "dense.weight", (H, H))
-        add(h + "dense.bias", (H,))
-        add(h + "layer_norm.weight", (H,))
-        add(h + "layer_norm.bias", (H,))
+        n = names.head(head)
+        add(n["bias"], (V,))
+        add(n["dense_w"], (H, H))
+        add(n["dense_b"], (H,))
+        add(n["ln_w"], (H,))
+        add(n["ln_b"], (H,))
         if head == "lm_cap_head":  # untied decoder; lm_head.decoder.weight IS the word embedding (xroberta.py:1209-1210)
-            add(h + "decoder.weight", (V, H))
+            add(n["dec_w"], (V, H))
 
 
 def add_mlp_head(fp, init, name, din, dout):
@@ -254,8 +280,9 @@ class VisionEncoder:
 # RoBERTa stack (text encoder / fusion encoder)
 # =====================================================================================================
 class RobertaStack:
-    def __init__(self, fp, cfg, prefix, layers, cross):
+    def __init__(self, fp, cfg, prefix, layers, cross, arch="roberta"):
         self.fp, self.cfg, self.prefix, self.layers, self.cross = fp, cfg, prefix, layers, cross
+        self.names = TextNames(arch)
         self.D, self.H, self.eps, self.pad = cfg["hidden"], cfg["heads"], cfg["ln_eps"], cfg["pad_id"]
         self.w = None
         self.collect = None  # tests: list receiving a f32 copy of every layer output
@@ -264,7 +291,7 @@ class RobertaStack:
         fp, D = self.fp, self.D
         self.w, self.gmap = [], []
         for i in range(self.layers):
-            l = f"{self.prefix}roberta.encoder.layer.{i}."
+            l = f"{self.prefix}{self.names.stem}encoder.layer.{i}."
             a, c = l + "attention.", l + "crossattention."
             w = dict(qkv_w16=fp.span16(a + "self.query.weight", a + "self.value.weight", (3 * D, D)),
                      qkv_b=fp.span32(a + "self.query.bias", a + "self.value.bias", (3 * D,)),
@@ -293,7 +320,7 @@ class RobertaStack:
                           c_ln_b=c + "output.LayerNorm.bias")
             self.w.append(w)
             self.gmap.append(gm)
-        e = self.prefix + "roberta.embeddings."
+        e = self.prefix + self.names.stem + "embeddings."
         self.e = e
         self.word, self.posw, self.typew = (fp.view32(e + "word_embeddings.weight"), fp.view32(e + "position_embeddings.weight"),
                                             fp.view32(e + "token_type_embeddings.weight"))
@@ -320,7 +347,8 @@ class RobertaStack:
         if self.w is None:
             self.refresh()
         y, pre, stats, pos_ids = L.roberta_embed_fwd(ids.contiguous(), self.word, self.posw, self.typew, self.eln_w,
-                                                     self.eln_b, self.pad, self.eps, want_pre=True)
+                                                     self.eln_b, self.pad, self.eps, want_pre=True,
+                                                     absolute_pos=self.names.arch == "bert")
         st = State()
         st.ids, st.pre, st.stats, st.pos_ids, st.seed, st.p = ids, pre, stats, pos_ids, 0, drop.p_hidden
         y32 = None
@@ -338,7 +366,8 @@ class RobertaStack:
         dpre = L.layernorm_bwd(dh.contiguous(), st.pre, st.stats, self.eln_w, fp.grad(e + "LayerNorm.weight"),
                                fp.grad(e + "LayerNorm.bias"))
         L.roberta_embed_bwd(dpre, st.ids.reshape(-1), st.pos_ids, fp.grad(e + "word_embeddings.weight"),
-                            fp.grad(e + "position_embeddings.weight"), fp.grad(e + "token_type_embeddings.weight"), self.pad)
+                            fp.grad(e + "position_embeddings.weight"), fp.grad(e + "token_type_embeddings.weight"), self.pad,
+                            pos_pad=-1 if self.names.arch == "bert" else self.pad)   # xbert.py:172-174 vs xroberta.py:92-102
 
     def layers_fwd(self, h, Bt, Lt, kmask, enc=None, Benc=0, Lenc=0, kv_index=None, drop=BK.NO_DROP, save=True, h32=None,
                    self_bias=None, enc_kmask=None):
@@ -462,22 +491,24 @@ class LMHead:
     """RobertaLMHead (xroberta.py:1313-1333) with the decoder tied to the word embeddings, fused with
     CE(ignore_index=-100) (xroberta.py:1298-1299).  The f32 logits are materialised once ([R, V] padded to 8)."""
 
-    def __init__(self, fp, cfg, prefix):
+    def __init__(self, fp, cfg, prefix, arch="roberta", head="lm_head"):
         self.fp, self.cfg, self.p = fp, cfg, prefix
         self.V, self.eps = cfg["vocab_size"], cfg["ln_eps"]
         self.ldv = (self.V + 7) // 8 * 8
+        names = TextNames(arch)
+        self.n = {k: prefix + v for k, v in names.head(head).items()}
+        self.word = prefix + names.stem + "embeddings.word_embeddings.weight"
 
     def logits(self, x, st=None):
         """x bf16 [R, D] -> f32 logits [R, ldv] (columns >= V are padding)."""
         fp, p = self.fp, self.p
         R = x.shape[0]
         pre = torch.empty_like(x)
-        a = L.gemm(x, fp.view16(p + "lm_head.dense.weight"), bias=fp.view32(p + "lm_head.dense.bias"), act=1, aux_out=pre)
-        y, stats, _ = L.layernorm_fwd(a, fp.view32(p + "lm_head.layer_norm.weight"), fp.view32(p + "lm_head.layer_norm.bias"),
-                                      self.eps)
+        n = self.n
+        a = L.gemm(x, fp.view16(n["dense_w"]), bias=fp.view32(n["dense_b"]), act=1, aux_out=pre)
+        y, stats, _ = L.layernorm_fwd(a, fp.view32(n["ln_w"]), fp.view32(n["ln_b"]), self.eps)
         logits = torch.empty((R, self.ldv), dtype=torch.float32, device=x.device)
-        L.gemm(y, fp.view16(p + "roberta.embeddings.word_embeddings.weight"), bias=fp.view32(p + "lm_head.bias"),
-               out=logits[:, :self.V])
+        L.gemm(y, fp.view16(self.word), bias=fp.view32(n["bias"]), out=logits[:, :self.V])
         if st is not None:
             st.x, st.pre, st.a, st.y, st.stats, st.logits = x, pre, a, y, stats, logits
         return logits
@@ -507,16 +538,16 @@ class LMHead:
         else:
             dlog = L.ce_bwd(st.logits, st.labels, st.lse, st.count, upstream, V, self.ldv)
         st.logits = None
-        L.colsum_into(dlog, fp.grad_padded(p + "lm_head.bias", self.ldv))
-        BK.wgrad(fp.grad(p + "roberta.embeddings.word_embeddings.weight"), dlog[:, :V], st.y)
-        dy = L.gemm(dlog[:, :V], fp.view16(p + "roberta.embeddings.word_embeddings.weight"), b_t=True)
-        da = L.layernorm_bwd(dy, st.a, st.stats, fp.view32(p + "lm_head.layer_norm.weight"),
-                             fp.grad(p + "lm_head.layer_norm.weight"), fp.grad(p + "lm_head.layer_norm.bias"),
+        n = self.n
+        L.colsum_into(dlog, fp.grad_padded(n["bias"], self.ldv))
+        BK.wgrad(fp.grad(self.word), dlog[:, :V], st.y)
+        dy = L.gemm(dlog[:, :V], fp.view16(self.word), b_t=True)
+        da = L.layernorm_bwd(dy, st.a, st.stats, fp.view32(n["ln_w"]), fp.grad(n["ln_w"]), fp.grad(n["ln_b"]),
                              out_dtype=torch.bfloat16)
         dpre = L.gelu_bwd(da, st.pre)
-        L.colsum_into(dpre, fp.grad(p + "lm_head.dense.bias"))
-        BK.wgrad(fp.grad(p + "lm_head.dense.weight"), dpre, st.x)
-        return L.gemm(dpre, fp.view16(p + "lm_head.dense.weight"), b_t=True)
+        L.colsum_into(dpre, fp.grad(n["dense_b"]))
+        BK.wgrad(fp.grad(n["dense_w"]), dpre, st.x)
+        return L.gemm(dpre, fp.view16(n["dense_w"]), b_t=True)
 
 
 class LinearCE:

@@ -358,7 +358,7 @@ def scale_by_scalar(t, scalar):
     return out
 
 
-def roberta_embed_fwd(ids, word, pos, type_emb, ln_w, ln_b, pad_id, eps, want_pre=True):
+def roberta_embed_fwd(ids, word, pos, type_emb, ln_w, ln_b, pad_id, eps, want_pre=True, absolute_pos=False):
     B, L = ids.shape
     D = word.shape[1]
     assert ids.dtype == torch.int64 and ids.is_contiguous()
@@ -367,15 +367,16 @@ def roberta_embed_fwd(ids, word, pos, type_emb, ln_w, ln_b, pad_id, eps, want_pr
     stats = torch.empty((B * L, 2), dtype=torch.float32, device=ids.device)
     pos_ids = torch.empty((B, L), dtype=torch.int32, device=ids.device)
     check(lib().xfm_roberta_embed_fwd(_p(ids), _p(word), _p(pos), _p(type_emb), _p(ln_w), _p(ln_b), _p(y), _p(pre),
-                                      _p(stats), _p(pos_ids), B, L, D, pad_id, C.c_float(eps), stream_ptr()),
+                                      _p(stats), _p(pos_ids), B, L, D, pad_id, int(absolute_pos), C.c_float(eps), stream_ptr()),
           "xfm_roberta_embed_fwd")
     return y, pre, stats, pos_ids
 
 
-def roberta_embed_bwd(dpre, ids, pos_ids, dword, dpos, dtype0, pad_id):
+def roberta_embed_bwd(dpre, ids, pos_ids, dword, dpos, dtype0, word_pad, pos_pad=None):
     rows, D = dpre.shape
-    check(lib().xfm_roberta_embed_bwd(_p(dpre), _p(ids), _p(pos_ids), _p(dword), _p(dpos), _p(dtype0), rows, D, pad_id,
-                                      stream_ptr()), "xfm_roberta_embed_bwd")
+    pos_pad = word_pad if pos_pad is None else pos_pad
+    check(lib().xfm_roberta_embed_bwd(_p(dpre), _p(ids), _p(pos_ids), _p(dword), _p(dpos), _p(dtype0), rows, D, word_pad,
+                                      pos_pad, stream_ptr()), "xfm_roberta_embed_bwd")
 
 
 def im2col(image, P, pre_mul=None):

@@ -216,7 +216,9 @@ class XFMBase(nn.Module):
             self.embed_dim = cfg["embed_dim"]
             fp.add("temp", (), init=torch.tensor(float(cfg["temp"])), trainable=self.learnable_temp)
         E.add_vision(fp, cfg, init)
-        E.add_roberta(fp, cfg, init, "text_encoder.", cfg["text_layers"], cross=False, enc_width=D)
+        arch = self.text_arch = cfg["text_arch"]
+        E.add_roberta(fp, cfg, init, "text_encoder.", cfg["text_layers"], cross=False, enc_width=D, arch=arch)
+        # the fusion encoder is always the RoBERTa class, built from the text encoder's config.json (xfm.py:524-531)
         E.add_roberta(fp, cfg, init, "fusion_encoder.", cfg["fusion_layers"], cross=True, enc_width=D)
         if use_contrastive_loss:
             for n, din in (("vision_proj", D), ("text_proj", Hd)):
@@ -265,11 +267,15 @@ class XFMBase(nn.Module):
                 p = nn.Parameter(fp.view32(name), requires_grad=seg.trainable)
             self._params[name] = p
             self._register(name, p)
-        for enc in ("text_encoder.", "fusion_encoder."):  # weight tying (xroberta.py:1209-1210,1321-1323)
-            self._register(enc + "lm_head.decoder.weight", self._params[enc + "roberta.embeddings.word_embeddings.weight"])
-            self._register(enc + "lm_head.decoder.bias", self._params[enc + "lm_head.bias"])
-            self._register(enc + "lm_cap_head.decoder.bias", self._params[enc + "lm_cap_head.bias"])
-            self._register_buffer(enc + "roberta.embeddings.position_ids", torch.arange(cfg["max_pos"]).expand((1, -1)).clone())
+        for enc, a in (("text_encoder.", arch), ("fusion_encoder.", "roberta")):
+            # weight tying (xroberta.py:1209-1210,1321-1323; xbert.py:687-692,1536-1537)
+            nm = E.TextNames(a)
+            h = nm.head("lm_head")
+            self._register(enc + h["dec_w"], self._params[enc + nm.stem + "embeddings.word_embeddings.weight"])
+            self._register(enc + h["dec_b"], self._params[enc + h["bias"]])
+            if a == "roberta":
+                self._register(enc + "lm_cap_head.decoder.bias", self._params[enc + "lm_cap_head.bias"])
+            self._register_buffer(enc + nm.stem + "embeddings.position_ids", torch.arange(cfg["max_pos"]).expand((1, -1)).clone())
         ws = cfg["image_res"] // cfg["patch_size"]
         rpi = relative_position_index(ws).to(dev)
         for i in range(cfg["vision_depth"]):
@@ -277,13 +283,13 @@ class XFMBase(nn.Module):
         # ---- runners
         self._rpi = rpi
         self._vis = E.VisionEncoder(fp, cfg, rel_index=rpi)
-        self._txt = E.RobertaStack(fp, cfg, "text_encoder.", cfg["text_layers"], cross=False)
+        self._txt = E.RobertaStack(fp, cfg, "text_encoder.", cfg["text_layers"], cross=False, arch=arch)
         self._fus = E.RobertaStack(fp, cfg, "fusion_encoder.", cfg["fusion_layers"], cross=True)
         self._vproj = E.ProjHead(fp, "vision_proj") if use_contrastive_loss else None
         self._tproj = E.ProjHead(fp, "text_proj") if use_contrastive_loss else None
         self._itm = E.MlpHead(fp, "itm_head", 2) if use_matching_loss else None
         self._mlm_fus = E.LMHead(fp, cfg, "fusion_encoder.")
-        self._mlm_txt = E.LMHead(fp, cfg, "text_encoder.")
+        self._mlm_txt = E.LMHead(fp, cfg, "text_encoder.", arch=arch)
         if self.use_vision_tokenizer:
             self._vq = E.VisionEncoder(fp, cfg, prefix="vqkd.encoder.", layerscale=False, relbias=False, abs_pos=True)
             self._mim_head = E.LinearCE(fp, "lm_head", cfg["codebook_size"])
@@ -470,7 +476,7 @@ class XFMBase(nn.Module):
             if msg.unexpected_keys:
                 print("Weights from pretrained model not used in VisionTransformer: {}".format(msg.unexpected_keys))
         if load_text_params:
-            sd = CK.roberta_init_state(str(config["text_encoder"]), self.cfg["text_layers"])
+            sd = CK.text_init_state(str(config["text_encoder"]), self.cfg["text_layers"], self.text_arch)
             msg = self.load_state_dict(sd, strict=False)
             missing = [k[len("text_encoder."):] for k in msg.missing_keys if k.startswith("text_encoder.")]
             print("missing_keys: ", missing, flush=True)
@@ -480,7 +486,8 @@ class XFMBase(nn.Module):
     def load_state_dict(self, state_dict, strict=True, assign=False):
         # fine-tuning models of the reference hold a bare RobertaModel as text_encoder (xfm.py:397-403), so their
         # checkpoints name it text_encoder.<x>; this module always keeps the pre-training layout text_encoder.roberta.<x>
-        state_dict = {(("text_encoder.roberta." + k[len("text_encoder."):])
+        stem = "text_encoder." + self.text_arch + "."
+        state_dict = {((stem + k[len("text_encoder."):])
                        if k.startswith(("text_encoder.embeddings.", "text_encoder.encoder.")) else k): v
                       for k, v in state_dict.items()}
         out = super().load_state_dict(state_dict, strict=strict, assign=False)
