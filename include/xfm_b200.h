@@ -36,6 +36,12 @@ int xfm_init(void);
 int64_t xfm_launch_count(void);
 /* Human-readable description of the last error recorded by this library on this thread. */
 const char* xfm_last_error(void);
+/* Seed salt: a device-resident 64-bit word (per device, initially 0) that every kernel drawing random numbers (dropout in
+ * the GEMM / attention / LayerNorm-backward kernels, hard-negative sampling) ADDS to the seed it is given.  CUDA-graph
+ * replays repeat kernel arguments verbatim; xfm_seed_salt_bump (a one-thread kernel, capturable) advances the word so each
+ * replayed step draws fresh masks, while the forward and backward kernels of one step still see the same value. */
+int xfm_seed_salt_bump(uint64_t inc, void* stream);
+int xfm_seed_salt_set(uint64_t value, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K1 — tcgen05 GEMM with fused epilogue.

@@ -126,7 +126,22 @@ def roberta_config_dir(cfg):
     return d
 
 
-def build_reference_xfm(cfg, sd_full, load_vision_params=False, load_text_params=False, vision_ckpt="", text_dir=None):
+def bert_config_dir(cfg):
+    """Directory holding a BERT config.json with the dims in `cfg` (path contains 'bert' and not 'roberta': xfm.py:260-265
+    then builds models/xbert.py's BertForMaskedLM)."""
+    d = tempfile.mkdtemp(prefix="bert-tiny-uncased-")
+    js = dict(architectures=["BertForMaskedLM"], attention_probs_dropout_prob=cfg["attn_dropout"], hidden_act="gelu",
+              hidden_dropout_prob=cfg["hidden_dropout"], hidden_size=cfg["hidden"], initializer_range=0.02,
+              intermediate_size=cfg["ffn"], layer_norm_eps=cfg["ln_eps"], max_position_embeddings=cfg["max_pos"],
+              model_type="bert", num_attention_heads=cfg["heads"], num_hidden_layers=cfg["text_layers"],
+              pad_token_id=cfg["pad_id"], type_vocab_size=cfg["type_vocab"], vocab_size=cfg["vocab_size"])
+    with open(os.path.join(d, "config.json"), "w") as f:
+        json.dump(js, f)
+    return d
+
+
+def build_reference_xfm(cfg, sd_full, load_vision_params=False, load_text_params=False, vision_ckpt="", text_dir=None,
+                        fp16_opt_level=None):
     """Build the reference's `models.model_pretrain.XFM` with dims from `cfg` and load `sd_full`
     (reference key layout, see oracle.xfm_oracle.expand_tied).  With sd_full None the model is returned as constructed;
     load_*_params / vision_ckpt / text_dir exercise the reference's constructor-time checkpoint import
@@ -138,7 +153,9 @@ def build_reference_xfm(cfg, sd_full, load_vision_params=False, load_text_params
     os.chdir(REF_ROOT)
     try:
         config = yaml.safe_load(open("configs/xfm-pt/Pretrain_XBrain_base_4m.yaml"))
-        config["text_encoder"] = text_dir or roberta_config_dir(cfg)
+        config["text_encoder"] = text_dir or (bert_config_dir(cfg) if cfg.get("text_arch") == "bert" else roberta_config_dir(cfg))
+        if fp16_opt_level is not None:   # xfm.py:288-290: anything but 'O0' sets config_text.fp16 (xbert: scale q, not the scores)
+            config["accelerator"] = dict(config.get("accelerator", {}), FP16_OPT_LEVEL=fp16_opt_level)
         config["image_res"] = cfg["image_res"]
         vdir = tempfile.mkdtemp(prefix="beit2-base-")
         with open(os.path.join(vdir, "config_beit2_base.json"), "w") as f:

@@ -38,6 +38,7 @@ def base_config(**over):
         num_masking_patches=75, min_num_patches=16,
         use_vision_tokenizer=False, codebook_size=8192, codebook_dim=32,
         use_bbox=True,
+        text_arch="roberta",   # "bert": the models/xbert.py text encoder (BertForMaskedLM naming, absolute position ids)
     )
     cfg.update(over)
     return cfg
@@ -114,7 +115,9 @@ def param_shapes(cfg):
     s[v + "fc_norm.weight"] = (D,)
     s[v + "fc_norm.bias"] = (D,)
 
-    def roberta(prefix, layers, cross, kin=D, heads=("lm_head", "lm_cap_head")):
+    def roberta(prefix, layers, cross, kin=D, heads=("lm_head", "lm_cap_head"), arch="roberta"):
+        if arch == "bert":
+            return bert(prefix, layers)
         e = prefix + "roberta.embeddings."
         s[e + "word_embeddings.weight"] = (V, H)
         s[e + "position_embeddings.weight"] = (cfg["max_pos"], H)
@@ -150,7 +153,33 @@ def param_shapes(cfg):
             if head == "lm_cap_head":  # untied (SURVEY.md §7 "Weight tying")
                 s[h + "decoder.weight"] = (V, H)
 
-    roberta("text_encoder.", cfg["text_layers"], cross=False)
+    def bert(prefix, layers):
+        """BertForMaskedLM without cross-attention (models/xbert.py:1523-1540, 663-707)."""
+        e = prefix + "bert.embeddings."
+        s[e + "word_embeddings.weight"] = (V, H)
+        s[e + "position_embeddings.weight"] = (cfg["max_pos"], H)
+        s[e + "token_type_embeddings.weight"] = (cfg["type_vocab"], H)
+        s[e + "LayerNorm.weight"] = (H,)
+        s[e + "LayerNorm.bias"] = (H,)
+        for i in range(layers):
+            l = f"{prefix}bert.encoder.layer.{i}."
+            for n, shape in (("attention.self.query.weight", (H, H)), ("attention.self.query.bias", (H,)),
+                             ("attention.self.key.weight", (H, H)), ("attention.self.key.bias", (H,)),
+                             ("attention.self.value.weight", (H, H)), ("attention.self.value.bias", (H,)),
+                             ("attention.output.dense.weight", (H, H)), ("attention.output.dense.bias", (H,)),
+                             ("attention.output.LayerNorm.weight", (H,)), ("attention.output.LayerNorm.bias", (H,)),
+                             ("intermediate.dense.weight", (Ff, H)), ("intermediate.dense.bias", (Ff,)),
+                             ("output.dense.weight", (H, Ff)), ("output.dense.bias", (H,)),
+                             ("output.LayerNorm.weight", (H,)), ("output.LayerNorm.bias", (H,))):
+                s[l + n] = shape
+        h = prefix + "cls.predictions."
+        s[h + "bias"] = (V,)
+        s[h + "transform.dense.weight"] = (H, H)
+        s[h + "transform.dense.bias"] = (H,)
+        s[h + "transform.LayerNorm.weight"] = (H,)
+        s[h + "transform.LayerNorm.bias"] = (H,)
+
+    roberta("text_encoder.", cfg["text_layers"], cross=False, arch=cfg.get("text_arch", "roberta"))
     roberta("fusion_encoder.", cfg["fusion_layers"], cross=True)
     if cfg.get("dec_layers", 0) > 0:
         # XFMForVQA.text_decoder = RobertaForCausalLM (models/model_generation.py:41-54): cross-attention over the
@@ -263,6 +292,11 @@ def expand_tied(sd, cfg):
     for i in range(cfg["vision_depth"]):
         out[f"vision_encoder.blocks.{i}.attn.relative_position_index"] = rpi.clone()
     for p in ("text_encoder.", "fusion_encoder."):
+        if p == "text_encoder." and cfg.get("text_arch", "roberta") == "bert":   # xbert.py:687-692,1536-1537
+            out[p + "bert.embeddings.position_ids"] = torch.arange(cfg["max_pos"]).expand((1, -1)).clone()
+            out[p + "cls.predictions.decoder.weight"] = out[p + "bert.embeddings.word_embeddings.weight"]
+            out[p + "cls.predictions.decoder.bias"] = out[p + "cls.predictions.bias"]
+            continue
         out[p + "roberta.embeddings.position_ids"] = torch.arange(cfg["max_pos"]).expand((1, -1)).clone()
         out[p + "lm_head.decoder.weight"] = out[p + "roberta.embeddings.word_embeddings.weight"]
         out[p + "lm_head.decoder.bias"] = out[p + "lm_head.bias"]
@@ -289,7 +323,7 @@ def make_batch(cfg, B, L=40, M=15, seed=1, image_uniform=False):
         image = torch.randn(B, 3, res, res, generator=g)
     V = cfg["vocab_size"]
     text_ids = torch.randint(3, V - 1, (B, L), generator=g)
-    text_ids[:, 0] = 0
+    text_ids[:, 0] = 0 if cfg["pad_id"] != 0 else 2   # bos / cls token: never the padding id
     text_atts = torch.ones(B, L, dtype=torch.long)
     for b in range(B):
         if b % 2 == 1:  # every other row padded to 3/4 length
@@ -461,12 +495,22 @@ def roberta_position_ids(input_ids, pad_id):
     return (torch.cumsum(mask, dim=1).type_as(mask) * mask).long() + pad_id
 
 
+def bert_embeddings(input_ids, sd, p, cfg):
+    """models/xbert.py:167-221 (eval): word + token_type[0] + position[0..L-1], LayerNorm."""
+    e = p + "bert.embeddings."
+    L = input_ids.shape[1]
+    emb = F.embedding(input_ids, sd[e + "word_embeddings.weight"], padding_idx=cfg["pad_id"])   # xbert.py:172
+    emb = emb + sd[e + "token_type_embeddings.weight"][0] + sd[e + "position_embeddings.weight"][:L]
+    return _ln(emb, sd, e + "LayerNorm", cfg["ln_eps"])
+
+
 def roberta_embeddings(input_ids, sd, p, cfg):
     """models/xroberta.py:104-137 (eval: dropout off)."""
     e = p + "roberta.embeddings."
     pos = roberta_position_ids(input_ids, cfg["pad_id"])
-    emb = F.embedding(input_ids, sd[e + "word_embeddings.weight"]) + sd[e + "token_type_embeddings.weight"][0]
-    emb = emb + F.embedding(pos, sd[e + "position_embeddings.weight"])
+    emb = F.embedding(input_ids, sd[e + "word_embeddings.weight"], padding_idx=cfg["pad_id"])   # xroberta.py:80,100-102
+    emb = emb + sd[e + "token_type_embeddings.weight"][0]
+    emb = emb + F.embedding(pos, sd[e + "position_embeddings.weight"], padding_idx=cfg["pad_id"])
     return _ln(emb, sd, e + "LayerNorm", cfg["ln_eps"])
 
 
@@ -475,14 +519,20 @@ def _heads(x, H):
     return x.view(B, L, H, D // H).permute(0, 2, 1, 3)
 
 
-def roberta_attention(h, ext_mask, sd, p, H, eps, enc=None, enc_mask=None):
-    """models/xroberta.py:201-289 (self / cross) + RobertaSelfOutput :300-304."""
+def roberta_attention(h, ext_mask, sd, p, H, eps, enc=None, enc_mask=None, scale_after=False):
+    """models/xroberta.py:201-289 (self / cross) + RobertaSelfOutput :300-304.  scale_after: models/xbert.py:296-301,329-330
+    without config.fp16 divides the SCORES by sqrt(d) instead of q."""
     q = F.linear(h, sd[p + "self.query.weight"], sd[p + "self.query.bias"])
     src, mask = (h, ext_mask) if enc is None else (enc, enc_mask)
     k = _heads(F.linear(src, sd[p + "self.key.weight"], sd[p + "self.key.bias"]), H)
     v = _heads(F.linear(src, sd[p + "self.value.weight"], sd[p + "self.value.bias"]), H)
-    q = _heads(q, H) / math.sqrt(q.shape[-1] // H)  # scaled BEFORE QK^T (:237)
+    d = q.shape[-1] // H
+    q = _heads(q, H)
+    if not scale_after:
+        q = q / math.sqrt(d)  # scaled BEFORE QK^T (:237)
     s = torch.matmul(q, k.transpose(-1, -2))
+    if scale_after:
+        s = s / math.sqrt(d)
     if mask is not None:
         s = s + mask
     pr = torch.softmax(s, dim=-1)
@@ -492,9 +542,9 @@ def roberta_attention(h, ext_mask, sd, p, H, eps, enc=None, enc_mask=None):
     return _ln(o + h, sd, p + "output.LayerNorm", eps)
 
 
-def roberta_layer(h, ext_mask, sd, p, cfg, enc=None, enc_mask=None):
-    """models/xroberta.py:405-473: self-attn -> [cross-attn] -> FFN, all post-LN."""
-    a = roberta_attention(h, ext_mask, sd, p + "attention.", cfg["heads"], cfg["ln_eps"])
+def roberta_layer(h, ext_mask, sd, p, cfg, enc=None, enc_mask=None, scale_after=False):
+    """models/xroberta.py:405-473 (= models/xbert.py:455-533): self-attn -> [cross-attn] -> FFN, all post-LN."""
+    a = roberta_attention(h, ext_mask, sd, p + "attention.", cfg["heads"], cfg["ln_eps"], scale_after=scale_after)
     if enc is not None:
         a = roberta_attention(a, ext_mask, sd, p + "crossattention.", cfg["heads"], cfg["ln_eps"], enc, enc_mask)
     i = F.gelu(F.linear(a, sd[p + "intermediate.dense.weight"], sd[p + "intermediate.dense.bias"]))
@@ -514,10 +564,13 @@ def inverted_mask(atts):
 
 def text_forward(text_ids, text_atts, sd, cfg, prefix="text_encoder.", collect=None):
     """XFMBase.get_text_embeds (models/xfm.py:600-611): 12 layers without cross-attention."""
-    h = roberta_embeddings(text_ids, sd, prefix, cfg)
+    bert = cfg.get("text_arch", "roberta") == "bert" and prefix == "text_encoder."
+    h = bert_embeddings(text_ids, sd, prefix, cfg) if bert else roberta_embeddings(text_ids, sd, prefix, cfg)
     m = extended_mask(text_atts)
+    stem = "bert." if bert else "roberta."
     for i in range(cfg["text_layers"]):
-        h = roberta_layer(h, m, sd, f"{prefix}roberta.encoder.layer.{i}.", cfg)
+        h = roberta_layer(h, m, sd, f"{prefix}{stem}encoder.layer.{i}.", cfg,
+                          scale_after=bert and not cfg.get("text_fp16", True))
         if collect is not None:
             collect.append(h)
     return h
@@ -537,7 +590,13 @@ def fusion_forward(text_embeds, text_atts, image_embeds, image_atts, sd, cfg, pr
 
 
 def lm_head(x, sd, p, cfg):
-    """RobertaLMHead (models/xroberta.py:1313-1333), decoder tied to the word embeddings."""
+    """RobertaLMHead (models/xroberta.py:1313-1333) / BertOnlyMLMHead (models/xbert.py:663-707), decoder tied to the word
+    embeddings."""
+    if cfg.get("text_arch", "roberta") == "bert" and p == "text_encoder.":
+        c = p + "cls.predictions."
+        x = F.linear(x, sd[c + "transform.dense.weight"], sd[c + "transform.dense.bias"])
+        x = _ln(F.gelu(x), sd, c + "transform.LayerNorm", cfg["ln_eps"])
+        return F.linear(x, sd[p + "bert.embeddings.word_embeddings.weight"], sd[c + "bias"])
     x = F.linear(x, sd[p + "lm_head.dense.weight"], sd[p + "lm_head.dense.bias"])
     x = _ln(F.gelu(x), sd, p + "lm_head.layer_norm", cfg["ln_eps"])
     return F.linear(x, sd[p + "roberta.embeddings.word_embeddings.weight"], sd[p + "lm_head.bias"])

@@ -354,6 +354,38 @@ def test_region_branch_against_reference(golden_dir, record):
         _grad_check(model, g["grads"], list(g["grads"]))
 
 
+def test_bert_text_encoder_variant_against_reference(golden_dir, record):
+    """SURVEY §8 row x2 (north_star names models/xbert.py BertSelfAttention): a BERT-class text encoder — BertForMaskedLM
+    parameter names, absolute position ids, padding_idx 0, LayerNorm eps 1e-12 — on the same kernels, against the fixture
+    the UNMODIFIED reference produced (identical for both placements of 1/sqrt(d), xbert.py:296-301,329-330)."""
+    from xfm_b200.model_pretrain import XFM
+    g = _load(golden_dir, "tiny_bert.pt")
+    cfg = g["cfg"]
+    model = XFM(dict(cfg), init=lambda n, s: O.make_tensor(n, s, 0), device="cuda").eval()
+    sd_names = set(model.state_dict())
+    for n in ("text_encoder.bert.embeddings.position_ids", "text_encoder.cls.predictions.decoder.weight",
+              "text_encoder.cls.predictions.transform.LayerNorm.weight", "fusion_encoder.roberta.embeddings.word_embeddings.weight"):
+        assert n in sd_names, n
+    assert not any(k.startswith("text_encoder.roberta.") or k.startswith("text_encoder.lm_") for k in sd_names)
+    b = {k: v.cuda() for k, v in O.make_batch(cfg, 4, L=24, M=6, seed=1).items()}
+    with torch.no_grad():
+        te = model.get_text_embeds(b["text_ids"], b["text_atts"])
+    assert _maxabs(te, g["text_embeds"]) <= 2e-2
+    model._forced_negatives = (g["image_neg_idx"], g["text_neg_idx"])
+    out = model(b["image"], b["text_ids"], b["text_atts"], text_ids_masked=b["text_ids_masked"], masked_pos=b["masked_pos"],
+                masked_ids=b["masked_ids"], ret_mim_loss=False, data_source="image")
+    for k, v in g["losses"].items():
+        rel = abs(float(out[k]) - v) / max(1.0, abs(v))
+        record("bert_variant", loss=k, mine=float(out[k]), reference=v, rel=rel)
+        assert rel <= (2e-3 if k == "loss_itc" else 1e-3), (k, float(out[k]), v)
+    (out["loss_itc"] + out["loss_itm"] + out["loss_mlm"]).backward()
+    _grad_check(model, g["grads"], list(g["grads"]))
+    model.zero_grad()
+    t = model(None, b["text_ids"], b["text_atts"], text_ids_masked=b["text_ids_masked"], masked_pos=b["masked_pos"],
+              masked_ids=b["masked_ids"])["loss_mlm"]
+    assert abs(float(t) - g["text_only_mlm"]) <= 1e-3 * abs(g["text_only_mlm"])
+
+
 def test_retrieval_model_against_oracle():
     """models/model_retrieval.py:26-37 (BASELINE config #3 shape, tiny widths): ITC with idx soft labels + idx-masked
     hard-negative ITM, text gradients through the fusion encoder (is_pretrain=False)."""

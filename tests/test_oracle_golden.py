@@ -172,3 +172,29 @@ def test_region_branch_against_reference(golden_dir):
     coord = torch.tensor([[0.5, 0.5, 0.2, 0.2], [0.3, 0.3, -0.1, 0.2]])
     lb, lg = O.bbox_loss(coord, torch.tensor([[0.5, 0.5, 0.2, 0.2], [0.3, 0.3, 0.1, 0.2]]))
     assert float(lg) == 0.0 and abs(float(lb) - 0.1) < 1e-7
+
+
+def test_bert_text_encoder_variant_against_reference(golden_dir):
+    """models/xbert.py as the text encoder: BertForMaskedLM naming, absolute position ids, and the
+    placement of 1/sqrt(d) (xbert.py:296-301,329-330) — the reference produced bit-identical results for both placements."""
+    g = _load(golden_dir, "tiny_bert.pt")
+    assert g["scale_order_identical"]
+    cfg = g["cfg"]
+    assert cfg["text_arch"] == "bert"
+    batch = O.make_batch(cfg, 4, L=24, M=6, seed=1)
+    for fp16 in (True, False):
+        sd = O.make_state_dict(cfg, seed=0)
+        for v in sd.values():
+            if v.dtype.is_floating_point:
+                v.requires_grad_(True)
+        c = dict(cfg, text_fp16=fp16)
+        out = O.pretrain_forward(sd, c, batch, g["image_neg_idx"], g["text_neg_idx"])
+        for k, v in g["losses"].items():
+            assert abs(float(out[k]) - v) <= 2e-5 * max(1.0, abs(v)), (fp16, k, float(out[k]), v)
+        mlm = O.text_mlm_loss(batch["text_ids_masked"], batch["text_atts"], batch["masked_pos"], batch["masked_ids"], sd, c)
+        assert abs(float(mlm) - g["text_only_mlm"]) <= 2e-5 * abs(g["text_only_mlm"])
+        torch.testing.assert_close(O.text_forward(batch["text_ids"], batch["text_atts"], sd, c).detach(), g["text_embeds"],
+                                   rtol=1e-5, atol=1e-5)
+        (out["loss_itc"] + out["loss_itm"] + out["loss_mlm"]).backward()
+        for n, ref in g["grads"].items():
+            assert float((sd[n].grad - ref).abs().max()) <= 1e-5 * float(ref.abs().max()) + 1e-9, (fp16, n)

@@ -12,6 +12,7 @@ What is recorded (all produced by the reference's own code, through oracle/ref_s
   * masks.pt     — MaskingGenerator outputs for fixed (random, np.random) seeds.
   * tiny_region.pt — the region / bbox branch of the pre-training forward (idx_to_group_img, region masks, L1 + GIoU):
                    `python tools/make_golden.py --only-region`.
+  * tiny_bert.pt — the same forward with the models/xbert.py text encoder (`--only-bert`), both scale orders.
   * tiny_vqa.pt  — XFMForVQA (models/model_generation.py), tiny config with a 2-layer causal decoder: training loss,
                    per-answer losses, question states, parameter gradients; rank_answer ids / probabilities.
                    `python tools/make_golden.py --only-vqa` regenerates just this file.
@@ -307,12 +308,63 @@ def region_golden():
                 text_neg_idx=torch.argmax(w_i2t, 1), grads={n: params[n].grad.detach().clone() for n in names}, **rec)
 
 
+def bert_golden():
+    """models/xbert.py text encoder (north_star names it): the pre-training forward with a BERT-class text
+    encoder, once with config.fp16 (1/sqrt(d) applied to q) and once without (applied to the scores, xbert.py:296-301,
+    329-330).  The two must be — and are — bit-identical at head_dim 64 (the factor is 0.125)."""
+    cfg = O.tiny_config(text_arch="bert", pad_id=0, type_vocab=2, ln_eps=1e-12)
+    sd = O.make_state_dict(cfg, seed=0)
+    batch = O.make_batch(cfg, 4, L=24, M=6, seed=1)
+    out = {}
+    for level in ("O1", "O0"):
+        model = ref_shim.build_reference_xfm(cfg, O.expand_tied(sd, cfg), fp16_opt_level=level)
+        assert type(model.text_encoder).__name__ == "BertForMaskedLM"
+        assert model.text_encoder.bert.encoder.layer[0].attention.self.fp16 == (level != "O0")
+        calls = []
+        orig = torch.multinomial
+        torch.multinomial = lambda w, n, *a, **k: (calls.append(w.detach().clone()), torch.argmax(w).view(1))[1]
+        rec = {}
+        orig_text = model.get_text_embeds
+
+        def spy_text(*a, **k):
+            o = orig_text(*a, **k)
+            rec.setdefault("text_embeds", o.detach().clone())
+            return o
+        model.get_text_embeds = spy_text
+        try:
+            model.zero_grad()
+            loss = model(ret_mim_loss=False, data_source="image", **batch)
+            (loss["loss_itc"] + loss["loss_itm"] + loss["loss_mlm"]).backward()
+            text_only = model(None, batch["text_ids"], batch["text_atts"], text_ids_masked=batch["text_ids_masked"],
+                              masked_pos=batch["masked_pos"], masked_ids=batch["masked_ids"])["loss_mlm"]
+        finally:
+            torch.multinomial = orig
+        B = 4
+        names = ["text_encoder.bert.embeddings.word_embeddings.weight", "text_encoder.bert.embeddings.position_embeddings.weight",
+                 "text_encoder.bert.embeddings.token_type_embeddings.weight",
+                 "text_encoder.bert.encoder.layer.1.attention.self.query.weight",
+                 "text_encoder.bert.encoder.layer.0.output.LayerNorm.weight", "text_proj.weight"]
+        params = dict(model.named_parameters())
+        out[level] = dict(losses={k: float(v) for k, v in loss.items() if k in ("loss_itc", "loss_itm", "loss_mlm")},
+                          text_only_mlm=float(text_only), text_embeds=rec["text_embeds"],
+                          image_neg_idx=torch.argmax(torch.stack(calls[:B], 0), 1),
+                          text_neg_idx=torch.argmax(torch.stack(calls[B:2 * B], 0), 1),
+                          grads={n: params[n].grad.detach().clone() for n in names})
+    assert out["O1"]["losses"] == out["O0"]["losses"] and torch.equal(out["O1"]["text_embeds"], out["O0"]["text_embeds"])
+    return dict(cfg=cfg, scale_order_identical=True, **out["O1"])
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     if "--only-vqa" in sys.argv:
         v = vqa_golden()
         torch.save(v, os.path.join(GOLD, "tiny_vqa.pt"))
         print("tiny_vqa", v["loss"], v["topk_ids"].tolist())
+        return
+    if "--only-bert" in sys.argv:
+        r = bert_golden()
+        torch.save(r, os.path.join(GOLD, "tiny_bert.pt"))
+        print("tiny_bert", r["losses"], r["text_only_mlm"])
         return
     if "--only-region" in sys.argv:
         r = region_golden()
@@ -333,6 +385,7 @@ def main():
     torch.save(itc_idx_golden(), os.path.join(GOLD, "itc_idx.pt"))
     torch.save(vqa_golden(), os.path.join(GOLD, "tiny_vqa.pt"))
     torch.save(region_golden(), os.path.join(GOLD, "tiny_region.pt"))
+    torch.save(bert_golden(), os.path.join(GOLD, "tiny_bert.pt"))
     tv = run_reference(O.tiny_config(use_vision_tokenizer=True), B=4, L=24, M=6, image_uniform=True, want_grads=True)
     torch.save(tv, os.path.join(GOLD, "tiny_vq.pt"))
     print("tiny_vq", tv["losses"])

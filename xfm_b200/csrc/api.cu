@@ -10,6 +10,9 @@ static thread_local char g_err[512] = "";
 static std::atomic<int64_t> g_launches{0};
 static TensorMapEncodeFn g_encode = nullptr;
 static int g_num_sms = 0;
+static uint64_t* g_salt[64] = {nullptr};
+
+__global__ void seed_salt_bump_kernel(uint64_t* salt, uint64_t inc) { *salt += inc; }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -20,6 +23,11 @@ void set_error(const char* fmt, ...) {
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 TensorMapEncodeFn get_tensor_map_encoder() { return g_encode; }
 int num_sms() { return g_num_sms > 0 ? g_num_sms : 148; }
+const uint64_t* seed_salt_ptr() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return g_salt[dev & 63];
+}
 
 }  // namespace xfm
 
@@ -45,7 +53,28 @@ int xfm_init(void) {
     }
     g_encode = (TensorMapEncodeFn)fn;
   }
+  if (!g_salt[dev & 63]) {
+    e = cudaMalloc((void**)&g_salt[dev & 63], sizeof(uint64_t));
+    if (e != cudaSuccess) { set_error("cudaMalloc(seed salt): %s", cudaGetErrorString(e)); return (int)e; }
+    e = cudaMemset(g_salt[dev & 63], 0, sizeof(uint64_t));
+    if (e != cudaSuccess) return (int)e;
+  }
   return 0;
+}
+
+int xfm_seed_salt_bump(uint64_t inc, void* stream) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!g_salt[dev & 63]) { set_error("xfm_init was not called on this device"); return XFM_ERR_BAD_ARG; }
+  seed_salt_bump_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(g_salt[dev & 63], inc);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+int xfm_seed_salt_set(uint64_t value, void* stream) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!g_salt[dev & 63]) { set_error("xfm_init was not called on this device"); return XFM_ERR_BAD_ARG; }
+  return (int)cudaMemcpyAsync(g_salt[dev & 63], &value, sizeof(value), cudaMemcpyHostToDevice, (cudaStream_t)stream);
 }
 
 int64_t xfm_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

@@ -36,6 +36,7 @@ struct AttnArgs {
   int B, H, Lq, Lk;
   float scale, dropout_p;
   uint64_t seed;
+  const uint64_t* salt;  // device word added to the seed (see internal.h seed_salt_ptr)
   // backward only
   const bf16* dout;
   int64_t do_stride;
@@ -148,7 +149,7 @@ XFM_DEVINL bool drop_keep(const AttnArgs& a, int b, int h, int q, int key) {
   // element index with an EVEN row stride: keys (2k, 2k+1) of a row share one hash pair (the tcgen05 kernels evaluate the
   // mask pair-wise; both kernel families must index identically so forward and backward regenerate the same mask)
   const uint64_t idx = (((uint64_t)b * a.H + h) * a.Lq + q) * (uint64_t)((a.Lk + 1) & ~1) + key;
-  return drop_keep_idx(a.seed, idx, a.dropout_p);
+  return drop_keep_idx(a.seed + *a.salt, idx, a.dropout_p);
 }
 
 // Pair-wise evaluation of the same mask: pair base of a (b, h, q) row, then both keys (key, key+1), key even, at once.
@@ -236,7 +237,7 @@ attn_fwd_kernel(const AttnArgs a) {
   for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
   const float inv_keep = a.dropout_p > 0.f ? 1.0f / (1.0f - a.dropout_p) : 1.0f;
-  const uint32_t seed_mix = drop_seed_mix(a.seed), thr = drop_threshold(a.dropout_p);
+  const uint32_t seed_mix = drop_seed_mix(a.seed + *a.salt), thr = drop_threshold(a.dropout_p);
   const uint64_t dp0 = drop_row_pair_base(a, b, h, r0), dp1 = drop_row_pair_base(a, b, h, r1);
   for (int kb = 0; kb < LkP; kb += AT_TILE) {
     float s[8][4];
@@ -363,7 +364,7 @@ attn_bwd_dq_kernel(const AttnArgs a) {
   const int64_t st = ((int64_t)b * a.H + h) * a.Lq;
   const float lse0 = r0 < a.Lq ? a.lse[st + r0] : 0.f, lse1 = r1 < a.Lq ? a.lse[st + r1] : 0.f;
   const float dl0 = r0 < a.Lq ? a.delta[st + r0] : 0.f, dl1 = r1 < a.Lq ? a.delta[st + r1] : 0.f;
-  const uint32_t seed_mix = drop_seed_mix(a.seed), thr = drop_threshold(a.dropout_p);
+  const uint32_t seed_mix = drop_seed_mix(a.seed + *a.salt), thr = drop_threshold(a.dropout_p);
   const uint64_t dpb0 = drop_row_pair_base(a, b, h, r0), dpb1 = drop_row_pair_base(a, b, h, r1);
   const float inv_keep = a.dropout_p > 0.f ? 1.0f / (1.0f - a.dropout_p) : 1.0f;
   float dq[8][4];
@@ -551,7 +552,7 @@ static void fill_args(const xfm_attn_params* p, AttnArgs& a) {
   a.out = (bf16*)p->out; a.o_stride = p->o_stride; a.lse = p->lse;
   a.bias = p->bias; a.bias_ld = p->bias_ld; a.kmask = p->kmask; a.kv_index = p->kv_index;
   a.B = p->B; a.H = p->H; a.Lq = p->Lq; a.Lk = p->Lk;
-  a.scale = p->scale; a.dropout_p = p->dropout_p; a.seed = p->dropout_seed;
+  a.scale = p->scale; a.dropout_p = p->dropout_p; a.seed = p->dropout_seed; a.salt = seed_salt_ptr();
   a.dout = (const bf16*)p->dout; a.do_stride = p->do_stride; a.delta = p->delta;
   a.dq = (bf16*)p->dq; a.dk = (bf16*)p->dk; a.dv = (bf16*)p->dv;
   a.dq_stride = p->dq_stride; a.dk_stride = p->dk_stride; a.dv_stride = p->dv_stride;

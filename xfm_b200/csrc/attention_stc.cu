@@ -32,6 +32,7 @@ struct SAttnArgs {
   int B, H, n_grp, n_tiles;
   float scale, dropout_p;
   uint64_t seed;
+  const uint64_t* salt;
   const float* delta;    // [B, H, 40]
   bf16 *dq, *dk, *dv;
   int64_t dq_stride, dk_stride, dv_stride;
@@ -182,7 +183,7 @@ sattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     const float scale2 = a.scale * ST_LOG2E;
     const bool drop_on = a.dropout_p > 0.f;
     const float inv_keep = drop_on ? 1.0f / (1.0f - a.dropout_p) : 1.0f;
-    const uint32_t seed_mix = drop_seed_mix(a.seed), thr = drop_threshold(a.dropout_p);
+    const uint32_t seed_mix = drop_seed_mix(a.seed + *a.salt), thr = drop_threshold(a.dropout_p);
     uint8_t* myP = sP + t * 32768 + (r >> 3) * 1024 + (r & 7) * 128;
     const int sw = r & 7;
     uint32_t ph = 0;
@@ -422,7 +423,7 @@ sattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     const float scale2 = a.scale * ST_LOG2E;
     const bool drop_on = a.dropout_p > 0.f;
     const float inv_keep = drop_on ? 1.0f / (1.0f - a.dropout_p) : 1.0f;
-    const uint32_t seed_mix = drop_seed_mix(a.seed), thr = drop_threshold(a.dropout_p);
+    const uint32_t seed_mix = drop_seed_mix(a.seed + *a.salt), thr = drop_threshold(a.dropout_p);
     uint8_t* myP = sP + (r >> 3) * 1024 + (r & 7) * 128;
     uint8_t* myD = sdS + (r >> 3) * 1024 + (r & 7) * 128;
     const int sw = r & 7;
@@ -568,7 +569,7 @@ bool self_attention_tc_supported(const xfm_attn_params* p) {
 
 static int st_fill(const xfm_attn_params* p, SAttnArgs& a) {
   a.out = (bf16*)p->out; a.o_stride = p->o_stride; a.lse = p->lse; a.kmask = p->kmask;
-  a.B = p->B; a.H = p->H; a.scale = p->scale; a.dropout_p = p->dropout_p; a.seed = p->dropout_seed;
+  a.B = p->B; a.H = p->H; a.scale = p->scale; a.dropout_p = p->dropout_p; a.seed = p->dropout_seed; a.salt = seed_salt_ptr();
   a.n_grp = (p->B + ST_SLOTS - 1) / ST_SLOTS;
   a.n_tiles = a.n_grp * a.H;
   a.delta = p->delta;

@@ -26,6 +26,7 @@ struct XAttnArgs {
   int B, Bkv, H;
   float scale, dropout_p;
   uint64_t seed;
+  const uint64_t* salt;
   int items_per_cta;
   // backward
   const float* delta;         // [B, H, LQS]
@@ -210,7 +211,7 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     const float scale2 = a.scale * 1.4426950408889634f;
     const bool drop_on = a.dropout_p > 0.f;
     const float inv_keep = drop_on ? 1.0f / (1.0f - a.dropout_p) : 1.0f;
-    const uint32_t seed_mix = drop_seed_mix(a.seed), thr = drop_threshold(a.dropout_p);
+    const uint32_t seed_mix = drop_seed_mix(a.seed + *a.salt), thr = drop_threshold(a.dropout_p);
     uint8_t* myP = sP + t * Cfg::P_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
     const int sw = r & 7;
     XWalker<GMAX> w(a, item0, item1);
@@ -444,7 +445,7 @@ xattn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     const float scale2 = a.scale * 1.4426950408889634f;
     const bool drop_on = a.dropout_p > 0.f;
     const float inv_keep = drop_on ? 1.0f / (1.0f - a.dropout_p) : 1.0f;
-    const uint32_t seed_mix = drop_seed_mix(a.seed), thr = drop_threshold(a.dropout_p);
+    const uint32_t seed_mix = drop_seed_mix(a.seed + *a.salt), thr = drop_threshold(a.dropout_p);
     uint8_t* myS = sdS + (r >> 3) * 1024 + (r & 7) * 128;
     const int sw = r & 7;
     const int cb = wg == 0 ? 0 : SPLIT, ce = wg == 0 ? SPLIT : LPAD;
@@ -687,7 +688,7 @@ xattn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
     const float scale2 = a.scale * 1.4426950408889634f;
     const bool drop_on = a.dropout_p > 0.f;
     const float inv_keep = drop_on ? 1.0f / (1.0f - a.dropout_p) : 1.0f;
-    const uint32_t seed_mix = drop_seed_mix(a.seed), thr = drop_threshold(a.dropout_p);
+    const uint32_t seed_mix = drop_seed_mix(a.seed + *a.salt), thr = drop_threshold(a.dropout_p);
     uint8_t* myP = sPT + (r >> 3) * 1024 + (r & 7) * 128;
     uint8_t* myD = sdST + (r >> 3) * 1024 + (r & 7) * 128;
     const int sw = r & 7;
@@ -995,7 +996,7 @@ xattn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
     const float scale2 = a.scale * 1.4426950408889634f;
     const bool drop_on = a.dropout_p > 0.f;
     const float inv_keep = drop_on ? 1.0f / (1.0f - a.dropout_p) : 1.0f;
-    const uint32_t seed_mix = drop_seed_mix(a.seed), thr = drop_threshold(a.dropout_p);
+    const uint32_t seed_mix = drop_seed_mix(a.seed + *a.salt), thr = drop_threshold(a.dropout_p);
     uint8_t* myS = sdS + (r >> 3) * 1024 + (r & 7) * 128;
     uint8_t* myP = sP + (r >> 3) * 1024 + (r & 7) * 128;
     const int sw = r & 7;
@@ -1164,7 +1165,7 @@ bool cross_attention_tc_supported(const xfm_attn_params* p) {
 static void xt_fill(const xfm_attn_params* p, XAttnArgs& a) {
   a.out = (bf16*)p->out; a.o_stride = p->o_stride; a.lse = p->lse;
   a.kv_offsets = p->kv_offsets; a.kv_samples = p->kv_samples;
-  a.B = p->B; a.Bkv = p->Bkv; a.H = p->H; a.scale = p->scale; a.dropout_p = p->dropout_p; a.seed = p->dropout_seed;
+  a.B = p->B; a.Bkv = p->Bkv; a.H = p->H; a.scale = p->scale; a.dropout_p = p->dropout_p; a.seed = p->dropout_seed; a.salt = seed_salt_ptr();
   a.delta = p->delta;
   a.dq = (bf16*)p->dq; a.dk = (bf16*)p->dk; a.dv = (bf16*)p->dv;
   a.dq_stride = p->dq_stride; a.dk_stride = p->dk_stride; a.dv_stride = p->dv_stride;

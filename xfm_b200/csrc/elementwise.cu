@@ -117,7 +117,8 @@ layernorm_bwd_kernel(const void* __restrict__ dy, int dy_dtype, const void* __re
                      const float* __restrict__ stats, const float* __restrict__ w, const void* __restrict__ add_in,
                      int add_dtype, void* __restrict__ dx, int dx_dtype, float* __restrict__ dw, float* __restrict__ db,
                      int M, int D, int rows_per_cta, int nw,   // nw: warps that own a staging ring (<= LN_WARPS)
-                     bf16* __restrict__ dx16, float* __restrict__ dbias, float drop_p, uint64_t drop_seed) {
+                     bf16* __restrict__ dx16, float* __restrict__ dbias, float drop_p, uint64_t drop_seed,
+                     const uint64_t* __restrict__ salt) {
   extern __shared__ __align__(16) uint8_t ln_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int dy_b = D * (dy_dtype == 1 ? 4 : 2), x_b = D * (x_dtype == 1 ? 4 : 2);
@@ -131,7 +132,7 @@ layernorm_bwd_kernel(const void* __restrict__ dy, int dy_dtype, const void* __re
 #pragma unroll
   for (int i = 0; i < (DENSE ? NV : 1); ++i) ad[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   const float inv_keep = (DENSE && drop_p > 0.f) ? 1.0f / (1.0f - drop_p) : 1.0f;
-  const uint32_t seed_mix = drop_seed_mix(drop_seed), thr = drop_threshold(drop_p);
+  const uint32_t seed_mix = drop_seed_mix(drop_seed + *salt), thr = drop_threshold(drop_p);
   const int row0 = blockIdx.x * rows_per_cta;
   const int row1 = (warp < nw) ? min(M, row0 + rows_per_cta) : 0;   // ring-less warps only join the final reduction
 
@@ -426,7 +427,8 @@ __global__ void gelu_bwd_kernel(const void* __restrict__ dy, int dy_dtype, const
 // y[i] = keep(seed, i) ? x[i] / (1-p) : 0 with the SAME (seed, row * N + col) indexing as the GEMM dropout epilogue, so
 // the backward pass re-applies the forward mask to the incoming gradient without storing it (xroberta.py:302,383).
 __global__ void dropout_apply_kernel(const void* __restrict__ x, int x_dtype, bf16* __restrict__ y, size_t n4, float p,
-                                     uint64_t seed) {
+                                     uint64_t seed, const uint64_t* __restrict__ salt) {
+  seed += *salt;
   const float inv_keep = 1.0f / (1.0f - p);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     float4 v = ld4(x, x_dtype, 4 * i);
@@ -818,7 +820,7 @@ int layernorm_bwd_dense(const void* dy, int dy_dtype, const void* x, int x_dtype
         attr = smem;
       }
       layernorm_bwd_kernel<NV, true><<<grid, LN_WARPS * 32, smem, s>>>(dy, dy_dtype, x, x_dtype, stats, w, add_in, add_dtype, dx,
-                                                                       dx_dtype, dw, db, M, D, rpc, nw, dx16, dbias, drop_p, drop_seed);
+                                                                       dx_dtype, dw, db, M, D, rpc, nw, dx16, dbias, drop_p, drop_seed, seed_salt_ptr());
     });
     LAUNCH_END();
   }
@@ -830,7 +832,7 @@ int layernorm_bwd_dense(const void* dy, int dy_dtype, const void* x, int x_dtype
       attr = smem;
     }
     layernorm_bwd_kernel<NV, false><<<grid, LN_WARPS * 32, smem, s>>>(dy, dy_dtype, x, x_dtype, stats, w, add_in, add_dtype, dx,
-                                                                      dx_dtype, dw, db, M, D, rpc, nw, nullptr, nullptr, 0.f, 0);
+                                                                      dx_dtype, dw, db, M, D, rpc, nw, nullptr, nullptr, 0.f, 0, seed_salt_ptr());
   });
   LAUNCH_END();
 }
@@ -908,7 +910,7 @@ int gelu_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, bf16* dx,
 int dropout_apply(const void* x, int x_dtype, bf16* y, size_t n, float p, uint64_t seed, cudaStream_t s) {
   if (n & 3) { set_error("dropout: n must be a multiple of 4"); return XFM_ERR_BAD_ARG; }
   if (!n) return 0;
-  dropout_apply_kernel<<<grid_1d(n / 4, 256), 256, 0, s>>>(x, x_dtype, y, n / 4, p, seed);
+  dropout_apply_kernel<<<grid_1d(n / 4, 256), 256, 0, s>>>(x, x_dtype, y, n / 4, p, seed, seed_salt_ptr());
   LAUNCH_END();
 }
 

@@ -33,6 +33,7 @@ struct GemmArgs {
   const void* residual;
   float dropout_p;
   uint64_t dropout_seed;
+  const uint64_t* seed_salt;  // device word added to every dropout seed (advanced once per step: CUDA-graph replays)
   int vec_ok;    // every epilogue pointer / leading dimension allows 2-element vector access at even columns
   int epi_mode;  // see epilogue_block
   int tma_epi;   // CTA-pair kernel: modes 0 / 1 store bf16 tiles with TMA (epilogue_tma_block); 2 = f32 TMA epilogue
@@ -209,8 +210,8 @@ XFM_DEVINL void epilogue_block(const GemmArgs& g, const float* stage, int row_ba
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const uint64_t base = (uint64_t)(row_base + rr0 + 2 * i) * (uint64_t)g.N + (uint64_t)col;
-          v[i].x = drop_keep_idx(g.dropout_seed, base, g.dropout_p) ? v[i].x * inv_keep : 0.f;
-          v[i].y = drop_keep_idx(g.dropout_seed, base + 1, g.dropout_p) ? v[i].y * inv_keep : 0.f;
+          v[i].x = drop_keep_idx(g.dropout_seed + *g.seed_salt, base, g.dropout_p) ? v[i].x * inv_keep : 0.f;
+          v[i].y = drop_keep_idx(g.dropout_seed + *g.seed_salt, base + 1, g.dropout_p) ? v[i].y * inv_keep : 0.f;
         }
       }
       if (want_res) {
@@ -697,7 +698,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     const bool has_scale = g.col_scale != nullptr || g.row_group_scale != nullptr;
     const bool has_drop = g.dropout_p > 0.f;
     const float inv_keep = has_drop ? 1.0f / (1.0f - g.dropout_p) : 1.0f;
-    const uint32_t seed_mix = drop_seed_mix(g.dropout_seed), thr = drop_threshold(g.dropout_p);
+    const uint32_t seed_mix = drop_seed_mix(g.dropout_seed + *g.seed_salt), thr = drop_threshold(g.dropout_p);
     // block sequence of this warp: tiles t = pair_id, pair_id + num_pairs, ...; blocks c_begin .. c_end-1 while inside N
     auto block_at = [&](int t, int c, int& rb, int& n) -> bool {
       if (t >= num_tiles) return false;
@@ -1138,7 +1139,7 @@ int gemm_bf16(const xfm_gemm_params* p, cudaStream_t stream) {
   g.ldc = p->ldc; g.ld_aux_in = p->ld_aux_in; g.ld_aux_out = p->ld_aux_out; g.ld_res = p->ld_res;
   g.C = p->C; g.bias = p->bias; g.aux_in = (const bf16*)p->aux_in; g.aux_out = (bf16*)p->aux_out;
   g.col_scale = p->col_scale; g.row_group_scale = p->row_group_scale; g.residual = p->residual;
-  g.dropout_p = p->dropout_p; g.dropout_seed = p->dropout_seed;
+  g.dropout_p = p->dropout_p; g.dropout_seed = p->dropout_seed; g.seed_salt = seed_salt_ptr();
   auto al = [](const void* q, size_t bytes) { return ((uintptr_t)q & (bytes - 1)) == 0; };
   bool vec = al(p->C, p->c_dtype == 0 ? 4 : 8) && (p->ldc & 1) == 0;
   if (p->aux_in) vec = vec && al(p->aux_in, 4) && (p->ld_aux_in & 1) == 0;

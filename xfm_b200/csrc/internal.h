@@ -15,6 +15,11 @@ TensorMapEncodeFn get_tensor_map_encoder();
 void set_error(const char* fmt, ...);
 int num_sms();
 void count_launch(int n = 1);
+// Device word (one per device, zero until xfm_seed_salt_* is used) that every kernel drawing a dropout mask / a hard
+// negative adds to its host-supplied seed.  A CUDA graph bakes kernel arguments, seeds included; advancing this word
+// on the device between replays (xfm_seed_salt_bump, itself a graph node) gives every replayed step fresh masks while
+// forward and backward of one step still agree.
+const uint64_t* seed_salt_ptr();
 
 int gemm_bf16(const xfm_gemm_params* p, cudaStream_t stream);
 int attention_fwd(const xfm_attn_params* p, cudaStream_t s);

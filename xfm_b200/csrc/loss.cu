@@ -259,7 +259,7 @@ int itc_loss_fused(const float* image_all, const float* text_all, int n, int E, 
 constexpr int HN_THREADS = 128;
 __global__ void __launch_bounds__(HN_THREADS)
 hard_negative_kernel(const float* __restrict__ image_feat, const float* __restrict__ text_feat, int B, int E,
-                     const float* __restrict__ temp, const int64_t* __restrict__ idx, uint64_t seed,
+                     const float* __restrict__ temp, const int64_t* __restrict__ idx, uint64_t seed, const uint64_t* __restrict__ salt,
                      float* __restrict__ w_i2t, float* __restrict__ w_t2i, int64_t* __restrict__ text_neg,
                      int64_t* __restrict__ image_neg) {
   extern __shared__ float sw[];  // [B] weights, then [E] the anchor row
@@ -300,7 +300,7 @@ hard_negative_kernel(const float* __restrict__ image_feat, const float* __restri
   if (threadIdx.x == 0) {
     float total = 0.f;
     for (int j = 0; j < B; ++j) total += sw[j];
-    const float u = hash_uniform(seed, (uint64_t)blockIdx.x) * total;
+    const float u = hash_uniform(seed + *salt, (uint64_t)blockIdx.x) * total;
     float c = 0.f;
     int pick = -1, last = 0;
     for (int j = 0; j < B; ++j) {
@@ -317,7 +317,7 @@ hard_negative_kernel(const float* __restrict__ image_feat, const float* __restri
 
 int hard_negatives(const float* image_feat, const float* text_feat, int B, int E, const float* temp, const int64_t* idx,
                    uint64_t seed, float* w_i2t, float* w_t2i, int64_t* text_neg, int64_t* image_neg, cudaStream_t s) {
-  hard_negative_kernel<<<2 * B, HN_THREADS, (size_t)(B + E) * sizeof(float), s>>>(image_feat, text_feat, B, E, temp, idx, seed,
+  hard_negative_kernel<<<2 * B, HN_THREADS, (size_t)(B + E) * sizeof(float), s>>>(image_feat, text_feat, B, E, temp, idx, seed, seed_salt_ptr(),
                                                                                 w_i2t, w_t2i, text_neg, image_neg);
   count_launch();
   return (int)cudaGetLastError();
