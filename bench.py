@@ -272,18 +272,23 @@ def run_ours(args):
     if clocks:
         clocks.start()
 
-    def timed(fn):
+    step_stats = {}
+
+    def timed(fn, tag=None):
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
         n0 = L.launch_count()
-        e0.record()
+        evs[0].record()
         for i in range(args.steps):
             fn(i)
-        e1.record()
+            evs[i + 1].record()
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        ms = torch.tensor([evs[0].elapsed_time(evs[-1])], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        if tag:   # per-step device times of this rank: a stall in one step shows as max >> median
+            per = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps))
+            step_stats[tag] = {"min": per[0], "median": per[len(per) // 2], "max": per[-1]}
         return float(ms) / args.steps, L.launch_count() - n0
 
     last = {}
@@ -319,8 +324,26 @@ def run_ours(args):
         consumed[s].record(torch.cuda.current_stream())
         last["host_loss"] = float(loss)  # D2H read of the step's result
 
-    ms_step, launches = timed(resident_step)
-    ms_e2e, _ = timed(e2e_step)
+    ms_step, launches = timed(resident_step, "resident")
+    ms_e2e, _ = timed(e2e_step, "e2e")
+    graph_info = None
+    if args.graph and world == 1:   # the same step replayed as ONE CUDA graph (xfm_b200/graph.py)
+        from xfm_b200.graph import GraphedStep
+
+        def loss_fn(m, b):
+            out = m(b["image"], b["text_ids"], b["text_atts"], text_ids_masked=b["text_ids_masked"], masked_pos=b["masked_pos"],
+                    masked_ids=b["masked_ids"], ret_mim_loss=True, data_source="image")
+            return out["loss_itc"] + out["loss_itm"] + out["loss_mlm"] + out["loss_mim"]
+        gs = GraphedStep(wrapped, opt, acc, loss_fn, resident[0], warmup=3, uses_mim_masks=True)
+        for i in range(3):
+            gs(resident[i % n_pool])
+        ms_g, _ = timed(lambda i: gs(resident[i % n_pool]))
+
+        def g_e2e(i):
+            last["host_loss"] = float(gs(host[i % n_pool])[0])
+        ms_ge, _ = timed(g_e2e)
+        graph_info = {"ms_per_step": ms_g, "value": B / (ms_g * 1e-3), "e2e_ms_per_step": ms_ge, "e2e_value": B / (ms_ge * 1e-3),
+                      "unit": UNIT, "what": "forward + backward + clip + AdamW + zero_grad replayed as one CUDA graph"}
     clk = clocks.stop() if clocks else None
 
     # ---- roofline leg: one more step with CUDA events around every launch of the dominant kernel (the tcgen05 GEMM)
@@ -385,7 +408,7 @@ def run_ours(args):
                      "gemm_ms_per_step": g_ms, "peak_source": f"{pk_kind} bf16_tflops_sustained",
                      "step_tflops_algorithmic": GFLOP_PER_PAIR * B / ms_step,
                      "step_frac_of_peak": GFLOP_PER_PAIR * B / ms_step / peak},
-        "clocks": clk, "losses_last_step": losses,
+        "clocks": clk, "losses_last_step": losses, "step_ms": step_stats,
         # BASELINE.json's second figure: the 12 fusion layers (fwd + bwd of the 4B-sample pass), CUDA events around the
         # fusion encoder in one profiled step.  "algorithmic" counts the reference's FLOPs (K/V projection of an image
         # recomputed for each of its 4 passes); this implementation projects every image once per layer.
@@ -395,6 +418,8 @@ def run_ours(args):
     }
     if eager is not None:
         line["gpu_eager_baseline"] = eager
+    if graph_info is not None:
+        line["cuda_graph"] = graph_info
     if rank == 0:
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(args, quick=True)
@@ -402,6 +427,155 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# fine-tuning configurations (BASELINE configs[2..4]): --config retrieval | nlvr | vqa
+# ----------------------------------------------------------------------------------------------------------------------
+FINETUNE = {  # per-GPU batch, fwd+bwd GFLOP per sample at 384 px, unit
+    "retrieval": (32, 579.36, "pairs/s", "COCO-shape retrieval fine-tune (Retrieval_coco.yaml): ITC with idx soft labels + hard-negative ITM"),
+    "nlvr": (64, 836.07, "texts/s", "NLVR2-shape fine-tune: two images per text through the fusion encoder"),
+    "vqa": (24, 448.46, "questions/s", "VQA-shape fine-tune with the 12-layer causal answer decoder (3 answers x 8 tokens)"),
+}
+
+
+def finetune_workload(task, res, B, dev):
+    """Model class + config, synthetic pinned host batches and the loss closure of one fine-tuning configuration."""
+    import types
+    B0, gflop, unit, what = FINETUNE[task]
+    B = B or B0
+    cfg = base_config()
+    cfg.update(image_res=res, use_vision_tokenizer=False)
+    if task == "retrieval":
+        from xfm_b200.model_retrieval import XFMForRetrieval as Model
+    elif task == "nlvr":
+        from xfm_b200.model_nlvr import XFMForNLVR as Model
+    else:
+        from xfm_b200.model_generation import XFMForVQA as Model
+        cfg.update(num_dec_layers=12, decoder_fusion_start_at=0, pad_token_id=1)
+    torch.manual_seed(1234)
+    g = torch.Generator().manual_seed(1)
+    V, Lt, La, n_ans = 50265, 40, 8, 3
+
+    def text(n, length, min_real):
+        ids = torch.randint(3, V - 1, (n, length), generator=g)
+        ids[:, 0] = 0
+        n_real = torch.randint(min_real, length + 1, (n,), generator=g)
+        pad = torch.arange(length).view(1, -1) >= n_real.view(-1, 1)
+        atts = torch.ones(n, length, dtype=torch.long)
+        atts[pad] = 0
+        ids[pad] = 1
+        return ids, atts
+
+    n_img = 2 * B if task == "nlvr" else B
+    host = [dict() for _ in range(2)]
+    for hb in host:
+        hb["image"] = torch.rand(n_img, 3, res, res, generator=g)
+        hb["text_ids"], hb["text_atts"] = text(B, Lt, Lt // 2)
+        if task == "retrieval":
+            hb["idx"] = torch.randint(0, max(1, B // 5 * 4), (B,), generator=g)     # 5 captions per image => duplicates
+        elif task == "nlvr":
+            hb["targets"] = torch.randint(0, 2, (B,), generator=g)
+        else:
+            hb["a_ids"], hb["a_atts"] = text(B * n_ans, La, 3)
+            hb["weights"] = torch.rand(B * n_ans, generator=g) * 0.8 + 0.2
+    host = [{k: v.pin_memory() for k, v in hb.items()} for hb in host]
+    k_dev = torch.full((B,), n_ans, dtype=torch.long, device=dev)
+
+    def loss_fn(model, b):
+        if task == "retrieval":
+            l_itc, l_itm = model(b["image"], b["text_ids"], b["text_atts"], idx=b["idx"])
+            return l_itc + l_itm
+        if task == "nlvr":
+            return model(b["image"], b["text_ids"], b["text_atts"], b["targets"])
+        q = types.SimpleNamespace(input_ids=b["text_ids"], attention_mask=b["text_atts"])
+        a = types.SimpleNamespace(input_ids=b["a_ids"], attention_mask=b["a_atts"])
+        return model(b["image"], q, a, k=k_dev, weights=b["weights"], train=True)
+
+    def build():
+        from xfm_b200.accelerator import B200DDPAccelerator, FlatAdamW
+        model = Model(cfg, init=gpu_init(dev, 0), device=dev).train()
+        opt = FlatAdamW(model, lr=3e-5, weight_decay=0.01, lr_mult=2.0)
+        acc = B200DDPAccelerator(dict(CLIP_GRAD_NORM=1.0))
+        wrapped, opt, _ = acc.set_up(model, opt, None, 0, 1, 0)
+        return model, wrapped, opt, acc
+    return dict(B=B, n_img=n_img, gflop=gflop, unit=unit, what=what, host=host, loss_fn=loss_fn, build=build)
+
+
+def run_finetune(args):
+    """One process, one GPU: the fine-tuning step (forward + backward + clip + AdamW) of BASELINE configs #3-#5 at 384 px,
+    timed as the eager launch sequence and as ONE replayed CUDA graph (xfm_b200/graph.py); `value` is the graph figure."""
+    from xfm_b200 import lib as L
+    from xfm_b200.graph import GraphedStep
+
+    task = args.config
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    res = args.res
+    wl = finetune_workload(task, res, args.batch if args.batch_given else 0, dev)
+    B, n_img, gflop, unit, what, host, loss_fn, build = (wl[k] for k in ("B", "n_img", "gflop", "unit", "what", "host", "loss_fn", "build"))
+    h2d = sum(v.numel() * v.element_size() for v in host[0].values())
+
+    def timed(fn, steps):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = L.launch_count()
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps, (L.launch_count() - n0) // steps
+
+    resident = [{k: v.to(dev) for k, v in hb.items()} for hb in host]
+    clocks = ClockSampler(dev.index or 0)
+    # ---- eager launch sequence
+    model, wrapped, opt, acc = build()
+
+    def eager_step(i):
+        loss = loss_fn(wrapped, resident[i & 1])
+        acc.backward_step(loss, opt)
+        acc.optimizer_step(opt, wrapped)
+        return loss
+    for i in range(max(args.warmup, 3)):
+        eager_step(i)
+    ms_eager, launches = timed(eager_step, args.steps)
+    del model, wrapped, opt, acc
+    torch.cuda.empty_cache()
+    # ---- one CUDA graph per step
+    model, wrapped, opt, acc = build()
+    step = GraphedStep(wrapped, opt, acc, loss_fn, resident[0], warmup=max(args.warmup, 3))
+    for i in range(3):
+        step(resident[i & 1])
+    clocks.start()
+    ms_graph, _ = timed(lambda i: step(resident[i & 1]), args.steps)
+    last = {}
+
+    def e2e_step(i):   # inputs from pinned host memory, loss read back, inside the timed region
+        out = step(host[i & 1])
+        last["loss"] = float(out[0])
+    ms_e2e, _ = timed(e2e_step, args.steps)
+    clk = clocks.stop()
+    pk, pk_kind = peaks()
+    peak = pk.get("bf16_tflops_sustained", 1400.0)
+    tfl = gflop * B / ms_graph if res == 384 else None
+    line = {
+        "metric": METRIC, "value": B / (ms_graph * 1e-3), "unit": unit, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_graph, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic (uniform images, random token ids; random-init XFM-base weights)",
+        "config": {"workload": what + f", {res} px / 40 tokens, fwd+bwd+clip+AdamW", "samples_per_gpu": B, "images_per_gpu": n_img,
+                   "parallelism": "dp1", "train_mode": True, "step": "one CUDA graph replay (xfm_b200/graph.py)",
+                   "l2": "activations exceed L2"},
+        "e2e": {"value": B / (ms_e2e * 1e-3), "unit": unit, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+        "gpu_launches": launches * args.steps, "kernels_per_step": launches,
+        "eager": {"value": B / (ms_eager * 1e-3), "unit": unit, "ms_per_step": ms_eager,
+                  "what": "the same step as ~kernels_per_step individual launches from Python"},
+        "roofline": {"bound": "tensor", "achieved": tfl, "peak": peak, "unit": "TFLOP/s", "frac": (tfl / peak) if tfl else None,
+                     "traffic": None, "kernel": "whole step (algorithmic FLOPs of SURVEY.md §8d per sample)",
+                     "peak_source": f"{pk_kind} bf16_tflops_sustained"},
+        "clocks": clk, "loss_last_step": last.get("loss"),
+    }
+    print(json.dumps(line), flush=True)
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -479,15 +653,25 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("XFM_BENCH_PAIRS", "96")), help="pairs per GPU (yaml: 96)")
+    ap.add_argument("--batch", type=int, default=None, help="samples per GPU (pre-train yaml: 96; fine-tune configs: 32 / 64 / 24)")
+    ap.add_argument("--config", default="pretrain", choices=["pretrain", "retrieval", "nlvr", "vqa"],
+                    help="pretrain = BASELINE configs[1] (the headline); retrieval / nlvr / vqa = configs[2..4] at --res")
+    ap.add_argument("--res", type=int, default=384, help="image resolution of the fine-tune configs")
+    ap.add_argument("--graph", action="store_true", help="pretrain config: replay the step as one CUDA graph (single GPU)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-eager", action="store_true", help="skip the gpu_eager_baseline leg (eager PyTorch on the same GPU)")
     ap.add_argument("--overlap", default="auto", help="accelerator OVERLAP_ALLREDUCE: auto | true | false")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     args.overlap = {"true": True, "false": False}.get(str(args.overlap).lower(), "auto")
+    args.batch_given = args.batch is not None
+    if args.batch is None:
+        args.batch = int(os.environ.get("XFM_BENCH_PAIRS", "96"))
     if args.impl == "reference":
         run_reference(args)
+    elif args.config != "pretrain":
+        if int(os.environ.get("RANK", "0")) == 0:
+            run_finetune(args)
     else:
         run_ours(args)
 

@@ -120,6 +120,7 @@ class FlatAdamW(torch.optim.Optimizer):
         self.norm = torch.zeros(1, dtype=torch.float32, device=dev)
         self.step_count = 0
         self.world_sync = None   # set by the accelerator: callable(uint8 tensor) -> tensor all-reduced with MIN over ranks
+        self._hp_static = None   # graph mode: device hyper-parameter block refreshed by refresh_hparams() between replays
 
     @property
     def flat(self):
@@ -139,13 +140,28 @@ class FlatAdamW(torch.optim.Optimizer):
         return L.adamw_hparams([x["lr"] for x in g], [x["weight_decay"] for x in g], d["betas"][0], d["betas"][1], d["eps"],
                                max_grad_norm, grad_mul, d["correct_bias"])
 
+    def static_hparams(self, max_grad_norm, grad_mul):
+        """CUDA-graph mode: from now on step() reads its hyper-parameters from one static device block; call
+        refresh_hparams() before each replay so that a scheduler's new learning rates reach the captured kernels."""
+        self._hp_args = (max_grad_norm, grad_mul)
+        self._hp_static = self.hparams(max_grad_norm, grad_mul).to(self.model.flat.P.device)
+        return self._hp_static
+
+    def refresh_hparams(self):
+        if self._hp_static is not None:
+            self._hp_static.copy_(self.hparams(*self._hp_args), non_blocking=True)
+
     @torch.no_grad()
     def step(self, closure=None, max_grad_norm=0.0, grad_mul=1.0):
         loss = closure() if closure is not None else None
         self.step_count += 1
         model = self.model
         dev = model.flat.P.device
-        hp = self.hparams(max_grad_norm, grad_mul).to(dev, non_blocking=True)
+        if self._hp_static is not None:
+            assert self._hp_args == (max_grad_norm, grad_mul), "graph mode: clip / grad_mul are fixed at capture time"
+            hp = self._hp_static
+        else:
+            hp = self.hparams(max_grad_norm, grad_mul).to(dev, non_blocking=True)
         model.collect_stray_grads()
         live = []
         for i, b in enumerate(self._buffers):

@@ -320,7 +320,25 @@ colsum_kernel(const bf16* __restrict__ in, int64_t ld, float* __restrict__ out, 
   const int row0 = blockIdx.y * rows_per_cta;
   const int row1 = min(M, row0 + rows_per_cta);
   if (c < N) {
-    for (int r = row0 + threadIdx.y; r < row1; r += 8) {
+    // four independent 16-byte loads in flight per thread (one per iteration left ~8 KB in flight per SM: 0.52 of the copy
+    // bandwidth, profiles/r01_dev_kernels.jsonl)
+    int r = row0 + threadIdx.y;
+    for (; r + 24 < row1; r += 32) {
+      uint4 u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) u[k] = *(const uint4*)(in + (int64_t)(r + 8 * k) * ld + c);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const __nv_bfloat162* h = (const __nv_bfloat162*)&u[k];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 f = __bfloat1622float2(h[q]);
+          acc[2 * q] += f.x;
+          acc[2 * q + 1] += f.y;
+        }
+      }
+    }
+    for (; r < row1; r += 8) {
       const uint4 u = *(const uint4*)(in + (int64_t)r * ld + c);
       const __nv_bfloat162* h = (const __nv_bfloat162*)&u;
 #pragma unroll
@@ -862,7 +880,7 @@ int colsum_bf16(const bf16* in, int64_t ld, float* out, int M, int N, cudaStream
   }
   if (M <= 0) return 0;
   const int gx = (N + 255) / 256;
-  int gy = (num_sms() * 2 + gx - 1) / gx;
+  int gy = (num_sms() * 4 + gx - 1) / gx;
   int rpc = (M + gy - 1) / gy;
   rpc = ((rpc + 7) / 8) * 8;
   gy = (M + rpc - 1) / rpc;

@@ -78,6 +78,15 @@ def lib():
     return l
 
 
+def seed_salt_bump(inc=1):
+    """Advance the device-resident word every dropout / sampling kernel adds to its seed (capturable: one tiny kernel)."""
+    check(lib().xfm_seed_salt_bump(C.c_uint64(inc), stream_ptr()), "xfm_seed_salt_bump")
+
+
+def seed_salt_set(value=0):
+    check(lib().xfm_seed_salt_set(C.c_uint64(value), stream_ptr()), "xfm_seed_salt_set")
+
+
 def launch_count():
     return int(load().xfm_launch_count())
 

@@ -136,7 +136,7 @@ class XFMForVQA(XFMBase):
         if train:
             # k: number of answers for each question; weights: weight for each answer
             answer_targets = answer.input_ids.masked_fill(answer.input_ids == self.pad_token_id, -100)
-            counts = torch.as_tensor(k, device=image.device)
+            counts = k if torch.is_tensor(k) else torch.as_tensor(k, device=image.device)   # (a device tensor avoids a copy)
             kv_index = torch.repeat_interleave(torch.arange(len(k), device=image.device), counts,
                                                output_size=answer.input_ids.shape[0])
             answer_loss = self._decode(answer.input_ids, answer.attention_mask, question_output, quesiton.attention_mask,

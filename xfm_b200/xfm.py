@@ -311,6 +311,7 @@ class XFMBase(nn.Module):
         self._attached = []
         self._forced_negatives = None   # tests: (image_neg_idx, text_neg_idx) replaces the on-device draw
         self._forced_masks = None       # tests: bool [B, np] replaces the host sampler
+        self._static_masks = None       # graph mode: (bool [B, np], int64 [B * n_mask]) device tensors, see graph.py
         self._drop_calls = 0
         self._seed = int(torch.initial_seed()) & 0x7FFFFFFF
         self.last_hard_negative_weights = None
@@ -576,7 +577,9 @@ class XFMBase(nn.Module):
         self._prep()
         B = image.shape[0]
         mask_dev = None
-        if do_mask:
+        if do_mask and self._static_masks is not None:   # CUDA-graph mode: device buffers refilled between replays
+            mask_dev, rows = self._static_masks
+        elif do_mask:
             if self._forced_masks is not None:
                 m = self._forced_masks.cpu()
                 rows = torch.from_numpy(__import__("numpy").flatnonzero(m.numpy()).astype("int64"))
