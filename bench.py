@@ -214,6 +214,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if "--graph" in sys.argv:   # collectives inside a captured graph: torch's own guidance for NCCL + CUDA graphs
+            os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
         # rank 0 prints ONE JSON line on stdout: NCCL's own output (the "NCCL version ..." banner it prints at
         # NCCL_DEBUG=VERSION / WARN, warnings) goes to stderr
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
@@ -324,10 +326,11 @@ def run_ours(args):
         consumed[s].record(torch.cuda.current_stream())
         last["host_loss"] = float(loss)  # D2H read of the step's result
 
+    pairs_all = B * world
     ms_step, launches = timed(resident_step, "resident")
     ms_e2e, _ = timed(e2e_step, "e2e")
     graph_info = None
-    if args.graph and world == 1:   # the same step replayed as ONE CUDA graph (xfm_b200/graph.py)
+    if args.graph:   # the same step replayed as ONE CUDA graph (xfm_b200/graph.py)
         from xfm_b200.graph import GraphedStep
 
         def loss_fn(m, b):
@@ -342,7 +345,8 @@ def run_ours(args):
         def g_e2e(i):
             last["host_loss"] = float(gs(host[i % n_pool])[0])
         ms_ge, _ = timed(g_e2e)
-        graph_info = {"ms_per_step": ms_g, "value": B / (ms_g * 1e-3), "e2e_ms_per_step": ms_ge, "e2e_value": B / (ms_ge * 1e-3),
+        graph_info = {"ms_per_step": ms_g, "value": pairs_all / (ms_g * 1e-3), "e2e_ms_per_step": ms_ge,
+                      "e2e_value": pairs_all / (ms_ge * 1e-3),
                       "unit": UNIT, "what": "forward + backward + clip + AdamW + zero_grad replayed as one CUDA graph"}
     clk = clocks.stop() if clocks else None
 

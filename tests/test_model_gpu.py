@@ -73,14 +73,17 @@ def test_tiny_vq_activations_losses_against_reference(golden_dir):
         out = _run(model, g, batch)
     nv, nt, nf = cfg["vision_depth"], cfg["text_layers"], cfg["fusion_layers"]
     vis, txt, fus = model._vis.collect, model._txt.collect, model._fus.collect
-    # call order: vision | text | text(masked) | fusion(4B pass: 3B ITM rows + B MLM rows) | vision(masked)
-    assert len(vis) == 2 * nv and len(txt) == 2 * nt and len(fus) == nf
+    # call order: vision | text (ONE 2B-sample pass: clean rows, then the masked copies) | fusion (4B pass: 3B ITM rows +
+    # B MLM rows) | vision(masked)
+    assert len(vis) == 2 * nv and len(txt) == nt and len(fus) == nf
     B = g["B"]
     for i in range(nv):
         assert _maxabs(vis[i], g["acts"]["vision"][i]) <= 2e-2, ("vision", i)
         assert _maxabs(vis[nv + i], g["acts"]["vision_masked"][i]) <= 2e-2, ("vision_masked", i)
     for i in range(nt):
-        assert _maxabs(txt[i], g["acts"]["text"][i]) <= 2e-2, ("text", i)
+        assert txt[i].shape[0] == 2 * B
+        assert _maxabs(txt[i][:B], g["acts"]["text"][i]) <= 2e-2, ("text", i)
+        assert _maxabs(txt[i][B:], g["acts"]["text_masked"][i]) <= 2e-2, ("text_masked", i)
     for i in range(nf):  # first B samples of the fusion pass are the positive pairs
         assert _maxabs(fus[i][:B], g["acts"]["fusion_pos"][i]) <= 2e-2, ("fusion", i)
     for k, v in g["losses"].items():
@@ -206,7 +209,8 @@ def test_base_config_against_reference(golden_dir, name):
         out = _run(model, g, batch)
     tok, nd, B = [0, 1, 7, -1], 16, g["B"]
     nv, nt, nf = cfg["vision_depth"], cfg["text_layers"], cfg["fusion_layers"]
-    groups = {"vision": model._vis.collect[:nv], "vision_masked": model._vis.collect[nv:], "text": model._txt.collect[:nt],
+    groups = {"vision": model._vis.collect[:nv], "vision_masked": model._vis.collect[nv:],
+              "text": [a[:B] for a in model._txt.collect[:nt]], "text_masked": [a[B:] for a in model._txt.collect[:nt]],
               "fusion_pos": [a[:B] for a in model._fus.collect[:nf]]}
     worst = 0.0
     for grp, acts in groups.items():

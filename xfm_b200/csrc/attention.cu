@@ -19,7 +19,7 @@
 namespace xfm {
 
 constexpr int HD = 64;        // head dim
-constexpr int AT_WARPS = 4;   // 4 warps x 16 rows = 64-row tile
+// CTAs of 4 or 8 warps x 16 rows (template parameter WARPS of the kernels below); keys / queries are walked in 64-row blocks
 constexpr int AT_TILE = 64;
 constexpr int ROW_BYTES = HD * 2;  // 128
 
@@ -211,17 +211,21 @@ XFM_DEVINL float logit2(const AttnArgs& a, float raw, float addend, int key) {
 }
 
 // ================================================================================================ forward
-__global__ void __launch_bounds__(AT_WARPS * 32)
+// WARPS x 16 query rows per CTA (4 or 8 warps): K / V of the whole sample are shared-memory resident, so at N = 577 (164 KB)
+// only one CTA fits an SM and the warp count per CTA is the SM's occupancy.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
 attn_fwd_kernel(const AttnArgs a) {
+  constexpr int RT = WARPS * 16;
   extern __shared__ __align__(128) uint8_t smem[];
   const int LkP = (a.Lk + AT_TILE - 1) / AT_TILE * AT_TILE;
   uint8_t* sQ = smem;
-  uint8_t* sK = sQ + AT_TILE * ROW_BYTES;
+  uint8_t* sK = sQ + RT * ROW_BYTES;
   uint8_t* sV = sK + LkP * ROW_BYTES;
-  const int q0 = blockIdx.x * AT_TILE, h = blockIdx.y, b = blockIdx.z;
+  const int q0 = blockIdx.x * RT, h = blockIdx.y, b = blockIdx.z;
   const int kvb = a.kv_index ? a.kv_index[b] : b;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  load_tile(sQ, a.q + ((int64_t)b * a.Lq + q0) * a.q_stride + h * HD, a.q_stride, min(AT_TILE, a.Lq - q0), AT_TILE);
+  load_tile(sQ, a.q + ((int64_t)b * a.Lq + q0) * a.q_stride + h * HD, a.q_stride, min(RT, a.Lq - q0), RT);
   load_tile(sK, a.k + (int64_t)kvb * a.Lk * a.k_stride + h * HD, a.k_stride, a.Lk, LkP);
   load_tile(sV, a.v + (int64_t)kvb * a.Lk * a.v_stride + h * HD, a.v_stride, a.Lk, LkP);
   cp_async_wait_all();
@@ -336,20 +340,22 @@ __global__ void attn_delta_kernel(const bf16* __restrict__ dout, int64_t do_stri
 }
 
 // Kernel A: dQ (+ optional bf16 dS dump).  Same tiling as the forward.
-__global__ void __launch_bounds__(AT_WARPS * 32)
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
 attn_bwd_dq_kernel(const AttnArgs a) {
+  constexpr int RT = WARPS * 16;
   extern __shared__ __align__(128) uint8_t smem[];
   const int LkP = (a.Lk + AT_TILE - 1) / AT_TILE * AT_TILE;
   uint8_t* sQ = smem;
-  uint8_t* sdO = sQ + AT_TILE * ROW_BYTES;
-  uint8_t* sK = sdO + AT_TILE * ROW_BYTES;
+  uint8_t* sdO = sQ + RT * ROW_BYTES;
+  uint8_t* sK = sdO + RT * ROW_BYTES;
   uint8_t* sV = sK + LkP * ROW_BYTES;
-  const int q0 = blockIdx.x * AT_TILE, h = blockIdx.y, b = blockIdx.z;
+  const int q0 = blockIdx.x * RT, h = blockIdx.y, b = blockIdx.z;
   const int kvb = a.kv_index ? a.kv_index[b] : b;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nq = min(AT_TILE, a.Lq - q0);
-  load_tile(sQ, a.q + ((int64_t)b * a.Lq + q0) * a.q_stride + h * HD, a.q_stride, nq, AT_TILE);
-  load_tile(sdO, a.dout + ((int64_t)b * a.Lq + q0) * a.do_stride + h * HD, a.do_stride, nq, AT_TILE);
+  const int nq = min(RT, a.Lq - q0);
+  load_tile(sQ, a.q + ((int64_t)b * a.Lq + q0) * a.q_stride + h * HD, a.q_stride, nq, RT);
+  load_tile(sdO, a.dout + ((int64_t)b * a.Lq + q0) * a.do_stride + h * HD, a.do_stride, nq, RT);
   load_tile(sK, a.k + (int64_t)kvb * a.Lk * a.k_stride + h * HD, a.k_stride, a.Lk, LkP);
   load_tile(sV, a.v + (int64_t)kvb * a.Lk * a.v_stride + h * HD, a.v_stride, a.Lk, LkP);
   cp_async_wait_all();
@@ -425,21 +431,23 @@ attn_bwd_dq_kernel(const AttnArgs a) {
 
 // Kernel B: dK, dV for one 64-key tile of one (K/V batch row, head); loops over every referencing sample and over
 // that sample's queries in blocks of 64.  Works on the transposed problem: rows = keys, columns = queries.
-__global__ void __launch_bounds__(AT_WARPS * 32)
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
 attn_bwd_dkv_kernel(const AttnArgs a) {
+  constexpr int RT = WARPS * 16;
   extern __shared__ __align__(128) uint8_t smem[];
   const int LqP = (a.Lq + AT_TILE - 1) / AT_TILE * AT_TILE;
   uint8_t* sK = smem;
-  uint8_t* sV = sK + AT_TILE * ROW_BYTES;
-  uint8_t* sQ = sV + AT_TILE * ROW_BYTES;
+  uint8_t* sV = sK + RT * ROW_BYTES;
+  uint8_t* sQ = sV + RT * ROW_BYTES;
   uint8_t* sdO = sQ + LqP * ROW_BYTES;
   float* sLse = (float*)(sdO + LqP * ROW_BYTES);
   float* sDelta = sLse + LqP;
-  const int k0 = blockIdx.x * AT_TILE, h = blockIdx.y, kvb = blockIdx.z;
+  const int k0 = blockIdx.x * RT, h = blockIdx.y, kvb = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nk = min(AT_TILE, a.Lk - k0);
-  load_tile(sK, a.k + ((int64_t)kvb * a.Lk + k0) * a.k_stride + h * HD, a.k_stride, nk, AT_TILE);
-  load_tile(sV, a.v + ((int64_t)kvb * a.Lk + k0) * a.v_stride + h * HD, a.v_stride, nk, AT_TILE);
+  const int nk = min(RT, a.Lk - k0);
+  load_tile(sK, a.k + ((int64_t)kvb * a.Lk + k0) * a.k_stride + h * HD, a.k_stride, nk, RT);
+  load_tile(sV, a.v + ((int64_t)kvb * a.Lk + k0) * a.v_stride + h * HD, a.v_stride, nk, RT);
   const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aQ = smem_u32(sQ), adO = smem_u32(sdO);
   const int g = lane >> 2, t = lane & 3;
   const int key0 = k0 + warp * 16 + g, key1 = key0 + 8;
@@ -569,14 +577,19 @@ int attention_fwd(const xfm_attn_params* p, cudaStream_t s) {
   AttnArgs a;
   fill_args(p, a);
   const int LkP = (a.Lk + AT_TILE - 1) / AT_TILE * AT_TILE;
-  const size_t smem = (size_t)(AT_TILE + 2 * LkP) * ROW_BYTES;
+  const bool big = a.Lq > 256;   // 8 warps (128 query rows) per CTA when the resident K / V leave room for one CTA per SM only
+  const int rt = big ? 128 : 64;
+  const size_t smem = (size_t)(rt + 2 * LkP) * ROW_BYTES;
   if (smem > 220 * 1024) {
     set_error("attention: Lk=%d needs %zu bytes of shared memory (max 220 KB; K/V streaming not built yet)", a.Lk, smem);
     return XFM_ERR_BAD_ARG;
   }
-  cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = big ? cudaFuncSetAttribute(attn_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                      : cudaFuncSetAttribute(attn_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  attn_fwd_kernel<<<dim3((a.Lq + AT_TILE - 1) / AT_TILE, a.H, a.B), AT_WARPS * 32, smem, s>>>(a);
+  const dim3 grid((a.Lq + rt - 1) / rt, a.H, a.B);
+  if (big) attn_fwd_kernel<8><<<grid, 256, smem, s>>>(a);
+  else attn_fwd_kernel<4><<<grid, 128, smem, s>>>(a);
   count_launch();
   return (int)cudaGetLastError();
 }
@@ -607,19 +620,26 @@ int attention_bwd(const xfm_attn_params* p, cudaStream_t s) {
     return vit_attention_bwd_tc(p, s);
   if (p->allow_tc && cross_attention_tc_supported(p) && !p->ds_dump) return cross_attention_bwd_tc(p, s);
   if (p->allow_tc && self_attention_tc_supported(p) && !p->ds_dump) return self_attention_bwd_tc(p, s);
-  const size_t smem_a = (size_t)(2 * AT_TILE + 2 * LkP) * ROW_BYTES;
-  const size_t smem_b = (size_t)(2 * AT_TILE + 2 * LqP) * ROW_BYTES + 2 * LqP * sizeof(float);
+  const bool big_q = a.Lq > 256, big_k = a.Lk > 256;
+  const int rq = big_q ? 128 : 64, rk = big_k ? 128 : 64;
+  const size_t smem_a = (size_t)(2 * rq + 2 * LkP) * ROW_BYTES;
+  const size_t smem_b = (size_t)(2 * rk + 2 * LqP) * ROW_BYTES + 2 * LqP * sizeof(float);
   if (smem_a > 220 * 1024 || smem_b > 220 * 1024) {
     set_error("attention_bwd: sequence too long for the shared-memory resident kernels");
     return XFM_ERR_BAD_ARG;
   }
-  cudaError_t e = cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
+  cudaError_t e = big_q ? cudaFuncSetAttribute(attn_bwd_dq_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a)
+                        : cudaFuncSetAttribute(attn_bwd_dq_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
   if (e != cudaSuccess) return (int)e;
-  e = cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
+  e = big_k ? cudaFuncSetAttribute(attn_bwd_dkv_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b)
+            : cudaFuncSetAttribute(attn_bwd_dkv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
   if (e != cudaSuccess) return (int)e;
-  attn_bwd_dq_kernel<<<dim3((a.Lq + AT_TILE - 1) / AT_TILE, a.H, a.B), AT_WARPS * 32, smem_a, s>>>(a);
+  const dim3 ga((a.Lq + rq - 1) / rq, a.H, a.B), gb((a.Lk + rk - 1) / rk, a.H, a.Bkv);
+  if (big_q) attn_bwd_dq_kernel<8><<<ga, 256, smem_a, s>>>(a);
+  else attn_bwd_dq_kernel<4><<<ga, 128, smem_a, s>>>(a);
   count_launch();
-  attn_bwd_dkv_kernel<<<dim3((a.Lk + AT_TILE - 1) / AT_TILE, a.H, a.Bkv), AT_WARPS * 32, smem_b, s>>>(a);
+  if (big_k) attn_bwd_dkv_kernel<8><<<gb, 256, smem_b, s>>>(a);
+  else attn_bwd_dkv_kernel<4><<<gb, 128, smem_b, s>>>(a);
   count_launch();
   return (int)cudaGetLastError();
 }

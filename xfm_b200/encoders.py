@@ -393,6 +393,32 @@ class RobertaStack:
                 self.collect.append(h32.view(Bt, Lt, -1).clone())
         return h, h32, (st if save else None)
 
+    @staticmethod
+    def slice_states(est, st, B):
+        """States of the first B samples of a pass that ran B' > B samples (no cross-attention): every saved tensor is
+        per-row / per-sample and dropout masks are functions of (seed, sample, position), so the backward over the slice is
+        the backward the B samples would have had on their own."""
+        Bt, Lt = st.Bt, st.Lt
+
+        def cut(v):
+            if torch.is_tensor(v) and v.dim() >= 1:
+                if v.shape[0] == Bt * Lt:
+                    return v[:B * Lt]
+                if v.shape[0] == Bt:
+                    return v[:B]
+            return v
+        out = State()
+        out.__dict__.update({k: cut(v) for k, v in st.__dict__.items()})
+        out.Bt = B
+        out.layers = []
+        for s in st.layers:
+            c = BK.Saved()
+            c.__dict__.update({k: cut(v) for k, v in s.__dict__.items()})
+            out.layers.append(c)
+        e = State()
+        e.__dict__.update({k: cut(v) for k, v in est.__dict__.items()})
+        return e, out
+
     def layers_bwd(self, st, dh, d_enc=None, need_dh=True, kv_offsets=None, kv_samples=None):
         """dh: bf16 / f32 [Bt*Lt, D].  d_enc: f32 [Benc*Lenc, Denc] accumulator (cross-attention K/V input gradient)."""
         if kv_samples is None:   # CSR built in layers_fwd (identity when every sample has its own image)

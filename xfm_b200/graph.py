@@ -15,7 +15,9 @@ What makes the step replayable (nothing in it may depend on a host value that ch
     block refreshed between replays, so an LR scheduler keeps working;
   * the MIM block masks of masking_generator.py are sampled on the host (bit-exact RNG streams) into pinned
     buffers and copied into static device tensors before each replay.
-Single-process (world size 1) capture; the multi-GPU path keeps its eager launch sequence (NCCL side-stream overlap).
+Under torchrun the captured step contains the NCCL collectives as graph nodes (ITC all-gather, the overlapped gradient
+all-reduces on the side stream become cross-stream graph edges); capture then uses capture_error_mode="thread_local"
+because NCCL's watchdog thread queries events while the capture is open.
 """
 import torch
 
@@ -30,7 +32,6 @@ class GraphedStep:
     in it is exposed, detached, as static outputs).  `inputs` is a dict of tensors with fixed shapes / dtypes."""
 
     def __init__(self, model, optimizer, accelerator, loss_fn, example_inputs, warmup=3, uses_mim_masks=None):
-        assert accelerator.world == 1, "CUDA-graph capture is single-process; use the eager step under torchrun"
         self.model, self.opt, self.acc, self.loss_fn = model, optimizer, accelerator, loss_fn
         core = model.module if hasattr(model, "module") and hasattr(model.module, "flat") else model
         self.core = core
@@ -42,7 +43,7 @@ class GraphedStep:
         if self.uses_masks:
             m, rows = sample_batch(core._sampler, B)
             core._static_masks = (m.to(dev), rows.to(dev))
-        optimizer.static_hparams(accelerator.clip, 1.0)
+        optimizer.static_hparams(accelerator.clip, 1.0 / accelerator.world)
         # warm-up on a side stream (allocator, lazy initialisation, autograd streams), as torch.cuda.graphs requires
         s = torch.cuda.Stream(device=dev)
         s.wait_stream(torch.cuda.current_stream(dev))
@@ -52,7 +53,8 @@ class GraphedStep:
         torch.cuda.current_stream(dev).wait_stream(s)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        mode = "global" if accelerator.world == 1 else "thread_local"
+        with torch.cuda.graph(self.graph, capture_error_mode=mode):
             self.outputs = self._eager_step()
             L.seed_salt_bump(1)
         self.launches_per_replay = 1

@@ -41,7 +41,8 @@ class XFM(XFMBase):
         zero = torch.tensor(0.0)
         loss_itc = loss_itm = loss_mlm = loss_mim = loss_bbox = loss_giou = zero
         if data_source != "imagenet":
-            text_embeds = self.get_text_embeds(text_ids, text_atts)
+            both = ret_match_loss and ret_mlm_loss and self.fuse_itm_mlm and text_ids_masked is not None
+            text_embeds = self.get_text_embeds(text_ids, text_atts, _also_masked=text_ids_masked if both else None)
             image_feat, text_feat = self.get_features(image_embeds, text_embeds)
             if ret_itc_loss:
                 loss_itc = self.get_contrastive_loss(image_feat, text_feat)

@@ -669,19 +669,33 @@ class XFMBase(nn.Module):
         return m.contiguous()
 
     # ------------------------------------------------------------------ text
-    def get_text_embeds(self, text_ids, text_atts):
-        """xfm.py:600-611: 12-layer text encoder (no cross-attention)."""
+    def get_text_embeds(self, text_ids, text_atts, _also_masked=None):
+        """xfm.py:600-611: 12-layer text encoder (no cross-attention).
+        _also_masked (xfm_b200 only): the masked copy of the same texts, which get_fuse_mlm_loss would encode in a second,
+        gradient-free pass (xfm.py:645-649, detach_text_forMLM).  Both copies then run as ONE 2B-sample pass — the 40-token
+        GEMMs of a B-sample pass sit on the launch-latency floor, a 2B-sample pass costs barely more — and the masked half is
+        handed to get_matching_and_fuse_mlm_loss; the backward runs over the clean half only."""
         assert text_atts is not None
         self._prep()
         model = self
         B, Lt = text_ids.shape
-        kmask = E.RobertaStack.additive_mask(text_atts)
+        self._masked_text = None
+        pair = _also_masked is not None and self.detach_text_forMLM
+        ids_all = torch.cat([text_ids, _also_masked]) if pair else text_ids
+        Ball = ids_all.shape[0]
+        kmask1 = E.RobertaStack.additive_mask(text_atts)
+        kmask = torch.cat([kmask1, kmask1]) if pair else kmask1
 
         class Impl:
             def fwd(self, ctx):
                 drop = model._drop()
-                h, h32, est = model._txt.embed(text_ids, drop, save=self.save)
-                h, h32, st = model._txt.layers_fwd(h, B, Lt, kmask, drop=drop, save=self.save, h32=h32)
+                h, h32, est = model._txt.embed(ids_all, drop, save=self.save)
+                h, h32, st = model._txt.layers_fwd(h, Ball, Lt, kmask, drop=drop, save=self.save, h32=h32)
+                if pair:
+                    model._masked_text = (_also_masked, h[B * Lt:], h32[B * Lt:])
+                    h, h32 = h[:B * Lt], h32[:B * Lt]
+                    if self.save:
+                        est, st = E.RobertaStack.slice_states(est, st, B)
                 self.h16 = h.view(B, Lt, -1)
                 if ctx is not None:
                     ctx.est, ctx.st = est, st
@@ -963,8 +977,12 @@ class XFMBase(nn.Module):
                 D = t16.shape[-1]
                 drop = model._drop()
                 keep_text = self.save and not detach
-                hm, hm32, est = model._txt.embed(text_ids_masked, drop, save=keep_text)
-                hm, hm32, tst = model._txt.layers_fwd(hm, B, Lt, kmask_mlm, drop=drop, save=keep_text, h32=hm32)
+                cached, model._masked_text = model._masked_text, None
+                if cached is not None and cached[0] is text_ids_masked and detach:   # encoded together with the clean texts
+                    hm, hm32, est, tst = cached[1], cached[2], None, None
+                else:
+                    hm, hm32, est = model._txt.embed(text_ids_masked, drop, save=keep_text)
+                    hm, hm32, tst = model._txt.layers_fwd(hm, B, Lt, kmask_mlm, drop=drop, save=keep_text, h32=hm32)
                 tall = torch.empty((4 * B * Lt, D), dtype=torch.bfloat16, device=dev)
                 tall32 = torch.empty((4 * B * Lt, D), dtype=torch.float32, device=dev)
                 tall[:3 * B * Lt] = L.gather_rows(t16.reshape(B, Lt * D), txt_index).view(3 * B * Lt, D)
