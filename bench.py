@@ -211,14 +211,23 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # Exactly ONE JSON line may reach stdout.  NCCL prints its "NCCL version ..." banner with printf at NCCL_DEBUG=VERSION
+    # (this image's default), so under torchrun file descriptor 1 is pointed at stderr for the whole run and the JSON line
+    # goes to a private duplicate of the original stdout.
+    out_stream = sys.stdout
+    if world > 1:
+        sys.stdout.flush()
+        out_stream = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+    wd = int(os.environ.get("XFM_BENCH_WATCHDOG", "0"))
+    if wd > 0:   # debugging aid: dump every thread's stack to stderr if the run is still alive after `wd` seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(wd, repeat=True, file=sys.stderr)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if "--graph" in sys.argv:   # collectives inside a captured graph: torch's own guidance for NCCL + CUDA graphs
+        if args.graph:   # collectives inside a captured graph: torch's own guidance for NCCL + CUDA graphs
             os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
-        # rank 0 prints ONE JSON line on stdout: NCCL's own output (the "NCCL version ..." banner it prints at
-        # NCCL_DEBUG=VERSION / WARN, warnings) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     B, Lt, M = args.batch, 40, 15
     import random
@@ -260,7 +269,10 @@ def run_ours(args):
     i = 0
     # W warm-up steps, and at least ~2 s of them: a GPU coming out of idle needs about a second under load before its
     # clocks and power state settle (first-loop timings varied by 15 % with 3 warm-up steps of 85 ms)
-    while i < args.warmup or (time.perf_counter() - t_warm < 2.0 and i < args.warmup + 40):
+    # The number of steps must be the SAME on every rank (each step contains collectives): the first W steps are timed
+    # locally, the number of extra steps is agreed with a MAX all-reduce.
+    n_warm = args.warmup
+    while i < n_warm:
         loss, out = step(resident[i % n_pool])
         if i == 0:
             arena = reserve_arena(factor=1.5)  # no cudaMalloc inside the timed regions (see accelerator.reserve_arena)
@@ -268,6 +280,13 @@ def run_ours(args):
         if i % 4 == 3:
             torch.cuda.synchronize()
         i += 1
+        if i == args.warmup:
+            torch.cuda.synchronize()
+            per = max((time.perf_counter() - t_warm) / max(args.warmup - 1, 1), 1e-3)
+            extra = torch.tensor([min(40, max(0, int((2.0 - (time.perf_counter() - t_warm)) / per) + 1))], device=dev)
+            if world > 1:
+                dist.all_reduce(extra, op=dist.ReduceOp.MAX)
+            n_warm = args.warmup + int(extra)
     warm_steps = i
     barrier()
     clocks = ClockSampler(local) if rank == 0 else None
@@ -276,7 +295,19 @@ def run_ours(args):
 
     step_stats = {}
 
+    import gc
+
     def timed(fn, tag=None):
+        # the cyclic garbage collector is run between the timed loops, not inside them: a generation-2 pass over the
+        # ~10^5 live Python objects of this process takes 20-40 ms and starves the GPU for one step (step_ms max >> median)
+        gc.collect()
+        gc.disable()
+        try:
+            return _timed(fn, tag)
+        finally:
+            gc.enable()
+
+    def _timed(fn, tag):
         barrier()
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
         n0 = L.launch_count()
@@ -340,11 +371,18 @@ def run_ours(args):
         gs = GraphedStep(wrapped, opt, acc, loss_fn, resident[0], warmup=3, uses_mim_masks=True)
         for i in range(3):
             gs(resident[i % n_pool])
-        ms_g, _ = timed(lambda i: gs(resident[i % n_pool]))
+        ms_g, _ = timed(lambda i: gs(resident[i % n_pool]), "graph_resident")
 
-        def g_e2e(i):
-            last["host_loss"] = float(gs(host[i % n_pool])[0])
-        ms_ge, _ = timed(g_e2e)
+        g_staged = {"next": None}
+
+        def g_e2e(i):   # inputs from pinned host memory (copy of step i+1 under step i, like a prefetching loader), loss read back
+            if g_staged["next"] != i:
+                gs.stage(host[i % n_pool])
+            gs.commit()
+            gs.stage(host[(i + 1) % n_pool])
+            g_staged["next"] = i + 1
+            last["host_loss"] = float(gs()[0])
+        ms_ge, _ = timed(g_e2e, "graph_e2e")
         graph_info = {"ms_per_step": ms_g, "value": pairs_all / (ms_g * 1e-3), "e2e_ms_per_step": ms_ge,
                       "e2e_value": pairs_all / (ms_ge * 1e-3),
                       "unit": UNIT, "what": "forward + backward + clip + AdamW + zero_grad replayed as one CUDA graph"}
@@ -382,6 +420,7 @@ def run_ours(args):
         rows.sort(key=lambda r: -r["ms"])
         with open(os.path.join(ROOT, "gpurun_out", "gemm_shapes.json"), "w") as f:
             json.dump(rows, f, indent=0)
+    g_bytes = sum(p[4] for p in prof)
     g_flops = sum(p[0] for p in prof)
     g_ms = sum(p[1].elapsed_time(p[2]) for p in prof)
     traffic = None
@@ -402,12 +441,13 @@ def run_ours(args):
         "config": {"workload": "XFM-base pretraining step ITC+ITM+MLM+MIM(VQ-KD), 224px / 40 tokens / 15 masked, "
                                "fwd+bwd+allreduce+clip+AdamW", "pairs_per_gpu": B, "global_pairs": pairs,
                    "parallelism": f"dp{world}", "arena_gib": round(arena / 2**30, 1), "l2": "inputs and activations exceed L2 (>= 58 MB per activation tensor)",
-                   "train_mode": True},
+                   "train_mode": True, "python_gc": "collected between the timed loops, disabled inside them"},
         "e2e": {"value": pairs / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                     "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write, mean of the profiled launches)",
+                     "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write, mean over every GEMM launch of a step)",
+                     "algorithmic_bytes_per_launch": g_bytes / max(len(prof), 1),
                      "kernel": "gemm_tcgen05_pair_kernel / gemm_tcgen05_kernel", "launches_per_step": len(prof),
                      "gemm_ms_per_step": g_ms, "peak_source": f"{pk_kind} bf16_tflops_sustained",
                      "step_tflops_algorithmic": GFLOP_PER_PAIR * B / ms_step,
@@ -423,14 +463,30 @@ def run_ours(args):
     if eager is not None:
         line["gpu_eager_baseline"] = eager
     if graph_info is not None:
+        # Headline = the step as the package's public API runs it for production (xfm_b200.graph.GraphedStep: the same
+        # kernels, one graph launch per step); the launch-by-launch sequence is kept beside it.
+        line["launch_sequence"] = {"value": line["value"], "ms_per_step": ms_step, "e2e_value": line["e2e"]["value"],
+                                   "e2e_ms_per_step": ms_e2e, "unit": UNIT,
+                                   "what": "the same step issued as individual kernel launches from Python (no graph)"}
+        line["value"], line["ms_per_step"] = graph_info["value"], graph_info["ms_per_step"]
+        line["e2e"].update(value=graph_info["e2e_value"], ms_per_step=graph_info["e2e_ms_per_step"])
+        line["config"]["step"] = "one CUDA graph replay per step (forward + backward + all-reduce + clip + AdamW + zero_grad)"
+        line["roofline"]["step_tflops_algorithmic"] = GFLOP_PER_PAIR * B / graph_info["ms_per_step"]
+        line["roofline"]["step_frac_of_peak"] = GFLOP_PER_PAIR * B / graph_info["ms_per_step"] / peak
+        line["graph_replays"] = args.steps
         line["cuda_graph"] = graph_info
     if rank == 0:
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(args, quick=True)
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=out_stream, flush=True)
     if world > 1:
+        # leave without running destructors: tearing down a process group while captured graphs / side streams still
+        # reference its communicator can block (seen with NCCL 2.28 after a graph capture)
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -555,9 +611,15 @@ def run_finetune(args):
     ms_graph, _ = timed(lambda i: step(resident[i & 1]), args.steps)
     last = {}
 
-    def e2e_step(i):   # inputs from pinned host memory, loss read back, inside the timed region
-        out = step(host[i & 1])
-        last["loss"] = float(out[0])
+    staged = {"next": None}
+
+    def e2e_step(i):   # inputs from pinned host memory (copy of step i+1 issued under step i), loss read back, all timed
+        if staged["next"] != i:
+            step.stage(host[i & 1])
+        step.commit()
+        step.stage(host[(i + 1) & 1])
+        staged["next"] = i + 1
+        last["loss"] = float(step()[0])
     ms_e2e, _ = timed(e2e_step, args.steps)
     clk = clocks.stop()
     pk, pk_kind = peaks()
@@ -661,7 +723,9 @@ def main():
     ap.add_argument("--config", default="pretrain", choices=["pretrain", "retrieval", "nlvr", "vqa"],
                     help="pretrain = BASELINE configs[1] (the headline); retrieval / nlvr / vqa = configs[2..4] at --res")
     ap.add_argument("--res", type=int, default=384, help="image resolution of the fine-tune configs")
-    ap.add_argument("--graph", action="store_true", help="pretrain config: replay the step as one CUDA graph (single GPU)")
+    ap.add_argument("--graph", dest="graph", action="store_true", default=True,
+                    help="pretrain config: time the step replayed as one CUDA graph and report it as the headline (default)")
+    ap.add_argument("--no-graph", dest="graph", action="store_false", help="headline = the launch-by-launch sequence")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-eager", action="store_true", help="skip the gpu_eager_baseline leg (eager PyTorch on the same GPU)")
     ap.add_argument("--overlap", default="auto", help="accelerator OVERLAP_ALLREDUCE: auto | true | false")

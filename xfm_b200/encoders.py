@@ -240,13 +240,19 @@ class VisionEncoder:
         x = L.assemble_tokens(patch, self.cls, self.mask_token, mask_u8, self.pos, B, npatch)
         st = State()
         st.blocks = []
+        ds_all = None
+        if train and max(self.drop_path) > 0:
+            # DropPath (beit2.py:35-45, one Bernoulli(keep) per sample per residual branch): all 2 x depth draws of the pass in
+            # three launches instead of three per branch
+            if getattr(self, "_keep", None) is None or self._keep.device != x.device:
+                self._keep = torch.tensor([1.0 - p for p in self.drop_path], device=x.device).view(-1, 1, 1)
+            ds_all = (torch.rand(self.depth, 2, B, device=x.device) < self._keep).float() / self._keep
         for i in range(self.depth):
             w = self.w[i]
             rb = L.relpos_bias_fwd(w["rel_table"], self.rel_index, N, self.H, self.bias_ld) if self.relbias else None
             ds = None
-            if train and self.drop_path[i] > 0:
-                keep = 1.0 - self.drop_path[i]
-                ds = tuple((torch.rand(B, device=x.device) < keep).float() / keep for _ in range(2))
+            if ds_all is not None and self.drop_path[i] > 0:
+                ds = (ds_all[i, 0], ds_all[i, 1])
             rel = (w["rel_table"], self.ws) if (self.relbias and self.rel_closed_form) else None
             x, s = BK.vit_block_fwd(x, w, B, N, self.H, self.eps, relbias=rb, drop_scale=ds, save=save, rel=rel)
             st.blocks.append(s)

@@ -77,6 +77,37 @@ class GraphedStep:
             self.core._static_masks[1].copy_(rows.pin_memory(), non_blocking=True)
         self.opt.refresh_hparams()
 
+    # ---- prefetching loader pattern: the host -> device copy of step i+1 runs on a side stream while the graph of step i
+    # executes; only a device -> device copy into the static tensors (microseconds) sits between two replays
+    def stage(self, host_inputs):
+        """Start copying a (pinned) host batch into the free staging slot, on the copy stream."""
+        if not hasattr(self, "_slots"):
+            dev = self.core.flat.P.device
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._slots = [{k: torch.empty_like(v) for k, v in self.static.items()} for _ in range(2)]
+            self._ready = [torch.cuda.Event(), torch.cuda.Event()]
+            self._consumed = [torch.cuda.Event(), torch.cuda.Event()]
+            for e in self._consumed:
+                e.record(torch.cuda.current_stream(dev))
+            self._next_slot, self._staged = 0, None
+        s = self._next_slot
+        self._copy_stream.wait_event(self._consumed[s])      # the commit that last read this slot has finished
+        with torch.cuda.stream(self._copy_stream):
+            for k, v in host_inputs.items():
+                self._slots[s][k].copy_(v, non_blocking=True)
+            self._ready[s].record(self._copy_stream)
+        self._staged, self._next_slot = s, s ^ 1
+
+    def commit(self):
+        """Move the staged batch into the static input tensors (device -> device) and refresh masks / hyper-parameters."""
+        s = self._staged
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._ready[s])
+        for k, v in self._slots[s].items():
+            self.static[k].copy_(v, non_blocking=True)
+        self._consumed[s].record(cur)
+        self.refill({})
+
     def __call__(self, inputs=None):
         """Replays the captured step on `inputs` (or on whatever the static tensors hold).  Returns the static output tensors
         (loss first, gradient norm last); their values are overwritten by the next call."""

@@ -165,7 +165,13 @@ def gemm(a, b, *, a_t=False, b_t=False, out=None, out_dtype=torch.bfloat16, bias
         e0.record()
         check(lib().xfm_gemm_bf16(C.byref(p), stream_ptr()), "xfm_gemm_bf16")
         e1.record()
-        gemm_profile.append((2.0 * M * N * K, e0, e1, (M, N, K, int(a_t), int(b_t))))
+        # algorithmic bytes of this launch: both operands once, the output once (read too when accumulating), every
+        # epilogue operand once
+        nbytes = 2 * (M * K + N * K) + out.element_size() * M * N * (2 if accumulate else 1)
+        for t in (aux_in, aux_out, residual):
+            if t is not None:
+                nbytes += t.element_size() * M * N
+        gemm_profile.append((2.0 * M * N * K, e0, e1, (M, N, K, int(a_t), int(b_t)), nbytes))
         return out
     check(lib().xfm_gemm_bf16(C.byref(p), stream_ptr()), "xfm_gemm_bf16")
     return out

@@ -10,7 +10,11 @@ parameter gradients straight into the flat gradient buffer.
 Differences a caller can observe (all documented in DESIGN.md):
   * tensors returned at the boundary are fp32 (like the reference) but computed in bf16 with fp32 accumulation;
   * get_hard_negatives returns two int64 device tensors (sampled on the GPU) instead of python lists — no host sync;
-  * parameters that took no part in a backward pass keep grad None, like the reference's unused parameters.
+  * parameters that took no part in a backward pass keep grad None, like the reference's unused parameters;
+  * get_matching_loss(..., return_cross_embeds=True) returns the positive pairs' CLS rows detached (no reference caller
+    back-propagates through them);
+  * get_text_embeds takes a private `_also_masked` argument and get_matching_and_fuse_mlm_loss exists besides the
+    reference's two separate methods: schedule-level fusions used by xfm_b200/model_pretrain.py, results identical.
 """
 import math
 import os
