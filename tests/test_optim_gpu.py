@@ -210,3 +210,39 @@ def test_lr_scheduler_values_reach_the_kernel():
         deltas.append(float((model.flat.view32(name) - before).abs().max()))
     # Adam with a constant gradient moves by exactly lr (bias-corrected m / sqrt(v) = 1)
     assert abs(deltas[0] - 1e-3) < 1e-6 and deltas[1] < 1e-9 and abs(deltas[2] - 5e-4) < 1e-6, deltas
+
+
+def test_optimizer_state_dict_round_trip_resumes_identically():
+    """Checkpoint / resume (Pretrain.py:438-442 reloads optimizer state): state_dict() in torch's layout (exp_avg, exp_avg_sq,
+    step per parameter) -> a fresh optimizer on an identical model -> the next step is bit-identical."""
+    from xfm_b200.accelerator import FlatAdamW
+    name = "vision_encoder.blocks.0.mlp.fc1.weight"
+    g = torch.Generator(device="cuda").manual_seed(0)
+
+    def fake_grads(model, k):
+        model.zero_grad()
+        for n in (name, "temp", "text_encoder.roberta.encoder.layer.1.output.LayerNorm.bias"):
+            v = model.flat.grad(n)
+            v.copy_(torch.randn(v.shape, device="cuda", generator=g) * (0.1 * (k + 1)))
+
+    a, _ = _tiny(vq=False)
+    opt_a = FlatAdamW(a, lr=1e-3, weight_decay=0.01, lr_mult=2.0)
+    for k in range(2):
+        fake_grads(a, k)
+        opt_a.step(max_grad_norm=1.0)
+    sd_model = {k: v.clone() for k, v in a.state_dict().items()}
+    sd_opt = opt_a.state_dict()
+    assert len(sd_opt["state"]) == 3 and all(s["step"] == 2 for s in sd_opt["state"].values())
+    b, _ = _tiny(vq=False)
+    b.load_state_dict(sd_model)
+    opt_b = FlatAdamW(b, lr=5e-4, weight_decay=0.0, lr_mult=1.0)
+    opt_b.load_state_dict(sd_opt)
+    assert [grp["lr"] for grp in opt_b.param_groups] == [grp["lr"] for grp in opt_a.param_groups]
+    g.manual_seed(7)
+    fake_grads(a, 2)
+    g.manual_seed(7)
+    fake_grads(b, 2)
+    opt_a.step(max_grad_norm=1.0)
+    opt_b.step(max_grad_norm=1.0)
+    assert torch.equal(a.flat.P, b.flat.P) and torch.equal(opt_a.M, opt_b.M) and torch.equal(opt_a.V, opt_b.V)
+    assert torch.equal(a.flat.S, b.flat.S)

@@ -90,11 +90,22 @@ class GraphedStep:
             for e in self._consumed:
                 e.record(torch.cuda.current_stream(dev))
             self._next_slot, self._staged = 0, None
+            if self.uses_masks:
+                for sl in self._slots:
+                    sl["__mask"] = torch.empty_like(self.core._static_masks[0])
+                    sl["__rows"] = torch.empty_like(self.core._static_masks[1])
         s = self._next_slot
+        masks = None
+        if self.uses_masks:   # host sampling for the NEXT step happens here, while the current replay runs on the device
+            m, rows = sample_batch(self.core._sampler, self._B)
+            masks = (m.pin_memory(), rows.pin_memory())
         self._copy_stream.wait_event(self._consumed[s])      # the commit that last read this slot has finished
         with torch.cuda.stream(self._copy_stream):
             for k, v in host_inputs.items():
                 self._slots[s][k].copy_(v, non_blocking=True)
+            if masks is not None:
+                self._slots[s]["__mask"].copy_(masks[0], non_blocking=True)
+                self._slots[s]["__rows"].copy_(masks[1], non_blocking=True)
             self._ready[s].record(self._copy_stream)
         self._staged, self._next_slot = s, s ^ 1
 
@@ -104,9 +115,14 @@ class GraphedStep:
         cur = torch.cuda.current_stream()
         cur.wait_event(self._ready[s])
         for k, v in self._slots[s].items():
-            self.static[k].copy_(v, non_blocking=True)
+            if k == "__mask":
+                self.core._static_masks[0].copy_(v, non_blocking=True)
+            elif k == "__rows":
+                self.core._static_masks[1].copy_(v, non_blocking=True)
+            else:
+                self.static[k].copy_(v, non_blocking=True)
         self._consumed[s].record(cur)
-        self.refill({})
+        self.opt.refresh_hparams()
 
     def __call__(self, inputs=None):
         """Replays the captured step on `inputs` (or on whatever the static tensors hold).  Returns the static output tensors
