@@ -245,4 +245,8 @@ def test_optimizer_state_dict_round_trip_resumes_identically():
     opt_a.step(max_grad_norm=1.0)
     opt_b.step(max_grad_norm=1.0)
     assert torch.equal(a.flat.P, b.flat.P) and torch.equal(opt_a.M, opt_b.M) and torch.equal(opt_a.V, opt_b.V)
-    assert torch.equal(a.flat.S, b.flat.S)
+    # the shadow of the updated segments is refreshed by the AdamW kernel itself (model `a` never ran a forward, so the
+    # rest of its shadow has not been written yet)
+    for n in (name, "temp", "text_encoder.roberta.encoder.layer.1.output.LayerNorm.bias"):
+        assert torch.equal(a.flat.view16(n), b.flat.view16(n))
+        assert torch.equal(a.flat.view16(n), a.flat.view32(n).to(torch.bfloat16))

@@ -1,0 +1,9 @@
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -15 > gpurun_out/r02k_pytest.log; tail -4 gpurun_out/r02k_pytest.log
+timeout 300 python tools/dev_kernels.py ln > gpurun_out/r02k_dev_ln.log 2>&1; tail -4 gpurun_out/r02k_dev_ln.log
+timeout 600 python bench.py --steps 20 --warmup 5 --no-eager --no-cpu > gpurun_out/r02k_bench.json 2> gpurun_out/r02k_bench.err; echo "bench rc=$?"
+timeout 600 python tools/gap_profile.py gpurun_out/r02k_gaps.txt > gpurun_out/r02k_gaps.log 2>&1; echo "gaps rc=$?"; tail -30 gpurun_out/r02k_gaps.txt
+python - <<PY
+import json
+d=json.load(open("gpurun_out/r02k_bench.json")); print("pretrain", d["value"], d["ms_per_step"], d["e2e"]["ms_per_step"], d["launch_sequence"]["ms_per_step"], d["step_ms"])
+PY

@@ -111,20 +111,41 @@ XFM_DEVINL float4 lds4(const uint8_t* slot, int dtype, int c) {  // 4 elements a
 // LayerNorm(dropout(dense(.)) + residual)): dx16 = bf16(dropout_mask * dx / (1 - p)) — the dgrad / wgrad operand, with the
 // forward's mask re-derived from (seed, row * D + col) like the GEMM epilogue that applied it — and dbias += its column
 // sums.  Replaces a dropout / cast pass and a column-sum pass over the same rows (2 launches per site, 60 sites per step).
-template <int NV, bool DENSE>
-__global__ void __launch_bounds__(LN_WARPS * 32, 1)
+//
+// Round 2 (ncu, profiles/r02j_ln_summary.txt): with 8 warps of 162 registers the kernel was bound by instruction latency,
+// not by DRAM (2 warps per scheduler, issue slots 30 % busy, 41 % of DRAM bandwidth).  Now 16 warps per CTA: the row's
+// g / xhat are not kept in registers between the two passes but recomputed from the staged row (it sits in shared memory
+// anyway), which brings the kernel under the 128 registers a 512-thread CTA may use; gamma is staged in shared memory too.
+constexpr int LNB_WARPS = 16;
+
+// DT >= 0 bakes the dtypes and D == NV * 128 into the instantiation (bit 0 dy fp32, bit 1 x fp32, bits 2-3 add_in: 0 none /
+// 1 bf16 / 2 fp32, bit 4 dx fp32): the per-load dtype branches and column bounds checks were ~40 % of the issued
+// instructions of the run-time version (DT = -1), which stays for every other shape.
+template <int NV, bool DENSE, int DT>
+__global__ void __launch_bounds__(LNB_WARPS * 32, 1)
 layernorm_bwd_kernel(const void* __restrict__ dy, int dy_dtype, const void* __restrict__ x, int x_dtype,
                      const float* __restrict__ stats, const float* __restrict__ w, const void* __restrict__ add_in,
                      int add_dtype, void* __restrict__ dx, int dx_dtype, float* __restrict__ dw, float* __restrict__ db,
-                     int M, int D, int rows_per_cta, int nw,   // nw: warps that own a staging ring (<= LN_WARPS)
+                     int M, int D, int rows_per_cta, int nw,   // nw: warps that own a staging ring (<= LNB_WARPS)
+                     int red_rows,                             // warps per group of the final reduction (divides LNB_WARPS)
                      bf16* __restrict__ dx16, float* __restrict__ dbias, float drop_p, uint64_t drop_seed,
                      const uint64_t* __restrict__ salt) {
   extern __shared__ __align__(16) uint8_t ln_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr bool FIX = DT >= 0;
+  if (FIX) {
+    D = NV * 128;
+    dy_dtype = DT & 1;
+    x_dtype = (DT >> 1) & 1;
+    add_dtype = ((DT >> 2) & 3) == 2;
+    dx_dtype = (DT >> 4) & 1;
+    if (((DT >> 2) & 3) == 0) add_in = nullptr;
+  }
   const int dy_b = D * (dy_dtype == 1 ? 4 : 2), x_b = D * (x_dtype == 1 ? 4 : 2);
   const int add_b = add_in ? D * (add_dtype == 1 ? 4 : 2) : 0;
   const int slot_b = dy_b + x_b + add_b + 16;   // + the row's (mean, rstd)
-  uint8_t* ring = ln_smem + (size_t)warp * 2 * slot_b;
+  const float* w_s = (const float*)ln_smem;     // gamma, staged once per CTA
+  uint8_t* ring = ln_smem + (size_t)D * 4 + (size_t)warp * 2 * slot_b;
   const uint32_t ring_a = smem_u32(ring);
   float4 aw[NV], ab[NV], ad[DENSE ? NV : 1];
 #pragma unroll
@@ -155,6 +176,8 @@ layernorm_bwd_kernel(const void* __restrict__ dy, int dy_dtype, const void* __re
   int row = row0 + warp;
   issue(row, 0);
   issue(row + nw, 1);
+  for (int c = threadIdx.x * 4; c < D; c += LNB_WARPS * 32 * 4) *(float4*)(ln_smem + (size_t)c * 4) = *(const float4*)(w + c);
+  __syncthreads();
   for (int k = 0; row < row1; ++k, row += nw) {
     cp_async_wait<1>();
     __syncwarp();
@@ -162,34 +185,43 @@ layernorm_bwd_kernel(const void* __restrict__ dy, int dy_dtype, const void* __re
     const float2 mr = *(const float2*)(slot + dy_b + x_b + add_b);
     const float mean = mr.x, rstd = mr.y;
     const size_t base = (size_t)row * D;
-    float4 g[NV], xh[NV];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
+    for (int i = 0; i < NV; ++i) {   // pass 1: the row's two means, dgamma / dbeta partial sums
       const int c = (i * 32 + lane) * 4;
-      if (c < D) {
+      if (FIX || c < D) {
         const float4 d = lds4(slot, dy_dtype, c);
         const float4 xv = lds4(slot + dy_b, x_dtype, c);
-        const float4 ww = *(const float4*)(w + c);
-        xh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
-        g[i] = make_float4(d.x * ww.x, d.y * ww.y, d.z * ww.z, d.w * ww.w);
-        s1 += g[i].x + g[i].y + g[i].z + g[i].w;
-        s2 += g[i].x * xh[i].x + g[i].y * xh[i].y + g[i].z * xh[i].z + g[i].w * xh[i].w;
-        aw[i].x += d.x * xh[i].x; aw[i].y += d.y * xh[i].y; aw[i].z += d.z * xh[i].z; aw[i].w += d.w * xh[i].w;
+        const float4 ww = *(const float4*)(w_s + c);
+        const float4 xh = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
+        const float4 g = make_float4(d.x * ww.x, d.y * ww.y, d.z * ww.z, d.w * ww.w);
+        s1 += g.x + g.y + g.z + g.w;
+        s2 += g.x * xh.x + g.y * xh.y + g.z * xh.z + g.w * xh.w;
+        aw[i].x += d.x * xh.x; aw[i].y += d.y * xh.y; aw[i].z += d.z * xh.z; aw[i].w += d.w * xh.w;
         ab[i].x += d.x; ab[i].y += d.y; ab[i].z += d.z; ab[i].w += d.w;
       }
     }
-    s1 = warp_sum(s1) / (float)D;
-    s2 = warp_sum(s2) / (float)D;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
+    for (int o = 16; o > 0; o >>= 1) {   // the two reductions interleaved: one shuffle latency per level, not two
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    s1 /= (float)D;
+    s2 /= (float)D;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {   // pass 2: dx (g and xhat recomputed from the staged row, bit-identical to pass 1)
       const int c = (i * 32 + lane) * 4;
-      if (c < D) {
+      if (FIX || c < D) {
+        const float4 d = lds4(slot, dy_dtype, c);
+        const float4 xv = lds4(slot + dy_b, x_dtype, c);
+        const float4 ww = *(const float4*)(w_s + c);
+        const float4 xh = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
+        const float4 g = make_float4(d.x * ww.x, d.y * ww.y, d.z * ww.z, d.w * ww.w);
         float4 o;
-        o.x = rstd * (g[i].x - s1 - xh[i].x * s2);
-        o.y = rstd * (g[i].y - s1 - xh[i].y * s2);
-        o.z = rstd * (g[i].z - s1 - xh[i].z * s2);
-        o.w = rstd * (g[i].w - s1 - xh[i].w * s2);
+        o.x = rstd * (g.x - s1 - xh.x * s2);
+        o.y = rstd * (g.y - s1 - xh.y * s2);
+        o.z = rstd * (g.z - s1 - xh.z * s2);
+        o.w = rstd * (g.w - s1 - xh.w * s2);
         if (add_in) {
           const float4 a = lds4(slot + dy_b + x_b, add_dtype, c);
           o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
@@ -220,42 +252,43 @@ layernorm_bwd_kernel(const void* __restrict__ dy, int dy_dtype, const void* __re
   }
   cp_async_wait<0>();
   if (!dw && !DENSE) return;
-  __syncthreads();                                   // the rings are dead: reuse shared memory for the cross-warp reduction
-  float* rw = (float*)ln_smem;
-  float* rb = rw + LN_WARPS * D;
-  float* rd = rb + LN_WARPS * D;
+  // The rings are dead: reuse shared memory for the cross-warp reduction, one accumulator array at a time and `red_rows`
+  // warps at a time (16 rows of D floats fit up to D = 3584; wider rows go in two or four groups).
+  float* rbuf = (float*)ln_smem;
+  auto reduce_into = [&](const float4* acc, float* out) {
+    for (int g0 = 0; g0 < LNB_WARPS; g0 += red_rows) {
+      __syncthreads();
+      if (warp >= g0 && warp < g0 + red_rows) {
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int c = (i * 32 + lane) * 4;
-    if (c < D) {
-      *(float4*)(rw + warp * D + c) = aw[i];
-      *(float4*)(rb + warp * D + c) = ab[i];
-      if (DENSE) *(float4*)(rd + warp * D + c) = ad[i];
+        for (int i = 0; i < NV; ++i) {
+          const int c = (i * 32 + lane) * 4;
+          if (FIX || c < D) *(float4*)(rbuf + (warp - g0) * D + c) = acc[i];
+        }
+      }
+      __syncthreads();
+      for (int c = threadIdx.x; c < D; c += blockDim.x) {
+        float t = 0.f;
+        for (int k = 0; k < red_rows; ++k) t += rbuf[k * D + c];
+        atomicAdd(out + c, t);
+      }
     }
+  };
+  if (dw) {
+    reduce_into(aw, dw);
+    reduce_into(ab, db);
   }
-  __syncthreads();
-  for (int c = threadIdx.x; c < D; c += blockDim.x) {
-    float sw = 0.f, sb = 0.f, sd = 0.f;
-#pragma unroll
-    for (int k = 0; k < LN_WARPS; ++k) {
-      sw += rw[k * D + c];
-      sb += rb[k * D + c];
-      if (DENSE) sd += rd[k * D + c];
-    }
-    if (dw) {
-      atomicAdd(dw + c, sw);
-      atomicAdd(db + c, sb);
-    }
-    if (DENSE && dbias) atomicAdd(dbias + c, sd);
-  }
+  if (DENSE && dbias) reduce_into(ad, dbias);
 }
 
 // -------------------------------------------------------------------------------- LayerScale backward
 // Forward (GEMM epilogue): x_out = x_in + rs[row/rpg] * gamma * z, z = acc + bias (saved as bf16).
 // Backward: dz = dx_out * gamma * rs (bf16 out), dgamma += sum_rows dx_out * rs * z, dbias += sum_rows dz.
 // Reference: beit2.py:204-205 (gamma_1 / gamma_2, DropPath).
+// A row's loads are all issued before anything consumes them (a separate, branch-free load phase): with the loads inside
+// the compute loop the compiler kept one DRAM round trip per 128 columns (ncu r02j: 78 % of the stalls on the first use
+// of each load, 38 % of DRAM bandwidth).
 template <int NV>
-__global__ void __launch_bounds__(LN_WARPS * 32)
+__global__ void __launch_bounds__(LN_WARPS * 32, NV <= 8 ? 2 : 1)
 layerscale_bwd_kernel(const float* __restrict__ dxo, const bf16* __restrict__ z, const float* __restrict__ gamma,
                       const float* __restrict__ rs, int rpg, bf16* __restrict__ dz, float* __restrict__ dgamma,
                       float* __restrict__ dbias, int M, int D, int rows_per_cta) {
@@ -266,22 +299,31 @@ layerscale_bwd_kernel(const float* __restrict__ dxo, const bf16* __restrict__ z,
   for (int i = 0; i < NV; ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   const int row0 = blockIdx.x * rows_per_cta;
   const int row1 = min(M, row0 + rows_per_cta);
+  float* gs = red + 2 * LN_WARPS * D;   // gamma, zero-padded to NV * 128 columns: the compute phase needs no bounds branch
+  for (int c = threadIdx.x; c < NV * 128; c += LN_WARPS * 32) gs[c] = c < D ? gamma[c] : 0.f;
+  __syncthreads();
   for (int row = row0 + warp; row < row1; row += LN_WARPS) {
     const size_t base = (size_t)row * D;
     const float s = rs ? rs[row / rpg] : 1.f;
+    float4 d[NV];
+    uint2 zr[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = (i * 32 + lane) * 4;
-      if (c < D) {
-        const float4 d = *(const float4*)(dxo + base + c);
-        const float4 zz = ld4(z, 0, base + c);
-        const float4 gm = *(const float4*)(gamma + c);
-        const float4 ds = make_float4(d.x * s, d.y * s, d.z * s, d.w * s);
-        const float4 o = make_float4(ds.x * gm.x, ds.y * gm.y, ds.z * gm.z, ds.w * gm.w);
-        st4(dz, 0, base + c, o);
-        ag[i].x += ds.x * zz.x; ag[i].y += ds.y * zz.y; ag[i].z += ds.z * zz.z; ag[i].w += ds.w * zz.w;
-        ab[i].x += o.x; ab[i].y += o.y; ab[i].z += o.z; ab[i].w += o.w;
-      }
+      const bool in = c < D;
+      d[i] = in ? __ldg((const float4*)(dxo + base + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      zr[i] = in ? __ldg((const uint2*)(z + base + c)) : make_uint2(0u, 0u);
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      const float2 z0 = __bfloat1622float2(*(const __nv_bfloat162*)&zr[i].x), z1 = __bfloat1622float2(*(const __nv_bfloat162*)&zr[i].y);
+      const float4 gm = *(const float4*)(gs + c);
+      const float4 ds = make_float4(d[i].x * s, d[i].y * s, d[i].z * s, d[i].w * s);
+      const float4 o = make_float4(ds.x * gm.x, ds.y * gm.y, ds.z * gm.z, ds.w * gm.w);
+      if (c < D) st4(dz, 0, base + c, o);
+      ag[i].x += ds.x * z0.x; ag[i].y += ds.y * z0.y; ag[i].z += ds.z * z1.x; ag[i].w += ds.w * z1.y;
+      ab[i].x += o.x; ab[i].y += o.y; ab[i].z += o.z; ab[i].w += o.w;
     }
   }
   float* rg = red;
@@ -785,14 +827,6 @@ int layernorm_fwd(const void* x, int x_dtype, const float* w, const float* b, vo
   LAUNCH_END();
 }
 
-static int rows_per_cta_for(int M) {
-  // ~3 CTAs per SM; each CTA reduces its rows before touching the global dw/db atomics
-  int ctas = num_sms() * 3;
-  int r = (M + ctas - 1) / ctas;
-  r = ((r + LN_WARPS - 1) / LN_WARPS) * LN_WARPS;
-  return r < LN_WARPS ? LN_WARPS : r;
-}
-
 int layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* stats, const float* w,
                   const void* add_in, int add_dtype, void* dx, int dx_dtype, float* dw, float* db, int M, int D,
                   cudaStream_t s) {
@@ -813,61 +847,87 @@ int layernorm_bwd_dense(const void* dy, int dy_dtype, const void* x, int x_dtype
     return XFM_ERR_BAD_ARG;
   }
   if (M <= 0) return 0;
-  // one CTA per SM (the staging rings take ~100-150 KB), >= 2 rows per warp so the ring actually pipelines
+  // one CTA of 16 warps per SM (the staging rings take ~100-220 KB), >= 2 rows per warp so the ring actually pipelines
+  const size_t slot = (size_t)D * ((dy_dtype == 1 ? 4 : 2) + (x_dtype == 1 ? 4 : 2) + (add_in ? (add_dtype == 1 ? 4 : 2) : 0)) + 16;
+  const size_t wbytes = (size_t)D * 4, budget = 224 * 1024;
+  int nw = LNB_WARPS;   // wide fp32 rows: fewer warps get a staging ring so the rings fit shared memory
+  while (nw > 1 && wbytes + (size_t)nw * 2 * slot > budget) --nw;
   int ctas = num_sms();
   int rpc = (M + ctas - 1) / ctas;
-  rpc = ((rpc + LN_WARPS - 1) / LN_WARPS) * LN_WARPS;
-  if (rpc < 2 * LN_WARPS) rpc = 2 * LN_WARPS;
+  if (rpc < 2 * nw) rpc = 2 * nw;
   const int grid = (M + rpc - 1) / rpc;
-  const size_t slot = (size_t)D * ((dy_dtype == 1 ? 4 : 2) + (x_dtype == 1 ? 4 : 2) + (add_in ? (add_dtype == 1 ? 4 : 2) : 0)) + 16;
-  int nw = LN_WARPS;   // wide fp32 rows: fewer warps get a staging ring so the rings fit shared memory
-  while (nw > 1 && (size_t)nw * 2 * slot > 200 * 1024) --nw;
-  size_t smem = (size_t)nw * 2 * slot;
-  const size_t red = (size_t)(dx16 ? 3 : 2) * LN_WARPS * D * sizeof(float);
+  size_t smem = wbytes + (size_t)nw * 2 * slot;
+  int red_rows = LNB_WARPS;
+  while (red_rows > 1 && (size_t)red_rows * D * sizeof(float) > budget) red_rows >>= 1;
+  const size_t red = (size_t)red_rows * D * sizeof(float);
   if (smem < red) smem = red;
-  if (smem > 220 * 1024) {
+  if (smem > 227 * 1024) {
     set_error("layernorm_bwd: D=%d needs %zu bytes of shared memory", D, smem);
     return XFM_ERR_BAD_ARG;
   }
-  if (dx16) {
-    LN_DISPATCH(D, {
-      static size_t attr = 0;  // one per instantiation
-      if (smem > attr) {
-        cudaError_t e = cudaFuncSetAttribute(layernorm_bwd_kernel<NV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        attr = smem;
+#define LNB_LAUNCH(NVv, DENSEv, DTv)                                                                                      \
+  do {                                                                                                                    \
+    auto kern = layernorm_bwd_kernel<NVv, DENSEv, DTv>;                                                                   \
+    static size_t attr = 0; /* one per instantiation */                                                                   \
+    if (smem > attr) {                                                                                                    \
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                 \
+      if (e != cudaSuccess) return (int)e;                                                                                \
+      attr = smem;                                                                                                        \
+    }                                                                                                                     \
+    kern<<<grid, LNB_WARPS * 32, smem, s>>>(dy, dy_dtype, x, x_dtype, stats, w, add_in, add_dtype, dx, dx_dtype, dw, db, M, D, \
+                                            rpc, nw, red_rows, dx16, dbias, drop_p, drop_seed, seed_salt_ptr());          \
+  } while (0)
+  if (!dx16) {
+    dbias = nullptr;
+    drop_p = 0.f;
+    drop_seed = 0;
+  }
+  if (D == 768 && x_dtype == 1 && dx_dtype == 1) {   // the shapes of the base model's steps: dtypes baked in
+    const int dt = (dy_dtype == 1 ? 1 : 0) | 2 | ((add_in ? (add_dtype == 1 ? 2 : 1) : 0) << 2) | 16;
+    bool done = true;
+    if (dx16) {
+      switch (dt) {
+        case 18: LNB_LAUNCH(6, true, 18); break;    // dy bf16
+        case 19: LNB_LAUNCH(6, true, 19); break;    // dy fp32
+        default: done = false;
       }
-      layernorm_bwd_kernel<NV, true><<<grid, LN_WARPS * 32, smem, s>>>(dy, dy_dtype, x, x_dtype, stats, w, add_in, add_dtype, dx,
-                                                                       dx_dtype, dw, db, M, D, rpc, nw, dx16, dbias, drop_p, drop_seed, seed_salt_ptr());
-    });
+    } else {
+      switch (dt) {
+        case 18: LNB_LAUNCH(6, false, 18); break;   // dy bf16, no add_in
+        case 19: LNB_LAUNCH(6, false, 19); break;   // dy fp32, no add_in
+        case 26: LNB_LAUNCH(6, false, 26); break;   // dy bf16, add_in fp32 (BEiT blocks)
+        case 27: LNB_LAUNCH(6, false, 27); break;   // dy fp32, add_in fp32
+        default: done = false;
+      }
+    }
+    if (done) {
+      LAUNCH_END();
+    }
+  }
+  if (dx16) {
+    LN_DISPATCH(D, LNB_LAUNCH(NV, true, -1));
     LAUNCH_END();
   }
-  LN_DISPATCH(D, {
-    static size_t attr = 0;  // one per instantiation
-    if (smem > attr) {
-      cudaError_t e = cudaFuncSetAttribute(layernorm_bwd_kernel<NV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return (int)e;
-      attr = smem;
-    }
-    layernorm_bwd_kernel<NV, false><<<grid, LN_WARPS * 32, smem, s>>>(dy, dy_dtype, x, x_dtype, stats, w, add_in, add_dtype, dx,
-                                                                      dx_dtype, dw, db, M, D, rpc, nw, nullptr, nullptr, 0.f, 0, seed_salt_ptr());
-  });
+  LN_DISPATCH(D, LNB_LAUNCH(NV, false, -1));
   LAUNCH_END();
+#undef LNB_LAUNCH
 }
 
 int layerscale_bwd(const float* dxo, const bf16* z, const float* gamma, const float* rs, int rpg, bf16* dz, float* dgamma,
                    float* dbias, int M, int D, cudaStream_t s) {
   if (ln_check(D)) return XFM_ERR_BAD_ARG;
   if (M <= 0) return 0;
-  const int rpc = rows_per_cta_for(M);
+  const int ctas = num_sms() * (D <= 1024 ? 2 : 1);   // the resident CTAs (register-bound): exactly one wave
+  int rpc = (M + ctas - 1) / ctas;
+  if (rpc < LN_WARPS) rpc = LN_WARPS;
   const int grid = (M + rpc - 1) / rpc;
   LN_DISPATCH(D, {
     static bool attr = false;
     if (!attr) {
-      cudaFuncSetAttribute(layerscale_bwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * LN_WARPS * NV * 128 * 4);
+      cudaFuncSetAttribute(layerscale_bwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * LN_WARPS + 1) * NV * 128 * 4);
       attr = true;
     }
-    layerscale_bwd_kernel<NV><<<grid, LN_WARPS * 32, (size_t)2 * LN_WARPS * D * sizeof(float), s>>>(
+    layerscale_bwd_kernel<NV><<<grid, LN_WARPS * 32, ((size_t)2 * LN_WARPS * D + NV * 128) * sizeof(float), s>>>(
         dxo, z, gamma, rs, rpg > 0 ? rpg : 1, dz, dgamma, dbias, M, D, rpc);
   });
   LAUNCH_END();

@@ -534,14 +534,22 @@ constexpr int PAIR_STAGE_BYTES = 2 * 16384;  // A 128 x 64 + B 128 x 64 (bf16)
 // the f32 TMA epilogue below): a ring of two 4 KB fp32 tiles per epilogue warp.  (A three-tile ring with 4 operand stages
 // was measured first: the K = 3072 GEMMs lost in the main loop what the epilogue gained.)
 constexpr int F32_EPI_TILE_BYTES = 32 * 32 * 4;
-constexpr int F32_EPI_RING = 2;
-template <int EPI>   // 0: classic / bf16 TMA-store epilogues, 1: f32 TMA epilogue, 2: dGELU (bf16 in / bf16 out) TMA epilogue
+// EPI = 3: the f32 TMA epilogue for SHORT-K GEMMs (K <= 1024: the N = K = 768 projections): 3 operand stages and a ring
+// of FOUR tiles per epilogue warp.  With two tiles the residual of block b + 1 can only be requested once the store of
+// block b - 1 has finished reading its tile, i.e. one block ahead and behind a store wait: every block then waits out a
+// DRAM round trip (r01g_gemm_proj_stalls: 38 % long-scoreboard stalls, 15 % of the samples at the final cluster barrier
+// waiting for the epilogue; 50 us where operands + residual + outputs are 27 us of HBM time).  Four tiles keep two
+// residual blocks in flight and never wait on the newest store; the main loop of these GEMMs is ~12 k-blocks per tile and
+// not the limiter, so it can give up two stages.
+template <int EPI>   // 0: classic / bf16 TMA-store epilogues, 1 / 3: f32 TMA epilogue, 2: dGELU (bf16 in / bf16 out) TMA epilogue
 struct PairCfg {
-  static constexpr int STAGES = 5;
-  static constexpr int EPI_BYTES = 8 * TMA_EPI_WARP_BYTES;   // >= the two-tile rings of the EPI = 1 / 2 variants
+  static constexpr int STAGES = EPI == 3 ? 3 : 5;
+  static constexpr int RING = EPI == 3 ? 4 : 2;
+  static constexpr int EPI_BYTES = EPI == 3 ? 8 * RING * F32_EPI_TILE_BYTES : 8 * TMA_EPI_WARP_BYTES;   // >= the rings of EPI = 1 / 2
   static constexpr int BAR_BYTES = 512;
   static constexpr int SMEM_BYTES = STAGES * PAIR_STAGE_BYTES + EPI_BYTES + BAR_BYTES;
-  static_assert(EPI_BYTES >= 8 * 32 * 34 * 4 && EPI_BYTES >= 8 * F32_EPI_RING * F32_EPI_TILE_BYTES, "staging must fit");
+  static_assert(EPI_BYTES >= 8 * 32 * 34 * 4 && EPI_BYTES >= 8 * RING * F32_EPI_TILE_BYTES, "staging must fit");
+  static_assert((2 * STAGES + 5 + 8 * RING) * 8 <= BAR_BYTES, "barriers must fit");
   static_assert(SMEM_BYTES <= 232448, "shared memory");
 };
 
@@ -558,6 +566,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
   constexpr bool DG_EPI = EPI == 2;    // dGELU: bf16 pre-activation in / bf16 out (EPI == 1: f32 residual in / f32 out)
   constexpr int RING_TILE_BYTES = DG_EPI ? 32 * 32 * 2 : F32_EPI_TILE_BYTES;
   constexpr int STAGES = PC::STAGES;
+  constexpr int F32_EPI_RING = PC::RING;
   constexpr int BLOCK_N = 256;
   extern __shared__ __align__(1024) uint8_t smem[];
   if (smem_u32(smem) & 1023) __trap();
@@ -718,7 +727,12 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
       ++pf_k;
       if (++pf_c >= c_end || !block_at(pf_t, pf_c, rb, n)) { pf_t += num_pairs; pf_c = c_begin; }
     };
-    if (want_res && lane == 0) prefetch();
+    // residual blocks requested ahead of the one being combined: 1 with the two-tile ring, 2 with the four-tile ring
+    constexpr int PF_AHEAD = F32_EPI_RING == 2 ? 1 : F32_EPI_RING - 2;
+    if (want_res && lane == 0) {
+#pragma unroll
+      for (int k = 0; k < PF_AHEAD; ++k) prefetch();
+    }
     int blk = 0;   // blocks consumed so far
     int as = 0;
     uint32_t aphase = 0;
@@ -745,8 +759,10 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
             for (int k = 0; k < 8; ++k) res[k] = *(const float4*)(tile + swz128(lane, k));
           }
           if (lane == 0) {
-            tma_store_wait_read<0>();          // the store of block blk - 1 has finished reading the other tile ...
-            prefetch();                        // ... which now receives the residual of block blk + 1
+            // the tile of block blk + PF_AHEAD was last read by the store of block blk + PF_AHEAD - RING: with two tiles
+            // that is the newest store (wait for all), with four the one before it (the newest may still be reading)
+            tma_store_wait_read<F32_EPI_RING - PF_AHEAD - 1>();
+            prefetch();
           }
         }
         const int row = row_base + lane;
@@ -1025,6 +1041,19 @@ static int launch_gemm_pair(const xfm_gemm_params* p, const GemmArgs& g, cudaStr
     if (!rc && p->residual) rc = encode_2d_f32(&map_aux, p->residual, p->N, p->M, p->ld_res);
     if (rc) return rc;
     g2.tma_epi = 2;
+    static const bool deep_on = getenv("XFM_GEMM_F32_DEEP") == nullptr || atoi(getenv("XFM_GEMM_F32_DEEP")) != 0;
+    if (deep_on && p->residual && g.kb_total <= 16) {   // short K: deep residual ring, 3 operand stages (PairCfg<3>)
+      auto kern3 = gemm_tcgen05_pair_kernel<A_MN, B_MN, 3>;
+      static bool attr3_set = false;
+      if (!attr3_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern3, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<3>::SMEM_BYTES);
+        if (e != cudaSuccess) return (int)e;
+        attr3_set = true;
+      }
+      kern3<<<2 * pairs, GEMM_THREADS, PairCfg<3>::SMEM_BYTES, stream>>>(map_a, map_b, map_c, map_aux, g2);
+      count_launch();
+      return (int)cudaGetLastError();
+    }
     auto kern32 = gemm_tcgen05_pair_kernel<A_MN, B_MN, 1>;
     static bool attr32_set = false;
     if (!attr32_set) {
