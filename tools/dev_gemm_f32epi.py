@@ -22,7 +22,10 @@ def rnd(*s, dt=torch.bfloat16, scale=0.5):
     return (torch.randn(*s, device="cuda", generator=g) * scale).to(dt)
 
 
-def case(name, M, N, K, layerscale=False, drop=0.0, b_t=False, nbuf=3, reps=30):
+def case(name, M, N, K, layerscale=False, drop=0.0, b_t=False, nbuf=3, reps=30, aux=None, scale=None):
+    """aux / scale override which halves of the LayerScale epilogue are on (timing only)."""
+    if aux is not None or scale is not None:
+        return parts(name, M, N, K, bool(aux), bool(scale), nbuf, reps)
     sets = []
     for i in range(nbuf):
         A, B = rnd(M, K), rnd(N, K, scale=0.05)
@@ -73,6 +76,39 @@ def case(name, M, N, K, layerscale=False, drop=0.0, b_t=False, nbuf=3, reps=30):
     print(rec, flush=True)
 
 
+def parts(name, M, N, K, aux, scale, nbuf, reps):
+    sets = [(rnd(M, K), rnd(N, K, scale=0.05), rnd(M, N, dt=torch.float32)) for _ in range(nbuf)]
+    bias, gamma = rnd(N, dt=torch.float32), rnd(N, dt=torch.float32)
+    rs = torch.rand(M // 197 + 1, device="cuda", generator=g) + 0.5
+    kw = dict(bias=bias, out_dtype=torch.float32)
+    if scale:
+        kw.update(col_scale=gamma, row_group_scale=rs, rows_per_group=197)
+    auxb = torch.empty(M, N, dtype=torch.bfloat16, device="cuda") if aux else None
+    outb = torch.empty(M, N, dtype=torch.float32, device="cuda")
+
+    def run(i):
+        A, B, res = sets[i % nbuf]
+        L.gemm(A, B, residual=res, aux_out=auxb, out=outb, **kw)
+    for i in range(3):
+        run(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(reps):
+        run(i)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / reps * 1e3
+    rec = dict(tag=tag, case=name, M=M, N=N, K=K, aux=aux, scale=scale, us=round(us, 1), tflops=round(2.0 * M * N * K / us / 1e6, 1))
+    OUT.write(json.dumps(rec) + "\n")
+    OUT.flush()
+    print(rec, flush=True)
+
+
+case("parts_res_only", 18912, 768, 768, aux=False, scale=False)
+case("parts_res_aux", 18912, 768, 768, aux=True, scale=False)
+case("parts_res_scale", 18912, 768, 768, aux=False, scale=True)
+case("parts_res_aux_scale", 18912, 768, 768, aux=True, scale=True)
 case("vit_proj_layerscale", 18912, 768, 768, layerscale=True)
 case("fusion_out_dense", 15360, 768, 768, drop=0.1)
 case("text_out_dense", 7680, 768, 768, drop=0.1)

@@ -534,18 +534,15 @@ constexpr int PAIR_STAGE_BYTES = 2 * 16384;  // A 128 x 64 + B 128 x 64 (bf16)
 // the f32 TMA epilogue below): a ring of two 4 KB fp32 tiles per epilogue warp.  (A three-tile ring with 4 operand stages
 // was measured first: the K = 3072 GEMMs lost in the main loop what the epilogue gained.)
 constexpr int F32_EPI_TILE_BYTES = 32 * 32 * 4;
-// EPI = 3: the f32 TMA epilogue for SHORT-K GEMMs (K <= 1024: the N = K = 768 projections): 3 operand stages and a ring
-// of FOUR tiles per epilogue warp.  With two tiles the residual of block b + 1 can only be requested once the store of
-// block b - 1 has finished reading its tile, i.e. one block ahead and behind a store wait: every block then waits out a
-// DRAM round trip (r01g_gemm_proj_stalls: 38 % long-scoreboard stalls, 15 % of the samples at the final cluster barrier
-// waiting for the epilogue; 50 us where operands + residual + outputs are 27 us of HBM time).  Four tiles keep two
-// residual blocks in flight and never wait on the newest store; the main loop of these GEMMs is ~12 k-blocks per tile and
-// not the limiter, so it can give up two stages.
-template <int EPI>   // 0: classic / bf16 TMA-store epilogues, 1 / 3: f32 TMA epilogue, 2: dGELU (bf16 in / bf16 out) TMA epilogue
+// (Round 2: a four-tile ring with three operand stages for the short-K projections — two residual blocks in flight, no
+// wait on the newest store — measured 54.1 us against 53.5 us for the 18912 x 768 x 768 projection, i.e. the residual
+// latency is not what bounds this epilogue; removed again.  What did cost time: the per-lane row stores of the saved
+// pre-scale value, see below.)
+template <int EPI>   // 0: classic / bf16 TMA-store epilogues, 1: f32 TMA epilogue, 2: dGELU (bf16 in / bf16 out) TMA epilogue
 struct PairCfg {
-  static constexpr int STAGES = EPI == 3 ? 3 : 5;
-  static constexpr int RING = EPI == 3 ? 4 : 2;
-  static constexpr int EPI_BYTES = EPI == 3 ? 8 * RING * F32_EPI_TILE_BYTES : 8 * TMA_EPI_WARP_BYTES;   // >= the rings of EPI = 1 / 2
+  static constexpr int STAGES = 5;
+  static constexpr int RING = 2;
+  static constexpr int EPI_BYTES = 8 * TMA_EPI_WARP_BYTES;   // >= the two-tile rings of the EPI = 1 / 2 variants
   static constexpr int BAR_BYTES = 512;
   static constexpr int SMEM_BYTES = STAGES * PAIR_STAGE_BYTES + EPI_BYTES + BAR_BYTES;
   static_assert(EPI_BYTES >= 8 * 32 * 34 * 4 && EPI_BYTES >= 8 * RING * F32_EPI_TILE_BYTES, "staging must fit");
@@ -768,9 +765,14 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
         const int row = row_base + lane;
         float rs = 1.f;
         if (g.row_group_scale) rs = __ldg(g.row_group_scale + min(row, g.M - 1) / g.rows_per_group);
-        float4 b4[8];   // requested before the TMEM wait so the two latencies overlap
+        float4 b4[8];   // requested before the TMEM wait so the latencies overlap
 #pragma unroll
         for (int k = 0; k < 8; ++k) b4[k] = g.bias ? __ldg((const float4*)(g.bias + n) + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 cs4[DG_EPI ? 1 : 8];   // LayerScale gamma of the block's columns, likewise
+        if (!DG_EPI && g.col_scale) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) cs4[k] = __ldg((const float4*)(g.col_scale + n) + k);
+        }
         tmem_ld_wait();
         float v[32];
 #pragma unroll
@@ -798,24 +800,34 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
             *(uint4*)(tile + swz64(lane, k)) = u;
           }
         } else {
-        if (g.aux_out && row < g.M) {
-          // saved pre-scale value z = acc + bias (bf16; LayerScale backward needs it): this lane's 64-byte row segment,
-          // written straight from registers (no shared-memory tile left for it; the stores are fire-and-forget)
-          uint4* ap = (uint4*)(g.aux_out + (int64_t)row * g.ld_aux_out + n);
+        if (g.aux_out) {
+          // saved pre-scale value z = acc + bias (bf16; LayerScale backward needs it).  Each lane holds the 64 bytes of
+          // ITS row: storing them from there costs 32 L1 wavefronts per instruction (32 rows), 128 per block — 8 us of the
+          // 50 us projection GEMM.  The block's tile is free between the residual read and the output write, so the rows
+          // are transposed through it (SWIZZLE_64B positions, conflict free both ways): four lanes then store one row's
+          // 64 bytes, 8 rows per instruction.
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             uint4 u;
             __nv_bfloat162 t0 = __floats2bfloat162_rn(v[8 * k], v[8 * k + 1]), t1 = __floats2bfloat162_rn(v[8 * k + 2], v[8 * k + 3]);
             __nv_bfloat162 t2 = __floats2bfloat162_rn(v[8 * k + 4], v[8 * k + 5]), t3 = __floats2bfloat162_rn(v[8 * k + 6], v[8 * k + 7]);
             u.x = *(uint32_t*)&t0; u.y = *(uint32_t*)&t1; u.z = *(uint32_t*)&t2; u.w = *(uint32_t*)&t3;
-            ap[k] = u;
+            *(uint4*)(tile + swz64(lane, k)) = u;
           }
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int r = 8 * j + (lane >> 2), kk = lane & 3;
+            const uint4 u = *(const uint4*)(tile + swz64(r, kk));
+            if (row_base + r < g.M) *(uint4*)(g.aux_out + (int64_t)(row_base + r) * g.ld_aux_out + n + 8 * kk) = u;
+          }
+          __syncwarp();   // the output rows overwrite the tile next
         }
         if (has_scale) {
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             float4 c4 = make_float4(1.f, 1.f, 1.f, 1.f);
-            if (g.col_scale) c4 = __ldg((const float4*)(g.col_scale + n) + k);
+            if (g.col_scale) c4 = cs4[k];
             v[4 * k] *= c4.x * rs;
             v[4 * k + 1] *= c4.y * rs;
             v[4 * k + 2] *= c4.z * rs;
@@ -1041,19 +1053,6 @@ static int launch_gemm_pair(const xfm_gemm_params* p, const GemmArgs& g, cudaStr
     if (!rc && p->residual) rc = encode_2d_f32(&map_aux, p->residual, p->N, p->M, p->ld_res);
     if (rc) return rc;
     g2.tma_epi = 2;
-    static const bool deep_on = getenv("XFM_GEMM_F32_DEEP") == nullptr || atoi(getenv("XFM_GEMM_F32_DEEP")) != 0;
-    if (deep_on && p->residual && g.kb_total <= 16) {   // short K: deep residual ring, 3 operand stages (PairCfg<3>)
-      auto kern3 = gemm_tcgen05_pair_kernel<A_MN, B_MN, 3>;
-      static bool attr3_set = false;
-      if (!attr3_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern3, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<3>::SMEM_BYTES);
-        if (e != cudaSuccess) return (int)e;
-        attr3_set = true;
-      }
-      kern3<<<2 * pairs, GEMM_THREADS, PairCfg<3>::SMEM_BYTES, stream>>>(map_a, map_b, map_c, map_aux, g2);
-      count_launch();
-      return (int)cudaGetLastError();
-    }
     auto kern32 = gemm_tcgen05_pair_kernel<A_MN, B_MN, 1>;
     static bool attr32_set = false;
     if (!attr32_set) {
