@@ -432,7 +432,7 @@ def run_ours(args):
     pk, pk_kind = peaks()
     peak = pk.get("bf16_tflops_sustained", 1400.0)
     ach = g_flops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
-    losses = {k: float(v) for k, v in last["out"].items() if k in ("loss_itc", "loss_itm", "loss_mlm", "loss_mim")}
+    losses = {k: float(v.detach()) for k, v in last["out"].items() if k in ("loss_itc", "loss_itm", "loss_mlm", "loss_mim")}
 
     pairs = B * world
     line = {

@@ -246,7 +246,13 @@ class B200DDPAccelerator:
     runs up to 5 backward passes per optimizer step, Pretrain.py:218-243) only the last backward of a step may reduce:
     "auto" learns the number of backward passes per optimizer step from the previous step.  If a backward pass does begin
     after ranges were reduced early, the reduced values are stashed and the ranges restart from zero, so the result stays
-    exact (one extra copy, only on a change of the accumulation pattern)."""
+    exact (one extra copy, only on a change of the accumulation pattern).
+
+    "auto" overlaps only on 2 ranks.  Measured on 8 x B200 (profiles/r02s_*): one exposed all-reduce of the 1.45 GB buffer
+    takes 3.5 ms at 4 and 8 ranks (NVLS, 730 GB/s bus bandwidth), while the overlapped mode costs MORE than it hides
+    (step 74.4 / 73.6 ms overlapped vs 72.3 ms exposed at 8 ranks; 73.4 vs 72.1 at 4): the GEMMs are persistent kernels with
+    a static tile schedule and one CTA pair per TPC, so every TPC an NCCL CTA occupies delays a whole CTA pair to a second
+    wave.  On 2 ranks (ring over one NVLink pair, 4.5 ms exposed) overlapping still wins (74.1 vs 75.5 ms)."""
 
     def __init__(self, cfg, logger=None):
         self.cfg = cfg if hasattr(cfg, "CLIP_GRAD_NORM") or not isinstance(cfg, dict) else _Cfg(cfg)
@@ -333,13 +339,16 @@ class B200DDPAccelerator:
     def _last_backward_expected(self):
         if self.overlap is True:
             return True
+        if self.world > 2:   # "auto": see the class docstring
+            return False
         return self._bw_per_step is not None and self._bw_seen >= self._bw_per_step
 
-    def _reduce_range(self, G, a, b):
+    def _reduce_range(self, G, a, b, buckets=None):
         n = b - a
         if n <= 0:
             return
-        per = (n + self.buckets - 1) // self.buckets
+        buckets = buckets or self.buckets
+        per = (n + buckets - 1) // buckets
         per = (per + 63) // 64 * 64
         for i in range(a, b, per):
             dist.all_reduce(G[i:min(b, i + per)], op=dist.ReduceOp.SUM)
@@ -390,7 +399,8 @@ class B200DDPAccelerator:
         for a, b in sorted(self._early):
             self._reduce_range(G, pos, a)
             pos = max(pos, b)
-        self._reduce_range(G, pos, self._train_end)
+        # nothing reduced early: ONE message (1.45 GB: 3.47 ms at 8 ranks; four 362 MB messages: 3.74 ms)
+        self._reduce_range(G, pos, self._train_end, buckets=1 if pos == 0 else None)
         self._early = []
         for a, b, t in self._stash:
             G[a:b].add_(t)
