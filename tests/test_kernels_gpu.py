@@ -233,6 +233,37 @@ def test_layernorm_bwd_dense_equals_the_three_pass_form(lib, M, p):
         assert abs(float((d16_1 != 0).float().mean()) - (1 - p)) < 0.01
 
 
+@pytest.mark.parametrize("dyd", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("with_add", [False, True])
+@pytest.mark.parametrize("dense", [False, True])
+def test_layernorm_bwd_specialised_instantiations(lib, dyd, with_add, dense):
+    """D = 768 with fp32 x / dx runs the dtype-specialised instantiations of layernorm_bwd_kernel (elementwise.cu, DT >= 0):
+    every one of them against torch autograd, ragged row count (the last CTA and the last warps have fewer rows)."""
+    if dense and with_add:
+        pytest.skip("the dense form has no add_in")
+    D, M = 768, 1237
+    g = G(31 + int(with_add) + 2 * int(dense))
+    x = torch.randn(M, D, generator=g) * 2 + 0.5
+    w, b = 1 + 0.1 * torch.randn(D, generator=g), 0.1 * torch.randn(D, generator=g)
+    dy = torch.randn(M, D, generator=g).to(dyd)
+    add = torch.randn(M, D, generator=g) if with_add else None
+    xr = x.clone().requires_grad_(True)
+    wr, br = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    F.layer_norm(xr, (D,), wr, br, 1e-5).backward(dy.float())
+    want = xr.grad + (add if with_add else 0)
+    _, stats, _ = lib.layernorm_fwd(x.cuda(), w.cuda(), b.cuda(), 1e-5)
+    dw, db = torch.zeros(D, device="cuda"), torch.zeros(D, device="cuda")
+    if dense:
+        dbias = torch.zeros(D, device="cuda")
+        dx, dx16 = lib.layernorm_bwd_dense(dy.cuda(), x.cuda(), stats, w.cuda(), dw, db, dbias)
+        assert torch.equal(dx16, dx.to(torch.bfloat16))
+        assert rel_err(dbias, dx16.float().sum(0)) < 1e-5
+    else:
+        dx = lib.layernorm_bwd(dy.cuda(), x.cuda(), stats, w.cuda(), dw, db, add_in=None if add is None else add.cuda())
+    assert rel_err(dx, want) < 1e-5
+    assert rel_err(dw, wr.grad) < 1e-5 and rel_err(db, br.grad) < 1e-5
+
+
 def test_layerscale_bwd_and_colsum(lib):
     g = G(9)
     M, D = 394, 768
