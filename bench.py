@@ -389,8 +389,8 @@ def run_ours(args):
                       "unit": UNIT, "what": "forward + backward + clip + AdamW + zero_grad replayed as one CUDA graph"}
     clk = clocks.stop() if clocks else None
 
-    # ---- roofline leg: one more step with CUDA events around every launch of the dominant kernel (the tcgen05 GEMM)
-    L.gemm_profile = []
+    # ---- fusion-layer leg: CUDA events around the 12 fusion layers (forward and backward of the 4B-sample pass) in three
+    # steps issued back to back (the launch queue stays full, so the bracket holds kernel time, not host time); minimum.
     fus_ev = []
 
     def timed_call(fn):
@@ -404,10 +404,20 @@ def run_ours(args):
         return wrapper
     fwd0, bwd0 = model._fus.layers_fwd, model._fus.layers_bwd
     model._fus.layers_fwd, model._fus.layers_bwd = timed_call(fwd0), timed_call(bwd0)
+    gc.collect()
+    gc.disable()
+    n_fus = 3
+    for i in range(n_fus):
+        step(resident[i % n_pool])
+    torch.cuda.synchronize()
+    gc.enable()
+    model._fus.layers_fwd, model._fus.layers_bwd = fwd0, bwd0
+    per = len(fus_ev) // n_fus
+    fus_ms = min(sum(a.elapsed_time(b) for a, b in fus_ev[i * per:(i + 1) * per]) for i in range(n_fus))
+    # ---- roofline leg: one more step with CUDA events around every launch of the dominant kernel (the tcgen05 GEMM)
+    L.gemm_profile = []
     step(resident[0])
     torch.cuda.synchronize()
-    model._fus.layers_fwd, model._fus.layers_bwd = fwd0, bwd0
-    fus_ms = sum(a.elapsed_time(b) for a, b in fus_ev)
     prof, L.gemm_profile = L.gemm_profile, None
     shapes = {}
     for p in prof:
