@@ -99,3 +99,15 @@ def test_host_construction_then_to_device_sequence_without_a_gpu():
     # learnable_temp False: temp is a python float and not a state_dict entry (xfm.py:505-507)
     frozen = XFM(dict(cfg, learnable_temp=False), init=lambda n, s: O.make_tensor(n, s, 0))
     assert isinstance(frozen.temp, float) and "temp" not in frozen.state_dict() and "temp" not in frozen.init_params
+
+
+def test_unbuilt_configurations_are_rejected_loudly():
+    """Layouts the reference supports but this package does not build must fail at construction, never run as something
+    else: local vision attention (beit2.py forward_localattn), CLIP / Swin vision encoders, text-side cross-attention."""
+    import pytest
+    from xfm_b200.config import normalize_config
+    base = dict(text_num_hidden_layers=2, fusion_num_hidden_layers=2)
+    normalize_config(dict(base, local_attn_depth=-1))
+    for bad in (dict(local_attn_depth=2), dict(use_beit_v2=False), dict(text_fusion_start_at=1), dict(fusion_fusion_start_at=1)):
+        with pytest.raises(NotImplementedError):
+            normalize_config(dict(base, **bad))

@@ -66,6 +66,9 @@ def normalize_config(config):
                                   "(text_fusion_start_at == text_num_hidden_layers)")
     if config.get("fusion_fusion_start_at", 0) != 0:
         raise NotImplementedError("xfm_b200 builds the shipped layout: cross-attention in every fusion layer")
+    if int(config.get("local_attn_depth", -1) or -1) > 0:
+        raise NotImplementedError("local_attn_depth > 0 (beit2.py forward_localattn) is not built: every shipped yaml sets -1, "
+                                  "region features come from the weighted average pool of beit2.py:468-475")
     if config.get("use_beit_v2", True) is not True:
         raise NotImplementedError("only the BEiT-v2 vision encoder (use_beit_v2: True) is built")
     if cfg["vision_width"] % 64 or cfg["hidden"] % 64 or cfg["vision_width"] // cfg["vision_heads"] != 64 or \
