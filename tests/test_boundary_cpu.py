@@ -111,3 +111,32 @@ def test_unbuilt_configurations_are_rejected_loudly():
     for bad in (dict(local_attn_depth=2), dict(use_beit_v2=False), dict(text_fusion_start_at=1), dict(fusion_fusion_start_at=1)):
         with pytest.raises(NotImplementedError):
             normalize_config(dict(base, **bad))
+
+
+def test_base_class_load_pretrained_resamples_for_a_larger_resolution(tmp_path):
+    """XFMBase.load_pretrained (xfm.py:542-557), the call Retrieval.py / NLVR.py make on a 224-px pre-training checkpoint with a
+    384-px model: here 64 px -> 96 px on the tiny layout.  Vision tables are resampled (beit2.py:753-808), every other weight
+    arrives unchanged, text keys of a bare-encoder checkpoint land on this module's layout."""
+    from oracle import xfm_oracle as O
+    from xfm_b200 import checkpoint as CK
+    from xfm_b200.model_pretrain import XFM
+    cfg = O.tiny_config(use_vision_tokenizer=False)
+    src = XFM(dict(cfg), init=lambda n, s: O.make_tensor(n, s, 3))
+    sd = {k: v.detach().clone() for k, v in src.state_dict().items()}
+    path = str(tmp_path / "pt.th")
+    torch.save({"model": sd}, path)
+    cfg2 = dict(cfg, image_res=96)
+    dst = XFM(dict(cfg2), init=lambda n, s: O.make_tensor(n, s, 5))
+    dst.load_pretrained(path, dict(cfg2, use_beit_v2=True, text_encoder="roberta-base"))
+    got = dst.state_dict()
+    tab = [k for k in sd if k.endswith("relative_position_bias_table")]
+    assert tab, "the tiny layout has relative-position tables"
+    for k, v in sd.items():
+        if k in tab:
+            assert got[k].shape != v.shape
+            want = CK.interpolate_rel_pos(v.cpu(), 2 * (96 // cfg["patch_size"]) - 1)
+            assert torch.allclose(got[k].cpu(), want, atol=1e-6), k
+        elif got[k].shape == v.shape:
+            assert torch.equal(got[k].cpu(), v.cpu()), k
+    assert torch.equal(got["text_encoder.roberta.encoder.layer.0.attention.self.query.weight"].cpu(),
+                       sd["text_encoder.roberta.encoder.layer.0.attention.self.query.weight"].cpu())

@@ -500,10 +500,14 @@ class XFMBase(nn.Module):
         return out
 
     def load_pretrained(self, ckpt_rpath, config, is_eval=False, is_domain_pretrain=False):
-        """xfm.py:542-557 for checkpoints already in this module's key layout (no position-bias interpolation)."""
-        ck = torch.load(ckpt_rpath, map_location="cpu")
-        sd = ck["model"] if "model" in ck else ck
-        sd = {k.replace("visual_encoder", "vision_encoder"): v for k, v in sd.items()}
+        """xfm.py:542-557: a domain-pre-training checkpoint is loaded as it is ('visual_encoder' keys renamed); anything else goes
+        through the module-level load_pretrained (vision tables resampled to this model's resolution, text keys renamed)."""
+        if is_domain_pretrain:
+            ck = torch.load(ckpt_rpath, map_location="cpu")
+            sd = ck["model"] if "model" in ck else ck
+            sd = {k.replace("visual_encoder", "vision_encoder"): v for k, v in sd.items()}
+        else:
+            sd = load_pretrained(self, ckpt_rpath, config, is_eval=is_eval, load_text=True)
         msg = self.load_state_dict(sd, strict=False)
         print("load checkpoint from %s" % ckpt_rpath)
         print("missing_keys: ", [p for p in msg.missing_keys if "vision_encoder" not in p])
