@@ -682,7 +682,7 @@ def _oracle_step_fn(B):
         loss.backward()
         torch.nn.utils.clip_grad_norm_(train, 1.0)
         optim.step()
-        return float(loss)
+        return float(loss.detach())
     return step
 
 

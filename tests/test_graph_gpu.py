@@ -45,7 +45,7 @@ def test_graphed_step_equals_eager_step():
         acc.backward_step(loss, opt)
         acc.optimizer_step(opt, wrapped)
         if i >= 3:
-            eager.append(float(loss))
+            eager.append(float(loss.detach()))
             sched.step()
     p_eager = model.flat.P.clone()
     # graphed

@@ -50,4 +50,4 @@ torch.cuda.profiler.start()
 loss = step()
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
-print("profiled step loss", float(loss))
+print("profiled step loss", float(loss.detach()))
