@@ -355,7 +355,7 @@ def run_ours(args):
         stage(i + 1)
         loss, _ = step(slots[s])
         consumed[s].record(torch.cuda.current_stream())
-        last["host_loss"] = float(loss)  # D2H read of the step's result
+        last["host_loss"] = float(loss.detach())  # D2H read of the step's result
 
     pairs_all = B * world
     ms_step, launches = timed(resident_step, "resident")
