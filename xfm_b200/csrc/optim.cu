@@ -40,7 +40,24 @@ sumsq_kernel(const float* __restrict__ g, const int32_t* __restrict__ chunk_seg,
   }
   float acc = 0.f;
   const size_t nvec = nchunks * 16;  // float4 per chunk = 16
-  for (size_t i = (size_t)blockIdx.x * OPT_THREADS + threadIdx.x; i < nvec; i += (size_t)gridDim.x * OPT_THREADS) {
+  const size_t stride = (size_t)gridDim.x * OPT_THREADS;
+  size_t i = (size_t)blockIdx.x * OPT_THREADS + threadIdx.x;
+  // four independent (segment lookup -> live test -> 16-byte load) chains in flight per thread: one chain per iteration
+  // left the kernel at 4.0 TB/s (0.62 of the copy rate)
+  for (; i + 3 * stride < nvec; i += 4 * stride) {
+    int seg[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) seg[k] = chunk_seg[(i + k * stride) >> 4];
+    bool live[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) live[k] = seg[k] >= 0 && seg_group[seg[k] < 0 ? 0 : seg[k]] != 255;
+    float4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = live[k] ? __ldg((const float4*)g + i + k * stride) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc += v[k].x * v[k].x + v[k].y * v[k].y + v[k].z * v[k].z + v[k].w * v[k].w;
+  }
+  for (; i < nvec; i += stride) {
     const int seg = chunk_seg[i >> 4];
     if (seg < 0 || seg_group[seg] == 255) continue;
     const float4 v = ((const float4*)g)[i];

@@ -127,6 +127,14 @@ class FlatParams:
             L.cast_to_bf16(self.P, self.S)
             self._shadow_version = v
 
+    def train_end(self):
+        """End (aligned) of the last trainable segment: nothing behind it (the frozen VQ-KD tokenizer, 437 MB) ever
+        receives a gradient, so zero_grad and the all-reduce stop there."""
+        if getattr(self, "_train_end_cache", None) is None or self._train_end_cache[0] != len(self.segments):
+            end = max([s.offset + (s.numel + ALIGN - 1) // ALIGN * ALIGN for s in self.segments.values() if s.trainable] or [0])
+            self._train_end_cache = (len(self.segments), end)
+        return self._train_end_cache[1]
+
     def zero_grad(self):
-        self.G.zero_()
+        self.G[:self.train_end()].zero_()
         self.touched.clear()
