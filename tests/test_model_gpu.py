@@ -73,13 +73,14 @@ def test_tiny_vq_activations_losses_against_reference(golden_dir):
         out = _run(model, g, batch)
     nv, nt, nf = cfg["vision_depth"], cfg["text_layers"], cfg["fusion_layers"]
     vis, txt, fus = model._vis.collect, model._txt.collect, model._fus.collect
-    # call order: vision | text (ONE 2B-sample pass: clean rows, then the masked copies) | fusion (4B pass: 3B ITM rows +
-    # B MLM rows) | vision(masked)
-    assert len(vis) == 2 * nv and len(txt) == nt and len(fus) == nf
+    # call order: vision (ONE 2B-sample pass: clean images, then their masked copies) | text (ONE 2B-sample pass: clean rows,
+    # then the masked copies) | fusion (4B pass: 3B ITM rows + B MLM rows)
+    assert len(vis) == nv and len(txt) == nt and len(fus) == nf
     B = g["B"]
     for i in range(nv):
-        assert _maxabs(vis[i], g["acts"]["vision"][i]) <= 2e-2, ("vision", i)
-        assert _maxabs(vis[nv + i], g["acts"]["vision_masked"][i]) <= 2e-2, ("vision_masked", i)
+        assert vis[i].shape[0] == 2 * B
+        assert _maxabs(vis[i][:B], g["acts"]["vision"][i]) <= 2e-2, ("vision", i)
+        assert _maxabs(vis[i][B:], g["acts"]["vision_masked"][i]) <= 2e-2, ("vision_masked", i)
     for i in range(nt):
         assert txt[i].shape[0] == 2 * B
         assert _maxabs(txt[i][:B], g["acts"]["text"][i]) <= 2e-2, ("text", i)
@@ -209,7 +210,7 @@ def test_base_config_against_reference(golden_dir, name):
         out = _run(model, g, batch)
     tok, nd, B = [0, 1, 7, -1], 16, g["B"]
     nv, nt, nf = cfg["vision_depth"], cfg["text_layers"], cfg["fusion_layers"]
-    groups = {"vision": model._vis.collect[:nv], "vision_masked": model._vis.collect[nv:],
+    groups = {"vision": [a[:B] for a in model._vis.collect[:nv]], "vision_masked": [a[B:] for a in model._vis.collect[:nv]],
               "text": [a[:B] for a in model._txt.collect[:nt]], "text_masked": [a[B:] for a in model._txt.collect[:nt]],
               "fusion_pos": [a[:B] for a in model._fus.collect[:nf]]}
     worst = 0.0

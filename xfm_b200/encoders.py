@@ -227,17 +227,28 @@ class VisionEncoder:
         gm, fp = self.gmap[i], self.fp
         return lambda k: fp.grad(gm[k])
 
-    def forward(self, image, mask_u8=None, train=False, save=True, pre_mul=None, pool=True):
+    def forward(self, image, mask_u8=None, train=False, save=True, pre_mul=None, pool=True, twin=False):
         """image f32 [B,3,R,R] -> (y32 [B,N,D] f32, y16 bf16 same shape, state).  pool=False (tokenizer) leaves
-        token 0 un-pooled."""
+        token 0 un-pooled.
+        twin=True: the clean images AND their masked copies (mask_u8) run as ONE pass of 2B samples — rows [0, B) clean,
+        [B, 2B) masked; the patch embedding is computed once.  Every GEMM / attention / LayerNorm launch of the encoder then
+        serves both copies (the pre-training step encodes every image both ways, model_pretrain.py:43,73)."""
         if self.w is None:
             self.refresh()
-        B = image.shape[0]
+        B0 = image.shape[0]
         N, D, npatch = self.N, self.D, self.np
         image = image.contiguous()
         cols = L.im2col(_f32(image), self.P, pre_mul)
         patch = L.gemm(cols, self.pe_w16, bias=self.pe_b, out_dtype=torch.float32)
-        x = L.assemble_tokens(patch, self.cls, self.mask_token, mask_u8, self.pos, B, npatch)
+        if twin:
+            assert mask_u8 is not None
+            B = 2 * B0
+            x = torch.empty((B * N, D), dtype=torch.float32, device=patch.device)
+            L.assemble_tokens(patch, self.cls, self.mask_token, None, self.pos, B0, npatch, out=x[:B0 * N])
+            L.assemble_tokens(patch, self.cls, self.mask_token, mask_u8, self.pos, B0, npatch, out=x[B0 * N:])
+        else:
+            B = B0
+            x = L.assemble_tokens(patch, self.cls, self.mask_token, mask_u8, self.pos, B, npatch)
         st = State()
         st.blocks = []
         ds_all = None
@@ -262,7 +273,7 @@ class VisionEncoder:
         if pool:
             L.meanpool_fwd_(y16, y32, B, npatch)
         if save:
-            st.cols, st.mask, st.x_final, st.stats, st.B = cols, mask_u8, x, stats, B
+            st.cols, st.mask, st.x_final, st.stats, st.B, st.twin = cols, mask_u8, x, stats, B, twin
         return y32.view(B, N, D), y16.view(B, N, D), (st if save else None)
 
     def backward(self, st, dy32, block_done=None):
@@ -277,9 +288,16 @@ class VisionEncoder:
             if block_done is not None:
                 block_done(i)
         dmask = fp.grad(p + "mask_token") if st.mask is not None else None
-        dpatch = L.assemble_tokens_bwd(dx, st.mask, fp.grad(p + "cls_token"), dmask, B, npatch)
-        L.colsum_into(dpatch, fp.grad(p + "patch_embed.proj.bias"))
-        BK.wgrad(fp.grad(p + "patch_embed.proj.weight").view(D, -1), dpatch, st.cols)
+        if getattr(st, "twin", False):   # both copies read the same patch embedding: two accumulating wgrads, like two passes
+            B0 = B // 2
+            halves = ((dx[:B0 * N], None, None), (dx[B0 * N:], st.mask, dmask))
+        else:
+            B0 = B
+            halves = ((dx, st.mask, dmask),)
+        for dxh, mask, dm in halves:
+            dpatch = L.assemble_tokens_bwd(dxh, mask, fp.grad(p + "cls_token"), dm, B0, npatch)
+            L.colsum_into(dpatch, fp.grad(p + "patch_embed.proj.bias"))
+            BK.wgrad(fp.grad(p + "patch_embed.proj.weight").view(D, -1), dpatch, st.cols)
 
 
 # =====================================================================================================

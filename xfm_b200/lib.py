@@ -404,9 +404,10 @@ def im2col(image, P, pre_mul=None):
     return out
 
 
-def assemble_tokens(patch, cls, mask_token, mask_u8, pos, B, npatch):
+def assemble_tokens(patch, cls, mask_token, mask_u8, pos, B, npatch, out=None):
     D = patch.shape[1]
-    x = torch.empty((B * (npatch + 1), D), dtype=torch.float32, device=patch.device)
+    x = out if out is not None else torch.empty((B * (npatch + 1), D), dtype=torch.float32, device=patch.device)
+    assert x.shape == (B * (npatch + 1), D) and x.dtype == torch.float32 and x.is_contiguous()
     check(lib().xfm_assemble_tokens(_p(patch), _p(cls), _p(mask_token), _p(mask_u8), _p(pos), _p(x), B, npatch, D,
                                     stream_ptr()), "xfm_assemble_tokens")
     return x

@@ -6,6 +6,8 @@ the package is usable where the reference tree is absent (the GPU box, bench.py,
 The region / bbox branch (ret_bbox_loss, ret_bbox_giou: idx_to_group_img gather, region-weighted pooling, L1 + GIoU box
 losses) follows model_pretrain.py:39-41,81-86.
 """
+import os
+
 import torch
 
 from .xfm import XFMBase
@@ -22,6 +24,8 @@ class XFM(XFMBase):
         self.do_image_mask = config.get("do_image_mask", True)
         self.use_mm_mim_loss = config.get("use_mm_mim_loss", True)
         self.fuse_itm_mlm = config.get("fuse_itm_mlm", True)  # xfm_b200 only: ITM + MLM in one fusion-encoder pass
+        # xfm_b200 only: clean + masked images in one 2B-sample vision pass (XFM_TWIN_VISION=0: A/B measurements)
+        self.twin_vision_pass = bool(config.get("twin_vision_pass", os.environ.get("XFM_TWIN_VISION", "1") != "0"))
         self.min_temp = config.get("min_temp", 0.001)
         self.max_temp = config.get("max_temp", 0.5)
 
@@ -37,7 +41,9 @@ class XFM(XFMBase):
             image_embeds, image_atts, image_embeds_fullatts = \
                 self.get_vision_embeds(image, image_atts=image_atts, idx_to_group_img=idx_to_group_img)
         else:
-            image_embeds, image_atts = self.get_vision_embeds(image)
+            # the masked copy of the same images is asked for below (MIM): both copies run as one 2B-sample encoder pass
+            image_embeds, image_atts = self.get_vision_embeds(
+                image, _also_masked=bool(ret_mim_loss and self.do_image_mask and self.twin_vision_pass))
         zero = torch.tensor(0.0)
         loss_itc = loss_itm = loss_mlm = loss_mim = loss_bbox = loss_giou = zero
         if data_source != "imagenet":

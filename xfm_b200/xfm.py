@@ -564,6 +564,7 @@ class XFMBase(nn.Module):
         return BK.DropCfg(self.cfg["hidden_dropout"], self.cfg["attn_dropout"], self._seed * 131 + self._drop_calls)
 
     _pending_nodes = 0
+    _masked_vision = None   # (image, (embeds, atts, mask)) of a twin vision pass, for the do_mask call that follows
     _last_node_hook = None
     _backward_begin_hook = None
 
@@ -576,18 +577,27 @@ class XFMBase(nn.Module):
         return impl.fwd(None, *tensors)
 
     # ------------------------------------------------------------------ vision
-    def get_vision_embeds(self, image, image_atts=None, idx_to_group_img=None, do_mask=False):
+    def get_vision_embeds(self, image, image_atts=None, idx_to_group_img=None, do_mask=False, _also_masked=False):
         """xfm.py:560-597.  With idx_to_group_img (region data: fewer images than samples) the encoded images are gathered per
         sample; with image_atts as well, token 0 becomes the region-weighted mean of the sample's patch tokens
-        (beit2.py:468-475) and the full-image embeddings are returned as a third value."""
+        (beit2.py:468-475) and the full-image embeddings are returned as a third value.
+        _also_masked (xfm_b200 only): the caller will ask for the masked copy of the SAME images next
+        (get_vision_embeds(image, do_mask=True), model_pretrain.py:73).  Both copies then run as one 2B-sample pass of the
+        encoder (VisionEncoder.forward twin=True); the masked half is kept for that next call.  Masks come from the same
+        sampler calls in the same order, so they are the ones the separate pass would have drawn."""
         if idx_to_group_img is not None:
             return self._region_vision_embeds(image, image_atts, idx_to_group_img)
+        kept = self._masked_vision
+        self._masked_vision = None
+        if do_mask and kept is not None and kept[0] is image:
+            return kept[1]
         self._prep()
         B = image.shape[0]
         mask_dev = None
-        if do_mask and self._static_masks is not None:   # CUDA-graph mode: device buffers refilled between replays
+        want_mask = do_mask or _also_masked
+        if want_mask and self._static_masks is not None:   # CUDA-graph mode: device buffers refilled between replays
             mask_dev, rows = self._static_masks
-        elif do_mask:
+        elif want_mask:
             if self._forced_masks is not None:
                 m = self._forced_masks.cpu()
                 rows = torch.from_numpy(__import__("numpy").flatnonzero(m.numpy()).astype("int64"))
@@ -597,30 +607,48 @@ class XFMBase(nn.Module):
             mask_dev = m.pin_memory().to(image.device, non_blocking=True)
             rows = rows.pin_memory().to(image.device, non_blocking=True)
         model = self
+        twin = bool(_also_masked) and not do_mask
 
         class Impl:
             def fwd(self, ctx, image):
                 mu8 = mask_dev.to(torch.uint8) if mask_dev is not None else None
-                y32, y16, st = model._vis.forward(image, mask_u8=mu8, train=model.training, save=self.save)
+                y32, y16, st = model._vis.forward(image, mask_u8=mu8, train=model.training, save=self.save, twin=twin)
                 self.y16 = y16
                 if ctx is not None:
                     ctx.st = st
+                if twin:
+                    return y32[:B], y32[B:]
                 return y32
 
-            def bwd(self, ctx, dy):
+            def bwd(self, ctx, *grads):
+                if twin:   # one backward pass over both copies, once both gradients are there
+                    z = [g if g is not None else torch.zeros((B,) + tuple(self.y16.shape[1:]), dtype=torch.float32,
+                                                             device=self.y16.device) for g in grads]
+                    dy = torch.cat([z[0].float(), z[1].float()])
+                else:
+                    dy = grads[0]
                 model._vis.backward(ctx.st, dy, block_done=getattr(self, "block_done", None))
                 ctx.st = None
                 return (None,)
         impl = Impl()
         impl.kind = "vision"
         y = self._call(impl, image)
+
+        def atts_of(t):
+            a = torch.ones(t.shape[:-1], dtype=torch.long, device=image.device)
+            a._xfm_all_ones = True   # lets the cross-attention skip the encoder mask (and stay on the tcgen05 kernel)
+            return a
+        if twin:
+            y, ym = y
+            y._xfm16, ym._xfm16 = impl.y16[:B], impl.y16[B:]
+            mask_dev._xfm_rows = rows
+            self._masked_vision = (image, (ym, atts_of(ym), mask_dev))
+            return y, atts_of(y)
         y._xfm16 = impl.y16
-        atts = torch.ones(y.shape[:-1], dtype=torch.long, device=image.device)
-        atts._xfm_all_ones = True   # lets the cross-attention skip the encoder mask (and stay on the tcgen05 kernel)
         if do_mask:
             mask_dev._xfm_rows = rows
-            return y, atts, mask_dev
-        return y, atts
+            return y, atts_of(y), mask_dev
+        return y, atts_of(y)
 
     def _region_vision_embeds(self, image, image_atts, idx_to_group_img):
         """xfm.py:574-597 + beit2.py:468-475."""
