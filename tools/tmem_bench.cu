@@ -1,0 +1,144 @@
+// Micro-benchmark: tcgen05.ld / tcgen05.st throughput and latency per SM as a function of the number of reading warps.
+// Answers one question for the attention kernels: how many cycles does a thread=row softmax pass over a 128 x N fp32
+// score tile in TMEM cost at the very least?   build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17
+// -I xfm_b200/csrc tools/tmem_bench.cu -o gpurun_out/tmem_bench      (standalone: no torch, no library)
+#include <cstdio>
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include "common.cuh"
+
+using namespace xfm;
+
+__device__ __forceinline__ void ld16(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+      "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+      "r"(r[31])
+      : "memory");
+}
+
+// mode 0: ld.x32 ; wait            (one load in flight per warp)
+// mode 1: ld.x32 ; ld.x32 ; wait   (two in flight)
+// mode 2: st.x32 ; wait::st
+// mode 3: ld.x32 ; wait ; 32 ex2 + 32 fma + 32 max  (the softmax pass-1/2 instruction mix, no stores)
+// mode 4: ld.x16 ; wait
+// mode 5: like 3 but the NEXT chunk's load is issued before the arithmetic of the current one (software pipeline)
+template <int MODE>
+__global__ void __launch_bounds__(1024, 1) tmem_kernel(int iters, long long* cycles, float* sink) {
+  __shared__ uint32_t tmem_ptr;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    tmem_alloc(&tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t base = tmem_ptr + ((uint32_t)((warp & 3) * 32) << 16);
+  uint32_t v[32], w[32];
+#pragma unroll
+  for (int e = 0; e < 32; ++e) v[e] = w[e] = 0x3f800000u + e;
+  float acc = 0.f, mx = -1e30f;
+  __syncthreads();
+  const long long t0 = clock64();
+  if (MODE == 5) { tmem_ld_32x32(base, v); }
+  for (int i = 0; i < iters; ++i) {
+    const uint32_t col = (uint32_t)((i * 32 + (warp >> 2) * 64) & 448);
+    if (MODE == 0) {
+      tmem_ld_32x32(base + col, v);
+      tmem_ld_wait();
+      acc += __uint_as_float(v[i & 31]);
+    } else if (MODE == 1) {
+      tmem_ld_32x32(base + col, v);
+      tmem_ld_32x32(base + ((col + 32) & 448), w);
+      tmem_ld_wait();
+      acc += __uint_as_float(v[i & 31]) + __uint_as_float(w[i & 31]);
+    } else if (MODE == 2) {
+      v[0] = i;
+      st32(base + col, v);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    } else if (MODE == 3) {
+      tmem_ld_32x32(base + col, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const float l = fmaf(__uint_as_float(v[e]), 0.18f, 0.01f * e);
+        mx = fmaxf(mx, l);
+        acc += ex2_approx(l - 3.0f);
+      }
+    } else if (MODE == 4) {
+      ld16(base + col, v);
+      tmem_ld_wait();
+      acc += __uint_as_float(v[i & 15]);
+    } else if (MODE == 5) {
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) w[e] = v[e];
+      tmem_ld_32x32(base + ((col + 32) & 448), v);
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const float l = fmaf(__uint_as_float(w[e]), 0.18f, 0.01f * e);
+        mx = fmaxf(mx, l);
+        acc += ex2_approx(l - 3.0f);
+      }
+    }
+  }
+  if (MODE == 5) tmem_ld_wait();
+  const long long t1 = clock64();
+  if ((threadIdx.x & 31) == 0) atomicMax((unsigned long long*)&cycles[blockIdx.x], (unsigned long long)(t1 - t0));
+  if (acc == 123.456f || mx == 77.f) sink[threadIdx.x] = acc + mx;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_ptr, 512);
+  }
+}
+
+template <int MODE>
+static void run(const char* name, int warps, int iters, int bytes_per_iter) {
+  long long* d;
+  float* sink;
+  cudaMalloc(&d, 148 * sizeof(long long));
+  cudaMalloc(&sink, 4096);
+  long long h[148];
+  for (int rep = 0; rep < 2; ++rep) {
+    cudaMemset(d, 0, 148 * sizeof(long long));
+    tmem_kernel<MODE><<<148, warps * 32>>>(iters, d, sink);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("{\"mode\": \"%s\", \"error\": \"%s\"}\n", name, cudaGetErrorString(e)); return; }
+  }
+  cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+  long long mx = 0;
+  for (int i = 0; i < 148; ++i) mx = h[i] > mx ? h[i] : mx;
+  const double per_iter = (double)mx / iters;
+  printf("{\"mode\": \"%s\", \"warps\": %d, \"cycles_per_iter_per_warp\": %.1f, \"tmem_bytes_per_clk_per_sm\": %.1f}\n", name, warps,
+         per_iter, (double)warps * bytes_per_iter / per_iter);
+  cudaFree(d);
+  cudaFree(sink);
+}
+
+int main() {
+  const int iters = 4096;
+  for (int w : {1, 4, 8, 16, 32}) run<0>("ld.x32+wait", w, iters, 4096);
+  for (int w : {4, 8, 16}) run<1>("2x ld.x32+wait", w, iters, 8192);
+  for (int w : {4, 8, 16}) run<4>("ld.x16+wait", w, iters, 2048);
+  for (int w : {4, 8, 16}) run<2>("st.x32+wait", w, iters, 4096);
+  for (int w : {4, 8, 16}) run<3>("ld.x32+wait+softmax-mix", w, iters, 4096);
+  for (int w : {4, 8, 16}) run<5>("pipelined ld.x32 + softmax-mix", w, iters, 4096);
+  return 0;
+}

@@ -16,6 +16,8 @@
 // beit2.py:104-114's index: with the window side W a template constant the column part of the index is an immediate,
 // so the gather is one LDS per score and the [H, N, N] bias tensor is never read.
 // Scores, probabilities and the bias tensor never touch HBM.
+#include <cstdio>
+#include <cstdlib>
 #include "common.cuh"
 #include "internal.h"
 
@@ -32,6 +34,7 @@ struct VitAttnArgs {
   int B, H;
   float scale;
   int items_per_cta;
+  long long* prof;       // XFM_ATTN_PROF=1: per-phase clock64 totals of CTA 0's first softmax warp (null otherwise)
 };
 
 template <int W>
@@ -199,6 +202,8 @@ vit_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     const int sw = r & 7;
     int cur_h = -1;
     float bias_c0 = 0.f;
+    long long pc[6] = {0, 0, 0, 0, 0, 0}, pt = clock64();
+    auto tick = [&](int i) { if (a.prof) { const long long n = clock64(); pc[i] += n - pt; pt = n; } };
     for (int tau = wg; tau < n_tiles; tau += 2) {
       const int item = item0 + tau / NT, t = tau % NT;
       const int h = item / a.B, b = item % a.B;
@@ -223,15 +228,20 @@ vit_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         rb = tab + Cfg::OFFMAX;
       }
       bias_c0 = tab[Cfg::OFFMAX + 1 + (qc >= 1 ? Cfg::T - 2 : Cfg::T - 1)];
+      tick(0);
       mbar_wait(&s_full[wg], (uint32_t)(tau >> 1) & 1u);
       tc_fence_after();
+      tick(1);
+      // a warp whose 32 rows all lie beyond the sample's last query (rows 224..255 of the second tile at L = 197) has nothing
+      // to compute: its P rows only feed output rows that are never stored.  It still takes part in every barrier.
+      const bool warp_live = t * 128 + quad * 32 < L;
+      float m = 0.f, sum = 1.f;
+      if (warp_live) {
       // ---- pass 1: logits (log2 domain) back into TMEM, row maximum
       float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
       for (int c0 = 0; c0 < LPAD; c0 += 32) {
         uint32_t v[32];
-        constexpr int dummy = 0;
-        (void)dummy;
         const bool full = c0 + 32 <= LPAD;
         if (full) tmem_ld_32x32(t_s + c0, v);
         else tmem_ld_32x32_16(t_s + c0, v);
@@ -251,8 +261,9 @@ vit_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         if (full) tmem_st_32x32(t_s + c0, v);
         else tmem_st_32x32_16(t_s + c0, v);
       }
-      const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+      m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
       tmem_st_wait();
+      tick(2);
       // ---- pass 2: p = 2^(l - m), row sum, bf16 P -> shared memory (K-major, SWIZZLE_128B)
       float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -281,24 +292,31 @@ vit_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
           }
         }
       }
-      const float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+      sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+      }
       fence_proxy_async();  // generic-proxy writes of P -> visible to the tensor core's async-proxy reads
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[wg]);
+      tick(3);
       // ---- epilogue: O / rowsum -> global, lse
       mbar_wait(&o_full[wg], (uint32_t)(tau >> 1) & 1u);
       tc_fence_after();
+      tick(4);
       uint32_t o[2][32];
-      tmem_ld_32x32(t_o, o[0]);
-      tmem_ld_32x32(t_o + 32, o[1]);
-      tmem_ld_wait();
+      if (warp_live) {
+        tmem_ld_32x32(t_o, o[0]);
+        tmem_ld_32x32(t_o + 32, o[1]);
+        tmem_ld_wait();
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(o_empty);  // the O accumulator is free for the next tile while we store
-      if (qi < L) {
+      if (warp_live) {
+        // thread = row would store 16-byte pieces of 32 different rows per instruction.  The row goes through this thread's
+        // own (now consumed: o_full) P row of key block 0 instead — same swizzle — and is read back four whole 128-byte rows
+        // per instruction, so every global store instruction writes complete lines.
         const float inv = 1.0f / sum;
-        bf16* orow = a.out + ((int64_t)b * L + qi) * a.o_stride + h * TC_HD;
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh)
 #pragma unroll
@@ -309,11 +327,24 @@ vit_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(o[hh][e + 4]) * inv, __uint_as_float(o[hh][e + 5]) * inv);
             __nv_bfloat162 t3 = __floats2bfloat162_rn(__uint_as_float(o[hh][e + 6]) * inv, __uint_as_float(o[hh][e + 7]) * inv);
             u.x = *(uint32_t*)&t0; u.y = *(uint32_t*)&t1; u.z = *(uint32_t*)&t2; u.w = *(uint32_t*)&t3;
-            *(uint4*)(orow + hh * 32 + e) = u;
+            *(uint4*)(myP + (((hh * 4 + (e >> 3)) ^ sw) << 4)) = u;
           }
-        if (a.lse) a.lse[((int64_t)b * a.H + h) * L + qi] = (m + log2f(sum)) * 0.6931471805599453f;
+        if (qi < L && a.lse) a.lse[((int64_t)b * a.H + h) * L + qi] = (m + log2f(sum)) * 0.6931471805599453f;
+        __syncwarp();
+        const int ch = lane & 7;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int r2 = quad * 32 + it * 4 + (lane >> 3);
+          const int q2 = t * 128 + r2;
+          const uint4 u = *(const uint4*)(sP + wg * Cfg::P_BYTES + (r2 >> 3) * 1024 + (r2 & 7) * 128 + ((ch ^ (r2 & 7)) << 4));
+          if (q2 < L) *(uint4*)(a.out + ((int64_t)b * L + q2) * a.o_stride + h * TC_HD + ch * 8) = u;
+        }
+        __syncwarp();  // the staging rows are overwritten by the next tile's probabilities
       }
+      tick(5);
     }
+    if (a.prof && blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 9))
+      for (int i = 0; i < 6; ++i) a.prof[(warp == 2 ? 0 : 6) + i] = pc[i];
   }
   tc_fence_before();
   __syncthreads();
@@ -345,6 +376,7 @@ struct VitBwdArgs {
   int B, H;
   float scale;
   int items_per_cta;
+  long long* prof;       // XFM_ATTN_PROF=1 (fused kernel): per-phase clock64 totals of CTA 0, warps 2 and 9
 };
 
 template <int W>
@@ -880,6 +912,8 @@ template <int W>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 vit_attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
                              const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
+                             const __grid_constant__ CUtensorMap map_dq, const __grid_constant__ CUtensorMap map_dk,
+                             const __grid_constant__ CUtensorMap map_dv, const __grid_constant__ CUtensorMap map_ds,
                              const VitBwdArgs a) {
   using Cfg = VitFusedCfg<W>;
   constexpr int L = Cfg::L, LPAD = Cfg::LPAD, NT = Cfg::NT, SPLIT = Cfg::SPLIT, NM = Cfg::NM;
@@ -903,6 +937,10 @@ vit_attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __
     tma_prefetch_desc(&map_do);
     tma_prefetch_desc(&map_k);
     tma_prefetch_desc(&map_v);
+    tma_prefetch_desc(&map_dq);
+    tma_prefetch_desc(&map_dk);
+    tma_prefetch_desc(&map_dv);
+    if (a.ds_dump) tma_prefetch_desc(&map_ds);
     mbar_init(kv_full, 1);
     mbar_init(kv_empty, 1);
     mbar_init(qdo_full, 1);
@@ -1002,7 +1040,10 @@ vit_attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __
     uint8_t* myP = sP + (r >> 3) * 1024 + (r & 7) * 128;
     const int sw = r & 7;
     constexpr int C_END0 = SPLIT, C_END1 = LPAD;
+    const bool elected = threadIdx.x == 64;   // issues every TMA store of this CTA (bulk groups are per thread)
     int cur_h = -1;
+    long long pc[5] = {0, 0, 0, 0, 0}, pt = clock64();
+    auto tick = [&](int i) { if (a.prof) { const long long n = clock64(); pc[i] += n - pt; pt = n; } };
     for (int tau = 0; tau < n_tiles; ++tau) {
       const int item = item0 + tau / NT, t = tau % NT;
       const int h = item / a.B, b = item % a.B;
@@ -1028,8 +1069,13 @@ vit_attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __
       const int64_t st_row = ((int64_t)b * a.H + h) * L + qc;
       const float lse2 = __ldg(a.lse + st_row) * 1.4426950408889634f;
       const float dl = __ldg(a.delta + st_row);
+      tick(0);
       mbar_wait(sd_full, par);
       tc_fence_after();
+      // the previous tile's output / dS stores still read the P / dS buffers this tile is about to overwrite
+      if (elected) tma_store_wait_read<0>();
+      named_bar_sync(1, 256);
+      tick(1);
       const int cb = wg == 0 ? 0 : C_END0, ce = wg == 0 ? C_END0 : C_END1;
 #pragma unroll
       for (int cc = 0; cc < LPAD; cc += 32) {
@@ -1081,70 +1127,99 @@ vit_attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __
           }
           st_bf16x8(myS + off8, ds);
           st_bf16x8(myP + off8, pp);
-          if (a.ds_dump && row_ok && col8 < a.ds_ld)
-            st_bf16x8((uint8_t*)(a.ds_dump + (st_row * a.ds_ld + col8)), ds);
         }
       }
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(ds_full);
-      // ---- outputs: 32-column units [dQ | dK tiles | dV tiles]; warpgroup 0 drains the first half, warpgroup 1 the rest
+      tick(2);
+      // ---- outputs: 32-column units [dQ | dK tiles | dV tiles], half of them per warpgroup.  thread = row would write (and,
+      // for the second query tile, read-modify-write) 16-byte pieces of 32 different rows per instruction: 45 % of this
+      // kernel's time.  Instead every 64-column output block is staged as bf16 in a SWIZZLE_128B [128 x 64] tile — the dK /
+      // dV blocks in the consumed P buffer, dQ in block 0 of the consumed dS buffer — and one thread issues TMA stores
+      // through 3D maps [sample, row, column] that clip at the sample's last row; the second query tile's dK / dV go out as
+      // TMA reduce-adds onto the first tile's.  dS itself (the table gradient's input) is stored by TMA from the dS operand
+      // buffer it already sits in.
       mbar_wait(out_full, par);
       tc_fence_after();
+      tick(3);
+      if (elected) {
+        if (a.ds_dump) {
+          const int nkb = (int)((a.ds_ld < LPAD ? a.ds_ld : LPAD) + 63) >> 6;
+          for (int kb = 0; kb < nkb; ++kb) tma_store_3d(&map_ds, sdS + kb * 16384, kb * 64, t * 128, b * a.H + h);
+        }
+        tma_store_commit();                      // (possibly empty) group: keeps the group count per tile fixed
+      }
       constexpr int UH = Cfg::UNITS / 2;
+      constexpr int DQ_ROUND = (UH - 2) & ~1;   // warpgroup 0 drains its dK units first and dQ (units 0, 1) last
+      auto unit_of = [&](int i) { return wg == 0 ? (i < UH - 2 ? i + 2 : i - (UH - 2)) : UH + i; };
 #pragma unroll
       for (int i0 = 0; i0 < UH; i0 += 2) {      // two units (64 registers) at a time
         uint32_t o[2][32];
-        tmem_ld_32x32(lane_base + (uint32_t)((wg * UH + i0) * 32), o[0]);
-        if (i0 + 1 < UH) tmem_ld_32x32(lane_base + (uint32_t)((wg * UH + i0 + 1) * 32), o[1]);
+        tmem_ld_32x32(lane_base + (uint32_t)(unit_of(i0) * 32), o[0]);
+        if (i0 + 1 < UH) tmem_ld_32x32(lane_base + (uint32_t)(unit_of(i0 + 1) * 32), o[1]);
         tmem_ld_wait();
         if (i0 + 2 >= UH) {                      // last read of this tile's outputs: TMEM may be overwritten
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(out_empty);
         }
+        if (wg == 0 && i0 == DQ_ROUND) {         // dQ is staged where dS lies: its TMA store must have read the buffer
+          if (elected) tma_store_wait_read<0>();
+          named_bar_sync(2, 128);
+        }
 #pragma unroll
         for (int ii = 0; ii < 2; ++ii) {
           if (i0 + ii >= UH) continue;
-          const int u = wg * UH + i0 + ii;      // unit -> (tensor, key tile, column half)
-          bf16* dst = nullptr;
+          const int u = unit_of(i0 + ii);       // unit -> (tensor, key tile, column half)
+          uint8_t* blk;
           float mul = a.scale;
-          bool add = false;
+          int half = u & 1;
           if (u < 2) {
-            if (row_ok) dst = a.dq + ((int64_t)b * L + qi) * a.dq_stride + h * TC_HD + u * 32;
+            blk = sdS;
           } else {
             const bool is_dv = u >= 2 + 2 * NM;
             const int uu = is_dv ? u - 2 - 2 * NM : u - 2;
-            const int key = (uu >> 1) * 128 + r;
-            if (key < L)
-              dst = (is_dv ? a.dv + ((int64_t)b * L + key) * a.dv_stride : a.dk + ((int64_t)b * L + key) * a.dk_stride) +
-                    h * TC_HD + (uu & 1) * 32;
+            blk = sP + ((is_dv ? NM : 0) + (uu >> 1)) * 16384;
+            half = uu & 1;
             if (is_dv) mul = 1.0f;
-            add = t > 0;
           }
-          if (dst) {
+          uint8_t* row = blk + (r >> 3) * 1024 + (r & 7) * 128;
 #pragma unroll
-            for (int e = 0; e < 32; e += 8) {
-              float v[8];
+          for (int e = 0; e < 32; e += 8) {
+            float v[8];
 #pragma unroll
-              for (int k = 0; k < 8; ++k) v[k] = __uint_as_float(o[ii][e + k]) * mul;
-              if (add) {
-                const uint4 prev = *(const uint4*)(dst + e);
-                const __nv_bfloat162* p2 = (const __nv_bfloat162*)&prev;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const float2 f = __bfloat1622float2(p2[k]);
-                  v[2 * k] += f.x;
-                  v[2 * k + 1] += f.y;
-                }
-              }
-              st_bf16x8((uint8_t*)(dst + e), v);
-            }
+            for (int k = 0; k < 8; ++k) v[k] = __uint_as_float(o[ii][e + k]) * mul;
+            st_bf16x8(row + (((half * 4 + (e >> 3)) ^ sw) << 4), v);
           }
         }
       }
+      fence_proxy_async();
+      named_bar_sync(1, 256);
+      if (elected) {
+        tma_store_3d(&map_dq, sdS, h * TC_HD, t * 128, b);
+        if (t == 0) {
+#pragma unroll
+          for (int m = 0; m < NM; ++m) {
+            tma_store_3d(&map_dk, sP + m * 16384, h * TC_HD, m * 128, b);
+            tma_store_3d(&map_dv, sP + (NM + m) * 16384, h * TC_HD, m * 128, b);
+          }
+        } else {
+          tma_store_wait_all<1>();               // the first tile's dK / dV stores have landed (only this tile's dS may be pending)
+#pragma unroll
+          for (int m = 0; m < NM; ++m) {
+            tma_reduce_add_3d(&map_dk, sP + m * 16384, h * TC_HD, m * 128, b);
+            tma_reduce_add_3d(&map_dv, sP + (NM + m) * 16384, h * TC_HD, m * 128, b);
+          }
+        }
+        tma_store_commit();
+      }
+      tick(4);
     }
+    if (a.prof && blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 9))
+      for (int i = 0; i < 5; ++i) a.prof[(warp == 2 ? 0 : 6) + i] = pc[i];
+    if (elected) tma_store_wait_all<0>();        // shared memory must outlive the reads; results complete before exit
   }
   tc_fence_before();
   __syncthreads();
@@ -1167,6 +1242,25 @@ static int encode_rows(CUtensorMap* map, const void* base, uint64_t cols, uint64
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("vit attention: cuTensorMapEncodeTiled failed: %d", (int)r);
+    return XFM_ERR_BAD_ARG;
+  }
+  return 0;
+}
+
+// [sample, row, 64-column block] view of a bf16 activation: boxes of 128 rows are clipped at the sample's last row
+static int encode_rows_3d(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows_per_sample, uint64_t samples,
+                          uint64_t ld_elems) {
+  auto fn = get_tensor_map_encoder();
+  if (!fn) return XFM_ERR_NO_DRIVER;
+  cuuint64_t dims[3] = {cols, rows_per_sample, samples};
+  cuuint64_t strides[2] = {ld_elems * 2, rows_per_sample * ld_elems * 2};
+  cuuint32_t box[3] = {TC_HD, 128, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("vit attention: cuTensorMapEncodeTiled (3D store map) failed: %d", (int)r);
     return XFM_ERR_BAD_ARG;
   }
   return 0;
@@ -1210,8 +1304,23 @@ static int launch_vit_fwd(const xfm_attn_params* p, cudaStream_t s) {
   const int ctas = n_items < num_sms() ? n_items : num_sms();
   a.items_per_cta = (n_items + ctas - 1) / ctas;
   const int grid = (n_items + a.items_per_cta - 1) / a.items_per_cta;
+  static const bool prof_on = getenv("XFM_ATTN_PROF") != nullptr;
+  static long long* prof_buf = nullptr;
+  a.prof = nullptr;
+  if (prof_on) {
+    if (!prof_buf) cudaMalloc(&prof_buf, 12 * sizeof(long long));
+    a.prof = prof_buf;
+  }
   vit_attn_fwd_tc_kernel<W><<<grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(mq, mk, mv, a);
   count_launch();
+  if (prof_on) {  // debugging aid: synchronous, prints the phase totals of CTA 0 (warp 2 = parity-0 rows 0..31, warp 9 = parity-1 rows 96..127)
+    long long h[12];
+    cudaStreamSynchronize(s);
+    cudaMemcpy(h, prof_buf, sizeof(h), cudaMemcpyDeviceToHost);
+    for (int w = 0; w < 2; ++w)
+      fprintf(stderr, "vit_attn_fwd prof %s: setup %lld wait_s %lld pass1 %lld pass2 %lld wait_o %lld epilogue %lld cycles (%d items/CTA)\n",
+              w ? "warp9" : "warp2", h[w * 6], h[w * 6 + 1], h[w * 6 + 2], h[w * 6 + 3], h[w * 6 + 4], h[w * 6 + 5], a.items_per_cta);
+  }
   return (int)cudaGetLastError();
 }
 
@@ -1219,6 +1328,7 @@ template <int W>
 static int launch_vit_bwd(const xfm_attn_params* p, cudaStream_t s) {
   using Cfg = VitBwdCfg<W>;
   VitBwdArgs a;
+  a.prof = nullptr;
   a.lse = p->lse; a.delta = p->delta; a.table = p->rel_table; a.dtable = p->rel_dtable;
   a.ds_dump = (bf16*)p->ds_dump; a.ds_ld = p->ds_ld;
   a.dq = (bf16*)p->dq; a.dk = (bf16*)p->dk; a.dv = (bf16*)p->dv;
@@ -1238,9 +1348,14 @@ static int launch_vit_bwd(const xfm_attn_params* p, cudaStream_t s) {
   const int n_items_f = a.B * a.H;
   if (!a.dtable) {   // table gradient (if any) comes from the dS dump: one fused kernel for dQ, dK and dV
     using FCfg = VitFusedCfg<W>;
-    CUtensorMap mq1, mdo1;
+    CUtensorMap mq1, mdo1, m_dq, m_dk, m_dv, m_ds;
     rc = encode_rows(&mq1, p->q, cols, rows, p->q_stride, 128);
     if (!rc) rc = encode_rows(&mdo1, p->dout, cols, rows, p->do_stride, 128);
+    if (!rc) rc = encode_rows_3d(&m_dq, p->dq, cols, Cfg::L, a.B, p->dq_stride);
+    if (!rc) rc = encode_rows_3d(&m_dk, p->dk, cols, Cfg::L, a.B, p->dk_stride);
+    if (!rc) rc = encode_rows_3d(&m_dv, p->dv, cols, Cfg::L, a.B, p->dv_stride);
+    m_ds = m_dq;
+    if (!rc && a.ds_dump) rc = encode_rows_3d(&m_ds, a.ds_dump, (uint64_t)a.ds_ld, Cfg::L, (uint64_t)a.B * a.H, (uint64_t)a.ds_ld);
     if (rc) return rc;
     static bool fattr = false;
     if (!fattr) {
@@ -1251,8 +1366,23 @@ static int launch_vit_bwd(const xfm_attn_params* p, cudaStream_t s) {
     const int ctas = n_items_f < num_sms() ? n_items_f : num_sms();
     a.items_per_cta = (n_items_f + ctas - 1) / ctas;
     const int grid = (n_items_f + a.items_per_cta - 1) / a.items_per_cta;
-    vit_attn_bwd_fused_tc_kernel<W><<<grid, TC_THREADS, FCfg::SMEM, s>>>(mq1, mdo1, mk_l, mv_l, a);
+    static const bool prof_on = getenv("XFM_ATTN_PROF") != nullptr;
+    static long long* prof_buf = nullptr;
+    a.prof = nullptr;
+    if (prof_on) {
+      if (!prof_buf) cudaMalloc(&prof_buf, 12 * sizeof(long long));
+      a.prof = prof_buf;
+    }
+    vit_attn_bwd_fused_tc_kernel<W><<<grid, TC_THREADS, FCfg::SMEM, s>>>(mq1, mdo1, mk_l, mv_l, m_dq, m_dk, m_dv, m_ds, a);
     count_launch();
+    if (prof_on) {  // debugging aid (synchronous)
+      long long h[12];
+      cudaStreamSynchronize(s);
+      cudaMemcpy(h, prof_buf, sizeof(h), cudaMemcpyDeviceToHost);
+      for (int w = 0; w < 2; ++w)
+        fprintf(stderr, "vit_attn_bwd_fused prof %s: setup %lld wait_sd %lld elementwise %lld wait_out %lld drain %lld cycles (%d items/CTA)\n",
+                w ? "warp9" : "warp2", h[w * 6], h[w * 6 + 1], h[w * 6 + 2], h[w * 6 + 3], h[w * 6 + 4], a.items_per_cta);
+    }
     return (int)cudaGetLastError();
   }
   static bool attr = false;

@@ -73,7 +73,24 @@ XFM_DEVINL void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                : "memory");
 }
+// 3D forms (c0 = contiguous dim, c1 = row inside a sample, c2 = sample): a box that starts inside a sample is clipped at the
+// sample's last row, which a flat 2D [rows, cols] map cannot do.
+XFM_DEVINL void tma_store_3d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+// element-wise add of the tile onto global memory (performed at L2; the tensor map's data type selects the arithmetic)
+XFM_DEVINL void tma_reduce_add_3d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 XFM_DEVINL void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+XFM_DEVINL void tma_store_wait_all() {    // at most N of this thread's bulk groups may still be incomplete (writes included)
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
 template <int N>
 XFM_DEVINL void tma_store_wait_read() {   // at most N of this thread's bulk groups may still be READING shared memory
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
