@@ -853,8 +853,11 @@ struct XFusedCfg {
 template <int LQS, int LK>
 __global__ void __launch_bounds__(XT_THREADS, 1)
 xattn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
-                          const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v, const XAttnArgs a) {
+                          const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
+                          const __grid_constant__ CUtensorMap map_dq, const __grid_constant__ CUtensorMap map_dk,
+                          const __grid_constant__ CUtensorMap map_dv, const XAttnArgs a) {
   using Cfg = XFusedCfg<LQS, LK>;
+  static_assert((LQS * 128) % 1024 == 0, "a sample's slot must start on a swizzle-pattern boundary (TMA source of the dQ stores)");
   constexpr int LPAD = Cfg::LPAD, GMAX = Cfg::GMAX, NM = Cfg::NM, SPLIT = Cfg::SPLIT;
   extern __shared__ __align__(1024) uint8_t smem[];
   if (smem_u32(smem) & 1023) __trap();
@@ -876,6 +879,9 @@ xattn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
     tma_prefetch_desc(&map_do);
     tma_prefetch_desc(&map_k);
     tma_prefetch_desc(&map_v);
+    tma_prefetch_desc(&map_dq);
+    tma_prefetch_desc(&map_dk);
+    tma_prefetch_desc(&map_dv);
     mbar_init(kv_full, 1);
     mbar_init(kv_empty, 1);
     mbar_init(qdo_full, 1);
@@ -1002,6 +1008,7 @@ xattn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
     const int sw = r & 7;
     const int cb = wg == 0 ? 0 : SPLIT, ce = wg == 0 ? SPLIT : LPAD;
     constexpr int LKE = (LK + 1) & ~1;
+    const bool elected = threadIdx.x == 64;   // issues every TMA store of this CTA (bulk groups are per thread)
     XWalker<GMAX> w(a, item0, item1);
     XUnit u;
     uint32_t up = 0;
@@ -1020,6 +1027,9 @@ xattn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
       const uint32_t pb_lo = (uint32_t)pair_base, pb_hi = (uint32_t)(pair_base >> 32);
       mbar_wait(sd_full, up);
       tc_fence_after();
+      // the previous unit's output stores still read the P / dS buffers this unit is about to overwrite
+      if (elected) tma_store_wait_read<0>();
+      named_bar_sync(1, 256);
 #pragma unroll 1
       for (int c0 = cb; c0 < ce; c0 += 32) {
         const bool full = c0 + 32 <= ce;
@@ -1074,6 +1084,10 @@ xattn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
       if (lane == 0) mbar_arrive(ds_full);
       mbar_wait(out_full, up);
       tc_fence_after();
+      // Outputs (see attention_tc.cu's fused backward): every 64-column block is staged as bf16 in a SWIZZLE_128B [128 x 64]
+      // tile — dK / dV in the consumed P buffer, dQ in block 0 of the consumed dS buffer — and stored by TMA: dQ one box of
+      // LQS rows per stacked sample, dK / dV through [image, key, column] maps that clip at the image's last key; later
+      // chunks of the same image go out as TMA reduce-adds onto the first chunk's rows.
       constexpr int UH = Cfg::UNITS / 2;
 #pragma unroll
       for (int i0 = 0; i0 < UH; i0 += 2) {
@@ -1090,44 +1104,52 @@ xattn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
         for (int ii = 0; ii < 2; ++ii) {
           if (i0 + ii >= UH) continue;
           const int un = wg * UH + i0 + ii;
-          bf16* dst = nullptr;
+          uint8_t* blk;
           float mul = a.scale;
-          bool add = false;
+          int half = un & 1;
           if (un < 2) {
-            if (valid) dst = a.dq + ((int64_t)b * LQS + q) * a.dq_stride + u.h * XT_HD + un * 32;
+            blk = sdS;
           } else {
             const bool is_dv = un >= 2 + 2 * NM;
             const int uu = is_dv ? un - 2 - 2 * NM : un - 2;
-            const int key = (uu >> 1) * 128 + r;
-            if (key < LK)
-              dst = (is_dv ? a.dv + ((int64_t)u.r * LK + key) * a.dv_stride : a.dk + ((int64_t)u.r * LK + key) * a.dk_stride) +
-                    u.h * XT_HD + (uu & 1) * 32;
+            blk = sP + ((is_dv ? NM : 0) + (uu >> 1)) * 16384;
+            half = uu & 1;
             if (is_dv) mul = 1.0f;
-            add = chunk_of_item > 0;
           }
-          if (dst) {
+          uint8_t* row = blk + (r >> 3) * 1024 + (r & 7) * 128;
 #pragma unroll
-            for (int e = 0; e < 32; e += 8) {
-              float vv[8];
+          for (int e = 0; e < 32; e += 8) {
+            float vv[8];
 #pragma unroll
-              for (int k = 0; k < 8; ++k) vv[k] = __uint_as_float(o[ii][e + k]) * mul;
-              if (add) {
-                const uint4 prev = *(const uint4*)(dst + e);
-                const __nv_bfloat162* p2 = (const __nv_bfloat162*)&prev;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const float2 f = __bfloat1622float2(p2[k]);
-                  vv[2 * k] += f.x;
-                  vv[2 * k + 1] += f.y;
-                }
-              }
-              xt_st_bf16x8((uint8_t*)(dst + e), vv);
-            }
+            for (int k = 0; k < 8; ++k) vv[k] = __uint_as_float(o[ii][e + k]) * mul;
+            xt_st_bf16x8(row + (((half * 4 + (e >> 3)) ^ sw) << 4), vv);
           }
         }
       }
+      fence_proxy_async();
+      named_bar_sync(1, 256);
+      if (elected) {
+        for (int g = 0; g < u.ns; ++g)
+          tma_store_2d(&map_dq, sdS + g * (LQS * 128), u.h * XT_HD, a.kv_samples[u.first + g] * LQS);
+        if (chunk_of_item == 0) {
+#pragma unroll
+          for (int m = 0; m < NM; ++m) {
+            tma_store_3d(&map_dk, sP + m * 16384, u.h * XT_HD, m * 128, u.r);
+            tma_store_3d(&map_dv, sP + (NM + m) * 16384, u.h * XT_HD, m * 128, u.r);
+          }
+        } else {
+          tma_store_wait_all<0>();               // the earlier chunks' dK / dV have landed
+#pragma unroll
+          for (int m = 0; m < NM; ++m) {
+            tma_reduce_add_3d(&map_dk, sP + m * 16384, u.h * XT_HD, m * 128, u.r);
+            tma_reduce_add_3d(&map_dv, sP + (NM + m) * 16384, u.h * XT_HD, m * 128, u.r);
+          }
+        }
+        tma_store_commit();
+      }
       up ^= 1;
     }
+    if (elected) tma_store_wait_all<0>();        // shared memory must outlive the reads; results complete before exit
   }
   tc_fence_before();
   __syncthreads();
@@ -1150,6 +1172,25 @@ static int xt_encode_rows(CUtensorMap* map, const void* base, uint64_t cols, uin
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cross attention: cuTensorMapEncodeTiled failed: %d", (int)r);
+    return XFM_ERR_BAD_ARG;
+  }
+  return 0;
+}
+
+// [image, key, 64-column block] view of dK / dV: boxes of 128 keys are clipped at the image's last key
+static int xt_encode_rows_3d(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows_per_sample, uint64_t samples,
+                             uint64_t ld_elems) {
+  auto fn = get_tensor_map_encoder();
+  if (!fn) return XFM_ERR_NO_DRIVER;
+  cuuint64_t dims[3] = {cols, rows_per_sample, samples};
+  cuuint64_t strides[2] = {ld_elems * 2, rows_per_sample * ld_elems * 2};
+  cuuint32_t box[3] = {XT_HD, 128, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cross attention: cuTensorMapEncodeTiled (3D store map) failed: %d", (int)r);
     return XFM_ERR_BAD_ARG;
   }
   return 0;
@@ -1228,9 +1269,14 @@ int cross_attention_bwd_tc(const xfm_attn_params* p, cudaStream_t s) {
       if (e != cudaSuccess) return (int)e;
       fattr = true;
     }
+    CUtensorMap m_dq, m_dk, m_dv;
+    rc = xt_encode_rows(&m_dq, p->dq, cols, (uint64_t)a.B * LQS, p->dq_stride, LQS);
+    if (!rc) rc = xt_encode_rows_3d(&m_dk, p->dk, cols, LK, a.Bkv, p->dk_stride);
+    if (!rc) rc = xt_encode_rows_3d(&m_dv, p->dv, cols, LK, a.Bkv, p->dv_stride);
+    if (rc) return rc;
     const int n_items_f = a.Bkv * a.H;
     const int grid_f = (n_items_f + a.items_per_cta - 1) / a.items_per_cta;
-    kf<<<grid_f, XT_THREADS, FCfg::SMEM, s>>>(mq, mdo, mk_l, mv_l, a);
+    kf<<<grid_f, XT_THREADS, FCfg::SMEM, s>>>(mq, mdo, mk_l, mv_l, m_dq, m_dk, m_dv, a);
     count_launch();
     return (int)cudaGetLastError();
   }

@@ -53,6 +53,9 @@ XFM_DEVINL void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(addr, parity)) __nanosleep(40);
 }
 
+// named barrier over a subset of the CTA's warps (id 0 is __syncthreads')
+XFM_DEVINL void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
 // ----------------------------------------------------------------------------- TMA
 XFM_DEVINL void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
