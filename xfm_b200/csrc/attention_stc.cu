@@ -65,7 +65,9 @@ XFM_DEVINL void st_union(int quad, int& ulo, int& uhi) {
 }
 
 // ================================================================================================ forward
-constexpr int SF_SMEM = 2 * 3 * 16384 + 2 * 32768 + 2 * 2 * 128 * 4 + 256;
+constexpr int SF_STAGE = 2 * 3 * 16384 + 2 * 32768 + 2 * 2 * 128 * 4 + 256;   // per-warp output staging: 8 x [32 rows][128 B]
+constexpr int SF_SMEM = SF_STAGE + 8 * 4096;
+static_assert(SF_STAGE % 128 == 0, "staging alignment");
 
 __global__ void __launch_bounds__(ST_THREADS, 1)
 sattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
@@ -266,9 +268,11 @@ sattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_empty[t]);
-      if (valid) {
-        const float inv = 1.0f / sum;
-        bf16* orow = a.out + ((int64_t)b * ST_L + q) * a.o_stride + h * ST_HD;
+      {
+        // thread = row would store 16-byte pieces of 32 different rows per instruction; the rows of a tile are consecutive
+        // rows of the output (grp * 120 + r), so each warp stages its 32 rows and stores four whole 128-byte rows per instruction
+        uint8_t* stg = smem + SF_STAGE + (warp - 2) * 4096;
+        const float inv = valid ? 1.0f / sum : 0.f;
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh)
 #pragma unroll
@@ -276,9 +280,19 @@ sattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             float vv[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) vv[k] = __uint_as_float(o[hh][e + k]) * inv;
-            st_st_bf16x8((uint8_t*)(orow + hh * 32 + e), vv);
+            st_st_bf16x8(stg + lane * 128 + (((hh * 4 + (e >> 3)) ^ (lane & 7)) << 4), vv);
           }
-        if (a.lse) a.lse[((int64_t)b * a.H + h) * ST_L + q] = (m + log2f(sum)) * 0.6931471805599453f;
+        if (valid && a.lse) a.lse[((int64_t)b * a.H + h) * ST_L + q] = (m + log2f(sum)) * 0.6931471805599453f;
+        __syncwarp();
+        const int ch = lane & 7;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int sl = it * 4 + (lane >> 3);
+          const int v2 = __shfl_sync(0xffffffffu, (int)valid, sl);
+          const uint4 v4 = *(const uint4*)(stg + sl * 128 + ((ch ^ (sl & 7)) << 4));
+          if (v2) *(uint4*)(a.out + ((int64_t)grp * ST_ROWS + quad * 32 + sl) * a.o_stride + h * ST_HD + ch * 8) = v4;
+        }
+        __syncwarp();
       }
       ph ^= 1;
     }
@@ -296,7 +310,9 @@ sattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 // write P~ = keep * P / (1-p) and dS = P o (keep * dP / (1-p) - delta) to shared memory; then dQ = dS K, dK = dS^T Q and
 // dV = P~^T dO accumulate into the TMEM columns S / dP occupied.  Operands and TMEM are double-buffered so the next tile's
 // S / dP are ready when the elementwise stage gets there; P~ / dS are single-buffered.
-constexpr int SB_SMEM = 2 * 4 * 16384 + 2 * 32768 + 2 * 128 * 4 + 256;
+constexpr int SB_STAGE = 2 * 4 * 16384 + 2 * 32768 + 2 * 128 * 4 + 256;   // per-warp output staging: 8 x [32 rows][64 B]
+constexpr int SB_SMEM = SB_STAGE + 8 * 2048;
+static_assert(SB_STAGE % 128 == 0, "staging alignment");
 
 __global__ void __launch_bounds__(ST_THREADS, 1)
 sattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
@@ -505,21 +521,24 @@ sattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tm_empty[st]);
-      if (valid) {
-        const int64_t row = (int64_t)b * ST_L + q;
-        bf16* pq = a.dq + row * a.dq_stride + h * ST_HD;
-        bf16* pk = a.dk + row * a.dk_stride + h * ST_HD;
-        bf16* pv = a.dv + row * a.dv_stride + h * ST_HD;
+      {
+        // wg 0: dQ[0:32) dQ[32:64) dK[0:32)     wg 1: dK[32:64) dV[0:32) dV[32:64).  Each 32-column part is staged per warp
+        // ([32 rows][64 B], chunk index xor-ed with (row >> 1) & 3: conflict-free both ways) and stored eight rows x 64 bytes
+        // per instruction: whole sectors instead of 16-byte pieces of 32 rows.  Tile rows are consecutive global rows.
+        uint8_t* stg = smem + SB_STAGE + (warp - 2) * 2048;
+        const int64_t row0 = (int64_t)grp * ST_ROWS + quad * 32;
 #pragma unroll
         for (int part = 0; part < 3; ++part) {
-          // wg 0: dQ[0:32) dQ[32:64) dK[0:32)     wg 1: dK[32:64) dV[0:32) dV[32:64)
           bf16* dst;
+          int64_t ld;
           float mul;
           if (wg == 0) {
-            dst = part < 2 ? pq + part * 32 : pk;
+            dst = part < 2 ? a.dq + part * 32 : a.dk;
+            ld = part < 2 ? a.dq_stride : a.dk_stride;
             mul = a.scale;
           } else {
-            dst = part == 0 ? pk + 32 : pv + (part - 1) * 32;
+            dst = part == 0 ? a.dk + 32 : a.dv + (part - 1) * 32;
+            ld = part == 0 ? a.dk_stride : a.dv_stride;
             mul = part == 0 ? a.scale : 1.0f;
           }
 #pragma unroll
@@ -527,8 +546,18 @@ sattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             float vv[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) vv[k] = __uint_as_float(o[part][e + k]) * mul;
-            st_st_bf16x8((uint8_t*)(dst + e), vv);
+            st_st_bf16x8(stg + lane * 64 + ((((e >> 3)) ^ ((lane >> 1) & 3)) << 4), vv);
           }
+          __syncwarp();
+          const int ch = lane & 3;
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int sl = it * 8 + (lane >> 2);
+            const int v2 = __shfl_sync(0xffffffffu, (int)valid, sl);
+            const uint4 v4 = *(const uint4*)(stg + sl * 64 + ((ch ^ ((sl >> 1) & 3)) << 4));
+            if (v2) *(uint4*)(dst + (row0 + sl) * ld + h * ST_HD + ch * 8) = v4;
+          }
+          __syncwarp();
         }
       }
     }
