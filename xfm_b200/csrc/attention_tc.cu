@@ -25,6 +25,7 @@ namespace xfm {
 
 constexpr int TC_HD = 64;
 constexpr int TC_THREADS = 64 + 256;
+constexpr int TCF_THREADS = 64 + 512;   // fused backward: four element-wise / drain warpgroups (four warps per scheduler)
 
 struct VitAttnArgs {
   bf16* out;
@@ -907,8 +908,8 @@ struct VitFusedCfg : VitCfg<W> {
   static_assert(SMEM <= 232448, "shared memory");
 };
 
-template <int W>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int W, bool PROF>
+__global__ void __launch_bounds__(TCF_THREADS, 1)
 vit_attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
                              const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
                              const __grid_constant__ CUtensorMap map_dq, const __grid_constant__ CUtensorMap map_dk,
@@ -945,9 +946,9 @@ vit_attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __
     mbar_init(qdo_full, 1);
     mbar_init(qdo_empty, 1);
     mbar_init(sd_full, 1);
-    mbar_init(ds_full, 8);
+    mbar_init(ds_full, 16);
     mbar_init(out_full, 1);
-    mbar_init(out_empty, 8);
+    mbar_init(out_empty, 16);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -1029,32 +1030,33 @@ vit_attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __
     }
     __syncwarp();
   } else {
-    const int wg = (warp - 2) >> 2;
+    const int wg = (warp - 2) >> 2;            // 0..3: column quarter in the element-wise stage, unit list in the drain
     const int quad = warp & 3;
     const int r = quad * 32 + lane;
-    const int wgt = threadIdx.x - 64;          // 0..255
+    const int wgt = threadIdx.x - 64;          // 0..511
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
     const float scale2 = a.scale * 1.4426950408889634f;
     uint8_t* myS = sdS + (r >> 3) * 1024 + (r & 7) * 128;
     uint8_t* myP = sP + (r >> 3) * 1024 + (r & 7) * 128;
     const int sw = r & 7;
-    constexpr int C_END0 = SPLIT, C_END1 = LPAD;
+    constexpr int N16 = LPAD / 16;             // 16-column chunks of a score row, split in four runs
+    const int ch_lo = (wg * N16) / 4, ch_hi = ((wg + 1) * N16) / 4;
     const bool elected = threadIdx.x == 64;   // issues every TMA store of this CTA (bulk groups are per thread)
     int cur_h = -1;
     long long pc[5] = {0, 0, 0, 0, 0}, pt = clock64();
-    auto tick = [&](int i) { if (a.prof) { const long long n = clock64(); pc[i] += n - pt; pt = n; } };
+    auto tick = [&](int i) { if (PROF) { const long long n = clock64(); pc[i] += n - pt; pt = n; } };
     for (int tau = 0; tau < n_tiles; ++tau) {
       const int item = item0 + tau / NT, t = tau % NT;
       const int h = item / a.B, b = item % a.B;
       const uint32_t par = (uint32_t)tau & 1u;
       const int qi = t * 128 + r;
       if (h != cur_h) {
-        named_bar_sync(1, 256);
-        for (int i = wgt; i < Cfg::T; i += 256)
+        named_bar_sync(1, 512);
+        for (int i = wgt; i < Cfg::T; i += 512)
           tab[Cfg::OFFMAX + 1 + i] = a.table ? __ldg(a.table + (int64_t)i * a.H + h) * 1.4426950408889634f : 0.f;
         const float row0 = a.table ? __ldg(a.table + (int64_t)(Cfg::T - 3) * a.H + h) * 1.4426950408889634f : 0.f;
-        for (int i = wgt; i <= Cfg::OFFMAX; i += 256) tab[i] = row0;
-        named_bar_sync(1, 256);
+        for (int i = wgt; i <= Cfg::OFFMAX; i += 512) tab[i] = row0;
+        named_bar_sync(1, 512);
         cur_h = h;
       }
       const int qc = qi < L ? qi : L - 1;
@@ -1073,52 +1075,36 @@ vit_attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __
       tc_fence_after();
       // the previous tile's output / dS stores still read the P / dS buffers this tile is about to overwrite
       if (elected) tma_store_wait_read<0>();
-      named_bar_sync(1, 256);
+      named_bar_sync(1, 512);
       tick(1);
-      const int cb = wg == 0 ? 0 : C_END0, ce = wg == 0 ? C_END0 : C_END1;
+      // ---- element-wise stage: 16-column chunks (four warps per scheduler hide the TMEM load latency; a second register
+      // buffer for the next chunk does not fit the 96 registers 18 warps leave per thread)
+      uint32_t vs[32], vp[32];                   // only [0..15] are used
 #pragma unroll
-      for (int cc = 0; cc < LPAD; cc += 32) {
-        if (cc >= (SPLIT > LPAD - SPLIT ? SPLIT : LPAD - SPLIT)) continue;
-        const int c0 = cb + cc;
-        if (c0 >= ce) continue;
-        const bool full = c0 + 32 <= ce;
+      for (int ch = 0; ch < N16; ++ch) {
+        if (ch < ch_lo || ch >= ch_hi) continue;   // warp-uniform
         if (!wv) {   // every row of this warp lies beyond the last query (second tile): only clear its operand rows
 #pragma unroll
-          for (int g8 = 0; g8 < 4; ++g8) {
-            if (!full && g8 >= 2) continue;
-            const int col8 = c0 + g8 * 8;
+          for (int g8 = 0; g8 < 2; ++g8) {
+            const int col8 = ch * 16 + g8 * 8;
             const int off8 = (col8 >> 6) * 16384 + ((((col8 & 63) >> 3) ^ sw) << 4);
             *(uint4*)(myS + off8) = make_uint4(0u, 0u, 0u, 0u);
             *(uint4*)(myP + off8) = make_uint4(0u, 0u, 0u, 0u);
           }
           continue;
         }
-        uint32_t vs[32], vp[32];
-        if (full) {
-          tmem_ld_32x32(lane_base + TM_S + c0, vs);
-          tmem_ld_32x32(lane_base + TM_DP + c0, vp);
-        } else {
-          tmem_ld_32x32_16(lane_base + TM_S + c0, vs);
-          tmem_ld_32x32_16(lane_base + TM_DP + c0, vp);
-        }
+        tmem_ld_32x32_16(lane_base + TM_S + ch * 16, vs);
+        tmem_ld_32x32_16(lane_base + TM_DP + ch * 16, vp);
         tmem_ld_wait();
 #pragma unroll
-        for (int g8 = 0; g8 < 4; ++g8) {
-          if (!full && g8 >= 2) continue;
-          const int col8 = c0 + g8 * 8;
+        for (int g8 = 0; g8 < 2; ++g8) {
+          const int col8 = ch * 16 + g8 * 8;
           const int off8 = (col8 >> 6) * 16384 + ((((col8 & 63) >> 3) ^ sw) << 4);
           float ds[8], pp[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            const int j = c0 + g8 * 8 + e;
-            float bias2;
-            if (wg == 0) {
-              const int jc = cc + g8 * 8 + e;
-              bias2 = jc == 0 ? bias_c0 : *(rb - rel_off<W>(jc));
-            } else {
-              const int jc = SPLIT + cc + g8 * 8 + e;
-              bias2 = *(rb - rel_off<W>(jc));
-            }
+            const int j = col8 + e;
+            const float bias2 = j == 0 ? bias_c0 : *(rb - rel_off<W>(j));
             float p = ex2_approx(fmaf(__uint_as_float(vs[g8 * 8 + e]), scale2, bias2) - lse2);
             if (j >= L || !row_ok) p = 0.f;
             pp[e] = p;
@@ -1133,13 +1119,13 @@ vit_attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __
       __syncwarp();
       if (lane == 0) mbar_arrive(ds_full);
       tick(2);
-      // ---- outputs: 32-column units [dQ | dK tiles | dV tiles], half of them per warpgroup.  thread = row would write (and,
-      // for the second query tile, read-modify-write) 16-byte pieces of 32 different rows per instruction: 45 % of this
-      // kernel's time.  Instead every 64-column output block is staged as bf16 in a SWIZZLE_128B [128 x 64] tile — the dK /
-      // dV blocks in the consumed P buffer, dQ in block 0 of the consumed dS buffer — and one thread issues TMA stores
-      // through 3D maps [sample, row, column] that clip at the sample's last row; the second query tile's dK / dV go out as
-      // TMA reduce-adds onto the first tile's.  dS itself (the table gradient's input) is stored by TMA from the dS operand
-      // buffer it already sits in.
+      // ---- outputs: 32-column units [dQ | dK tiles | dV tiles].  thread = row would write (and, for the second query tile,
+      // read-modify-write) 16-byte pieces of 32 different rows per instruction: 45 % of this kernel's time.  Instead every
+      // 64-column output block is staged as bf16 in a SWIZZLE_128B [128 x 64] tile — the dK / dV blocks in the consumed P
+      // buffer, dQ in block 0 of the consumed dS buffer — and one thread issues TMA stores through 3D maps [sample, row,
+      // column] that clip at the sample's last row; the second query tile's dK / dV go out as TMA reduce-adds onto the first
+      // tile's.  dS itself (the table gradient's input) is stored by TMA from the dS operand buffer it already sits in.
+      // Units per warpgroup: 0: {dK unit 2, then dQ = units 0, 1}, 1: {3, 4, 5}, 2: {6, 7}, 3: {8, 9} (UNITS = 10; 6: only 0 and 1).
       mbar_wait(out_full, par);
       tc_fence_after();
       tick(3);
@@ -1150,52 +1136,46 @@ vit_attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __
         }
         tma_store_commit();                      // (possibly empty) group: keeps the group count per tile fixed
       }
-      constexpr int UH = Cfg::UNITS / 2;
-      constexpr int DQ_ROUND = (UH - 2) & ~1;   // warpgroup 0 drains its dK units first and dQ (units 0, 1) last
-      auto unit_of = [&](int i) { return wg == 0 ? (i < UH - 2 ? i + 2 : i - (UH - 2)) : UH + i; };
+      static_assert(Cfg::UNITS == 10 || Cfg::UNITS == 6, "unit lists below");
+      const int n_mine = wg < 2 ? 3 : (Cfg::UNITS == 10 ? 2 : 0);
+      const int u_first = wg == 0 ? 2 : (wg == 1 ? 3 : 2 + 2 * wg);   // wg 0 continues with units 0, 1
 #pragma unroll
-      for (int i0 = 0; i0 < UH; i0 += 2) {      // two units (64 registers) at a time
-        uint32_t o[2][32];
-        tmem_ld_32x32(lane_base + (uint32_t)(unit_of(i0) * 32), o[0]);
-        if (i0 + 1 < UH) tmem_ld_32x32(lane_base + (uint32_t)(unit_of(i0 + 1) * 32), o[1]);
+      for (int i = 0; i < 3; ++i) {
+        if (i >= n_mine) continue;               // warp-uniform
+        const int u = wg == 0 ? (i == 0 ? 2 : i - 1) : u_first + i;
+        uint32_t o[32];
+        tmem_ld_32x32(lane_base + (uint32_t)(u * 32), o);
         tmem_ld_wait();
-        if (i0 + 2 >= UH) {                      // last read of this tile's outputs: TMEM may be overwritten
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(out_empty);
-        }
-        if (wg == 0 && i0 == DQ_ROUND) {         // dQ is staged where dS lies: its TMA store must have read the buffer
+        if (wg == 0 && i == 1) {                 // dQ is staged where dS lies: its TMA store must have read the buffer
           if (elected) tma_store_wait_read<0>();
           named_bar_sync(2, 128);
         }
+        uint8_t* blk;
+        float mul = a.scale;
+        int half = u & 1;
+        if (u < 2) {
+          blk = sdS;
+        } else {
+          const bool is_dv = u >= 2 + 2 * NM;
+          const int uu = is_dv ? u - 2 - 2 * NM : u - 2;
+          blk = sP + ((is_dv ? NM : 0) + (uu >> 1)) * 16384;
+          half = uu & 1;
+          if (is_dv) mul = 1.0f;
+        }
+        uint8_t* row = blk + (r >> 3) * 1024 + (r & 7) * 128;
 #pragma unroll
-        for (int ii = 0; ii < 2; ++ii) {
-          if (i0 + ii >= UH) continue;
-          const int u = unit_of(i0 + ii);       // unit -> (tensor, key tile, column half)
-          uint8_t* blk;
-          float mul = a.scale;
-          int half = u & 1;
-          if (u < 2) {
-            blk = sdS;
-          } else {
-            const bool is_dv = u >= 2 + 2 * NM;
-            const int uu = is_dv ? u - 2 - 2 * NM : u - 2;
-            blk = sP + ((is_dv ? NM : 0) + (uu >> 1)) * 16384;
-            half = uu & 1;
-            if (is_dv) mul = 1.0f;
-          }
-          uint8_t* row = blk + (r >> 3) * 1024 + (r & 7) * 128;
+        for (int e = 0; e < 32; e += 8) {
+          float v[8];
 #pragma unroll
-          for (int e = 0; e < 32; e += 8) {
-            float v[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = __uint_as_float(o[ii][e + k]) * mul;
-            st_bf16x8(row + (((half * 4 + (e >> 3)) ^ sw) << 4), v);
-          }
+          for (int k = 0; k < 8; ++k) v[k] = __uint_as_float(o[e + k]) * mul;
+          st_bf16x8(row + (((half * 4 + (e >> 3)) ^ sw) << 4), v);
         }
       }
+      tc_fence_before();                         // every TMEM read of this warp is complete (tcgen05.wait::ld above)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(out_empty);
       fence_proxy_async();
-      named_bar_sync(1, 256);
+      named_bar_sync(1, 512);
       if (elected) {
         tma_store_3d(&map_dq, sdS, h * TC_HD, t * 128, b);
         if (t == 0) {
@@ -1216,7 +1196,7 @@ vit_attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __
       }
       tick(4);
     }
-    if (a.prof && blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 9))
+    if (PROF && blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 15))
       for (int i = 0; i < 5; ++i) a.prof[(warp == 2 ? 0 : 6) + i] = pc[i];
     if (elected) tma_store_wait_all<0>();        // shared memory must outlive the reads; results complete before exit
   }
@@ -1358,7 +1338,9 @@ static int launch_vit_bwd(const xfm_attn_params* p, cudaStream_t s) {
     if (rc) return rc;
     static bool fattr = false;
     if (!fattr) {
-      cudaError_t e = cudaFuncSetAttribute(vit_attn_bwd_fused_tc_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, FCfg::SMEM);
+      cudaError_t e = cudaFuncSetAttribute(vit_attn_bwd_fused_tc_kernel<W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FCfg::SMEM);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(vit_attn_bwd_fused_tc_kernel<W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FCfg::SMEM);
       if (e != cudaSuccess) return (int)e;
       fattr = true;
     }
@@ -1372,7 +1354,8 @@ static int launch_vit_bwd(const xfm_attn_params* p, cudaStream_t s) {
       if (!prof_buf) cudaMalloc(&prof_buf, 12 * sizeof(long long));
       a.prof = prof_buf;
     }
-    vit_attn_bwd_fused_tc_kernel<W><<<grid, TC_THREADS, FCfg::SMEM, s>>>(mq1, mdo1, mk_l, mv_l, m_dq, m_dk, m_dv, m_ds, a);
+    if (prof_on) vit_attn_bwd_fused_tc_kernel<W, true><<<grid, TCF_THREADS, FCfg::SMEM, s>>>(mq1, mdo1, mk_l, mv_l, m_dq, m_dk, m_dv, m_ds, a);
+    else vit_attn_bwd_fused_tc_kernel<W, false><<<grid, TCF_THREADS, FCfg::SMEM, s>>>(mq1, mdo1, mk_l, mv_l, m_dq, m_dk, m_dv, m_ds, a);
     count_launch();
     if (prof_on) {  // debugging aid (synchronous)
       long long h[12];
@@ -1380,7 +1363,7 @@ static int launch_vit_bwd(const xfm_attn_params* p, cudaStream_t s) {
       cudaMemcpy(h, prof_buf, sizeof(h), cudaMemcpyDeviceToHost);
       for (int w = 0; w < 2; ++w)
         fprintf(stderr, "vit_attn_bwd_fused prof %s: setup %lld wait_sd %lld elementwise %lld wait_out %lld drain %lld cycles (%d items/CTA)\n",
-                w ? "warp9" : "warp2", h[w * 6], h[w * 6 + 1], h[w * 6 + 2], h[w * 6 + 3], h[w * 6 + 4], a.items_per_cta);
+                w ? "warp15" : "warp2", h[w * 6], h[w * 6 + 1], h[w * 6 + 2], h[w * 6 + 3], h[w * 6 + 4], a.items_per_cta);
     }
     return (int)cudaGetLastError();
   }
