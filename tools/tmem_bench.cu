@@ -36,6 +36,7 @@ __device__ __forceinline__ void st32(uint32_t taddr, const uint32_t (&r)[32]) {
 // mode 2: st.x32 ; wait::st
 // mode 3: ld.x32 ; wait ; 32 ex2 + 32 fma + 32 max  (the softmax pass-1/2 instruction mix, no stores)
 // mode 4: ld.x16 ; wait
+// mode 6: ld.x32 ; wait ; 32 x (fma + max) only (no MUFU)
 // mode 5: like 3 but the NEXT chunk's load is issued before the arithmetic of the current one (software pipeline)
 template <int MODE>
 __global__ void __launch_bounds__(1024, 1) tmem_kernel(int iters, long long* cycles, float* sink) {
@@ -61,12 +62,12 @@ __global__ void __launch_bounds__(1024, 1) tmem_kernel(int iters, long long* cyc
     if (MODE == 0) {
       tmem_ld_32x32(base + col, v);
       tmem_ld_wait();
-      acc += __uint_as_float(v[i & 31]);
+      acc += __uint_as_float(v[0] ^ v[13] ^ v[31]);   // static indices: a dynamic one sends v[] to local memory
     } else if (MODE == 1) {
       tmem_ld_32x32(base + col, v);
       tmem_ld_32x32(base + ((col + 32) & 448), w);
       tmem_ld_wait();
-      acc += __uint_as_float(v[i & 31]) + __uint_as_float(w[i & 31]);
+      acc += __uint_as_float(v[0] ^ v[31] ^ w[0] ^ w[31]);
     } else if (MODE == 2) {
       v[0] = i;
       st32(base + col, v);
@@ -80,10 +81,15 @@ __global__ void __launch_bounds__(1024, 1) tmem_kernel(int iters, long long* cyc
         mx = fmaxf(mx, l);
         acc += ex2_approx(l - 3.0f);
       }
+    } else if (MODE == 6) {
+      tmem_ld_32x32(base + col, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) mx = fmaxf(mx, fmaf(__uint_as_float(v[e]), 0.18f, 0.01f * e));
     } else if (MODE == 4) {
       ld16(base + col, v);
       tmem_ld_wait();
-      acc += __uint_as_float(v[i & 15]);
+      acc += __uint_as_float(v[0] ^ v[15]);
     } else if (MODE == 5) {
       tmem_ld_wait();
 #pragma unroll
@@ -138,6 +144,7 @@ int main() {
   for (int w : {4, 8, 16}) run<1>("2x ld.x32+wait", w, iters, 8192);
   for (int w : {4, 8, 16}) run<4>("ld.x16+wait", w, iters, 2048);
   for (int w : {4, 8, 16}) run<2>("st.x32+wait", w, iters, 4096);
+  for (int w : {4, 8, 16}) run<6>("ld.x32+wait+fma/max", w, iters, 4096);
   for (int w : {4, 8, 16}) run<3>("ld.x32+wait+softmax-mix", w, iters, 4096);
   for (int w : {4, 8, 16}) run<5>("pipelined ld.x32 + softmax-mix", w, iters, 4096);
   return 0;

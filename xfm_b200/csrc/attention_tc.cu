@@ -916,7 +916,7 @@ vit_attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __
                              const __grid_constant__ CUtensorMap map_dv, const __grid_constant__ CUtensorMap map_ds,
                              const VitBwdArgs a) {
   using Cfg = VitFusedCfg<W>;
-  constexpr int L = Cfg::L, LPAD = Cfg::LPAD, NT = Cfg::NT, SPLIT = Cfg::SPLIT, NM = Cfg::NM;
+  constexpr int L = Cfg::L, LPAD = Cfg::LPAD, NT = Cfg::NT, NM = Cfg::NM;
   extern __shared__ __align__(1024) uint8_t smem[];
   if (smem_u32(smem) & 1023) __trap();
   uint8_t* sQ = smem;                       // one 128-row query tile

@@ -16,6 +16,7 @@ namespace xfm {
 
 constexpr int XT_HD = 64;
 constexpr int XT_THREADS = 64 + 256;
+constexpr int XTF_THREADS = 64 + 512;   // fused backward: four element-wise / drain warpgroups
 
 struct XAttnArgs {
   bf16* out;
@@ -851,14 +852,14 @@ struct XFusedCfg {
 };
 
 template <int LQS, int LK>
-__global__ void __launch_bounds__(XT_THREADS, 1)
+__global__ void __launch_bounds__(XTF_THREADS, 1)
 xattn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
                           const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
                           const __grid_constant__ CUtensorMap map_dq, const __grid_constant__ CUtensorMap map_dk,
                           const __grid_constant__ CUtensorMap map_dv, const XAttnArgs a) {
   using Cfg = XFusedCfg<LQS, LK>;
   static_assert((LQS * 128) % 1024 == 0, "a sample's slot must start on a swizzle-pattern boundary (TMA source of the dQ stores)");
-  constexpr int LPAD = Cfg::LPAD, GMAX = Cfg::GMAX, NM = Cfg::NM, SPLIT = Cfg::SPLIT;
+  constexpr int LPAD = Cfg::LPAD, GMAX = Cfg::GMAX, NM = Cfg::NM;
   extern __shared__ __align__(1024) uint8_t smem[];
   if (smem_u32(smem) & 1023) __trap();
   uint8_t* sQ = smem;
@@ -887,9 +888,9 @@ xattn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
     mbar_init(qdo_full, 1);
     mbar_init(qdo_empty, 1);
     mbar_init(sd_full, 1);
-    mbar_init(ds_full, 8);
+    mbar_init(ds_full, 16);
     mbar_init(out_full, 1);
-    mbar_init(out_empty, 8);
+    mbar_init(out_empty, 16);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -1006,7 +1007,8 @@ xattn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
     uint8_t* myS = sdS + (r >> 3) * 1024 + (r & 7) * 128;
     uint8_t* myP = sP + (r >> 3) * 1024 + (r & 7) * 128;
     const int sw = r & 7;
-    const int cb = wg == 0 ? 0 : SPLIT, ce = wg == 0 ? SPLIT : LPAD;
+    constexpr int N16 = LPAD / 16;             // 16-column chunks of a score row, split in four runs
+    const int ch_lo = (wg * N16) / 4, ch_hi = ((wg + 1) * N16) / 4;
     constexpr int LKE = (LK + 1) & ~1;
     const bool elected = threadIdx.x == 64;   // issues every TMA store of this CTA (bulk groups are per thread)
     XWalker<GMAX> w(a, item0, item1);
@@ -1029,24 +1031,18 @@ xattn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
       tc_fence_after();
       // the previous unit's output stores still read the P / dS buffers this unit is about to overwrite
       if (elected) tma_store_wait_read<0>();
-      named_bar_sync(1, 256);
+      named_bar_sync(1, 512);
 #pragma unroll 1
-      for (int c0 = cb; c0 < ce; c0 += 32) {
-        const bool full = c0 + 32 <= ce;
-        uint32_t vs[32], vp[32];
+      for (int ch = ch_lo; ch < ch_hi; ++ch) {
+        const int c0 = ch * 16;
+        uint32_t vs[32], vp[32];                 // [0..15] used
         if (wv) {   // tcgen05.ld is warp-collective: decide per warp, mask per thread
-          if (full) {
-            xt_ld32(lane_base + TM_S + c0, vs);
-            xt_ld32(lane_base + TM_DP + c0, vp);
-          } else {
-            xt_ld16(lane_base + TM_S + c0, vs);
-            xt_ld16(lane_base + TM_DP + c0, vp);
-          }
+          xt_ld16(lane_base + TM_S + c0, vs);
+          xt_ld16(lane_base + TM_DP + c0, vp);
           tmem_ld_wait();
         }
 #pragma unroll
-        for (int g8 = 0; g8 < 4; ++g8) {
-          if (!full && g8 >= 2) continue;
+        for (int g8 = 0; g8 < 2; ++g8) {
           float ds[8], pp[8];
 #pragma unroll
           for (int e = 0; e < 8; e += 2) {
@@ -1088,46 +1084,43 @@ xattn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
       // tile — dK / dV in the consumed P buffer, dQ in block 0 of the consumed dS buffer — and stored by TMA: dQ one box of
       // LQS rows per stacked sample, dK / dV through [image, key, column] maps that clip at the image's last key; later
       // chunks of the same image go out as TMA reduce-adds onto the first chunk's rows.
-      constexpr int UH = Cfg::UNITS / 2;
+      // Units per warpgroup: 0: {0, 1, 2} (dQ and the first dK unit), 1: {3, 4, 5}, 2: {6, 7}, 3: {8, 9} (UNITS = 10; 6: only 0 and 1).
+      static_assert(Cfg::UNITS == 10 || Cfg::UNITS == 6, "unit lists below");
+      const int n_mine = wg < 2 ? 3 : (Cfg::UNITS == 10 ? 2 : 0);
+      const int u_first = wg < 2 ? 3 * wg : 2 + 2 * wg;
 #pragma unroll
-      for (int i0 = 0; i0 < UH; i0 += 2) {
-        uint32_t o[2][32];
-        xt_ld32(lane_base + (uint32_t)((wg * UH + i0) * 32), o[0]);
-        if (i0 + 1 < UH) xt_ld32(lane_base + (uint32_t)((wg * UH + i0 + 1) * 32), o[1]);
+      for (int i = 0; i < 3; ++i) {
+        if (i >= n_mine) continue;               // warp-uniform
+        const int un = u_first + i;
+        uint32_t o[32];
+        xt_ld32(lane_base + (uint32_t)(un * 32), o);
         tmem_ld_wait();
-        if (i0 + 2 >= UH) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(out_empty);
+        uint8_t* blk;
+        float mul = a.scale;
+        int half = un & 1;
+        if (un < 2) {
+          blk = sdS;
+        } else {
+          const bool is_dv = un >= 2 + 2 * NM;
+          const int uu = is_dv ? un - 2 - 2 * NM : un - 2;
+          blk = sP + ((is_dv ? NM : 0) + (uu >> 1)) * 16384;
+          half = uu & 1;
+          if (is_dv) mul = 1.0f;
         }
+        uint8_t* row = blk + (r >> 3) * 1024 + (r & 7) * 128;
 #pragma unroll
-        for (int ii = 0; ii < 2; ++ii) {
-          if (i0 + ii >= UH) continue;
-          const int un = wg * UH + i0 + ii;
-          uint8_t* blk;
-          float mul = a.scale;
-          int half = un & 1;
-          if (un < 2) {
-            blk = sdS;
-          } else {
-            const bool is_dv = un >= 2 + 2 * NM;
-            const int uu = is_dv ? un - 2 - 2 * NM : un - 2;
-            blk = sP + ((is_dv ? NM : 0) + (uu >> 1)) * 16384;
-            half = uu & 1;
-            if (is_dv) mul = 1.0f;
-          }
-          uint8_t* row = blk + (r >> 3) * 1024 + (r & 7) * 128;
+        for (int e = 0; e < 32; e += 8) {
+          float vv[8];
 #pragma unroll
-          for (int e = 0; e < 32; e += 8) {
-            float vv[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) vv[k] = __uint_as_float(o[ii][e + k]) * mul;
-            xt_st_bf16x8(row + (((half * 4 + (e >> 3)) ^ sw) << 4), vv);
-          }
+          for (int k = 0; k < 8; ++k) vv[k] = __uint_as_float(o[e + k]) * mul;
+          xt_st_bf16x8(row + (((half * 4 + (e >> 3)) ^ sw) << 4), vv);
         }
       }
+      tc_fence_before();                         // every TMEM read of this warp is complete (tcgen05.wait::ld above)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(out_empty);
       fence_proxy_async();
-      named_bar_sync(1, 256);
+      named_bar_sync(1, 512);
       if (elected) {
         for (int g = 0; g < u.ns; ++g)
           tma_store_2d(&map_dq, sdS + g * (LQS * 128), u.h * XT_HD, a.kv_samples[u.first + g] * LQS);
@@ -1276,7 +1269,7 @@ int cross_attention_bwd_tc(const xfm_attn_params* p, cudaStream_t s) {
     if (rc) return rc;
     const int n_items_f = a.Bkv * a.H;
     const int grid_f = (n_items_f + a.items_per_cta - 1) / a.items_per_cta;
-    kf<<<grid_f, XT_THREADS, FCfg::SMEM, s>>>(mq, mdo, mk_l, mv_l, m_dq, m_dk, m_dv, a);
+    kf<<<grid_f, XTF_THREADS, FCfg::SMEM, s>>>(mq, mdo, mk_l, mv_l, m_dq, m_dk, m_dv, a);
     count_launch();
     return (int)cudaGetLastError();
   }
