@@ -553,6 +553,55 @@ def test_vit_attention_tcgen05_backward(lib, B, H, ws, with_table):
     assert err < 1e-2 * max(1.0, float(s.grad.abs().max())), ("ds_dump", err)
 
 
+@pytest.mark.parametrize("B,H,with_table", [(2, 3, True), (1, 2, False), (5, 12, True)])
+def test_vit_attention_tcgen05_backward_key_blocks(lib, B, H, with_table):
+    """384 px (W = 24, 577 tokens): the fused tcgen05 backward runs one launch per block of 192 keys — dQ accumulated across the
+    launches by TMA reduce-add, dK / dV rows and the dS columns written per block — against torch autograd.  The forward
+    (and its lse) is the mma.sync kernel with the materialised bias."""
+    from xfm_b200.encoders import closed_form_rel_index
+    ws = 24
+    g = G(ws * 1000 + B)
+    L, D = ws * ws + 1, H * 64
+    qkv = bf(torch.randn(B * L, 3 * D, generator=g) * 0.7)
+    dout = bf(torch.randn(B * L, D, generator=g))
+    f = qkv.float().view(B, L, 3, H, 64).permute(2, 0, 3, 1, 4)
+    qf, kf, vf = (t.clone().requires_grad_(True) for t in (f[0], f[1], f[2]))
+    s = (qf * 0.125) @ kf.transpose(-1, -2)
+    ld = (L + 7) // 8 * 8
+    table, bias = None, None
+    if with_table:
+        T = (2 * ws - 1) ** 2 + 3
+        table = torch.randn(T, H, generator=g)
+        dense = table[closed_form_rel_index(ws).view(-1)].view(L, L, H).permute(2, 0, 1)
+        s = s + dense
+        bias = torch.zeros(H, L, ld)
+        bias[..., :L] = dense
+        bias = bias.cuda()
+    s.retain_grad()
+    ref = torch.softmax(s, -1) @ vf
+    ref.backward(dout.float().view(B, L, H, 64).permute(0, 2, 1, 3))
+    want = torch.stack([qf.grad, kf.grad, vf.grad]).permute(1, 3, 0, 2, 4).reshape(B * L, 3 * D)
+    c, do = qkv.cuda(), dout.cuda()
+    q, k, v = c[:, :D], c[:, D:2 * D], c[:, 2 * D:]
+    out, lse = lib.attention_fwd(q, k, v, B, H, L, L, 0.125, bias=bias)
+    n0 = lib.launch_count()
+    ds = torch.full((B, H, L, ld), float("nan"), dtype=torch.bfloat16, device="cuda")
+    dqkv = torch.full_like(c, float("nan"))
+    lib.attention_bwd(do, q, k, v, out, lse, B, H, L, L, 0.125, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], bias=bias,
+                      ds_dump=ds, rel_table=None if table is None else table.cuda(), rel_window=ws if with_table else 0)
+    assert lib.launch_count() - n0 == 4      # row-delta kernel + three key-block launches (not the mma.sync pair)
+    got = dqkv.float().cpu()
+    assert torch.isfinite(got).all()
+    scale = float(want.abs().max())
+    for name, sl in (("dq", slice(0, D)), ("dk", slice(D, 2 * D)), ("dv", slice(2 * D, 3 * D))):
+        err = float((got[:, sl] - want[:, sl]).abs().max())
+        assert err < 2.5e-2 * max(1.0, scale), (name, err, scale)
+    dsf = ds.float().cpu()
+    assert torch.isfinite(dsf).all() and float(dsf[..., L:].abs().max()) == 0.0      # padding columns are written as zeros
+    err = float((dsf[..., :L] - s.grad).abs().max())
+    assert err < 1e-2 * max(1.0, float(s.grad.abs().max())), ("ds_dump", err)
+
+
 def _cross_case(B, Bkv, H, g, kv_index):
     Lq, Lk, D = 40, 197, H * 64
     q2 = bf(torch.randn(B * Lq, D, generator=g))

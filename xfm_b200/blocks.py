@@ -91,7 +91,7 @@ def vit_block_bwd(dx2, s, w, g, B, N, H, rel_index=None):
     dattn = L.gemm(dz1, w["proj_w16"], b_t=True)
     dqkv = torch.empty_like(s.qkv)
     ds = None
-    tc = s.rel is not None and L.vit_attention_tc_ok(N)  # tcgen05 backward kernels (closed-form bias)
+    tc = s.rel is not None and L.vit_attention_bwd_tc_ok(N)  # tcgen05 backward kernels (closed-form bias)
     if s.relbias is not None:
         ds = torch.empty((B, H, N, s.relbias.shape[2]), dtype=torch.bfloat16, device=dx2.device)
         if s.relbias.shape[2] != N:

@@ -616,7 +616,7 @@ int attention_bwd(const xfm_attn_params* p, cudaStream_t s) {
   }
   // tcgen05 path: needs the closed-form table whenever there is a bias; the table gradient either comes out of the bf16
   // dS dump (reduced by the caller) or is accumulated in-kernel into rel_dtable (shared-memory atomics: slower)
-  if (p->allow_tc && vit_attention_tc_supported(p) && (!p->bias || p->rel_table))
+  if (p->allow_tc && vit_attention_tc_supported(p, true) && (!p->bias || p->rel_table))
     return vit_attention_bwd_tc(p, s);
   if (p->allow_tc && cross_attention_tc_supported(p) && !p->ds_dump) return cross_attention_bwd_tc(p, s);
   if (p->allow_tc && self_attention_tc_supported(p) && !p->ds_dump) return self_attention_bwd_tc(p, s);

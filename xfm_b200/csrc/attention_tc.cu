@@ -895,20 +895,33 @@ vit_attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __gr
 // kernels, therefore runs once per (query, key) pair instead of once in a dQ kernel and again in a dK/dV kernel.  The outputs
 // re-use the TMEM columns of S / dP; the second query tile of a (sample, head) adds its dK / dV to the first tile's rows in
 // global memory (same thread, same rows: no synchronisation needed).
+// Samples with more than 208 keys (384 px: W = 24, L = 577) are processed one KEY BLOCK of 192 keys per launch (the last
+// block takes the remainder, 193): the backward needs no online softmax — P = 2^(S - lse) with the forward's lse — so a
+// key block is just a narrower K / V operand, an offset into the relative-position index, per-block dK / dV rows, and dQ
+// accumulated across the launches (block 0 stores, later blocks TMA-reduce-add; launches of one stream run in order).
 template <int W>
-struct VitFusedCfg : VitCfg<W> {
-  using Base = VitCfg<W>;
-  static constexpr int SPLIT = ((Base::LPAD / 2 + 15) / 16) * 16;
-  static constexpr int NM = (Base::LPAD + 127) / 128;             // 128-key M tiles of dK / dV
+struct VitFusedCfg {
+  static constexpr int L = W * W + 1;
+  static constexpr bool BLOCKED = L > 208;
+  static constexpr int KBS = BLOCKED ? 192 : L;                    // keys per block
+  static constexpr int NB = BLOCKED ? (L - 1) / 192 : 1;           // key blocks = launches
+  static constexpr int LAST = L - (NB - 1) * KBS;                  // keys of the last block
+  static constexpr int LPAD = BLOCKED ? 208 : (L + 15) / 16 * 16;  // score columns in TMEM / operand rows in shared memory
+  static constexpr int NT = (L + 127) / 128;
+  static constexpr int T = (2 * W - 1) * (2 * W - 1) + 3;
+  static constexpr int OFFMAX = (W - 1) * (2 * W - 1) + (W - 1);
+  static constexpr int TAB_FLOATS = (OFFMAX + 1 + T + 7) & ~7;
+  static constexpr int KV_BYTES = LPAD * 128;
+  static constexpr int NM = (LPAD + 127) / 128;                    // 128-key M tiles of dK / dV
   static constexpr int PD_BYTES = 2 * NM * 16384;                  // P / dS operand: whole 64-key blocks for every M tile
-  static constexpr int SMEM = 2 * 16384 + 2 * Base::KV_BYTES + 2 * PD_BYTES + Base::TAB_FLOATS * 4 + 128;
+  static constexpr int SMEM = 2 * 16384 + 2 * KV_BYTES + 2 * PD_BYTES + TAB_FLOATS * 4 + 128;
   static constexpr int TM_DQ = 0, TM_DK = 64, TM_DV = 64 + 64 * NM, TM_END = 64 + 128 * NM;
   static constexpr int UNITS = TM_END / 32;                        // 32-column drain units, split between the warpgroups
-  static_assert(2 * Base::LPAD <= 512 && TM_END <= 512, "TMEM");
+  static_assert(LAST <= LPAD && 2 * LPAD <= 512 && TM_END <= 512, "TMEM");
   static_assert(SMEM <= 232448, "shared memory");
 };
 
-template <int W, bool PROF>
+template <int W, int KB, bool PROF>
 __global__ void __launch_bounds__(TCF_THREADS, 1)
 vit_attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
                              const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
@@ -917,6 +930,9 @@ vit_attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __
                              const VitBwdArgs a) {
   using Cfg = VitFusedCfg<W>;
   constexpr int L = Cfg::L, LPAD = Cfg::LPAD, NT = Cfg::NT, NM = Cfg::NM;
+  constexpr int K0 = KB * Cfg::KBS;                                   // first key of this launch's block
+  constexpr int KLEN = KB == Cfg::NB - 1 ? Cfg::LAST : Cfg::KBS;      // its keys
+  static_assert(KB < Cfg::NB, "key block");
   extern __shared__ __align__(1024) uint8_t smem[];
   if (smem_u32(smem) & 1023) __trap();
   uint8_t* sQ = smem;                       // one 128-row query tile
@@ -974,8 +990,8 @@ vit_attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __
         if (t == 0) {
           mbar_wait_relaxed(kv_empty, ((uint32_t)(tau / NT) & 1u) ^ 1u);
           mbar_arrive_expect_tx(kv_full, 2 * Cfg::KV_BYTES);
-          tma_load_2d(sK, &map_k, kv_full, h * TC_HD, b * L);
-          tma_load_2d(sV, &map_v, kv_full, h * TC_HD, b * L);
+          tma_load_2d(sK, &map_k, kv_full, h * TC_HD, b * L + K0);
+          tma_load_2d(sV, &map_v, kv_full, h * TC_HD, b * L + K0);
         }
         mbar_wait_relaxed(qdo_empty, ((uint32_t)tau & 1u) ^ 1u);
         mbar_arrive_expect_tx(qdo_full, 2 * 16384);
@@ -1103,10 +1119,10 @@ vit_attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __
           float ds[8], pp[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            const int j = col8 + e;
-            const float bias2 = j == 0 ? bias_c0 : *(rb - rel_off<W>(j));
+            const int j = col8 + e;              // key inside the block; K0 + j inside the sample
+            const float bias2 = K0 + j == 0 ? bias_c0 : *(rb - rel_off<W>(K0 + j));
             float p = ex2_approx(fmaf(__uint_as_float(vs[g8 * 8 + e]), scale2, bias2) - lse2);
-            if (j >= L || !row_ok) p = 0.f;
+            if (j >= KLEN || !row_ok) p = 0.f;
             pp[e] = p;
             ds[e] = p * (__uint_as_float(vp[g8 * 8 + e]) - dl);
           }
@@ -1130,9 +1146,11 @@ vit_attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __
       tc_fence_after();
       tick(3);
       if (elected) {
-        if (a.ds_dump) {
-          const int nkb = (int)((a.ds_ld < LPAD ? a.ds_ld : LPAD) + 63) >> 6;
-          for (int kb = 0; kb < nkb; ++kb) tma_store_3d(&map_ds, sdS + kb * 16384, kb * 64, t * 128, b * a.H + h);
+        if (a.ds_dump) {   // this block's columns; the last block also covers the zero padding up to ds_ld
+          const int rem = (int)a.ds_ld - K0;
+          const int ncols = KB == Cfg::NB - 1 ? (rem < LPAD ? rem : LPAD) : KLEN;
+          for (int kb = 0; kb < (ncols + 63) >> 6; ++kb)
+            tma_store_3d(&map_ds, sdS + kb * 16384, K0 + kb * 64, t * 128, b * a.H + h);
         }
         tma_store_commit();                      // (possibly empty) group: keeps the group count per tile fixed
       }
@@ -1177,7 +1195,8 @@ vit_attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __
       fence_proxy_async();
       named_bar_sync(1, 512);
       if (elected) {
-        tma_store_3d(&map_dq, sdS, h * TC_HD, t * 128, b);
+        if (KB == 0) tma_store_3d(&map_dq, sdS, h * TC_HD, t * 128, b);
+        else tma_reduce_add_3d(&map_dq, sdS, h * TC_HD, t * 128, b);   // onto the earlier key blocks' launches
         if (t == 0) {
 #pragma unroll
           for (int m = 0; m < NM; ++m) {
@@ -1228,11 +1247,12 @@ static int encode_rows(CUtensorMap* map, const void* base, uint64_t cols, uint64
 
 // [sample, row, 64-column block] view of a bf16 activation: boxes of 128 rows are clipped at the sample's last row
 static int encode_rows_3d(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows_per_sample, uint64_t samples,
-                          uint64_t ld_elems) {
+                          uint64_t ld_elems, uint64_t sample_stride_rows = 0) {
   auto fn = get_tensor_map_encoder();
   if (!fn) return XFM_ERR_NO_DRIVER;
+  if (sample_stride_rows == 0) sample_stride_rows = rows_per_sample;   // > rows_per_sample: a row window of every sample
   cuuint64_t dims[3] = {cols, rows_per_sample, samples};
-  cuuint64_t strides[2] = {ld_elems * 2, rows_per_sample * ld_elems * 2};
+  cuuint64_t strides[2] = {ld_elems * 2, sample_stride_rows * ld_elems * 2};
   cuuint32_t box[3] = {TC_HD, 128, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
@@ -1245,18 +1265,21 @@ static int encode_rows_3d(CUtensorMap* map, const void* base, uint64_t cols, uin
   return 0;
 }
 
-// window sides with an instantiated kernel: 14 (224 px / 16), 12 and 7 (test sizes), 4 (tiny parity model)
-static int window_for(int L) {
-  const int ws[] = {14, 12, 7, 4};
-  for (int w : ws)
-    if (w * w + 1 == L) return w;
+// window sides with an instantiated kernel: 14 (224 px / 16), 12 and 7 (test sizes), 4 (tiny parity model); the fused
+// backward also 24 (384 px / 16: three key blocks per sample)
+static int window_for(int L, bool bwd = false) {
+  const int ws[] = {14, 12, 7, 4, 24};
+  for (int i = 0; i < (bwd ? 5 : 4); ++i)
+    if (ws[i] * ws[i] + 1 == L) return ws[i];
   return 0;
 }
 
-bool vit_attention_tc_supported(const xfm_attn_params* p) {
-  return p->head_dim == TC_HD && p->Lq == p->Lk && window_for(p->Lk) > 0 && !p->kmask && !p->kv_index &&
+bool vit_attention_tc_supported(const xfm_attn_params* p, bool bwd) {
+  const int w = window_for(p->Lk, bwd);
+  if (w == 24 && p->rel_dtable) return false;   // key-blocked shape: fused kernel only (table gradient from the dS dump)
+  return p->head_dim == TC_HD && p->Lq == p->Lk && w > 0 && !p->kmask && !p->kv_index &&
          (!p->bias || p->rel_table) && !(p->dropout_p > 0.f) && (p->Bkv == 0 || p->Bkv == p->B) &&
-         (p->rel_table == nullptr || p->rel_window == window_for(p->Lk)) &&
+         (p->rel_table == nullptr || p->rel_window == w) &&
          ((uintptr_t)p->q & 15) == 0 && ((uintptr_t)p->k & 15) == 0 && ((uintptr_t)p->v & 15) == 0 &&
          ((p->q_stride | p->k_stride | p->v_stride | p->o_stride) & 7) == 0;
 }
@@ -1303,6 +1326,78 @@ static int launch_vit_fwd(const xfm_attn_params* p, cudaStream_t s) {
   return (int)cudaGetLastError();
 }
 
+// One fused kernel for dQ, dK and dV (the table gradient, if any, comes from the dS dump); one launch per key block.
+template <int W, int KB>
+static int launch_vit_bwd_fused_block(const xfm_attn_params* p, const VitBwdArgs& a0, const CUtensorMap& mq1, const CUtensorMap& mdo1,
+                                      const CUtensorMap& mk_l, const CUtensorMap& mv_l, const CUtensorMap& m_dq,
+                                      const CUtensorMap& m_ds, cudaStream_t s) {
+  using FCfg = VitFusedCfg<W>;
+  constexpr int K0 = KB * FCfg::KBS, KLEN = KB == FCfg::NB - 1 ? FCfg::LAST : FCfg::KBS;
+  VitBwdArgs a = a0;
+  const uint64_t cols = (uint64_t)a.H * TC_HD;
+  CUtensorMap m_dk, m_dv;   // this block's key rows of every sample
+  int rc = encode_rows_3d(&m_dk, (const bf16*)p->dk + (int64_t)K0 * p->dk_stride, cols, KLEN, a.B, p->dk_stride, FCfg::L);
+  if (!rc) rc = encode_rows_3d(&m_dv, (const bf16*)p->dv + (int64_t)K0 * p->dv_stride, cols, KLEN, a.B, p->dv_stride, FCfg::L);
+  if (rc) return rc;
+  static bool fattr = false;
+  if (!fattr) {
+    cudaError_t e = cudaFuncSetAttribute(vit_attn_bwd_fused_tc_kernel<W, KB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FCfg::SMEM);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(vit_attn_bwd_fused_tc_kernel<W, KB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FCfg::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    fattr = true;
+  }
+  const int n_items_f = a.B * a.H;
+  const int ctas = n_items_f < num_sms() ? n_items_f : num_sms();
+  a.items_per_cta = (n_items_f + ctas - 1) / ctas;
+  const int grid = (n_items_f + a.items_per_cta - 1) / a.items_per_cta;
+  static const bool prof_on = getenv("XFM_ATTN_PROF") != nullptr;
+  static long long* prof_buf = nullptr;
+  a.prof = nullptr;
+  if (prof_on) {
+    if (!prof_buf) cudaMalloc(&prof_buf, 12 * sizeof(long long));
+    a.prof = prof_buf;
+  }
+  if (prof_on) vit_attn_bwd_fused_tc_kernel<W, KB, true><<<grid, TCF_THREADS, FCfg::SMEM, s>>>(mq1, mdo1, mk_l, mv_l, m_dq, m_dk, m_dv, m_ds, a);
+  else vit_attn_bwd_fused_tc_kernel<W, KB, false><<<grid, TCF_THREADS, FCfg::SMEM, s>>>(mq1, mdo1, mk_l, mv_l, m_dq, m_dk, m_dv, m_ds, a);
+  count_launch();
+  if (prof_on) {  // debugging aid (synchronous)
+    long long h[12];
+    cudaStreamSynchronize(s);
+    cudaMemcpy(h, prof_buf, sizeof(h), cudaMemcpyDeviceToHost);
+    for (int w = 0; w < 2; ++w)
+      fprintf(stderr, "vit_attn_bwd_fused prof %s: setup %lld wait_sd %lld elementwise %lld wait_out %lld drain %lld cycles (%d items/CTA)\n",
+              w ? "warp15" : "warp2", h[w * 6], h[w * 6 + 1], h[w * 6 + 2], h[w * 6 + 3], h[w * 6 + 4], a.items_per_cta);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  if constexpr (KB + 1 < FCfg::NB) return launch_vit_bwd_fused_block<W, KB + 1>(p, a0, mq1, mdo1, mk_l, mv_l, m_dq, m_ds, s);
+  return 0;
+}
+
+template <int W>
+static int launch_vit_bwd_fused(const xfm_attn_params* p, cudaStream_t s) {
+  using FCfg = VitFusedCfg<W>;
+  VitBwdArgs a;
+  a.prof = nullptr;
+  a.lse = p->lse; a.delta = p->delta; a.table = p->rel_table; a.dtable = nullptr;
+  a.ds_dump = (bf16*)p->ds_dump; a.ds_ld = p->ds_ld;
+  a.dq = (bf16*)p->dq; a.dk = (bf16*)p->dk; a.dv = (bf16*)p->dv;
+  a.dq_stride = p->dq_stride; a.dk_stride = p->dk_stride; a.dv_stride = p->dv_stride;
+  a.B = p->B; a.H = p->H; a.scale = p->scale;
+  const uint64_t rows = (uint64_t)a.B * FCfg::L, cols = (uint64_t)a.H * TC_HD;
+  CUtensorMap mq1, mdo1, mk_l, mv_l, m_dq, m_ds;
+  int rc = encode_rows(&mq1, p->q, cols, rows, p->q_stride, 128);
+  if (!rc) rc = encode_rows(&mdo1, p->dout, cols, rows, p->do_stride, 128);
+  if (!rc) rc = encode_rows(&mk_l, p->k, cols, rows, p->k_stride, FCfg::LPAD);
+  if (!rc) rc = encode_rows(&mv_l, p->v, cols, rows, p->v_stride, FCfg::LPAD);
+  if (!rc) rc = encode_rows_3d(&m_dq, p->dq, cols, FCfg::L, a.B, p->dq_stride);
+  m_ds = m_dq;
+  if (!rc && a.ds_dump) rc = encode_rows_3d(&m_ds, a.ds_dump, (uint64_t)a.ds_ld, FCfg::L, (uint64_t)a.B * a.H, (uint64_t)a.ds_ld);
+  if (rc) return rc;
+  return launch_vit_bwd_fused_block<W, 0>(p, a, mq1, mdo1, mk_l, mv_l, m_dq, m_ds, s);
+}
+
 template <int W>
 static int launch_vit_bwd(const xfm_attn_params* p, cudaStream_t s) {
   using Cfg = VitBwdCfg<W>;
@@ -1324,49 +1419,7 @@ static int launch_vit_bwd(const xfm_attn_params* p, cudaStream_t s) {
   if (!rc) rc = encode_rows(&mk_t, p->k, cols, rows, p->k_stride, 128);
   if (!rc) rc = encode_rows(&mv_t, p->v, cols, rows, p->v_stride, 128);
   if (rc) return rc;
-  const int n_items_f = a.B * a.H;
-  if (!a.dtable) {   // table gradient (if any) comes from the dS dump: one fused kernel for dQ, dK and dV
-    using FCfg = VitFusedCfg<W>;
-    CUtensorMap mq1, mdo1, m_dq, m_dk, m_dv, m_ds;
-    rc = encode_rows(&mq1, p->q, cols, rows, p->q_stride, 128);
-    if (!rc) rc = encode_rows(&mdo1, p->dout, cols, rows, p->do_stride, 128);
-    if (!rc) rc = encode_rows_3d(&m_dq, p->dq, cols, Cfg::L, a.B, p->dq_stride);
-    if (!rc) rc = encode_rows_3d(&m_dk, p->dk, cols, Cfg::L, a.B, p->dk_stride);
-    if (!rc) rc = encode_rows_3d(&m_dv, p->dv, cols, Cfg::L, a.B, p->dv_stride);
-    m_ds = m_dq;
-    if (!rc && a.ds_dump) rc = encode_rows_3d(&m_ds, a.ds_dump, (uint64_t)a.ds_ld, Cfg::L, (uint64_t)a.B * a.H, (uint64_t)a.ds_ld);
-    if (rc) return rc;
-    static bool fattr = false;
-    if (!fattr) {
-      cudaError_t e = cudaFuncSetAttribute(vit_attn_bwd_fused_tc_kernel<W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FCfg::SMEM);
-      if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(vit_attn_bwd_fused_tc_kernel<W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FCfg::SMEM);
-      if (e != cudaSuccess) return (int)e;
-      fattr = true;
-    }
-    const int ctas = n_items_f < num_sms() ? n_items_f : num_sms();
-    a.items_per_cta = (n_items_f + ctas - 1) / ctas;
-    const int grid = (n_items_f + a.items_per_cta - 1) / a.items_per_cta;
-    static const bool prof_on = getenv("XFM_ATTN_PROF") != nullptr;
-    static long long* prof_buf = nullptr;
-    a.prof = nullptr;
-    if (prof_on) {
-      if (!prof_buf) cudaMalloc(&prof_buf, 12 * sizeof(long long));
-      a.prof = prof_buf;
-    }
-    if (prof_on) vit_attn_bwd_fused_tc_kernel<W, true><<<grid, TCF_THREADS, FCfg::SMEM, s>>>(mq1, mdo1, mk_l, mv_l, m_dq, m_dk, m_dv, m_ds, a);
-    else vit_attn_bwd_fused_tc_kernel<W, false><<<grid, TCF_THREADS, FCfg::SMEM, s>>>(mq1, mdo1, mk_l, mv_l, m_dq, m_dk, m_dv, m_ds, a);
-    count_launch();
-    if (prof_on) {  // debugging aid (synchronous)
-      long long h[12];
-      cudaStreamSynchronize(s);
-      cudaMemcpy(h, prof_buf, sizeof(h), cudaMemcpyDeviceToHost);
-      for (int w = 0; w < 2; ++w)
-        fprintf(stderr, "vit_attn_bwd_fused prof %s: setup %lld wait_sd %lld elementwise %lld wait_out %lld drain %lld cycles (%d items/CTA)\n",
-                w ? "warp15" : "warp2", h[w * 6], h[w * 6 + 1], h[w * 6 + 2], h[w * 6 + 3], h[w * 6 + 4], a.items_per_cta);
-    }
-    return (int)cudaGetLastError();
-  }
+  if (!a.dtable) return launch_vit_bwd_fused<W>(p, s);   // table gradient (if any) comes from the dS dump
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(vit_attn_bwd_dq_tc_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::DQ_SMEM);
@@ -1393,7 +1446,8 @@ int vit_attention_bwd_tc(const xfm_attn_params* p, cudaStream_t s) {
     set_error("vit attention bwd: operands must be 16-byte aligned with row strides that are multiples of 8");
     return XFM_ERR_BAD_ARG;
   }
-  switch (window_for(p->Lk)) {
+  switch (window_for(p->Lk, true)) {
+    case 24: return launch_vit_bwd_fused<24>(p, s);
     case 14: return launch_vit_bwd<14>(p, s);
     case 12: return launch_vit_bwd<12>(p, s);
     case 7: return launch_vit_bwd<7>(p, s);

@@ -24,7 +24,7 @@ const uint64_t* seed_salt_ptr();
 int gemm_bf16(const xfm_gemm_params* p, cudaStream_t stream);
 int attention_fwd(const xfm_attn_params* p, cudaStream_t s);
 int attention_bwd(const xfm_attn_params* p, cudaStream_t s);
-bool vit_attention_tc_supported(const xfm_attn_params* p);
+bool vit_attention_tc_supported(const xfm_attn_params* p, bool bwd = false);
 int vit_attention_fwd_tc(const xfm_attn_params* p, cudaStream_t s);
 int vit_attention_bwd_tc(const xfm_attn_params* p, cudaStream_t s);
 bool cross_attention_tc_supported(const xfm_attn_params* p);

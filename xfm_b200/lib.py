@@ -283,6 +283,11 @@ def vit_attention_tc_ok(n_tokens):
     return n_tokens in (197, 145, 50, 17)
 
 
+def vit_attention_bwd_tc_ok(n_tokens):
+    """Token counts the fused tcgen05 backward handles: the forward's plus 577 (384 px), processed in three key blocks."""
+    return n_tokens in (197, 145, 50, 17, 577)
+
+
 # ------------------------------------------------------------------------------------------------------
 # thin wrappers over the remaining entry points
 # ------------------------------------------------------------------------------------------------------
