@@ -602,8 +602,8 @@ def test_vit_attention_tcgen05_backward_key_blocks(lib, B, H, with_table):
     assert err < 1e-2 * max(1.0, float(s.grad.abs().max())), ("ds_dump", err)
 
 
-def _cross_case(B, Bkv, H, g, kv_index):
-    Lq, Lk, D = 40, 197, H * 64
+def _cross_case(B, Bkv, H, g, kv_index, Lk=197):
+    Lq, D = 40, H * 64
     q2 = bf(torch.randn(B * Lq, D, generator=g))
     kv2 = bf(torch.randn(Bkv * Lk, 2 * D, generator=g))
     order = torch.argsort(kv_index.long(), stable=True).to(torch.int32)
@@ -687,6 +687,54 @@ def test_cross_attention_tcgen05_backward(lib, B, Bkv, H, pattern):
         assert float((got - want).abs().max()) < 2.5e-2 * max(1.0, float(want.abs().max())), name
     a, b_ = run(True, 0.2), run(False, 0.2)
     for name, x, y in zip(("dq", "dk", "dv"), a, b_):
+        assert torch.isfinite(x).all(), name
+        assert float((x - y).abs().max()) < 3e-2 * max(1.0, float(y.abs().max())), name
+
+
+@pytest.mark.parametrize("B,Bkv,H,pattern", [(8, 2, 2, "even"), (9, 3, 12, "random"), (14, 2, 3, "big_groups")])
+def test_cross_attention_tcgen05_backward_key_blocks(lib, B, Bkv, H, pattern):
+    """384 px: 40 text tokens attending to 577 image tokens.  The fused tcgen05 backward runs one launch per block of 192 keys
+    (dQ accumulated across the launches by TMA reduce-add); the forward is the mma.sync kernel.  Against torch autograd
+    (no dropout) and against the mma.sync backward with the shared dropout mask (p = 0.2: the key index inside the whole
+    row feeds the hash)."""
+    g = G(B * 19 + Bkv)
+    if pattern == "even":
+        kv_index = (torch.arange(B) % Bkv).to(torch.int32)
+    elif pattern == "big_groups":
+        kv_index = torch.tensor([0] * 9 + [1] * 5, dtype=torch.int32)
+    else:
+        kv_index = torch.randint(0, Bkv, (B,), generator=g).to(torch.int32)
+        kv_index[:Bkv] = torch.arange(Bkv, dtype=torch.int32)
+    Lq, Lk, D, q2, kv2, order, offs = _cross_case(B, Bkv, H, g, kv_index, Lk=577)
+    dout = bf(torch.randn(B * Lq, D, generator=g))
+    qf = q2.float().view(B, Lq, H, 64).permute(0, 2, 1, 3).clone().requires_grad_(True)
+    kb = kv2.float()[:, :D].reshape(Bkv, Lk, H, 64).permute(0, 2, 1, 3).clone().requires_grad_(True)
+    vb = kv2.float()[:, D:].reshape(Bkv, Lk, H, 64).permute(0, 2, 1, 3).clone().requires_grad_(True)
+    s = (qf * 0.125) @ kb[kv_index.long()].transpose(-1, -2)
+    ref = torch.softmax(s, -1) @ vb[kv_index.long()]
+    ref.backward(dout.float().view(B, Lq, H, 64).permute(0, 2, 1, 3))
+    want = (qf.grad.permute(0, 2, 1, 3).reshape(B * Lq, D), kb.grad.permute(0, 2, 1, 3).reshape(Bkv * Lk, D),
+            vb.grad.permute(0, 2, 1, 3).reshape(Bkv * Lk, D))
+    qd, kvd, do = q2.cuda(), kv2.cuda(), dout.cuda()
+    kw = dict(Bkv=Bkv, kv_index=kv_index.cuda(), kv_offsets=offs.cuda(), kv_samples=order.cuda())
+
+    def run(tc, p):
+        out, lse = lib.attention_fwd(qd, kvd[:, :D], kvd[:, D:], B, H, Lq, Lk, 0.125, dropout_p=p, dropout_seed=9, allow_tc=tc, **kw)
+        dq = torch.full_like(qd, float("nan"))
+        dkv = torch.full_like(kvd, float("nan"))
+        n0 = lib.launch_count()
+        lib.attention_bwd(do, qd, kvd[:, :D], kvd[:, D:], out, lse, B, H, Lq, Lk, 0.125, dq, dkv[:, :D], dkv[:, D:],
+                          dropout_p=p, dropout_seed=9, allow_tc=tc, **kw)
+        return dq.float().cpu(), dkv[:, :D].float().cpu(), dkv[:, D:].float().cpu(), lib.launch_count() - n0
+
+    dq, dk, dv, n = run(True, 0.0)
+    assert n == 4      # row-delta kernel + three key-block launches
+    for name, got, w in zip(("dq", "dk", "dv"), (dq, dk, dv), want):
+        assert torch.isfinite(got).all(), name
+        assert float((got - w).abs().max()) < 2.5e-2 * max(1.0, float(w.abs().max())), name
+    a, b_ = run(True, 0.2), run(False, 0.2)
+    assert b_[3] == 3  # row-delta + the two mma.sync kernels
+    for name, x, y in zip(("dq", "dk", "dv"), a[:3], b_[:3]):
         assert torch.isfinite(x).all(), name
         assert float((x - y).abs().max()) < 3e-2 * max(1.0, float(y.abs().max())), name
 

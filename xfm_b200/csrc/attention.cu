@@ -618,7 +618,7 @@ int attention_bwd(const xfm_attn_params* p, cudaStream_t s) {
   // dS dump (reduced by the caller) or is accumulated in-kernel into rel_dtable (shared-memory atomics: slower)
   if (p->allow_tc && vit_attention_tc_supported(p, true) && (!p->bias || p->rel_table))
     return vit_attention_bwd_tc(p, s);
-  if (p->allow_tc && cross_attention_tc_supported(p) && !p->ds_dump) return cross_attention_bwd_tc(p, s);
+  if (p->allow_tc && cross_attention_tc_supported(p, true) && !p->ds_dump) return cross_attention_bwd_tc(p, s);
   if (p->allow_tc && self_attention_tc_supported(p) && !p->ds_dump) return self_attention_bwd_tc(p, s);
   const bool big_q = a.Lq > 256, big_k = a.Lk > 256;
   const int rq = big_q ? 128 : 64, rk = big_k ? 128 : 64;

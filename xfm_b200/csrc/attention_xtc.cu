@@ -839,19 +839,24 @@ template <int LQS, int LK>
 struct XFusedCfg {
   static constexpr int GMAX = 3;
   static_assert(GMAX * LQS <= 128, "three samples per query tile");
-  static constexpr int LPAD = (LK + 15) / 16 * 16;
+  // Images with more than 208 tokens (384 px: 577) are processed one block of 192 keys per launch, like the ViT backward
+  // (attention_tc.cu::VitFusedCfg): P = 2^(S - lse) needs no online softmax; dQ accumulates across the launches.
+  static constexpr bool BLOCKED = LK > 208;
+  static constexpr int KBS = BLOCKED ? 192 : LK;
+  static constexpr int NB = BLOCKED ? (LK - 1) / 192 : 1;
+  static constexpr int LAST = LK - (NB - 1) * KBS;
+  static constexpr int LPAD = BLOCKED ? 208 : (LK + 15) / 16 * 16;
   static constexpr int NM = (LPAD + 127) / 128;
   static constexpr int KV_BYTES = LPAD * 128;
   static constexpr int PD_BYTES = 2 * NM * 16384;
   static constexpr int SMEM = 2 * 16384 + 2 * KV_BYTES + 2 * PD_BYTES + 128;
-  static constexpr int SPLIT = ((LPAD / 2 + 15) / 16) * 16;
   static constexpr int TM_DQ = 0, TM_DK = 64, TM_DV = 64 + 64 * NM, TM_END = 64 + 128 * NM;
   static constexpr int UNITS = TM_END / 32;
-  static_assert(2 * LPAD <= 512 && TM_END <= 512, "TMEM");
+  static_assert(LAST <= LPAD && (NB == 1 || KBS % 2 == 0) && 2 * LPAD <= 512 && TM_END <= 512, "TMEM / dropout pairs");
   static_assert(SMEM <= 232448, "shared memory");
 };
 
-template <int LQS, int LK>
+template <int LQS, int LK, int KB>
 __global__ void __launch_bounds__(XTF_THREADS, 1)
 xattn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
                           const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
@@ -860,6 +865,9 @@ xattn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
   using Cfg = XFusedCfg<LQS, LK>;
   static_assert((LQS * 128) % 1024 == 0, "a sample's slot must start on a swizzle-pattern boundary (TMA source of the dQ stores)");
   constexpr int LPAD = Cfg::LPAD, GMAX = Cfg::GMAX, NM = Cfg::NM;
+  constexpr int K0 = KB * Cfg::KBS;                                   // first key of this launch's block
+  constexpr int KLEN = KB == Cfg::NB - 1 ? Cfg::LAST : Cfg::KBS;      // its keys
+  static_assert(KB < Cfg::NB, "key block");
   extern __shared__ __align__(1024) uint8_t smem[];
   if (smem_u32(smem) & 1023) __trap();
   uint8_t* sQ = smem;
@@ -920,8 +928,8 @@ xattn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
         if (id != cur) {
           mbar_wait_relaxed(kv_empty, ip ^ 1);
           mbar_arrive_expect_tx(kv_full, 2 * Cfg::KV_BYTES);
-          tma_load_2d(sK, &map_k, kv_full, u.h * XT_HD, u.r * LK);
-          tma_load_2d(sV, &map_v, kv_full, u.h * XT_HD, u.r * LK);
+          tma_load_2d(sK, &map_k, kv_full, u.h * XT_HD, u.r * LK + K0);
+          tma_load_2d(sV, &map_v, kv_full, u.h * XT_HD, u.r * LK + K0);
           ip ^= 1;
           cur = id;
         }
@@ -1048,12 +1056,12 @@ xattn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
           for (int e = 0; e < 8; e += 2) {
             const int j = c0 + g8 * 8 + e;   // even
             float d0 = 0.f, d1 = 0.f, p0 = 0.f, p1 = 0.f;
-            if (valid && j < LK) {
+            if (valid && j < KLEN) {
               p0 = ex2_approx(fmaf(__uint_as_float(vs[g8 * 8 + e]), scale2, -lse2));
-              p1 = j + 1 < LK ? ex2_approx(fmaf(__uint_as_float(vs[g8 * 8 + e + 1]), scale2, -lse2)) : 0.f;
+              p1 = j + 1 < KLEN ? ex2_approx(fmaf(__uint_as_float(vs[g8 * 8 + e + 1]), scale2, -lse2)) : 0.f;
               float k0 = 1.f, k1 = 1.f;
               if (drop_on) {
-                const uint32_t lo = pb_lo + (uint32_t)(j >> 1);
+                const uint32_t lo = pb_lo + (uint32_t)((K0 + j) >> 1);   // key index inside the whole row (K0 is even)
                 const uint32_t keep = drop_keep_pair(seed_mix, lo, pb_hi + (lo < pb_lo ? 1u : 0u), thr);
                 k0 = (keep & 1u) ? inv_keep : 0.f;
                 k1 = (keep & 2u) ? inv_keep : 0.f;
@@ -1122,8 +1130,10 @@ xattn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
       fence_proxy_async();
       named_bar_sync(1, 512);
       if (elected) {
-        for (int g = 0; g < u.ns; ++g)
-          tma_store_2d(&map_dq, sdS + g * (LQS * 128), u.h * XT_HD, a.kv_samples[u.first + g] * LQS);
+        for (int g = 0; g < u.ns; ++g) {
+          if (KB == 0) tma_store_2d(&map_dq, sdS + g * (LQS * 128), u.h * XT_HD, a.kv_samples[u.first + g] * LQS);
+          else tma_reduce_add_2d(&map_dq, sdS + g * (LQS * 128), u.h * XT_HD, a.kv_samples[u.first + g] * LQS);   // earlier key blocks' launches
+        }
         if (chunk_of_item == 0) {
 #pragma unroll
           for (int m = 0; m < NM; ++m) {
@@ -1172,11 +1182,12 @@ static int xt_encode_rows(CUtensorMap* map, const void* base, uint64_t cols, uin
 
 // [image, key, 64-column block] view of dK / dV: boxes of 128 keys are clipped at the image's last key
 static int xt_encode_rows_3d(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows_per_sample, uint64_t samples,
-                             uint64_t ld_elems) {
+                             uint64_t ld_elems, uint64_t sample_stride_rows = 0) {
   auto fn = get_tensor_map_encoder();
   if (!fn) return XFM_ERR_NO_DRIVER;
+  if (sample_stride_rows == 0) sample_stride_rows = rows_per_sample;   // > rows_per_sample: a row window of every image
   cuuint64_t dims[3] = {cols, rows_per_sample, samples};
-  cuuint64_t strides[2] = {ld_elems * 2, rows_per_sample * ld_elems * 2};
+  cuuint64_t strides[2] = {ld_elems * 2, sample_stride_rows * ld_elems * 2};
   cuuint32_t box[3] = {XT_HD, 128, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
@@ -1190,8 +1201,8 @@ static int xt_encode_rows_3d(CUtensorMap* map, const void* base, uint64_t cols, 
 }
 
 // Instantiated shape: 40 text tokens attending to 197 image tokens (BASELINE configs[1]), up to 6 samples per chunk.
-bool cross_attention_tc_supported(const xfm_attn_params* p) {
-  return p->head_dim == XT_HD && p->Lq == 40 && p->Lk == 197 && !p->kmask && !p->bias && p->kv_offsets && p->kv_samples &&
+bool cross_attention_tc_supported(const xfm_attn_params* p, bool bwd) {
+  return p->head_dim == XT_HD && p->Lq == 40 && (p->Lk == 197 || (bwd && p->Lk == 577 && !p->ds_dump)) && !p->kmask && !p->bias && p->kv_offsets && p->kv_samples &&
          p->Bkv > 0 && ((uintptr_t)p->q & 15) == 0 && ((uintptr_t)p->k & 15) == 0 && ((uintptr_t)p->v & 15) == 0 &&
          ((p->q_stride | p->k_stride | p->v_stride | p->o_stride) & 7) == 0;
 }
@@ -1233,6 +1244,50 @@ int cross_attention_fwd_tc(const xfm_attn_params* p, cudaStream_t s) {
   return (int)cudaGetLastError();
 }
 
+// Fused backward, one launch per key block.
+template <int LQS, int LK, int KB>
+static int xt_launch_fused_block(const xfm_attn_params* p, const XAttnArgs& a, const CUtensorMap& mq, const CUtensorMap& mdo,
+                                 const CUtensorMap& mk_l, const CUtensorMap& mv_l, const CUtensorMap& m_dq, cudaStream_t s) {
+  using FCfg = XFusedCfg<LQS, LK>;
+  constexpr int K0 = KB * FCfg::KBS, KLEN = KB == FCfg::NB - 1 ? FCfg::LAST : FCfg::KBS;
+  auto kf = xattn_bwd_fused_tc_kernel<LQS, LK, KB>;
+  static bool fattr = false;
+  if (!fattr) {
+    cudaError_t e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, FCfg::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    fattr = true;
+  }
+  const uint64_t cols = (uint64_t)a.H * XT_HD;
+  CUtensorMap m_dk, m_dv;   // this block's key rows of every image
+  int rc = xt_encode_rows_3d(&m_dk, (const bf16*)p->dk + (int64_t)K0 * p->dk_stride, cols, KLEN, a.Bkv, p->dk_stride, LK);
+  if (!rc) rc = xt_encode_rows_3d(&m_dv, (const bf16*)p->dv + (int64_t)K0 * p->dv_stride, cols, KLEN, a.Bkv, p->dv_stride, LK);
+  if (rc) return rc;
+  const int n_items_f = a.Bkv * a.H;
+  const int grid_f = (n_items_f + a.items_per_cta - 1) / a.items_per_cta;
+  kf<<<grid_f, XTF_THREADS, FCfg::SMEM, s>>>(mq, mdo, mk_l, mv_l, m_dq, m_dk, m_dv, a);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  if constexpr (KB + 1 < FCfg::NB) return xt_launch_fused_block<LQS, LK, KB + 1>(p, a, mq, mdo, mk_l, mv_l, m_dq, s);
+  return 0;
+}
+
+template <int LQS, int LK>
+static int xt_launch_fused(const xfm_attn_params* p, cudaStream_t s) {
+  using FCfg = XFusedCfg<LQS, LK>;
+  XAttnArgs a;
+  xt_fill(p, a);
+  const uint64_t cols = (uint64_t)a.H * XT_HD;
+  CUtensorMap mq, mdo, mk_l, mv_l, m_dq;
+  int rc = xt_encode_rows(&mq, p->q, cols, (uint64_t)a.B * LQS, p->q_stride, LQS);
+  if (!rc) rc = xt_encode_rows(&mdo, p->dout, cols, (uint64_t)a.B * LQS, p->do_stride, LQS);
+  if (!rc) rc = xt_encode_rows(&mk_l, p->k, cols, (uint64_t)a.Bkv * LK, p->k_stride, FCfg::LPAD);
+  if (!rc) rc = xt_encode_rows(&mv_l, p->v, cols, (uint64_t)a.Bkv * LK, p->v_stride, FCfg::LPAD);
+  if (!rc) rc = xt_encode_rows(&m_dq, p->dq, cols, (uint64_t)a.B * LQS, p->dq_stride, LQS);
+  if (rc) return rc;
+  return xt_launch_fused_block<LQS, LK, 0>(p, a, mq, mdo, mk_l, mv_l, m_dq, s);
+}
+
 int cross_attention_bwd_tc(const xfm_attn_params* p, cudaStream_t s) {
   constexpr int LQS = 40, LK = 197, GMAX = 6;
   using Cfg = XCfg<LQS, LK, GMAX>;
@@ -1242,6 +1297,7 @@ int cross_attention_bwd_tc(const xfm_attn_params* p, cudaStream_t s) {
     set_error("cross attention bwd: operands must be 16-byte aligned with row strides that are multiples of 8");
     return XFM_ERR_BAD_ARG;
   }
+  if (!p->ds_dump) return p->Lk == 577 ? xt_launch_fused<LQS, 577>(p, s) : xt_launch_fused<LQS, LK>(p, s);   // one fused kernel
   XAttnArgs a;
   xt_fill(p, a);
   const uint64_t cols = (uint64_t)a.H * XT_HD;
@@ -1253,26 +1309,6 @@ int cross_attention_bwd_tc(const xfm_attn_params* p, cudaStream_t s) {
   if (!rc) rc = xt_encode_rows(&mk_t, p->k, cols, (uint64_t)a.Bkv * LK, p->k_stride, 128);
   if (!rc) rc = xt_encode_rows(&mv_t, p->v, cols, (uint64_t)a.Bkv * LK, p->v_stride, 128);
   if (rc) return rc;
-  if (!p->ds_dump) {   // one fused kernel for dQ, dK and dV
-    using FCfg = XFusedCfg<LQS, LK>;
-    auto kf = xattn_bwd_fused_tc_kernel<LQS, LK>;
-    static bool fattr = false;
-    if (!fattr) {
-      cudaError_t e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, FCfg::SMEM);
-      if (e != cudaSuccess) return (int)e;
-      fattr = true;
-    }
-    CUtensorMap m_dq, m_dk, m_dv;
-    rc = xt_encode_rows(&m_dq, p->dq, cols, (uint64_t)a.B * LQS, p->dq_stride, LQS);
-    if (!rc) rc = xt_encode_rows_3d(&m_dk, p->dk, cols, LK, a.Bkv, p->dk_stride);
-    if (!rc) rc = xt_encode_rows_3d(&m_dv, p->dv, cols, LK, a.Bkv, p->dv_stride);
-    if (rc) return rc;
-    const int n_items_f = a.Bkv * a.H;
-    const int grid_f = (n_items_f + a.items_per_cta - 1) / a.items_per_cta;
-    kf<<<grid_f, XTF_THREADS, FCfg::SMEM, s>>>(mq, mdo, mk_l, mv_l, m_dq, m_dk, m_dv, a);
-    count_launch();
-    return (int)cudaGetLastError();
-  }
   constexpr int DQ_SMEM = 2 * Cfg::Q_BYTES + 2 * Cfg::KV_BYTES + Cfg::P_BYTES + 128;
   auto kdq = xattn_bwd_dq_tc_kernel<LQS, LK, GMAX>;
   auto kdkv = xattn_bwd_dkv_tc_kernel<LQS, LK, GMAX>;

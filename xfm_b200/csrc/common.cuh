@@ -76,6 +76,11 @@ XFM_DEVINL void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                : "memory");
 }
+XFM_DEVINL void tma_reduce_add_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
 // 3D forms (c0 = contiguous dim, c1 = row inside a sample, c2 = sample): a box that starts inside a sample is clipped at the
 // sample's last row, which a flat 2D [rows, cols] map cannot do.
 XFM_DEVINL void tma_store_3d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2) {

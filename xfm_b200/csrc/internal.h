@@ -27,7 +27,7 @@ int attention_bwd(const xfm_attn_params* p, cudaStream_t s);
 bool vit_attention_tc_supported(const xfm_attn_params* p, bool bwd = false);
 int vit_attention_fwd_tc(const xfm_attn_params* p, cudaStream_t s);
 int vit_attention_bwd_tc(const xfm_attn_params* p, cudaStream_t s);
-bool cross_attention_tc_supported(const xfm_attn_params* p);
+bool cross_attention_tc_supported(const xfm_attn_params* p, bool bwd = false);
 int cross_attention_fwd_tc(const xfm_attn_params* p, cudaStream_t s);
 int cross_attention_bwd_tc(const xfm_attn_params* p, cudaStream_t s);
 bool self_attention_tc_supported(const xfm_attn_params* p);
