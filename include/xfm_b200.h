@@ -131,6 +131,11 @@ typedef struct xfm_attn_params {
   const float* rel_table;
   int32_t rel_window;
   int32_t allow_tc;
+  /* Forward scratch for samples processed in blocks of 192 keys (Lq = Lk = 577, 384 px): bf16 [3, B*Lq, H*64] block-normalised
+   * partial outputs and f32 [3, B, H, Lq] block lse, merged into out / lse by a last kernel.  Without them the 577-token
+   * forward runs on the mma.sync kernel. */
+  void* part_out;
+  float* part_lse;
   float* rel_dtable; /* backward: gradient of rel_table, accumulated (+=) by the tcgen05 dQ kernel; when null or when the
                       * tcgen05 path is not taken the caller derives it from ds_dump */ /* 1: use the tcgen05 / TMEM kernel when the problem fits it (self-attention, Lk <= 208) */
 } xfm_attn_params;

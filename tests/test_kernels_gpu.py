@@ -553,6 +553,41 @@ def test_vit_attention_tcgen05_backward(lib, B, H, ws, with_table):
     assert err < 1e-2 * max(1.0, float(s.grad.abs().max())), ("ds_dump", err)
 
 
+@pytest.mark.parametrize("B,H,with_table", [(2, 3, True), (1, 2, False), (5, 12, True), (32, 12, True)])
+def test_vit_attention_tcgen05_forward_key_blocks(lib, B, H, with_table):
+    """384 px (W = 24, 577 tokens) forward on tcgen05: one launch per block of 192 keys (block-normalised partial output +
+    block lse) and a merge kernel, against an fp32 torch reference and against the mma.sync kernel (output and lse)."""
+    from xfm_b200.encoders import closed_form_rel_index
+    ws = 24
+    g = G(ws * 77 + B)
+    L, D = ws * ws + 1, H * 64
+    qkv = bf(torch.randn(B * L, 3 * D, generator=g) * 0.7)
+    ld = (L + 7) // 8 * 8
+    table, bias = None, None
+    c = qkv.cuda()
+    q, k, v = c[:, :D], c[:, D:2 * D], c[:, 2 * D:]
+    f = c.float().view(B, L, 3, H, 64).permute(2, 0, 3, 1, 4)
+    s = (f[0] * 0.125) @ f[1].transpose(-1, -2)
+    if with_table:
+        T = (2 * ws - 1) ** 2 + 3
+        table = torch.randn(T, H, generator=g).cuda()
+        dense = table[closed_form_rel_index(ws).view(-1).cuda()].view(L, L, H).permute(2, 0, 1)
+        s = s + dense
+        bias = torch.zeros(H, L, ld, device="cuda")
+        bias[..., :L] = dense
+    ref = (torch.softmax(s, -1) @ f[2]).permute(0, 2, 1, 3).reshape(B * L, D)
+    lse_ref = torch.logsumexp(s, -1)
+    n0 = lib.launch_count()
+    out, lse = lib.attention_fwd(q, k, v, B, H, L, L, 0.125, bias=bias, rel_table=table, rel_window=ws if with_table else 0)
+    assert lib.launch_count() - n0 == 4      # three key-block launches + the merge
+    out2, lse2 = lib.attention_fwd(q, k, v, B, H, L, L, 0.125, bias=bias, allow_tc=False)
+    assert torch.isfinite(out.float()).all()
+    assert float((out.float() - ref).abs().max()) < 2e-2
+    assert float((lse - lse_ref).abs().max()) < 2e-3
+    assert float((out.float() - out2.float()).abs().max()) < 2e-2
+    assert float((lse - lse2).abs().max()) < 2e-3
+
+
 @pytest.mark.parametrize("B,H,with_table", [(2, 3, True), (1, 2, False), (5, 12, True)])
 def test_vit_attention_tcgen05_backward_key_blocks(lib, B, H, with_table):
     """384 px (W = 24, 577 tokens): the fused tcgen05 backward runs one launch per block of 192 keys — dQ accumulated across the

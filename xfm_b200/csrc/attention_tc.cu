@@ -35,6 +35,7 @@ struct VitAttnArgs {
   int B, H;
   float scale;
   int items_per_cta;
+  int ctas_per_head;     // key-blocked shapes: a CTA walks items of ONE head
   long long* prof;       // XFM_ATTN_PROF=1: per-phase clock64 totals of CTA 0's first softmax warp (null otherwise)
 };
 
@@ -53,6 +54,33 @@ struct VitCfg {
   static constexpr int SMEM_BYTES = Q_BYTES + 2 * KV_BYTES + 2 * P_BYTES + 2 * TAB_FLOATS * 4 + 128;
   static constexpr int TMEM_O = 2 * LPAD;  // O accumulator columns; S buffers at 0 and LPAD
   static_assert(2 * LPAD + 64 <= 512, "scores of two tiles + one output tile must fit TMEM");
+};
+// Forward configuration.  Up to 208 keys: an item is one (sample, head) with all its query tiles (== VitCfg).  More (384 px,
+// W = 24, L = 577): one launch per block of 192 keys writes a block-normalised partial output and the block's lse; the
+// partials are merged afterwards (merge_parts_kernel).  An item is then a PAIR of query tiles of a (sample, head), a CTA
+// stays on one head (one copy of the bias table, loaded once), and the K / V block is re-loaded per item (L2 hits).
+template <int W>
+struct VitFwdCfg {
+  static constexpr int L = W * W + 1;
+  static constexpr bool BLOCKED = L > 208;
+  static constexpr int KBS = BLOCKED ? 192 : L;
+  static constexpr int NB = BLOCKED ? (L - 1) / 192 : 1;
+  static constexpr int LAST = L - (NB - 1) * KBS;
+  static constexpr int LPAD = BLOCKED ? 208 : (L + 15) / 16 * 16;
+  static constexpr int NT = BLOCKED ? 2 : (L + 127) / 128;          // query tiles per item
+  static constexpr int NTP = BLOCKED ? ((L + 127) / 128 + 1) / 2 : 1;  // items per (sample, head)
+  static constexpr int NKB = (LPAD + 63) / 64;
+  static constexpr int T = (2 * W - 1) * (2 * W - 1) + 3;
+  static constexpr int OFFMAX = (W - 1) * (2 * W - 1) + (W - 1);
+  static constexpr int TAB_FLOATS = (OFFMAX + 1 + T + 7) & ~7;  // [OFFMAX+1 copies of table[T-3]] ++ [table]
+  static constexpr int NTAB = BLOCKED ? 1 : 2;
+  static constexpr int Q_BYTES = NT * 128 * 128;
+  static constexpr int KV_BYTES = LPAD * 128;
+  static constexpr int P_BYTES = NKB * 16384;
+  static constexpr int SMEM_BYTES = Q_BYTES + 2 * KV_BYTES + 2 * P_BYTES + NTAB * TAB_FLOATS * 4 + 128;
+  static constexpr int TMEM_O = 2 * LPAD;  // O accumulator columns; S buffers at 0 and LPAD
+  static_assert(LAST <= LPAD && 2 * LPAD + 64 <= 512, "scores of two tiles + one output tile must fit TMEM");
+  static_assert(SMEM_BYTES <= 232448, "shared memory");
 };
 // column part of the relative-position index (beit2.py:104-108) of key j >= 1
 template <int W>
@@ -91,20 +119,24 @@ XFM_DEVINL void tmem_st_32x32_16(uint32_t taddr, const uint32_t (&r)[32]) {
 XFM_DEVINL void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 
-template <int W>
+template <int W, int KB>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 vit_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                        const __grid_constant__ CUtensorMap map_v, const VitAttnArgs a) {
-  using Cfg = VitCfg<W>;
+  using Cfg = VitFwdCfg<W>;
   constexpr int L = Cfg::L, LPAD = Cfg::LPAD, NT = Cfg::NT;
+  constexpr bool BLOCKED = Cfg::BLOCKED;
+  constexpr int K0 = KB * Cfg::KBS;                                   // first key of this launch's block
+  constexpr int KLEN = KB == Cfg::NB - 1 ? Cfg::LAST : Cfg::KBS;      // its keys
+  static_assert(KB < Cfg::NB, "key block");
   extern __shared__ __align__(1024) uint8_t smem[];
   if (smem_u32(smem) & 1023) __trap();  // SWIZZLE_128B tiles need the 1024-byte alignment the declaration asks for
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + Cfg::Q_BYTES;
   uint8_t* sV = sK + Cfg::KV_BYTES;
   uint8_t* sP = sV + Cfg::KV_BYTES;                          // [2][P_BYTES]
-  float* tabs = (float*)(sP + 2 * Cfg::P_BYTES);             // [2 warpgroups][TAB_FLOATS]
-  uint64_t* bars = (uint64_t*)(tabs + 2 * Cfg::TAB_FLOATS);
+  float* tabs = (float*)(sP + 2 * Cfg::P_BYTES);             // [2 warpgroups][TAB_FLOATS] (key-blocked: one shared copy)
+  uint64_t* bars = (uint64_t*)(tabs + Cfg::NTAB * Cfg::TAB_FLOATS);
   uint64_t *qk_full = bars, *qk_empty = bars + 1, *v_full = bars + 2, *v_empty = bars + 3;
   uint64_t *s_full = bars + 4, *p_full = bars + 6, *o_full = bars + 8, *o_empty = bars + 10;
   uint32_t* tmem_ptr = (uint32_t*)(bars + 11);
@@ -135,23 +167,37 @@ vit_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  const int n_items = a.B * a.H;
-  const int item0 = blockIdx.x * a.items_per_cta;
+  // item -> (head, sample, first query row).  Key-blocked: the CTA's head is fixed, items = (sample, tile pair) of that head.
+  const int h_cta = BLOCKED ? (int)blockIdx.x / a.ctas_per_head : 0;
+  const int n_items = BLOCKED ? a.B * Cfg::NTP : a.B * a.H;
+  const int item0 = (BLOCKED ? (int)blockIdx.x % a.ctas_per_head : (int)blockIdx.x) * a.items_per_cta;
   const int item1 = min(n_items, item0 + a.items_per_cta);
   const int n_tiles = (item1 - item0) * NT;
+  auto decode = [&](int it, int& h, int& b, int& q0) {
+    if (BLOCKED) { h = h_cta; b = it / Cfg::NTP; q0 = (it % Cfg::NTP) * (NT * 128); }
+    else { h = it / a.B; b = it % a.B; q0 = 0; }
+  };
+  if (BLOCKED) {   // the head never changes: one table copy, loaded here by every thread (log2 domain)
+    for (int i = threadIdx.x; i < Cfg::T; i += blockDim.x)
+      tabs[Cfg::OFFMAX + 1 + i] = a.table ? __ldg(a.table + (int64_t)i * a.H + h_cta) * 1.4426950408889634f : 0.f;
+    const float row0 = a.table ? __ldg(a.table + (int64_t)(Cfg::T - 3) * a.H + h_cta) * 1.4426950408889634f : 0.f;
+    for (int i = threadIdx.x; i <= Cfg::OFFMAX; i += blockDim.x) tabs[i] = row0;
+    __syncthreads();
+  }
 
   if (warp == 0) {
     if (lane == 0) {
       for (int it = item0; it < item1; ++it) {
         const uint32_t ph = (uint32_t)(it - item0) & 1u;
-        const int h = it / a.B, b = it % a.B;
+        int h, b, q0;
+        decode(it, h, b, q0);
         mbar_wait_relaxed(qk_empty, ph ^ 1);
         mbar_arrive_expect_tx(qk_full, Cfg::Q_BYTES + Cfg::KV_BYTES);
-        tma_load_2d(sQ, &map_q, qk_full, h * TC_HD, b * L);
-        tma_load_2d(sK, &map_k, qk_full, h * TC_HD, b * L);
+        tma_load_2d(sQ, &map_q, qk_full, h * TC_HD, b * L + q0);
+        tma_load_2d(sK, &map_k, qk_full, h * TC_HD, b * L + K0);
         mbar_wait_relaxed(v_empty, ph ^ 1);
         mbar_arrive_expect_tx(v_full, Cfg::KV_BYTES);
-        tma_load_2d(sV, &map_v, v_full, h * TC_HD, b * L);
+        tma_load_2d(sV, &map_v, v_full, h * TC_HD, b * L + K0);
       }
     }
   } else if (warp == 1) {
@@ -196,18 +242,19 @@ vit_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     const int wgt = (threadIdx.x - 64) & 127;  // 0..127 inside the warpgroup
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
     const uint32_t t_s = lane_base + (uint32_t)(wg * LPAD), t_o = lane_base + (uint32_t)Cfg::TMEM_O;
-    float* tab = tabs + wg * Cfg::TAB_FLOATS;  // this warpgroup's copy: [0, OFFMAX] = table[T-3], then the table
+    float* tab = tabs + (BLOCKED ? 0 : wg) * Cfg::TAB_FLOATS;  // this warpgroup's copy: [0, OFFMAX] = table[T-3], then the table
     const float scale2 = a.scale * 1.4426950408889634f;
     uint8_t* myP = sP + wg * Cfg::P_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
     const int sw = r & 7;
-    int cur_h = -1;
+    int cur_h = BLOCKED ? h_cta : -1;
     float bias_c0 = 0.f;
     long long pc[6] = {0, 0, 0, 0, 0, 0}, pt = clock64();
     auto tick = [&](int i) { if (a.prof) { const long long n = clock64(); pc[i] += n - pt; pt = n; } };
     for (int tau = wg; tau < n_tiles; tau += 2) {
       const int item = item0 + tau / NT, t = tau % NT;
-      const int h = item / a.B, b = item % a.B;
-      const int qi = t * 128 + r;              // query index inside the sample
+      int h, b, q0;
+      decode(item, h, b, q0);
+      const int qi = q0 + t * 128 + r;         // query index inside the sample
       if (h != cur_h) {                         // (re)load this head's table column (log2 domain)
         named_bar_sync(1 + wg, 128);
         for (int i = wgt; i < Cfg::T; i += 128)
@@ -234,7 +281,7 @@ vit_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
       tick(1);
       // a warp whose 32 rows all lie beyond the sample's last query (rows 224..255 of the second tile at L = 197) has nothing
       // to compute: its P rows only feed output rows that are never stored.  It still takes part in every barrier.
-      const bool warp_live = t * 128 + quad * 32 < L;
+      const bool warp_live = q0 + t * 128 + quad * 32 < L;
       float m = 0.f, sum = 1.f;
       if (warp_live) {
       // ---- pass 1: logits (log2 domain) back into TMEM, row maximum
@@ -250,10 +297,10 @@ vit_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         for (int e = 0; e < 32; ++e) {
           const int j = c0 + e;
           if (j < LPAD) {
-            float l;
-            if (j >= L) l = -INFINITY;
-            else if (j == 0) l = fmaf(__uint_as_float(v[e]), scale2, bias_c0);
-            else l = fmaf(__uint_as_float(v[e]), scale2, *(rb - rel_off<W>(j)));
+            float l;                               // j: key inside the block, K0 + j inside the sample
+            if (j >= KLEN) l = -INFINITY;
+            else if (K0 + j == 0) l = fmaf(__uint_as_float(v[e]), scale2, bias_c0);
+            else l = fmaf(__uint_as_float(v[e]), scale2, *(rb - rel_off<W>(K0 + j)));
             m4[e & 3] = fmaxf(m4[e & 3], l);
             v[e] = __float_as_uint(l);
           }
@@ -335,7 +382,7 @@ vit_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int r2 = quad * 32 + it * 4 + (lane >> 3);
-          const int q2 = t * 128 + r2;
+          const int q2 = q0 + t * 128 + r2;
           const uint4 u = *(const uint4*)(sP + wg * Cfg::P_BYTES + (r2 >> 3) * 1024 + (r2 & 7) * 128 + ((ch ^ (r2 & 7)) << 4));
           if (q2 < L) *(uint4*)(a.out + ((int64_t)b * L + q2) * a.o_stride + h * TC_HD + ch * 8) = u;
         }
@@ -1275,7 +1322,7 @@ static int window_for(int L, bool bwd = false) {
 }
 
 bool vit_attention_tc_supported(const xfm_attn_params* p, bool bwd) {
-  const int w = window_for(p->Lk, bwd);
+  const int w = window_for(p->Lk, bwd || (p->part_out && p->part_lse));   // forward at 24: needs the key-block scratch
   if (w == 24 && p->rel_dtable) return false;   // key-blocked shape: fused kernel only (table gradient from the dS dump)
   return p->head_dim == TC_HD && p->Lq == p->Lk && w > 0 && !p->kmask && !p->kv_index &&
          (!p->bias || p->rel_table) && !(p->dropout_p > 0.f) && (p->Bkv == 0 || p->Bkv == p->B) &&
@@ -1284,28 +1331,74 @@ bool vit_attention_tc_supported(const xfm_attn_params* p, bool bwd) {
          ((p->q_stride | p->k_stride | p->v_stride | p->o_stride) & 7) == 0;
 }
 
-template <int W>
-static int launch_vit_fwd(const xfm_attn_params* p, cudaStream_t s) {
-  using Cfg = VitCfg<W>;
-  VitAttnArgs a;
-  a.out = (bf16*)p->out; a.o_stride = p->o_stride; a.lse = p->lse; a.table = p->rel_table;
-  a.B = p->B; a.H = p->H; a.scale = p->scale;
-  const uint64_t rows = (uint64_t)a.B * Cfg::L, cols = (uint64_t)a.H * TC_HD;
-  CUtensorMap mq, mk, mv;
-  int rc = encode_rows(&mq, p->q, cols, rows, p->q_stride, Cfg::NT * 128);
-  if (!rc) rc = encode_rows(&mk, p->k, cols, rows, p->k_stride, Cfg::LPAD);
-  if (!rc) rc = encode_rows(&mv, p->v, cols, rows, p->v_stride, Cfg::LPAD);
-  if (rc) return rc;
+// Merge of the key blocks' partial results: out = sum_k w_k O_k with w_k = exp(lse_k - lse), lse = log sum_k exp(lse_k).
+// One CTA per token row, one thread per 8 output columns (a head is 8 threads).
+template <int NB>
+__global__ void merge_parts_kernel(const bf16* __restrict__ part_out, const float* __restrict__ part_lse, bf16* __restrict__ out,
+                                   int64_t o_stride, float* __restrict__ lse, int B, int H, int L) {
+  const int row = blockIdx.x, c = threadIdx.x, h = c >> 3;
+  const int b = row / L, q = row % L;
+  const int64_t rows = (int64_t)B * L, lrow = ((int64_t)b * H + h) * L + q, lse_n = (int64_t)B * H * L;
+  float l[NB], m = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < NB; ++k) {
+    l[k] = __ldg(part_lse + k * lse_n + lrow);
+    m = fmaxf(m, l[k]);
+  }
+  float wsum = 0.f;
+#pragma unroll
+  for (int k = 0; k < NB; ++k) {
+    l[k] = __expf(l[k] - m);
+    wsum += l[k];
+  }
+  const float inv = 1.0f / wsum;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < NB; ++k) {
+    const uint4 u = *(const uint4*)(part_out + (k * rows + row) * (int64_t)(H * TC_HD) + c * 8);
+    const __nv_bfloat162* p2 = (const __nv_bfloat162*)&u;
+    const float w = l[k] * inv;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __bfloat1622float2(p2[e]);
+      acc[2 * e] = fmaf(w, f.x, acc[2 * e]);
+      acc[2 * e + 1] = fmaf(w, f.y, acc[2 * e + 1]);
+    }
+  }
+  st_bf16x8((uint8_t*)(out + row * o_stride + c * 8), acc);
+  if (lse && (c & 7) == 0) lse[lrow] = m + __logf(wsum);
+}
+
+template <int W, int KB>
+static int launch_vit_fwd_block(const xfm_attn_params* p, const VitAttnArgs& a0, const CUtensorMap& mq, const CUtensorMap& mk,
+                                const CUtensorMap& mv, cudaStream_t s) {
+  using Cfg = VitFwdCfg<W>;
+  VitAttnArgs a = a0;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(vit_attn_fwd_tc_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(vit_attn_fwd_tc_kernel<W, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     attr = true;
   }
-  const int n_items = a.B * a.H;
-  const int ctas = n_items < num_sms() ? n_items : num_sms();
-  a.items_per_cta = (n_items + ctas - 1) / ctas;
-  const int grid = (n_items + a.items_per_cta - 1) / a.items_per_cta;
+  int grid;
+  if (Cfg::BLOCKED) {   // a CTA stays on one head; this block's partial output / lse
+    const int64_t rows = (int64_t)a.B * Cfg::L;
+    a.out = (bf16*)p->part_out + KB * rows * (int64_t)(a.H * TC_HD);
+    a.o_stride = (int64_t)a.H * TC_HD;
+    a.lse = p->part_lse + KB * (int64_t)a.B * a.H * Cfg::L;
+    const int per_head = a.B * Cfg::NTP;
+    int cph = num_sms() / a.H;
+    cph = cph < 1 ? 1 : (cph > per_head ? per_head : cph);
+    a.items_per_cta = (per_head + cph - 1) / cph;
+    a.ctas_per_head = (per_head + a.items_per_cta - 1) / a.items_per_cta;
+    grid = a.ctas_per_head * a.H;
+  } else {
+    const int n_items = a.B * a.H;
+    const int ctas = n_items < num_sms() ? n_items : num_sms();
+    a.items_per_cta = (n_items + ctas - 1) / ctas;
+    a.ctas_per_head = 0;
+    grid = (n_items + a.items_per_cta - 1) / a.items_per_cta;
+  }
   static const bool prof_on = getenv("XFM_ATTN_PROF") != nullptr;
   static long long* prof_buf = nullptr;
   a.prof = nullptr;
@@ -1313,7 +1406,7 @@ static int launch_vit_fwd(const xfm_attn_params* p, cudaStream_t s) {
     if (!prof_buf) cudaMalloc(&prof_buf, 12 * sizeof(long long));
     a.prof = prof_buf;
   }
-  vit_attn_fwd_tc_kernel<W><<<grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(mq, mk, mv, a);
+  vit_attn_fwd_tc_kernel<W, KB><<<grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(mq, mk, mv, a);
   count_launch();
   if (prof_on) {  // debugging aid: synchronous, prints the phase totals of CTA 0 (warp 2 = parity-0 rows 0..31, warp 9 = parity-1 rows 96..127)
     long long h[12];
@@ -1323,6 +1416,33 @@ static int launch_vit_fwd(const xfm_attn_params* p, cudaStream_t s) {
       fprintf(stderr, "vit_attn_fwd prof %s: setup %lld wait_s %lld pass1 %lld pass2 %lld wait_o %lld epilogue %lld cycles (%d items/CTA)\n",
               w ? "warp9" : "warp2", h[w * 6], h[w * 6 + 1], h[w * 6 + 2], h[w * 6 + 3], h[w * 6 + 4], h[w * 6 + 5], a.items_per_cta);
   }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  if constexpr (KB + 1 < Cfg::NB) return launch_vit_fwd_block<W, KB + 1>(p, a0, mq, mk, mv, s);
+  return 0;
+}
+
+template <int W>
+static int launch_vit_fwd(const xfm_attn_params* p, cudaStream_t s) {
+  using Cfg = VitFwdCfg<W>;
+  VitAttnArgs a;
+  a.out = (bf16*)p->out; a.o_stride = p->o_stride; a.lse = p->lse; a.table = p->rel_table;
+  a.B = p->B; a.H = p->H; a.scale = p->scale;
+  if (Cfg::BLOCKED && (!p->part_out || !p->part_lse || a.H * 8 > 1024)) {
+    set_error("vit attention fwd: %d tokens need the part_out / part_lse scratch buffers", Cfg::L);
+    return XFM_ERR_BAD_ARG;
+  }
+  const uint64_t rows = (uint64_t)a.B * Cfg::L, cols = (uint64_t)a.H * TC_HD;
+  CUtensorMap mq, mk, mv;
+  int rc = encode_rows(&mq, p->q, cols, rows, p->q_stride, Cfg::NT * 128);
+  if (!rc) rc = encode_rows(&mk, p->k, cols, rows, p->k_stride, Cfg::LPAD);
+  if (!rc) rc = encode_rows(&mv, p->v, cols, rows, p->v_stride, Cfg::LPAD);
+  if (rc) return rc;
+  rc = launch_vit_fwd_block<W, 0>(p, a, mq, mk, mv, s);
+  if (rc || !Cfg::BLOCKED) return rc;
+  merge_parts_kernel<Cfg::NB><<<(unsigned)rows, a.H * 8, 0, s>>>((const bf16*)p->part_out, p->part_lse, (bf16*)p->out, p->o_stride,
+                                                               p->lse, a.B, a.H, Cfg::L);
+  count_launch();
   return (int)cudaGetLastError();
 }
 
@@ -1458,7 +1578,8 @@ int vit_attention_bwd_tc(const xfm_attn_params* p, cudaStream_t s) {
 }
 
 int vit_attention_fwd_tc(const xfm_attn_params* p, cudaStream_t s) {
-  switch (window_for(p->Lk)) {
+  switch (window_for(p->Lk, true)) {
+    case 24: return launch_vit_fwd<24>(p, s);
     case 14: return launch_vit_fwd<14>(p, s);
     case 12: return launch_vit_fwd<12>(p, s);
     case 7: return launch_vit_fwd<7>(p, s);

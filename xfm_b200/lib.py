@@ -194,7 +194,8 @@ class AttnParams(C.Structure):
         ("do_stride", C.c_int64), ("dq_stride", C.c_int64), ("dk_stride", C.c_int64), ("dv_stride", C.c_int64),
         ("ds_ld", C.c_int64),
         ("kv_offsets", C.c_void_p), ("kv_samples", C.c_void_p),
-        ("rel_table", C.c_void_p), ("rel_window", C.c_int32), ("allow_tc", C.c_int32), ("rel_dtable", C.c_void_p),
+        ("rel_table", C.c_void_p), ("rel_window", C.c_int32), ("allow_tc", C.c_int32),
+        ("part_out", C.c_void_p), ("part_lse", C.c_void_p), ("rel_dtable", C.c_void_p),
     ]
 
 
@@ -235,6 +236,13 @@ def attention_fwd(q, k, v, B, H, Lq, Lk, scale, *, Bkv=None, bias=None, kmask=No
         assert rel_table.dtype == torch.float32 and rel_table.is_contiguous() and rel_table.shape[1] == H
         assert rel_table.shape[0] == (2 * rel_window - 1) ** 2 + 3
         p.rel_table, p.rel_window = rel_table.data_ptr(), rel_window
+    parts = None
+    if (allow_tc and Lq == Lk == 577 and kmask is None and kv_index is None and dropout_p == 0.0
+            and (bias is None or rel_table is not None)):
+        # 384 px self-attention on tcgen05: one launch per block of 192 keys + a merge; scratch for the partial results
+        parts = (torch.empty((3, B * Lq, H * 64), dtype=torch.bfloat16, device=q.device),
+                 torch.empty((3, B, H, Lq), dtype=torch.float32, device=q.device))
+        p.part_out, p.part_lse = parts[0].data_ptr(), parts[1].data_ptr()
     if kv_samples is not None:  # CSR inverse of kv_index: lets the tcgen05 cross-attention kernel stack the samples of an image
         assert kv_offsets.dtype == torch.int32 and kv_samples.dtype == torch.int32
         assert kv_offsets.numel() == Bkv + 1 and kv_samples.numel() == B
