@@ -647,10 +647,12 @@ def _cross_case(B, Bkv, H, g, kv_index, Lk=197):
     return Lq, Lk, D, q2, kv2, order, offs
 
 
+@pytest.mark.parametrize("Lk_", [197, 577])
 @pytest.mark.parametrize("B,Bkv,H,pattern", [(8, 2, 2, "even"), (24, 6, 12, "random"), (14, 2, 3, "big_groups"), (6, 6, 2, "identity")])
-def test_cross_attention_tcgen05_forward(lib, B, Bkv, H, pattern):
+def test_cross_attention_tcgen05_forward(lib, B, Bkv, H, pattern, Lk_):
     """tcgen05 cross-attention (attention_xtc.cu): samples stacked per image (1..>GMAX samples per image) against torch and
-    against the mma.sync kernel; with dropout the two kernels must produce the same mask (same (seed, index) hash)."""
+    against the mma.sync kernel; with dropout the two kernels must produce the same mask (same (seed, index) hash).  577 image
+    tokens (384 px): one launch per block of 192 keys + the merge of the block-normalised partials."""
     g = G(B * 31 + Bkv)
     if pattern == "even":
         kv_index = (torch.arange(B) % Bkv).to(torch.int32)
@@ -661,7 +663,7 @@ def test_cross_attention_tcgen05_forward(lib, B, Bkv, H, pattern):
     else:
         kv_index = torch.randint(0, Bkv, (B,), generator=g).to(torch.int32)
         kv_index[:Bkv] = torch.arange(Bkv, dtype=torch.int32)
-    Lq, Lk, D, q2, kv2, order, offs = _cross_case(B, Bkv, H, g, kv_index)
+    Lq, Lk, D, q2, kv2, order, offs = _cross_case(B, Bkv, H, g, kv_index, Lk=Lk_)
     qf = q2.float().view(B, Lq, H, 64).permute(0, 2, 1, 3)
     kf = kv2.float()[:, :D].reshape(Bkv, Lk, H, 64).permute(0, 2, 1, 3)[kv_index.long()]
     vf = kv2.float()[:, D:].reshape(Bkv, Lk, H, 64).permute(0, 2, 1, 3)[kv_index.long()]
@@ -669,7 +671,9 @@ def test_cross_attention_tcgen05_forward(lib, B, Bkv, H, pattern):
     ref = (torch.softmax(s, -1) @ vf).permute(0, 2, 1, 3).reshape(B * Lq, D)
     qd, kvd = q2.cuda(), kv2.cuda()
     kw = dict(Bkv=Bkv, kv_index=kv_index.cuda(), kv_offsets=offs.cuda(), kv_samples=order.cuda())
+    n0 = lib.launch_count()
     out, lse = lib.attention_fwd(qd, kvd[:, :D], kvd[:, D:], B, H, Lq, Lk, 0.125, **kw)
+    assert lib.launch_count() - n0 == (4 if Lk == 577 else 1)
     out2, lse2 = lib.attention_fwd(qd, kvd[:, :D], kvd[:, D:], B, H, Lq, Lk, 0.125, allow_tc=False, **kw)
     assert float((out.float().cpu() - ref).abs().max()) < 2e-2
     assert float((lse.cpu() - torch.logsumexp(s, -1)).abs().max()) < 2e-3

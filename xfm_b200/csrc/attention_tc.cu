@@ -1369,6 +1369,17 @@ __global__ void merge_parts_kernel(const bf16* __restrict__ part_out, const floa
   if (lse && (c & 7) == 0) lse[lrow] = m + __logf(wsum);
 }
 
+int launch_merge_parts(int nb, const void* part_out, const float* part_lse, void* out, int64_t o_stride, float* lse, int B, int H,
+                       int L, cudaStream_t s) {
+  if (nb != 3 || H * 8 > 1024) {
+    set_error("merge of key-block partials: %d blocks / %d heads not instantiated", nb, H);
+    return XFM_ERR_BAD_ARG;
+  }
+  merge_parts_kernel<3><<<(unsigned)(B * L), H * 8, 0, s>>>((const bf16*)part_out, part_lse, (bf16*)out, o_stride, lse, B, H, L);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
 template <int W, int KB>
 static int launch_vit_fwd_block(const xfm_attn_params* p, const VitAttnArgs& a0, const CUtensorMap& mq, const CUtensorMap& mk,
                                 const CUtensorMap& mv, cudaStream_t s) {
@@ -1440,10 +1451,7 @@ static int launch_vit_fwd(const xfm_attn_params* p, cudaStream_t s) {
   if (rc) return rc;
   rc = launch_vit_fwd_block<W, 0>(p, a, mq, mk, mv, s);
   if (rc || !Cfg::BLOCKED) return rc;
-  merge_parts_kernel<Cfg::NB><<<(unsigned)rows, a.H * 8, 0, s>>>((const bf16*)p->part_out, p->part_lse, (bf16*)p->out, p->o_stride,
-                                                               p->lse, a.B, a.H, Cfg::L);
-  count_launch();
-  return (int)cudaGetLastError();
+  return launch_merge_parts(Cfg::NB, p->part_out, p->part_lse, p->out, p->o_stride, p->lse, a.B, a.H, Cfg::L, s);
 }
 
 // One fused kernel for dQ, dK and dV (the table gradient, if any, comes from the dS dump); one launch per key block.

@@ -41,7 +41,14 @@ struct XCfg {
   static constexpr int PER_TILE = (GMAX + 1) / 2;            // sample slots per 128-row query tile
   static_assert(PER_TILE * LQS <= 128, "slots of one tile must fit 128 rows");
   static_assert((LQS * 128) % 1024 == 0, "a sample's rows must start on a swizzle-atom boundary (LQS multiple of 8)");
-  static constexpr int LPAD = (LK + 15) / 16 * 16;
+  // more than 208 keys (384 px: 577): one launch per block of 192 keys, partial results merged afterwards (forward) — see
+  // attention_tc.cu::VitFwdCfg
+  static constexpr bool BLOCKED = LK > 208;
+  static constexpr int KBS = BLOCKED ? 192 : LK;
+  static constexpr int NB = BLOCKED ? (LK - 1) / 192 : 1;
+  static constexpr int LAST = LK - (NB - 1) * KBS;
+  static constexpr int LPAD = BLOCKED ? 208 : (LK + 15) / 16 * 16;
+  static_assert(LAST <= LPAD && (NB == 1 || KBS % 2 == 0), "key blocks");
   static constexpr int NKB = (LPAD + 63) / 64;
   static constexpr int Q_BYTES = 2 * 128 * 128;
   static constexpr int KV_BYTES = LPAD * 128;
@@ -96,12 +103,15 @@ struct XWalker {
   }
 };
 
-template <int LQS, int LK, int GMAX>
+template <int LQS, int LK, int GMAX, int KB>
 __global__ void __launch_bounds__(XT_THREADS, 1)
 xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                     const __grid_constant__ CUtensorMap map_v, const XAttnArgs a) {
   using Cfg = XCfg<LQS, LK, GMAX>;
   constexpr int LPAD = Cfg::LPAD, PER_TILE = Cfg::PER_TILE;
+  constexpr int K0 = KB * Cfg::KBS;                                   // first key of this launch's block
+  constexpr int KLEN = KB == Cfg::NB - 1 ? Cfg::LAST : Cfg::KBS;      // its keys
+  static_assert(KB < Cfg::NB, "key block");
   extern __shared__ __align__(1024) uint8_t smem[];
   if (smem_u32(smem) & 1023) __trap();
   uint8_t* sQ = smem;
@@ -157,10 +167,10 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
           const int b = a.kv_samples[u.first + g];
           tma_load_2d(sQ + (g & 1) * 16384 + (g >> 1) * (LQS * 128), &map_q, qk_full, u.h * XT_HD, b * LQS);
         }
-        tma_load_2d(sK, &map_k, qk_full, u.h * XT_HD, u.r * LK);
+        tma_load_2d(sK, &map_k, qk_full, u.h * XT_HD, u.r * LK + K0);
         mbar_wait_relaxed(v_empty, ph ^ 1);
         mbar_arrive_expect_tx(v_full, Cfg::KV_BYTES);
-        tma_load_2d(sV, &map_v, v_full, u.h * XT_HD, u.r * LK);
+        tma_load_2d(sV, &map_v, v_full, u.h * XT_HD, u.r * LK + K0);
         ph ^= 1;
       }
     }
@@ -239,7 +249,7 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
           tmem_ld_wait();
 #pragma unroll
           for (int e = 0; e < 32; ++e)
-            if (c0 + e < LK) m4[e & 3] = fmaxf(m4[e & 3], __uint_as_float(v[e]));
+            if (c0 + e < KLEN) m4[e & 3] = fmaxf(m4[e & 3], __uint_as_float(v[e]));
         }
         m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * scale2;   // scale2 > 0: max commutes with the scaling
       }
@@ -260,13 +270,13 @@ xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             for (int e = 0; e < 8; e += 2) {
               const int j = c0 + g8 * 8 + e;   // even
               float p0 = 0.f, p1 = 0.f;
-              if (valid && j < LK) {
+              if (valid && j < KLEN) {
                 p0 = ex2_approx(fmaf(__uint_as_float(v[g8 * 8 + e]), scale2, -m));
-                if (j + 1 < LK) p1 = ex2_approx(fmaf(__uint_as_float(v[g8 * 8 + e + 1]), scale2, -m));
+                if (j + 1 < KLEN) p1 = ex2_approx(fmaf(__uint_as_float(v[g8 * 8 + e + 1]), scale2, -m));
                 s4[e & 3] += p0;
                 s4[(e + 1) & 3] += p1;
                 if (drop_on) {
-                  const uint32_t lo = pb_lo + (uint32_t)(j >> 1);
+                  const uint32_t lo = pb_lo + (uint32_t)((K0 + j) >> 1);   // key index inside the whole row
                   const uint32_t keep = drop_keep_pair(seed_mix, lo, pb_hi + (lo < pb_lo ? 1u : 0u), thr);
                   p0 = (keep & 1u) ? p0 * inv_keep : 0.f;
                   p1 = (keep & 2u) ? p1 * inv_keep : 0.f;
@@ -1202,7 +1212,7 @@ static int xt_encode_rows_3d(CUtensorMap* map, const void* base, uint64_t cols, 
 
 // Instantiated shape: 40 text tokens attending to 197 image tokens (BASELINE configs[1]), up to 6 samples per chunk.
 bool cross_attention_tc_supported(const xfm_attn_params* p, bool bwd) {
-  return p->head_dim == XT_HD && p->Lq == 40 && (p->Lk == 197 || (bwd && p->Lk == 577 && !p->ds_dump)) && !p->kmask && !p->bias && p->kv_offsets && p->kv_samples &&
+  return p->head_dim == XT_HD && p->Lq == 40 && (p->Lk == 197 || (p->Lk == 577 && (bwd ? !p->ds_dump : (p->part_out && p->part_lse)))) && !p->kmask && !p->bias && p->kv_offsets && p->kv_samples &&
          p->Bkv > 0 && ((uintptr_t)p->q & 15) == 0 && ((uintptr_t)p->k & 15) == 0 && ((uintptr_t)p->v & 15) == 0 &&
          ((p->q_stride | p->k_stride | p->v_stride | p->o_stride) & 7) == 0;
 }
@@ -1219,18 +1229,17 @@ static void xt_fill(const xfm_attn_params* p, XAttnArgs& a) {
   a.items_per_cta = (n_items + ctas - 1) / ctas;
 }
 
-int cross_attention_fwd_tc(const xfm_attn_params* p, cudaStream_t s) {
-  constexpr int LQS = 40, LK = 197, GMAX = 6;
+template <int LQS, int LK, int GMAX, int KB>
+static int xt_launch_fwd_block(const xfm_attn_params* p, const XAttnArgs& a0, const CUtensorMap& mq, const CUtensorMap& mk,
+                               const CUtensorMap& mv, cudaStream_t s) {
   using Cfg = XCfg<LQS, LK, GMAX>;
-  XAttnArgs a;
-  xt_fill(p, a);
-  const uint64_t cols = (uint64_t)a.H * XT_HD;
-  CUtensorMap mq, mk, mv;
-  int rc = xt_encode_rows(&mq, p->q, cols, (uint64_t)a.B * LQS, p->q_stride, LQS);
-  if (!rc) rc = xt_encode_rows(&mk, p->k, cols, (uint64_t)a.Bkv * LK, p->k_stride, Cfg::LPAD);
-  if (!rc) rc = xt_encode_rows(&mv, p->v, cols, (uint64_t)a.Bkv * LK, p->v_stride, Cfg::LPAD);
-  if (rc) return rc;
-  auto kern = xattn_fwd_tc_kernel<LQS, LK, GMAX>;
+  XAttnArgs a = a0;
+  if (Cfg::BLOCKED) {   // this block's partial output / lse
+    a.out = (bf16*)p->part_out + KB * (int64_t)a.B * LQS * (a.H * XT_HD);
+    a.o_stride = (int64_t)a.H * XT_HD;
+    a.lse = p->part_lse + KB * (int64_t)a.B * a.H * LQS;
+  }
+  auto kern = xattn_fwd_tc_kernel<LQS, LK, GMAX, KB>;
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_FWD);
@@ -1241,7 +1250,30 @@ int cross_attention_fwd_tc(const xfm_attn_params* p, cudaStream_t s) {
   const int grid = (n_items + a.items_per_cta - 1) / a.items_per_cta;
   kern<<<grid, XT_THREADS, Cfg::SMEM_FWD, s>>>(mq, mk, mv, a);
   count_launch();
-  return (int)cudaGetLastError();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  if constexpr (KB + 1 < Cfg::NB) return xt_launch_fwd_block<LQS, LK, GMAX, KB + 1>(p, a0, mq, mk, mv, s);
+  return 0;
+}
+
+template <int LQS, int LK, int GMAX>
+static int xt_launch_fwd(const xfm_attn_params* p, cudaStream_t s) {
+  using Cfg = XCfg<LQS, LK, GMAX>;
+  XAttnArgs a;
+  xt_fill(p, a);
+  const uint64_t cols = (uint64_t)a.H * XT_HD;
+  CUtensorMap mq, mk, mv;
+  int rc = xt_encode_rows(&mq, p->q, cols, (uint64_t)a.B * LQS, p->q_stride, LQS);
+  if (!rc) rc = xt_encode_rows(&mk, p->k, cols, (uint64_t)a.Bkv * LK, p->k_stride, Cfg::LPAD);
+  if (!rc) rc = xt_encode_rows(&mv, p->v, cols, (uint64_t)a.Bkv * LK, p->v_stride, Cfg::LPAD);
+  if (rc) return rc;
+  rc = xt_launch_fwd_block<LQS, LK, GMAX, 0>(p, a, mq, mk, mv, s);
+  if (rc || !Cfg::BLOCKED) return rc;
+  return launch_merge_parts(Cfg::NB, p->part_out, p->part_lse, p->out, p->o_stride, p->lse, a.B, a.H, LQS, s);
+}
+
+int cross_attention_fwd_tc(const xfm_attn_params* p, cudaStream_t s) {
+  return p->Lk == 577 ? xt_launch_fwd<40, 577, 6>(p, s) : xt_launch_fwd<40, 197, 6>(p, s);
 }
 
 // Fused backward, one launch per key block.

@@ -27,6 +27,9 @@ int attention_bwd(const xfm_attn_params* p, cudaStream_t s);
 bool vit_attention_tc_supported(const xfm_attn_params* p, bool bwd = false);
 int vit_attention_fwd_tc(const xfm_attn_params* p, cudaStream_t s);
 int vit_attention_bwd_tc(const xfm_attn_params* p, cudaStream_t s);
+// out / lse from nb key-block partials (bf16 [nb, B*L, H*64], f32 [nb, B, H, L]); attention_tc.cu
+int launch_merge_parts(int nb, const void* part_out, const float* part_lse, void* out, int64_t o_stride, float* lse, int B, int H,
+                       int L, cudaStream_t s);
 bool cross_attention_tc_supported(const xfm_attn_params* p, bool bwd = false);
 int cross_attention_fwd_tc(const xfm_attn_params* p, cudaStream_t s);
 int cross_attention_bwd_tc(const xfm_attn_params* p, cudaStream_t s);

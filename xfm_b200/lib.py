@@ -243,6 +243,10 @@ def attention_fwd(q, k, v, B, H, Lq, Lk, scale, *, Bkv=None, bias=None, kmask=No
         parts = (torch.empty((3, B * Lq, H * 64), dtype=torch.bfloat16, device=q.device),
                  torch.empty((3, B, H, Lq), dtype=torch.float32, device=q.device))
         p.part_out, p.part_lse = parts[0].data_ptr(), parts[1].data_ptr()
+    if allow_tc and Lq == 40 and Lk == 577 and kv_samples is not None and kmask is None and bias is None:   # cross-attention, 384 px
+        parts = (torch.empty((3, B * Lq, H * 64), dtype=torch.bfloat16, device=q.device),
+                 torch.empty((3, B, H, Lq), dtype=torch.float32, device=q.device))
+        p.part_out, p.part_lse = parts[0].data_ptr(), parts[1].data_ptr()
     if kv_samples is not None:  # CSR inverse of kv_index: lets the tcgen05 cross-attention kernel stack the samples of an image
         assert kv_offsets.dtype == torch.int32 and kv_samples.dtype == torch.int32
         assert kv_offsets.numel() == Bkv + 1 and kv_samples.numel() == B
