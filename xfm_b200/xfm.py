@@ -699,6 +699,8 @@ class XFMBase(nn.Module):
         for fp32, xroberta.py:903-909), or None for the all-ones masks get_vision_embeds produces.  index: sample -> mask row."""
         if image_atts is None or getattr(image_atts, "_xfm_all_ones", False):
             return None
+        if getattr(getattr(image_atts, "_base", None), "_xfm_all_ones", False):
+            return None   # a slice view of get_vision_embeds' all-ones mask (model_nlvr.py:33-36 splits it per image)
         m = ((1.0 - image_atts.to(torch.float32)) * -1e9)
         if index is not None:
             m = m.index_select(0, index.long())
