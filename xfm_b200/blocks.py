@@ -94,7 +94,7 @@ def vit_block_bwd(dx2, s, w, g, B, N, H, rel_index=None):
     tc = s.rel is not None and L.vit_attention_bwd_tc_ok(N)  # tcgen05 backward kernels (closed-form bias)
     if s.relbias is not None:
         ds = torch.empty((B, H, N, s.relbias.shape[2]), dtype=torch.bfloat16, device=dx2.device)
-        if s.relbias.shape[2] != N:
+        if s.relbias.shape[2] != N and not tc:   # the tcgen05 kernel's TMA store writes the padding columns (zeros) itself
             ds[..., N:].zero_()
     q, k, v = s.qkv[:, :D], s.qkv[:, D:2 * D], s.qkv[:, 2 * D:]
     L.attention_bwd(dattn, q, k, v, s.attn, s.lse, B, H, N, N, 0.125, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:],

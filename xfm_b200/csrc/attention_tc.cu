@@ -119,7 +119,9 @@ XFM_DEVINL void tmem_st_32x32_16(uint32_t taddr, const uint32_t (&r)[32]) {
 XFM_DEVINL void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 
-template <int W, int KB>
+// HAS_TAB = false (no relative-position bias: the VQ-KD tokenizer's ViT): no bias gather, and the first pass only takes the
+// maximum of the raw scores — nothing is written back to TMEM — because scale * s - m is one FMA in the second pass.
+template <int W, int KB, bool HAS_TAB>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 vit_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                        const __grid_constant__ CUtensorMap map_v, const VitAttnArgs a) {
@@ -247,7 +249,13 @@ vit_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     uint8_t* myP = sP + wg * Cfg::P_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
     const int sw = r & 7;
     int cur_h = BLOCKED ? h_cta : -1;
-    float bias_c0 = 0.f;
+    float bias_c0 = 0.f, bias_max = 0.f;
+    auto table_max = [&]() {   // every thread scans the head's table itself (a few hundred loads per head change)
+      float mx = -INFINITY;
+      for (int i = 0; i < Cfg::T; ++i) mx = fmaxf(mx, tab[Cfg::OFFMAX + 1 + i]);
+      return mx;
+    };
+    if (BLOCKED && HAS_TAB) bias_max = table_max();
     long long pc[6] = {0, 0, 0, 0, 0, 0}, pt = clock64();
     auto tick = [&](int i) { if (a.prof) { const long long n = clock64(); pc[i] += n - pt; pt = n; } };
     for (int tau = wg; tau < n_tiles; tau += 2) {
@@ -263,6 +271,7 @@ vit_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         for (int i = wgt; i <= Cfg::OFFMAX; i += 128) tab[i] = row0;
         named_bar_sync(1 + wg, 128);
         cur_h = h;
+        if (HAS_TAB) bias_max = table_max();
       }
       // closed form of beit2.py:104-114: idx(i, j) = base_i - off_j for i, j >= 1; row 0 reads the replicated
       // table[T-3] block through the same address arithmetic; column 0 is a per-row constant
@@ -284,7 +293,7 @@ vit_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
       const bool warp_live = q0 + t * 128 + quad * 32 < L;
       float m = 0.f, sum = 1.f;
       if (warp_live) {
-      // ---- pass 1: logits (log2 domain) back into TMEM, row maximum
+      // ---- pass 1: maximum of the raw scores of the row (nothing is written back)
       float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
       for (int c0 = 0; c0 < LPAD; c0 += 32) {
@@ -294,24 +303,16 @@ vit_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         else tmem_ld_32x32_16(t_s + c0, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const int j = c0 + e;
-          if (j < LPAD) {
-            float l;                               // j: key inside the block, K0 + j inside the sample
-            if (j >= KLEN) l = -INFINITY;
-            else if (K0 + j == 0) l = fmaf(__uint_as_float(v[e]), scale2, bias_c0);
-            else l = fmaf(__uint_as_float(v[e]), scale2, *(rb - rel_off<W>(K0 + j)));
-            m4[e & 3] = fmaxf(m4[e & 3], l);
-            v[e] = __float_as_uint(l);
-          }
-        }
-        if (full) tmem_st_32x32(t_s + c0, v);
-        else tmem_st_32x32_16(t_s + c0, v);
+        for (int e = 0; e < 32; ++e)
+          if (c0 + e < KLEN) m4[e & 3] = fmaxf(m4[e & 3], __uint_as_float(v[e]));
       }
-      m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-      tmem_st_wait();
+      // softmax is shift-invariant: any m >= the row's largest logit keeps 2^(l - m) <= 1.  scale2 * max(s) + max(bias of the
+      // head) is such a bound (scale2 > 0) and needs neither the bias gather nor a write-back of the logits in this pass; the
+      // row's largest probability is then >= 2^-(spread of the head's bias table), far inside fp32 / bf16 range for any
+      // trained table (entries of a few units).  lse = m + log2(sum) stays exact.
+      m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * scale2 + (HAS_TAB ? bias_max : 0.f);
       tick(2);
-      // ---- pass 2: p = 2^(l - m), row sum, bf16 P -> shared memory (K-major, SWIZZLE_128B)
+      // ---- pass 2: p = 2^(scale2 s + bias - m), row sum, bf16 P -> shared memory (K-major, SWIZZLE_128B)
       float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int c0 = 0; c0 < LPAD; c0 += 32) {
@@ -328,7 +329,10 @@ vit_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             float p[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              p[e] = ex2_approx(__uint_as_float(v[g8 * 8 + e]) - m);
+              const int j = c0 + g8 * 8 + e;       // key inside the block, K0 + j inside the sample
+              float bias2 = 0.f;
+              if constexpr (HAS_TAB) bias2 = K0 + j == 0 ? bias_c0 : *(rb - rel_off<W>(K0 + j));
+              p[e] = j < KLEN ? ex2_approx(fmaf(__uint_as_float(v[g8 * 8 + e]), scale2, bias2 - m)) : 0.f;
               s4[e & 3] += p[e];
             }
             uint4 u;
@@ -1387,7 +1391,9 @@ static int launch_vit_fwd_block(const xfm_attn_params* p, const VitAttnArgs& a0,
   VitAttnArgs a = a0;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(vit_attn_fwd_tc_kernel<W, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(vit_attn_fwd_tc_kernel<W, KB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(vit_attn_fwd_tc_kernel<W, KB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     attr = true;
   }
@@ -1417,7 +1423,8 @@ static int launch_vit_fwd_block(const xfm_attn_params* p, const VitAttnArgs& a0,
     if (!prof_buf) cudaMalloc(&prof_buf, 12 * sizeof(long long));
     a.prof = prof_buf;
   }
-  vit_attn_fwd_tc_kernel<W, KB><<<grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(mq, mk, mv, a);
+  if (a.table) vit_attn_fwd_tc_kernel<W, KB, true><<<grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(mq, mk, mv, a);
+  else vit_attn_fwd_tc_kernel<W, KB, false><<<grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(mq, mk, mv, a);
   count_launch();
   if (prof_on) {  // debugging aid: synchronous, prints the phase totals of CTA 0 (warp 2 = parity-0 rows 0..31, warp 9 = parity-1 rows 96..127)
     long long h[12];
