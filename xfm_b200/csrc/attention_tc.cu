@@ -249,13 +249,7 @@ vit_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     uint8_t* myP = sP + wg * Cfg::P_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
     const int sw = r & 7;
     int cur_h = BLOCKED ? h_cta : -1;
-    float bias_c0 = 0.f, bias_max = 0.f;
-    auto table_max = [&]() {   // every thread scans the head's table itself (a few hundred loads per head change)
-      float mx = -INFINITY;
-      for (int i = 0; i < Cfg::T; ++i) mx = fmaxf(mx, tab[Cfg::OFFMAX + 1 + i]);
-      return mx;
-    };
-    if (BLOCKED && HAS_TAB) bias_max = table_max();
+    float bias_c0 = 0.f;
     long long pc[6] = {0, 0, 0, 0, 0, 0}, pt = clock64();
     auto tick = [&](int i) { if (a.prof) { const long long n = clock64(); pc[i] += n - pt; pt = n; } };
     for (int tau = wg; tau < n_tiles; tau += 2) {
@@ -271,7 +265,6 @@ vit_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         for (int i = wgt; i <= Cfg::OFFMAX; i += 128) tab[i] = row0;
         named_bar_sync(1 + wg, 128);
         cur_h = h;
-        if (HAS_TAB) bias_max = table_max();
       }
       // closed form of beit2.py:104-114: idx(i, j) = base_i - off_j for i, j >= 1; row 0 reads the replicated
       // table[T-3] block through the same address arithmetic; column 0 is a per-row constant
@@ -293,7 +286,7 @@ vit_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
       const bool warp_live = q0 + t * 128 + quad * 32 < L;
       float m = 0.f, sum = 1.f;
       if (warp_live) {
-      // ---- pass 1: maximum of the raw scores of the row (nothing is written back)
+      // ---- pass 1: row maximum (with the bias: logits written back to TMEM)
       float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
       for (int c0 = 0; c0 < LPAD; c0 += 32) {
@@ -302,17 +295,36 @@ vit_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         if (full) tmem_ld_32x32(t_s + c0, v);
         else tmem_ld_32x32_16(t_s + c0, v);
         tmem_ld_wait();
+        if constexpr (HAS_TAB) {   // logits (log2 domain) back into TMEM, exact row maximum
 #pragma unroll
-        for (int e = 0; e < 32; ++e)
-          if (c0 + e < KLEN) m4[e & 3] = fmaxf(m4[e & 3], __uint_as_float(v[e]));
+          for (int e = 0; e < 32; ++e) {
+            const int j = c0 + e;
+            if (j < LPAD) {
+              float l;                               // j: key inside the block, K0 + j inside the sample
+              if (j >= KLEN) l = -INFINITY;
+              else if (K0 + j == 0) l = fmaf(__uint_as_float(v[e]), scale2, bias_c0);
+              else l = fmaf(__uint_as_float(v[e]), scale2, *(rb - rel_off<W>(K0 + j)));
+              m4[e & 3] = fmaxf(m4[e & 3], l);
+              v[e] = __float_as_uint(l);
+            }
+          }
+          if (full) tmem_st_32x32(t_s + c0, v);
+          else tmem_st_32x32_16(t_s + c0, v);
+        } else {                   // no bias: the maximum of the raw scores is the row maximum up to the scale
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (c0 + e < KLEN) m4[e & 3] = fmaxf(m4[e & 3], __uint_as_float(v[e]));
+        }
       }
-      // softmax is shift-invariant: any m >= the row's largest logit keeps 2^(l - m) <= 1.  scale2 * max(s) + max(bias of the
-      // head) is such a bound (scale2 > 0) and needs neither the bias gather nor a write-back of the logits in this pass; the
-      // row's largest probability is then >= 2^-(spread of the head's bias table), far inside fp32 / bf16 range for any
-      // trained table (entries of a few units).  lse = m + log2(sum) stays exact.
-      m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * scale2 + (HAS_TAB ? bias_max : 0.f);
+      // The maximum must be the EXACT row maximum: the dominant probability is then exactly 1 and survives the bf16 rounding
+      // of P unchanged, which the fp32 normaliser assumes.  (An upper bound — raw maximum + the head's largest bias — would
+      // save the gather and the write-back of this pass, 59 -> 55 us, but shifts the dominant term off a power of two: its
+      // rounding error, up to 2^-9, then goes straight into the output; measured as 3.5x the ITM-loss deviation.)
+      m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+      if constexpr (HAS_TAB) tmem_st_wait();
+      else m *= scale2;                            // scale2 > 0: the maximum commutes with the scaling
       tick(2);
-      // ---- pass 2: p = 2^(scale2 s + bias - m), row sum, bf16 P -> shared memory (K-major, SWIZZLE_128B)
+      // ---- pass 2: p = 2^(l - m), row sum, bf16 P -> shared memory (K-major, SWIZZLE_128B)
       float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int c0 = 0; c0 < LPAD; c0 += 32) {
@@ -329,10 +341,8 @@ vit_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             float p[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              const int j = c0 + g8 * 8 + e;       // key inside the block, K0 + j inside the sample
-              float bias2 = 0.f;
-              if constexpr (HAS_TAB) bias2 = K0 + j == 0 ? bias_c0 : *(rb - rel_off<W>(K0 + j));
-              p[e] = j < KLEN ? ex2_approx(fmaf(__uint_as_float(v[g8 * 8 + e]), scale2, bias2 - m)) : 0.f;
+              if constexpr (HAS_TAB) p[e] = ex2_approx(__uint_as_float(v[g8 * 8 + e]) - m);
+              else p[e] = c0 + g8 * 8 + e < KLEN ? ex2_approx(fmaf(__uint_as_float(v[g8 * 8 + e]), scale2, -m)) : 0.f;
               s4[e & 3] += p[e];
             }
             uint4 u;
