@@ -327,15 +327,16 @@ int hard_negatives(const float* image_feat, const float* text_feat, int B, int E
 // ids[r] = argmin_n ( ||z_r||^2 + ||e_n||^2 - 2 z_r . e_n ), z l2-normalised over the 32 channels, first index on
 // ties (norm_ema_quantizer.py:152-162).  Exact fp32 FMAs in the reference's operation order (sum, sum, -2*dot);
 // neither `d` nor the one-hot matrix is materialised.  A CTA owns 128 z rows; the codebook streams through shared memory
-// in tiles of 1024 codes.  Four thread slices per row each scan a quarter of every tile (every lane of a warp reads the
-// same code: broadcast loads) with FOUR codes in flight per thread — each dot product is still the sequential 32-step
-// FMA chain of the oracle, but four independent chains per thread and 16 warps per SM hide the FMA latency that bound the
-// one-thread-per-row, one-code-at-a-time version (0.89 ms: one warp per scheduler waiting on a 32-deep dependent chain).
-// Candidates of the four slices are merged by (distance, index), which is the first-index rule.
+// in tiles of 1024 codes.  A thread owns TWO rows and one of eight code slices of every tile (every lane of a warp reads the
+// same code: broadcast loads, each feeding two dot products) with FOUR codes in flight — each dot product is still the
+// sequential 32-step FMA chain of the oracle, but eight independent chains per thread and 16 warps per SM hide the FMA
+// latency that bound the one-thread-per-row, one-code-at-a-time version (0.89 ms: one warp per scheduler waiting on a
+// 32-deep dependent chain).  Candidates of the slices are merged by (distance, index), which is the first-index rule.
 constexpr int VQ_DIM = 32;
-constexpr int VQ_ROWS = 128;
-constexpr int VQ_SLICES = 4;
-constexpr int VQ_THREADS = VQ_ROWS * VQ_SLICES;
+constexpr int VQ_ROWS = 128;          // z rows per CTA
+constexpr int VQ_RPT = 2;             // rows per thread: every code read from shared memory feeds two dot products
+constexpr int VQ_SLICES = 8;          // code slices per row pair
+constexpr int VQ_THREADS = VQ_ROWS / VQ_RPT * VQ_SLICES;   // 512
 constexpr int VQ_TILE = 1024;  // codes per shared-memory tile (128 KB + 4 KB norms)
 constexpr int VQ_ILP = 4;
 
@@ -344,28 +345,34 @@ vq_argmin_kernel(const float* __restrict__ z, const float* __restrict__ codebook
   extern __shared__ __align__(16) float vq_smem[];
   float* se = vq_smem;                     // [VQ_TILE][32]
   float* see = vq_smem + VQ_TILE * VQ_DIM; // [VQ_TILE]
-  const int slice = threadIdx.x / VQ_ROWS, lr = threadIdx.x % VQ_ROWS;
-  const int row = blockIdx.x * VQ_ROWS + lr;
-  float zn[VQ_DIM];
-  float zz = 0.f;
-  {
-    const float* zr = z + (size_t)min(row, R - 1) * VQ_DIM;
+  constexpr int PAIRS = VQ_ROWS / VQ_RPT;
+  const int slice = threadIdx.x / PAIRS, lp = threadIdx.x % PAIRS;
+  const int row0 = blockIdx.x * VQ_ROWS + lp * VQ_RPT;
+  float zn[VQ_RPT][VQ_DIM];
+  float zz[VQ_RPT];
+#pragma unroll
+  for (int t = 0; t < VQ_RPT; ++t) {
+    const float* zr = z + (size_t)min(row0 + t, R - 1) * VQ_DIM;
     float nrm = 0.f;
 #pragma unroll
     for (int k = 0; k < VQ_DIM; k += 4) {
       const float4 v = *(const float4*)(zr + k);
-      zn[k] = v.x; zn[k + 1] = v.y; zn[k + 2] = v.z; zn[k + 3] = v.w;
+      zn[t][k] = v.x; zn[t][k + 1] = v.y; zn[t][k + 2] = v.z; zn[t][k + 3] = v.w;
     }
 #pragma unroll
-    for (int k = 0; k < VQ_DIM; ++k) nrm = fmaf(zn[k], zn[k], nrm);
+    for (int k = 0; k < VQ_DIM; ++k) nrm = fmaf(zn[t][k], zn[t][k], nrm);
     const float denom = fmaxf(sqrtf(nrm), 1e-12f);  // F.normalize eps
 #pragma unroll
-    for (int k = 0; k < VQ_DIM; ++k) zn[k] = zn[k] / denom;
+    for (int k = 0; k < VQ_DIM; ++k) zn[t][k] = zn[t][k] / denom;
+    float acc = 0.f;
 #pragma unroll
-    for (int k = 0; k < VQ_DIM; ++k) zz = fmaf(zn[k], zn[k], zz);
+    for (int k = 0; k < VQ_DIM; ++k) acc = fmaf(zn[t][k], zn[t][k], acc);
+    zz[t] = acc;
   }
-  float best = INFINITY;
-  int best_i = 0;
+  float best[VQ_RPT];
+  int best_i[VQ_RPT];
+#pragma unroll
+  for (int t = 0; t < VQ_RPT; ++t) { best[t] = INFINITY; best_i[t] = 0; }
   for (int c0 = 0; c0 < K; c0 += VQ_TILE) {
     const int nc = min(VQ_TILE, K - c0);
     __syncthreads();
@@ -379,61 +386,84 @@ vq_argmin_kernel(const float* __restrict__ z, const float* __restrict__ codebook
       see[c] = e2;
     }
     __syncthreads();
-    // this slice's quarter of the tile, in ascending code order
+    // this slice's share of the tile, in ascending code order
     const int per = (nc + VQ_SLICES - 1) / VQ_SLICES;
     const int cb = slice * per, ce = min(nc, cb + per);
     int c = cb;
     for (; c + VQ_ILP <= ce; c += VQ_ILP) {
-      float dot[VQ_ILP];
+      float dot[VQ_RPT][VQ_ILP];
 #pragma unroll
-      for (int u = 0; u < VQ_ILP; ++u) dot[u] = 0.f;
+      for (int t = 0; t < VQ_RPT; ++t)
+#pragma unroll
+        for (int u = 0; u < VQ_ILP; ++u) dot[t][u] = 0.f;
 #pragma unroll
       for (int k = 0; k < VQ_DIM / 4; ++k) {
 #pragma unroll
         for (int u = 0; u < VQ_ILP; ++u) {
           const float4 e = ((const float4*)(se + (c + u) * VQ_DIM))[k];
-          dot[u] = fmaf(zn[4 * k], e.x, dot[u]);
-          dot[u] = fmaf(zn[4 * k + 1], e.y, dot[u]);
-          dot[u] = fmaf(zn[4 * k + 2], e.z, dot[u]);
-          dot[u] = fmaf(zn[4 * k + 3], e.w, dot[u]);
+#pragma unroll
+          for (int t = 0; t < VQ_RPT; ++t) {
+            dot[t][u] = fmaf(zn[t][4 * k], e.x, dot[t][u]);
+            dot[t][u] = fmaf(zn[t][4 * k + 1], e.y, dot[t][u]);
+            dot[t][u] = fmaf(zn[t][4 * k + 2], e.z, dot[t][u]);
+            dot[t][u] = fmaf(zn[t][4 * k + 3], e.w, dot[t][u]);
+          }
         }
       }
 #pragma unroll
       for (int u = 0; u < VQ_ILP; ++u) {
-        const float d = (zz + see[c + u]) - 2.f * dot[u];
-        if (d < best) { best = d; best_i = c0 + c + u; }
+        const float e2 = see[c + u];
+#pragma unroll
+        for (int t = 0; t < VQ_RPT; ++t) {
+          const float d = (zz[t] + e2) - 2.f * dot[t][u];
+          if (d < best[t]) { best[t] = d; best_i[t] = c0 + c + u; }
+        }
       }
     }
     for (; c < ce; ++c) {
       const float4* e4 = (const float4*)(se + c * VQ_DIM);
-      float dot = 0.f;
+      float dot[VQ_RPT];
+#pragma unroll
+      for (int t = 0; t < VQ_RPT; ++t) dot[t] = 0.f;
 #pragma unroll
       for (int k = 0; k < VQ_DIM / 4; ++k) {
         const float4 e = e4[k];
-        dot = fmaf(zn[4 * k], e.x, dot);
-        dot = fmaf(zn[4 * k + 1], e.y, dot);
-        dot = fmaf(zn[4 * k + 2], e.z, dot);
-        dot = fmaf(zn[4 * k + 3], e.w, dot);
+#pragma unroll
+        for (int t = 0; t < VQ_RPT; ++t) {
+          dot[t] = fmaf(zn[t][4 * k], e.x, dot[t]);
+          dot[t] = fmaf(zn[t][4 * k + 1], e.y, dot[t]);
+          dot[t] = fmaf(zn[t][4 * k + 2], e.z, dot[t]);
+          dot[t] = fmaf(zn[t][4 * k + 3], e.w, dot[t]);
+        }
       }
-      const float d = (zz + see[c]) - 2.f * dot;
-      if (d < best) { best = d; best_i = c0 + c; }
+#pragma unroll
+      for (int t = 0; t < VQ_RPT; ++t) {
+        const float d = (zz[t] + see[c]) - 2.f * dot[t];
+        if (d < best[t]) { best[t] = d; best_i[t] = c0 + c; }
+      }
     }
   }
   // merge the slices' candidates: smallest distance, then smallest index (= the first index among equal distances)
   __syncthreads();
   float* cd = vq_smem;                              // [VQ_SLICES][VQ_ROWS]
   int* ci = (int*)(vq_smem + VQ_SLICES * VQ_ROWS);  // [VQ_SLICES][VQ_ROWS]
-  cd[slice * VQ_ROWS + lr] = best;
-  ci[slice * VQ_ROWS + lr] = best_i;
+#pragma unroll
+  for (int t = 0; t < VQ_RPT; ++t) {
+    cd[slice * VQ_ROWS + lp * VQ_RPT + t] = best[t];
+    ci[slice * VQ_ROWS + lp * VQ_RPT + t] = best_i[t];
+  }
   __syncthreads();
-  if (slice == 0 && row < R) {
+  if (threadIdx.x < VQ_ROWS) {
+    const int lr = threadIdx.x, row = blockIdx.x * VQ_ROWS + lr;
+    float b = cd[lr];
+    int bi = ci[lr];
 #pragma unroll
     for (int s2 = 1; s2 < VQ_SLICES; ++s2) {
       const float d = cd[s2 * VQ_ROWS + lr];
       const int i = ci[s2 * VQ_ROWS + lr];
-      if (d < best || (d == best && i < best_i)) { best = d; best_i = i; }
+      if (d < b || (d == b && i < bi)) { b = d; bi = i; }
     }
-    ids[row] = best_i;
+    if (row < R) ids[row] = bi;
   }
 }
 
