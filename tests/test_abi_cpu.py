@@ -139,3 +139,43 @@ def test_vqa_causal_bias_matches_the_reference_mask_rule():
     assert torch.equal(mine < 0, ref < 0)
     s = torch.randn(2, L, L)
     assert torch.equal(torch.softmax(s + mine, -1), torch.softmax(s + ref, -1))
+
+
+def test_ctypes_struct_mirrors_match_the_header(tmp_path):
+    """xfm_b200/lib.py mirrors xfm_gemm_params / xfm_attn_params field for field: sizes and the offset of every field are
+    compared with what gcc computes from include/xfm_b200.h (a silent mismatch would shift every later pointer)."""
+    import ctypes
+    import os
+    import shutil
+    import subprocess
+
+    from xfm_b200 import lib as L
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    structs = {"xfm_gemm_params": L.GemmParams, "xfm_attn_params": L.AttnParams}
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "xfm_b200.h"', "int main(void) {"]
+    for cname, cls in structs.items():
+        lines.append('  printf("%s size %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('  printf("%s %s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    subprocess.run([gcc, "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    seen = 0
+    for line in out:
+        parts = line.split()
+        if len(parts) != 3:
+            continue
+        cname, fname, val = parts
+        cls = structs[cname]
+        if fname == "size":
+            assert ctypes.sizeof(cls) == int(val), (cname, ctypes.sizeof(cls), val)
+        else:
+            assert getattr(cls, fname).offset == int(val), (cname, fname, getattr(cls, fname).offset, val)
+        seen += 1
+    assert seen == sum(len(c._fields_) + 1 for c in structs.values())
