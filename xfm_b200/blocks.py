@@ -141,11 +141,13 @@ def _attn_out_fwd(ctx, w, pre, resid, eps, drop, s, tag):
 
 
 def roberta_layer_fwd(h, w, Bt, Lt, H, eps, kmask, enc=None, Benc=0, Lenc=0, kv_index=None, drop=NO_DROP, save=True,
-                      h32=None, kv_offsets=None, kv_samples=None, self_bias=None, enc_kmask=None):
+                      h32=None, kv_offsets=None, kv_samples=None, self_bias=None, enc_kmask=None, kvc=None):
     """h: bf16 [Bt*Lt, D] (h32: the same hidden state in f32, used as the residual when given).
     enc: bf16 [Benc*Lenc, Denc] image tokens (cross-attention) or None.  Returns (h_out bf16, h_out f32, saved).
     self_bias: f32 [H, Lt, ld] additive self-attention term (the decoder's causal mask, xroberta.py:771-806);
-    enc_kmask: f32 [Bt, Lenc] additive key mask of the cross-attention (xroberta.py:903-909)."""
+    enc_kmask: f32 [Bt, Lenc] additive key mask of the cross-attention (xroberta.py:903-909).
+    kvc: this layer's cross-attention K | V projection of `enc` when the caller computed it for all layers in one GEMM (a
+    column slice of that GEMM's output, encoders.RobertaStack.layers_fwd)."""
     D = h.shape[1]
     s = Saved() if save else None
     scale = 1.0 / math.sqrt(64)
@@ -160,7 +162,8 @@ def roberta_layer_fwd(h, w, Bt, Lt, H, eps, kmask, enc=None, Benc=0, Lenc=0, kv_
     h2, h2_32 = h1, h1_32
     if enc is not None:
         qc = L.gemm(h1, w["c_q_w16"], bias=w["c_q_b"])
-        kvc = L.gemm(enc, w["c_kv_w16"], bias=w["c_kv_b"])
+        if kvc is None:
+            kvc = L.gemm(enc, w["c_kv_w16"], bias=w["c_kv_b"])
         seed_c = drop.next_seed() if drop.p_attn > 0 else 0
         cctx, clse = L.attention_fwd(qc, kvc[:, :D], kvc[:, D:], Bt, H, Lt, Lenc, scale, Bkv=Benc, kv_index=kv_index,
                                      kmask=enc_kmask, dropout_p=drop.p_attn, dropout_seed=seed_c, kv_offsets=kv_offsets,
@@ -199,9 +202,10 @@ def _attn_out_bwd(dh, s, w, g, pre, tag, ctx):
 
 
 def roberta_layer_bwd(dh3, s, w, g, Bt, Lt, H, kmask, Benc=0, Lenc=0, kv_index=None, kv_offsets=None, kv_samples=None,
-                      d_enc=None, need_dh=True, self_bias=None, enc_kmask=None):
+                      d_enc=None, need_dh=True, self_bias=None, enc_kmask=None, dkvc_out=None):
     """dh3: bf16 or fp32 [Bt*Lt, D].  d_enc: fp32 [Benc*Lenc, Denc] accumulator for the image-token gradient.
-    Returns the fp32 gradient wrt the layer input (or None)."""
+    dkvc_out: where this layer's K | V gradient goes when the caller back-propagates all layers' K / V projections in one
+    GEMM afterwards (the per-layer d_enc GEMM is then skipped).  Returns the fp32 gradient wrt the layer input (or None)."""
     D = s.h.shape[1]
     scale = 1.0 / math.sqrt(64)
     f32 = torch.float32
@@ -219,7 +223,7 @@ def roberta_layer_bwd(dh3, s, w, g, Bt, Lt, H, kmask, Benc=0, Lenc=0, kv_index=N
     if s.has_cross:
         d_res, d_cctx = _attn_out_bwd(dh2, s, w, g, "c_", "c", s.cctx)
         dqc = torch.empty_like(s.qc)
-        dkvc = torch.empty_like(s.kvc)
+        dkvc = torch.empty_like(s.kvc) if dkvc_out is None else dkvc_out
         L.attention_bwd(d_cctx, s.qc, s.kvc[:, :D], s.kvc[:, D:], s.cctx, s.clse, Bt, H, Lt, Lenc, scale, dqc, dkvc[:, :D],
                         dkvc[:, D:], Bkv=Benc, kv_index=kv_index, kv_offsets=kv_offsets, kv_samples=kv_samples,
                         kmask=enc_kmask, dropout_p=s.p_attn, dropout_seed=s.seed_c)
@@ -228,7 +232,7 @@ def roberta_layer_bwd(dh3, s, w, g, Bt, Lt, H, kmask, Benc=0, Lenc=0, kv_index=N
         dh1 = L.gemm(dqc, w["c_q_w16"], b_t=True, residual=d_res, out_dtype=f32)
         L.colsum_into(dkvc, g("c_kv_b"))
         wgrad(g("c_kv_w"), dkvc, s.enc)
-        if d_enc is not None:
+        if d_enc is not None and dkvc_out is None:
             L.gemm(dkvc, w["c_kv_w16"], b_t=True, out=d_enc, accumulate=True)
     # ---- self-attention
     d_res, d_ctx = _attn_out_bwd(dh1, s, w, g, "a_", "a", s.ctx)

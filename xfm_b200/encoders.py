@@ -408,10 +408,22 @@ class RobertaStack:
                 st.kv_samples = torch.arange(Bt, dtype=torch.int32, device=h.device)
             else:
                 st.kv_offsets, st.kv_samples = csr_inverse(kv_index, Benc)
+        # The cross-attention K | V projections of all layers read the same `enc`: one GEMM with the layers' weights stacked
+        # along N (and, in the backward, one GEMM with them stacked along K for the gradient wrt `enc`: no fp32 read-modify-
+        # write of the accumulator per layer) instead of one launch per layer.
+        st.kvc_all = st.kv_wall = None
+        kv_w = [w.get("c_kv_w16") for w in self.w]
+        merged = enc is not None and self.layers > 1 and all(x is not None for x in kv_w) and MERGE_CROSS_KV
+        D2 = 0
+        if merged:
+            D2 = kv_w[0].shape[0]
+            st.kv_wall = torch.cat(kv_w, 0)
+            st.kvc_all = L.gemm(enc, st.kv_wall, bias=torch.cat([w["c_kv_b"] for w in self.w]))
         for i in range(self.layers):
             h, h32, s = BK.roberta_layer_fwd(h, self.w[i], Bt, Lt, self.H, self.eps, kmask, enc=enc, Benc=Benc, Lenc=Lenc,
                                              kv_index=kv_index, drop=drop, save=save, h32=h32, kv_offsets=st.kv_offsets,
-                                             kv_samples=st.kv_samples, self_bias=self_bias, enc_kmask=enc_kmask)
+                                             kv_samples=st.kv_samples, self_bias=self_bias, enc_kmask=enc_kmask,
+                                             kvc=st.kvc_all[:, i * D2:(i + 1) * D2] if merged else None)
             st.layers.append(s)
             if self.collect is not None:
                 self.collect.append(h32.view(Bt, Lt, -1).clone())
@@ -447,14 +459,24 @@ class RobertaStack:
         """dh: bf16 / f32 [Bt*Lt, D].  d_enc: f32 [Benc*Lenc, Denc] accumulator (cross-attention K/V input gradient)."""
         if kv_samples is None:   # CSR built in layers_fwd (identity when every sample has its own image)
             kv_offsets, kv_samples = st.kv_offsets, st.kv_samples
+        kvc_all = getattr(st, "kvc_all", None)
+        dkvc_all = torch.empty_like(kvc_all) if kvc_all is not None else None
+        D2 = kvc_all.shape[1] // self.layers if kvc_all is not None else 0
         for i in reversed(range(self.layers)):
             last = i == 0
             dh = BK.roberta_layer_bwd(dh, st.layers[i], self.w[i], self._g(i), st.Bt, st.Lt, self.H, st.kmask, Benc=st.Benc,
                                       Lenc=st.Lenc, kv_index=st.kv_index, kv_offsets=kv_offsets, kv_samples=kv_samples,
                                       d_enc=d_enc, need_dh=(need_dh or not last), self_bias=st.self_bias,
-                                      enc_kmask=st.enc_kmask)
+                                      enc_kmask=st.enc_kmask,
+                                      dkvc_out=dkvc_all[:, i * D2:(i + 1) * D2] if dkvc_all is not None else None)
             st.layers[i] = None
+        if dkvc_all is not None and d_enc is not None:   # gradient wrt the image tokens: all layers in one long-K GEMM
+            L.gemm(dkvc_all, st.kv_wall, b_t=True, out=d_enc, accumulate=True)
+        st.kvc_all = st.kv_wall = None
         return dh
+
+
+MERGE_CROSS_KV = __import__("os").environ.get("XFM_MERGE_CROSS_KV", "1") != "0"   # A/B switch for measurements
 
 
 def csr_inverse(kv_index, Bkv):
