@@ -455,8 +455,9 @@ class RobertaStack:
         e.__dict__.update({k: cut(v) for k, v in est.__dict__.items()})
         return e, out
 
-    def layers_bwd(self, st, dh, d_enc=None, need_dh=True, kv_offsets=None, kv_samples=None):
-        """dh: bf16 / f32 [Bt*Lt, D].  d_enc: f32 [Benc*Lenc, Denc] accumulator (cross-attention K/V input gradient)."""
+    def layers_bwd(self, st, dh, d_enc=None, need_dh=True, kv_offsets=None, kv_samples=None, d_enc_fresh=False):
+        """dh: bf16 / f32 [Bt*Lt, D].  d_enc: f32 [Benc*Lenc, Denc] accumulator (cross-attention K/V input gradient);
+        d_enc_fresh: it is uninitialised memory that the merged K | V gradient GEMM may simply overwrite."""
         if kv_samples is None:   # CSR built in layers_fwd (identity when every sample has its own image)
             kv_offsets, kv_samples = st.kv_offsets, st.kv_samples
         kvc_all = getattr(st, "kvc_all", None)
@@ -471,7 +472,7 @@ class RobertaStack:
                                       dkvc_out=dkvc_all[:, i * D2:(i + 1) * D2] if dkvc_all is not None else None)
             st.layers[i] = None
         if dkvc_all is not None and d_enc is not None:   # gradient wrt the image tokens: all layers in one long-K GEMM
-            L.gemm(dkvc_all, st.kv_wall, b_t=True, out=d_enc, accumulate=True)
+            L.gemm(dkvc_all, st.kv_wall, b_t=True, out=d_enc, accumulate=not d_enc_fresh)
         st.kvc_all = st.kv_wall = None
         return dh
 

@@ -848,8 +848,11 @@ class XFMBase(nn.Module):
                                     drop=self._drop(), save=save, h32=text32, enc_kmask=enc_kmask)
 
     def _fusion_back(self, st, dh, Bi, Ni, need_dtext, kv_index):
-        d_enc = torch.zeros((Bi * Ni, self.vision_width), dtype=torch.float32, device=dh.device)
-        d_text = self._fus.layers_bwd(st, dh, d_enc=d_enc, need_dh=need_dtext)  # CSR of kv_index: built once in layers_fwd
+        # with the layers' K | V projections merged, ONE GEMM writes the image-token gradient: no zero fill, no accumulate
+        fresh = getattr(st, "kvc_all", None) is not None
+        alloc = torch.empty if fresh else torch.zeros
+        d_enc = alloc((Bi * Ni, self.vision_width), dtype=torch.float32, device=dh.device)
+        d_text = self._fus.layers_bwd(st, dh, d_enc=d_enc, need_dh=need_dtext, d_enc_fresh=fresh)  # CSR: built in layers_fwd
         return d_text, d_enc.view(Bi, Ni, -1)
 
     def get_cross_embeds(self, image_embeds, image_atts, text_ids=None, text_embeds=None, text_atts=None, is_pretrain=True):
