@@ -276,6 +276,17 @@ int xfm_bbox_loss(const float* coord, const float* target, const float* is_image
                   float* d_bbox, float* d_giou, void* stream);
 int xfm_axpby_scalars(const float* a, const float* sa, const float* b, const float* sb, float* out, int n, void* stream);
 
+/* Batch feeder, device half (loader side): the tail of the reference's image transform —
+ * transforms.ToTensor() + transforms.Normalize(mean, std) (dataset/__init__.py:26-35; the same two lines close every Compose
+ * there) and optionally the RandomHorizontalFlip of that Compose — on the uint8 crops the decode workers produce.
+ *   in   u8  [B, H, W, 3]  device, 4-byte aligned (HWC as PIL / numpy hand it over); W % 4 == 0
+ *   out  f32 [B, 3, H, W]  device, 16-byte aligned: out[b, c, y, x] = (in[b, y, x', c] / 255 - mean[c]) / std[c], IEEE
+ *                          round-to-nearest divisions as in the CPU transform (bit-identical results)
+ *   flip u8  [B] or null   1 = x' = W - 1 - x (torchvision hflip), 0 = x' = x
+ *   mean, stdv             HOST pointers to 3 floats each (baked into the launch; graph-capturable) */
+int xfm_image_u8_to_f32(const uint8_t* in, float* out, const uint8_t* flip, int B, int H, int W, const float* mean,
+                        const float* stdv, void* stream);
+
 /* Flat-buffer optimizer step (accelerators/ddp_accelerator.py:89-98 clip_grad_norm_ + optimizer.step with the
  * transformers AdamW of optim.py:4-50).  P/G/M/V: f32 buffers of nchunks*64 elements, S: bf16 shadow (may be null).
  *   chunk_seg[nchunks] int32  static: parameter segment of every 64-element chunk, -1 = frozen / padding (never touched)

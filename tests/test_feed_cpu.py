@@ -1,0 +1,177 @@
+"""Host half of the batch feeder (xfm_b200/feed.py, SURVEY.md §8 f4 loader side) against tests/golden/feed.json, which
+tools/make_golden_feed.py wrote by running the unmodified reference loader code (dataset/pretrain_dataset.py) on the same seeded
+inputs.  Everything here is integer / index work: the bar is exact equality, including the state of the global `random`
+generator afterwards (same number of draws in the same order)."""
+import json
+import os
+import random
+import sys
+
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from feed_stub import StubTokenizer  # noqa: E402
+from xfm_b200 import feed  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def golden(golden_dir):
+    with open(os.path.join(golden_dir, "feed.json")) as f:
+        return json.load(f)
+
+
+def test_text_masker_matches_reference(golden):
+    toks = {s: StubTokenizer(s) for s in ("roberta", "bert")}
+    assert len(golden["masker"]) == 48
+    hit_trim = hit_random_word = 0
+    for g in golden["masker"]:
+        prob, mmax, sprb, ssize, whole, use_rob = g["cfg"]
+        m = feed.TextMasker(toks[g["style"]], prob, mmax, sprb, ssize, whole, use_roberta=use_rob)
+        random.seed(g["seed"])
+        got, pos = m(list(g["tokens"]))
+        assert got == g["tokens_masked"] and pos == g["masked_pos"], g
+        assert random.random() == g["next_random"]      # same number of draws
+        assert len(pos) <= mmax and 0 not in pos
+        hit_random_word += sum(1 for a, b in zip(got, g["tokens"]) if a != b and a != toks[g["style"]].mask_token)
+        hit_trim += len(pos) == min(mmax, max(1, int(round(len(g["tokens"]) * prob))))
+    assert hit_random_word > 0 and hit_trim > 0          # the fixture reaches the random-word and the full-budget branches
+
+
+def test_text_masker_private_generator_and_errors():
+    tok = StubTokenizer("roberta")
+    tokens = [tok.cls_token] + tok.tokenize("a man riding a horse on the street") + [tok.sep_token]
+    a = feed.TextMasker(tok, 0.3, 5, rng=random.Random(5))(list(tokens))
+    random.seed(5)
+    b = feed.TextMasker(tok, 0.3, 5)(list(tokens))
+    assert a == b
+    with pytest.raises(AssertionError):
+        feed.TextMasker(tok, 0.3, 5)(tokens[1:])
+    with pytest.raises(ValueError):
+        feed.TextMasker(({0: "a", 2: "b"}, "a", "b"), 0.3, 5)
+
+
+def test_pre_caption():
+    assert feed.pre_caption("A Man, riding/holding the-horse!  <person> (left)\n", 50) == "a man riding holding the horse person left"
+    assert feed.pre_caption("one two three four", 2) == "one two"
+    with pytest.raises(ValueError):
+        feed.pre_caption(" ?! ", 5)
+
+
+def _text(tok, style, tokenized, lang, corpus=False):
+    masker = feed.TextMasker(tok, 0.25, 5, 0.2, 3, style == "bert")
+    return feed.TextPreprocessor(tok, masker, max_tokens=12, max_masks=5, max_words=7, tokenized=tokenized, language_chosen=lang,
+                                 corpus=corpus)
+
+
+def test_preprocess_matches_reference(golden):
+    toks = {s: StubTokenizer(s) for s in ("roberta", "bert")}
+    assert len(golden["preprocess"]) == 24 and len(golden["corpus"]) == 12
+    for g in golden["preprocess"]:
+        tp = _text(toks[g["style"]], g["style"], g["tokenized"], g["lang"])
+        random.seed(g["seed"])
+        out = tp.preprocess(g["text"])
+        assert [list(o) for o in out] == g["out"], g
+        ids, atts, ids_m, pos, mids = out
+        assert len(ids) == len(atts) == len(ids_m) == 12 and len(pos) == len(mids) == 5
+        assert all(m == -100 or ids[p] == m for p, m in zip(pos, mids))
+    for g in golden["corpus"]:
+        tp = _text(toks[g["style"]], g["style"], g["tokenized"], None, corpus=True)
+        random.seed(g["seed"])
+        assert [list(o) for o in tp.preprocess(g["text"])] == g["out"], g
+
+
+def test_region_image_atts_matches_reference(golden):
+    assert len(golden["image_atts"]) == 48
+    for g in golden["image_atts"]:
+        atts = feed.region_image_atts(*g["box"], g["patch_size"], g["num_patch"])
+        assert atts == g["atts"], g["box"]
+        assert atts[0] == 1 and sum(atts) >= 2
+
+
+def _region_sampler(cfg, tok):
+    careful, max_regions, min_perc, lang = cfg
+    text = feed.TextPreprocessor(tok, feed.TextMasker(tok, 0.25, 4, 0.2, 3, False), max_tokens=10, max_masks=4, max_words=7,
+                                 language_chosen=lang)
+    return feed.RegionSampler(text, image_res=224, patch_size=16, max_regions=max_regions, min_perc_in_image=min_perc,
+                              careful_hflip=careful)
+
+
+def _region_samples(golden):
+    tok = StubTokenizer("roberta")
+    samples = []
+    for g in golden["region"]:
+        rs = _region_sampler(g["cfg"], tok)
+        W, H = g["ann"]["size"]
+        random.seed(g["seed"])
+        plan = rs.plan(g["ann"], W, H)
+        sample = rs.finish(g["ann"], plan, torch.zeros(3, 2, 2))
+        samples.append((g, plan, sample, random.random()))
+    return samples
+
+
+def test_region_sampler_matches_reference(golden):
+    assert len(golden["region"]) == 15
+    n_regions = n_full = 0
+    for g, plan, sample, nxt in _region_samples(golden):
+        W, H = g["ann"]["size"]
+        assert 0 <= plan.x0 and 0 <= plan.y0 and plan.x0 + plan.w0 <= W and plan.y0 + plan.h0 <= H
+        assert len(sample[0]) == g["n_images"]
+        assert [[list(r) for r in col] for col in sample[1:7]] == g["lists"], g["seed"]
+        assert [t.tolist() for t in sample[7]] == g["target_bbox"]       # float32 values, exact
+        assert list(sample[8]) == g["is_image"]
+        assert nxt == g["next_random"]
+        n_regions += g["is_image"].count(0)
+        n_full += g["is_image"].count(1)
+    assert n_regions > 10 and n_full > 3
+
+
+def test_collate_and_region_collate_match_reference(golden):
+    g = golden["collate"][0]
+    batch = [(torch.full((3, 2, 2), float(i)), [i, 1, 2], [1, 1, 0], None) for i in range(4)]
+    img, ids, atts, none = feed.collate(batch)
+    assert img.tolist() == g["image"] and ids.tolist() == g["ids"] and atts.tolist() == g["atts"] and none is None
+    assert ids.dtype == torch.int64
+
+    samples = [s for _, _, s, _ in _region_samples(golden)]
+    branches = set()
+    for g in golden["region_collate"]:
+        group = [samples[i] for i in g["samples"]]
+        n = sum(len(s[1]) for s in group)
+        branches.add("sample" if n >= g["batch_size"] else "pad" if 2 * n >= g["batch_size"] else "repeat")
+        random.seed(g["seed"])
+        bt = feed.region_collate(group, g["batch_size"], warn=lambda *a, **k: None)
+        assert list(bt[0].shape) == g["images_shape"]
+        assert [t.tolist() for t in bt[1:]] == g["tensors"], g["seed"]
+        assert random.random() == g["next_random"]
+        idx = bt[1]
+        assert idx.dtype == torch.int64 and idx.numel() == g["batch_size"] and int(idx.max()) < bt[0].shape[0]
+        assert bt[7].shape == (g["batch_size"], 197) and bt[8].shape == (g["batch_size"], 4) and bt[8].dtype == torch.float32
+    assert branches == {"sample", "pad", "repeat"}
+
+
+def test_to_uint8_hwc_and_cpu_transform_restatement():
+    """`to_uint8_hwc` hands over the pixels untouched, and (u8 / 255 - mean) / std — what tests/test_feed_gpu.py holds the
+    kernel to — IS torchvision's ToTensor + Normalize on that crop."""
+    np = pytest.importorskip("numpy")
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, 256, size=(32, 24, 3), dtype=np.uint8)
+    t = feed.to_uint8_hwc(a)
+    assert t.dtype == torch.uint8 and t.shape == (32, 24, 3) and (t.numpy() == a).all()
+    with pytest.raises(ValueError):
+        feed.to_uint8_hwc(a[:, :, 0])
+    tv = pytest.importorskip("torchvision.transforms")
+    from PIL import Image
+    ref = tv.Compose([tv.ToTensor(), tv.Normalize(feed.CLIP_MEAN, feed.CLIP_STD)])(Image.fromarray(a))
+    x = t.permute(2, 0, 1).contiguous().to(torch.float32).div(255)
+    mean = torch.tensor(feed.CLIP_MEAN, dtype=torch.float32)[:, None, None]
+    std = torch.tensor(feed.CLIP_STD, dtype=torch.float32)[:, None, None]
+    assert torch.equal((x - mean) / std, ref)
+    assert (feed.to_uint8_hwc(Image.fromarray(a)) == t).all()
+
+
+def test_device_feeder_refuses_to_run_without_cuda():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(RuntimeError):
+        feed.DeviceFeeder([])

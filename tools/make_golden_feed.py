@@ -1,0 +1,202 @@
+"""Generate tests/golden/feed.json by running the UNMODIFIED reference loader code (/root/reference/dataset/pretrain_dataset.py:
+TextMaskingGenerator, ImageTextJsonDataset.preprocess / collate_fn, TextJsonDataset.preprocess, RegionTextJsonDataset.__iter__ /
+get_image_attns / collate_fn) on seeded inputs with the stub tokenizer of tests/feed_stub.py.  Runs in the build container only
+(the reference tree is not on the GPU box); the fixture it writes is what tests/test_feed_cpu.py checks xfm_b200.feed against.
+
+    python tools/make_golden_feed.py
+"""
+import base64
+import contextlib
+import importlib.abc
+import importlib.machinery
+import io
+import json
+import os
+import random
+import sys
+import types
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+REF_ROOT = "/root/reference"
+ABSENT = {"pycocotools", "pycocoevalcap", "skimage", "matplotlib", "ruamel", "h5py", "cv2", "ftfy", "timm"}
+
+
+class _Stub(types.ModuleType):
+    def __getattr__(self, k):
+        if k.startswith("__"):
+            raise AttributeError(k)
+        return type(k, (), {})
+
+
+class _Finder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+    """Evaluation-only dependencies of dataset/__init__.py that are not in the image import as empty stubs."""
+
+    def find_spec(self, name, path, target=None):
+        if name.split(".")[0] in ABSENT:
+            return importlib.machinery.ModuleSpec(name, self, is_package=True)
+
+    def create_module(self, spec):
+        m = _Stub(spec.name)
+        m.__path__ = []
+        return m
+
+    def exec_module(self, m):
+        pass
+
+
+def reference_module():
+    import transformers  # noqa: F401  (before the stubs exist)
+    sys.meta_path.append(_Finder())
+    sys.path.insert(0, REF_ROOT)
+    with contextlib.redirect_stdout(io.StringIO()):
+        import dataset.pretrain_dataset as pd
+    return pd
+
+
+def bare(cls, **attrs):
+    """An instance without __init__ (which lists data files on HDFS): only the attributes the methods under test read."""
+    o = object.__new__(cls)
+    o.__dict__.update(attrs)
+    return o
+
+
+def sentence(rng, n):
+    from feed_stub import WORDS
+    return " ".join(rng.choice(WORDS) for _ in range(n))
+
+
+def main():
+    import torch
+    from PIL import Image
+    from feed_stub import StubTokenizer
+
+    pd = reference_module()
+    gen = random.Random(1234)            # drives the INPUTS; the code under test draws from the global generator
+    out = dict(masker=[], preprocess=[], corpus=[], image_atts=[], region=[], collate=[], region_collate=[])
+    quiet = contextlib.redirect_stdout(io.StringIO())
+
+    # ---- TextMaskingGenerator
+    for style in ("roberta", "bert"):
+        tok = StubTokenizer(style)
+        for (prob, mmax, sprb, ssize, whole, use_rob) in [(0.25, 8, 0.2, 3, False, False), (0.4, 6, 0.5, 3, True, style == "roberta"),
+                                                          (0.15, 4, 0.0, 3, True, style == "roberta"), (0.5, 10, 1.0, 2, False, False)]:
+            with quiet:
+                mg = pd.TextMaskingGenerator(tok, prob, mmax, sprb, ssize, whole, use_roberta=use_rob)
+            for seed in range(6):
+                tokens = [tok.cls_token] + tok.tokenize(sentence(gen, gen.randint(1, 9))) + [tok.sep_token]
+                random.seed(seed)
+                got, pos = mg(list(tokens))
+                out["masker"].append(dict(style=style, cfg=[prob, mmax, sprb, ssize, whole, use_rob], seed=seed, tokens=tokens,
+                                          tokens_masked=got, masked_pos=pos, next_random=random.random()))
+
+    # ---- preprocess (image-text stream, pretrain_dataset.py:264-300) and the text-only stream (:690-726)
+    for style in ("roberta", "bert"):
+        tok = StubTokenizer(style)
+        with quiet:
+            mg = pd.TextMaskingGenerator(tok, 0.25, 5, 0.2, 3, style == "bert")
+        for tokenized, lang in [(False, None), (True, None), (False, "zh")]:
+            ds = bare(pd.ImageTextJsonDataset, tokenized=tokenized, language_chosen=lang, max_words=7, max_tokens=12, max_masks=5,
+                      tokenizer=tok, cls_token=tok.cls_token, eos_token=tok.sep_token, pad_token_id=tok.pad_token_id,
+                      add_eos=True, mask_generator=mg, PAD_mask=-100)
+            for seed in range(4):
+                text = sentence(gen, gen.randint(1, 10))
+                if seed == 1:
+                    text = "A Man, riding/holding the-horse!  <person> (left)  " + text
+                if tokenized and style == "bert":
+                    text = " ".join(tok.tokenize(text))
+                random.seed(100 + seed)
+                res = ds.preprocess(text)
+                out["preprocess"].append(dict(style=style, tokenized=tokenized, lang=lang, seed=100 + seed, text=text,
+                                              out=[list(map(int, r)) for r in res]))
+        for tokenized in (False, True):
+            ds = bare(pd.TextJsonDataset, tokenized=tokenized, max_words=7, max_tokens=12, max_masks=5, tokenizer=tok,
+                      cls_token=tok.cls_token, eos_token=tok.sep_token, pad_token_id=tok.pad_token_id, add_eos=True,
+                      mask_generator=mg, PAD_mask=-100)
+            for seed in range(3):
+                text = sentence(gen, gen.randint(1, 14))
+                if tokenized:
+                    text = " ".join(tok.tokenize(text))
+                random.seed(200 + seed)
+                res = ds.preprocess(text)
+                out["corpus"].append(dict(style=style, tokenized=tokenized, seed=200 + seed, text=text,
+                                          out=[list(map(int, r)) for r in res]))
+
+    # ---- get_image_attns
+    for ps, res in [(16, 224), (16, 384), (32, 224)]:
+        ds = bare(pd.RegionTextJsonDataset, patch_size=ps, num_patch=res // ps)
+        for _ in range(12):
+            x, y = gen.uniform(0, res), gen.uniform(0, res)
+            w, h = gen.uniform(0.01, res - x + 3), gen.uniform(0.01, res - y + 3)
+            out["image_atts"].append(dict(patch_size=ps, num_patch=res // ps, box=[x, y, w, h],
+                                          atts=ds.get_image_attns(x, y, w, h)))
+        for box in ([0, 0, res, res], [res - 1e-3, res - 1e-3, 5.0, 5.0], [16.0, 32.0, 16.0, 16.0], [15.999, 0.0, 0.002, 1.0]):
+            out["image_atts"].append(dict(patch_size=ps, num_patch=res // ps, box=list(box), atts=ds.get_image_attns(*box)))
+
+    # ---- RegionTextJsonDataset.__iter__ (one annotated image -> region samples) and collate_fn
+    tok = StubTokenizer("roberta")
+    with quiet:
+        mg = pd.TextMaskingGenerator(tok, 0.25, 4, 0.2, 3, False)
+
+    def make_ann(W, H, n_elems, with_caption, multilingual=False):
+        buf = io.BytesIO()
+        Image.new("RGB", (W, H), (gen.randrange(256), gen.randrange(256), gen.randrange(256))).save(buf, format="PNG")
+        elems = []
+        for _ in range(n_elems):
+            x, y = gen.randrange(0, W - 8), gen.randrange(0, H - 8)
+            w, h = gen.randrange(4, W - x + 1), gen.randrange(4, H - y + 1)
+            cap = sentence(gen, gen.randint(1, 6))
+            e = dict(bb=[x, y, w, h], caption=[cap, sentence(gen, 3)] if gen.random() < 0.4 else cap)
+            if gen.random() < 0.4:
+                e["attributes"] = [sentence(gen, 1), sentence(gen, 2)]
+            elems.append(e)
+        ann = dict(binary=base64.b64encode(buf.getvalue()).decode(), elems=elems, size=[W, H])
+        if with_caption:
+            ann["caption"] = dict(en=sentence(gen, 5), de=sentence(gen, 4)) if multilingual else sentence(gen, 6)
+        return ann
+
+    region_samples = []
+    for case, (careful, max_regions, min_perc, lang) in enumerate([(False, 5, 0.5, None), (True, 3, 0.2, None), (True, 8, 0.7, "en")]):
+        ds = bare(pd.RegionTextJsonDataset, image_key="binary", is_image_rpath=False, caption_key="caption", careful_hflip=careful,
+                  max_regions=max_regions, min_perc_in_image=min_perc, box_transform=lambda im: torch.zeros(3, 2, 2),
+                  tokenized=False, language_chosen=lang, max_words=7, max_tokens=10, max_masks=4, tokenizer=tok,
+                  cls_token=tok.cls_token, eos_token=tok.sep_token, pad_token_id=tok.pad_token_id, add_eos=True, mask_generator=mg,
+                  PAD_mask=-100, image_res=224, patch_size=16, num_patch=14, print_broken_data=True, batch_size=6)
+        for seed in range(5):
+            ann = make_ann(gen.randrange(40, 400), gen.randrange(40, 400), gen.randint(1, 7), gen.random() < 0.6,
+                           multilingual=gen.random() < 0.3)
+            ds.generate = lambda ann=ann: iter([json.dumps(ann)])
+            random.seed(300 + seed)
+            (sample,) = list(ds)
+            region_samples.append(sample)
+            lists = [[list(map(int, r)) for r in col] for col in sample[1:7]]
+            ann_in = {k: v for k, v in ann.items() if k != "binary"}
+            out["region"].append(dict(cfg=[careful, max_regions, min_perc, lang], seed=300 + seed, ann=ann_in,
+                                      n_images=len(sample[0]), lists=lists, target_bbox=[t.tolist() for t in sample[7]],
+                                      is_image=list(sample[8]), next_random=random.random()))
+    # collate: sub-sampling, padding by re-sampling and padding by repetition
+    for seed, (idxs, bs) in enumerate([(list(range(0, 5)), 6), (list(range(5, 10)), 16), (list(range(10, 12)), 40),
+                                       (list(range(3, 15, 2)), 9), (list(range(15)), 12)]):
+        ds.batch_size = bs
+        group = [region_samples[i] for i in idxs]
+        assert any(len(s[1]) for s in group)
+        random.seed(400 + seed)
+        with quiet:
+            bt = ds.collate_fn(group)
+        out["region_collate"].append(dict(seed=400 + seed, samples=idxs, batch_size=bs, images_shape=list(bt[0].shape),
+                                          tensors=[t.tolist() for t in bt[1:]], next_random=random.random()))
+
+    # ---- ImageTextJsonDataset.collate_fn
+    ds = bare(pd.ImageTextJsonDataset)
+    batch = [(torch.full((3, 2, 2), float(i)), [i, 1, 2], [1, 1, 0], None) for i in range(4)]
+    bt = ds.collate_fn(batch)
+    out["collate"].append(dict(image=bt[0].tolist(), ids=bt[1].tolist(), atts=bt[2].tolist(), none=bt[3]))
+
+    path = os.path.join(ROOT, "tests", "golden", "feed.json")
+    with open(path, "w") as f:
+        json.dump(out, f, separators=(",", ":"))
+    print(path, os.path.getsize(path), "bytes;", {k: len(v) for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    main()

@@ -217,6 +217,10 @@ int xfm_bbox_loss(const float* coord, const float* target, const float* is_image
 int xfm_axpby_scalars(const float* a, const float* sa, const float* b, const float* sb, float* out, int n, void* stream) {
   return axpby_scalars(a, sa, b, sb, out, n, ST);
 }
+int xfm_image_u8_to_f32(const uint8_t* in, float* out, const uint8_t* flip, int B, int H, int W, const float* mean,
+                        const float* stdv, void* stream) {
+  return image_u8_to_f32(in, out, flip, B, H, W, mean, stdv, ST);
+}
 int xfm_grad_sumsq(const float* g, const int32_t* chunk_seg, const uint8_t* seg_group, size_t nchunks, int32_t* seg_step,
                    float* seg_bc, int nseg, const float* hp, float* out, int accumulate, void* stream) {
   return grad_sumsq(g, chunk_seg, seg_group, nchunks, seg_step, seg_bc, nseg, hp, out, accumulate, ST);

@@ -1,0 +1,445 @@
+"""Batch feeder: the loader half of SURVEY.md §8 f4 — everything between a decoded crop / a caption string and the tensors
+`XFM.forward` takes on the device.
+
+Host half (bit-exact restatements of the reference's sample and batch assembly, same `random` call order so that a seeded
+run produces the reference's batches):
+  * `TextMasker`              dataset/pretrain_dataset.py:60-150  (TextMaskingGenerator: n-gram / whole-word MLM masking)
+  * `pre_caption`             dataset/utils.py:38-66
+  * `TextPreprocessor`        dataset/pretrain_dataset.py:264-300 (image-text) and :690-726 (text-only corpus)
+  * `region_image_atts`       dataset/pretrain_dataset.py:577-592 (box -> patch mask with token 0 always on)
+  * `RegionSampler`           dataset/pretrain_dataset.py:445-575 (random crop around a region, careful hflip, per-region texts,
+                              patch masks and cxcywh targets; the pixel work stays with the caller between the two phases)
+  * `collate`, `region_collate`  dataset/pretrain_dataset.py:302-312, :594-643 (`idx_to_group_img`, fixed-size region batches)
+
+Device half:
+  * `to_uint8_hwc`            replaces the `ToTensor(), normalize` tail of every Compose in dataset/__init__.py:26-68: the
+                              worker hands over the crop as uint8 [H, W, 3]
+  * `DeviceFeeder`            pinned double-buffered staging, host->device copies on a side stream `depth` batches ahead, and
+                              `xfm_image_u8_to_f32` (csrc/feed.cu) doing ToTensor + Normalize (+ hflip) on the GPU: a 224-px
+                              batch of 96 crosses PCIe as 14.5 MB instead of 57.8 MB and the result is bit-identical to the CPU
+                              transform.
+
+JPEG decode, RandomResizedCrop and RandAugment stay PIL work in the DataLoader workers.  There is no CPU path for
+the device half: `DeviceFeeder` raises without a CUDA device.
+"""
+import math
+import random as _random
+import re
+
+import torch
+
+CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)   # dataset/__init__.py:26
+CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
+PAD_MASK = -100                                   # pretrain_dataset.py:195: the MLM loss ignores it
+
+
+# ------------------------------------------------------------------------------------------------------------ text side
+class TextMasker:
+    """MLM position sampling and token corruption (pretrain_dataset.py:60-150).
+
+    `vocab`: a tokenizer (anything with get_vocab / cls_token / mask_token) or a (id2token, cls_token, mask_token) triple.
+    `rng`: an object with shuffle / random / randint — the `random` module by default, because the reference draws from
+    the process-global generator (`from random import randint, shuffle`), so `random.seed(s)` reproduces its stream.
+    The draws happen in the reference's order: one shuffle of the candidate positions; per visited position one
+    random() for the n-gram decision (only when skipgram_prb > 0 and skipgram_size >= 2) followed by randint(2, size)
+    when it fires; one shuffle if whole-word / n-gram expansion overshot; per kept position random() < 0.8 -> mask token,
+    else random() < 0.5 -> randint over the vocabulary, else unchanged."""
+
+    def __init__(self, vocab, mask_prob, mask_max, skipgram_prb=0.2, skipgram_size=3, mask_whole_word=True, use_roberta=False,
+                 rng=None):
+        if hasattr(vocab, "get_vocab"):
+            table = vocab.get_vocab()
+            self.id2token = {i: w for w, i in table.items()}
+            self.cls_token, self.mask_token = vocab.cls_token, vocab.mask_token
+        else:
+            id2token, self.cls_token, self.mask_token = vocab
+            self.id2token = dict(enumerate(id2token)) if not isinstance(id2token, dict) else id2token
+        n = len(self.id2token)
+        if any(i not in self.id2token for i in range(n)):
+            raise ValueError("TextMasker: vocabulary ids must be dense 0..V-1 (pretrain_dataset.py:67-68)")
+        self.vocab_size = n
+        self.mask_prob, self.mask_max = mask_prob, mask_max
+        self.skipgram_prb, self.skipgram_size = skipgram_prb, skipgram_size
+        self.mask_whole_word, self.use_roberta = mask_whole_word, use_roberta
+        self.rng = rng if rng is not None else _random
+
+    def _word_span(self, tokens, st, end):
+        """Grow [st, end) to word boundaries: byte-level BPE marks a word START with 'Ġ', WordPiece a CONTINUATION with
+        '##' (pretrain_dataset.py:102-118, including its asymmetric lower bounds 1 and 0)."""
+        n = len(tokens)
+        if self.use_roberta:
+            while st > 1 and tokens[st][0] != "Ġ":
+                st -= 1
+            while end < n and tokens[end][0] != "Ġ":
+                end += 1
+        else:
+            while st >= 0 and tokens[st].startswith("##"):
+                st -= 1
+            while end < n and tokens[end].startswith("##"):
+                end += 1
+        return st, end
+
+    def __call__(self, tokens):
+        """tokens: list of token strings starting with the cls token; corrupted IN PLACE.  Returns (tokens, masked_pos)."""
+        rng = self.rng
+        if tokens[0] != self.cls_token:
+            raise AssertionError("TextMasker: tokens must start with the cls token")
+        budget = min(self.mask_max, max(1, int(round(len(tokens) * self.mask_prob))))
+        order = list(range(1, len(tokens)))
+        rng.shuffle(order)
+        last = max(order)
+        ngrams = self.skipgram_prb > 0 and self.skipgram_size >= 2
+        chosen = set()                    # a set, like the reference: list(chosen) below inherits CPython's set order
+        for pos in order:
+            if len(chosen) >= budget:
+                break
+            if pos in chosen:
+                continue
+            width = rng.randint(2, self.skipgram_size) if (ngrams and rng.random() < self.skipgram_prb) else 1
+            st, end = (self._word_span(tokens, pos, pos + width) if self.mask_whole_word else (pos, pos + width))
+            for mp in range(st, end):
+                if not 0 < mp <= last:
+                    break
+                chosen.add(mp)
+        masked_pos = list(chosen)
+        if len(masked_pos) > budget:
+            rng.shuffle(masked_pos)
+            masked_pos = masked_pos[:budget]
+        for pos in masked_pos:
+            if rng.random() < 0.8:
+                tokens[pos] = self.mask_token
+            elif rng.random() < 0.5:
+                tokens[pos] = self.id2token[rng.randint(0, self.vocab_size - 1)]
+        return tokens, masked_pos
+
+
+_PUNCT = re.compile(r"([,.'!?\"()*#:;~])")
+_SPACES = re.compile(r"\s{2,}")
+
+
+def pre_caption(caption, max_words):
+    """dataset/utils.py:38-66: lower-case, punctuation -> space, '-' and '/' -> space, '<person>' -> 'person', runs of
+    white space collapsed, stripped, truncated to max_words; an empty result is an error."""
+    raw = caption
+    c = _PUNCT.sub(" ", caption.lower()).replace("-", " ").replace("/", " ").replace("<person>", "person")
+    c = _SPACES.sub(" ", c).rstrip("\n").strip(" ")
+    words = c.split(" ")
+    if len(words) > max_words:
+        c = " ".join(words[:max_words])
+    if not c:
+        raise ValueError(f"pre_caption yields invalid text (raw: {raw})")
+    return c
+
+
+class TextPreprocessor:
+    """caption -> (text_ids, text_atts, text_ids_masked, masked_pos, masked_ids), python int lists padded to max_tokens /
+    max_masks (pretrain_dataset.py:264-300; `corpus=True`: the text-only stream of :690-726, which skips pre_caption and
+    splits pre-tokenized text on spaces)."""
+
+    def __init__(self, tokenizer, masker, max_tokens, max_masks, max_words=None, tokenized=False, language_chosen=None,
+                 corpus=False, add_eos=True):
+        self.tokenizer, self.masker = tokenizer, masker
+        self.max_tokens, self.max_masks, self.max_words = max_tokens, max_masks, max_words
+        self.tokenized, self.language_chosen, self.corpus, self.add_eos = tokenized, language_chosen, corpus, add_eos
+        self.cls_token, self.eos_token = tokenizer.cls_token, tokenizer.sep_token
+        self.pad_token_id = tokenizer.pad_token_id
+
+    def tokens_of(self, text):
+        if self.corpus:
+            if self.tokenized:
+                return text.strip().split(" ")
+            if self.language_chosen == "zh":
+                text = text.replace(" ", "")
+            return self.tokenizer.tokenize(text)
+        if self.tokenized:      # regions tokenized by BERT earlier: glue the word pieces back before re-tokenizing
+            text = text.strip().replace(" ##", "")
+        if self.language_chosen == "zh":
+            text = text.replace(" ", "")
+        return self.tokenizer.tokenize(pre_caption(text, self.max_words))
+
+    def preprocess(self, text):
+        L = self.max_tokens
+        tokens = [self.cls_token] + self.tokens_of(text)[:L - 1]
+        if self.add_eos:
+            tokens = tokens[:L - 1] + [self.eos_token]
+        n = len(tokens)
+        if n < 2:
+            raise AssertionError("len(word tokens) < 2")
+        ids = self.tokenizer.convert_tokens_to_ids(tokens)
+        corrupted, masked_pos = self.masker(list(tokens))
+        ids_masked = self.tokenizer.convert_tokens_to_ids(corrupted)
+        masked_ids = [ids[p] for p in masked_pos]
+        pad, mpad = [self.pad_token_id] * (L - n), self.max_masks - len(masked_ids)
+        return (ids + pad, [1] * n + [0] * (L - n), ids_masked + pad, masked_pos + [0] * mpad, masked_ids + [PAD_MASK] * mpad)
+
+
+# ---------------------------------------------------------------------------------------------------------- region side
+def region_image_atts(x, y, w, h, patch_size, num_patch):
+    """Pixel box (after crop / flip / resize) -> 0/1 list of length 1 + num_patch^2: token 0 always on, then every patch the
+    box touches, at least one per axis (pretrain_dataset.py:577-592)."""
+    x0 = min(math.floor(x / patch_size), num_patch - 1)
+    x1 = max(x0 + 1, min(math.ceil((x + w) / patch_size), num_patch))
+    y0 = min(math.floor(y / patch_size), num_patch - 1)
+    y1 = max(y0 + 1, min(math.ceil((y + h) / patch_size), num_patch))
+    atts = [0] * (1 + num_patch * num_patch)
+    atts[0] = 1
+    for i in range(y0, y1):
+        row = num_patch * i + 1
+        for j in range(x0, x1):
+            if not 0 < row + j <= num_patch * num_patch:
+                raise AssertionError(f"patch index out of range, index: {row + j}")
+            atts[row + j] = 1
+    return atts
+
+
+class RegionSampler:
+    """One region-annotated image -> the per-region samples of pretrain_dataset.py:445-575, in two phases because the pixel
+    work (crop, flip, resize, box_transform — whose RandAugment draws from the same global generator) sits between them:
+
+        plan = sampler.plan(ann, W, H)            # random crop containing one region + the flip decision
+        image = box_transform(resize(maybe_hflip(pil.crop(plan.crop_box))))
+        sample = sampler.finish(ann, plan, image)  # texts, patch masks, cxcywh targets, is_image flags
+    """
+
+    class Plan:
+        __slots__ = ("x0", "y0", "w0", "h0", "hflip")
+
+        @property
+        def crop_box(self):
+            return (self.x0, self.y0, self.x0 + self.w0, self.y0 + self.h0)
+
+    def __init__(self, text, image_res, patch_size, max_regions, min_perc_in_image, careful_hflip=False, rng=None):
+        self.text, self.image_res, self.patch_size = text, image_res, patch_size
+        if image_res % patch_size:
+            raise AssertionError("image_res must be a multiple of patch_size")
+        self.num_patch = image_res // patch_size
+        self.max_regions, self.min_perc, self.careful_hflip = max_regions, min_perc_in_image, careful_hflip
+        self.rng = rng if rng is not None else _random
+
+    @staticmethod
+    def _bb(elem):
+        x, y, w, h = elem["bb"]
+        return int(x), int(y), int(w), int(h)
+
+    @staticmethod
+    def mentions_side(ann):
+        """'left' / 'right' in any caption of the image or its regions (pretrain_dataset.py:425-443): such images are not
+        flipped when careful_hflip is set."""
+        def has(e):
+            c = e["caption"]
+            return any(("left" in s) or ("right" in s) for s in (c if isinstance(c, list) else [c]))
+        return ("caption" in ann and has(ann)) or any(has(e) for e in ann["elems"])
+
+    def _caption(self, c):
+        rng = self.rng
+        if isinstance(c, list):
+            c = rng.choice(c)
+        if isinstance(c, str):
+            return c
+        if isinstance(c, dict):
+            lang = self.text.language_chosen
+            v = rng.choice(list(c.values())) if lang is None else c[lang]
+            if not isinstance(v, str):
+                raise AssertionError("caption entry is not a string")
+            return v
+        raise ValueError(c)
+
+    def plan(self, ann, W, H):
+        rng = self.rng
+        x, y, w, h = self._bb(rng.choice(ann["elems"]))
+        if not (x >= 0 and y >= 0 and x + w <= W and y + h <= H and w > 0 and h > 0):
+            raise AssertionError("elem invalid")
+        p = self.Plan()
+        p.x0, p.y0 = rng.randint(0, math.floor(x)), rng.randint(0, math.floor(y))
+        x1, y1 = rng.randint(min(math.ceil(x + w), W), W), rng.randint(min(math.ceil(y + h), H), H)
+        p.w0, p.h0 = x1 - p.x0, y1 - p.y0
+        if not (p.x0 >= 0 and p.y0 >= 0 and p.x0 + p.w0 <= W and p.y0 + p.h0 <= H and p.w0 > 0 and p.h0 > 0):
+            raise AssertionError("elem randomcrop, invalid")
+        p.hflip = rng.random() < 0.5 and not (self.careful_hflip and self.mentions_side(ann))
+        return p
+
+    def finish(self, ann, plan, image):
+        res, left = self.image_res, self.max_regions
+        cols = [[] for _ in range(8)]   # ids, atts, ids_masked, masked_pos, masked_ids, image_atts, target_bbox, is_image
+
+        def push(text5, atts, box, flag):
+            for c, v in zip(cols, (*text5, atts, box, flag)):
+                c.append(v)
+
+        if "caption" in ann:
+            push(self.text.preprocess(self._caption(ann["caption"])), [1] * (self.num_patch ** 2 + 1),
+                 torch.tensor([0.5, 0.5, 1, 1], dtype=torch.float), 1)
+            left -= 1
+        x0, y0, W, H = plan.x0, plan.y0, plan.w0, plan.h0
+        for elem in self.rng.sample(ann["elems"], len(ann["elems"])):
+            if left <= 0:
+                break
+            x, y, w, h = self._bb(elem)
+            xx, yy, xm, ym = max(x0, x), max(y0, y), min(x0 + W, x + w), min(y0 + H, y + h)
+            if not (xm > xx and ym > yy and (xm - xx) * (ym - yy) / (w * h) > self.min_perc):
+                continue
+            x, y, w, h = xx - x0, yy - y0, xm - xx, ym - yy        # the visible part, in crop coordinates
+            if plan.hflip:
+                x = (W - x) - w
+            x, w, y, h = res / W * x, res / W * w, res / H * y, res / H * h
+            caption = self._caption(elem["caption"])
+            if "attributes" in elem:
+                caption = self._caption(elem["attributes"]) + " " + caption
+            text5 = self.text.preprocess(caption)
+            push(text5, region_image_atts(x, y, w, h, self.patch_size, self.num_patch),
+                 torch.tensor([(x + 1 / 2 * w) / res, (y + 1 / 2 * h) / res, w / res, h / res], dtype=torch.float), 0)
+            left -= 1
+        return ([image] if cols[0] else [], *cols)
+
+
+def _stack_column(x):
+    if x[0] is None:
+        return None
+    if isinstance(x[0], torch.Tensor):
+        return torch.stack(x)
+    return torch.tensor(x, dtype=torch.long)
+
+
+def collate(batch):
+    """List of per-sample tuples -> list of batch tensors: tensors stacked, int lists as int64, None kept
+    (pretrain_dataset.py:302-312)."""
+    return [_stack_column(x) for x in zip(*batch)]
+
+
+def region_collate(batch_sample, batch_size, rng=None, warn=print):
+    """RegionSampler samples -> [images, idx_to_group_img, text_ids, text_atts, text_ids_masked, masked_pos, masked_ids,
+    image_atts, target_bbox, is_image] with exactly batch_size region samples (pretrain_dataset.py:594-643): all images that
+    produced at least one sample are stacked, the flattened samples are sub-sampled (or padded by re-sampling, or by
+    repetition when fewer than half are there) to the fixed size every rank must have."""
+    rng = rng if rng is not None else _random
+    images, *cols = (list(c) for c in zip(*batch_sample))
+    group, img = [], -1
+    for s in cols[0]:
+        if len(s):
+            img += 1
+            group += [img] * len(s)
+    n = len(group)
+    keep = list(range(n))
+    if n >= batch_size:
+        keep = rng.sample(keep, batch_size)
+    else:
+        try:
+            extra = rng.sample(keep, batch_size - n)
+            keep += extra
+            warn("### warning: pad region_batch by sampling, ", len(extra), flush=True)
+        except ValueError:
+            warn("### warning: pad region_batch by expanding, ", batch_size - n, flush=True)
+            keep = (keep * math.ceil(batch_size / n))[:batch_size]
+    out = [torch.stack([im for per in images for im in per]), torch.tensor([group[i] for i in keep], dtype=torch.long)]
+    for c in cols:
+        flat = [v for per in c for v in per]
+        out.append(_stack_column([flat[i] for i in keep]))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------- device side
+def to_uint8_hwc(pic):
+    """The transform that replaces `transforms.ToTensor(), normalize` at the end of a Compose: PIL RGB image or uint8
+    ndarray [H, W, 3] -> torch.uint8 [H, W, 3] (no arithmetic; DeviceFeeder finishes the transform on the GPU)."""
+    import numpy as np
+
+    a = np.asarray(pic)
+    if a.dtype != np.uint8 or a.ndim != 3 or a.shape[2] != 3:
+        raise ValueError(f"to_uint8_hwc: expected an RGB uint8 image, got {a.dtype} {a.shape}")
+    return torch.from_numpy(np.ascontiguousarray(a) if a.flags.writeable else np.array(a))
+
+
+def _is_u8_image(t):
+    return t.dtype == torch.uint8 and t.dim() == 4 and t.shape[3] == 3
+
+
+class DeviceFeeder:
+    """Iterate `loader` (batches = list / tuple / dict of tensors, None or plain python values) and yield the same
+    structure on the device, `depth` batches ahead of the consumer.
+
+    Per batch: every host tensor is staged in a pinned buffer of its slot (skipped when the loader already pins), copied on a
+    private copy stream, and uint8 [B, H, W, 3] image tensors are finished there by `xfm_image_u8_to_f32` (ToTensor +
+    Normalize with `mean` / `std`, optional random hflip with probability `flip_prob` per sample drawn from `generator`).
+    `__next__` makes the consumer's current stream wait for that batch's event — no host synchronisation — and hands the
+    tensors over with `record_stream`, so the caching allocator does not recycle them under the consumer.
+    `h2d_bytes` counts what crossed PCIe."""
+
+    def __init__(self, loader, device=None, depth=2, mean=CLIP_MEAN, std=CLIP_STD, flip_prob=0.0, generator=None):
+        from . import lib
+        if not torch.cuda.is_available():
+            raise RuntimeError("xfm_b200.feed.DeviceFeeder needs a CUDA device (sm_100a); there is no CPU path")
+        lib.lib()
+        self._L = lib
+        self.loader, self.depth = loader, max(1, int(depth))
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.mean, self.std, self.flip_prob, self.generator = tuple(mean), tuple(std), float(flip_prob), generator
+        self.stream = torch.cuda.Stream(self.device)
+        self._slots = [dict(pinned={}, event=None) for _ in range(self.depth + 1)]
+        self._n = 0
+        self.h2d_bytes = 0
+
+    def __len__(self):
+        return len(self.loader)
+
+    def _stage(self, slot, key, t):
+        if t.is_pinned():
+            return t
+        t = t.contiguous()
+        buf = slot["pinned"].get(key)
+        if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
+            buf = slot["pinned"][key] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        buf.copy_(t)
+        return buf
+
+    def _upload(self, batch):
+        slot = self._slots[self._n % len(self._slots)]
+        self._n += 1
+        if slot["event"] is not None:
+            slot["event"].synchronize()      # the copies that last read this slot's pinned buffers (depth + 1 batches ago)
+        items = batch.items() if isinstance(batch, dict) else enumerate(batch)
+        out = {}
+        with torch.cuda.stream(self.stream):
+            for k, v in items:
+                if not isinstance(v, torch.Tensor):
+                    out[k] = v
+                    continue
+                if v.device.type != "cpu":
+                    out[k] = v
+                    continue
+                d = self._stage(slot, k, v).to(self.device, non_blocking=True)
+                self.h2d_bytes += d.numel() * d.element_size()
+                if _is_u8_image(d):
+                    flip = None
+                    if self.flip_prob > 0:
+                        draw = torch.rand(d.shape[0], generator=self.generator) < self.flip_prob
+                        flip = self._stage(slot, (k, "flip"), draw.to(torch.uint8)).to(self.device, non_blocking=True)
+                        self.h2d_bytes += flip.numel()
+                    d = self._L.image_u8_to_f32(d, self.mean, self.std, flip=flip)
+                out[k] = d
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        slot["event"] = ev
+        if isinstance(batch, dict):
+            return out, ev
+        seq = [out[i] for i in range(len(out))]
+        return (tuple(seq) if isinstance(batch, tuple) else seq), ev
+
+    def __iter__(self):
+        it = iter(self.loader)
+        queue = []
+        done = False
+        while True:
+            while not done and len(queue) < self.depth:
+                try:
+                    queue.append(self._upload(next(it)))
+                except StopIteration:
+                    done = True
+            if not queue:
+                return
+            batch, ev = queue.pop(0)
+            cur = torch.cuda.current_stream(self.device)
+            cur.wait_event(ev)
+            for v in (batch.values() if isinstance(batch, dict) else batch):
+                if isinstance(v, torch.Tensor) and v.is_cuda:
+                    v.record_stream(cur)
+            yield batch

@@ -648,6 +648,20 @@ def bbox_loss(coord, target, is_image=None):
     return lb, lg, db, dg
 
 
+def image_u8_to_f32(img_u8, mean, std, flip=None, out=None):
+    """ToTensor + Normalize (+ hflip) of dataset/__init__.py:26-35 on the device: img_u8 u8 [B, H, W, 3] -> f32 [B, 3, H, W]
+    = (u8 / 255 - mean[c]) / std[c]; flip u8 [B] or None.  Bit-identical to the CPU transform."""
+    assert img_u8.dtype == torch.uint8 and img_u8.dim() == 4 and img_u8.shape[3] == 3 and img_u8.is_contiguous()
+    B, H, W, _ = img_u8.shape
+    assert flip is None or (flip.dtype == torch.uint8 and flip.numel() == B and flip.is_contiguous())
+    if out is None:
+        out = torch.empty((B, 3, H, W), dtype=torch.float32, device=img_u8.device)
+    assert out.dtype == torch.float32 and out.shape == (B, 3, H, W) and out.is_contiguous()
+    m, s = (C.c_float * 3)(*[float(v) for v in mean]), (C.c_float * 3)(*[float(v) for v in std])
+    check(lib().xfm_image_u8_to_f32(_p(img_u8), _p(out), _p(flip), B, H, W, m, s, stream_ptr()), "xfm_image_u8_to_f32")
+    return out
+
+
 def axpby_scalars(a, sa, b, sb):
     """a * sa[0] + b * sb[0] (sa / sb: f32 [1] device tensors or None = 0)."""
     assert a.dtype == torch.float32 and a.is_contiguous() and b.is_contiguous() and a.shape == b.shape
