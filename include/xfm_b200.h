@@ -286,6 +286,16 @@ int xfm_axpby_scalars(const float* a, const float* sa, const float* b, const flo
  *   mean, stdv             HOST pointers to 3 floats each (baked into the launch; graph-capturable) */
 int xfm_image_u8_to_f32(const uint8_t* in, float* out, const uint8_t* flip, int B, int H, int W, const float* mean,
                         const float* stdv, void* stream);
+/* Crop + bicubic resize of B ragged uint8 RGB images to [OH, OW]: RandomResizedCrop / Resize with InterpolationMode.BICUBIC
+ * (dataset/__init__.py:28-30,63-67) and crop + resize of dataset/pretrain_dataset.py:470-483, i.e. Pillow's ImagingResample
+ * (third party, reached through torchvision): horizontal then vertical pass in 8.22 fixed point with a uint8 intermediate.
+ *   src   u8 packed images, each [h, w, 3]           desc  int64 [B, 8]: {byte offset in src, image width, crop x0, crop y0,
+ *   hb/vb int32 [B, OW|OH, 2]: first tap, tap count        crop width, crop height, byte offset of the image's rows in tmp, 0}
+ *   hk/vk int32 [B, OW|OH, KH|KV]: taps * 2^22 (Pillow's precompute_coeffs + normalize_coeffs_8bpc, computed on the host)
+ *   tmp   u8 scratch, sum_b crop_height_b * OW * 3 bytes   out   u8 [B, OH, OW, 3]      max_rows = max_b crop height
+ * All pointers are device pointers.  Bit-identical to PIL.Image.crop(box).resize((OW, OH), BICUBIC). */
+int xfm_resize_bicubic_u8(const uint8_t* src, const int64_t* desc, const int32_t* hb, const int32_t* hk, int KH, const int32_t* vb,
+                          const int32_t* vk, int KV, uint8_t* tmp, uint8_t* out, int B, int max_rows, int OH, int OW, void* stream);
 
 /* Flat-buffer optimizer step (accelerators/ddp_accelerator.py:89-98 clip_grad_norm_ + optimizer.step with the
  * transformers AdamW of optim.py:4-50).  P/G/M/V: f32 buffers of nchunks*64 elements, S: bf16 shadow (may be null).

@@ -175,3 +175,53 @@ def test_device_feeder_refuses_to_run_without_cuda():
         pytest.skip("CUDA present")
     with pytest.raises(RuntimeError):
         feed.DeviceFeeder([])
+
+
+def _resample_with_taps(img, box, out_h, out_w):
+    """Evaluate xfm_b200.feed's tap tables the way csrc/feed.cu does (horizontal pass into uint8, then vertical), in numpy."""
+    import numpy as np
+    x0, y0, x1, y1 = box
+    plan = feed.crop_resize_plan([img.shape[:2]], [box], out_h, out_w)
+    src = img[y0:y1, x0:x1].astype(np.int64)
+    hb, hk, vb, vk = (plan[k][0].numpy().astype(np.int64) for k in ("hb", "hk", "vb", "vk"))
+    idx = np.minimum(hb[:, :1] + np.arange(hk.shape[1])[None, :], src.shape[1] - 1)
+    tmp = np.clip(((src[:, idx, :] * hk[None, :, :, None]).sum(2) + (1 << 21)) >> 22, 0, 255)
+    idx = np.minimum(vb[:, :1] + np.arange(vk.shape[1])[None, :], src.shape[0] - 1)
+    return np.clip(((tmp[idx, :, :] * vk[:, :, None, None]).sum(1) + (1 << 21)) >> 22, 0, 255).astype(np.uint8)
+
+
+def test_pillow_bicubic_taps_reproduce_pil_resize():
+    """The host half of the GPU crop + resize: tap tables in Pillow's 8.22 fixed point.  Evaluated with integer arithmetic they
+    give PIL's `crop(box).resize(size, BICUBIC)` bit for bit (down- and up-scaling, full image, thin crops)."""
+    np = pytest.importorskip("numpy")
+    from PIL import Image
+    rng = np.random.default_rng(7)
+    for t in range(24):
+        H, W = int(rng.integers(12, 500)), int(rng.integers(12, 500))
+        img = rng.integers(0, 256, size=(H, W, 3), dtype=np.uint8)
+        x0, y0 = int(rng.integers(0, W - 6)), int(rng.integers(0, H - 6))
+        box = (x0, y0, int(rng.integers(x0 + 3, W + 1)), int(rng.integers(y0 + 3, H + 1)))
+        if t % 4 == 0:
+            box = (0, 0, W, H)
+        oh, ow = [(224, 224), (384, 384), (32, 48)][t % 3]
+        ref = np.asarray(Image.fromarray(img).crop(box).resize((ow, oh), Image.BICUBIC))
+        assert (_resample_with_taps(img, box, oh, ow) == ref).all(), (t, (H, W), box, (oh, ow))
+    first, count, taps = feed.pillow_bicubic_taps(224, 224)          # same size: the identity
+    assert (taps.sum(1) == 1 << 22).all() and ((taps != 0).sum(1) == 1).all()
+    assert (first + np.argmax(taps, 1) == np.arange(224)).all()
+
+
+def test_crop_resize_plan_layout_and_errors():
+    plan = feed.crop_resize_plan([(50, 40), (30, 70)], [(0, 0, 40, 50), (10, 5, 70, 25)], 16, 24)
+    d = plan["desc"]
+    assert d.dtype == torch.int64 and d.shape == (2, 8)
+    assert d[0].tolist() == [0, 40, 0, 0, 40, 50, 0, 0] and d[1].tolist() == [50 * 40 * 3, 70, 10, 5, 60, 20, 50 * 24 * 3, 0]
+    assert plan["src_bytes"] == (50 * 40 + 30 * 70) * 3 and plan["tmp_bytes"] == (50 + 20) * 24 * 3 and plan["max_rows"] == 50
+    assert plan["hb"].shape == (2, 24, 2) and plan["vb"].shape == (2, 16, 2) and plan["hk"].dtype == torch.int32
+    assert plan["hk"].shape[2] == max(feed.pillow_bicubic_taps(40, 24)[2].shape[1], feed.pillow_bicubic_taps(60, 24)[2].shape[1])
+    for bad in [(0, 0, 41, 50), (5, 0, 5, 50), (-1, 0, 40, 50)]:
+        with pytest.raises(ValueError):
+            feed.crop_resize_plan([(50, 40)], [bad], 16, 24)
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            feed.crop_resize([torch.zeros(8, 8, 3, dtype=torch.uint8)], [None], 4, 4)

@@ -119,3 +119,44 @@ def test_device_feeder_feeds_the_pretraining_model():
     assert fed.keys() == direct.keys() and fed["loss_itc"] > 0 and fed["loss_mlm"] > 0
     for k in fed:   # identical inputs; the loss reductions use fp32 atomics, hence not `==`
         assert abs(fed[k] - direct[k]) <= 1e-5 * max(1.0, abs(direct[k])), (k, fed[k], direct[k])
+
+
+@pytest.mark.parametrize("res", [224, 384])
+def test_crop_resize_is_bit_identical_to_pil(res):
+    """RandomResizedCrop / Resize with InterpolationMode.BICUBIC (dataset/__init__.py:28-30,63-67) on a ragged batch: the GPU
+    result equals PIL's crop(box).resize((res, res), BICUBIC) byte for byte; chained with the normalize kernel it equals
+    torchvision's Resize -> ToTensor -> Normalize."""
+    import numpy as np
+    from PIL import Image
+    from xfm_b200 import feed, lib
+    rng = np.random.default_rng(res)
+    images, boxes = [], []
+    for t in range(9):
+        H, W = int(rng.integers(16, 640)), int(rng.integers(16, 640))
+        img = rng.integers(0, 256, size=(H, W, 3), dtype=np.uint8)
+        if t % 3 == 1:      # smooth content
+            img = ((np.add.outer(np.arange(H) * 2, np.arange(W))[:, :, None] * np.array([1, 2, 3])) % 256).astype(np.uint8)
+        x0, y0 = int(rng.integers(0, W - 8)), int(rng.integers(0, H - 8))
+        box = (x0, y0, int(rng.integers(x0 + 4, W + 1)), int(rng.integers(y0 + 4, H + 1)))
+        images.append(img)
+        boxes.append(None if t % 4 == 0 else box)
+    images.append(rng.integers(0, 256, size=(res, res, 3), dtype=np.uint8))     # already the target size: identity
+    boxes.append(None)
+    n0 = lib.launch_count()
+    out = feed.crop_resize([torch.from_numpy(im) for im in images], boxes, res, res)
+    assert lib.launch_count() - n0 == 2
+    assert out.is_cuda and out.dtype == torch.uint8 and out.shape == (len(images), res, res, 3)
+    got = out.cpu().numpy()
+    for i, (img, box) in enumerate(zip(images, boxes)):
+        pil = Image.fromarray(img)
+        ref = np.asarray((pil if box is None else pil.crop(box)).resize((res, res), Image.BICUBIC))
+        assert (got[i] == ref).all(), (i, img.shape, box, int(np.abs(got[i].astype(int) - ref.astype(int)).max()))
+    assert (got[-1] == images[-1]).all()
+    tv = pytest.importorskip("torchvision.transforms")
+    test_transform = tv.Compose([tv.Resize((res, res), interpolation=tv.InterpolationMode.BICUBIC), tv.ToTensor(),
+                                 tv.Normalize(feed.CLIP_MEAN, feed.CLIP_STD)])
+    whole = [i for i, b in enumerate(boxes) if b is None]
+    f32 = lib.image_u8_to_f32(out, feed.CLIP_MEAN, feed.CLIP_STD).cpu()
+    for i in whole:
+        assert torch.equal(f32[i], test_transform(Image.fromarray(images[i])))
+    assert feed.crop_resize([], [], res, res).shape == (0, res, res, 3)

@@ -217,6 +217,10 @@ int xfm_bbox_loss(const float* coord, const float* target, const float* is_image
 int xfm_axpby_scalars(const float* a, const float* sa, const float* b, const float* sb, float* out, int n, void* stream) {
   return axpby_scalars(a, sa, b, sb, out, n, ST);
 }
+int xfm_resize_bicubic_u8(const uint8_t* src, const int64_t* desc, const int32_t* hb, const int32_t* hk, int KH, const int32_t* vb,
+                          const int32_t* vk, int KV, uint8_t* tmp, uint8_t* out, int B, int max_rows, int OH, int OW, void* stream) {
+  return resize_bicubic_u8(src, desc, hb, hk, KH, vb, vk, KV, tmp, out, B, max_rows, OH, OW, ST);
+}
 int xfm_image_u8_to_f32(const uint8_t* in, float* out, const uint8_t* flip, int B, int H, int W, const float* mean,
                         const float* stdv, void* stream) {
   return image_u8_to_f32(in, out, flip, B, H, W, mean, stdv, ST);

@@ -77,4 +77,73 @@ int image_u8_to_f32(const uint8_t* in, float* out, const uint8_t* flip, int B, i
   return (int)cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Crop + bicubic resize of uint8 images: what `RandomResizedCrop(res, interpolation=BICUBIC)`, `Resize((res, res), BICUBIC)`
+// (dataset/__init__.py:28-30,63-67) and `image.crop(...)` + `resize(image, [res, res], BICUBIC)` (dataset/pretrain_dataset.py:
+// 470-483) do through torchvision -> Pillow (third party; Pillow's ImagingResample, src/libImaging/Resample.c): a separable
+// convolution in 8.22 fixed point, horizontal pass first into a uint8 intermediate, then the vertical pass, each output
+// = clip8((2^21 + sum_k coef[k] * pixel[k]) >> 22).  The coefficient tables come from the host (xfm_b200/feed.py restates
+// Pillow's precompute_coeffs / normalize_coeffs_8bpc in float64); the kernels do the integer arithmetic, so the result is
+// bit-identical to Pillow's (tests/test_feed_gpu.py compares with PIL itself).
+//
+// Images are ragged: `src` is one packed byte buffer; desc[b] = {byte offset of image b, its width in pixels, crop x0, crop y0,
+// crop width, crop height, byte offset of its rows in `tmp`, 0}.
+struct ResizeDesc {
+  int64_t src_off, src_w, x0, y0, cw, ch, tmp_off, pad;
+};
+
+XFM_DEVINL uint8_t clip8_fixed(int v) {
+  v >>= 22;
+  return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+}
+
+// tmp[b][row][x][c] = horizontal pass of crop row `row`; one thread per output pixel (3 channels), grid (x blocks, rows, B).
+__global__ void __launch_bounds__(128)
+resize_h_kernel(const uint8_t* __restrict__ src, const ResizeDesc* __restrict__ desc, const int32_t* __restrict__ hb,
+                const int32_t* __restrict__ hk, int KH, uint8_t* __restrict__ tmp, int OW) {
+  const int b = blockIdx.z, row = blockIdx.y, x = blockIdx.x * blockDim.x + threadIdx.x;
+  const ResizeDesc d = desc[b];
+  if (row >= d.ch || x >= OW) return;
+  const int xmin = hb[((size_t)b * OW + x) * 2], n = hb[((size_t)b * OW + x) * 2 + 1];
+  const int32_t* k = hk + ((size_t)b * OW + x) * KH;
+  const uint8_t* p = src + d.src_off + ((d.y0 + row) * d.src_w + d.x0 + xmin) * 3;
+  int r = 1 << 21, g = 1 << 21, bl = 1 << 21;
+  for (int i = 0; i < n; ++i) {
+    const int w = __ldg(k + i);
+    r += w * p[3 * i]; g += w * p[3 * i + 1]; bl += w * p[3 * i + 2];
+  }
+  uint8_t* o = tmp + d.tmp_off + ((size_t)row * OW + x) * 3;
+  o[0] = clip8_fixed(r); o[1] = clip8_fixed(g); o[2] = clip8_fixed(bl);
+}
+
+// out[b][y][x][c] = vertical pass over tmp; one thread per output BYTE (x * 3 + c): fully coalesced rows.
+__global__ void __launch_bounds__(128)
+resize_v_kernel(const uint8_t* __restrict__ tmp, const ResizeDesc* __restrict__ desc, const int32_t* __restrict__ vb,
+                const int32_t* __restrict__ vk, int KV, uint8_t* __restrict__ out, int OH, int OW) {
+  const int b = blockIdx.z, y = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= OW * 3) return;
+  const ResizeDesc d = desc[b];
+  const int ymin = vb[((size_t)b * OH + y) * 2], n = vb[((size_t)b * OH + y) * 2 + 1];
+  const int32_t* k = vk + ((size_t)b * OH + y) * KV;
+  const uint8_t* p = tmp + d.tmp_off + (size_t)ymin * OW * 3 + j;
+  int acc = 1 << 21;
+  for (int i = 0; i < n; ++i) acc += __ldg(k + i) * p[(size_t)i * OW * 3];
+  out[((size_t)b * OH + y) * OW * 3 + j] = clip8_fixed(acc);
+}
+
+int resize_bicubic_u8(const uint8_t* src, const int64_t* desc, const int32_t* hb, const int32_t* hk, int KH, const int32_t* vb,
+                      const int32_t* vk, int KV, uint8_t* tmp, uint8_t* out, int B, int max_rows, int OH, int OW, cudaStream_t s) {
+  if (B < 0 || OH <= 0 || OW <= 0 || KH <= 0 || KV <= 0 || max_rows <= 0 || max_rows > 65535 || OH > 65535 || B > 65535) {
+    set_error("resize_bicubic_u8: need 0 <= B <= 65535, 0 < OH, max_rows <= 65535, OW > 0, KH > 0, KV > 0");
+    return XFM_ERR_BAD_ARG;
+  }
+  if (B == 0) return 0;
+  if (!src || !desc || !hb || !hk || !vb || !vk || !tmp || !out) { set_error("resize_bicubic_u8: null pointer"); return XFM_ERR_BAD_ARG; }
+  static_assert(sizeof(ResizeDesc) == 8 * sizeof(int64_t), "desc layout");
+  resize_h_kernel<<<dim3((OW + 127) / 128, max_rows, B), 128, 0, s>>>(src, (const ResizeDesc*)desc, hb, hk, KH, tmp, OW);
+  resize_v_kernel<<<dim3((OW * 3 + 127) / 128, OH, B), 128, 0, s>>>(tmp, (const ResizeDesc*)desc, vb, vk, KV, out, OH, OW);
+  count_launch(2);
+  return (int)cudaGetLastError();
+}
+
 }  // namespace xfm

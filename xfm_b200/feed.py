@@ -19,7 +19,14 @@ Device half:
                               batch of 96 crosses PCIe as 14.5 MB instead of 57.8 MB and the result is bit-identical to the CPU
                               transform.
 
-JPEG decode, RandomResizedCrop and RandAugment stay PIL work in the DataLoader workers.  There is no CPU path for
+  * `crop_resize`             `RandomResizedCrop(BICUBIC)` / `Resize(BICUBIC)` (dataset/__init__.py:28-30,63-67) and the region
+                              loader's crop + resize (pretrain_dataset.py:470-483) on the GPU for ragged uint8 images:
+                              Pillow's fixed-point separable resampler, tap tables from the host (`pillow_bicubic_taps`),
+                              integer passes in `xfm_resize_bicubic_u8`; bit-identical to PIL.  Complete for the evaluation
+                              transform (decode -> resize -> normalize); the training Compose keeps RandAugment (cv2, on the
+                              host) between crop and ToTensor, so there it is an option for loaders that augment after it.
+
+JPEG decode and RandAugment stay CPU work in the DataLoader workers.  There is no CPU path for
 the device half: `DeviceFeeder` raises without a CUDA device.
 """
 import math
@@ -347,6 +354,95 @@ def to_uint8_hwc(pic):
     if a.dtype != np.uint8 or a.ndim != 3 or a.shape[2] != 3:
         raise ValueError(f"to_uint8_hwc: expected an RGB uint8 image, got {a.dtype} {a.shape}")
     return torch.from_numpy(np.ascontiguousarray(a) if a.flags.writeable else np.array(a))
+
+
+# ------------------------------------------------------------------------------------- crop + bicubic resize (Pillow-exact)
+_PRECISION_BITS = 32 - 8 - 2      # Pillow, src/libImaging/Resample.c: 8-bit pixels, 22 fractional bits, int32 accumulator
+
+
+def pillow_bicubic_taps(in_size, out_size):
+    """The tap tables Pillow builds for `resize(..., BICUBIC)` of an axis of in_size pixels to out_size
+    (precompute_coeffs with box (0, in_size) + normalize_coeffs_8bpc; bicubic with a = -0.5, support 2 * max(scale, 1)):
+    (first int32 [out], count int32 [out], taps int32 [out, ksize]) with output = clip8((2^21 + sum taps * pixels) >> 22).
+    float64 arithmetic in Pillow's operation order, so the integers are Pillow's."""
+    import numpy as np
+
+    scale = float(in_size) / out_size
+    fs = max(scale, 1.0)
+    support = 2.0 * fs
+    ksize = int(math.ceil(support)) * 2 + 1
+    center = 0.0 + (np.arange(out_size, dtype=np.float64) + 0.5) * scale
+    first = np.maximum((center - support + 0.5).astype(np.int64), 0)          # C's (int) cast: truncation
+    count = np.minimum((center + support + 0.5).astype(np.int64), in_size) - first
+    k = np.arange(ksize)[None, :]
+    x = np.abs((k + first[:, None] - center[:, None] + 0.5) * (1.0 / fs))
+    a = -0.5
+    w = np.where(x < 1.0, ((a + 2.0) * x - (a + 3.0)) * x * x + 1, np.where(x < 2.0, (((x - 5) * x + 8) * x - 4) * a, 0.0))
+    live = k < count[:, None]
+    w = np.where(live, w, 0.0)
+    total = np.zeros(out_size)
+    for j in range(ksize):            # Pillow sums the taps left to right
+        total = total + w[:, j]
+    w = np.where(live & (total[:, None] != 0.0), w / np.where(total == 0.0, 1.0, total)[:, None], w)
+    q = w * (1 << _PRECISION_BITS)
+    taps = np.where(w < 0, (-0.5 + q).astype(np.int64), (0.5 + q).astype(np.int64)).astype(np.int32)
+    return first.astype(np.int32), count.astype(np.int32), taps
+
+
+def crop_resize_plan(sizes, boxes, out_h, out_w):
+    """Host tables for `xfm_resize_bicubic_u8`: sizes [(h, w)] of the packed images, boxes [(x0, y0, x1, y1)] integer crop
+    boxes (PIL convention, inside the image).  Returns dict(desc, hb, hk, vb, vk, tmp_bytes, max_rows, src_bytes)."""
+    import numpy as np
+
+    B = len(sizes)
+    desc = np.zeros((B, 8), dtype=np.int64)
+    rows = []
+    src_off = tmp_off = 0
+    for b, ((h, w), (x0, y0, x1, y1)) in enumerate(zip(sizes, boxes)):
+        if not (0 <= x0 < x1 <= w and 0 <= y0 < y1 <= h):
+            raise ValueError(f"crop box {(x0, y0, x1, y1)} is not inside image {b} of size {(h, w)}")
+        cw, ch = x1 - x0, y1 - y0
+        desc[b] = (src_off, w, x0, y0, cw, ch, tmp_off, 0)
+        rows.append((pillow_bicubic_taps(cw, out_w), pillow_bicubic_taps(ch, out_h)))
+        src_off += h * w * 3
+        tmp_off += ch * out_w * 3
+    KH = max([r[0][2].shape[1] for r in rows], default=1)
+    KV = max([r[1][2].shape[1] for r in rows], default=1)
+    hb, hk = np.zeros((B, out_w, 2), np.int32), np.zeros((B, out_w, KH), np.int32)
+    vb, vk = np.zeros((B, out_h, 2), np.int32), np.zeros((B, out_h, KV), np.int32)
+    for b, ((hf, hc, ht), (vf, vc, vt)) in enumerate(rows):
+        hb[b, :, 0], hb[b, :, 1], hk[b, :, :ht.shape[1]] = hf, hc, ht
+        vb[b, :, 0], vb[b, :, 1], vk[b, :, :vt.shape[1]] = vf, vc, vt
+    t = torch.from_numpy
+    return dict(desc=t(desc), hb=t(hb), hk=t(hk), vb=t(vb), vk=t(vk), tmp_bytes=max(tmp_off, 1), src_bytes=src_off,
+                max_rows=int(desc[:, 5].max()) if B else 1)
+
+
+def crop_resize(images, boxes, out_h, out_w, device=None):
+    """images: list of uint8 [h, w, 3] host tensors (decoded RGB, any sizes); boxes: integer crop boxes (x0, y0, x1, y1) or
+    None = the whole image.  Returns uint8 [B, out_h, out_w, 3] on the device, bit-identical to
+    PIL `image.crop(box).resize((out_w, out_h), BICUBIC)` — i.e. to `RandomResizedCrop` / `Resize` with
+    InterpolationMode.BICUBIC once the crop box is drawn.  `lib.image_u8_to_f32` finishes the transform."""
+    from . import lib
+    if not torch.cuda.is_available():
+        raise RuntimeError("xfm_b200.feed.crop_resize needs a CUDA device (sm_100a); there is no CPU path")
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    sizes = [(int(im.shape[0]), int(im.shape[1])) for im in images]
+    for im in images:
+        if im.dtype != torch.uint8 or im.dim() != 3 or im.shape[2] != 3:
+            raise ValueError("crop_resize: images must be uint8 [h, w, 3]")
+    boxes = [(0, 0, w, h) if bx is None else tuple(int(v) for v in bx) for bx, (h, w) in zip(boxes, sizes)]
+    plan = crop_resize_plan(sizes, boxes, out_h, out_w)
+    B = len(images)
+    out = torch.empty((B, out_h, out_w, 3), dtype=torch.uint8, device=device)
+    if B == 0:
+        return out
+    packed = torch.empty(plan["src_bytes"], dtype=torch.uint8, pin_memory=True)
+    torch.cat([im.reshape(-1) for im in images], out=packed)
+    dev = {k: plan[k].pin_memory().to(device, non_blocking=True) for k in ("desc", "hb", "hk", "vb", "vk")}
+    tmp = torch.empty(plan["tmp_bytes"], dtype=torch.uint8, device=device)
+    return lib.resize_bicubic_u8(packed.to(device, non_blocking=True), dev["desc"], dev["hb"], dev["hk"], dev["vb"], dev["vk"],
+                                 tmp, out, plan["max_rows"])
 
 
 def _is_u8_image(t):

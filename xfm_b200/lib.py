@@ -662,6 +662,20 @@ def image_u8_to_f32(img_u8, mean, std, flip=None, out=None):
     return out
 
 
+def resize_bicubic_u8(src, desc, hb, hk, vb, vk, tmp, out, max_rows):
+    """Crop + bicubic resize of ragged uint8 images (Pillow's ImagingResample; see include/xfm_b200.h).  src u8 packed; desc
+    int64 [B, 8]; hb / vb int32 [B, OW|OH, 2]; hk / vk int32 [B, OW|OH, K]; tmp u8 scratch; out u8 [B, OH, OW, 3]."""
+    B, OH, OW, _ = out.shape
+    assert out.dtype == torch.uint8 and out.shape[3] == 3 and out.is_contiguous() and src.dtype == torch.uint8 and tmp.dtype == torch.uint8
+    assert desc.dtype == torch.int64 and desc.shape == (B, 8) and desc.is_contiguous()
+    for b_, k_, n_ in ((hb, hk, OW), (vb, vk, OH)):
+        assert b_.dtype == torch.int32 and k_.dtype == torch.int32 and b_.shape == (B, n_, 2) and k_.shape[:2] == (B, n_)
+        assert b_.is_contiguous() and k_.is_contiguous()
+    check(lib().xfm_resize_bicubic_u8(_p(src), _p(desc), _p(hb), _p(hk), hk.shape[2], _p(vb), _p(vk), vk.shape[2], _p(tmp),
+                                      _p(out), B, int(max_rows), OH, OW, stream_ptr()), "xfm_resize_bicubic_u8")
+    return out
+
+
 def axpby_scalars(a, sa, b, sb):
     """a * sa[0] + b * sb[0] (sa / sb: f32 [1] device tensors or None = 0)."""
     assert a.dtype == torch.float32 and a.is_contiguous() and b.is_contiguous() and a.shape == b.shape
