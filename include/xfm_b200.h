@@ -294,6 +294,11 @@ int xfm_image_u8_to_f32(const uint8_t* in, float* out, const uint8_t* flip, int 
  *   hk/vk int32 [B, OW|OH, KH|KV]: taps * 2^22 (Pillow's precompute_coeffs + normalize_coeffs_8bpc, computed on the host)
  *   tmp   u8 scratch, sum_b crop_height_b * OW * 3 bytes   out   u8 [B, OH, OW, 3]      max_rows = max_b crop height
  * All pointers are device pointers.  Bit-identical to PIL.Image.crop(box).resize((OW, OH), BICUBIC). */
+/* xfm_resize_taps fills hb / hk / vb / vk on the device from desc (crop width / height per image): Pillow's precompute_coeffs +
+ * normalize_coeffs_8bpc for BICUBIC in float64 with explicitly rounded operations — the integers Pillow computes on the host.
+ * KH / KV >= ceil(2 * max(crop / out, 1)) * 2 + 1 for every image (the caller sizes the tables). */
+int xfm_resize_taps(const int64_t* desc, int32_t* hb, int32_t* hk, int KH, int32_t* vb, int32_t* vk, int KV, int B, int OH, int OW,
+                    void* stream);
 int xfm_resize_bicubic_u8(const uint8_t* src, const int64_t* desc, const int32_t* hb, const int32_t* hk, int KH, const int32_t* vb,
                           const int32_t* vk, int KV, uint8_t* tmp, uint8_t* out, int B, int max_rows, int OH, int OW, void* stream);
 

@@ -121,8 +121,27 @@ def test_device_feeder_feeds_the_pretraining_model():
         assert abs(fed[k] - direct[k]) <= 1e-5 * max(1.0, abs(direct[k])), (k, fed[k], direct[k])
 
 
+def test_device_tap_tables_equal_the_host_tables():
+    """xfm_resize_taps (float64 on the GPU, explicitly rounded operations) against feed.pillow_bicubic_taps (numpy float64, pinned
+    to PIL in tests/test_feed_cpu.py): every first tap, tap count and fixed-point tap identical, from 1-pixel crops to 16x
+    down-scaling, both axes, ragged table widths."""
+    import numpy as np
+    from xfm_b200 import feed, lib
+    rng = np.random.default_rng(5)
+    for oh, ow in [(224, 224), (384, 384), (30, 50)]:
+        sizes = [(int(h), int(w)) for h, w in zip(rng.integers(1, 3600, 70), rng.integers(1, 3600, 70))]
+        sizes += [(oh, ow), (1, 1), (2 * oh, 2 * ow), (oh + 1, ow - 1), (3 * oh + 1, 5 * ow - 2)]
+        plan = feed.crop_resize_plan(sizes, [(0, 0, w, h) for h, w in sizes], oh, ow)
+        n0 = lib.launch_count()
+        hb, hk, vb, vk = lib.resize_taps(plan["desc"].cuda(), oh, ow, plan["KH"], plan["KV"])
+        assert lib.launch_count() - n0 == 1
+        for name, got in zip(("hb", "hk", "vb", "vk"), (hb, hk, vb, vk)):
+            assert torch.equal(got.cpu(), plan[name]), (name, oh, ow, int((got.cpu() != plan[name]).sum()))
+
+
+@pytest.mark.parametrize("taps", ["device", "host"])
 @pytest.mark.parametrize("res", [224, 384])
-def test_crop_resize_is_bit_identical_to_pil(res):
+def test_crop_resize_is_bit_identical_to_pil(res, taps):
     """RandomResizedCrop / Resize with InterpolationMode.BICUBIC (dataset/__init__.py:28-30,63-67) on a ragged batch: the GPU
     result equals PIL's crop(box).resize((res, res), BICUBIC) byte for byte; chained with the normalize kernel it equals
     torchvision's Resize -> ToTensor -> Normalize."""
@@ -143,8 +162,8 @@ def test_crop_resize_is_bit_identical_to_pil(res):
     images.append(rng.integers(0, 256, size=(res, res, 3), dtype=np.uint8))     # already the target size: identity
     boxes.append(None)
     n0 = lib.launch_count()
-    out = feed.crop_resize([torch.from_numpy(im) for im in images], boxes, res, res)
-    assert lib.launch_count() - n0 == 2
+    out = feed.crop_resize([torch.from_numpy(im) for im in images], boxes, res, res, taps=taps)
+    assert lib.launch_count() - n0 == (3 if taps == "device" else 2)
     assert out.is_cuda and out.dtype == torch.uint8 and out.shape == (len(images), res, res, 3)
     got = out.cpu().numpy()
     for i, (img, box) in enumerate(zip(images, boxes)):

@@ -221,6 +221,10 @@ int xfm_resize_bicubic_u8(const uint8_t* src, const int64_t* desc, const int32_t
                           const int32_t* vk, int KV, uint8_t* tmp, uint8_t* out, int B, int max_rows, int OH, int OW, void* stream) {
   return resize_bicubic_u8(src, desc, hb, hk, KH, vb, vk, KV, tmp, out, B, max_rows, OH, OW, ST);
 }
+int xfm_resize_taps(const int64_t* desc, int32_t* hb, int32_t* hk, int KH, int32_t* vb, int32_t* vk, int KV, int B, int OH, int OW,
+                    void* stream) {
+  return resize_taps(desc, hb, hk, KH, vb, vk, KV, B, OH, OW, ST);
+}
 int xfm_image_u8_to_f32(const uint8_t* in, float* out, const uint8_t* flip, int B, int H, int W, const float* mean,
                         const float* stdv, void* stream) {
   return image_u8_to_f32(in, out, flip, B, H, W, mean, stdv, ST);

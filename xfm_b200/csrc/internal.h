@@ -102,6 +102,8 @@ int bbox_loss(const float* coord, const float* target, const float* is_image, in
 int axpby_scalars(const float* a, const float* sa, const float* b, const float* sb, float* out, int n, cudaStream_t s);
 int resize_bicubic_u8(const uint8_t* src, const int64_t* desc, const int32_t* hb, const int32_t* hk, int KH, const int32_t* vb,
                       const int32_t* vk, int KV, uint8_t* tmp, uint8_t* out, int B, int max_rows, int OH, int OW, cudaStream_t s);
+int resize_taps(const int64_t* desc, int32_t* hb, int32_t* hk, int KH, int32_t* vb, int32_t* vk, int KV, int B, int OH, int OW,
+                cudaStream_t s);
 int image_u8_to_f32(const uint8_t* in, float* out, const uint8_t* flip, int B, int H, int W, const float* mean, const float* stdv,
                     cudaStream_t s);
 int grad_sumsq(const float* g, const int32_t* chunk_seg, const uint8_t* seg_group, size_t nchunks, int32_t* seg_step,

@@ -389,40 +389,49 @@ def pillow_bicubic_taps(in_size, out_size):
     return first.astype(np.int32), count.astype(np.int32), taps
 
 
-def crop_resize_plan(sizes, boxes, out_h, out_w):
+def bicubic_ksize(in_size, out_size):
+    """Width of Pillow's tap table for this axis: ceil(2 * max(in / out, 1)) * 2 + 1."""
+    return int(math.ceil(2.0 * max(float(in_size) / out_size, 1.0))) * 2 + 1
+
+
+def crop_resize_plan(sizes, boxes, out_h, out_w, taps=True):
     """Host tables for `xfm_resize_bicubic_u8`: sizes [(h, w)] of the packed images, boxes [(x0, y0, x1, y1)] integer crop
-    boxes (PIL convention, inside the image).  Returns dict(desc, hb, hk, vb, vk, tmp_bytes, max_rows, src_bytes)."""
+    boxes (PIL convention, inside the image).  Returns dict(desc, KH, KV, tmp_bytes, max_rows, src_bytes) and, with
+    taps=True, the tap tables hb / hk / vb / vk computed on the host (`xfm_resize_taps` computes the same on the device)."""
     import numpy as np
 
     B = len(sizes)
     desc = np.zeros((B, 8), dtype=np.int64)
-    rows = []
     src_off = tmp_off = 0
+    KH = KV = 1
     for b, ((h, w), (x0, y0, x1, y1)) in enumerate(zip(sizes, boxes)):
         if not (0 <= x0 < x1 <= w and 0 <= y0 < y1 <= h):
             raise ValueError(f"crop box {(x0, y0, x1, y1)} is not inside image {b} of size {(h, w)}")
         cw, ch = x1 - x0, y1 - y0
         desc[b] = (src_off, w, x0, y0, cw, ch, tmp_off, 0)
-        rows.append((pillow_bicubic_taps(cw, out_w), pillow_bicubic_taps(ch, out_h)))
+        KH, KV = max(KH, bicubic_ksize(cw, out_w)), max(KV, bicubic_ksize(ch, out_h))
         src_off += h * w * 3
         tmp_off += ch * out_w * 3
-    KH = max([r[0][2].shape[1] for r in rows], default=1)
-    KV = max([r[1][2].shape[1] for r in rows], default=1)
-    hb, hk = np.zeros((B, out_w, 2), np.int32), np.zeros((B, out_w, KH), np.int32)
-    vb, vk = np.zeros((B, out_h, 2), np.int32), np.zeros((B, out_h, KV), np.int32)
-    for b, ((hf, hc, ht), (vf, vc, vt)) in enumerate(rows):
-        hb[b, :, 0], hb[b, :, 1], hk[b, :, :ht.shape[1]] = hf, hc, ht
-        vb[b, :, 0], vb[b, :, 1], vk[b, :, :vt.shape[1]] = vf, vc, vt
-    t = torch.from_numpy
-    return dict(desc=t(desc), hb=t(hb), hk=t(hk), vb=t(vb), vk=t(vk), tmp_bytes=max(tmp_off, 1), src_bytes=src_off,
+    plan = dict(desc=torch.from_numpy(desc), KH=KH, KV=KV, tmp_bytes=max(tmp_off, 1), src_bytes=src_off,
                 max_rows=int(desc[:, 5].max()) if B else 1)
+    if taps:
+        hb, hk = np.zeros((B, out_w, 2), np.int32), np.zeros((B, out_w, KH), np.int32)
+        vb, vk = np.zeros((B, out_h, 2), np.int32), np.zeros((B, out_h, KV), np.int32)
+        for b in range(B):
+            hf, hc, ht = pillow_bicubic_taps(int(desc[b, 4]), out_w)
+            vf, vc, vt = pillow_bicubic_taps(int(desc[b, 5]), out_h)
+            hb[b, :, 0], hb[b, :, 1], hk[b, :, :ht.shape[1]] = hf, hc, ht
+            vb[b, :, 0], vb[b, :, 1], vk[b, :, :vt.shape[1]] = vf, vc, vt
+        plan.update(hb=torch.from_numpy(hb), hk=torch.from_numpy(hk), vb=torch.from_numpy(vb), vk=torch.from_numpy(vk))
+    return plan
 
 
-def crop_resize(images, boxes, out_h, out_w, device=None):
+def crop_resize(images, boxes, out_h, out_w, device=None, taps="device"):
     """images: list of uint8 [h, w, 3] host tensors (decoded RGB, any sizes); boxes: integer crop boxes (x0, y0, x1, y1) or
     None = the whole image.  Returns uint8 [B, out_h, out_w, 3] on the device, bit-identical to
     PIL `image.crop(box).resize((out_w, out_h), BICUBIC)` — i.e. to `RandomResizedCrop` / `Resize` with
-    InterpolationMode.BICUBIC once the crop box is drawn.  `lib.image_u8_to_f32` finishes the transform."""
+    InterpolationMode.BICUBIC once the crop box is drawn.  `lib.image_u8_to_f32` finishes the transform.  taps="device"
+    (default) builds Pillow's tap tables on the GPU (`xfm_resize_taps`); taps="host" computes them in numpy (same integers)."""
     from . import lib
     if not torch.cuda.is_available():
         raise RuntimeError("xfm_b200.feed.crop_resize needs a CUDA device (sm_100a); there is no CPU path")
@@ -432,17 +441,20 @@ def crop_resize(images, boxes, out_h, out_w, device=None):
         if im.dtype != torch.uint8 or im.dim() != 3 or im.shape[2] != 3:
             raise ValueError("crop_resize: images must be uint8 [h, w, 3]")
     boxes = [(0, 0, w, h) if bx is None else tuple(int(v) for v in bx) for bx, (h, w) in zip(boxes, sizes)]
-    plan = crop_resize_plan(sizes, boxes, out_h, out_w)
+    plan = crop_resize_plan(sizes, boxes, out_h, out_w, taps=(taps == "host"))
     B = len(images)
     out = torch.empty((B, out_h, out_w, 3), dtype=torch.uint8, device=device)
     if B == 0:
         return out
     packed = torch.empty(plan["src_bytes"], dtype=torch.uint8, pin_memory=True)
     torch.cat([im.reshape(-1) for im in images], out=packed)
-    dev = {k: plan[k].pin_memory().to(device, non_blocking=True) for k in ("desc", "hb", "hk", "vb", "vk")}
+    desc = plan["desc"].pin_memory().to(device, non_blocking=True)
+    if taps == "host":
+        hb, hk, vb, vk = (plan[k].pin_memory().to(device, non_blocking=True) for k in ("hb", "hk", "vb", "vk"))
+    else:
+        hb, hk, vb, vk = lib.resize_taps(desc, out_h, out_w, plan["KH"], plan["KV"])
     tmp = torch.empty(plan["tmp_bytes"], dtype=torch.uint8, device=device)
-    return lib.resize_bicubic_u8(packed.to(device, non_blocking=True), dev["desc"], dev["hb"], dev["hk"], dev["vb"], dev["vk"],
-                                 tmp, out, plan["max_rows"])
+    return lib.resize_bicubic_u8(packed.to(device, non_blocking=True), desc, hb, hk, vb, vk, tmp, out, plan["max_rows"])
 
 
 def _is_u8_image(t):

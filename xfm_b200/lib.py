@@ -662,6 +662,18 @@ def image_u8_to_f32(img_u8, mean, std, flip=None, out=None):
     return out
 
 
+def resize_taps(desc, out_h, out_w, KH, KV):
+    """Pillow's bicubic tap tables for every image of desc (int64 [B, 8] device), computed on the device.
+    Returns (hb, hk, vb, vk) for resize_bicubic_u8."""
+    B = desc.shape[0]
+    assert desc.dtype == torch.int64 and desc.shape == (B, 8) and desc.is_contiguous() and desc.is_cuda
+    i32 = dict(dtype=torch.int32, device=desc.device)
+    hb, hk = torch.empty((B, out_w, 2), **i32), torch.empty((B, out_w, KH), **i32)
+    vb, vk = torch.empty((B, out_h, 2), **i32), torch.empty((B, out_h, KV), **i32)
+    check(lib().xfm_resize_taps(_p(desc), _p(hb), _p(hk), KH, _p(vb), _p(vk), KV, B, out_h, out_w, stream_ptr()), "xfm_resize_taps")
+    return hb, hk, vb, vk
+
+
 def resize_bicubic_u8(src, desc, hb, hk, vb, vk, tmp, out, max_rows):
     """Crop + bicubic resize of ragged uint8 images (Pillow's ImagingResample; see include/xfm_b200.h).  src u8 packed; desc
     int64 [B, 8]; hb / vb int32 [B, OW|OH, 2]; hk / vk int32 [B, OW|OH, K]; tmp u8 scratch; out u8 [B, OH, OW, 3]."""
