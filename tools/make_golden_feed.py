@@ -73,7 +73,7 @@ def main():
 
     pd = reference_module()
     gen = random.Random(1234)            # drives the INPUTS; the code under test draws from the global generator
-    out = dict(masker=[], preprocess=[], corpus=[], image_atts=[], region=[], collate=[], region_collate=[])
+    out = dict(masker=[], preprocess=[], corpus=[], image_atts=[], region=[], collate=[], region_collate=[])   # + lines, image_text
     quiet = contextlib.redirect_stdout(io.StringIO())
 
     # ---- TextMaskingGenerator
@@ -185,6 +185,80 @@ def main():
             bt = ds.collate_fn(group)
         out["region_collate"].append(dict(seed=400 + seed, samples=idxs, batch_size=bs, images_shape=list(bt[0].shape),
                                           tensors=[t.tolist() for t in bt[1:]], next_random=random.random()))
+
+    # ---- DistLineReadingDataset.generate (dist_dataset.py:44-83) on local files: rank / worker shards, in-place shuffles, repeat
+    import tempfile
+    import itertools
+    import dataset.dist_dataset as dd
+    tmpd = tempfile.mkdtemp(prefix="feed-lines-")
+    names = []
+    for i in range(7):
+        path = os.path.join(tmpd, f"part-{i:02d}")
+        with open(path, "w") as f:
+            for j in range(1 + i % 3):
+                f.write(f"file{i}-line{j}\n")
+        names.append(f"part-{i:02d}")
+    open(os.path.join(tmpd, "_SUCCESS"), "w").close()
+    out["lines"] = []
+    for world, rank, shuffle, repeat, workers, wid in [(1, 0, False, False, 0, 0), (1, 0, True, True, 0, 0), (2, 0, True, False, 0, 0),
+                                                       (2, 1, True, True, 0, 0), (3, 2, False, False, 2, 1), (2, 1, True, True, 2, 0),
+                                                       (7, 3, True, False, 0, 0)]:
+        files = sorted(os.path.join(tmpd, n) for n in os.listdir(tmpd))
+        ds = object.__new__(dd.DistLineReadingDataset)
+        ds.__dict__.update(shuffle=shuffle, rank=rank, world_size=world, repeat=repeat,
+                           files=[f for f in files if f.find("_SUCCESS") < 0])
+        info = types.SimpleNamespace(id=wid, num_workers=workers) if workers else None
+        orig = torch.utils.data.get_worker_info
+        torch.utils.data.get_worker_info = lambda info=info: info
+        try:
+            random.seed(500 + world + rank)
+            with quiet:
+                got = list(itertools.islice(ds.generate(), 40))
+        finally:
+            torch.utils.data.get_worker_info = orig
+        out["lines"].append(dict(world=world, rank=rank, shuffle=shuffle, repeat=repeat, workers=workers, worker_id=wid,
+                                 seed=500 + world + rank, names=names, lines=got, next_random=random.random()))
+    out["line_files"] = {n: open(os.path.join(tmpd, n)).read() for n in names}
+
+    # ---- ImageTextJsonDataset.__iter__ (:225-262) and ImageJsonDataset.__iter__ (:368-394)
+    def png(w, h, rgb):
+        buf = io.BytesIO()
+        Image.new("RGB", (w, h), rgb).save(buf, format="PNG")
+        return base64.b64encode(buf.getvalue()).decode()
+
+    def probe(im):      # which image was decoded (no random draws inside the transform)
+        return torch.tensor([im.size[0], im.size[1], *im.getpixel((0, 0))])
+
+    tok = StubTokenizer("roberta")
+    with quiet:
+        mg = pd.TextMaskingGenerator(tok, 0.25, 4, 0.2, 3, False)
+    lines = []
+    for i in range(10):
+        imgs = [png(2 + gen.randrange(5), 2 + gen.randrange(5), (gen.randrange(256), gen.randrange(256), gen.randrange(256)))
+                for _ in range(1 + gen.randrange(3))]
+        cap = sentence(gen, gen.randint(1, 6))
+        kind = i % 5
+        ann = dict(binary=imgs[0] if kind in (0, 3) else imgs,
+                   desc=[cap, sentence(gen, 2)] if kind == 1 else dict(en=cap, fr=sentence(gen, 3)) if kind == 2 else cap)
+        lines.append(json.dumps(ann))
+    lines.insert(3, json.dumps(dict(binary=[], desc="a dog")))                  # no image: skipped silently
+    lines.insert(5, json.dumps(dict(binary=png(3, 3, (1, 2, 3)), desc="")))      # empty caption: broken sample
+    lines.insert(7, "{not json")                                                  # broken line
+    lines.insert(8, json.dumps(["a", "list"]))                                    # not a dict
+    out["image_text"] = []
+    for lang, text_stream in [(None, True), ("en", True), (None, False)]:
+        cls = pd.ImageTextJsonDataset if text_stream else pd.ImageJsonDataset
+        ds = bare(cls, image_key="binary", is_image_rpath=False, caption_key="desc", tokenized=False, language_chosen=lang,
+                  max_words=7, max_tokens=10, max_masks=4, tokenizer=tok, cls_token=tok.cls_token, eos_token=tok.sep_token,
+                  pad_token_id=tok.pad_token_id, add_eos=True, mask_generator=mg, PAD_mask=-100, transform=probe,
+                  print_broken_data=False, prefix=['A image of ', 'The image contains ', 'We can see ', 'A picture of '])
+        use = [l for l in lines if lang is None or '"fr"' in l or '"desc": "' in l or not l.startswith("{\"binary")]
+        ds.generate = lambda use=use: iter(use)
+        random.seed(600)
+        samples = list(ds)
+        out["image_text"].append(dict(lang=lang, text=text_stream, seed=600, lines=use,
+                                      samples=[[s[0].tolist()] + [None if v is None else list(map(int, v)) for v in s[1:]]
+                                               for s in samples], next_random=random.random()))
 
     # ---- ImageTextJsonDataset.collate_fn
     ds = bare(pd.ImageTextJsonDataset)

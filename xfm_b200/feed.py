@@ -6,6 +6,8 @@ run produces the reference's batches):
   * `TextMasker`              dataset/pretrain_dataset.py:60-150  (TextMaskingGenerator: n-gram / whole-word MLM masking)
   * `pre_caption`             dataset/utils.py:38-66
   * `TextPreprocessor`        dataset/pretrain_dataset.py:264-300 (image-text) and :690-726 (text-only corpus)
+  * `LineShards`, `split_shard`  dataset/dist_dataset.py:44-94 (files sharded over ranks, then DataLoader workers; shuffles)
+  * `ImageTextStream`         dataset/pretrain_dataset.py:225-262, :368-394 (JSON line -> decoded image + text sample)
   * `region_image_atts`       dataset/pretrain_dataset.py:577-592 (box -> patch mask with token 0 always on)
   * `RegionSampler`           dataset/pretrain_dataset.py:445-575 (random crop around a region, careful hflip, per-region texts,
                               patch masks and cxcywh targets; the pixel work stays with the caller between the two phases)
@@ -180,6 +182,111 @@ class TextPreprocessor:
         return (ids + pad, [1] * n + [0] * (L - n), ids_masked + pad, masked_pos + [0] * mpad, masked_ids + [PAD_MASK] * mpad)
 
 
+def pick_caption(c, language_chosen=None, rng=None):
+    """One caption out of a str / list of them / {language: str} (pretrain_dataset.py:206-223): a list costs one
+    rng.choice, a multilingual dict another one unless a language is fixed."""
+    rng = rng if rng is not None else _random
+    if isinstance(c, list):
+        c = rng.choice(c)
+    if isinstance(c, str):
+        return c
+    if isinstance(c, dict):
+        v = rng.choice(list(c.values())) if language_chosen is None else c[language_chosen]
+        if not isinstance(v, str):
+            raise AssertionError("caption entry is not a string")
+        return v
+    raise ValueError(c)
+
+
+# ---------------------------------------------------------------------------------------------------------- sample streams
+def split_shard(data, shard_idx, shard_size):
+    """Contiguous shard shard_idx of shard_size (dataset/dist_dataset.py:88-94); fewer items than shards is an error."""
+    n = len(data)
+    if n < shard_size:
+        raise RuntimeError("num:{} < shard size:{}".format(n, shard_size))
+    return data[n * shard_idx // shard_size: n * (shard_idx + 1) // shard_size]
+
+
+class LineShards:
+    """Lines of this rank's (and this DataLoader worker's) share of `files` (dataset/dist_dataset.py:44-83, local files): files
+    are sharded over ranks unless there is one rank or one file, then over workers; with `shuffle` the rank's list is
+    shuffled IN PLACE once per epoch and the worker's list once more (the same list twice without workers), as the reference
+    does — the in-place permutation carries over to the next epoch of `repeat`."""
+
+    def __init__(self, files, rank=0, world_size=1, shuffle=False, repeat=False, rng=None, worker_info=None):
+        self.files = [f for f in files if f.find("_SUCCESS") < 0]
+        self.rank, self.world_size, self.shuffle, self.repeat = rank, world_size, shuffle, repeat
+        self.rng = rng if rng is not None else _random
+        self.worker_info = worker_info if worker_info is not None else torch.utils.data.get_worker_info
+
+    def __iter__(self):
+        mine = self.files if (self.world_size == 1 or len(self.files) == 1) else split_shard(self.files, self.rank, self.world_size)
+        while True:
+            if self.shuffle:
+                self.rng.shuffle(mine)
+            info = self.worker_info()
+            part = mine if info is None else split_shard(mine, info.id, info.num_workers)
+            if self.shuffle:
+                self.rng.shuffle(part)
+            for path in part:
+                with open(path, "r") as reader:
+                    yield from reader
+            if not self.repeat:
+                return
+
+
+def _open_rgb(ref, is_path):
+    import io
+    from base64 import b64decode
+    from PIL import Image
+    return Image.open(ref if is_path else io.BytesIO(b64decode(ref))).convert("RGB")
+
+
+class ImageTextStream:
+    """JSON lines -> (image, text_ids, text_atts, text_ids_masked, masked_pos, masked_ids) samples
+    (ImageTextJsonDataset.__iter__, pretrain_dataset.py:225-262; `text=None`: the image-only stream of ImageJsonDataset.__iter__,
+    :368-394, which yields (image, None x 5)).  A list of images costs one rng.choice for the prompt prefix and one for the
+    image; broken lines are reported through `on_error` and skipped, like the reference's try / except."""
+
+    PREFIX = ("A image of ", "The image contains ", "We can see ", "A picture of ")
+
+    def __init__(self, lines, transform, text, image_key, caption_key=None, is_image_rpath=False, rng=None, on_error=None):
+        self.lines, self.transform, self.text = lines, transform, text
+        self.image_key, self.caption_key, self.is_image_rpath = image_key, caption_key, is_image_rpath
+        self.rng = rng if rng is not None else _random
+        self.on_error = on_error
+
+    def _sample(self, ann):
+        rng, ref = self.rng, ann[self.image_key]
+        several = type(ref) == list
+        caption = None
+        if self.text is not None:
+            prefix = rng.choice(self.PREFIX) if several else ""          # drawn before the caption, as in the reference
+            caption = prefix + pick_caption(ann[self.caption_key], self.text.language_chosen, rng)
+        if several and not self.is_image_rpath:
+            ref = rng.choice(ref)
+        image = self.transform(_open_rgb(ref, self.is_image_rpath))
+        if self.text is None:
+            return (image, None, None, None, None, None)
+        if not len(caption):
+            raise ValueError({k: v for k, v in ann.items() if k != self.image_key})
+        return (image, *self.text.preprocess(caption))
+
+    def __iter__(self):
+        import json
+        for line in self.lines:
+            try:
+                ann = json.loads(line)
+                if not isinstance(ann, dict):
+                    raise AssertionError("ann is not dict")
+                if type(ann[self.image_key]) == list and len(ann[self.image_key]) == 0:
+                    continue
+                yield self._sample(ann)
+            except Exception as e:  # noqa: BLE001 — the reference skips any broken sample
+                if self.on_error is not None:
+                    self.on_error(e)
+
+
 # ---------------------------------------------------------------------------------------------------------- region side
 def region_image_atts(x, y, w, h, patch_size, num_patch):
     """Pixel box (after crop / flip / resize) -> 0/1 list of length 1 + num_patch^2: token 0 always on, then every patch the
@@ -238,18 +345,7 @@ class RegionSampler:
         return ("caption" in ann and has(ann)) or any(has(e) for e in ann["elems"])
 
     def _caption(self, c):
-        rng = self.rng
-        if isinstance(c, list):
-            c = rng.choice(c)
-        if isinstance(c, str):
-            return c
-        if isinstance(c, dict):
-            lang = self.text.language_chosen
-            v = rng.choice(list(c.values())) if lang is None else c[lang]
-            if not isinstance(v, str):
-                raise AssertionError("caption entry is not a string")
-            return v
-        raise ValueError(c)
+        return pick_caption(c, self.text.language_chosen, self.rng)
 
     def plan(self, ann, W, H):
         rng = self.rng
