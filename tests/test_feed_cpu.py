@@ -276,3 +276,28 @@ def test_image_text_stream_matches_reference(golden):
         assert len(samples) >= 8 and len(errors) == (3 if g["text"] else 2)     # empty caption only matters with text
         batch = feed.collate([tuple([torch.tensor(s[0])] + s[1:]) for s in samples])
         assert batch[0].shape == (len(samples), 5) and (batch[1] is None) == (not g["text"])
+
+
+def test_random_resized_crop_box_draws_what_torchvision_draws():
+    """Same seed -> same crop box as transforms.RandomResizedCrop.get_params, and the same generator state afterwards (the
+    fallback branch included: extreme aspect ratios never fit)."""
+    tv = pytest.importorskip("torchvision.transforms")
+    from PIL import Image
+    n_fallback = 0
+    for t, (w, h) in enumerate([(640, 480), (480, 640), (224, 224), (37, 501), (3000, 20), (20, 3000), (1, 1), (500, 333)] * 3):
+        scale = [(0.2, 1.0), (0.5, 1.0), (0.9, 1.0)][t % 3]
+        img = Image.new("RGB", (w, h))
+        torch.manual_seed(t)
+        i, j, ch, cw = tv.RandomResizedCrop.get_params(img, scale=scale, ratio=(3.0 / 4.0, 4.0 / 3.0))
+        after = torch.rand(1).item()
+        torch.manual_seed(t)
+        box = feed.random_resized_crop_box(w, h, scale=scale)
+        assert box == (j, i, j + cw, i + ch), (t, (w, h), box, (i, j, ch, cw))
+        assert torch.rand(1).item() == after
+        assert 0 <= box[0] < box[2] <= w and 0 <= box[1] < box[3] <= h
+        n_fallback += (w, h) in [(3000, 20), (20, 3000)]
+    assert n_fallback == 6
+    g = torch.Generator().manual_seed(3)
+    state = torch.random.get_rng_state()
+    feed.random_resized_crop_box(640, 480, generator=g)
+    assert torch.equal(torch.random.get_rng_state(), state)      # a private generator leaves the global one alone

@@ -522,6 +522,33 @@ def crop_resize_plan(sizes, boxes, out_h, out_w, taps=True):
     return plan
 
 
+def random_resized_crop_box(width, height, scale=(0.2, 1.0), ratio=(3.0 / 4.0, 4.0 / 3.0), generator=None):
+    """The crop box `transforms.RandomResizedCrop(res, scale=scale)` (dataset/__init__.py:28-29,37-38) draws for an image of
+    this size, as a PIL box (x0, y0, x1, y1) for `crop_resize`.  torchvision's rule (third party): up to ten attempts of
+    area ~ U(scale) * image area and log-aspect ~ U(log ratio), accepted when the box fits, then its corner uniformly; else the
+    largest centred box whose aspect is clamped into `ratio`.  The draws are the same torch calls in the same order, so with
+    the global generator (generator=None) a seeded run crops exactly what torchvision would."""
+    area = height * width
+    log_ratio = torch.log(torch.tensor(ratio))
+    for _ in range(10):
+        target = area * torch.empty(1).uniform_(scale[0], scale[1], generator=generator).item()
+        aspect = torch.exp(torch.empty(1).uniform_(log_ratio[0], log_ratio[1], generator=generator)).item()
+        w, h = int(round(math.sqrt(target * aspect))), int(round(math.sqrt(target / aspect)))
+        if 0 < w <= width and 0 < h <= height:
+            y0 = torch.randint(0, height - h + 1, size=(1,), generator=generator).item()
+            x0 = torch.randint(0, width - w + 1, size=(1,), generator=generator).item()
+            return (x0, y0, x0 + w, y0 + h)
+    image_ratio = float(width) / float(height)
+    if image_ratio < min(ratio):
+        w, h = width, int(round(width / min(ratio)))
+    elif image_ratio > max(ratio):
+        w, h = int(round(height * max(ratio))), height
+    else:
+        w, h = width, height
+    x0, y0 = (width - w) // 2, (height - h) // 2
+    return (x0, y0, x0 + w, y0 + h)
+
+
 def crop_resize(images, boxes, out_h, out_w, device=None, taps="device"):
     """images: list of uint8 [h, w, 3] host tensors (decoded RGB, any sizes); boxes: integer crop boxes (x0, y0, x1, y1) or
     None = the whole image.  Returns uint8 [B, out_h, out_w, 3] on the device, bit-identical to
