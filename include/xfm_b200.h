@@ -294,6 +294,9 @@ int xfm_image_u8_to_f32(const uint8_t* in, float* out, const uint8_t* flip, int 
  *   hk/vk int32 [B, OW|OH, KH|KV]: taps * 2^22 (Pillow's precompute_coeffs + normalize_coeffs_8bpc, computed on the host)
  *   tmp   u8 scratch, sum_b crop_height_b * OW * 3 bytes   out   u8 [B, OH, OW, 3]      max_rows = max_b crop height
  * All pointers are device pointers.  Bit-identical to PIL.Image.crop(box).resize((OW, OH), BICUBIC). */
+/* Host-only helper of the batch feeder: copy n byte ranges back to back into dst (normally pinned staging memory) with up to
+ * `threads` threads (equal byte spans across segment boundaries).  No CUDA call; all pointers are HOST pointers. */
+int xfm_host_pack(const void* const* srcs, const int64_t* nbytes, int n, void* dst, int threads);
 /* xfm_resize_taps fills hb / hk / vb / vk on the device from desc (crop width / height per image): Pillow's precompute_coeffs +
  * normalize_coeffs_8bpc for BICUBIC in float64 with explicitly rounded operations — the integers Pillow computes on the host.
  * KH / KV >= ceil(2 * max(crop / out, 1)) * 2 + 1 for every image (the caller sizes the tables). */

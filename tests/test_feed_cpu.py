@@ -301,3 +301,20 @@ def test_random_resized_crop_box_draws_what_torchvision_draws():
     state = torch.random.get_rng_state()
     feed.random_resized_crop_box(640, 480, generator=g)
     assert torch.equal(torch.random.get_rng_state(), state)      # a private generator leaves the global one alone
+
+
+def test_host_pack_gathers_bytes_with_any_thread_count():
+    """xfm_host_pack (host-only entry point of the C-ABI): ragged tensors, empty segments, segment boundaries inside a thread's
+    span; equal to torch.cat for 1..16 threads."""
+    from xfm_b200 import lib
+    g = torch.Generator().manual_seed(0)
+    parts = [torch.randint(0, 256, (int(n),), dtype=torch.uint8, generator=g) for n in (0, 1, 7, 5 << 20, 3, 9 << 20, 0, 4 << 20, 11)]
+    parts.append(torch.randint(0, 1000, (1000, 3), dtype=torch.int64, generator=g))
+    ref = torch.cat([p.reshape(-1).view(torch.uint8) for p in parts])
+    for threads in (1, 2, 3, 8, 16):
+        out = torch.zeros(ref.numel() + 5, dtype=torch.uint8)
+        lib.host_pack(parts, out, threads=threads)
+        assert torch.equal(out[:-5], ref) and int(out[-5:].sum()) == 0
+    lib.host_pack([], torch.zeros(1, dtype=torch.uint8))
+    with pytest.raises(AssertionError):
+        lib.host_pack([torch.zeros(4, dtype=torch.uint8)], torch.zeros(3, dtype=torch.uint8))

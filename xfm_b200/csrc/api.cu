@@ -1,7 +1,11 @@
 // xfm_b200 — extern "C" entry points (the C-ABI declared in include/xfm_b200.h).
+#include <algorithm>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstring>
+#include <thread>
+#include <vector>
 #include "internal.h"
 
 namespace xfm {
@@ -220,6 +224,36 @@ int xfm_axpby_scalars(const float* a, const float* sa, const float* b, const flo
 int xfm_resize_bicubic_u8(const uint8_t* src, const int64_t* desc, const int32_t* hb, const int32_t* hk, int KH, const int32_t* vb,
                           const int32_t* vk, int KV, uint8_t* tmp, uint8_t* out, int B, int max_rows, int OH, int OW, void* stream) {
   return resize_bicubic_u8(src, desc, hb, hk, KH, vb, vk, KV, tmp, out, B, max_rows, OH, OW, ST);
+}
+// Host-side: gather n byte ranges into one (pinned) staging buffer with several threads — the packing step of the batch feeder
+// (a single-threaded copy of a 96-image batch, 82 MB, costs 7.5 ms; the H2D copy that follows 1.6 ms).  The total is cut into
+// equal byte spans, one per thread, across segment boundaries.  No CUDA calls: usable (and tested) without a device.
+int xfm_host_pack(const void* const* srcs, const int64_t* nbytes, int n, void* dst, int threads) {
+  if (n < 0 || (n > 0 && (!srcs || !nbytes || !dst))) { set_error("host_pack: null pointer"); return XFM_ERR_BAD_ARG; }
+  std::vector<int64_t> start(n + 1, 0);
+  for (int i = 0; i < n; ++i) {
+    if (nbytes[i] < 0 || (nbytes[i] > 0 && !srcs[i])) { set_error("host_pack: bad segment %d", i); return XFM_ERR_BAD_ARG; }
+    start[i + 1] = start[i] + nbytes[i];
+  }
+  const int64_t total = start[n];
+  int T = threads < 1 ? 1 : threads;
+  const int64_t by_size = total / (4 << 20) + 1;            // at least 4 MB per thread
+  if (T > by_size) T = (int)by_size;
+  auto span = [&](int64_t lo, int64_t hi) {
+    int i = (int)(std::upper_bound(start.begin(), start.end(), lo) - start.begin()) - 1;
+    while (lo < hi) {
+      const int64_t end = start[i + 1] < hi ? start[i + 1] : hi;
+      if (end > lo) std::memcpy((char*)dst + lo, (const char*)srcs[i] + (lo - start[i]), (size_t)(end - lo));
+      lo = end;
+      ++i;
+    }
+  };
+  if (T == 1) { span(0, total); return 0; }
+  std::vector<std::thread> pool;
+  for (int t = 1; t < T; ++t) pool.emplace_back(span, total * t / T, total * (t + 1) / T);
+  span(0, total / T);
+  for (auto& th : pool) th.join();
+  return 0;
 }
 int xfm_resize_taps(const int64_t* desc, int32_t* hb, int32_t* hk, int KH, int32_t* vb, int32_t* vk, int KV, int B, int OH, int OW,
                     void* stream) {

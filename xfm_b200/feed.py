@@ -570,7 +570,7 @@ def crop_resize(images, boxes, out_h, out_w, device=None, taps="device"):
     if B == 0:
         return out
     packed = torch.empty(plan["src_bytes"], dtype=torch.uint8, pin_memory=True)
-    torch.cat([im.reshape(-1) for im in images], out=packed)
+    lib.host_pack([im.contiguous() for im in images], packed)      # multi-threaded gather into the staging buffer
     desc = plan["desc"].pin_memory().to(device, non_blocking=True)
     if taps == "host":
         hb, hk, vb, vk = (plan[k].pin_memory().to(device, non_blocking=True) for k in ("hb", "hk", "vb", "vk"))

@@ -662,6 +662,19 @@ def image_u8_to_f32(img_u8, mean, std, flip=None, out=None):
     return out
 
 
+def host_pack(tensors, out, threads=8):
+    """Copy the bytes of the (contiguous, host) tensors back to back into `out` (uint8, host; normally pinned) with several
+    threads.  Host-only: works without a CUDA device."""
+    n = len(tensors)
+    assert out.device.type == "cpu" and out.dtype == torch.uint8 and out.is_contiguous()
+    sizes = [t.numel() * t.element_size() for t in tensors]
+    assert all(t.device.type == "cpu" and t.is_contiguous() for t in tensors) and sum(sizes) <= out.numel()
+    srcs = (C.c_void_p * max(n, 1))(*[t.data_ptr() for t in tensors])
+    nb = (C.c_int64 * max(n, 1))(*sizes)
+    check(load().xfm_host_pack(srcs, nb, n, C.c_void_p(out.data_ptr()), int(threads)), "xfm_host_pack")
+    return out
+
+
 def resize_taps(desc, out_h, out_w, KH, KV):
     """Pillow's bicubic tap tables for every image of desc (int64 [B, 8] device), computed on the device.
     Returns (hb, hk, vb, vk) for resize_bicubic_u8."""
