@@ -198,3 +198,62 @@ def test_bert_text_encoder_variant_against_reference(golden_dir):
         (out["loss_itc"] + out["loss_itm"] + out["loss_mlm"]).backward()
         for n, ref in g["grads"].items():
             assert float((sd[n].grad - ref).abs().max()) <= 1e-5 * float(ref.abs().max()) + 1e-9, (fp16, n)
+
+
+def test_finetune_forwards_against_reference(golden_dir):
+    """BASELINE configs #3 / #4 at tiny widths: the oracle pieces, composed the way tests/test_model_gpu.py composes them for
+    the retrieval and NLVR models, equal the reference's OWN models/model_retrieval.py:26-37 and models/model_nlvr.py:28-44
+    forwards (tiny_finetune.pt: losses, prediction, gradients incl. the text path opened by is_pretrain=False)."""
+    g = _load(golden_dir, "tiny_finetune.pt")
+    cfg = O.tiny_config()
+
+    def fresh_sd():
+        sd = O.make_state_dict(cfg, seed=0)
+        for v in sd.values():
+            if v.dtype.is_floating_point:
+                v.requires_grad_(True)
+        return sd
+
+    def close(a, b, what):
+        assert float((a - b).abs().max()) <= 2e-5 * float(b.abs().max()) + 1e-9, what
+
+    # retrieval: ITC with idx soft labels + idx-masked hard negatives (the heaviest one, as the fixture's multinomial stand-in)
+    r, sd = g["retrieval"], fresh_sd()
+    batch = O.make_batch(cfg, 6, L=24, M=6, seed=3)
+    ie = O.vision_forward(batch["image"], sd, cfg)
+    ia = torch.ones(ie.shape[:2], dtype=torch.long)
+    te = O.text_forward(batch["text_ids"], batch["text_atts"], sd, cfg)
+    fi, ft = O.get_features(ie, te, sd)
+    w_i2t, w_t2i = O.hard_negative_weights(fi.detach(), ft.detach(), sd["temp"].detach(), r["idx"])
+    tneg, ineg = w_i2t.argmax(1), w_t2i.argmax(1)
+    itc = O.contrastive_loss(fi, ft, sd["temp"], r["idx"])
+    itm, _ = O.matching_loss(ie, ia, te, batch["text_atts"], ineg, tneg, sd, cfg, is_pretrain=False)
+    assert abs(float(itc) - r["loss_itc"]) <= 2e-5 * abs(r["loss_itc"]), (float(itc), r["loss_itc"])
+    assert abs(float(itm) - r["loss_itm"]) <= 2e-5 * abs(r["loss_itm"]), (float(itm), r["loss_itm"])
+    (itc + itm).backward()
+    for n, ref in r["grads"].items():
+        close(sd[n].grad.reshape(ref.shape), ref, n)
+    assert float(r["grads"]["text_encoder.roberta.encoder.layer.0.intermediate.dense.weight"].abs().max()) > 0
+
+    # NLVR: two images per text, shared text states, concatenated CLS -> Linear, LayerNorm, GELU, Linear -> CE
+    n, sd = g["nlvr"], fresh_sd()
+    B = n["targets"].numel()
+    head = {k: v.clone().requires_grad_(True) for k, v in n["head"].items()}
+    for k, v in head.items():
+        assert torch.equal(v.detach(), O.make_tensor("cls_head." + k, tuple(v.shape), 0))
+    batch = O.make_batch(cfg, 2 * B, L=24, M=6, seed=5)
+    ids, atts = batch["text_ids"][:B], batch["text_atts"][:B]
+    ie = O.vision_forward(batch["image"], sd, cfg)
+    ia = torch.ones(ie.shape[:2], dtype=torch.long)
+    te = O.text_forward(ids, atts, sd, cfg)
+    x = torch.cat([O.fusion_forward(te, atts, ie[:B], ia[:B], sd, cfg)[:, 0], O.fusion_forward(te, atts, ie[B:], ia[B:], sd, cfg)[:, 0]], -1)
+    x = torch.nn.functional.linear(x, head["0.weight"], head["0.bias"])
+    x = torch.nn.functional.gelu(torch.nn.functional.layer_norm(x, (x.shape[-1],), head["1.weight"], head["1.bias"], 1e-5))
+    pred = torch.nn.functional.linear(x, head["3.weight"], head["3.bias"])
+    loss = torch.nn.functional.cross_entropy(pred, n["targets"])
+    assert abs(float(loss) - n["loss"]) <= 2e-5 * abs(n["loss"]), (float(loss), n["loss"])
+    close(pred.detach(), n["prediction"], "prediction")
+    loss.backward()
+    for k, ref in n["grads"].items():
+        got = head[k[len("cls_head."):]].grad if k.startswith("cls_head.") else sd[k].grad
+        close(got.reshape(ref.shape), ref, k)

@@ -16,6 +16,8 @@ What is recorded (all produced by the reference's own code, through oracle/ref_s
   * tiny_vqa.pt  — XFMForVQA (models/model_generation.py), tiny config with a 2-layer causal decoder: training loss,
                    per-answer losses, question states, parameter gradients; rank_answer ids / probabilities.
                    `python tools/make_golden.py --only-vqa` regenerates just this file.
+  * tiny_finetune.pt — the reference's model_retrieval.py / model_nlvr.py forwards (BASELINE configs #3 / #4 at tiny widths):
+                   losses, prediction, gradients.  `python tools/make_golden.py --only-finetune`.
 Synthetic weights come from oracle.xfm_oracle.make_state_dict (a pure function of parameter names), so the
 fixtures stay small: tests regenerate the same weights instead of loading them.
 """
@@ -354,8 +356,70 @@ def bert_golden():
     return dict(cfg=cfg, scale_order_identical=True, **out["O1"])
 
 
+FT_GRADS = ["itm_head.0.weight", "fusion_encoder.roberta.encoder.layer.1.crossattention.self.key.weight",
+            "text_encoder.roberta.encoder.layer.0.intermediate.dense.weight", "vision_proj.weight", "text_proj.weight",
+            "vision_encoder.blocks.1.mlp.fc2.weight", "temp"]
+
+
+def finetune_golden():
+    """The reference's OWN fine-tuning forwards — models/model_retrieval.py:26-37 (ITC with idx soft labels + idx-masked
+    hard-negative ITM, text gradients through the fusion encoder) and models/model_nlvr.py:28-44 (two images per text,
+    concatenated CLS -> build_mlp -> CE) — run as unbound methods on the shim-built XFMBase (their __init__ only
+    selects losses and adds the head): losses, prediction, gradients."""
+    ref_shim.install()
+    from models.model_retrieval import XFMForRetrieval
+    from models.model_nlvr import XFMForNLVR
+    from models.xfm import build_mlp
+    cfg = O.tiny_config()
+    sd = O.make_state_dict(cfg, seed=0)
+    out = {}
+    orig = torch.multinomial
+
+    def fake(w, n, *a, **k):
+        return torch.argmax(w).view(1)
+
+    # retrieval (same inputs as tests/test_model_gpu.py::test_retrieval_model_against_oracle)
+    model = ref_shim.build_reference_xfm(cfg, O.expand_tied(sd, cfg))
+    batch = O.make_batch(cfg, 6, L=24, M=6, seed=3)
+    idx = torch.tensor([0, 1, 0, 2, 1, 3])
+    torch.multinomial = fake
+    try:
+        l_itc, l_itm = XFMForRetrieval.forward(model, batch["image"], batch["text_ids"], batch["text_atts"], idx=idx)
+    finally:
+        torch.multinomial = orig
+    (l_itc + l_itm).backward()
+    named = dict(model.named_parameters())
+    out["retrieval"] = dict(idx=idx, loss_itc=float(l_itc), loss_itm=float(l_itm),
+                            grads={k: named[k].grad.detach().clone() for k in FT_GRADS})
+
+    # NLVR (same inputs as test_nlvr_model_against_oracle; the head's weights are a pure function of their names)
+    model = ref_shim.build_reference_xfm(cfg, O.expand_tied(sd, cfg))
+    model.cls_head = build_mlp(input_dim=model.text_width * 2, output_dim=2)
+    head = {k: O.make_tensor("cls_head." + k, tuple(v.shape), 0) for k, v in model.cls_head.state_dict().items()}
+    model.cls_head.load_state_dict(head)
+    model.eval()
+    B = 4
+    batch = O.make_batch(cfg, 2 * B, L=24, M=6, seed=5)
+    ids, atts, targets = batch["text_ids"][:B], batch["text_atts"][:B], torch.tensor([0, 1, 1, 0])
+    loss = XFMForNLVR.forward(model, batch["image"], ids, atts, targets)
+    loss.backward()
+    with torch.no_grad():
+        pred = XFMForNLVR.forward(model, batch["image"], ids, atts, targets, train=False)
+    named = dict(model.named_parameters())
+    keys = ["cls_head.0.weight", "cls_head.3.bias", "fusion_encoder.roberta.encoder.layer.1.crossattention.self.key.weight",
+            "text_encoder.roberta.encoder.layer.0.intermediate.dense.weight", "vision_encoder.blocks.1.mlp.fc2.weight"]
+    out["nlvr"] = dict(targets=targets, loss=float(loss), prediction=pred.clone(), head={k: v.clone() for k, v in head.items()},
+                       grads={k: named[k].grad.detach().clone() for k in keys})
+    return out
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
+    if "--only-finetune" in sys.argv:
+        r = finetune_golden()
+        torch.save(r, os.path.join(GOLD, "tiny_finetune.pt"))
+        print("tiny_finetune", r["retrieval"]["loss_itc"], r["retrieval"]["loss_itm"], r["nlvr"]["loss"])
+        return
     if "--only-vqa" in sys.argv:
         v = vqa_golden()
         torch.save(v, os.path.join(GOLD, "tiny_vqa.pt"))
