@@ -318,3 +318,13 @@ def test_host_pack_gathers_bytes_with_any_thread_count():
     lib.host_pack([], torch.zeros(1, dtype=torch.uint8))
     with pytest.raises(AssertionError):
         lib.host_pack([torch.zeros(4, dtype=torch.uint8)], torch.zeros(3, dtype=torch.uint8))
+
+
+def test_vqa_collate_matches_reference(golden):
+    g = golden["vqa_collate"][0]
+    vb = [(torch.full((3, 2, 2), float(i)), f"question {i}", [f"a{i}{j}" for j in range(1 + i % 3)],
+           [0.25 * (j + 1) for j in range(1 + i % 3)]) for i in range(5)]
+    im, qs, ans, w, n = feed.vqa_collate(vb)
+    assert im.tolist() == g["image"] and qs == g["questions"] and ans == g["answers"] and n == g["n"]
+    assert w.tolist() == g["weights"] and str(w.dtype) == g["weights_dtype"] == "torch.float32"
+    assert sum(n) == len(ans) == w.numel()

@@ -266,6 +266,13 @@ def main():
     bt = ds.collate_fn(batch)
     out["collate"].append(dict(image=bt[0].tolist(), ids=bt[1].tolist(), atts=bt[2].tolist(), none=bt[3]))
 
+    # ---- vqa_collate_fn (dataset/__init__.py:200-208)
+    import dataset as ref_dataset
+    vb = [(torch.full((3, 2, 2), float(i)), f"question {i}", [f"a{i}{j}" for j in range(1 + i % 3)],
+           [0.25 * (j + 1) for j in range(1 + i % 3)]) for i in range(5)]
+    im, qs, ans, w, n = ref_dataset.vqa_collate_fn(vb)
+    out["vqa_collate"] = [dict(image=im.tolist(), questions=qs, answers=ans, weights=w.tolist(), weights_dtype=str(w.dtype), n=n)]
+
     path = os.path.join(ROOT, "tests", "golden", "feed.json")
     with open(path, "w") as f:
         json.dump(out, f, separators=(",", ":"))

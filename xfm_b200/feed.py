@@ -12,6 +12,7 @@ run produces the reference's batches):
   * `RegionSampler`           dataset/pretrain_dataset.py:445-575 (random crop around a region, careful hflip, per-region texts,
                               patch masks and cxcywh targets; the pixel work stays with the caller between the two phases)
   * `collate`, `region_collate`  dataset/pretrain_dataset.py:302-312, :594-643 (`idx_to_group_img`, fixed-size region batches)
+  * `vqa_collate`             dataset/__init__.py:200-208
 
 Device half:
   * `to_uint8_hwc`            replaces the `ToTensor(), normalize` tail of every Compose in dataset/__init__.py:26-68: the
@@ -407,6 +408,19 @@ def collate(batch):
     """List of per-sample tuples -> list of batch tensors: tensors stacked, int lists as int64, None kept
     (pretrain_dataset.py:302-312)."""
     return [_stack_column(x) for x in zip(*batch)]
+
+
+def vqa_collate(batch):
+    """[(image, question str, answers [str], weights [float])] -> (images [B, ...], questions, flattened answers, weights as a
+    float32 tensor, answers per question) — `vqa_collate_fn`, dataset/__init__.py:200-208 (BASELINE config #5 loader)."""
+    images, questions, answers, weights, counts = [], [], [], [], []
+    for image, question, ans, w in batch:
+        images.append(image)
+        questions.append(question)
+        answers += ans
+        weights += w
+        counts.append(len(ans))
+    return torch.stack(images, dim=0), questions, answers, torch.Tensor(weights), counts
 
 
 def region_collate(batch_sample, batch_size, rng=None, warn=print):
