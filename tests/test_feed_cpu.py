@@ -328,3 +328,34 @@ def test_vqa_collate_matches_reference(golden):
     assert im.tolist() == g["image"] and qs == g["questions"] and ans == g["answers"] and n == g["n"]
     assert w.tolist() == g["weights"] and str(w.dtype) == g["weights_dtype"] == "torch.float32"
     assert sum(n) == len(ans) == w.numel()
+
+
+def test_finetune_loader_sample_logic_matches_reference(golden):
+    """BASELINE configs #3 - #5: what the reference's re_train_dataset / re_eval_dataset / nlvr_dataset / vqa_dataset compute
+    besides decoding pixels — the ITC `idx`, txt2img / img2txt, cleaned sentences, labels, the mirror decision and the
+    answer weights — on the same annotations and `random` seed."""
+    r = golden["retrieval"][0]
+    index = feed.retrieval_image_index(r["train_anns"])
+    assert [[k, v] for k, v in index.items()] == r["img_ids"]
+    assert [[feed.pre_caption(a["caption"], 30), index[a["image_id"]]] for a in r["train_anns"]] == r["samples"]
+    texts, images, txt2img, img2txt = feed.retrieval_eval_index(r["eval_anns"])
+    assert texts == r["text"] and images == r["image"]
+    assert [[k, v] for k, v in txt2img.items()] == r["txt2img"] and [[k, v] for k, v in img2txt.items()] == r["img2txt"]
+    assert max(len(t.split(" ")) for t in texts) == 30                      # pre_caption truncates at max_words
+
+    n = golden["nlvr"][0]
+    assert [[feed.pre_caption(a["sentence"], 30), feed.nlvr_label(a)] for a in n["anns"]] == n["samples"]
+    with pytest.raises(ValueError):
+        feed.nlvr_label(dict(label="maybe"))
+
+    v = golden["vqa"][0]
+    for q, k, want in v["pre_question"]:
+        assert feed.pre_question(q, k) == want, (q, k)
+    random.seed(v["seed"])
+    got = [list(feed.vqa_train_sample(a)) for a in v["anns"]]
+    assert got == v["samples"]
+    assert random.random() == v["next_random"]
+    assert any(s[0] for s in got) and not all(s[0] for s in got)
+    assert not any(s[0] for s, a in zip(got, v["anns"]) if feed.vqa_mentions_side(a["question"], a["answer"]))
+    for s, a in zip(got, v["anns"]):
+        assert (s[3] == [0.5]) == (a.get("dataset") == "vg") and abs(sum(s[3]) - (0.5 if a.get("dataset") == "vg" else 1.0)) < 1e-9

@@ -266,6 +266,69 @@ def main():
     bt = ds.collate_fn(batch)
     out["collate"].append(dict(image=bt[0].tolist(), ids=bt[1].tolist(), atts=bt[2].tolist(), none=bt[3]))
 
+    # ---- fine-tuning loaders: re_train_dataset / re_eval_dataset / nlvr_dataset / vqa_dataset sample logic
+    import dataset.retrieval_dataset as rd
+    import dataset.nlvr_dataset  # noqa: F401  (the package attribute of the same name is the class: take the modules from sys.modules)
+    import dataset.vqa_dataset  # noqa: F401
+    nd, vd = sys.modules["dataset.nlvr_dataset"], sys.modules["dataset.vqa_dataset"]
+    import dataset.utils as du
+    tmpd2 = tempfile.mkdtemp(prefix="feed-ft-")
+    Image.new("RGB", (8, 6), (10, 20, 30)).save(os.path.join(tmpd2, "a.png"))
+    ids = [gen.choice(["coco_7", "coco_3", 11, "coco_9", 5]) for _ in range(14)]
+    train_anns = [dict(image="a.png", image_id=i, caption=sentence(gen, 4)) for i in ids]
+    f1 = os.path.join(tmpd2, "train.json")
+    json.dump(train_anns, open(f1, "w"))
+    ds = rd.re_train_dataset([f1], lambda im: torch.zeros(1), tmpd2)
+    got = [ds[i] for i in range(len(ds))]
+    eval_anns = [dict(image=f"img{i}.png", caption=["A Dog, on the-left!  " + sentence(gen, gen.randint(2, 40)) for _ in range(1 + i % 3)])
+                 for i in range(6)]
+    f2 = os.path.join(tmpd2, "eval.json")
+    json.dump(eval_anns, open(f2, "w"))
+    es = rd.re_eval_dataset(f2, None, tmpd2)
+    out["retrieval"] = [dict(train_anns=train_anns, img_ids=[[k, v] for k, v in ds.img_ids.items()],
+                             samples=[[c, i] for _, c, i in got], eval_anns=eval_anns, text=es.text, image=es.image,
+                             txt2img=[[k, v] for k, v in es.txt2img.items()], img2txt=[[k, v] for k, v in es.img2txt.items()])]
+    nl = [dict(images=["a.png", "a.png"], sentence="The LEFT image: two dogs/cats, (maybe)  " + sentence(gen, 35), label=l)
+          for l in ("True", "False", "True")]
+    f3 = os.path.join(tmpd2, "nlvr.json")
+    json.dump(nl, open(f3, "w"))
+    ns = nd.nlvr_dataset([f3], lambda im: torch.zeros(1), tmpd2)
+    out["nlvr"] = [dict(anns=nl, samples=[[ns[i][2], ns[i][3]] for i in range(len(ns))])]
+    vq = []
+    for i in range(12):
+        kind = i % 4
+        q = ["What is on the LEFT side?", "How many dogs/cats are there, really?", "Is this a wooden-table (or not)?  ",
+             "what color is the " + sentence(gen, 40)][kind]
+        if kind == 1:
+            vq.append(dict(image="a.png", dataset="vg", question=q, answer="two", question_id=i))
+        else:
+            ans = [gen.choice(["yes", "no", "left", "red", "two"]) for _ in range(10)]
+            a = dict(image="a.png", question=q, answer=ans, question_id=i)
+            if kind == 2:
+                a["dataset"] = "vqa"
+            vq.append(a)
+    f4 = os.path.join(tmpd2, "vqa.json")
+    json.dump(vq, open(f4, "w"))
+    flips = []
+    orig_hflip = vd.hflip
+    vd.hflip = lambda im: (flips.append(True), im)[1]
+    orig_tok = vd.build_tokenizer
+    vd.build_tokenizer = lambda *_: StubTokenizer("roberta")
+    try:
+        with quiet:
+            vs = vd.vqa_dataset([f4], lambda im: torch.zeros(1), tmpd2, tmpd2, split="train")
+        samples = []
+        random.seed(700)
+        for i in range(len(vs)):
+            n0 = len(flips)
+            _, q, a, w = vs[i]
+            samples.append([len(flips) > n0, q, a, w])
+        nxt = random.random()
+    finally:
+        vd.hflip, vd.build_tokenizer = orig_hflip, orig_tok
+    out["vqa"] = [dict(anns=vq, seed=700, samples=samples, next_random=nxt,
+                       pre_question=[[q, n, du.pre_question(q, n)] for q in [a["question"] for a in vq] for n in (3, 30, 50)])]
+
     # ---- vqa_collate_fn (dataset/__init__.py:200-208)
     import dataset as ref_dataset
     vb = [(torch.full((3, 2, 2), float(i)), f"question {i}", [f"a{i}{j}" for j in range(1 + i % 3)],

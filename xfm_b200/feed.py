@@ -13,6 +13,9 @@ run produces the reference's batches):
                               patch masks and cxcywh targets; the pixel work stays with the caller between the two phases)
   * `collate`, `region_collate`  dataset/pretrain_dataset.py:302-312, :594-643 (`idx_to_group_img`, fixed-size region batches)
   * `vqa_collate`             dataset/__init__.py:200-208
+  * `pre_question`, `retrieval_image_index`, `retrieval_eval_index`, `nlvr_label`, `vqa_train_sample`
+                              the sample logic of the fine-tuning loaders (dataset/utils.py:22-35, retrieval_dataset.py:18-57,
+                              nlvr_dataset.py:38-43, vqa_dataset.py:44-125): `idx`, txt2img / img2txt, answer weights
 
 Device half:
   * `to_uint8_hwc`            replaces the `ToTensor(), normalize` tail of every Compose in dataset/__init__.py:26-68: the
@@ -286,6 +289,67 @@ class ImageTextStream:
             except Exception as e:  # noqa: BLE001 — the reference skips any broken sample
                 if self.on_error is not None:
                     self.on_error(e)
+
+
+# ----------------------------------------------------------------------- fine-tuning loaders (BASELINE configs #3 - #5)
+def pre_question(question, max_ques_words):
+    """dataset/utils.py:22-35: lower-case, punctuation -> space, '-' and '/' -> space, trailing blanks stripped, truncated."""
+    q = _PUNCT.sub(" ", question.lower()).replace("-", " ").replace("/", " ").rstrip(" ")
+    words = q.split(" ")
+    return " ".join(words[:max_ques_words]) if len(words) > max_ques_words else q
+
+
+def retrieval_image_index(anns):
+    """image_id -> dense index in first-appearance order (re_train_dataset, dataset/retrieval_dataset.py:18-25): the `idx`
+    of ITC / ITM at fine-tuning time (captions of one image share it)."""
+    index = {}
+    for ann in anns:
+        index.setdefault(ann["image_id"], len(index))
+    return index
+
+
+def retrieval_eval_index(anns, max_words=30):
+    """Evaluation split -> (texts, images, txt2img, img2txt) (re_eval_dataset, dataset/retrieval_dataset.py:44-57): captions
+    cleaned with pre_caption and numbered in file order; what `retrieval_eval.itm_eval` scores against."""
+    texts, images, txt2img, img2txt = [], [], {}, {}
+    for img_id, ann in enumerate(anns):
+        images.append(ann["image"])
+        img2txt[img_id] = []
+        for caption in ann["caption"]:
+            txt2img[len(texts)] = img_id
+            img2txt[img_id].append(len(texts))
+            texts.append(pre_caption(caption, max_words))
+    return texts, images, txt2img, img2txt
+
+
+def nlvr_label(ann):
+    """'True' / 'False' -> 1 / 0 (dataset/nlvr_dataset.py:38-43)."""
+    if ann["label"] == "True":
+        return 1
+    if ann["label"] == "False":
+        return 0
+    raise ValueError(f"unsupported label: {ann['label']}")
+
+
+def vqa_mentions_side(question, answer):
+    """dataset/vqa_dataset.py:44-62: 'left' / 'right' in the question or any answer — such samples are never mirrored."""
+    answers = answer if isinstance(answer, list) else [answer]
+    return any(("left" in s) or ("right" in s) for s in [question] + answers)
+
+
+def vqa_train_sample(ann, max_ques_words=30, rng=None):
+    """One VQA training annotation -> (hflip, question, answers, weights) (dataset/vqa_dataset.py:64-125, minus the pixels):
+    one rng.random() decides the mirror (suppressed for left / right samples), Visual-Genome answers weigh 0.5, VQA answers
+    their share among the annotators, in first-appearance order."""
+    rng = rng if rng is not None else _random
+    hflip = rng.random() < 0.5 and not vqa_mentions_side(ann["question"], ann["answer"])
+    question = pre_question(ann["question"], max_ques_words)
+    if ann.get("dataset") == "vg":
+        return hflip, question, [ann["answer"]], [0.5]
+    share = {}
+    for a in ann["answer"]:
+        share[a] = share[a] + 1 / len(ann["answer"]) if a in share else 1 / len(ann["answer"])
+    return hflip, question, list(share.keys()), list(share.values())
 
 
 # ---------------------------------------------------------------------------------------------------------- region side
