@@ -159,3 +159,50 @@ def test_stray_parameters_are_adopted_into_a_flat_buffer():
     assert w.grad.data_ptr() == g.data_ptr() and float(g.mean()) == 2.0
     model.zero_grad()
     assert float(g.abs().sum()) == 0.0 and w.grad.data_ptr() == g.data_ptr()
+
+
+def test_create_scheduler_matches_reference_schedule():
+    """xfm_b200.accelerator.create_scheduler against scheduler.py:4-32 run by tools/make_golden_feed.py: the learning rates
+    of a two-group optimizer over the whole schedule (float and int warm-up, zero warm-up, past the end) and the values the
+    reference writes back into args."""
+    import json
+    from xfm_b200.accelerator import create_scheduler
+
+    class AttrDict(dict):
+        def __init__(self, *a, **k):
+            super().__init__(*a, **k)
+            self.__dict__ = self
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "feed.json")) as f:
+        cases = json.load(f)["scheduler"]
+    assert len(cases) == 4
+    for g in cases:
+        args = AttrDict(dict(g["args"]))
+        opt = torch.optim.SGD([dict(params=[torch.nn.Parameter(torch.zeros(1))], lr=1e-4),
+                               dict(params=[torch.nn.Parameter(torch.zeros(1))], lr=2e-4)], lr=1e-4)
+        sch = create_scheduler(args, opt)
+        assert [args["num_training_steps"], args["num_warmup_steps"]] == g["resolved"]
+        lrs = []
+        for _ in range(args["num_training_steps"] + 3):
+            lrs.append([grp["lr"] for grp in opt.param_groups])
+            opt.step()
+            sch.step()
+        assert lrs == g["lrs"], g["args"]
+    with pytest.raises(NotImplementedError):
+        create_scheduler(AttrDict(sched="cosine", num_training_steps=4, num_warmup_steps=1), opt)
+
+
+def test_create_optimizer_mirrors_optim_py_factory():
+    """create_optimizer(args, model) (optim.py:4-50): lr / weight_decay / optional lr_mult from args, betas (0.9, 0.98), eps 1e-8."""
+    import types
+    from xfm_b200.accelerator import FlatAdamW, create_optimizer
+    from xfm_b200.model_pretrain import XFM
+    model = XFM(dict(O.tiny_config()), init=lambda n, s: torch.zeros(s), device="cpu")
+    opt = create_optimizer(types.SimpleNamespace(lr=3e-4, weight_decay=0.05, lr_mult=2), model)
+    assert isinstance(opt, FlatAdamW)
+    assert [g["lr"] for g in opt.param_groups] == [3e-4, 3e-4, 6e-4, 6e-4]
+    assert [g["weight_decay"] for g in opt.param_groups] == [0.05, 0.0, 0.05, 0.0]
+    hp = opt.hparams(max_grad_norm=1.0, grad_mul=1.0)
+    torch.testing.assert_close(hp[8:11], torch.tensor([0.9, 0.98, 1e-8]))
+    plain = create_optimizer(types.SimpleNamespace(lr=1e-4, weight_decay=0.01), XFM(dict(O.tiny_config()), init=lambda n, s: torch.zeros(s), device="cpu"))
+    assert [g["lr"] for g in plain.param_groups] == [1e-4] * 4          # lr_mult defaults to 1

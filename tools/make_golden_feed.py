@@ -329,6 +329,24 @@ def main():
     out["vqa"] = [dict(anns=vq, seed=700, samples=samples, next_random=nxt,
                        pre_question=[[q, n, du.pre_question(q, n)] for q in [a["question"] for a in vq] for n in (3, 30, 50)])]
 
+    # ---- scheduler.py create_scheduler: lr of a 2-group optimizer over the whole schedule
+    import scheduler as ref_sched
+    import utils as ref_utils
+    out["scheduler"] = []
+    for a in [dict(sched="linear", epochs=3, step_per_epoch=7, num_warmup_steps=0.2), dict(sched="linear", num_training_steps=25, num_warmup_steps=5),
+              dict(sched="linear", num_training_steps=10, num_warmup_steps=0), dict(sched="linear", epochs=1, step_per_epoch=4, num_warmup_steps=0.9)]:
+        args = ref_utils.AttrDict(dict(a))
+        w = torch.nn.Parameter(torch.zeros(1))
+        opt = torch.optim.SGD([dict(params=[w], lr=1e-4), dict(params=[torch.nn.Parameter(torch.zeros(1))], lr=2e-4)], lr=1e-4)
+        with quiet:
+            sch = ref_sched.create_scheduler(args, opt)
+        lrs = []
+        for _ in range(args["num_training_steps"] + 3):
+            lrs.append([g["lr"] for g in opt.param_groups])
+            opt.step()
+            sch.step()
+        out["scheduler"].append(dict(args=a, resolved=[args["num_training_steps"], args["num_warmup_steps"]], lrs=lrs))
+
     # ---- vqa_collate_fn (dataset/__init__.py:200-208)
     import dataset as ref_dataset
     vb = [(torch.full((3, 2, 2), float(i)), f"question {i}", [f"a{i}{j}" for j in range(1 + i % 3)],

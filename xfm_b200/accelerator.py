@@ -222,6 +222,34 @@ class FlatAdamW(torch.optim.Optimizer):
             b.seg_step[b.index[n]] = int(st["step"])
 
 
+def create_optimizer(args, model):
+    """optim.py:4-50 `create_optimizer(args, model)`: args.lr, args.weight_decay and the optional args.lr_mult (default 1)
+    — the four {decay, no-decay} x {lr, lr * lr_mult} groups, eps 1e-8, betas (0.9, 0.98) — as a FlatAdamW."""
+    return FlatAdamW(model, lr=args.lr, weight_decay=args.weight_decay, lr_mult=getattr(args, "lr_mult", 1), betas=(0.9, 0.98),
+                     eps=1e-8)
+
+
+def create_scheduler(args, optimizer):
+    """scheduler.py:4-32 `create_scheduler(args, optimizer)` (args: the reference's attribute-dict): linear warm-up over
+    num_warmup_steps (an int, or a float fraction of the training steps, resolved in place like the reference does) then
+    linear decay to zero at num_training_steps (= epochs * step_per_epoch when absent); any other args.sched is an error."""
+    if "num_training_steps" not in args:
+        args["num_training_steps"] = args["epochs"] * args["step_per_epoch"]
+    if isinstance(args["num_warmup_steps"], float):
+        if not 0 <= args["num_warmup_steps"] < 1:
+            raise AssertionError("a float num_warmup_steps is a fraction of the training steps")
+        args["num_warmup_steps"] = int(args["num_training_steps"] * args["num_warmup_steps"])
+    if args["sched"] != "linear":
+        raise NotImplementedError(f"args.sched == {args['sched']}")
+    total, warm = args["num_training_steps"], args["num_warmup_steps"]
+
+    def factor(step):
+        if step < warm:
+            return float(step) / float(max(1, warm))
+        return max(0.0, float(total - step) / float(max(1, total - warm)))
+    return torch.optim.lr_scheduler.LambdaLR(optimizer, factor, last_epoch=-1)
+
+
 class _Cfg:
     def __init__(self, d):
         self.__dict__.update(d)
