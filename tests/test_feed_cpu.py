@@ -359,3 +359,23 @@ def test_finetune_loader_sample_logic_matches_reference(golden):
     assert not any(s[0] for s, a in zip(got, v["anns"]) if feed.vqa_mentions_side(a["question"], a["answer"]))
     for s, a in zip(got, v["anns"]):
         assert (s[3] == [0.5]) == (a.get("dataset") == "vg") and abs(sum(s[3]) - (0.5 if a.get("dataset") == "vg" else 1.0)) < 1e-9
+
+
+def test_pillow_bicubic_taps_many_axis_lengths():
+    """One-row strips, 300 random (in, out) lengths from 1-pixel sources to 20x down-scaling: the tap tables evaluated in integer
+    arithmetic equal PIL's horizontal BICUBIC pass everywhere (the vertical pass of a 1 -> 1 axis is the identity)."""
+    np = pytest.importorskip("numpy")
+    from PIL import Image
+    rng = np.random.default_rng(11)
+    sizes = [(1, 1), (1, 7), (2, 384), (3, 224), (4480, 224), (223, 224), (225, 224), (447, 224), (449, 224), (224, 1)]
+    sizes += [(int(rng.integers(1, 2500)), int(rng.integers(1, 500))) for _ in range(290)]
+    for w_in, w_out in sizes:
+        strip = rng.integers(0, 256, size=(1, w_in, 3), dtype=np.uint8)
+        ref = np.asarray(Image.fromarray(strip).resize((w_out, 1), Image.BICUBIC))
+        first, count, taps = feed.pillow_bicubic_taps(w_in, w_out)
+        assert taps.shape[1] == feed.bicubic_ksize(w_in, w_out) and int(count.max()) <= taps.shape[1]
+        assert int(first.min()) >= 0 and int((first + count).max()) <= w_in
+        idx = np.minimum(first[:, None].astype(np.int64) + np.arange(taps.shape[1])[None, :], w_in - 1)
+        acc = (strip[0].astype(np.int64)[idx, :] * taps.astype(np.int64)[:, :, None]).sum(1) + (1 << 21)
+        got = np.clip(acc >> 22, 0, 255).astype(np.uint8)
+        assert (got == ref[0]).all(), (w_in, w_out)
