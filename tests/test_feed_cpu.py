@@ -379,3 +379,40 @@ def test_pillow_bicubic_taps_many_axis_lengths():
         acc = (strip[0].astype(np.int64)[idx, :] * taps.astype(np.int64)[:, :, None]).sum(1) + (1 << 21)
         got = np.clip(acc >> 22, 0, 255).astype(np.uint8)
         assert (got == ref[0]).all(), (w_in, w_out)
+
+
+def test_randaugment_sampling_and_table_operations_match_reference(golden):
+    """dataset/randaugment.py: (1) which operations fire with which arguments — the reference's own RandomAugment.__call__ with
+    its operation functions replaced by recorders — for the pre-training and the box_transform operation lists and the full
+    14-operation default, same numpy.random stream afterwards; (2) Identity / AutoContrast / Equalize / Brightness outputs,
+    including the reference's uint8 negation in AutoContrast."""
+    np = pytest.importorskip("numpy")
+    assert len(golden["randaugment"]) == 4
+    seen = set()
+    for g in golden["randaugment"]:
+        sampler = feed.RandAugmentSampler(g["N"], g["M"], g["augs"])
+        np.random.seed(g["seed"])
+        for want in g["runs"]:
+            got = [[n, [list(a) if isinstance(a, tuple) else a for a in args]] for n, args in sampler.sample()]
+            assert got == want
+            seen.update(n for n, _ in got)
+        assert float(np.random.random()) == g["next_random"]
+    assert seen == set(feed.RandAugmentSampler.ALL)
+    private = feed.RandAugmentSampler(2, 7, ["Rotate", "ShearX"], rng=np.random.RandomState(1)).sample()
+    np.random.seed(1)
+    assert private == feed.RandAugmentSampler(2, 7, ["Rotate", "ShearX"]).sample()
+
+    assert len(golden["randaugment_ops"]) == 8
+    wrapped = 0
+    for g in golden["randaugment_ops"]:
+        img = np.array(g["image"], dtype=np.uint8)
+        for key, want in g.items():
+            if key == "image":
+                continue
+            name, _, f = key.partition(":")
+            got = feed.apply_channel_tables(img, name, (float(f),) if f else ())
+            assert got.dtype == np.uint8 and (got == np.array(want, dtype=np.uint8)).all(), key
+        wrapped += int(img.min(axis=(0, 1)).max() > 0)
+    assert wrapped >= 2                                   # channels with min > 0 exercise the wrapped offset
+    with pytest.raises(ValueError):
+        feed.channel_table(img[:, :, 0], "Rotate")

@@ -347,6 +347,50 @@ def main():
             sch.step()
         out["scheduler"].append(dict(args=a, resolved=[args["num_training_steps"], args["num_warmup_steps"]], lrs=lrs))
 
+    # ---- dataset/randaugment.py: operation sampling (all 14 operations; the functions replaced by recorders, cv2 is not in the
+    # image) and the four look-up-table operations (cv2.split / merge / calcHist stand-ins in numpy: channel views, stacking,
+    # a float32 [256, 1] count column — what those calls return)
+    import numpy as np
+    import dataset.randaugment as ra
+    cv2 = sys.modules["cv2"]
+    cv2.split = lambda img: [img[:, :, c] for c in range(img.shape[2])]
+    cv2.merge = lambda chs: np.stack(chs, axis=2)
+    cv2.calcHist = lambda imgs, ch, mask, size, rng_: np.bincount(imgs[0].reshape(-1), minlength=size[0]).astype(np.float32).reshape(-1, 1)
+    out["randaugment"] = []
+    fired = []
+    orig_funcs = dict(ra.func_dict)
+    for name in ra.func_dict:
+        ra.func_dict[name] = (lambda name: lambda img, *args: (fired.append([name, list(args)]), img)[1])(name)
+    try:
+        for N, M, augs in [(2, 7, ['Identity', 'AutoContrast', 'Equalize', 'Brightness', 'Sharpness', 'ShearX', 'ShearY', 'TranslateX',
+                                   'TranslateY', 'Rotate']), (2, 7, ['Identity', 'AutoContrast', 'Equalize', 'Brightness', 'Sharpness']),
+                           (3, 10, []), (1, 3, [])]:
+            aug = ra.RandomAugment(N, M, isPIL=True, augs=augs)
+            runs = []
+            np.random.seed(800 + N + M)
+            for _ in range(25):
+                del fired[:]
+                aug(Image.new("RGB", (4, 4)))
+                runs.append([[n, [list(a) if isinstance(a, tuple) else a for a in args]] for n, args in fired])
+            out["randaugment"].append(dict(N=N, M=M, augs=augs, seed=800 + N + M, runs=runs, next_random=float(np.random.random())))
+    finally:
+        ra.func_dict.update(orig_funcs)
+    out["randaugment_ops"] = []
+    nrng = np.random.default_rng(3)
+    for t in range(8):
+        img = nrng.integers(0, 256, size=(12, 10, 3), dtype=np.uint8)
+        if t == 1:
+            img[:, :, 0] = 77                       # a constant channel: high <= low, equalize step 0
+        if t == 2:
+            img = (img // 4 + 90).astype(np.uint8)  # narrow range
+        if t == 3:
+            img[:] = nrng.integers(0, 2, size=img.shape) * 255
+        res = dict(image=img.tolist(), AutoContrast=ra.autocontrast_func(img).tolist(), Equalize=ra.equalize_func(img).tolist(),
+                   Identity=ra.identity_func(img).tolist())
+        for f in (0.1, 0.1 + 1.8 * 0.7, 1.9):
+            res[f"Brightness:{f!r}"] = ra.brightness_func(img, f).tolist()
+        out["randaugment_ops"].append(res)
+
     # ---- vqa_collate_fn (dataset/__init__.py:200-208)
     import dataset as ref_dataset
     vb = [(torch.full((3, 2, 2), float(i)), f"question {i}", [f"a{i}{j}" for j in range(1 + i % 3)],

@@ -17,6 +17,9 @@ run produces the reference's batches):
                               the sample logic of the fine-tuning loaders (dataset/utils.py:22-35, retrieval_dataset.py:18-57,
                               nlvr_dataset.py:38-43, vqa_dataset.py:44-125): `idx`, txt2img / img2txt, answer weights
 
+  * `RandAugmentSampler`, `channel_table`  dataset/randaugment.py:13-70,129-135,215-340 (which operations fire with which
+                              arguments; the four look-up-table operations.  The cv2 warps / filter stay with the caller)
+
 Device half:
   * `to_uint8_hwc`            replaces the `ToTensor(), normalize` tail of every Compose in dataset/__init__.py:26-68: the
                               worker hands over the crop as uint8 [H, W, 3]
@@ -516,6 +519,91 @@ def region_collate(batch_sample, batch_size, rng=None, warn=print):
         flat = [v for per in c for v in per]
         out.append(_stack_column([flat[i] for i in keep]))
     return out
+
+
+# ------------------------------------------------------------------------------------------- RandAugment (host logic)
+class RandAugmentSampler:
+    """Which operations `RandomAugment(N, M, augs=...)` applies to one image, and with which arguments
+    (dataset/randaugment.py:215-340): N names drawn with replacement by ONE rng.choice, then per name one rng.random() — the
+    operation is skipped when it exceeds 0.5 — and, for the geometric operations, one more rng.random() for the sign of the
+    magnitude (Rotate negates below 0.5, the shears / translations above).  `rng` defaults to `numpy.random`, the generator
+    the reference draws from.  Magnitudes at level M of 10: enhancement factor 0.1 + 1.8 M/10, shear 0.3 M/10, translation
+    10 M/10 pixels, rotation 30 M/10 degrees, solarize threshold int(256 M/10), posterize bits int(4 M/10); fill (128, 128, 128)."""
+
+    MAX_LEVEL, TRANSLATE, FILL = 10, 10, (128, 128, 128)
+    ALL = ("Identity", "AutoContrast", "Equalize", "Rotate", "Solarize", "Color", "Contrast", "Brightness", "Sharpness", "ShearX",
+           "TranslateX", "TranslateY", "Posterize", "ShearY")
+
+    def __init__(self, N=2, M=10, augs=None, rng=None):
+        import numpy as np
+        self.N, self.M, self.augs = N, M, list(augs) if augs else list(self.ALL)
+        self.rng = rng if rng is not None else np.random
+
+    def _args(self, name):
+        rng, frac = self.rng, self.M / self.MAX_LEVEL
+        if name in ("Identity", "AutoContrast", "Equalize"):
+            return ()
+        if name in ("Color", "Contrast", "Brightness", "Sharpness"):
+            return (frac * 1.8 + 0.1,)
+        if name == "Solarize":
+            return (int(frac * 256),)
+        if name == "Posterize":
+            return (int(frac * 4),)
+        if name == "Rotate":
+            level = frac * 30
+            return (-level if rng.random() < 0.5 else level, self.FILL)
+        level = frac * 0.3 if name in ("ShearX", "ShearY") else frac * float(self.TRANSLATE)
+        return (-level if rng.random() > 0.5 else level, self.FILL)
+
+    def sample(self):
+        """[(name, args)] of the operations that fire, in application order."""
+        fired = []
+        for name in self.rng.choice(self.augs, self.N):
+            if self.rng.random() > 0.5:
+                continue
+            fired.append((str(name), self._args(str(name))))
+        return fired
+
+
+def channel_table(ch, name, args=()):
+    """The 256-entry uint8 look-up table that Identity / AutoContrast / Equalize / Brightness apply to one channel `ch`
+    (uint8 [H, W]) of an image (dataset/randaugment.py:13-70,129-135; cutoff 0): these four of the box_transform's five
+    operations (dataset/__init__.py:57-61) are per-channel tables of the channel's own histogram, so they compose with each
+    other — and with ToTensor + Normalize — into ONE table per image and channel."""
+    import numpy as np
+    ident = np.arange(256)
+    if name == "Identity":
+        table = ident
+    elif name == "Brightness":
+        return (np.arange(256, dtype=np.float32) * args[0]).clip(0, 255).astype(np.uint8)
+    elif name == "AutoContrast":
+        high, low = ch.max(), ch.min()
+        if high <= low:
+            table = ident
+        else:
+            # the reference negates `low` as a numpy uint8 scalar (randaugment.py:36 `offset = -low * scale`), which wraps to
+            # 256 - low: for low > 0 the table saturates early instead of stretching [low, high] to [0, 255].  Kept as is —
+            # this restates what the reference's loaders feed the model, not PIL's autocontrast.
+            scale = 255 / (int(high) - int(low))
+            table = (ident * scale + ((256 - int(low)) % 256) * scale).clip(0, 255)
+    elif name == "Equalize":
+        hist = np.bincount(ch.reshape(-1), minlength=256).astype(np.float32)
+        step = np.sum(hist[hist != 0][:-1]) // 255
+        if step == 0:
+            table = ident
+        else:
+            shifted = np.empty_like(hist)
+            shifted[0], shifted[1:] = step // 2, hist[:-1]
+            table = np.cumsum(shifted) // step
+    else:
+        raise ValueError(f"{name} is not a per-channel table operation")
+    return np.asarray(table).clip(0, 255).astype(np.uint8)
+
+
+def apply_channel_tables(img, name, args=()):
+    """img uint8 [H, W, 3] -> the operation applied channel by channel (table[ch] per channel)."""
+    import numpy as np
+    return np.stack([channel_table(img[:, :, c], name, args)[img[:, :, c]] for c in range(img.shape[2])], axis=2)
 
 
 # ---------------------------------------------------------------------------------------------------------- device side
