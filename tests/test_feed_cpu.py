@@ -416,3 +416,19 @@ def test_randaugment_sampling_and_table_operations_match_reference(golden):
     assert wrapped >= 2                                   # channels with min > 0 exercise the wrapped offset
     with pytest.raises(ValueError):
         feed.channel_table(img[:, :, 0], "Rotate")
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree not present")
+def test_live_differential_against_the_reference_loader_code():
+    """Beyond the committed fixture: tests/feed_probe.py imports the reference's dataset package in a subprocess and compares
+    it with xfm_b200.feed on fresh random configurations and seeds (600 masker / preprocess cases over random mask
+    probabilities, budgets, n-gram settings, whole-word modes and lengths; 400 boxes; 400 RandAugment draws)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "feed_probe.py"), "2026"], capture_output=True, text=True,
+                       timeout=600)
+    lines = [l for l in r.stdout.splitlines() if l.startswith("PROBE_JSON ")]
+    assert r.returncode == 0 and lines, r.stderr[-3000:]
+    res = json.loads(lines[-1][len("PROBE_JSON "):])
+    assert res["mismatches"] == [], res["mismatches"]
+    assert res["masker"] == 600 and res["preprocess"] == 600 and res["image_atts"] == 400 and res["randaugment"] == 400
