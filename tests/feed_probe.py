@@ -85,8 +85,103 @@ def main():
             res["randaugment"] += 1
             if a != b:
                 res["mismatches"].append(["randaugment", N, M, augs, seed - 1])
+    res["datasets"] = datasets(pd, G, gen, res["mismatches"])
     res["mismatches"] = res["mismatches"][:5]
     print("PROBE_JSON " + json.dumps(res))
+
+
+def datasets(pd, G, gen, mismatches):
+    """The four dataset classes end to end on JSON-line files written here: the reference's ImageTextJsonDataset /
+    ImageJsonDataset / RegionTextJsonDataset / TextJsonDataset (build_tokenizer replaced by the stub tokenizer) against the
+    classes of the same names in xfm_b200.feed — every sample of one epoch (shuffled, sharded over ranks) and one collated
+    batch, same `random` seed."""
+    import base64
+    import tempfile
+    import torch
+    from PIL import Image
+    from feed_stub import StubTokenizer, WORDS
+    from xfm_b200 import feed
+
+    tok = StubTokenizer("roberta")
+    pd.build_tokenizer = lambda *_: tok
+    quiet = contextlib.redirect_stdout(io.StringIO())
+
+    def words(n):
+        return " ".join(gen.choice(WORDS) for _ in range(n))
+
+    def png(w, h):
+        im = Image.new("RGB", (w, h))
+        im.putdata([(gen.randrange(256), gen.randrange(256), gen.randrange(256)) for _ in range(w * h)])
+        buf = io.BytesIO()
+        im.save(buf, format="PNG")
+        return base64.b64encode(buf.getvalue()).decode()
+
+    root = tempfile.mkdtemp(prefix="feed-ds-")
+    dirs = {}
+    for kind in ("pairs", "regions", "texts"):
+        d = dirs[kind] = os.path.join(root, kind)
+        os.makedirs(d)
+        for f in range(4):
+            with open(os.path.join(d, f"part-{f}"), "w") as fh:
+                for _ in range(5):
+                    if kind == "pairs":
+                        ann = dict(binary=png(gen.randint(2, 6), gen.randint(2, 6)), desc=gen.choice([words(gen.randint(1, 9)), [words(3), words(5)], ""]))
+                    elif kind == "texts":
+                        ann = dict(text="  " + words(gen.randint(1, 20)) + " ")
+                    else:
+                        W, H = gen.randint(30, 90), gen.randint(30, 90)
+                        elems = []
+                        for _ in range(gen.randint(1, 5)):
+                            x, y = gen.randrange(0, W - 8), gen.randrange(0, H - 8)
+                            e = dict(bb=[x, y, gen.randrange(4, W - x + 1), gen.randrange(4, H - y + 1)],
+                                     caption=gen.choice([words(3), [words(2), "on the left " + words(2)]]))
+                            if gen.random() < 0.3:
+                                e["attributes"] = [words(1), words(2)]
+                            elems.append(e)
+                        ann = dict(binary=png(W, H), elems=elems)
+                        if gen.random() < 0.5:
+                            ann["caption"] = words(4)
+                    fh.write(json.dumps(ann) + "\n")
+    config = dict(text_encoder="roberta-base", mask_prob=0.25, max_masks=4, skipgram_prb=0.2, skipgram_size=3, mask_whole_word=True,
+                  max_words=8, max_tokens=12, image_res=32, patch_size=16, print_broken_data=False,
+                  images=dict(image_key="binary", is_image_rpath=False, caption_key="desc", batch_size=3, tokenized=False),
+                  regions=dict(image_key="binary", is_image_rpath=False, caption_key="caption", batch_size=7, tokenized=False,
+                               max_regions=3, min_perc_in_image=0.3, careful_hflip=True),
+                  texts=dict(text_key="text", batch_size=4, tokenized=False, mask_prob=0.3, max_masks=5, mask_whole_word=False,
+                             max_words=30, max_tokens=10))
+
+    def pixels(im):
+        return torch.tensor(list(im.getdata()), dtype=torch.uint8).reshape(im.size[1], im.size[0], 3)
+
+    def plain(x):
+        if isinstance(x, torch.Tensor):
+            return x.tolist()
+        if isinstance(x, (list, tuple)):
+            return [plain(v) for v in x]
+        return x
+
+    checked = 0
+    for name, d, kw in [("ImageTextJsonDataset", "pairs", dict(transform=lambda im: torch.tensor(im.size))),
+                        ("ImageJsonDataset", "pairs", dict(transform=lambda im: torch.tensor(im.size))),
+                        ("RegionTextJsonDataset", "regions", dict(transform=None, box_transform=pixels)),
+                        ("TextJsonDataset", "texts", {})]:
+        for rank, world in [(0, 1), (1, 2), (0, 4)]:
+            seed = gen.randrange(1 << 30)
+            outs = []
+            for side in (pd, feed):
+                extra = dict(tokenizer=tok) if side is feed else {}
+                with quiet:
+                    ds = getattr(side, name)(dict(config, images=dict(config["images"]), regions=dict(config["regions"]), texts=dict(config["texts"])),
+                                            dirs[d], rank=rank, world_size=world, shuffle=True, repeat=False, **kw, **extra)
+                    random.seed(seed)
+                    samples = list(ds)
+                    batch = ds.collate_fn(samples[:ds.batch_size]) if name != "RegionTextJsonDataset" else \
+                        ds.collate_fn([s for s in samples if len(s[0])][:4])
+                outs.append((plain(samples), plain(batch), random.random()))
+            checked += len(outs[0][0])
+            if outs[0] != outs[1]:
+                mismatches.append(["dataset", name, rank, world, seed])
+    return checked
 
 
 if __name__ == "__main__":

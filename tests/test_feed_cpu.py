@@ -422,7 +422,9 @@ def test_randaugment_sampling_and_table_operations_match_reference(golden):
 def test_live_differential_against_the_reference_loader_code():
     """Beyond the committed fixture: tests/feed_probe.py imports the reference's dataset package in a subprocess and compares
     it with xfm_b200.feed on fresh random configurations and seeds (600 masker / preprocess cases over random mask
-    probabilities, budgets, n-gram settings, whole-word modes and lengths; 400 boxes; 400 RandAugment draws)."""
+    probabilities, budgets, n-gram settings, whole-word modes and lengths; 400 boxes; 400 RandAugment draws), and runs the
+    reference's four dataset classes against the classes of the same names in xfm_b200.feed on JSON-line files (every sample
+    of a shuffled, rank-sharded epoch incl. the region loader's crop / flip / BICUBIC-resize pixels, and a collated batch)."""
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, os.path.join(root, "tests", "feed_probe.py"), "2026"], capture_output=True, text=True,
@@ -432,3 +434,30 @@ def test_live_differential_against_the_reference_loader_code():
     res = json.loads(lines[-1][len("PROBE_JSON "):])
     assert res["mismatches"] == [], res["mismatches"]
     assert res["masker"] == 600 and res["preprocess"] == 600 and res["image_atts"] == 400 and res["randaugment"] == 400
+    assert res["datasets"] >= 100      # samples of the four dataset classes compared end to end (3 rank / world settings each)
+
+
+def test_text_dataset_through_a_dataloader_with_workers(tmp_path):
+    """feed.TextJsonDataset under torch's DataLoader with two worker processes (the real get_worker_info): the workers split the
+    rank's files, every line arrives exactly once, batches have the collate layout."""
+    import json as _json
+    tok = StubTokenizer("roberta")
+    want = []
+    for f in range(4):
+        with open(tmp_path / f"part-{f}", "w") as fh:
+            for j in range(3):
+                text = f"the dog table {['red', 'blue', 'green'][j]} " + " ".join(["cat"] * f)
+                want.append(tok.convert_tokens_to_ids([tok.cls_token] + tok.tokenize(text))[:9])
+                fh.write(_json.dumps(dict(text=text)) + "\n")
+    config = dict(text_encoder="roberta-base", skipgram_prb=0.2, skipgram_size=3, print_broken_data=True,
+                  texts=dict(text_key="text", batch_size=4, tokenized=False, mask_prob=0.2, max_masks=3, mask_whole_word=False,
+                             max_words=30, max_tokens=10))
+    ds = feed.TextJsonDataset(config, str(tmp_path), rank=0, world_size=1, shuffle=False, repeat=False, tokenizer=tok)
+    loader = torch.utils.data.DataLoader(ds, batch_size=ds.batch_size, num_workers=2, collate_fn=ds.collate_fn, timeout=120)
+    rows = []
+    for ids, atts, ids_masked, pos, mids in loader:
+        assert ids.dtype == torch.int64 and ids.shape[1] == 10 and pos.shape[1] == 3 and atts.shape == ids.shape
+        rows += [r[:int(a.sum()) - 1].tolist() for r, a in zip(ids, atts)]          # without the eos token
+    assert sorted(rows) == sorted(want) and len(rows) == 12
+    with pytest.raises(NotImplementedError):
+        feed.list_files("hdfs://cluster/path")

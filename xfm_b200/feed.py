@@ -17,6 +17,9 @@ run produces the reference's batches):
                               the sample logic of the fine-tuning loaders (dataset/utils.py:22-35, retrieval_dataset.py:18-57,
                               nlvr_dataset.py:38-43, vqa_dataset.py:44-125): `idx`, txt2img / img2txt, answer weights
 
+  * `ImageTextJsonDataset`, `ImageJsonDataset`, `RegionTextJsonDataset`, `TextJsonDataset`
+                              the four IterableDatasets of dataset/pretrain_dataset.py assembled from the pieces above: same
+                              constructor arguments, configuration keys, samples and `collate_fn`
   * `RandAugmentSampler`, `channel_table`  dataset/randaugment.py:13-70,129-135,215-340 (which operations fire with which
                               arguments; the four look-up-table operations.  The cv2 warps / filter stay with the caller)
 
@@ -519,6 +522,178 @@ def region_collate(batch_sample, batch_size, rng=None, warn=print):
         flat = [v for per in c for v in per]
         out.append(_stack_column([flat[i] for i in keep]))
     return out
+
+
+# -------------------------------------------------------------------------- the reference's dataset classes, assembled
+def list_files(data_path):
+    """'dir_or_file[,dir_or_file...]' -> file list (utils/hdfs_io.py:55-79, local paths: a directory contributes
+    os.listdir order, a file itself).  hdfs:// paths need the reference's hadoop client and are refused."""
+    import os
+    files = []
+    for folder in data_path.split(","):
+        if folder.startswith("hdfs"):
+            raise NotImplementedError("xfm_b200.feed reads local files; mount or copy hdfs:// data first")
+        if os.path.isdir(folder):
+            files.extend(os.path.join(folder, d) for d in os.listdir(folder))
+        elif os.path.isfile(folder):
+            files.append(folder)
+        else:
+            print("Path {} is invalid".format(folder), flush=True)
+    return files
+
+
+def _report_broken(enabled):
+    import traceback
+
+    def report(e):
+        if enabled:
+            print("".join(traceback.format_exception(type(e), e, e.__traceback__)))
+            print("encounter broken data: %s" % e)
+            print("-" * 20, flush=True)
+    return report
+
+
+class _JsonLineDataset(torch.utils.data.IterableDataset):
+    """Shared constructor work of the four pre-training datasets (pretrain_dataset.py:154-204,315-365,408-419,645-671):
+    file list, rank / worker sharding, tokenizer, masker with the configuration's MLM settings.  `tokenizer=None` builds
+    the HuggingFace tokenizer of config['text_encoder'] like `build_tokenizer` (:35-57)."""
+
+    def __init__(self, config, data_path, rank, world_size, shuffle, repeat, tokenizer, section, whole_word):
+        super().__init__()
+        self.lines = LineShards(list_files(data_path), rank, world_size, shuffle, repeat)
+        self.batch_size = config[section]["batch_size"]
+        self.tokenized = config[section]["tokenized"]
+        self.report = _report_broken(config["print_broken_data"] if "print_broken_data" in config else True)
+        self.tokenizer = tokenizer if tokenizer is not None else build_tokenizer(config["text_encoder"])
+        self.masker = TextMasker(self.tokenizer, whole_word["mask_prob"], whole_word["max_masks"], config["skipgram_prb"],
+                                 config["skipgram_size"], whole_word["mask_whole_word"])
+
+
+def build_tokenizer(text_encoder):
+    """pretrain_dataset.py:35-57: BERT / RoBERTa / XLM-R tokenizer by directory name, with bos / eos aliases filled in."""
+    from transformers import BertTokenizer, RobertaTokenizer, XLMRobertaTokenizer
+    if any(k in text_encoder for k in ("bert-base-uncased", "bert-large-uncased", "chinese-roberta-wwm-ext")):
+        tok = BertTokenizer.from_pretrained(text_encoder)
+    elif "xlm-roberta-base" in text_encoder or "xlm-roberta-large" in text_encoder:
+        tok = XLMRobertaTokenizer.from_pretrained(text_encoder)
+    elif "roberta-base" in text_encoder or "roberta-large" in text_encoder:
+        tok = RobertaTokenizer.from_pretrained(text_encoder)
+    else:
+        raise NotImplementedError(f"tokenizer for {text_encoder}")
+    if tok.bos_token is None:
+        tok.add_special_tokens({"bos_token": tok.cls_token})
+    if tok.eos_token is None:
+        tok.add_special_tokens({"eos_token": tok.sep_token})
+    return tok
+
+
+def _mlm_settings(config):
+    """Image-text streams take the top-level MLM keys; whole-word masking is forced off unless the encoder is
+    bert-{base,large}-uncased, and the change is written back into config like the reference does (:186-189)."""
+    if "bert-base-uncased" not in config["text_encoder"] and "bert-large-uncased" not in config["text_encoder"]:
+        config["mask_whole_word"] = False
+    return dict(mask_prob=config["mask_prob"], max_masks=config["max_masks"], mask_whole_word=config["mask_whole_word"])
+
+
+class ImageTextJsonDataset(_JsonLineDataset):
+    """pretrain_dataset.py:154-312: same constructor arguments and configuration keys (config[config_key]: image_key,
+    is_image_rpath, caption_key / aux_caption_key, batch_size, tokenized, optional language_chosen; config: text_encoder,
+    mask_prob, max_masks, skipgram_prb, skipgram_size, mask_whole_word, max_words, max_tokens, image_res, patch_size),
+    same samples, same `collate_fn`.  Use with `DataLoader(ds, batch_size=ds.batch_size, collate_fn=ds.collate_fn, ...)`."""
+
+    text_stream = True
+
+    def __init__(self, config, data_path, rank=0, world_size=1, shuffle=True, repeat=True, transform=None, add_eos=True,
+                 is_aux=False, config_key="images", tokenizer=None):
+        super().__init__(config, data_path, rank, world_size, shuffle, repeat, tokenizer, config_key, _mlm_settings(config))
+        sec = config[config_key]
+        self.image_key, self.is_image_rpath = sec["image_key"], sec["is_image_rpath"]
+        self.caption_key = sec["aux_caption_key"] if is_aux else sec["caption_key"]
+        self.language_chosen = sec.get("language_chosen")
+        if self.language_chosen is not None and not isinstance(self.language_chosen, str):
+            raise AssertionError("language_chosen must be a string")
+        self.transform, self.image_res, self.patch_size = transform, config["image_res"], config["patch_size"]
+        if self.image_res % self.patch_size:
+            raise AssertionError("image_res must be a multiple of patch_size")
+        self.num_patch = self.image_res // self.patch_size
+        self.text = TextPreprocessor(self.tokenizer, self.masker, config["max_tokens"], config["max_masks"], config["max_words"],
+                                     tokenized=self.tokenized, language_chosen=self.language_chosen)
+
+    def __iter__(self):
+        return iter(ImageTextStream(self.lines, self.transform, self.text if self.text_stream else None, self.image_key,
+                                    self.caption_key, self.is_image_rpath, on_error=self.report))
+
+    def collate_fn(self, batch):
+        return collate(batch)
+
+
+class ImageJsonDataset(ImageTextJsonDataset):
+    """pretrain_dataset.py:314-407: the image-only stream (ImageNet-style data for MIM): samples are (image, None x 5)."""
+    text_stream = False
+
+
+class RegionTextJsonDataset(ImageTextJsonDataset):
+    """pretrain_dataset.py:409-643: one annotated image -> a random crop around one of its regions, mirrored with probability
+    1/2 (never when careful_hflip is set and a caption says left / right), resized to image_res (BICUBIC), `box_transform`,
+    and up to max_regions (text, patch mask, box) samples; `collate_fn` = the fixed-size region batch."""
+
+    def __init__(self, config, data_path, rank=0, world_size=1, shuffle=True, repeat=True, transform=None, box_transform=None,
+                 config_key="regions", tokenizer=None):
+        super().__init__(config, data_path, rank=rank, world_size=world_size, shuffle=shuffle, repeat=repeat, transform=transform,
+                         config_key=config_key, tokenizer=tokenizer)
+        if self.caption_key != "caption":
+            raise AssertionError("please follow my data format")
+        sec = config[config_key]
+        self.box_transform = box_transform
+        self.sampler = RegionSampler(self.text, self.image_res, self.patch_size, sec["max_regions"], sec["min_perc_in_image"],
+                                     careful_hflip=sec.get("careful_hflip", False))
+
+    def __iter__(self):
+        import json
+        from PIL import Image
+        for line in self.lines:
+            try:
+                ann = json.loads(line)
+                if not isinstance(ann, dict):
+                    raise AssertionError("ann is not dict")
+                image = _open_rgb(ann[self.image_key], self.is_image_rpath)
+                plan = self.sampler.plan(ann, *image.size)
+                image = image.crop(plan.crop_box)
+                if plan.hflip:
+                    image = image.transpose(Image.FLIP_LEFT_RIGHT)
+                image = self.box_transform(image.resize((self.image_res, self.image_res), Image.BICUBIC))
+                yield self.sampler.finish(ann, plan, image)
+            except Exception as e:  # noqa: BLE001 — the reference skips any broken sample
+                self.report(e)
+
+    def collate_fn(self, batch_sample):
+        return region_collate(batch_sample, self.batch_size)
+
+
+class TextJsonDataset(_JsonLineDataset):
+    """pretrain_dataset.py:645-737: the text-only corpus stream (config['texts']: text_key, batch_size, tokenized, mask_prob,
+    max_masks, mask_whole_word, max_words, max_tokens); samples are the five text lists."""
+
+    def __init__(self, config, data_path, rank=0, world_size=1, shuffle=True, repeat=True, tokenizer=None):
+        sec = config["texts"]
+        super().__init__(config, data_path, rank, world_size, shuffle, repeat, tokenizer, "texts", sec)
+        self.text_key = sec["text_key"]
+        self.text = TextPreprocessor(self.tokenizer, self.masker, sec["max_tokens"], sec["max_masks"], sec["max_words"],
+                                     tokenized=self.tokenized, corpus=True)
+
+    def __iter__(self):
+        import json
+        for line in self.lines:
+            try:
+                ann = json.loads(line)
+                if not isinstance(ann, dict):
+                    raise AssertionError("ann is not dict")
+                yield self.text.preprocess(ann[self.text_key].strip())
+            except Exception as e:  # noqa: BLE001
+                self.report(e)
+
+    def collate_fn(self, batch):
+        return collate(batch)
 
 
 # ------------------------------------------------------------------------------------------- RandAugment (host logic)
