@@ -163,10 +163,10 @@ def test_to_uint8_hwc_and_cpu_transform_restatement():
     tv = pytest.importorskip("torchvision.transforms")
     from PIL import Image
     ref = tv.Compose([tv.ToTensor(), tv.Normalize(feed.CLIP_MEAN, feed.CLIP_STD)])(Image.fromarray(a))
-    x = t.permute(2, 0, 1).contiguous().to(torch.float32).div(255)
-    mean = torch.tensor(feed.CLIP_MEAN, dtype=torch.float32)[:, None, None]
-    std = torch.tensor(feed.CLIP_STD, dtype=torch.float32)[:, None, None]
-    assert torch.equal((x - mean) / std, ref)
+    from oracle.feed_oracle import to_tensor_normalize
+    assert torch.equal(to_tensor_normalize(t[None], feed.CLIP_MEAN, feed.CLIP_STD)[0], ref)
+    flipped = to_tensor_normalize(t[None], feed.CLIP_MEAN, feed.CLIP_STD, flip=torch.ones(1))[0]
+    assert torch.equal(flipped, tv.Compose([tv.RandomHorizontalFlip(1.0), tv.ToTensor(), tv.Normalize(feed.CLIP_MEAN, feed.CLIP_STD)])(Image.fromarray(a)))
     assert (feed.to_uint8_hwc(Image.fromarray(a)) == t).all()
 
 
@@ -178,23 +178,17 @@ def test_device_feeder_refuses_to_run_without_cuda():
 
 
 def _resample_with_taps(img, box, out_h, out_w):
-    """Evaluate xfm_b200.feed's tap tables the way csrc/feed.cu does (horizontal pass into uint8, then vertical), in numpy."""
-    import numpy as np
-    x0, y0, x1, y1 = box
+    """xfm_b200.feed's tap tables evaluated the way csrc/feed.cu evaluates them (oracle/feed_oracle.py)."""
+    from oracle.feed_oracle import resample_with_taps
     plan = feed.crop_resize_plan([img.shape[:2]], [box], out_h, out_w)
-    src = img[y0:y1, x0:x1].astype(np.int64)
-    hb, hk, vb, vk = (plan[k][0].numpy().astype(np.int64) for k in ("hb", "hk", "vb", "vk"))
-    idx = np.minimum(hb[:, :1] + np.arange(hk.shape[1])[None, :], src.shape[1] - 1)
-    tmp = np.clip(((src[:, idx, :] * hk[None, :, :, None]).sum(2) + (1 << 21)) >> 22, 0, 255)
-    idx = np.minimum(vb[:, :1] + np.arange(vk.shape[1])[None, :], src.shape[0] - 1)
-    return np.clip(((tmp[idx, :, :] * vk[:, :, None, None]).sum(1) + (1 << 21)) >> 22, 0, 255).astype(np.uint8)
+    return resample_with_taps(img, box, *(plan[k][0].numpy() for k in ("hb", "hk", "vb", "vk")))
 
 
 def test_pillow_bicubic_taps_reproduce_pil_resize():
     """The host half of the GPU crop + resize: tap tables in Pillow's 8.22 fixed point.  Evaluated with integer arithmetic they
     give PIL's `crop(box).resize(size, BICUBIC)` bit for bit (down- and up-scaling, full image, thin crops)."""
     np = pytest.importorskip("numpy")
-    from PIL import Image
+    from oracle.feed_oracle import pil_crop_resize
     rng = np.random.default_rng(7)
     for t in range(24):
         H, W = int(rng.integers(12, 500)), int(rng.integers(12, 500))
@@ -204,7 +198,7 @@ def test_pillow_bicubic_taps_reproduce_pil_resize():
         if t % 4 == 0:
             box = (0, 0, W, H)
         oh, ow = [(224, 224), (384, 384), (32, 48)][t % 3]
-        ref = np.asarray(Image.fromarray(img).crop(box).resize((ow, oh), Image.BICUBIC))
+        ref = pil_crop_resize(img, box, oh, ow)
         assert (_resample_with_taps(img, box, oh, ow) == ref).all(), (t, (H, W), box, (oh, ow))
     first, count, taps = feed.pillow_bicubic_taps(224, 224)          # same size: the identity
     assert (taps.sum(1) == 1 << 22).all() and ((taps != 0).sum(1) == 1).all()
