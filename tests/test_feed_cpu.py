@@ -455,3 +455,23 @@ def test_text_dataset_through_a_dataloader_with_workers(tmp_path):
     assert sorted(rows) == sorted(want) and len(rows) == 12
     with pytest.raises(NotImplementedError):
         feed.list_files("hdfs://cluster/path")
+
+
+def test_flipped_crops_reproduce_crop_hflip_resize_order():
+    """crop -> hflip -> resize (region loader, pretrain_dataset.py:470-483) == resize of the mirrored crop: `flipped_crops`
+    hands `crop_resize` exactly the pixels PIL's crop + transpose produce, and leaves unflagged images untouched."""
+    np = pytest.importorskip("numpy")
+    from PIL import Image
+    from oracle.feed_oracle import pil_crop_resize
+    rng = np.random.default_rng(2)
+    imgs = [rng.integers(0, 256, size=(int(h), int(w), 3), dtype=np.uint8) for h, w in [(20, 30), (17, 9), (40, 40)]]
+    boxes = [(3, 2, 25, 18), None, (0, 5, 40, 33)]
+    tens = [torch.from_numpy(i) for i in imgs]
+    out_images, out_boxes = feed.flipped_crops(tens, boxes, [1, 1, 0])
+    assert out_boxes == [None, None, boxes[2]] and out_images[2] is tens[2]
+    for im, bx, got in zip(imgs[:2], boxes[:2], out_images[:2]):
+        pil = Image.fromarray(im)
+        pil = (pil if bx is None else pil.crop(bx)).transpose(Image.FLIP_LEFT_RIGHT)
+        assert got.is_contiguous() and (got.numpy() == np.asarray(pil)).all()
+        assert (pil_crop_resize(got.numpy(), None, 16, 16) == np.asarray(pil.resize((16, 16), Image.BICUBIC))).all()
+    assert feed.flipped_crops(tens, boxes, None) == (tens, boxes)

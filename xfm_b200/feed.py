@@ -890,7 +890,23 @@ def random_resized_crop_box(width, height, scale=(0.2, 1.0), ratio=(3.0 / 4.0, 4
     return (x0, y0, x0 + w, y0 + h)
 
 
-def crop_resize(images, boxes, out_h, out_w, device=None, taps="device"):
+def flipped_crops(images, boxes, flips):
+    """Images whose flag is set are replaced by their mirrored crop (and the box by None = whole image): crop -> hflip ->
+    resize, the order of the region loader (pretrain_dataset.py:470-483), then is a plain resize of the mirrored crop.  Host
+    work: one crop-sized copy per mirrored image."""
+    if flips is None:
+        return list(images), list(boxes)
+    out_images, out_boxes = [], []
+    for im, bx, fl in zip(images, boxes, flips):
+        if fl:
+            x0, y0, x1, y1 = (0, 0, im.shape[1], im.shape[0]) if bx is None else bx
+            im, bx = im[y0:y1, x0:x1].flip(1).contiguous(), None
+        out_images.append(im)
+        out_boxes.append(bx)
+    return out_images, out_boxes
+
+
+def crop_resize(images, boxes, out_h, out_w, device=None, taps="device", flips=None):
     """images: list of uint8 [h, w, 3] host tensors (decoded RGB, any sizes); boxes: integer crop boxes (x0, y0, x1, y1) or
     None = the whole image.  Returns uint8 [B, out_h, out_w, 3] on the device, bit-identical to
     PIL `image.crop(box).resize((out_w, out_h), BICUBIC)` — i.e. to `RandomResizedCrop` / `Resize` with
@@ -900,6 +916,7 @@ def crop_resize(images, boxes, out_h, out_w, device=None, taps="device"):
     if not torch.cuda.is_available():
         raise RuntimeError("xfm_b200.feed.crop_resize needs a CUDA device (sm_100a); there is no CPU path")
     device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    images, boxes = flipped_crops(images, boxes, flips)      # flips: optional per-image flags, mirror the crop before resizing
     sizes = [(int(im.shape[0]), int(im.shape[1])) for im in images]
     for im in images:
         if im.dtype != torch.uint8 or im.dim() != 3 or im.shape[2] != 3:
