@@ -911,7 +911,8 @@ def crop_resize(images, boxes, out_h, out_w, device=None, taps="device", flips=N
     None = the whole image.  Returns uint8 [B, out_h, out_w, 3] on the device, bit-identical to
     PIL `image.crop(box).resize((out_w, out_h), BICUBIC)` — i.e. to `RandomResizedCrop` / `Resize` with
     InterpolationMode.BICUBIC once the crop box is drawn.  `lib.image_u8_to_f32` finishes the transform.  taps="device"
-    (default) builds Pillow's tap tables on the GPU (`xfm_resize_taps`); taps="host" computes them in numpy (same integers)."""
+    (default) builds Pillow's tap tables on the GPU (`xfm_resize_taps`); taps="host" computes them in numpy (same integers).
+    flips: optional per-image flags — the crop is mirrored before it is resized (`flipped_crops`)."""
     from . import lib
     if not torch.cuda.is_available():
         raise RuntimeError("xfm_b200.feed.crop_resize needs a CUDA device (sm_100a); there is no CPU path")
